@@ -1,0 +1,118 @@
+// Internal declarations shared by the translation units of libariadne_b200.so.
+// Nothing here is part of the C ABI (that is include/ariadne_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ariadne_b200.h"
+
+#define AK_API extern "C" __attribute__((visibility("default")))
+
+namespace ak {
+
+void set_error(const char* fmt, ...);
+
+#define AK_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ak::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return AK_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+#define AK_TRY(expr)              \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc < 0) return _rc;  \
+    } while (0)
+
+#define AK_REQUIRE(cond, msg)                                          \
+    do {                                                               \
+        if (!(cond)) {                                                 \
+            ak::set_error("%s:%d: %s", __FILE__, __LINE__, msg);       \
+            return AK_ERR_ARG;                                         \
+        }                                                              \
+    } while (0)
+
+// Upper bound on blocks of any reduction kernel (size of the partials buffer).
+constexpr int kMaxPartials = 1 << 16;
+constexpr int kNumSMsDefault = 148;
+
+struct Comm;  // NCCL state (context.cu)
+
+struct Ctx {
+    int device = 0;
+    int num_sms = kNumSMsDefault;
+    cudaStream_t stream = nullptr;
+    // grid-wide reduction scratch (kernels on one stream never overlap)
+    double* partials = nullptr;     // kMaxPartials doubles
+    unsigned int* ticket = nullptr; // last-block-done counter, self-resetting
+    // device scalar bank + pinned host mirror for synchronous scalar returns
+    double* dscal = nullptr;        // 64 doubles
+    double* hscal = nullptr;        // 64 doubles, pinned
+    int64_t launches = 0;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    // multi-GPU
+    Comm* comm = nullptr;
+    int rank = 0, nranks = 1;
+    double* halo_lo = nullptr;      // nx doubles: row gy0-1 (from rank-1)
+    double* halo_hi = nullptr;      // nx doubles: row gy0+ny (from rank+1)
+    double* halo_send = nullptr;
+    int64_t halo_cap = 0;
+};
+
+// --- comm (context.cu) --------------------------------------------------------
+// In-stream sum all-reduce of `count` device doubles (no-op on one rank).
+int allreduce_sum(Ctx* ctx, double* dev, int count);
+// Fill ctx->halo_lo / halo_hi with the neighbours' boundary rows of `v` (nx*ny slab).
+// Returns pointers to use as ghost rows (nullptr => implicit zero).
+int exchange_halo_rows(Ctx* ctx, const double* v, int64_t nx, int64_t ny, int32_t bc,
+                       const double** lo, const double** hi);
+
+// --- blas1.cu -------------------------------------------------------------------
+int launch_dot(Ctx* ctx, int64_t n, const double* x, const double* y, double* out_dev);
+int launch_sumsq(Ctx* ctx, int64_t n, const double* x, double* out_dev);
+int launch_scal(Ctx* ctx, int64_t n, double s, double* x);
+int launch_axpy(Ctx* ctx, int64_t n, double s, const double* x, double* y);
+// y += (sign * *s_dev) * x   — scalar read from device memory
+int launch_axpy_dev(Ctx* ctx, int64_t n, const double* s_dev, double sign, const double* x, double* y);
+int launch_axpby(Ctx* ctx, int64_t n, double s, const double* x, double t, double* y);
+int launch_copy(Ctx* ctx, int64_t n, double* y, const double* x);
+int launch_fill(Ctx* ctx, int64_t n, double* x, double v);
+int launch_ref(Ctx* ctx, int64_t n, double* x, double* y, double c, double s);
+int launch_divcopy(Ctx* ctx, int64_t n, double* y, const double* x, double s);
+// y <- x / (*s_dev)
+int launch_divcopy_dev(Ctx* ctx, int64_t n, double* y, const double* x, const double* s_dev, const int* stop_flag);
+// Fused modified-Gram-Schmidt step (arnoldi kernels, blas1.cu):
+//   if vi:    w <- w - (*h_in) * vi
+//   if vnext: *out = <vnext, w_new>     else if want_sumsq: *out = <w_new, w_new>
+// `stop_flag` (device int, may be null): kernel is a no-op when *stop_flag != 0.
+int launch_mgs_step(Ctx* ctx, int64_t n, double* w, const double* vi, const double* h_in,
+                    const double* vnext, int want_sumsq, double* out_dev, const int* stop_flag);
+// x <- x + sum_i y[i] V[i]  (sequential axpy order), optionally u <- u - x fused (single pass)
+int launch_basis_combine(Ctx* ctx, int64_t n, double* x, const double* const* V_dev, const double* y_dev,
+                         int k, int zero_x_first);
+
+// --- stencil.cu -----------------------------------------------------------------
+// res <- F(u); if sumsq_dev != null also *sumsq_dev = ||res||^2 (global when comm is set)
+int launch_residual(Ctx* ctx, const ak_problem* p, double* u, double* res, double* sumsq_dev);
+// out <- J(u) v; if dot_with != null also *dot_dev = <dot_with, out>
+// if scale_src != null: v is first formed as scale_src / (*denom_dev) and written to v (fused divcopy)
+struct JvpFusion {
+    const double* scale_src = nullptr;  // w_prev: v <- scale_src / denom, written to v
+    const double* denom_dev = nullptr;  // device scalar
+    const double* dot_with = nullptr;   // V[0]
+    double* dot_dev = nullptr;
+    const int* stop_flag = nullptr;
+};
+int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double* out, const JvpFusion* f);
+int launch_jvp_transpose(Ctx* ctx, const ak_problem* p, const double* u, double* v, double* out);
+
+// --- krylov.cu ------------------------------------------------------------------
+}  // namespace ak
+
+struct ak_ctx {
+    ak::Ctx c;
+};

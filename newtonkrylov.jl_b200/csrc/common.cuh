@@ -1,0 +1,111 @@
+// Device-side helpers: wide streaming loads/stores, deterministic grid reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define AK_DEV __device__ __forceinline__
+
+namespace ak {
+
+// ---- 256-bit / 128-bit streaming accesses (sm_100a has LDG.E.256 / STG.E.256) ------
+struct alignas(32) d4 {
+    double x, y, z, w;
+};
+
+// read-only data that is touched once per kernel: non-coherent path, do not allocate in L1
+AK_DEV d4 ld4_stream(const double* p) {
+    d4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+                 : "l"(p));
+    return r;
+}
+// data the same kernel also writes (no .nc)
+AK_DEV d4 ld4(const double* p) {
+    d4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+                 : "l"(p));
+    return r;
+}
+AK_DEV void st4(double* p, const d4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z),
+                 "d"(v.w)
+                 : "memory");
+}
+AK_DEV double2 ld2_stream(const double* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+AK_DEV double ld1_stream(const double* p) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+
+// ---- deterministic reductions ---------------------------------------------------------
+// Butterfly: every lane ends with the same value, order fixed.
+AK_DEV double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the block (any block shape); result valid in flat thread 0.
+// `sh` must hold >= 32 doubles.
+AK_DEV double block_sum(double v, double* sh) {
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int lane = tid & 31, wid = tid >> 5;
+    const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect sh from a previous use
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (wid == 0) {
+        r = (lane < nw) ? sh[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// Grid-wide sum with a fixed summation order: each block deposits its partial, the block
+// that takes the last ticket adds the partials in index order and stores the result.
+// `nblocks` = total blocks of the launch, `bid` = this block's linear id.
+// Must be called by all threads of every block.  Result: *out (+)= sum.
+AK_DEV void grid_sum_finish(double block_partial_in_t0, double* partials, unsigned int* ticket, int bid,
+                            int nblocks, double* out, double* sh) {
+    __shared__ bool is_last;
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int nthreads = blockDim.x * blockDim.y;
+    if (tid == 0) {
+        partials[bid] = block_partial_in_t0;
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == (unsigned int)(nblocks - 1));
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double s = 0.0;
+        for (int i = tid; i < nblocks; i += nthreads) s += __ldcg(partials + i);
+        // block_sum assumes 1-D indexing through threadIdx.x; handle 2-D blocks via flat id
+        const int lane = tid & 31, wid = tid >> 5;
+        const int nw = (nthreads + 31) >> 5;
+        s = warp_sum(s);
+        __syncthreads();
+        if (lane == 0) sh[wid] = s;
+        __syncthreads();
+        if (wid == 0) {
+            double r = (lane < nw) ? sh[lane] : 0.0;
+            r = warp_sum(r);
+            if (lane == 0) {
+                *out = r;
+                *ticket = 0u;  // self-reset for the next launch on this stream
+            }
+        }
+    }
+}
+
+}  // namespace ak

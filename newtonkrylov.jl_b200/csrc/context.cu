@@ -1,0 +1,358 @@
+// Context, device memory, HaloVector layout bridge and the multi-GPU plumbing
+// (NCCL all-reduce for the Arnoldi inner products, nearest-neighbour halo rows for the
+// 2-D stencils — the distributed form of bc!(u), examples/heat_2D.jl:51, on the slab
+// decomposition modelled on examples/halovector.jl).
+//
+// NCCL is resolved at run time with dlopen/dlsym so that libariadne_b200.so has no link-time
+// dependency on it (single-GPU users never load it, and inside a torch process the already
+// loaded libnccl.so.2 is reused).
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "ak_internal.h"
+#include "common.cuh"
+
+namespace ak {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- minimal NCCL surface (ABI-stable since NCCL 2.x) -----------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8, ncclSum = 0 };
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+    if (g_nccl.lib) return AK_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* nm : names) {
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        set_error("cannot dlopen libnccl.so.2: %s", dlerror());
+        return AK_ERR_NCCL;
+    }
+#define AK_SYM(field, name)                                        \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                     \
+    if (!g_nccl.field) {                                           \
+        set_error("libnccl: missing symbol %s", name);             \
+        return AK_ERR_NCCL;                                        \
+    }
+    AK_SYM(GetUniqueId, "ncclGetUniqueId");
+    AK_SYM(CommInitRank, "ncclCommInitRank");
+    AK_SYM(CommDestroy, "ncclCommDestroy");
+    AK_SYM(AllReduce, "ncclAllReduce");
+    AK_SYM(Send, "ncclSend");
+    AK_SYM(Recv, "ncclRecv");
+    AK_SYM(GroupStart, "ncclGroupStart");
+    AK_SYM(GroupEnd, "ncclGroupEnd");
+    AK_SYM(GetErrorString, "ncclGetErrorString");
+#undef AK_SYM
+    g_nccl.lib = h;
+    return AK_OK;
+}
+
+#define AK_NCCL(expr)                                                                                  \
+    do {                                                                                               \
+        ncclResult_t _r = (expr);                                                                      \
+        if (_r != 0) {                                                                                 \
+            ak::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, ak::g_nccl.GetErrorString(_r)); \
+            return AK_ERR_NCCL;                                                                        \
+        }                                                                                              \
+    } while (0)
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+};
+
+int allreduce_sum(Ctx* ctx, double* dev, int count) {
+    if (ctx->nranks <= 1) return AK_OK;
+    AK_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclFloat64, ncclSum, ctx->comm->comm, ctx->stream));
+    return AK_OK;
+}
+
+int exchange_halo_rows(Ctx* ctx, const double* v, int64_t nx, int64_t ny, int32_t bc, const double** lo,
+                       const double** hi) {
+    const int P = ctx->nranks, r = ctx->rank;
+    if (ctx->halo_cap < nx) {
+        AK_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->halo_lo) AK_CUDA(cudaFree(ctx->halo_lo));
+        if (ctx->halo_hi) AK_CUDA(cudaFree(ctx->halo_hi));
+        AK_CUDA(cudaMalloc(&ctx->halo_lo, sizeof(double) * (size_t)nx));
+        AK_CUDA(cudaMalloc(&ctx->halo_hi, sizeof(double) * (size_t)nx));
+        ctx->halo_cap = nx;
+    }
+    const bool periodic = (bc == AK_BC_PERIODIC);
+    const int down = (r > 0) ? r - 1 : (periodic ? P - 1 : -1);  // owner of row gy0-1
+    const int up = (r < P - 1) ? r + 1 : (periodic ? 0 : -1);    // owner of row gy0+ny
+    // Per peer, NCCL matches sends and receives in posting order; with P == 2 and periodic
+    // wrap both neighbours are the same rank, so "last row up" is posted before "first row down"
+    // and "lo from down" before "hi from up".
+    AK_NCCL(g_nccl.GroupStart());
+    if (up >= 0) AK_NCCL(g_nccl.Send(v + (ny - 1) * nx, (size_t)nx, ncclFloat64, up, ctx->comm->comm, ctx->stream));
+    if (down >= 0) AK_NCCL(g_nccl.Send(v, (size_t)nx, ncclFloat64, down, ctx->comm->comm, ctx->stream));
+    if (down >= 0) AK_NCCL(g_nccl.Recv(ctx->halo_lo, (size_t)nx, ncclFloat64, down, ctx->comm->comm, ctx->stream));
+    if (up >= 0) AK_NCCL(g_nccl.Recv(ctx->halo_hi, (size_t)nx, ncclFloat64, up, ctx->comm->comm, ctx->stream));
+    AK_NCCL(g_nccl.GroupEnd());
+    *lo = down >= 0 ? ctx->halo_lo : nullptr;
+    *hi = up >= 0 ? ctx->halo_hi : nullptr;
+    return AK_OK;
+}
+
+// ---- HaloVector layout bridge -----------------------------------------------------------
+__global__ void k_halo_pack(double* __restrict__ compact, const double* __restrict__ padded, int64_t nx, int64_t ny) {
+    const int64_t n = nx * ny;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = t / nx, i = t - j * nx;
+        compact[t] = padded[(j + 1) * (nx + 2) + (i + 1)];
+    }
+}
+__global__ void k_halo_unpack(double* __restrict__ padded, const double* __restrict__ compact, int64_t nx, int64_t ny,
+                              int bc) {
+    const int64_t px = nx + 2, py = ny + 2, n = px * py;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t J = t / px, I = t - J * px;
+        int64_t i = I - 1, j = J - 1;
+        double v = 0.0;
+        bool ghost = (i < 0 || i >= nx || j < 0 || j >= ny);
+        if (!ghost) {
+            v = compact[j * nx + i];
+        } else if (bc == AK_BC_PERIODIC) {
+            // bc_periodic!: heat_2D.jl:15-26 (x ghosts first, then whole ghost rows incl. corners)
+            if (i < 0) i = nx - 1; else if (i >= nx) i = 0;
+            if (j < 0) j = ny - 1; else if (j >= ny) j = 0;
+            v = compact[j * nx + i];
+        }
+        padded[t] = v;
+    }
+}
+
+}  // namespace ak
+
+using namespace ak;
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+AK_API int ak_abi_version(void) { return AK_ABI_VERSION; }
+AK_API const char* ak_last_error(void) { return g_err; }
+
+AK_API int ak_ctx_create(int device, ak_ctx** out) {
+    AK_REQUIRE(out != nullptr, "ak_ctx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("ak_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        (void)cudaGetLastError();
+        return AK_ERR_CUDA;
+    }
+    AK_REQUIRE(device >= 0 && device < ndev, "ak_ctx_create: device index out of range");
+    AK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    AK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("ak_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                  prop.minor);
+        return AK_ERR_UNSUPPORTED;
+    }
+    ak_ctx* ctx = new ak_ctx();
+    Ctx* c = &ctx->c;
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    AK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    AK_CUDA(cudaMalloc(&c->partials, sizeof(double) * kMaxPartials));
+    AK_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned int)));
+    AK_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
+    AK_CUDA(cudaMalloc(&c->dscal, sizeof(double) * 64));
+    AK_CUDA(cudaMemset(c->dscal, 0, sizeof(double) * 64));
+    AK_CUDA(cudaHostAlloc((void**)&c->hscal, sizeof(double) * 64, cudaHostAllocDefault));
+    AK_CUDA(cudaEventCreate(&c->ev_t0));
+    AK_CUDA(cudaEventCreate(&c->ev_t1));
+    *out = ctx;
+    return AK_OK;
+}
+
+AK_API int ak_ctx_destroy(ak_ctx* ctx) {
+    if (!ctx) return AK_OK;
+    Ctx* c = &ctx->c;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) {
+        if (c->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm->comm);
+        delete c->comm;
+    }
+    cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->dscal);
+    cudaFree(c->halo_lo); cudaFree(c->halo_hi); cudaFree(c->halo_send);
+    if (c->hscal) cudaFreeHost(c->hscal);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete ctx;
+    return AK_OK;
+}
+
+AK_API int ak_ctx_sync(ak_ctx* ctx) {
+    AK_REQUIRE(ctx, "ak_ctx_sync: NULL ctx");
+    AK_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    return AK_OK;
+}
+AK_API uint64_t ak_ctx_stream(ak_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->c.stream : 0; }
+AK_API int64_t ak_ctx_launch_count(ak_ctx* ctx, int reset) {
+    if (!ctx) return 0;
+    int64_t v = ctx->c.launches;
+    if (reset) ctx->c.launches = 0;
+    return v;
+}
+AK_API int ak_timer_start(ak_ctx* ctx) {
+    AK_REQUIRE(ctx, "ak_timer_start: NULL ctx");
+    AK_CUDA(cudaEventRecord(ctx->c.ev_t0, ctx->c.stream));
+    return AK_OK;
+}
+AK_API int ak_timer_stop(ak_ctx* ctx, double* ms_out) {
+    AK_REQUIRE(ctx && ms_out, "ak_timer_stop: NULL argument");
+    AK_CUDA(cudaEventRecord(ctx->c.ev_t1, ctx->c.stream));
+    AK_CUDA(cudaEventSynchronize(ctx->c.ev_t1));
+    float ms = 0.f;
+    AK_CUDA(cudaEventElapsedTime(&ms, ctx->c.ev_t0, ctx->c.ev_t1));
+    *ms_out = (double)ms;
+    return AK_OK;
+}
+
+AK_API int ak_malloc(ak_ctx* ctx, int64_t n, double** out) {
+    AK_REQUIRE(ctx && out && n >= 0, "ak_malloc: bad argument");
+    AK_CUDA(cudaSetDevice(ctx->c.device));
+    cudaError_t e = cudaMalloc(out, sizeof(double) * (size_t)(n > 0 ? n : 1));
+    if (e != cudaSuccess) {
+        set_error("ak_malloc: %lld doubles: %s", (long long)n, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return AK_ERR_NOMEM;
+    }
+    return AK_OK;
+}
+AK_API int ak_free(ak_ctx* ctx, double* p) {
+    AK_REQUIRE(ctx, "ak_free: NULL ctx");
+    if (!p) return AK_OK;
+    AK_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    AK_CUDA(cudaFree(p));
+    return AK_OK;
+}
+AK_API int ak_upload(ak_ctx* ctx, double* dst_dev, const double* src_host, int64_t n) {
+    AK_REQUIRE(ctx && n >= 0, "ak_upload: bad argument");
+    AK_CUDA(cudaMemcpyAsync(dst_dev, src_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->c.stream));
+    AK_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    return AK_OK;
+}
+AK_API int ak_download(ak_ctx* ctx, double* dst_host, const double* src_dev, int64_t n) {
+    AK_REQUIRE(ctx && n >= 0, "ak_download: bad argument");
+    AK_CUDA(cudaMemcpyAsync(dst_host, src_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->c.stream));
+    AK_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    return AK_OK;
+}
+AK_API int ak_host_alloc(int64_t n, double** out) {
+    AK_REQUIRE(out && n >= 0, "ak_host_alloc: bad argument");
+    cudaError_t e = cudaHostAlloc((void**)out, sizeof(double) * (size_t)(n > 0 ? n : 1), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        set_error("ak_host_alloc: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return AK_ERR_NOMEM;
+    }
+    return AK_OK;
+}
+AK_API int ak_host_free(double* p) {
+    if (p) AK_CUDA(cudaFreeHost(p));
+    return AK_OK;
+}
+
+AK_API int ak_halo_pack(ak_ctx* ctx, double* compact, const double* padded, int64_t nx, int64_t ny) {
+    AK_REQUIRE(ctx && compact && padded && nx >= 1 && ny >= 1, "ak_halo_pack: bad argument");
+    int64_t n = nx * ny;
+    int blocks = (int)((n + 255) / 256 < ctx->c.num_sms * 8 ? (n + 255) / 256 : ctx->c.num_sms * 8);
+    k_halo_pack<<<blocks, 256, 0, ctx->c.stream>>>(compact, padded, nx, ny);
+    ctx->c.launches++;
+    AK_CUDA(cudaGetLastError());
+    return AK_OK;
+}
+AK_API int ak_halo_unpack(ak_ctx* ctx, double* padded, const double* compact, int64_t nx, int64_t ny, int32_t bc) {
+    AK_REQUIRE(ctx && compact && padded && nx >= 1 && ny >= 1, "ak_halo_unpack: bad argument");
+    int64_t n = (nx + 2) * (ny + 2);
+    int blocks = (int)((n + 255) / 256 < ctx->c.num_sms * 8 ? (n + 255) / 256 : ctx->c.num_sms * 8);
+    k_halo_unpack<<<blocks, 256, 0, ctx->c.stream>>>(padded, compact, nx, ny, bc);
+    ctx->c.launches++;
+    AK_CUDA(cudaGetLastError());
+    return AK_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------
+AK_API int ak_comm_unique_id(char id_out[128]) {
+    AK_REQUIRE(id_out, "ak_comm_unique_id: NULL");
+    AK_TRY(load_nccl());
+    ncclUniqueId id;
+    AK_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, id.internal, 128);
+    return AK_OK;
+}
+AK_API int ak_comm_init(ak_ctx* ctx, int nranks, int rank, const char id_in[128]) {
+    AK_REQUIRE(ctx && id_in && nranks >= 1 && rank >= 0 && rank < nranks, "ak_comm_init: bad argument");
+    AK_REQUIRE(ctx->c.comm == nullptr, "ak_comm_init: communicator already initialised");
+    if (nranks == 1) {
+        ctx->c.rank = 0;
+        ctx->c.nranks = 1;
+        return AK_OK;
+    }
+    AK_TRY(load_nccl());
+    AK_CUDA(cudaSetDevice(ctx->c.device));
+    ncclUniqueId id;
+    memcpy(id.internal, id_in, 128);
+    Comm* cm = new Comm();
+    ncclResult_t r = g_nccl.CommInitRank(&cm->comm, nranks, id, rank);
+    if (r != 0) {
+        set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+        delete cm;
+        return AK_ERR_NCCL;
+    }
+    ctx->c.comm = cm;
+    ctx->c.rank = rank;
+    ctx->c.nranks = nranks;
+    return AK_OK;
+}
+AK_API int ak_comm_rank(ak_ctx* ctx, int* rank, int* nranks) {
+    AK_REQUIRE(ctx, "ak_comm_rank: NULL ctx");
+    if (rank) *rank = ctx->c.rank;
+    if (nranks) *nranks = ctx->c.nranks;
+    return AK_OK;
+}
+AK_API int ak_comm_barrier(ak_ctx* ctx) {
+    AK_REQUIRE(ctx, "ak_comm_barrier: NULL ctx");
+    Ctx* c = &ctx->c;
+    if (c->nranks > 1) {
+        AK_CUDA(cudaMemsetAsync(c->dscal + 63, 0, sizeof(double), c->stream));
+        AK_TRY(allreduce_sum(c, c->dscal + 63, 1));
+    }
+    AK_CUDA(cudaStreamSynchronize(c->stream));
+    return AK_OK;
+}

@@ -1,0 +1,729 @@
+// Krylov workspace + GMRES / CG drivers.
+//
+// Replaces `krylov_workspace(algo, KrylovConstructor(res))` and
+// `krylov_solve!(workspace, J, copy(res); kwargs...)` at src/Ariadne.jl:317-318,338-340,
+// i.e. Krylov.jl's gmres!/cg! (not vendored in the reference; restated from the published
+// algorithm) with the operator J = JacobianOperator(F!, res, u, p) of src/Ariadne.jl:34-57.
+//
+// B200-first structure: the whole Arnoldi iteration lives on the device.  Inner products land
+// in a device column `hcol`, a one-thread kernel applies the Givens reflections, updates the
+// least-squares right-hand side, evaluates the stopping tests and raises a device-side `stop`
+// flag; every vector kernel starts by reading that flag.  The host therefore launches iteration
+// k+1 before it knows the outcome of iteration k (it reads a pinned status record one iteration
+// late), so the stream never drains inside a pass.  The Krylov basis stays resident in HBM.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "ak_internal.h"
+#include "common.cuh"
+
+namespace ak {
+
+struct KrylovCtl {  // device-resident control block
+    double eps, rNorm, beta, Hbis, btol, atol, rtol;
+    // CG scalars
+    double gamma, gamma_next, pAp, pNorm2, alpha, neg_alpha, cg_beta;
+    int stop, solved, breakdown, inconsistent, inner_iter, zerocurv;
+};
+struct KrylovStatus {  // pinned host ring, written by the scalar kernels
+    double rNorm, Hbis, beta;
+    int iter, stop, solved, breakdown, zerocurv, pad;
+};
+constexpr int kStatusRing = 8;   // per-iteration records; slot kStatusRing is the pass prologue
+constexpr int kStatusSlots = kStatusRing + 1;
+
+}  // namespace ak
+
+struct ak_krylov {
+    ak::Ctx* ctx = nullptr;
+    int32_t algo = AK_ALGO_GMRES;
+    int64_t n = 0;
+    int32_t mem = 20;
+    int64_t max_basis = 0;
+    // vectors
+    double* x = nullptr;
+    double* w[2] = {nullptr, nullptr};
+    double* dx = nullptr;  // xr when restart
+    std::vector<double*> V;          // basis vectors
+    std::vector<double*> chunks;     // cudaMalloc'ed blocks backing V / misc vectors
+    const double** V_dev = nullptr;  // device table of basis pointers
+    int64_t V_dev_cap = 0;
+    // scalars (device)
+    int64_t kcap = 0;  // columns of R that fit
+    double *R = nullptr, *c = nullptr, *s = nullptr, *z = nullptr, *hcol = nullptr, *hist = nullptr;
+    int64_t hist_cap = 0;
+    ak::KrylovCtl* ctl = nullptr;
+    ak::KrylovStatus* status = nullptr;  // pinned
+    cudaEvent_t ev[ak::kStatusSlots] = {};
+    // cg
+    double *r = nullptr, *p = nullptr, *Ap = nullptr;
+};
+
+namespace ak {
+
+// ---------------------------------------------------------------------------------------
+// scalar kernels (1 thread)
+// ---------------------------------------------------------------------------------------
+// start of a solve / of a restart pass: beta = ||r0||, z[0] = beta, stopping tolerance
+__global__ void k_gmres_begin(KrylovCtl* ctl, const double* sumsq, double* z, double* hist, int first_pass,
+                              double atol, double rtol, KrylovStatus* st) {
+    if (threadIdx.x != 0) return;
+    const double beta = sqrt(*sumsq);
+    if (first_pass) {
+        ctl->beta = beta;
+        ctl->rNorm = beta;
+        ctl->eps = atol + rtol * beta;
+        ctl->btol = pow(2.220446049250313e-16, 0.75);
+        ctl->breakdown = 0;
+        ctl->inconsistent = 0;
+        if (hist) hist[0] = beta;
+    }
+    z[0] = beta;
+    ctl->solved = (ctl->rNorm <= ctl->eps) || (beta == 0.0);
+    ctl->stop = ctl->solved;
+    ctl->inner_iter = 0;
+    st->rNorm = ctl->rNorm;
+    st->beta = beta;
+    st->Hbis = 0.0;
+    st->iter = 0;
+    st->stop = ctl->stop;
+    st->solved = ctl->solved;
+    st->breakdown = 0;
+}
+
+__device__ __forceinline__ double sgn(double x) { return (double)((x > 0.0) - (x < 0.0)); }
+
+// Krylov.jl sym_givens (real), then the update of iteration k (1-based) — gmres! steps 6-8
+__global__ void k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, double* c, double* s, double* z,
+                               const double* hcol, int reorth, double* hist, int64_t hist_pos, int inner_limit,
+                               KrylovStatus* st) {
+    if (threadIdx.x != 0) return;
+    if (ctl->stop) return;
+    // column k of H: h_1k..h_kk from the MGS sweep(s), h_{k+1,k} = ||q||
+    const double* h2 = hcol + (k + 1);
+    for (int i = 0; i < k; ++i) R[nr + i] = reorth ? hcol[i] + h2[i] : hcol[i];
+    const double Hbis = sqrt(reorth ? h2[k] : hcol[k]);
+    for (int i = 0; i + 1 < k; ++i) {
+        const double Rt = c[i] * R[nr + i] + s[i] * R[nr + i + 1];
+        R[nr + i + 1] = s[i] * R[nr + i] - c[i] * R[nr + i + 1];
+        R[nr + i] = Rt;
+    }
+    const double a = R[nr + k - 1], b = Hbis;
+    double ck, sk, rho;
+    if (b == 0.0) {
+        ck = (a == 0.0) ? 1.0 : sgn(a);
+        sk = 0.0;
+        rho = fabs(a);
+    } else if (a == 0.0) {
+        ck = 0.0;
+        sk = sgn(b);
+        rho = fabs(b);
+    } else if (fabs(b) > fabs(a)) {
+        const double t = a / b;
+        sk = sgn(b) / sqrt(1.0 + t * t);
+        ck = sk * t;
+        rho = b / sk;
+    } else {
+        const double t = b / a;
+        ck = sgn(a) / sqrt(1.0 + t * t);
+        sk = ck * t;
+        rho = a / ck;
+    }
+    c[k - 1] = ck;
+    s[k - 1] = sk;
+    R[nr + k - 1] = rho;
+    const double zeta = sk * z[k - 1];
+    z[k - 1] = ck * z[k - 1];
+    const double rNorm = fabs(zeta);
+    if (hist) hist[hist_pos] = rNorm;
+    const int mach = (rNorm + 1.0 <= 1.0);
+    const int solved = (rNorm <= ctl->eps) || mach;
+    const int breakdown = (Hbis <= ctl->btol);
+    const int tired = (k >= inner_limit);
+    ctl->rNorm = rNorm;
+    ctl->Hbis = Hbis;
+    ctl->solved = solved;
+    ctl->breakdown = breakdown;
+    ctl->inner_iter = k;
+    const int stop = solved || breakdown || tired;
+    if (!stop) z[k] = zeta;
+    ctl->stop = stop;
+    st->rNorm = rNorm;
+    st->Hbis = Hbis;
+    st->iter = k;
+    st->stop = stop;
+    st->solved = solved;
+    st->breakdown = breakdown;
+}
+
+// CG scalar updates (Krylov.jl cg!, M = I, radius = 0, linesearch = false)
+__global__ void k_cg_begin(KrylovCtl* ctl, const double* sumsq, double* hist, double atol, double rtol,
+                           KrylovStatus* st) {
+    if (threadIdx.x != 0) return;
+    const double gamma = *sumsq;
+    const double rNorm = sqrt(gamma);
+    ctl->gamma = gamma;
+    ctl->pNorm2 = gamma;
+    ctl->rNorm = rNorm;
+    ctl->beta = rNorm;
+    ctl->eps = atol + rtol * rNorm;
+    ctl->solved = (rNorm <= ctl->eps) || (gamma == 0.0);
+    ctl->zerocurv = 0;
+    ctl->inconsistent = 0;
+    ctl->stop = ctl->solved;
+    ctl->inner_iter = 0;
+    if (hist) hist[0] = rNorm;
+    st->rNorm = rNorm; st->beta = rNorm; st->iter = 0; st->stop = ctl->stop; st->solved = ctl->solved; st->zerocurv = 0;
+}
+// after pAp = <p, Ap>
+__global__ void k_cg_alpha(KrylovCtl* ctl, const double* pAp_dev, KrylovStatus* st) {
+    if (threadIdx.x != 0) return;
+    if (ctl->stop) return;
+    const double pAp = *pAp_dev;
+    const double epsm = 2.220446049250313e-16;
+    ctl->pAp = pAp;
+    if (pAp <= epsm * ctl->pNorm2 && fabs(pAp) <= epsm * ctl->pNorm2) {
+        ctl->zerocurv = 1;
+        ctl->inconsistent = 1;
+        ctl->stop = 1;
+        st->rNorm = ctl->rNorm;
+        st->iter = ctl->inner_iter;
+        st->solved = 0;
+        st->stop = 1;
+        st->zerocurv = 1;
+        return;
+    }
+    ctl->alpha = ctl->gamma / pAp;
+    ctl->neg_alpha = -ctl->alpha;
+}
+// after gamma_next = <r, r>
+__global__ void k_cg_beta(KrylovCtl* ctl, const double* gnext_dev, int iter, int64_t itmax, double* hist,
+                          KrylovStatus* st) {
+    if (threadIdx.x != 0) return;
+    if (ctl->stop) return;
+    const double gn = *gnext_dev;
+    const double rNorm = sqrt(gn);
+    if (hist) hist[iter] = rNorm;
+    const int mach = (rNorm + 1.0 <= 1.0);
+    const int solved = (rNorm <= ctl->eps) || mach;
+    ctl->rNorm = rNorm;
+    ctl->solved = solved;
+    if (!solved) {
+        const double beta = gn / ctl->gamma;
+        ctl->pNorm2 = gn + beta * beta * ctl->pNorm2;
+        ctl->gamma = gn;
+        ctl->cg_beta = beta;
+    }
+    ctl->inner_iter = iter;
+    const int stop = solved || (iter >= itmax);
+    ctl->stop = stop;
+    st->rNorm = rNorm; st->iter = iter; st->stop = stop; st->solved = solved; st->zerocurv = 0;
+}
+// p <- r + beta p  with beta from the control block
+__global__ void __launch_bounds__(256) k_cg_update_p(double* __restrict__ p, const double* __restrict__ r,
+                                                     const KrylovCtl* __restrict__ ctl, int64_t n) {
+    if (ctl->stop) return;
+    const double beta = ctl->cg_beta;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += nth) p[j] = fma(beta, p[j], r[j]);
+}
+
+// ---------------------------------------------------------------------------------------
+// workspace memory
+// ---------------------------------------------------------------------------------------
+static int ws_alloc_vec(ak_krylov* ws, double** out) {
+    double* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, sizeof(double) * (size_t)(ws->n > 0 ? ws->n : 1));
+    if (e != cudaSuccess) {
+        set_error("krylov workspace: cudaMalloc of %lld doubles failed: %s", (long long)ws->n, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return AK_ERR_NOMEM;
+    }
+    ws->chunks.push_back(p);
+    *out = p;
+    return AK_OK;
+}
+
+static int ws_grow_scalars(ak_krylov* ws, int64_t kcap_new) {
+    Ctx* c = ws->ctx;
+    if (kcap_new <= ws->kcap) return AK_OK;
+    AK_CUDA(cudaStreamSynchronize(c->stream));
+    const int64_t nR = kcap_new * (kcap_new + 1) / 2;
+    auto regrow = [&](double** arr, int64_t old_n, int64_t new_n) -> int {
+        double* q = nullptr;
+        AK_CUDA(cudaMalloc(&q, sizeof(double) * (size_t)new_n));
+        AK_CUDA(cudaMemsetAsync(q, 0, sizeof(double) * (size_t)new_n, c->stream));
+        if (*arr && old_n > 0)
+            AK_CUDA(cudaMemcpyAsync(q, *arr, sizeof(double) * (size_t)old_n, cudaMemcpyDeviceToDevice, c->stream));
+        AK_CUDA(cudaStreamSynchronize(c->stream));
+        if (*arr) AK_CUDA(cudaFree(*arr));
+        *arr = q;
+        return AK_OK;
+    };
+    const int64_t oldk = ws->kcap;
+    AK_TRY(regrow(&ws->R, oldk * (oldk + 1) / 2, nR));
+    AK_TRY(regrow(&ws->c, oldk, kcap_new));
+    AK_TRY(regrow(&ws->s, oldk, kcap_new));
+    AK_TRY(regrow(&ws->z, oldk ? oldk + 1 : 0, kcap_new + 1));
+    AK_TRY(regrow(&ws->hcol, oldk ? 2 * (oldk + 1) : 0, 2 * (kcap_new + 1)));
+    ws->kcap = kcap_new;
+    return AK_OK;
+}
+
+static int ws_grow_hist(ak_krylov* ws, int64_t need) {
+    if (need <= ws->hist_cap) return AK_OK;
+    Ctx* c = ws->ctx;
+    int64_t nc = ws->hist_cap ? ws->hist_cap * 2 : 256;
+    if (nc < need) nc = need;
+    AK_CUDA(cudaStreamSynchronize(c->stream));
+    double* q = nullptr;
+    AK_CUDA(cudaMalloc(&q, sizeof(double) * (size_t)nc));
+    if (ws->hist) {
+        AK_CUDA(cudaMemcpy(q, ws->hist, sizeof(double) * (size_t)ws->hist_cap, cudaMemcpyDeviceToDevice));
+        AK_CUDA(cudaFree(ws->hist));
+    }
+    ws->hist = q;
+    ws->hist_cap = nc;
+    return AK_OK;
+}
+
+// make sure basis vectors V[0..count) exist
+static int ws_ensure_basis(ak_krylov* ws, int64_t count) {
+    if ((int64_t)ws->V.size() >= count) return AK_OK;
+    if (ws->max_basis > 0 && count > ws->max_basis) {
+        set_error("krylov workspace: basis would grow past max_basis = %lld", (long long)ws->max_basis);
+        return AK_ERR_NOMEM;
+    }
+    // grow in steps of `mem` vectors (Krylov.jl pushes one at a time; chunking amortises cudaMalloc)
+    int64_t target = (int64_t)ws->V.size() + ws->mem;
+    if (target < count) target = count;
+    if (ws->max_basis > 0 && target > ws->max_basis) target = ws->max_basis;
+    while ((int64_t)ws->V.size() < target) {
+        double* v = nullptr;
+        int rc = ws_alloc_vec(ws, &v);
+        if (rc != AK_OK) {
+            if ((int64_t)ws->V.size() >= count) break;  // enough for now
+            return rc;
+        }
+        ws->V.push_back(v);
+    }
+    return AK_OK;
+}
+
+static int ws_upload_basis_table(ak_krylov* ws, int64_t k) {
+    Ctx* c = ws->ctx;
+    if (k > ws->V_dev_cap) {
+        AK_CUDA(cudaStreamSynchronize(c->stream));
+        if (ws->V_dev) AK_CUDA(cudaFree((void*)ws->V_dev));
+        int64_t cap = ws->V_dev_cap ? ws->V_dev_cap * 2 : 64;
+        if (cap < k) cap = k;
+        AK_CUDA(cudaMalloc((void**)&ws->V_dev, sizeof(double*) * (size_t)cap));
+        ws->V_dev_cap = cap;
+    }
+    AK_CUDA(cudaMemcpyAsync((void*)ws->V_dev, ws->V.data(), sizeof(double*) * (size_t)k, cudaMemcpyHostToDevice,
+                            c->stream));
+    return AK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// GMRES
+// ---------------------------------------------------------------------------------------
+static int wait_status(ak_krylov* ws, int slot, KrylovStatus* out) {
+    AK_CUDA(cudaEventSynchronize(ws->ev[slot]));
+    memcpy(out, (const void*)&ws->status[slot], sizeof(KrylovStatus));
+    return AK_OK;
+}
+
+static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, const double* b,
+                       const ak_krylov_opts* o, ak_krylov_stats* st, double* hist_host, int64_t hist_cap) {
+    Ctx* c = ws->ctx;
+    const int64_t n = ws->n;
+    const int mem = ws->mem;
+    const int restart = o->restart, reorth = o->reorthogonalization;
+    const int fuse = o->fuse;
+    const bool want_hist = (hist_host != nullptr && hist_cap > 0) || o->history;
+    cudaStream_t sm = c->stream;
+
+    int64_t itmax = o->itmax == 0 ? 2 * n : o->itmax;
+    double* x = ws->x;
+    double* xr = x;
+    if (restart) {
+        if (!ws->dx) AK_TRY(ws_alloc_vec(ws, &ws->dx));
+        xr = ws->dx;
+    }
+    if (fuse == AK_FUSE_FULL && !ws->w[1]) AK_TRY(ws_alloc_vec(ws, &ws->w[1]));
+    AK_TRY(ws_ensure_basis(ws, mem));
+    AK_TRY(ws_grow_scalars(ws, mem));
+    if (want_hist) AK_TRY(ws_grow_hist(ws, 257));
+
+    int wi = 0;  // index of the buffer currently holding w / r0
+    double* w = ws->w[wi];
+    AK_TRY(launch_fill(c, n, x, 0.0));
+    AK_TRY(launch_copy(c, n, w, b));
+
+    memset(st, 0, sizeof(*st));
+    int64_t iter = 0, inner_itmax = itmax;
+    int npass = 0;
+    bool solved = false, tired = false, breakdown = false, inconsistent = false;
+    double rNorm = 0.0, beta0 = 0.0;
+    std::vector<double> Rh, zh;
+
+    while (true) {
+        // ---- pass prologue -------------------------------------------------------------
+        if (restart) {
+            AK_TRY(launch_fill(c, n, xr, 0.0));
+            if (npass >= 1) {
+                // w <- b - A x
+                AK_TRY(launch_jvp(c, prob, u, x, w, nullptr));
+                AK_TRY(launch_axpby(c, n, 1.0, b, -1.0, w));
+            }
+        }
+        AK_TRY(launch_sumsq(c, n, w, ws->hcol));
+        k_gmres_begin<<<1, 32, 0, sm>>>(ws->ctl, ws->hcol, ws->z, want_hist ? ws->hist : nullptr, npass == 0, o->atol,
+                                        o->rtol, &ws->status[kStatusRing]);
+        c->launches++;
+        AK_CUDA(cudaGetLastError());
+        AK_CUDA(cudaEventRecord(ws->ev[kStatusRing], sm));
+        // V[0] <- r0 / rNorm   (no-op when already converged / zero residual)
+        AK_TRY(launch_divcopy_dev(c, n, ws->V[0], w, &ws->ctl->rNorm, &ws->ctl->stop));
+        npass += 1;
+
+        const int64_t inner_limit = restart ? (mem < inner_itmax ? mem : inner_itmax) : inner_itmax;
+        int64_t K = 0;  // completed inner iterations of this pass
+        KrylovStatus hs;
+        AK_TRY(wait_status(ws, kStatusRing, &hs));
+        if (npass == 1) { beta0 = hs.beta; rNorm = hs.rNorm; }
+        if (hs.stop) {
+            solved = hs.solved != 0;
+            K = 0;
+        } else {
+            int64_t k = 0;
+            bool scale_pending = false;  // FUSE_FULL: V[k] = w/Hbis is folded into the next JVP
+            while (true) {
+                k += 1;
+                // storage for this iteration (basis vector k receives q/Hbis, 0-based)
+                if (!restart || k < mem) {
+                    if (k + 1 > (int64_t)ws->V.size()) {
+                        int rc = ws_ensure_basis(ws, k + 1);
+                        if (rc != AK_OK) {
+                            // cannot grow further: treat as out of iterations (reference would keep growing)
+                            if (k > 1) AK_TRY(wait_status(ws, (int)((k - 1) % kStatusRing), &hs));
+                            K = k - 1;
+                            tired = true;
+                            break;
+                        }
+                    }
+                }
+                if (k > ws->kcap) AK_TRY(ws_grow_scalars(ws, ws->kcap * 2 > k ? ws->kcap * 2 : k));
+                if (want_hist) AK_TRY(ws_grow_hist(ws, iter + k + 1));
+                const int64_t nr = k * (k - 1) / 2;
+                const int* stop = &ws->ctl->stop;
+                double* hcol = ws->hcol;
+
+                // w <- A V[k-1]  (+ fused divcopy of V[k-1], + fused first dot)
+                JvpFusion jf;
+                jf.stop_flag = stop;
+                double* wout = w;
+                if (fuse == AK_FUSE_FULL) {
+                    if (scale_pending) {
+                        jf.scale_src = w;
+                        jf.denom_dev = &ws->ctl->Hbis;
+                        wi ^= 1;
+                        wout = ws->w[wi];
+                    }
+                    jf.dot_with = ws->V[0];
+                    jf.dot_dev = hcol;
+                }
+                AK_TRY(launch_jvp(c, prob, u, ws->V[k - 1], wout, &jf));
+                w = wout;
+                // modified Gram-Schmidt
+                if (fuse == AK_FUSE_NONE) {
+                    for (int64_t i = 0; i < k; ++i) {
+                        AK_TRY(launch_mgs_step(c, n, w, nullptr, nullptr, ws->V[i], 0, hcol + i, stop));   // h = <V_i, w>
+                        AK_TRY(launch_mgs_step(c, n, w, ws->V[i], hcol + i, nullptr, 0, nullptr, stop));   // w -= h V_i
+                    }
+                    if (reorth) {
+                        double* h2 = hcol + (k + 1);
+                        for (int64_t i = 0; i < k; ++i) {
+                            AK_TRY(launch_mgs_step(c, n, w, nullptr, nullptr, ws->V[i], 0, h2 + i, stop));
+                            AK_TRY(launch_mgs_step(c, n, w, ws->V[i], h2 + i, nullptr, 0, nullptr, stop));
+                        }
+                        AK_TRY(launch_mgs_step(c, n, w, nullptr, nullptr, nullptr, 1, h2 + k, stop));
+                    } else {
+                        AK_TRY(launch_mgs_step(c, n, w, nullptr, nullptr, nullptr, 1, hcol + k, stop));
+                    }
+                } else {
+                    if (fuse != AK_FUSE_FULL)
+                        AK_TRY(launch_mgs_step(c, n, w, nullptr, nullptr, ws->V[0], 0, hcol, stop));
+                    for (int64_t i = 0; i + 1 < k; ++i)
+                        AK_TRY(launch_mgs_step(c, n, w, ws->V[i], hcol + i, ws->V[i + 1], 0, hcol + i + 1, stop));
+                    if (reorth) {
+                        double* h2 = hcol + (k + 1);
+                        // last axpy of sweep 1 fused with first dot of sweep 2
+                        AK_TRY(launch_mgs_step(c, n, w, ws->V[k - 1], hcol + k - 1, ws->V[0], 0, h2, stop));
+                        for (int64_t i = 0; i + 1 < k; ++i)
+                            AK_TRY(launch_mgs_step(c, n, w, ws->V[i], h2 + i, ws->V[i + 1], 0, h2 + i + 1, stop));
+                        AK_TRY(launch_mgs_step(c, n, w, ws->V[k - 1], h2 + k - 1, nullptr, 1, h2 + k, stop));
+                    } else {
+                        AK_TRY(launch_mgs_step(c, n, w, ws->V[k - 1], hcol + k - 1, nullptr, 1, hcol + k, stop));
+                    }
+                }
+                const int slot = (int)(k % kStatusRing);
+                k_gmres_givens<<<1, 32, 0, sm>>>(ws->ctl, (int)k, nr, ws->R, ws->c, ws->s, ws->z, hcol, reorth,
+                                                 want_hist ? ws->hist : nullptr, iter + k, (int)inner_limit,
+                                                 &ws->status[slot]);
+                c->launches++;
+                AK_CUDA(cudaGetLastError());
+                AK_CUDA(cudaEventRecord(ws->ev[slot], sm));
+                // V[k] <- w / Hbis (skipped on the device when this iteration stopped the pass)
+                if (k < inner_limit) {
+                    if (fuse == AK_FUSE_FULL) scale_pending = true;
+                    else AK_TRY(launch_divcopy_dev(c, n, ws->V[k], w, &ws->ctl->Hbis, stop));
+                }
+                // look at the previous iteration's verdict while this one runs
+                if (k > 1) {
+                    AK_TRY(wait_status(ws, (int)((k - 1) % kStatusRing), &hs));
+                    if (hs.stop) { K = k - 1; break; }
+                }
+                if (k >= inner_limit) {
+                    AK_TRY(wait_status(ws, slot, &hs));
+                    K = hs.stop && hs.iter == k ? k : hs.iter;
+                    break;
+                }
+            }
+            solved = hs.solved != 0;
+            breakdown = hs.breakdown != 0;
+            rNorm = hs.rNorm;
+            K = hs.iter;
+        }
+
+        // ---- solve R y = z on the host (K x K packed upper triangle), x += V y ------------
+        if (K > 0) {
+            const int64_t nR = K * (K + 1) / 2;
+            Rh.resize((size_t)nR);
+            zh.resize((size_t)K);
+            AK_CUDA(cudaMemcpyAsync(Rh.data(), ws->R, sizeof(double) * (size_t)nR, cudaMemcpyDeviceToHost, sm));
+            AK_CUDA(cudaMemcpyAsync(zh.data(), ws->z, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost, sm));
+            AK_CUDA(cudaStreamSynchronize(sm));
+            const double btol = pow(2.220446049250313e-16, 0.75);
+            double* y = zh.data();
+            for (int64_t i = K; i >= 1; --i) {
+                int64_t pos = nR + i - K - 1;
+                for (int64_t j = K; j >= i + 1; --j) {
+                    y[i - 1] = y[i - 1] - Rh[(size_t)pos] * y[j - 1];
+                    pos = pos - j + 1;
+                }
+                if (fabs(Rh[(size_t)pos]) <= btol) { y[i - 1] = 0.0; inconsistent = true; }
+                else y[i - 1] = y[i - 1] / Rh[(size_t)pos];
+            }
+            AK_CUDA(cudaMemcpyAsync(ws->hcol, y, sizeof(double) * (size_t)K, cudaMemcpyHostToDevice, sm));
+            AK_TRY(ws_upload_basis_table(ws, K));
+            AK_TRY(launch_basis_combine(c, n, xr, ws->V_dev, ws->hcol, (int)K, /*zero_x_first=*/1));
+            if (restart) AK_TRY(launch_axpy(c, n, 1.0, xr, x));
+            // y lives in host memory that the async copy reads: drain before the vectors are reused
+            AK_CUDA(cudaStreamSynchronize(sm));
+        }
+        inner_itmax -= K;
+        iter += K;
+        if (iter >= itmax) tired = true;
+        if (solved || tired || breakdown) break;
+        // FUSE_FULL leaves the last residual candidate in w[wi]; the restart recomputes w anyway
+        w = ws->w[wi];
+    }
+
+    st->niter = iter;
+    st->solved = solved ? 1 : 0;
+    st->inconsistent = inconsistent ? 1 : 0;
+    st->breakdown = breakdown ? 1 : 0;
+    st->npass = npass;
+    st->rnorm = rNorm;
+    st->beta = beta0;
+    if (hist_host && hist_cap > 0 && ws->hist) {
+        int64_t m = iter + 1 < hist_cap ? iter + 1 : hist_cap;
+        AK_CUDA(cudaMemcpyAsync(hist_host, ws->hist, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, sm));
+        AK_CUDA(cudaStreamSynchronize(sm));
+    }
+    int flags = 0;
+    if (!solved) flags |= AK_FLAG_NOT_SOLVED;
+    if (breakdown) flags |= AK_FLAG_BREAKDOWN;
+    if (inconsistent) flags |= AK_FLAG_INCONSISTENT;
+    return flags;
+}
+
+// ---------------------------------------------------------------------------------------
+// CG (Krylov.jl cg!, M = I) — every call site in examples/bratu.jl:59-108 uses algo = :cg
+// ---------------------------------------------------------------------------------------
+static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, const double* b, const ak_krylov_opts* o,
+                    ak_krylov_stats* st, double* hist_host, int64_t hist_cap) {
+    Ctx* c = ws->ctx;
+    const int64_t n = ws->n;
+    cudaStream_t sm = c->stream;
+    const bool want_hist = (hist_host != nullptr && hist_cap > 0) || o->history;
+    const int64_t itmax = o->itmax == 0 ? 2 * n : o->itmax;
+    if (!ws->hcol) AK_TRY(ws_grow_scalars(ws, 4));
+    if (want_hist) AK_TRY(ws_grow_hist(ws, 257));
+    double *x = ws->x, *r = ws->r, *p = ws->p, *Ap = ws->Ap;
+    const int* stop = &ws->ctl->stop;
+    AK_TRY(launch_fill(c, n, x, 0.0));
+    AK_TRY(launch_copy(c, n, r, b));
+    AK_TRY(launch_copy(c, n, p, r));
+    AK_TRY(launch_sumsq(c, n, r, ws->hcol));
+    k_cg_begin<<<1, 32, 0, sm>>>(ws->ctl, ws->hcol, want_hist ? ws->hist : nullptr, o->atol, o->rtol, &ws->status[kStatusRing]);
+    c->launches++;
+    AK_CUDA(cudaGetLastError());
+    AK_CUDA(cudaEventRecord(ws->ev[kStatusRing], sm));
+    KrylovStatus hs;
+    AK_TRY(wait_status(ws, kStatusRing, &hs));
+    memset(st, 0, sizeof(*st));
+    st->beta = hs.beta;
+    int64_t iter = 0;
+    bool solved = hs.solved != 0, zerocurv = false;
+    double rNorm = hs.rNorm;
+    if (!hs.stop && itmax > 0) {
+        int64_t k = 0;
+        while (true) {
+            k += 1;
+            if (want_hist) AK_TRY(ws_grow_hist(ws, k + 1));
+            JvpFusion jf;
+            jf.stop_flag = stop;
+            jf.dot_with = p;
+            jf.dot_dev = ws->hcol + 1;
+            AK_TRY(launch_jvp(c, prob, u, p, Ap, &jf));  // Ap = A p, pAp = <p, Ap>
+            const int slot = (int)(k % kStatusRing);
+            k_cg_alpha<<<1, 32, 0, sm>>>(ws->ctl, ws->hcol + 1, &ws->status[slot]);
+            c->launches++;
+            // x += alpha p ; r -= alpha Ap (+ gamma_next = <r, r>)
+            {
+                // y += s_dev * x  kernels honour the stop flag through launch_mgs_step / k_ew
+                AK_TRY(launch_mgs_step(c, n, x, p, &ws->ctl->neg_alpha, nullptr, 0, nullptr, stop));
+                AK_TRY(launch_mgs_step(c, n, r, Ap, &ws->ctl->alpha, nullptr, 1, ws->hcol + 2, stop));
+            }
+            k_cg_beta<<<1, 32, 0, sm>>>(ws->ctl, ws->hcol + 2, (int)k, itmax, want_hist ? ws->hist : nullptr,
+                                        &ws->status[slot]);
+            c->launches++;
+            AK_CUDA(cudaGetLastError());
+            AK_CUDA(cudaEventRecord(ws->ev[slot], sm));
+            // p <- r + beta p
+            {
+                int blocks = (int)((n + 255) / 256);
+                if (blocks > c->num_sms * 8) blocks = c->num_sms * 8;
+                k_cg_update_p<<<blocks, 256, 0, sm>>>(p, r, ws->ctl, n);
+                c->launches++;
+                AK_CUDA(cudaGetLastError());
+            }
+            if (k > 1) {
+                AK_TRY(wait_status(ws, (int)((k - 1) % kStatusRing), &hs));
+                if (hs.stop) break;
+            }
+            if (k >= itmax) {
+                AK_TRY(wait_status(ws, slot, &hs));
+                break;
+            }
+        }
+        // the record we stopped on
+        solved = hs.solved != 0;
+        zerocurv = hs.zerocurv != 0;
+        iter = hs.iter;
+        rNorm = hs.rNorm;
+    }
+    AK_CUDA(cudaStreamSynchronize(sm));
+    st->niter = iter;
+    st->solved = solved;
+    st->inconsistent = zerocurv;
+    st->npass = 1;
+    st->rnorm = rNorm;
+    if (hist_host && hist_cap > 0 && ws->hist) {
+        int64_t m = iter + 1 < hist_cap ? iter + 1 : hist_cap;
+        AK_CUDA(cudaMemcpy(hist_host, ws->hist, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost));
+    }
+    int flags = 0;
+    if (!solved) flags |= AK_FLAG_NOT_SOLVED;
+    if (zerocurv) flags |= AK_FLAG_INCONSISTENT;
+    return flags;
+}
+
+int krylov_solve_internal(ak_krylov* ws, const ak_problem* p, const double* u, const double* b,
+                          const ak_krylov_opts* opts, ak_krylov_stats* st, double* hist_host, int64_t hist_cap) {
+    if (ws->algo == AK_ALGO_CG) return cg_solve(ws, p, u, b, opts, st, hist_host, hist_cap);
+    return gmres_solve(ws, p, u, b, opts, st, hist_host, hist_cap);
+}
+
+}  // namespace ak
+
+using namespace ak;
+
+AK_API void ak_krylov_default_opts(ak_krylov_opts* o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->atol = sqrt(2.220446049250313e-16);
+    o->rtol = sqrt(2.220446049250313e-16);
+    o->fuse = AK_FUSE_MGS;
+}
+
+AK_API int ak_krylov_create(ak_ctx* ctx, int32_t algo, int64_t n, int32_t memory, int64_t max_basis, ak_krylov** out) {
+    AK_REQUIRE(ctx && out && n >= 1, "ak_krylov_create: bad argument");
+    AK_REQUIRE(algo == AK_ALGO_GMRES || algo == AK_ALGO_CG, "ak_krylov_create: unknown algo");
+    AK_REQUIRE(memory >= 1, "ak_krylov_create: memory must be >= 1");
+    ak_krylov* ws = new ak_krylov();
+    ws->ctx = &ctx->c;
+    ws->algo = algo;
+    ws->n = n;
+    ws->mem = memory;
+    ws->max_basis = max_basis;
+    int rc = AK_OK;
+    do {
+        if ((rc = ws_alloc_vec(ws, &ws->x)) != AK_OK) break;
+        if (algo == AK_ALGO_GMRES) {
+            if ((rc = ws_alloc_vec(ws, &ws->w[0])) != AK_OK) break;
+            if ((rc = ws_ensure_basis(ws, memory)) != AK_OK) break;
+        } else {
+            if ((rc = ws_alloc_vec(ws, &ws->r)) != AK_OK) break;
+            if ((rc = ws_alloc_vec(ws, &ws->p)) != AK_OK) break;
+            if ((rc = ws_alloc_vec(ws, &ws->Ap)) != AK_OK) break;
+        }
+        if (cudaMalloc(&ws->ctl, sizeof(KrylovCtl)) != cudaSuccess) { rc = AK_ERR_NOMEM; break; }
+        cudaMemset(ws->ctl, 0, sizeof(KrylovCtl));
+        if (cudaHostAlloc((void**)&ws->status, sizeof(KrylovStatus) * kStatusSlots, cudaHostAllocMapped) != cudaSuccess) {
+            rc = AK_ERR_NOMEM;
+            break;
+        }
+        memset(ws->status, 0, sizeof(KrylovStatus) * kStatusSlots);
+        for (int i = 0; i < kStatusSlots; ++i)
+            if (cudaEventCreateWithFlags(&ws->ev[i], cudaEventDisableTiming) != cudaSuccess) { rc = AK_ERR_CUDA; break; }
+        if (rc != AK_OK) break;
+        rc = ws_grow_scalars(ws, memory > 4 ? memory : 4);
+    } while (0);
+    if (rc != AK_OK) {
+        if (rc == AK_ERR_NOMEM) set_error("ak_krylov_create: out of device memory (n = %lld, memory = %d)", (long long)n, memory);
+        ak_krylov_destroy(ws);
+        return rc;
+    }
+    *out = ws;
+    return AK_OK;
+}
+
+AK_API int ak_krylov_destroy(ak_krylov* ws) {
+    if (!ws) return AK_OK;
+    if (ws->ctx && ws->ctx->stream) cudaStreamSynchronize(ws->ctx->stream);
+    for (double* p : ws->chunks) cudaFree(p);
+    if (ws->V_dev) cudaFree((void*)ws->V_dev);
+    cudaFree(ws->R); cudaFree(ws->c); cudaFree(ws->s); cudaFree(ws->z); cudaFree(ws->hcol); cudaFree(ws->hist);
+    cudaFree(ws->ctl);
+    if (ws->status) cudaFreeHost(ws->status);
+    for (int i = 0; i < kStatusSlots; ++i)
+        if (ws->ev[i]) cudaEventDestroy(ws->ev[i]);
+    delete ws;
+    return AK_OK;
+}
+
+AK_API int ak_krylov_solve(ak_krylov* ws, const ak_problem* p, const double* u, const double* b,
+                           const ak_krylov_opts* opts, ak_krylov_stats* stats_out, double* hist_host,
+                           int64_t hist_cap) {
+    AK_REQUIRE(ws && p && b && opts && stats_out, "ak_krylov_solve: NULL argument");
+    AK_REQUIRE(ak_problem_size(p) == ws->n, "ak_krylov_solve: problem size does not match the workspace");
+    return krylov_solve_internal(ws, p, u, b, opts, stats_out, hist_host, hist_cap);
+}
+
+AK_API double* ak_krylov_x(ak_krylov* ws) { return ws ? ws->x : nullptr; }

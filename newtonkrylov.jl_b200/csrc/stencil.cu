@@ -1,0 +1,807 @@
+// Residual F!(res,u,p) and exact tangent-linear JVP kernels (fp64, HBM-bound).
+//
+// Reference computations replaced (paths relative to the reference tree):
+//   bratu!               examples/bratu.jl:14-24            -> OP_RES_BRATU (1-D), and its 2-D extension
+//   heat_1D! + bc!       examples/heat_1D.jl:12-37,39-42     -> OP_RES_HEAT (1-D)
+//   diffusion! + bc_*!   examples/heat_2D.jl:15-62           -> OP_RES_HEAT (2-D)
+//   heat_1D! (DG)        examples/heat_1D_DG.jl:17-36        -> k_dg
+//   G_Euler!/G_Midpoint!/G_Trapezoid!  examples/implicit.jl:8-37
+//   mul!(out, J, v)      src/Ariadne.jl:48-57 (Enzyme forward mode) -> OP_JVP_* (hand-derived tangents)
+//
+// Layout: compact nx*ny slab, x fastest, no ghost cells.  Dirichlet ghosts are implicit zeros,
+// periodic ghosts are index wraps, inter-GPU ghosts arrive as two row pointers (lo, hi).
+//
+// Arithmetic follows the Julia source's operation order; __dadd_rn/__dmul_rn/__ddiv_rn are used
+// so that nvcc does not contract across the reference's rounding points.
+//
+// 2-D kernels march down RY rows keeping a 3-row window in registers (each row is read once per
+// tile, +2 ghost rows per tile that hit L2), x-neighbours come from warp shuffles.
+#include "ak_internal.h"
+#include "common.cuh"
+
+namespace ak {
+
+enum { OP_RES_BRATU = 0, OP_JVP_BRATU = 1, OP_RES_HEAT = 2, OP_JVP_HEAT = 3 };
+enum { RED_NONE = 0, RED_SUMSQ = 1, RED_DOT = 2 };
+
+struct StencilArgs {
+    int64_t nx, ny;
+    int32_t ry;          // rows per tile (2-D)
+    int32_t wrap_x;      // periodic in x
+    int32_t bc;          // AK_BC_* (1-D boundary-point semantics)
+    int32_t scheme;      // AK_EULER / AK_MIDPOINT / AK_TRAPEZOID (heat)
+    double dx2, dy2, lambda, a, dt;
+    double c0, c1;       // JVP_HEAT: out = c1 * L(c0 * v) - v
+    const double* in;    // u (residual) or v (JVP) or scale_src (fused divcopy)
+    const double* lo;    // ghost row y = -1  (nullptr -> 0)
+    const double* hi;    // ghost row y = ny  (nullptr -> 0)
+    const double* aux;   // RES_HEAT: u_n ; JVP_BRATU: coef (or u when coef_from_u)
+    const double* aux_lo;  // ghost rows of u_n (midpoint / trapezoid only)
+    const double* aux_hi;
+    double* aux_out;     // RES_BRATU: coef out (may be null)
+    double* out;
+    double* in_write;    // fused divcopy: scaled `in` is stored here (own rows) ; 1-D heat: BC write-back target
+    const double* denom; // fused divcopy: device scalar
+    const double* dot_with;
+    double* red_out;
+    double* partials;
+    unsigned int* ticket;
+    const int* stop;
+    int32_t coef_from_u;
+};
+
+// ---- vector row accessors --------------------------------------------------------------
+template <int VEC>
+AK_DEV void ldv(const double* p, double (&r)[VEC]);
+template <>
+AK_DEV void ldv<1>(const double* p, double (&r)[1]) { r[0] = *p; }
+template <>
+AK_DEV void ldv<2>(const double* p, double (&r)[2]) {
+    const double2 t = *reinterpret_cast<const double2*>(p);
+    r[0] = t.x; r[1] = t.y;
+}
+template <>
+AK_DEV void ldv<4>(const double* p, double (&r)[4]) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3]) : "l"(p));
+}
+// streaming variant for operands read exactly once (coef, u_n, dot_with)
+template <int VEC>
+AK_DEV void ldv_s(const double* p, double (&r)[VEC]);
+template <>
+AK_DEV void ldv_s<1>(const double* p, double (&r)[1]) { r[0] = ld1_stream(p); }
+template <>
+AK_DEV void ldv_s<2>(const double* p, double (&r)[2]) {
+    const double2 t = ld2_stream(p);
+    r[0] = t.x; r[1] = t.y;
+}
+template <>
+AK_DEV void ldv_s<4>(const double* p, double (&r)[4]) {
+    const d4 t = ld4_stream(p);
+    r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+}
+template <int VEC>
+AK_DEV void stv(double* p, const double (&r)[VEC]);
+template <>
+AK_DEV void stv<1>(double* p, const double (&r)[1]) { *p = r[0]; }
+template <>
+AK_DEV void stv<2>(double* p, const double (&r)[2]) { *reinterpret_cast<double2*>(p) = make_double2(r[0], r[1]); }
+template <>
+AK_DEV void stv<4>(double* p, const double (&r)[4]) {
+    d4 t = {r[0], r[1], r[2], r[3]};
+    st4(p, t);
+}
+
+// second difference in the reference's association: ((e - 2c) + w) / d2
+AK_DEV double second_diff(double e, double c, double w, double d2) {
+    return __ddiv_rn(__dadd_rn(__dsub_rn(e, __dmul_rn(2.0, c)), w), d2);
+}
+
+// ========================================================================================
+// 2-D five-point kernels
+// ========================================================================================
+constexpr int kTX = 128;  // threads per block, all along x
+
+template <int OP, int VEC, bool SCALE, int RED>
+__global__ void __launch_bounds__(kTX) k_stencil2d(const StencilArgs p) {
+    __shared__ double sh[32];
+    if (p.stop != nullptr && *p.stop != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t nx = p.nx, ny = p.ny;
+    const int64_t x0 = ((int64_t)blockIdx.x * kTX + threadIdx.x) * VEC;
+    const bool active = x0 < nx;
+    const int64_t y0 = (int64_t)blockIdx.y * p.ry;
+    const int64_t y1 = (y0 + p.ry < ny) ? y0 + p.ry : ny;
+    const double denom = SCALE ? *p.denom : 1.0;
+
+    auto row_ptr = [&](int64_t y) -> const double* {
+        if (y < 0) return p.lo;
+        if (y >= ny) return p.hi;
+        return p.in + y * nx;
+    };
+    auto load_row = [&](const double* src, double (&r)[VEC]) {
+        if (!active || src == nullptr) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) r[i] = 0.0;
+            return;
+        }
+        ldv<VEC>(src + x0, r);
+        if (SCALE) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) r[i] = __ddiv_rn(r[i], denom);
+        }
+    };
+    // x-neighbour that is not held by a lane of this warp
+    auto edge = [&](const double* src, int64_t x) -> double {
+        if (src == nullptr) return 0.0;
+        if (x < 0) { if (!p.wrap_x) return 0.0; x += nx; }
+        else if (x >= nx) { if (!p.wrap_x) return 0.0; x -= nx; }
+        double v = src[x];
+        if (SCALE) v = __ddiv_rn(v, denom);
+        return v;
+    };
+
+    double prev[VEC], cur[VEC], next[VEC];
+    const double* cur_src = row_ptr(y0);
+    load_row(row_ptr(y0 - 1), prev);
+    load_row(cur_src, cur);
+    double acc = 0.0;
+
+    for (int64_t y = y0; y < y1; ++y) {
+        const double* next_src = row_ptr(y + 1);
+        load_row(next_src, next);
+        double left = __shfl_up_sync(0xffffffffu, cur[VEC - 1], 1);
+        double right = __shfl_down_sync(0xffffffffu, cur[0], 1);
+        if (active) {
+            if (lane == 0) left = edge(cur_src, x0 - 1);
+            if (lane == 31 || x0 + VEC >= nx) right = edge(cur_src, x0 + VEC);
+            const int64_t off = y * nx + x0;
+            double aux[VEC], o[VEC];
+            if (OP == OP_JVP_BRATU || OP == OP_RES_HEAT) ldv_s<VEC>(p.aux + off, aux);
+            double cf[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const double w = (i == 0) ? left : cur[i - 1];
+                const double e = (i == VEC - 1) ? right : cur[(i + 1) % VEC];
+                const double c = cur[i];
+                const double xx = second_diff(e, c, w, p.dx2);
+                const double yy = second_diff(next[i], c, prev[i], p.dy2);
+                const double lap = __dadd_rn(xx, yy);
+                if (OP == OP_RES_BRATU) {
+                    cf[i] = __dmul_rn(p.lambda, exp(c));
+                    o[i] = __dadd_rn(lap, cf[i]);
+                } else if (OP == OP_JVP_BRATU) {
+                    const double k = p.coef_from_u ? __dmul_rn(p.lambda, exp(aux[i])) : aux[i];
+                    o[i] = __dadd_rn(lap, __dmul_rn(k, c));
+                } else if (OP == OP_RES_HEAT) {  // G_Euler!: (un + dt*du) - u
+                    const double du = __dmul_rn(p.a, lap);
+                    o[i] = __dsub_rn(__dadd_rn(aux[i], __dmul_rn(p.dt, du)), c);
+                } else {  // OP_JVP_HEAT: c1 * dv - v
+                    const double dv = __dmul_rn(p.a, lap);
+                    o[i] = __dsub_rn(__dmul_rn(p.c1, dv), c);
+                }
+            }
+            stv<VEC>(p.out + off, o);
+            if (OP == OP_RES_BRATU && p.aux_out != nullptr) stv<VEC>(p.aux_out + off, cf);
+            if (SCALE) stv<VEC>(p.in_write + off, cur);
+            if (RED == RED_SUMSQ) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc = fma(o[i], o[i], acc);
+            } else if (RED == RED_DOT) {
+                double dw[VEC];
+                ldv_s<VEC>(p.dot_with + off, dw);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc = fma(dw[i], o[i], acc);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { prev[i] = cur[i]; cur[i] = next[i]; }
+        cur_src = next_src;
+    }
+    if (RED != RED_NONE) {
+        const double s = block_sum(acc, sh);
+        const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+        grid_sum_finish(s, p.partials, p.ticket, bid, gridDim.x * gridDim.y, p.red_out, sh);
+    }
+}
+
+// ========================================================================================
+// 1-D three-point kernels (Bratu 1-D, heat 1-D with its two boundary points)
+// ========================================================================================
+constexpr int kT1 = 256;
+
+// value of the 1-D heat state at index i after bc!/periodic_bc! has been applied
+AK_DEV double heat1d_bc_value(const double* src, int64_t i, int64_t n, int bc) {
+    if (i == 0) return bc == AK_BC_ZERO ? 0.0 : src[n - 2];
+    if (i == n - 1) return bc == AK_BC_ZERO ? 0.0 : src[1];
+    return src[i];
+}
+
+template <int OP, int VEC, bool SCALE, int RED>
+__global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
+    __shared__ double sh[32];
+    if (p.stop != nullptr && *p.stop != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t n = p.nx;
+    const int64_t x0 = ((int64_t)blockIdx.x * kT1 + threadIdx.x) * VEC;
+    const bool active = x0 < n;
+    const double denom = SCALE ? *p.denom : 1.0;
+    constexpr bool HEAT = (OP == OP_RES_HEAT || OP == OP_JVP_HEAT);
+
+    auto value = [&](int64_t i) -> double {  // scalar access incl. boundary semantics
+        double v;
+        if (HEAT) {
+            v = heat1d_bc_value(p.in, i, n, p.bc);
+        } else {  // Bratu: y_0 = y_{N+1} = 0 outside the array
+            if (i < 0 || i >= n) return 0.0;
+            v = p.in[i];
+        }
+        if (SCALE) v = __ddiv_rn(v, denom);
+        return v;
+    };
+
+    double cur[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) cur[i] = 0.0;
+    if (active) {
+        ldv<VEC>(p.in + x0, cur);
+        if (SCALE) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) cur[i] = __ddiv_rn(cur[i], denom);
+        }
+        if (HEAT) {  // boundary points take their BC value
+            if (x0 == 0) cur[0] = value(0);
+            if (x0 + VEC == n) cur[VEC - 1] = value(n - 1);
+        }
+    }
+    double left = __shfl_up_sync(0xffffffffu, cur[VEC - 1], 1);
+    double right = __shfl_down_sync(0xffffffffu, cur[0], 1);
+    double acc = 0.0;
+    if (active) {
+        if (lane == 0) left = (x0 == 0) ? 0.0 : value(x0 - 1);
+        if (lane == 31 || x0 + VEC >= n) right = (x0 + VEC >= n) ? 0.0 : value(x0 + VEC);
+        double aux[VEC], o[VEC], cf[VEC];
+        if (OP == OP_JVP_BRATU || OP == OP_RES_HEAT) ldv_s<VEC>(p.aux + x0, aux);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const double w = (i == 0) ? left : cur[i - 1];
+            const double e = (i == VEC - 1) ? right : cur[(i + 1) % VEC];
+            const double c = cur[i];
+            if (OP == OP_RES_BRATU) {
+                cf[i] = __dmul_rn(p.lambda, exp(c));
+                o[i] = __dadd_rn(second_diff(e, c, w, p.dx2), cf[i]);
+            } else if (OP == OP_JVP_BRATU) {
+                const double k = p.coef_from_u ? __dmul_rn(p.lambda, exp(aux[i])) : aux[i];
+                o[i] = __dadd_rn(second_diff(e, c, w, p.dx2), __dmul_rn(k, c));
+            } else {
+                // heat_1D.jl:22: du[i] = a * (u[i+1] - 2u[i] + u[i-1]) / dx^2 ; du[1] = du[end] = 0
+                const int64_t gi = x0 + i;
+                const bool bnd = (gi == 0 || gi == n - 1);
+                const double du =
+                    bnd ? 0.0 : __ddiv_rn(__dmul_rn(p.a, __dadd_rn(__dsub_rn(e, __dmul_rn(2.0, c)), w)), p.dx2);
+                if (OP == OP_RES_HEAT) o[i] = __dsub_rn(__dadd_rn(aux[i], __dmul_rn(p.dt, du)), c);
+                else o[i] = __dsub_rn(__dmul_rn(p.c1, du), c);
+            }
+        }
+        stv<VEC>(p.out + x0, o);
+        if (OP == OP_RES_BRATU && p.aux_out != nullptr) stv<VEC>(p.aux_out + x0, cf);
+        if (SCALE) {
+            stv<VEC>(p.in_write + x0, cur);
+        } else if (HEAT && p.in_write != nullptr) {
+            // the reference's bc!(u) mutates the state / tangent seed in place (heat_1D.jl:16,34-42)
+            if (x0 == 0) p.in_write[0] = cur[0];
+            if (x0 + VEC == n) p.in_write[n - 1] = cur[VEC - 1];
+        }
+        if (RED == RED_SUMSQ) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc = fma(o[i], o[i], acc);
+        } else if (RED == RED_DOT) {
+            double dw[VEC];
+            ldv_s<VEC>(p.dot_with + x0, dw);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc = fma(dw[i], o[i], acc);
+        }
+    }
+    if (RED != RED_NONE) {
+        const double s = block_sum(acc, sh);
+        grid_sum_finish(s, p.partials, p.ticket, blockIdx.x, gridDim.x, p.red_out, sh);
+    }
+}
+
+// ========================================================================================
+// DG (SBP, 4 LGL nodes per element, periodic): du = D1m * (D1p * u)   heat_1D_DG.jl:32-36
+// one thread per element; neighbour coupling through warp shuffles
+// ========================================================================================
+struct DgArgs {
+    int64_t ne;        // elements
+    double D[4][4];    // LGL derivative matrix
+    double jac;        // 2/h
+    double mw;         // (h/2) * w_edge,  w_edge = 1/6
+    double dt, c0, c1;
+    const double* in;
+    const double* un;  // residual only
+    double* out;
+    double* in_write;
+    const double* denom;
+    const double* dot_with;
+    double* red_out;
+    double* partials;
+    unsigned int* ticket;
+    const int* stop;
+};
+
+AK_DEV void dg_local(const double (&D)[4][4], double jac, const double (&u)[4], double (&o)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        double s = __dmul_rn(D[j][0], u[0]);
+        s = __dadd_rn(s, __dmul_rn(D[j][1], u[1]));
+        s = __dadd_rn(s, __dmul_rn(D[j][2], u[2]));
+        s = __dadd_rn(s, __dmul_rn(D[j][3], u[3]));
+        o[j] = __dmul_rn(jac, s);
+    }
+}
+
+template <bool RESIDUAL, bool SCALE, int RED>
+__global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
+    __shared__ double sh[32];
+    if (p.stop != nullptr && *p.stop != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t ne = p.ne;
+    const int64_t e = (int64_t)blockIdx.x * kT1 + threadIdx.x;
+    const bool active = e < ne;
+    const double denom = SCALE ? *p.denom : 1.0;
+
+    auto load_elem = [&](int64_t el, double (&r)[4]) {
+        ldv<4>(p.in + 4 * el, r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (SCALE) r[i] = __ddiv_rn(r[i], denom);
+            if (!RESIDUAL) r[i] = __dmul_rn(p.c0, r[i]);
+        }
+    };
+    double u[4] = {0, 0, 0, 0}, raw[4] = {0, 0, 0, 0};
+    if (active) {
+        ldv<4>(p.in + 4 * e, raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (SCALE) raw[i] = __ddiv_rn(raw[i], denom);
+            u[i] = RESIDUAL ? raw[i] : __dmul_rn(p.c0, raw[i]);
+        }
+    }
+    // D1p: needs first node of the element to the right
+    double u_next0 = __shfl_down_sync(0xffffffffu, u[0], 1);
+    if (active && (lane == 31 || e + 1 >= ne)) {
+        const int64_t en = (e + 1 == ne) ? 0 : e + 1;
+        double t = p.in[4 * en];
+        if (SCALE) t = __ddiv_rn(t, denom);
+        u_next0 = RESIDUAL ? t : __dmul_rn(p.c0, t);
+    }
+    double t1[4] = {0, 0, 0, 0};
+    if (active) {
+        dg_local(p.D, p.jac, u, t1);
+        t1[3] = __dadd_rn(t1[3], __ddiv_rn(__dsub_rn(u_next0, u[3]), p.mw));
+    }
+    // D1m: needs last node of (D1p u) of the element to the left
+    double t_prev3 = __shfl_up_sync(0xffffffffu, t1[3], 1);
+    if (active && lane == 0) {
+        const int64_t ep = (e == 0) ? ne - 1 : e - 1;
+        double up[4], tp[4];
+        load_elem(ep, up);
+        dg_local(p.D, p.jac, up, tp);
+        t_prev3 = __dadd_rn(tp[3], __ddiv_rn(__dsub_rn(u[0], up[3]), p.mw));
+    }
+    double acc = 0.0;
+    if (active) {
+        double du[4], o[4];
+        dg_local(p.D, p.jac, t1, du);
+        du[0] = __dadd_rn(du[0], __ddiv_rn(__dsub_rn(t1[0], t_prev3), p.mw));
+        if (RESIDUAL) {
+            double un[4];
+            ldv_s<4>(p.un + 4 * e, un);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dadd_rn(un[i], __dmul_rn(p.dt, du[i])), raw[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dmul_rn(p.c1, du[i]), raw[i]);
+        }
+        stv<4>(p.out + 4 * e, o);
+        if (SCALE) stv<4>(p.in_write + 4 * e, raw);
+        if (RED == RED_SUMSQ) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc = fma(o[i], o[i], acc);
+        } else if (RED == RED_DOT) {
+            double dw[4];
+            ldv_s<4>(p.dot_with + 4 * e, dw);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc = fma(dw[i], o[i], acc);
+        }
+    }
+    if (RED != RED_NONE) {
+        const double s = block_sum(acc, sh);
+        grid_sum_finish(s, p.partials, p.ticket, blockIdx.x, gridDim.x, p.red_out, sh);
+    }
+}
+
+// ========================================================================================
+// 2x2 system of test/runtests.jl:4-7 (known-answer path for the host logic)
+// ========================================================================================
+__global__ void k_simple2(const double* u, const double* v, double* out, double* red_out, int mode,
+                          const double* dot_with, const int* stop) {
+    if (stop != nullptr && *stop != 0) return;
+    if (threadIdx.x != 0) return;
+    const double x = u[0], y = u[1];
+    double o0, o1;
+    if (mode == 0) {  // residual
+        o0 = __dsub_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), 2.0);
+        o1 = __dsub_rn(__dadd_rn(exp(__dsub_rn(x, 1.0)), __dmul_rn(y, y)), 2.0);
+    } else if (mode == 1) {  // J v
+        o0 = __dadd_rn(__dmul_rn(__dmul_rn(2.0, x), v[0]), __dmul_rn(__dmul_rn(2.0, y), v[1]));
+        o1 = __dadd_rn(__dmul_rn(exp(__dsub_rn(x, 1.0)), v[0]), __dmul_rn(__dmul_rn(2.0, y), v[1]));
+    } else {  // J^T v
+        o0 = __dadd_rn(__dmul_rn(__dmul_rn(2.0, x), v[0]), __dmul_rn(exp(__dsub_rn(x, 1.0)), v[1]));
+        o1 = __dadd_rn(__dmul_rn(__dmul_rn(2.0, y), v[0]), __dmul_rn(__dmul_rn(2.0, y), v[1]));
+    }
+    out[0] = o0;
+    out[1] = o1;
+    if (red_out != nullptr) {
+        if (dot_with != nullptr) *red_out = fma(dot_with[1], o1, dot_with[0] * o0);
+        else *red_out = fma(o1, o1, o0 * o0);
+    }
+}
+
+// ========================================================================================
+// host-side dispatch
+// ========================================================================================
+static inline bool al(const void* p, int bytes) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % bytes) == 0; }
+
+template <int OP, int VEC>
+static void launch2d_v(Ctx* ctx, const StencilArgs& a, bool scale, int red, dim3 grid) {
+#define AK_L2D(S, R) k_stencil2d<OP, VEC, S, R><<<grid, kTX, 0, ctx->stream>>>(a)
+    if (scale) {
+        if (red == RED_DOT) AK_L2D(true, RED_DOT);
+        else AK_L2D(true, RED_NONE);
+    } else {
+        if (red == RED_DOT) AK_L2D(false, RED_DOT);
+        else if (red == RED_SUMSQ) AK_L2D(false, RED_SUMSQ);
+        else AK_L2D(false, RED_NONE);
+    }
+#undef AK_L2D
+}
+template <int OP>
+static int launch2d(Ctx* ctx, StencilArgs& a, bool scale, int red) {
+    // widest vector the row pitch and every operand allow
+    int vec = 1;
+    const void* ptrs[] = {a.in, a.lo, a.hi, a.aux, a.aux_out, a.out, a.in_write, a.dot_with};
+    auto ok = [&](int v) {
+        if (a.nx % v) return false;
+        for (const void* q : ptrs)
+            if (!al(q, 8 * v)) return false;
+        return true;
+    };
+    if (ok(4)) vec = 4;
+    else if (ok(2)) vec = 2;
+    // rows per tile: enough tiles to fill the machine several times over, few ghost re-reads
+    int64_t gx = (a.nx + (int64_t)kTX * vec - 1) / ((int64_t)kTX * vec);
+    int ry = 16;
+    while (ry > 2 && gx * ((a.ny + ry - 1) / ry) < (int64_t)ctx->num_sms * 16 * 4) ry >>= 1;
+    a.ry = ry;
+    int64_t gy = (a.ny + ry - 1) / ry;
+    if (gx * gy > kMaxPartials && red != RED_NONE) {  // keep the partials buffer in bounds
+        ry = (int)((a.ny * gx + kMaxPartials - 1) / kMaxPartials);
+        a.ry = ry;
+        gy = (a.ny + ry - 1) / ry;
+    }
+    if (gy > 65535) { a.ry = (int32_t)((a.ny + 65534) / 65535); gy = (a.ny + a.ry - 1) / a.ry; }
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (vec == 4) launch2d_v<OP, 4>(ctx, a, scale, red, grid);
+    else if (vec == 2) launch2d_v<OP, 2>(ctx, a, scale, red, grid);
+    else launch2d_v<OP, 1>(ctx, a, scale, red, grid);
+    ctx->launches++;
+    AK_CUDA(cudaGetLastError());
+    return AK_OK;
+}
+
+template <int OP, int VEC>
+static void launch1d_v(Ctx* ctx, const StencilArgs& a, bool scale, int red, int grid) {
+#define AK_L1D(S, R) k_stencil1d<OP, VEC, S, R><<<grid, kT1, 0, ctx->stream>>>(a)
+    if (scale) {
+        if (red == RED_DOT) AK_L1D(true, RED_DOT);
+        else AK_L1D(true, RED_NONE);
+    } else {
+        if (red == RED_DOT) AK_L1D(false, RED_DOT);
+        else if (red == RED_SUMSQ) AK_L1D(false, RED_SUMSQ);
+        else AK_L1D(false, RED_NONE);
+    }
+#undef AK_L1D
+}
+template <int OP>
+static int launch1d(Ctx* ctx, StencilArgs& a, bool scale, int red) {
+    int vec = 1;
+    const void* ptrs[] = {a.in, a.aux, a.aux_out, a.out, a.in_write, a.dot_with};
+    auto ok = [&](int v) {
+        if (a.nx % v) return false;
+        for (const void* q : ptrs)
+            if (!al(q, 8 * v)) return false;
+        return true;
+    };
+    if (ok(4)) vec = 4;
+    else if (ok(2)) vec = 2;
+    int64_t grid = (a.nx + (int64_t)kT1 * vec - 1) / ((int64_t)kT1 * vec);
+    if (grid > kMaxPartials && red != RED_NONE) {
+        set_error("1-D stencil with fused reduction: n too large for the partials buffer");
+        return AK_ERR_UNSUPPORTED;
+    }
+    if (vec == 4) launch1d_v<OP, 4>(ctx, a, scale, red, (int)grid);
+    else if (vec == 2) launch1d_v<OP, 2>(ctx, a, scale, red, (int)grid);
+    else launch1d_v<OP, 1>(ctx, a, scale, red, (int)grid);
+    ctx->launches++;
+    AK_CUDA(cudaGetLastError());
+    return AK_OK;
+}
+
+static void dg_constants(DgArgs& d, double h) {
+    const double s5 = sqrt(5.0);
+    const double a = (5.0 + 5.0 * s5) / 4.0, b = (5.0 - 5.0 * s5) / 4.0;
+    const double c = (1.0 + s5) / 4.0, dd = s5 / 2.0, e = (s5 - 1.0) / 4.0;
+    const double M[4][4] = {{-3.0, a, b, 0.5}, {-c, 0.0, dd, -e}, {e, -dd, 0.0, c}, {-0.5, -b, -a, 3.0}};
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) d.D[i][j] = M[i][j];
+    d.jac = 2.0 / h;
+    d.mw = (h / 2.0) * (1.0 / 6.0);
+}
+
+static int launch_dg(Ctx* ctx, DgArgs& d, bool residual, bool scale, int red) {
+    const int64_t grid = (d.ne + kT1 - 1) / kT1;
+    if (grid > kMaxPartials && red != RED_NONE) {
+        set_error("DG stencil with fused reduction: n too large for the partials buffer");
+        return AK_ERR_UNSUPPORTED;
+    }
+#define AK_LDG(RS, S, R) k_dg<RS, S, R><<<(int)grid, kT1, 0, ctx->stream>>>(d)
+    if (residual) {
+        if (red == RED_SUMSQ) AK_LDG(true, false, RED_SUMSQ);
+        else AK_LDG(true, false, RED_NONE);
+    } else if (scale) {
+        if (red == RED_DOT) AK_LDG(false, true, RED_DOT);
+        else AK_LDG(false, true, RED_NONE);
+    } else {
+        if (red == RED_DOT) AK_LDG(false, false, RED_DOT);
+        else AK_LDG(false, false, RED_NONE);
+    }
+#undef AK_LDG
+    ctx->launches++;
+    AK_CUDA(cudaGetLastError());
+    return AK_OK;
+}
+
+static int check_problem(const ak_problem* p) {
+    AK_REQUIRE(p != nullptr, "problem is NULL");
+    AK_REQUIRE(p->kind >= AK_SIMPLE2 && p->kind <= AK_HEAT1D_DG, "unknown problem kind");
+    if (p->kind == AK_SIMPLE2) return AK_OK;
+    AK_REQUIRE(p->nx >= 1, "nx must be >= 1");
+    const bool is2d = (p->kind == AK_BRATU2D || p->kind == AK_HEAT2D);
+    if (is2d) AK_REQUIRE(p->ny >= 1, "ny must be >= 1");
+    if (p->kind == AK_HEAT1D) AK_REQUIRE(p->nx >= 3, "heat 1-D needs >= 3 points (2 boundary points)");
+    if (p->kind == AK_HEAT1D_DG) AK_REQUIRE(p->nx % 4 == 0 && p->nx >= 8, "DG: nx must be 4 * elements, >= 2 elements");
+    const bool timedep = (p->kind == AK_HEAT1D || p->kind == AK_HEAT2D || p->kind == AK_HEAT1D_DG);
+    if (timedep) {
+        if (p->scheme != AK_EULER) {
+            set_error("scheme %d is not implemented on the device path yet (only AK_EULER)", p->scheme);
+            return AK_ERR_UNSUPPORTED;
+        }
+    } else {
+        AK_REQUIRE(p->scheme == AK_STEADY, "Bratu problems are steady (scheme must be AK_STEADY)");
+    }
+    if (p->jvp_mode != AK_JVP_ANALYTIC) {
+        set_error("jvp_mode %d is not implemented (only AK_JVP_ANALYTIC)", p->jvp_mode);
+        return AK_ERR_UNSUPPORTED;
+    }
+    return AK_OK;
+}
+
+static void base_args(Ctx* ctx, const ak_problem* p, StencilArgs& a) {
+    a = StencilArgs{};
+    a.nx = p->nx;
+    a.ny = p->ny;
+    a.wrap_x = (p->bc == AK_BC_PERIODIC);
+    a.bc = p->bc;
+    a.scheme = p->scheme;
+    a.dx2 = p->dx * p->dx;
+    a.dy2 = p->dy * p->dy;
+    a.lambda = p->lambda;
+    a.a = p->a;
+    a.dt = p->dt;
+    a.c0 = 1.0;
+    a.c1 = p->dt;
+    a.partials = ctx->partials;
+    a.ticket = ctx->ticket;
+}
+
+// ghost rows for a 2-D slab: neighbours' rows (multi-GPU), own rows (periodic on one GPU) or zeros
+static int ghost_rows(Ctx* ctx, const ak_problem* p, const double* v, const double** lo, const double** hi) {
+    if (ctx->nranks > 1) return exchange_halo_rows(ctx, v, p->nx, p->ny, p->bc, lo, hi);
+    if (p->bc == AK_BC_PERIODIC) {
+        *lo = v + (p->ny - 1) * p->nx;
+        *hi = v;
+    } else {
+        *lo = nullptr;
+        *hi = nullptr;
+    }
+    return AK_OK;
+}
+
+int launch_residual(Ctx* ctx, const ak_problem* p, double* u, double* res, double* sumsq_dev) {
+    AK_TRY(check_problem(p));
+    const int red = sumsq_dev ? RED_SUMSQ : RED_NONE;
+    if (p->kind == AK_SIMPLE2) {
+        k_simple2<<<1, 32, 0, ctx->stream>>>(u, nullptr, res, sumsq_dev, 0, nullptr, nullptr);
+        ctx->launches++;
+        AK_CUDA(cudaGetLastError());
+        return AK_OK;
+    }
+    if (p->kind == AK_HEAT1D_DG) {
+        AK_REQUIRE(p->un != nullptr, "time-dependent residual needs p->un");
+        DgArgs d{};
+        dg_constants(d, p->dx);
+        d.ne = p->nx / 4;
+        d.dt = p->dt; d.c0 = 1.0; d.c1 = p->dt;
+        d.in = u; d.un = p->un; d.out = res;
+        d.red_out = sumsq_dev; d.partials = ctx->partials; d.ticket = ctx->ticket;
+        AK_REQUIRE(al(u, 32) && al(res, 32) && al(p->un, 32), "DG vectors must be 32-byte aligned");
+        AK_TRY(launch_dg(ctx, d, true, false, red));
+        if (sumsq_dev) AK_TRY(allreduce_sum(ctx, sumsq_dev, 1));
+        return AK_OK;
+    }
+    StencilArgs a;
+    base_args(ctx, p, a);
+    a.in = u;
+    a.out = res;
+    a.red_out = sumsq_dev;
+    int rc = AK_OK;
+    switch (p->kind) {
+        case AK_BRATU1D:
+            a.aux_out = p->coef;
+            rc = launch1d<OP_RES_BRATU>(ctx, a, false, red);
+            break;
+        case AK_HEAT1D:
+            AK_REQUIRE(p->un != nullptr, "time-dependent residual needs p->un");
+            a.aux = p->un;
+            a.in_write = u;  // bc!(u) side effect
+            rc = launch1d<OP_RES_HEAT>(ctx, a, false, red);
+            break;
+        case AK_BRATU2D:
+            AK_TRY(ghost_rows(ctx, p, u, &a.lo, &a.hi));
+            a.aux_out = p->coef;
+            rc = launch2d<OP_RES_BRATU>(ctx, a, false, red);
+            break;
+        case AK_HEAT2D:
+            AK_REQUIRE(p->un != nullptr, "time-dependent residual needs p->un");
+            AK_TRY(ghost_rows(ctx, p, u, &a.lo, &a.hi));
+            a.aux = p->un;
+            rc = launch2d<OP_RES_HEAT>(ctx, a, false, red);
+            break;
+        default: break;
+    }
+    AK_TRY(rc);
+    if (sumsq_dev) AK_TRY(allreduce_sum(ctx, sumsq_dev, 1));
+    return AK_OK;
+}
+
+int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double* out, const JvpFusion* f) {
+    AK_TRY(check_problem(p));
+    JvpFusion nofuse;
+    if (!f) f = &nofuse;
+    const bool scale = f->scale_src != nullptr;
+    const int red = f->dot_with ? RED_DOT : RED_NONE;
+    if (p->kind == AK_SIMPLE2) {
+        if (scale) AK_TRY(launch_divcopy_dev(ctx, 2, v, f->scale_src, f->denom_dev, f->stop_flag));
+        k_simple2<<<1, 32, 0, ctx->stream>>>(u, v, out, f->dot_dev, 1, f->dot_with, f->stop_flag);
+        ctx->launches++;
+        AK_CUDA(cudaGetLastError());
+        return AK_OK;
+    }
+    if (p->kind == AK_HEAT1D_DG) {
+        DgArgs d{};
+        dg_constants(d, p->dx);
+        d.ne = p->nx / 4;
+        d.dt = p->dt; d.c0 = 1.0; d.c1 = p->dt;
+        d.in = scale ? f->scale_src : v;
+        d.in_write = v; d.denom = f->denom_dev;
+        d.out = out; d.dot_with = f->dot_with; d.red_out = f->dot_dev;
+        d.partials = ctx->partials; d.ticket = ctx->ticket; d.stop = f->stop_flag;
+        AK_REQUIRE(al(d.in, 32) && al(v, 32) && al(out, 32) && al(f->dot_with, 32), "DG vectors must be 32-byte aligned");
+        AK_TRY(launch_dg(ctx, d, false, scale, red));
+        if (red) AK_TRY(allreduce_sum(ctx, f->dot_dev, 1));
+        return AK_OK;
+    }
+    StencilArgs a;
+    base_args(ctx, p, a);
+    a.in = scale ? f->scale_src : v;
+    a.in_write = scale ? v : nullptr;
+    a.denom = f->denom_dev;
+    a.out = out;
+    a.dot_with = f->dot_with;
+    a.red_out = f->dot_dev;
+    a.stop = f->stop_flag;
+    int rc = AK_OK;
+    switch (p->kind) {
+        case AK_BRATU1D:
+            a.aux = p->coef ? p->coef : u;
+            a.coef_from_u = p->coef ? 0 : 1;
+            rc = launch1d<OP_JVP_BRATU>(ctx, a, scale, red);
+            break;
+        case AK_HEAT1D:
+            if (!scale) a.in_write = v;  // tangent of bc!(u): boundary entries of v are overwritten
+            rc = launch1d<OP_JVP_HEAT>(ctx, a, scale, red);
+            break;
+        case AK_BRATU2D:
+            AK_TRY(ghost_rows(ctx, p, a.in, &a.lo, &a.hi));
+            a.aux = p->coef ? p->coef : u;
+            a.coef_from_u = p->coef ? 0 : 1;
+            rc = launch2d<OP_JVP_BRATU>(ctx, a, scale, red);
+            break;
+        case AK_HEAT2D:
+            AK_TRY(ghost_rows(ctx, p, a.in, &a.lo, &a.hi));
+            rc = launch2d<OP_JVP_HEAT>(ctx, a, scale, red);
+            break;
+        default: break;
+    }
+    AK_TRY(rc);
+    if (red) AK_TRY(allreduce_sum(ctx, f->dot_dev, 1));
+    return AK_OK;
+}
+
+int launch_jvp_transpose(Ctx* ctx, const ak_problem* p, const double* u, double* v, double* out) {
+    AK_TRY(check_problem(p));
+    switch (p->kind) {
+        case AK_SIMPLE2:
+            k_simple2<<<1, 32, 0, ctx->stream>>>(u, v, out, nullptr, 2, nullptr, nullptr);
+            ctx->launches++;
+            AK_CUDA(cudaGetLastError());
+            return AK_OK;
+        case AK_BRATU1D:
+        case AK_BRATU2D:
+        case AK_HEAT2D:
+            // Laplacian (Dirichlet-0 or periodic) + diagonal: J is symmetric, J^T v == J v
+            return launch_jvp(ctx, p, u, v, out, nullptr);
+        case AK_HEAT1D:
+            if (p->bc == AK_BC_ZERO) return launch_jvp(ctx, p, u, v, out, nullptr);  // zero boundary rows/cols: symmetric
+            break;
+        default: break;
+    }
+    set_error("ak_jvp_transpose: not implemented for kind %d bc %d", p->kind, p->bc);
+    return AK_ERR_UNSUPPORTED;
+}
+
+}  // namespace ak
+
+using namespace ak;
+
+AK_API int64_t ak_problem_size(const ak_problem* p) {
+    if (!p) return 0;
+    switch (p->kind) {
+        case AK_SIMPLE2: return 2;
+        case AK_BRATU1D: case AK_HEAT1D: case AK_HEAT1D_DG: return p->nx;
+        default: return p->nx * p->ny;
+    }
+}
+
+AK_API int ak_residual(ak_ctx* ctx, const ak_problem* p, double* u, double* res, double* nrm_out_host) {
+    AK_REQUIRE(ctx && p && u && res, "ak_residual: NULL argument");
+    Ctx* c = &ctx->c;
+    AK_TRY(launch_residual(c, p, u, res, nrm_out_host ? c->dscal : nullptr));
+    if (nrm_out_host) {
+        AK_CUDA(cudaMemcpyAsync(c->hscal, c->dscal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        AK_CUDA(cudaStreamSynchronize(c->stream));
+        *nrm_out_host = sqrt(c->hscal[0]);
+    }
+    return AK_OK;
+}
+
+AK_API int ak_jvp(ak_ctx* ctx, const ak_problem* p, const double* u, double* v, double* out) {
+    AK_REQUIRE(ctx && p && v && out, "ak_jvp: NULL argument");
+    return launch_jvp(&ctx->c, p, u, v, out, nullptr);
+}
+
+AK_API int ak_jvp_transpose(ak_ctx* ctx, const ak_problem* p, const double* u, double* v, double* out) {
+    AK_REQUIRE(ctx && p && v && out, "ak_jvp_transpose: NULL argument");
+    return launch_jvp_transpose(&ctx->c, p, u, v, out);
+}

@@ -1,0 +1,821 @@
+/*
+ * nk_oracle.c — CPU restatement of the reference's JFNK hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (newtonkrylov.jl_b200/, the
+ * C-ABI library) may link, import or execute this file; only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do,
+ * and only as the checker or the timed CPU column.
+ *
+ * What it follows (paths relative to the reference tree, vchuravy/NewtonKrylov.jl):
+ *   ok_newton        src/Ariadne.jl:288-372   (Newton outer loop, Stats :265-276)
+ *   ok_forcing_ew    src/Ariadne.jl:207-216   (Eisenstat-Walker, Eq 3.5/3.6)
+ *   ok_jvp           src/Ariadne.jl:48-57     (exact forward-mode tangent of F!,
+ *                                              including the BC side effect on v)
+ *   ok_residual      examples/bratu.jl:14-24, heat_1D.jl:12-37, heat_2D.jl:15-62,
+ *                    heat_1D_DG.jl:17-36, implicit.jl:8-37, test/runtests.jl:4-7
+ *   ok_gmres / ok_cg Krylov.jl (compat 0.10.1, Project.toml:14) — NOT vendored in the
+ *                    reference tree.  Restated from the published algorithm
+ *                    (gmres.jl / cg.jl / krylov_utils.jl sym_givens); call sites
+ *                    src/Ariadne.jl:317-318,338-340,367.
+ *   ok_halo_*        examples/halovector.jl:3-45 layout
+ *   ok_implicit      examples/implicit.jl:54-78
+ *
+ * PARITY PIN STATUS
+ *   pinned by reference-owned known answers (tests/golden/runtests_known_answers.json):
+ *     J([3,5])*[1,0] == [6.0, 7.38905609893065]  and  J'*[1,0] == [6,10]
+ *     (test/runtests.jl:36-42); both 2x2 solves reach solved (test/runtests.jl:15-23);
+ *     analytic 1-D Bratu solution (examples/bratu.jl:33-37) to O(dx^2).
+ *   PARITY UNPINNED: GMRES/CG iteration counts and residual histories (Krylov.jl is
+ *     not in the tree and Julia is not installed), the DG operator entries
+ *     (SummationByPartsOperators.jl is not in the tree), everything about 2-D Bratu
+ *     (not in the reference; defined by this repo).  Those are "vs. this restatement".
+ *
+ * Arithmetic follows the Julia source's operation order (no FMA contraction:
+ * compile with -ffp-contract=off): `(y_r - 2y[i] + y_l) / dx^2`, `a * (...) / dx^2`,
+ * `un + dt*du - u`.
+ *
+ * Layout: compact nx*ny slab, x fastest, no ghost cells (see include/ariadne_b200.h).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/ariadne_b200.h"
+
+#define OK_EXPORT __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------- */
+/* helpers                                                                    */
+/* ------------------------------------------------------------------------- */
+static double* ok_alloc(int64_t n) {
+    double* p = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    if (!p) { fprintf(stderr, "oracle: out of memory (%lld doubles)\n", (long long)n); abort(); }
+    return p;
+}
+
+OK_EXPORT int ok_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+OK_EXPORT int64_t ok_problem_size(const ak_problem* p) {
+    switch (p->kind) {
+        case AK_SIMPLE2: return 2;
+        case AK_BRATU1D: case AK_HEAT1D: case AK_HEAT1D_DG: return p->nx;
+        default: return p->nx * p->ny;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* vector kernels: Krylov.k* as overloaded in examples/halovector.jl:51-147    */
+/* (interior only; on the compact slab that is simply the whole array)        */
+/* ------------------------------------------------------------------------- */
+OK_EXPORT double ok_dot(int64_t n, const double* x, const double* y) {
+    double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+    for (int64_t i = 0; i < n; ++i) s += x[i] * y[i];
+    return s;
+}
+OK_EXPORT double ok_nrm2(int64_t n, const double* x) { return sqrt(ok_dot(n, x, x)); }
+OK_EXPORT void ok_scal(int64_t n, double s, double* x) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) x[i] = s * x[i];
+}
+OK_EXPORT void ok_axpy(int64_t n, double s, const double* x, double* y) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) y[i] += s * x[i];
+}
+OK_EXPORT void ok_axpby(int64_t n, double s, const double* x, double t, double* y) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) y[i] = s * x[i] + t * y[i];
+}
+OK_EXPORT void ok_copy(int64_t n, double* y, const double* x) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) y[i] = x[i];
+}
+OK_EXPORT void ok_fill(int64_t n, double* x, double v) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) x[i] = v;
+}
+OK_EXPORT void ok_ref(int64_t n, double* x, double* y, double c, double s) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double xi = x[i], yi = y[i];
+        x[i] = c * xi + s * yi;
+        y[i] = s * xi - c * yi;
+    }
+}
+OK_EXPORT void ok_divcopy(int64_t n, double* y, const double* x, double s) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) y[i] = x[i] / s;
+}
+
+/* HaloVector bridge: padded is (nx+2)x(ny+2), first index fastest (Julia column-major
+ * OffsetArray 0:N+1 x 0:M+1, heat_2D.jl:76).  compact[j*nx+i] = padded[(j+1)*(nx+2)+(i+1)]. */
+OK_EXPORT void ok_halo_pack(double* compact, const double* padded, int64_t nx, int64_t ny) {
+    for (int64_t j = 0; j < ny; ++j)
+        for (int64_t i = 0; i < nx; ++i) compact[j * nx + i] = padded[(j + 1) * (nx + 2) + (i + 1)];
+}
+OK_EXPORT void ok_halo_unpack(double* padded, const double* compact, int64_t nx, int64_t ny, int32_t bc) {
+    int64_t px = nx + 2;
+    for (int64_t j = 0; j < ny; ++j)
+        for (int64_t i = 0; i < nx; ++i) padded[(j + 1) * px + (i + 1)] = compact[j * nx + i];
+    if (bc == AK_BC_ZERO) { /* bc_zero!: heat_2D.jl:28-38 */
+        for (int64_t i = 0; i < px; ++i) { padded[i] = 0.0; padded[(ny + 1) * px + i] = 0.0; }
+        for (int64_t j = 0; j < ny + 2; ++j) { padded[j * px] = 0.0; padded[j * px + nx + 1] = 0.0; }
+    } else { /* bc_periodic!: heat_2D.jl:15-26, in the reference's statement order */
+        /* u[0,:] = u[N,:]; u[N+1,:] = u[1,:]  (first index = x) */
+        for (int64_t j = 0; j < ny + 2; ++j) {
+            padded[j * px + 0] = padded[j * px + nx];
+            padded[j * px + nx + 1] = padded[j * px + 1];
+        }
+        /* u[:,0] = u[:,N]; u[:,N+1] = u[:,1] */
+        for (int64_t i = 0; i < px; ++i) {
+            padded[0 * px + i] = padded[ny * px + i];
+            padded[(ny + 1) * px + i] = padded[1 * px + i];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* DG / SBP operator: 4-node Legendre-Gauss-Lobatto derivative matrix          */
+/* (SummationByPartsOperators.legendre_derivative_operator, N=4; un-vendored)  */
+/* ------------------------------------------------------------------------- */
+static void dg_matrix(double D[4][4]) {
+    const double s5 = sqrt(5.0);
+    const double a = (5.0 + 5.0 * s5) / 4.0; /*  4.045084971874737 */
+    const double b = (5.0 - 5.0 * s5) / 4.0; /* -1.545084971874737 */
+    const double c = (1.0 + s5) / 4.0;       /*  0.8090169943749473 */
+    const double d = s5 / 2.0;               /*  1.118033988749895 */
+    const double e = (s5 - 1.0) / 4.0;       /*  0.3090169943749475 */
+    double M[4][4] = {{-3.0, a, b, 0.5}, {-c, 0.0, d, -e}, {e, -d, 0.0, c}, {-0.5, -b, -a, 3.0}};
+    memcpy(D, M, sizeof(M));
+}
+OK_EXPORT void ok_dg_matrix(double* D16) {
+    double D[4][4];
+    dg_matrix(D);
+    memcpy(D16, D, sizeof(D));
+}
+
+/* du1 = D1p*u ; du = D1m*du1   (heat_1D_DG.jl:32-36); periodic mesh, ne elements of width h.
+ * (D+ u)_{e,j} = (2/h) sum_m D[j][m] u_{e,m} + [j==3] (u_{e+1,0} - u_{e,3}) / ((h/2) w)
+ * (D- u)_{e,j} = (2/h) sum_m D[j][m] u_{e,m} + [j==0] (u_{e,0} - u_{e-1,3}) / ((h/2) w),  w = 1/6 */
+static void dg_apply_plus(const double* u, double* out, int64_t ne, double h) {
+    double D[4][4];
+    dg_matrix(D);
+    const double jac = 2.0 / h, mw = (h / 2.0) * (1.0 / 6.0);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < ne; ++e) {
+        const double* ue = u + 4 * e;
+        for (int j = 0; j < 4; ++j) {
+            double s = D[j][0] * ue[0];
+            s = s + D[j][1] * ue[1];
+            s = s + D[j][2] * ue[2];
+            s = s + D[j][3] * ue[3];
+            out[4 * e + j] = jac * s;
+        }
+        int64_t en = (e + 1 == ne) ? 0 : e + 1;
+        out[4 * e + 3] = out[4 * e + 3] + (u[4 * en] - ue[3]) / mw;
+    }
+}
+static void dg_apply_minus(const double* u, double* out, int64_t ne, double h) {
+    double D[4][4];
+    dg_matrix(D);
+    const double jac = 2.0 / h, mw = (h / 2.0) * (1.0 / 6.0);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < ne; ++e) {
+        const double* ue = u + 4 * e;
+        for (int j = 0; j < 4; ++j) {
+            double s = D[j][0] * ue[0];
+            s = s + D[j][1] * ue[1];
+            s = s + D[j][2] * ue[2];
+            s = s + D[j][3] * ue[3];
+            out[4 * e + j] = jac * s;
+        }
+        int64_t ep = (e == 0) ? ne - 1 : e - 1;
+        out[4 * e] = out[4 * e] + (ue[0] - u[4 * ep + 3]) / mw;
+    }
+}
+OK_EXPORT void ok_dg_plus(const double* u, double* out, int64_t ne, double h) { dg_apply_plus(u, out, ne, h); }
+OK_EXPORT void ok_dg_minus(const double* u, double* out, int64_t ne, double h) { dg_apply_minus(u, out, ne, h); }
+
+/* ------------------------------------------------------------------------- */
+/* right-hand sides f!(du, u, p, t) and their tangents                         */
+/* `tangent` = 0: du = f(u) (and the BC mutation of u);                         */
+/* `tangent` = 1: u is the tangent seed v: du = f'(.) v — all shipped f are linear
+ * except Bratu, which is handled separately.                                   */
+/* ------------------------------------------------------------------------- */
+static void rhs_heat1d(const ak_problem* p, double* du, double* u) {
+    /* heat_1D.jl:12-25 */
+    const int64_t N = p->nx;
+    const double a = p->a, dx2 = p->dx * p->dx;
+    if (p->bc == AK_BC_ZERO) { u[0] = 0.0; u[N - 1] = 0.0; }          /* bc!          :34-37 */
+    else { u[0] = u[N - 2]; u[N - 1] = u[1]; }                         /* periodic_bc! :39-42 */
+    du[0] = 0.0;
+    du[N - 1] = 0.0;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 1; i < N - 1; ++i) du[i] = a * ((u[i + 1] - 2.0 * u[i]) + u[i - 1]) / dx2;
+}
+
+static inline double at2(const ak_problem* p, const double* u, int64_t i, int64_t j) {
+    /* value of u at (i,j) with the ghost ring of bc_zero!/bc_periodic! (heat_2D.jl:15-38) */
+    const int64_t nx = p->nx, ny = p->ny;
+    if (p->bc == AK_BC_PERIODIC) {
+        if (i < 0) i += nx; else if (i >= nx) i -= nx;
+        if (j < 0) j += ny; else if (j >= ny) j -= ny;
+        return u[j * nx + i];
+    }
+    if (i < 0 || i >= nx || j < 0 || j >= ny) return 0.0;
+    return u[j * nx + i];
+}
+static void rhs_heat2d(const ak_problem* p, double* du, const double* u) {
+    /* diffusion!: heat_2D.jl:45-62 */
+    const int64_t nx = p->nx, ny = p->ny;
+    const double a = p->a, dx2 = p->dx * p->dx, dy2 = p->dy * p->dy;
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < ny; ++j)
+        for (int64_t i = 0; i < nx; ++i) {
+            double c = u[j * nx + i];
+            double xx = ((at2(p, u, i + 1, j) - 2.0 * c) + at2(p, u, i - 1, j)) / dx2;
+            double yy = ((at2(p, u, i, j + 1) - 2.0 * c) + at2(p, u, i, j - 1)) / dy2;
+            du[j * nx + i] = a * (xx + yy);
+        }
+}
+static void rhs_dg(const ak_problem* p, double* du, const double* u, double* tmp) {
+    dg_apply_plus(u, tmp, p->nx / 4, p->dx);
+    dg_apply_minus(tmp, du, p->nx / 4, p->dx);
+}
+/* linear RHS dispatcher; `u` may be mutated by boundary code (1-D heat) */
+static void rhs_linear(const ak_problem* p, double* du, double* u, double* tmp) {
+    switch (p->kind) {
+        case AK_HEAT1D: rhs_heat1d(p, du, u); break;
+        case AK_HEAT2D: rhs_heat2d(p, du, u); break;
+        case AK_HEAT1D_DG: rhs_dg(p, du, u, tmp); break;
+        default: fprintf(stderr, "oracle: rhs_linear kind %d\n", p->kind); abort();
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* residual F!(res,u,p)                                                        */
+/* ------------------------------------------------------------------------- */
+OK_EXPORT void ok_residual(const ak_problem* p, double* u, double* res) {
+    const int64_t n = ok_problem_size(p);
+    if (p->kind == AK_SIMPLE2) { /* test/runtests.jl:4-7 */
+        res[0] = u[0] * u[0] + u[1] * u[1] - 2.0;
+        res[1] = exp(u[0] - 1.0) + u[1] * u[1] - 2.0;
+        return;
+    }
+    if (p->kind == AK_BRATU1D) { /* bratu.jl:14-24 */
+        const int64_t N = p->nx;
+        const double dx2 = p->dx * p->dx, lam = p->lambda;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < N; ++i) {
+            double yl = (i == 0) ? 0.0 : u[i - 1];
+            double yr = (i == N - 1) ? 0.0 : u[i + 1];
+            double ypp = ((yr - 2.0 * u[i]) + yl) / dx2;
+            res[i] = ypp + lam * exp(u[i]);
+        }
+        return;
+    }
+    if (p->kind == AK_BRATU2D) { /* defined by this repo: SURVEY §8a A12 */
+        const int64_t nx = p->nx, ny = p->ny;
+        const double dx2 = p->dx * p->dx, dy2 = p->dy * p->dy, lam = p->lambda;
+#pragma omp parallel for schedule(static)
+        for (int64_t j = 0; j < ny; ++j)
+            for (int64_t i = 0; i < nx; ++i) {
+                double c = u[j * nx + i];
+                double xx = ((at2(p, u, i + 1, j) - 2.0 * c) + at2(p, u, i - 1, j)) / dx2;
+                double yy = ((at2(p, u, i, j + 1) - 2.0 * c) + at2(p, u, i, j - 1)) / dy2;
+                res[j * nx + i] = (xx + yy) + lam * exp(c);
+            }
+        return;
+    }
+    /* time-discretised linear RHS: implicit.jl */
+    double* du = ok_alloc(n);
+    double* tmp = ok_alloc(n);
+    const double dt = p->dt;
+    const double* un = p->un;
+    if (p->scheme == AK_EULER) { /* G_Euler!: implicit.jl:8-13 */
+        rhs_linear(p, du, u, tmp);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) res[i] = (un[i] + dt * du[i]) - u[i];
+    } else if (p->scheme == AK_MIDPOINT) { /* G_Midpoint!: implicit.jl:17-25, alpha = 0.5 */
+        const double al = 0.5;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) res[i] = al * un[i] + (1.0 - al) * u[i];
+        rhs_linear(p, du, res, tmp); /* BC mutation lands on res (the temporary), not on u */
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) res[i] = (un[i] + dt * du[i]) - u[i];
+    } else if (p->scheme == AK_TRAPEZOID) { /* G_Trapezoid!: implicit.jl:29-37 */
+        double* un_mut = ok_alloc(n); /* f!(du_n, u_n): BC mutation would land on u_n; values already satisfy it */
+        memcpy(un_mut, un, sizeof(double) * (size_t)n);
+        rhs_linear(p, res, un_mut, tmp);
+        free(un_mut);
+        rhs_linear(p, du, u, tmp);
+        const double h = dt / 2.0;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) res[i] = (un[i] + h * (res[i] + du[i])) - u[i];
+    } else {
+        fprintf(stderr, "oracle: scheme %d with kind %d\n", p->scheme, p->kind); abort();
+    }
+    free(du);
+    free(tmp);
+}
+
+/* ------------------------------------------------------------------------- */
+/* JVP: out = J(u) v, exact tangent (src/Ariadne.jl:48-57)                      */
+/* ------------------------------------------------------------------------- */
+OK_EXPORT void ok_jvp(const ak_problem* p, const double* u, double* v, double* out) {
+    const int64_t n = ok_problem_size(p);
+    if (p->kind == AK_SIMPLE2) {
+        out[0] = 2.0 * u[0] * v[0] + 2.0 * u[1] * v[1];
+        out[1] = exp(u[0] - 1.0) * v[0] + 2.0 * u[1] * v[1];
+        return;
+    }
+    if (p->kind == AK_BRATU1D) {
+        const int64_t N = p->nx;
+        const double dx2 = p->dx * p->dx, lam = p->lambda;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < N; ++i) {
+            double vl = (i == 0) ? 0.0 : v[i - 1];
+            double vr = (i == N - 1) ? 0.0 : v[i + 1];
+            double vpp = ((vr - 2.0 * v[i]) + vl) / dx2;
+            out[i] = vpp + (lam * exp(u[i])) * v[i];
+        }
+        return;
+    }
+    if (p->kind == AK_BRATU2D) {
+        const int64_t nx = p->nx, ny = p->ny;
+        const double dx2 = p->dx * p->dx, dy2 = p->dy * p->dy, lam = p->lambda;
+#pragma omp parallel for schedule(static)
+        for (int64_t j = 0; j < ny; ++j)
+            for (int64_t i = 0; i < nx; ++i) {
+                double c = v[j * nx + i];
+                double xx = ((at2(p, v, i + 1, j) - 2.0 * c) + at2(p, v, i - 1, j)) / dx2;
+                double yy = ((at2(p, v, i, j + 1) - 2.0 * c) + at2(p, v, i, j - 1)) / dy2;
+                out[j * nx + i] = (xx + yy) + (lam * exp(u[j * nx + i])) * c;
+            }
+        return;
+    }
+    double* dv = ok_alloc(n);
+    double* tmp = ok_alloc(n);
+    const double dt = p->dt;
+    if (p->scheme == AK_EULER) {
+        rhs_linear(p, dv, v, tmp); /* tangent BC applied to v in place */
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) out[i] = dt * dv[i] - v[i];
+    } else if (p->scheme == AK_MIDPOINT) {
+        const double al = 0.5;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) out[i] = (1.0 - al) * v[i];
+        rhs_linear(p, dv, out, tmp);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) out[i] = dt * dv[i] - v[i];
+    } else if (p->scheme == AK_TRAPEZOID) {
+        rhs_linear(p, dv, v, tmp);
+        const double h = dt / 2.0;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) out[i] = h * dv[i] - v[i];
+    } else {
+        fprintf(stderr, "oracle: jvp scheme %d kind %d\n", p->scheme, p->kind); abort();
+    }
+    free(dv);
+    free(tmp);
+}
+
+/* out = J(u)^T v (src/Ariadne.jl:93-107).  Dense-probe implementation for small n only
+ * (tests): column j of J is J e_j. */
+OK_EXPORT void ok_jvp_transpose_dense(const ak_problem* p, const double* u, const double* v, double* out) {
+    const int64_t n = ok_problem_size(p);
+    double* e = ok_alloc(n);
+    double* col = ok_alloc(n);
+    for (int64_t j = 0; j < n; ++j) {
+        for (int64_t i = 0; i < n; ++i) e[i] = 0.0;
+        e[j] = 1.0;
+        ok_jvp(p, u, e, col);
+        double s = 0.0;
+        for (int64_t i = 0; i < n; ++i) s += col[i] * v[i];
+        out[j] = s;
+    }
+    free(e);
+    free(col);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Krylov.jl sym_givens (krylov_utils.jl), real case                            */
+/* ------------------------------------------------------------------------- */
+static double sgn(double x) { return (x > 0.0) - (x < 0.0); }
+OK_EXPORT void ok_sym_givens(double a, double b, double* c, double* s, double* rho) {
+    if (b == 0.0) {
+        *c = (a == 0.0) ? 1.0 : sgn(a);
+        *s = 0.0;
+        *rho = fabs(a);
+    } else if (a == 0.0) {
+        *c = 0.0;
+        *s = sgn(b);
+        *rho = fabs(b);
+    } else if (fabs(b) > fabs(a)) {
+        double t = a / b;
+        *s = sgn(b) / sqrt(1.0 + t * t);
+        *c = *s * t;
+        *rho = b / *s;
+    } else {
+        double t = b / a;
+        *c = sgn(a) / sqrt(1.0 + t * t);
+        *s = *c * t;
+        *rho = a / *c;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Krylov workspace (krylov_workspace(:gmres / :cg, KrylovConstructor(res)))     */
+/* ------------------------------------------------------------------------- */
+typedef struct ok_krylov {
+    int32_t algo;
+    int64_t n;
+    int32_t mem;      /* initial memory (20) */
+    int64_t nV;       /* allocated basis vectors (grows when restart == false) */
+    double** V;
+    double *x, *w, *dx; /* dx: xr when restart */
+    double *c, *s, *z, *R;
+    int64_t cap_cs, cap_z, cap_R;
+    /* cg */
+    double *r, *pp, *Ap;
+} ok_krylov;
+
+OK_EXPORT ok_krylov* ok_krylov_create(int32_t algo, int64_t n, int32_t memory) {
+    ok_krylov* ws = (ok_krylov*)calloc(1, sizeof(ok_krylov));
+    ws->algo = algo;
+    ws->n = n;
+    ws->mem = memory;
+    ws->x = ok_alloc(n);
+    if (algo == AK_ALGO_GMRES) {
+        ws->w = ok_alloc(n);
+        ws->nV = memory;
+        ws->V = (double**)calloc((size_t)memory, sizeof(double*));
+        for (int i = 0; i < memory; ++i) ws->V[i] = ok_alloc(n);
+        ws->cap_cs = memory;
+        ws->cap_z = memory;
+        ws->cap_R = (int64_t)memory * (memory + 1) / 2;
+        ws->c = ok_alloc(ws->cap_cs);
+        ws->s = ok_alloc(ws->cap_cs);
+        ws->z = ok_alloc(ws->cap_z);
+        ws->R = ok_alloc(ws->cap_R);
+    } else {
+        ws->r = ok_alloc(n);
+        ws->pp = ok_alloc(n);
+        ws->Ap = ok_alloc(n);
+    }
+    return ws;
+}
+OK_EXPORT void ok_krylov_destroy(ok_krylov* ws) {
+    if (!ws) return;
+    for (int64_t i = 0; i < ws->nV; ++i) free(ws->V[i]);
+    free(ws->V); free(ws->x); free(ws->w); free(ws->dx);
+    free(ws->c); free(ws->s); free(ws->z); free(ws->R);
+    free(ws->r); free(ws->pp); free(ws->Ap);
+    free(ws);
+}
+OK_EXPORT double* ok_krylov_x(ok_krylov* ws) { return ws->x; }
+OK_EXPORT int64_t ok_krylov_basis_size(ok_krylov* ws) { return ws->nV; }
+
+static void grow(double** a, int64_t* cap, int64_t need) {
+    if (need <= *cap) return;
+    int64_t nc = *cap * 2;
+    if (nc < need) nc = need;
+    *a = (double*)realloc(*a, sizeof(double) * (size_t)nc);
+    if (!*a) abort();
+    for (int64_t i = *cap; i < nc; ++i) (*a)[i] = 0.0;
+    *cap = nc;
+}
+
+/* GMRES, Krylov.jl gmres! with M = N = I.  Returns stats; x in ws->x.
+ * `u` is the linearisation point of J = JacobianOperator(F!, res, u, p). */
+OK_EXPORT int ok_gmres(ok_krylov* ws, const ak_problem* p, const double* u, const double* b,
+                       const ak_krylov_opts* o, ak_krylov_stats* st, double* hist, int64_t hist_cap) {
+    const int64_t n = ws->n;
+    const int32_t mem = ws->mem;
+    const int restart = o->restart, reorth = o->reorthogonalization;
+    double* x = ws->x;
+    double* w = ws->w;
+    double* xr = x;
+    int64_t nh = 0;
+    if (restart) {
+        if (!ws->dx) ws->dx = ok_alloc(n);
+        xr = ws->dx;
+    }
+    ok_fill(n, x, 0.0);
+    ok_copy(n, w, b);          /* w <- b ; r0 === w (no left preconditioner) */
+    double* r0 = w;
+    double beta = ok_nrm2(n, r0);
+    double rNorm = beta;
+    if (hist && nh < hist_cap) hist[nh++] = beta;
+    const double eps = o->atol + o->rtol * rNorm;
+    memset(st, 0, sizeof(*st));
+    st->beta = beta;
+    st->rnorm = rNorm;
+    if (beta == 0.0) { st->niter = 0; st->solved = 1; return 0; }
+
+    int64_t itmax = o->itmax == 0 ? 2 * n : o->itmax;
+    int64_t inner_itmax = itmax;
+    int64_t iter = 0, inner_iter = 0;
+    int32_t npass = 0;
+    const double btol = pow(2.220446049250313e-16, 0.75);
+    int breakdown = 0, inconsistent = 0;
+    int solved = rNorm <= eps;
+    int tired = iter >= itmax;
+    int inner_tired;
+
+    while (!(solved || tired || breakdown)) {
+        int64_t nr = 0;
+        for (int64_t i = 0; i < mem; ++i) ok_fill(n, ws->V[i], 0.0);
+        for (int64_t i = 0; i < mem; ++i) { ws->s[i] = 0.0; ws->c[i] = 0.0; ws->z[i] = 0.0; }
+        for (int64_t i = 0; i < (int64_t)mem * (mem + 1) / 2; ++i) ws->R[i] = 0.0;
+        if (restart) {
+            ok_fill(n, xr, 0.0);
+            if (npass >= 1) {
+                /* w <- b - A x  (mul!(w, A, x); kaxpby!(n, 1, b, -1, w)) */
+                ok_jvp(p, u, x, w);
+                ok_axpby(n, 1.0, b, -1.0, w);
+            }
+        }
+        beta = ok_nrm2(n, r0);
+        ws->z[0] = beta;
+        ok_divcopy(n, ws->V[0], r0, rNorm);
+        npass += 1;
+        solved = rNorm <= eps;
+        inner_iter = 0;
+        inner_tired = 0;
+
+        while (!(solved || inner_tired || breakdown)) {
+            inner_iter += 1;
+            const int64_t k = inner_iter;
+            if (!restart && k > mem) {
+                grow(&ws->R, &ws->cap_R, nr + k + k); /* push k zeros */
+                int64_t cc = ws->cap_cs;
+                grow(&ws->s, &cc, k + 1);
+                grow(&ws->c, &ws->cap_cs, k + 1);
+            }
+            /* w <- A v_k */
+            ok_jvp(p, u, ws->V[k - 1], w);
+            double* q = w;
+            for (int64_t i = 0; i < k; ++i) { /* modified Gram-Schmidt */
+                double h = ok_dot(n, ws->V[i], q);
+                ws->R[nr + i] = h;
+                ok_axpy(n, -h, ws->V[i], q);
+            }
+            if (reorth) {
+                for (int64_t i = 0; i < k; ++i) {
+                    double ht = ok_dot(n, ws->V[i], q);
+                    ws->R[nr + i] += ht;
+                    ok_axpy(n, -ht, ws->V[i], q);
+                }
+            }
+            double Hbis = ok_nrm2(n, q);
+            for (int64_t i = 0; i + 1 < k; ++i) { /* previous reflections */
+                double Rt = ws->c[i] * ws->R[nr + i] + ws->s[i] * ws->R[nr + i + 1];
+                ws->R[nr + i + 1] = ws->s[i] * ws->R[nr + i] - ws->c[i] * ws->R[nr + i + 1];
+                ws->R[nr + i] = Rt;
+            }
+            ok_sym_givens(ws->R[nr + k - 1], Hbis, &ws->c[k - 1], &ws->s[k - 1], &ws->R[nr + k - 1]);
+            double zeta = ws->s[k - 1] * ws->z[k - 1];
+            ws->z[k - 1] = ws->c[k - 1] * ws->z[k - 1];
+            rNorm = fabs(zeta);
+            if (hist && nh < hist_cap) hist[nh++] = rNorm;
+            nr += k;
+            int mach = (rNorm + 1.0 <= 1.0);
+            int lim = rNorm <= eps;
+            breakdown = Hbis <= btol;
+            solved = lim || mach;
+            int64_t lim_it = restart ? (mem < inner_itmax ? mem : inner_itmax) : inner_itmax;
+            inner_tired = inner_iter >= lim_it;
+            if (!(solved || inner_tired || breakdown)) {
+                if (!restart && k >= mem) {
+                    if (k + 1 > ws->nV) {
+                        ws->V = (double**)realloc(ws->V, sizeof(double*) * (size_t)(k + 1));
+                        ws->V[k] = ok_alloc(n);
+                        ws->nV = k + 1;
+                    }
+                    grow(&ws->z, &ws->cap_z, k + 1);
+                }
+                ok_divcopy(n, ws->V[k], q, Hbis);
+                ws->z[k] = zeta;
+            }
+        }
+        /* back-substitution R y = z (packed column-major upper triangle) */
+        double* y = ws->z;
+        for (int64_t i = inner_iter; i >= 1; --i) {
+            int64_t pos = nr + i - inner_iter - 1; /* 0-based position of r_{i,k} */
+            for (int64_t j = inner_iter; j >= i + 1; --j) {
+                y[i - 1] = y[i - 1] - ws->R[pos] * y[j - 1];
+                pos = pos - j + 1;
+            }
+            if (fabs(ws->R[pos]) <= btol) { y[i - 1] = 0.0; inconsistent = 1; }
+            else y[i - 1] = y[i - 1] / ws->R[pos];
+        }
+        for (int64_t i = 0; i < inner_iter; ++i) ok_axpy(n, y[i], ws->V[i], xr);
+        if (restart) ok_axpy(n, 1.0, xr, x);
+        inner_itmax -= inner_iter;
+        iter += inner_iter;
+        tired = iter >= itmax;
+    }
+    st->niter = iter;
+    st->solved = solved;
+    st->inconsistent = inconsistent;
+    st->breakdown = breakdown;
+    st->npass = npass;
+    st->rnorm = rNorm;
+    return 0;
+}
+
+/* CG, Krylov.jl cg! with M = I, radius = 0, linesearch = false. */
+OK_EXPORT int ok_cg(ok_krylov* ws, const ak_problem* p, const double* u, const double* b,
+                    const ak_krylov_opts* o, ak_krylov_stats* st, double* hist, int64_t hist_cap) {
+    const int64_t n = ws->n;
+    double *x = ws->x, *r = ws->r, *pp = ws->pp, *Ap = ws->Ap;
+    int64_t nh = 0;
+    ok_fill(n, x, 0.0);
+    ok_copy(n, r, b);
+    ok_copy(n, pp, r); /* z === r, p <- z */
+    double gamma = ok_dot(n, r, r);
+    double rNorm = sqrt(gamma);
+    if (hist && nh < hist_cap) hist[nh++] = rNorm;
+    memset(st, 0, sizeof(*st));
+    st->beta = rNorm;
+    st->rnorm = rNorm;
+    if (gamma == 0.0) { st->solved = 1; return 0; }
+    int64_t itmax = o->itmax == 0 ? 2 * n : o->itmax;
+    int64_t iter = 0;
+    double pAp = 0.0, pNorm2 = gamma;
+    const double eps = o->atol + o->rtol * rNorm;
+    const double epsm = 2.220446049250313e-16;
+    int solved = rNorm <= eps, tired = iter >= itmax, zerocurv = 0, inconsistent = 0;
+    while (!(solved || tired || zerocurv)) {
+        ok_jvp(p, u, pp, Ap);
+        pAp = ok_dot(n, pp, Ap);
+        if (pAp <= epsm * pNorm2) { /* radius == 0 branch */
+            if (fabs(pAp) <= epsm * pNorm2) { zerocurv = 1; inconsistent = 1; }
+        }
+        if (zerocurv) break;
+        double alpha = gamma / pAp;
+        ok_axpy(n, alpha, pp, x);
+        ok_axpy(n, -alpha, Ap, r);
+        double gamma_next = ok_dot(n, r, r);
+        rNorm = sqrt(gamma_next);
+        if (hist && nh < hist_cap) hist[nh++] = rNorm;
+        int mach = (rNorm + 1.0 <= 1.0);
+        solved = (rNorm <= eps) || mach;
+        if (!solved) {
+            double beta = gamma_next / gamma;
+            pNorm2 = gamma_next + beta * beta * pNorm2;
+            gamma = gamma_next;
+            ok_axpby(n, 1.0, r, beta, pp);
+        }
+        iter += 1;
+        tired = iter >= itmax;
+    }
+    st->niter = iter;
+    st->solved = solved;
+    st->inconsistent = inconsistent;
+    st->rnorm = rNorm;
+    st->npass = 1;
+    return 0;
+}
+
+OK_EXPORT int ok_krylov_solve(ok_krylov* ws, const ak_problem* p, const double* u, const double* b,
+                              const ak_krylov_opts* o, ak_krylov_stats* st, double* hist, int64_t hist_cap) {
+    return ws->algo == AK_ALGO_CG ? ok_cg(ws, p, u, b, o, st, hist, hist_cap)
+                                  : ok_gmres(ws, p, u, b, o, st, hist, hist_cap);
+}
+
+OK_EXPORT void ok_krylov_default_opts(ak_krylov_opts* o) {
+    memset(o, 0, sizeof(*o));
+    o->atol = sqrt(2.220446049250313e-16);
+    o->rtol = sqrt(2.220446049250313e-16);
+}
+
+/* ------------------------------------------------------------------------- */
+/* forcing: src/Ariadne.jl:185-217                                             */
+/* ------------------------------------------------------------------------- */
+OK_EXPORT double ok_forcing_ew(double eta_max, double gamma, double eta, double tol, double n_res,
+                               double n_res_prior) {
+    double eta_res = gamma * (n_res * n_res) / (n_res_prior * n_res_prior);
+    double eta_safe;
+    if (gamma * (eta * eta) <= 0.1) eta_safe = fmin(eta_max, eta_res);
+    else eta_safe = fmin(eta_max, fmax(eta_res, gamma * (eta * eta)));
+    return fmin(eta_max, fmax(eta_safe, 0.5 * tol / n_res));
+}
+
+OK_EXPORT void ok_newton_default_opts(ak_newton_opts* o) {
+    memset(o, 0, sizeof(*o));
+    o->tol_rel = 1.0e-6;
+    o->tol_abs = 1.0e-12;
+    o->max_niter = 50;
+    o->forcing = AK_FORCING_EW;
+    o->eta = 0.1;
+    o->eta_max = 0.999;
+    o->gamma = 0.9;
+    o->algo = AK_ALGO_GMRES;
+    o->memory = 20;
+    ok_krylov_default_opts(&o->krylov);
+}
+
+/* ------------------------------------------------------------------------- */
+/* newton_krylov!: src/Ariadne.jl:288-372                                      */
+/* ------------------------------------------------------------------------- */
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static int ok_newton_ws(const ak_problem* p, double* u, double* res, const ak_newton_opts* o,
+                        ok_krylov* ws, ak_newton_stats* st, double* hist_nres, int64_t* hist_inner,
+                        double* hist_eta, int32_t hist_cap) {
+    const int64_t n = ok_problem_size(p);
+    double t0 = now_s();
+    ok_residual(p, u, res);
+    double n_res = ok_nrm2(n, res);
+    int32_t nh = 0;
+    if (hist_nres && nh < hist_cap) { hist_nres[nh] = n_res; if (hist_inner) hist_inner[nh] = 0; if (hist_eta) hist_eta[nh] = 0.0; nh++; }
+    const double tol = o->tol_rel * n_res + o->tol_abs;
+    double eta = 0.0;
+    if (o->forcing == AK_FORCING_FIXED) eta = o->eta;
+    else if (o->forcing == AK_FORCING_EW) eta = o->eta_max;
+    double* rhs = ok_alloc(n);
+    int32_t outer = 0;
+    int64_t inner = 0;
+    int32_t flags = 0;
+    while (n_res > tol && outer <= o->max_niter) {
+        ak_krylov_opts ko = o->krylov;
+        if (o->forcing != AK_FORCING_NONE && !o->krylov_rtol_override) ko.rtol = eta;
+        ok_copy(n, rhs, res); /* copy(res): mul! rewrites J.res */
+        ak_krylov_stats ks;
+        ok_krylov_solve(ws, p, u, rhs, &ko, &ks, NULL, 0);
+        const double* d = ws->x;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) u[i] -= 1.0 * d[i];
+        double n_res_prior = n_res;
+        ok_residual(p, u, res);
+        n_res = ok_nrm2(n, res);
+        double eta_used = eta;
+        if (isinf(n_res) || isnan(n_res)) { flags |= AK_FLAG_NAN; break; }
+        if (o->forcing == AK_FORCING_EW) eta = ok_forcing_ew(o->eta_max, o->gamma, eta, tol, n_res, n_res_prior);
+        outer += 1;
+        inner += ks.niter;
+        if (hist_nres && nh < hist_cap) { hist_nres[nh] = n_res; if (hist_inner) hist_inner[nh] = ks.niter; if (hist_eta) hist_eta[nh] = eta_used; nh++; }
+    }
+    free(rhs);
+    st->solved = n_res <= tol;
+    st->outer_iterations = outer;
+    st->inner_iterations = inner;
+    st->n_res = n_res;
+    st->tol = tol;
+    st->t_seconds = now_s() - t0;
+    st->flags = flags | (st->solved ? 0 : AK_FLAG_NOT_SOLVED);
+    return 0;
+}
+
+OK_EXPORT int ok_newton(const ak_problem* p, double* u, double* res, const ak_newton_opts* o,
+                        ak_newton_stats* st, double* hist_nres, int64_t* hist_inner, double* hist_eta,
+                        int32_t hist_cap) {
+    ok_krylov* ws = ok_krylov_create(o->algo, ok_problem_size(p), o->memory);
+    int rc = ok_newton_ws(p, u, res, o, ws, st, hist_nres, hist_inner, hist_eta, hist_cap);
+    ok_krylov_destroy(ws);
+    return rc;
+}
+
+/* solve(G!, f!, u_n, p, dt, ts): examples/implicit.jl:54-78; tol_abs = 6e-6 (:69).
+ * u carries over between steps (warm start); a fresh workspace per step like the reference. */
+OK_EXPORT int ok_implicit_solve(ak_problem* p, double* un, int32_t nsteps, const ak_newton_opts* o_in,
+                                int32_t* per_step_newton, int64_t* per_step_inner, int32_t* per_step_solved) {
+    const int64_t n = ok_problem_size(p);
+    ak_newton_opts o = *o_in;
+    double* u = ok_alloc(n);
+    double* res = ok_alloc(n);
+    memcpy(u, un, sizeof(double) * (size_t)n);
+    ok_fill(n, res, 0.0);
+    const double* saved = p->un;
+    p->un = un;
+    for (int32_t s = 0; s < nsteps; ++s) {
+        ak_newton_stats st;
+        ok_newton(p, u, res, &o, &st, NULL, NULL, NULL, 0);
+        if (per_step_newton) per_step_newton[s] = st.outer_iterations;
+        if (per_step_inner) per_step_inner[s] = st.inner_iterations;
+        if (per_step_solved) per_step_solved[s] = st.solved;
+        memcpy(un, u, sizeof(double) * (size_t)n);
+    }
+    p->un = saved;
+    free(u);
+    free(res);
+    return 0;
+}
