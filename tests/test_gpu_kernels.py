@@ -1,0 +1,200 @@
+"""GPU parity tests, kernel level: every call goes through the C ABI (ctypes) and is compared
+with the CPU oracle on the same seeded inputs.
+
+Tolerances: the heat / DG stencils use only +,-,*,/ in the reference's order -> bit-exact.
+Bratu involves exp(): CUDA libdevice and glibc each stay within 1 ulp of the true value, so the
+coefficient lambda*exp(u) may differ by a few ulp -> compared relative to the row scale.
+Reductions differ in summation order -> 1e-13 relative.
+"""
+import numpy as np
+import pytest
+
+from newtonkrylov_jl_b200 import _abi as A
+import problems as P
+
+pytestmark = pytest.mark.gpu
+
+RNG = np.random.default_rng(0)
+
+CASES = [
+    ("bratu1d", lambda: P.bratu1d(1000)),
+    ("bratu1d_odd", lambda: P.bratu1d(1001)),
+    ("bratu1d_tiny", lambda: P.bratu1d(3)),
+    ("bratu2d", lambda: P.bratu2d(64)),
+    ("bratu2d_rect", lambda: P.bratu2d(130, 37)),
+    ("bratu2d_odd", lambda: P.bratu2d(33, 31)),
+    ("bratu2d_wide", lambda: P.bratu2d(1024, 8)),
+    ("heat1d", lambda: P.heat1d(100)),
+    ("heat1d_periodic", lambda: P.heat1d(101, bc=A.AK_BC_PERIODIC)),
+    ("heat1d_min", lambda: P.heat1d(1)),
+    ("heat2d", lambda: P.heat2d(40)),
+    ("heat2d_periodic", lambda: P.heat2d(40, bc=A.AK_BC_PERIODIC, ic="poly")),
+    ("heat2d_odd", lambda: P.heat2d(37, ic="poly")),
+    ("dg", lambda: P.heat1d_dg(40)),
+    ("dg_unaligned_warp", lambda: P.heat1d_dg(77)),
+    ("dg_min", lambda: P.heat1d_dg(2)),
+]
+EXACT = {A.AK_HEAT1D, A.AK_HEAT2D, A.AK_HEAT1D_DG}
+
+
+@pytest.mark.parametrize("name,make", CASES, ids=[c[0] for c in CASES])
+def test_residual_matches_oracle(nk, ctx, oracle, name, make):
+    d = make()
+    u0 = d["u0"] + 0.01 * RNG.standard_normal(d["u0"].shape)
+    d = dict(d, u0=u0)
+    un_host = d["u0"] * 0.9 if d["kind"] in EXACT else None
+    F_, u, p, un = P.device_setup(nk, ctx, d)
+    if un is not None:
+        un.set(un_host)
+    res = u.zero()
+    F_(res, u, p)
+    po = P.oracle_problem(oracle, d, un=un_host)
+    ref, u_after = oracle.residual(po, u0)
+    got = res.numpy()
+    if d["kind"] in EXACT:
+        assert np.array_equal(got, ref), f"max ulp {P.ulp_diff(got, ref)}"
+    else:
+        scale = np.max(np.abs(ref))
+        assert np.max(np.abs(got - ref)) <= 4e-16 * scale * 8
+    # boundary side effect of bc!(u) (heat_1D.jl:16)
+    assert np.array_equal(u.numpy(), u_after)
+
+
+@pytest.mark.parametrize("name,make", CASES, ids=[c[0] for c in CASES])
+def test_jvp_matches_oracle(nk, ctx, oracle, name, make):
+    d = make()
+    v0 = RNG.standard_normal(d["u0"].shape)
+    F_, u, p, un = P.device_setup(nk, ctx, d)
+    res = u.zero()
+    v = nk.DeviceVector.from_numpy(v0, ctx)
+    out = u.zero()
+    J = nk.JacobianOperator(F_, res, u, p)
+    assert J.size() == (u.n, u.n) and len(J) == u.n * u.n and J.eltype() == np.float64
+    nk.mul_(out, J, v)
+    po = P.oracle_problem(oracle, d, un=d["u0"] if d["kind"] in EXACT else None)
+    ref, v_after = oracle.jvp(po, d["u0"], v0)
+    got = out.numpy()
+    if d["kind"] in EXACT:
+        assert np.array_equal(got, ref), f"max ulp {P.ulp_diff(got, ref)}"
+    else:
+        assert np.max(np.abs(got - ref)) <= 1e-15 * np.max(np.abs(ref)) * 8
+    # tangent BC: v's boundary entries are overwritten like forward mode through bc!(u) does
+    assert np.array_equal(v.numpy(), v_after)
+
+
+def test_jvp_with_cached_coefficient_equals_recomputed(nk, ctx):
+    """Bratu: JVP reading lambda*exp(u) cached by ak_residual == JVP recomputing exp(u)."""
+    for d in (P.bratu1d(513), P.bratu2d(96, 40)):
+        F_, u, p, _ = P.device_setup(nk, ctx, d)
+        res, coef = u.zero(), u.similar()
+        prob = F_.problem(u, p, coef=coef)
+        import ctypes as C
+        nk._lib.check(ctx.lib.ak_residual(ctx.h, C.byref(prob), C.c_void_p(u.ptr), C.c_void_p(res.ptr), None))
+        v = nk.DeviceVector.from_numpy(RNG.standard_normal(d["u0"].shape), ctx)
+        o1, o2 = u.zero(), u.zero()
+        nk.mul_(o1, nk.JacobianOperator(F_, res, u, p, coef=coef), v)
+        nk.mul_(o2, nk.JacobianOperator(F_, res, u, p), v)
+        assert np.array_equal(o1.numpy(), o2.numpy())
+
+
+def test_known_answer_jacobian_2x2(nk, ctx):
+    """test/runtests.jl:28-54 through the GPU path."""
+    u = nk.DeviceVector.from_numpy(np.array([3.0, 5.0]), ctx)
+    res = u.zero()
+    J = nk.JacobianOperator(nk.simple_F_, res, u, None)
+    assert J.size() == (2, 2) and len(J) == 4 and J.eltype() == np.float64
+    out = nk.DeviceVector.from_numpy(np.array([np.nan, np.nan]), ctx)
+    nk.mul_(out, J, nk.DeviceVector.from_numpy(np.array([1.0, 0.0]), ctx))
+    assert np.array_equal(out.numpy(), np.array([6.0, 7.38905609893065]))
+    nk.mul_(out, nk.transpose(J), nk.DeviceVector.from_numpy(np.array([1.0, 0.0]), ctx))
+    assert np.array_equal(out.numpy(), np.array([6.0, 10.0]))
+    Jd = nk.collect(J)
+    assert np.array_equal(Jd, np.array([[6.0, 10.0], [np.exp(2.0), 10.0]]))
+    assert np.array_equal(nk.collect(nk.transpose(J)), Jd.T)
+    v = RNG.random(2)
+    nk.mul_(out, J, nk.DeviceVector.from_numpy(v, ctx))
+    assert np.allclose(out.numpy(), Jd @ v, rtol=1e-15)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 31, 1000, 4099, 1 << 20])
+def test_vector_hooks(nk, ctx, oracle, n):
+    """Krylov.k* hooks (examples/halovector.jl:51-147) vs numpy on ragged sizes."""
+    x0, y0 = RNG.standard_normal(n), RNG.standard_normal(n)
+    x, y = nk.DeviceVector.from_numpy(x0, ctx), nk.DeviceVector.from_numpy(y0, ctx)
+    assert nk.kdot(n, x, y) == pytest.approx(float(np.dot(x0, y0)), rel=1e-12, abs=1e-12 * np.sqrt(n))
+    assert nk.knorm(n, x) == pytest.approx(float(np.linalg.norm(x0)), rel=1e-13)
+    nk.kaxpy_(n, 0.3, x, y)
+    y1 = np.array([np.float64(0.3) * a for a in x0]) + y0 if n < 10 else 0.3 * x0 + y0
+    assert np.allclose(y.numpy(), y1, rtol=1e-15, atol=1e-16)
+    y1 = y.numpy()
+    nk.kaxpby_(n, 2.0, x, -0.5, y)
+    assert np.allclose(y.numpy(), 2.0 * x0 - 0.5 * y1, rtol=1e-15, atol=1e-16)
+    nk.kscal_(n, 3.0, x)
+    assert np.array_equal(x.numpy(), 3.0 * x0)
+    nk.kcopy_(n, y, x)
+    assert np.array_equal(y.numpy(), x.numpy())
+    nk.kfill_(y, 1.25)
+    assert np.array_equal(y.numpy(), np.full(n, 1.25))
+    nk.kdivcopy_(n, y, x, 7.0)
+    assert np.array_equal(y.numpy(), (3.0 * x0) / 7.0)
+    xa, ya = x.numpy(), y.numpy()
+    c, s = 0.6, 0.8
+    nk.kref_(n, x, y, c, s)
+    assert np.allclose(x.numpy(), c * xa + s * ya, rtol=1e-15, atol=1e-16)
+    assert np.allclose(y.numpy(), s * xa - c * ya, rtol=1e-15, atol=1e-16)
+
+
+def test_vector_hooks_unaligned_views(nk, ctx):
+    """Operands that are not 32-byte aligned take the scalar path and give the same numbers."""
+    n = 1003
+    base = nk.DeviceVector.from_numpy(RNG.standard_normal(2 * n + 8), ctx)
+    h = base.numpy()
+    x = nk.DeviceVector(ctx, (n,), ptr=base.ptr + 8, owner=base)
+    y = nk.DeviceVector(ctx, (n,), ptr=base.ptr + 8 * (n + 3), owner=base)
+    x0, y0 = h[1:1 + n], h[n + 3:2 * n + 3]
+    assert nk.kdot(n, x, y) == pytest.approx(float(np.dot(x0, y0)), rel=1e-12)
+    nk.kaxpy_(n, -1.5, x, y)
+    assert np.allclose(y.numpy(), y0 - 1.5 * x0, rtol=1e-15, atol=1e-16)
+
+
+def test_halovector_layout_bridge(nk, ctx, oracle):
+    """examples/halovector.jl:3-45 / heat_2D.jl:76-91: padded OffsetArray <-> compact slab."""
+    nx, ny = 12, 9
+    padded = RNG.standard_normal((nx + 2, ny + 2))  # Julia index order [i, j]
+    hv = nk.HaloVector.from_padded(padded, ctx)
+    assert len(hv) == nx * ny  # logical length = interior only (halovector.jl:17-21)
+    assert np.array_equal(hv.numpy(), padded[1:-1, 1:-1].T)
+    z = hv.padded(A.AK_BC_ZERO)
+    assert np.array_equal(z[1:-1, 1:-1], padded[1:-1, 1:-1])
+    assert np.all(z[0, :] == 0) and np.all(z[-1, :] == 0) and np.all(z[:, 0] == 0) and np.all(z[:, -1] == 0)
+    per = hv.padded(A.AK_BC_PERIODIC)
+    ref = np.zeros((ny + 2, nx + 2))
+    import ctypes as C
+    comp = np.ascontiguousarray(padded[1:-1, 1:-1].T)
+    oracle.load().ok_halo_unpack(ref.ctypes.data_as(A.c_double_p), comp.ctypes.data_as(A.c_double_p), nx, ny, A.AK_BC_PERIODIC)
+    assert np.array_equal(per, ref.T)
+
+
+def test_linearity_and_symmetry_large(nk, ctx):
+    """Size-independent properties at a size the oracle is not asked to match (2048^2):
+    J(u)(a v + b w) == a J v + b J w to rounding, and <w, J v> == <v, J w> (symmetric J)."""
+    d = P.bratu2d(2048)
+    F_, u, p, _ = P.device_setup(nk, ctx, d)
+    res = u.zero()
+    J = nk.JacobianOperator(F_, res, u, p)
+    n = u.n
+    v = nk.DeviceVector.from_numpy(RNG.standard_normal(d["u0"].shape), ctx)
+    w = nk.DeviceVector.from_numpy(RNG.standard_normal(d["u0"].shape), ctx)
+    Jv, Jw, comb, Jc = u.zero(), u.zero(), u.zero(), u.zero()
+    nk.mul_(Jv, J, v)
+    nk.mul_(Jw, J, w)
+    nk.kcopy_(n, comb, w)
+    nk.kaxpby_(n, 2.0, v, -3.0, comb)  # comb = 2v - 3w
+    nk.mul_(Jc, J, comb)
+    nk.kaxpby_(n, 2.0, Jv, -3.0, Jw)   # Jw <- 2 Jv - 3 Jw
+    nk.kaxpy_(n, -1.0, Jw, Jc)
+    assert nk.knorm(n, Jc) <= 1e-12 * nk.knorm(n, Jw)
+    nk.mul_(Jv, J, v)
+    nk.mul_(Jw, J, w)
+    a, b = nk.kdot(n, w, Jv), nk.kdot(n, v, Jw)
+    assert a == pytest.approx(b, rel=1e-11)

@@ -1,0 +1,262 @@
+"""GPU parity tests, solver level (through the C ABI): GMRES / CG / Newton / implicit stepping
+against the CPU oracle.  Tolerances are the ones BASELINE.json's north_star states:
+same Newton iteration count, per-iteration ||F|| within 1e-10 relative, final u within 1e-8
+relative; in addition the GMRES iteration count of every Newton step must agree.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from newtonkrylov_jl_b200 import _abi as A
+import problems as P
+
+pytestmark = pytest.mark.gpu
+RNG = np.random.default_rng(1)
+
+TOL_NRES = 1e-10
+TOL_U = 1e-8
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.ravel(a) - np.ravel(b)) / max(np.linalg.norm(np.ravel(b)), 1e-300))
+
+
+def device_krylov(nk, ctx, d, b0, algo="gmres", memory=20, **kw):
+    F_, u, p, _ = P.device_setup(nk, ctx, d)
+    res = u.zero()
+    J = nk.JacobianOperator(F_, res, u, p)
+    b = nk.DeviceVector.from_numpy(b0, ctx)
+    ws = nk.krylov_workspace(algo, nk.KrylovConstructor(res), memory=memory)
+    nk.krylov_solve_(ws, J, b, history=True, **kw)
+    return ws.x.numpy(), ws.stats
+
+
+LIN_CASES = [
+    ("bratu1d", lambda: P.bratu1d(200), dict(rtol=1e-8)),
+    ("bratu2d", lambda: P.bratu2d(24), dict(rtol=1e-8)),
+    ("heat1d", lambda: P.heat1d(100), dict(rtol=1e-8)),
+    ("heat2d", lambda: P.heat2d(24, dt_scale=64.0, ic="poly"), dict(rtol=1e-10)),
+    ("dg", lambda: P.heat1d_dg(16, dt=1e-3), dict(rtol=1e-8)),
+]
+
+
+@pytest.mark.parametrize("fuse", ["none", "mgs", "full"])
+@pytest.mark.parametrize("name,make,kw", LIN_CASES, ids=[c[0] for c in LIN_CASES])
+def test_gmres_matches_oracle(nk, ctx, oracle, name, make, kw, fuse):
+    d = make()
+    b0 = RNG.standard_normal(d["u0"].shape)
+    if d["kind"] == A.AK_HEAT1D:
+        b0[0] = b0[-1] = 0.0  # consistent with the zero boundary rows of J (heat_1D.jl:57-89)
+    x, st = device_krylov(nk, ctx, d, b0, fuse=fuse, **kw)
+    po = P.oracle_problem(oracle, d, un=d["u0"] if d.get("scheme") else None)
+    xr, sr, hr = oracle.krylov_solve(po, d["u0"], b0, hist_cap=100000, **kw)
+    assert st.niter == sr["niter"] and st.solved == sr["solved"] and st.npass == sr["npass"]
+    assert rel(x, xr) < 1e-9
+    h = np.array(st.residuals)
+    assert len(h) == len(hr)
+    # recurrence residual norms agree relative to ||b|| (they differ by rounding of the dots only)
+    assert np.max(np.abs(h - hr)) <= 1e-10 * hr[0]
+
+
+@pytest.mark.parametrize("fuse", ["none", "mgs", "full"])
+@pytest.mark.parametrize("opts", [dict(restart=True, itmax=45), dict(restart=True, reorthogonalization=True, itmax=33),
+                                  dict(reorthogonalization=True), dict(itmax=7), dict(restart=True)],
+                         ids=["restart45", "restart_reorth33", "reorth", "itmax7", "restart_conv"])
+def test_gmres_options(nk, ctx, oracle, opts, fuse):
+    """restart / reorthogonalization / itmax semantics of Krylov.jl's gmres! (memory = 5)."""
+    d = P.bratu2d(20)
+    b0 = RNG.standard_normal(d["u0"].shape)
+    x, st = device_krylov(nk, ctx, d, b0, memory=5, rtol=1e-9, fuse=fuse, **opts)
+    po = P.oracle_problem(oracle, d)
+    xr, sr, hr = oracle.krylov_solve(po, d["u0"], b0, memory=5, hist_cap=100000, rtol=1e-9, **opts)
+    assert (st.niter, st.solved, st.npass) == (sr["niter"], sr["solved"], sr["npass"])
+    assert rel(x, xr) < 1e-8
+    assert np.max(np.abs(np.array(st.residuals) - hr)) <= 1e-9 * hr[0]
+
+
+def test_gmres_zero_rhs_and_basis_growth(nk, ctx, oracle):
+    d = P.bratu1d(300)
+    x, st = device_krylov(nk, ctx, d, np.zeros(300))
+    assert st.niter == 0 and st.solved and np.all(x == 0)  # "x is a zero-residual solution"
+    # non-restarted GMRES grows the basis past memory = 20 (Krylov.jl pushes new vectors)
+    b0 = RNG.standard_normal(300)
+    x, st = device_krylov(nk, ctx, d, b0, rtol=1e-10)
+    po = P.oracle_problem(oracle, d)
+    xr, sr, hr = oracle.krylov_solve(po, d["u0"], b0, rtol=1e-10, hist_cap=1000)
+    assert st.niter == sr["niter"] > 20 and sr["basis"] > 20
+    assert rel(x, xr) < 1e-8
+
+
+@pytest.mark.parametrize("name,make", [("bratu1d", lambda: P.bratu1d(300, lam=1.0)), ("bratu2d", lambda: P.bratu2d(24, lam=1.0))],
+                         ids=["bratu1d", "bratu2d"])
+def test_cg_matches_oracle(nk, ctx, oracle, name, make):
+    """algo = :cg (every solve in examples/bratu.jl:59-108).  J is symmetric negative definite
+    for small lambda; CG is applied to it exactly as the reference does."""
+    d = make()
+    b0 = RNG.standard_normal(d["u0"].shape)
+    x, st = device_krylov(nk, ctx, d, b0, algo="cg", rtol=1e-8)
+    po = P.oracle_problem(oracle, d)
+    xr, sr, hr = oracle.krylov_solve(po, d["u0"], b0, algo=A.AK_ALGO_CG, rtol=1e-8, hist_cap=100000)
+    assert (st.niter, st.solved) == (sr["niter"], sr["solved"])
+    assert rel(x, xr) < 1e-8
+    h = np.array(st.residuals)
+    assert len(h) == len(hr) and np.max(np.abs(h - hr)) <= 1e-9 * hr[0]
+
+
+def newton_both(nk, ctx, oracle, d, native, **kw):
+    F_, u, p, _ = P.device_setup(nk, ctx, d)
+    hist = []
+    fn = nk.newton_krylov_native_ if native else nk.newton_krylov_
+    _, r = fn(F_, u, p, None, history=hist, **kw)
+    po = P.oracle_problem(oracle, d, un=d["u0"] if d.get("scheme") else None)
+    kk = dict(kw.get("krylov_kwargs") or {})
+    kk.pop("fuse", None)
+    o = nk.host._newton_opts(kw.get("tol_rel", 1e-6), kw.get("tol_abs", 1e-12), kw.get("max_niter", 50),
+                             kw.get("forcing", nk.EisenstatWalker()), kw.get("algo", "gmres"), 20, 0, kk)
+    ur, sr, hr = oracle.newton(po, d["u0"], o, hist_cap=64)
+    return u.numpy(), r, hist, ur, sr, hr
+
+
+def assert_newton_parity(u, r, hist, ur, sr, hr):
+    assert r.solved == sr["solved"]
+    assert r.stats.outer_iterations == sr["outer_iterations"]
+    assert [h["inner"] for h in hist] == [h["inner"] for h in hr]
+    n0 = hr[0]["n_res"]
+    for a, b in zip(hist, hr):
+        # 1e-10 relative, down to the noise floor of the norm reduction (~1e-13 ||F_0||)
+        assert abs(a["n_res"] - b["n_res"]) <= TOL_NRES * b["n_res"] + 1e-13 * n0
+    assert rel(u, ur) < TOL_U
+
+
+@pytest.mark.parametrize("native", [False, True], ids=["host_loop", "c_loop"])
+@pytest.mark.parametrize("x0", [[2.0, 0.5], [3.0, 5.0]])
+def test_newton_2x2_reference_tests(nk, ctx, oracle, x0, native):
+    """test/runtests.jl:15-23: both solves reach solved == true with default options."""
+    d = dict(kind=A.AK_SIMPLE2, nx=2, ny=1, u0=np.array(x0))
+    u = nk.DeviceVector.from_numpy(d["u0"], ctx)
+    hist = []
+    fn = nk.newton_krylov_native_ if native else nk.newton_krylov_
+    _, r = fn(nk.simple_F_, u, None, None, history=hist)
+    assert r.solved
+    po = oracle.make_problem(A.AK_SIMPLE2, 2)
+    ur, sr, hr = oracle.newton(po, d["u0"])
+    assert_newton_parity(u.numpy(), r, hist, ur, sr, hr)
+
+
+NEWTON_CASES = [
+    ("bratu1d_200", lambda: P.bratu1d(200), {}),
+    ("bratu1d_1000", lambda: P.bratu1d(1000), {}),
+    ("bratu2d_32", lambda: P.bratu2d(32), {}),
+    ("bratu2d_64_fixed", lambda: P.bratu2d(64), dict(forcing="fixed")),
+    ("bratu2d_48x20_noforcing", lambda: P.bratu2d(48, 20), dict(forcing=None)),
+    ("bratu2d_64_restart", lambda: P.bratu2d(64), dict(krylov_kwargs=dict(restart=True, itmax=400))),
+    ("bratu1d_cg", lambda: P.bratu1d(400, lam=1.0), dict(algo="cg")),
+]
+
+
+@pytest.mark.parametrize("native", [False, True], ids=["host_loop", "c_loop"])
+@pytest.mark.parametrize("name,make,kw", NEWTON_CASES, ids=[c[0] for c in NEWTON_CASES])
+def test_newton_matches_oracle(nk, ctx, oracle, name, make, kw, native):
+    kw = dict(kw)
+    if kw.get("forcing") == "fixed":
+        kw["forcing"] = nk.Fixed(0.1)
+    u, r, hist, ur, sr, hr = newton_both(nk, ctx, oracle, make(), native, **kw)
+    assert r.solved
+    assert_newton_parity(u, r, hist, ur, sr, hr)
+
+
+@pytest.mark.parametrize("fuse", ["none", "full"])
+def test_newton_fusion_levels_agree(nk, ctx, oracle, fuse):
+    d = P.bratu2d(40)
+    u, r, hist, ur, sr, hr = newton_both(nk, ctx, oracle, d, True, krylov_kwargs=dict(fuse=fuse))
+    assert_newton_parity(u, r, hist, ur, sr, hr)
+
+
+def test_newton_gives_up_after_max_niter_plus_one(nk, ctx, oracle):
+    """`while n_res > tol && outer_iterations <= max_niter` admits max_niter + 1 steps (src/Ariadne.jl:321)."""
+    d = P.bratu1d(64)
+    u, r, hist, ur, sr, hr = newton_both(nk, ctx, oracle, d, True, max_niter=2, tol_rel=1e-14,
+                                         krylov_kwargs=dict(itmax=1))
+    assert not r.solved and r.stats.outer_iterations == 3 == sr["outer_iterations"]
+
+
+def test_bratu1d_analytic_solution(nk, ctx):
+    """examples/bratu.jl:33-37: converged u == analytic solution to O(dx^2) (lambda = 3.51382 is too close
+    to the fold for plain GMRES, the example says so itself; use the lower-branch solution at lambda = 1)."""
+    from scipy.optimize import brentq
+    lam, N = 1.0, 400
+    theta = brentq(lambda t: t - np.sqrt(2 * lam) * np.cosh(t / 4), 0.1, 3.0)
+    d = P.bratu1d(N, lam=lam)
+    F_, u, p, _ = P.device_setup(nk, ctx, d)
+    nk.kfill_(u, 0.0)
+    _, r = nk.newton_krylov_(F_, u, p, None, tol_rel=1e-10)
+    assert r.solved
+    exact = -2.0 * np.log(np.cosh(theta * (d["x"] - 0.5) / 2) / np.cosh(theta / 4))
+    assert np.max(np.abs(u.numpy() - exact)) < 5e-6
+
+
+IMPLICIT_CASES = [
+    ("heat1d", lambda: P.heat1d(100), 3, {}),
+    ("heat2d_reference_ic", lambda: P.heat2d(40), 3, dict(reorthogonalization=True)),
+    ("heat2d_poly_stiff", lambda: P.heat2d(32, dt_scale=64.0, ic="poly"), 3, dict(reorthogonalization=True)),
+    ("heat2d_periodic", lambda: P.heat2d(24, dt_scale=16.0, bc=A.AK_BC_PERIODIC, ic="poly"), 2, {}),
+    ("dg", lambda: P.heat1d_dg(40, dt=0.01), 2, {}),
+]
+
+
+@pytest.mark.parametrize("name,make,nsteps,kk", IMPLICIT_CASES, ids=[c[0] for c in IMPLICIT_CASES])
+def test_implicit_time_stepping_matches_oracle(nk, ctx, oracle, name, make, nsteps, kk):
+    """solve(G_Euler!, f!, u_n, p, dt, ts) — examples/implicit.jl:54-78 (tol_abs = 6e-6)."""
+    d = make()
+    po = P.oracle_problem(oracle, d, un=d["u0"])
+    o = nk.host._newton_opts(1e-6, 6e-6, 50, nk.EisenstatWalker(), "gmres", 20, 0, kk)
+    ur, newt_r, inner_r, solved_r = oracle.implicit_solve(po, d["u0"], nsteps, o)
+    # (a) host-language time loop (mirror of implicit.jl)
+    F_, u, p, un = P.device_setup(nk, ctx, d)
+    stats = []
+    ts = [i * d["dt"] for i in range(nsteps + 1)]
+    nk.solve(nk.G_Euler_, F_.f_, un, p[3], d["dt"], ts, krylov_kwargs=kk, step_stats=stats)
+    assert [s.stats.outer_iterations for s in stats] == list(newt_r)
+    assert [s.stats.inner_iterations for s in stats] == list(inner_r)
+    assert [s.solved for s in stats] == [bool(s) for s in solved_r]
+    assert rel(un.numpy(), ur) < TOL_U
+    # (b) the single C entry point ak_implicit_solve
+    F_, u, p, un = P.device_setup(nk, ctx, d)
+    prob = F_.problem(u, p)
+    newt = np.zeros(nsteps, dtype=np.int32)
+    inner = np.zeros(nsteps, dtype=np.int64)
+    solved = np.zeros(nsteps, dtype=np.int32)
+    nk._lib.check(ctx.lib.ak_implicit_solve(ctx.h, C.byref(prob), C.c_void_p(un.ptr), nsteps, C.byref(o),
+                                            newt.ctypes.data_as(A.c_int32_p), inner.ctypes.data_as(A.c_int64_p),
+                                            solved.ctypes.data_as(A.c_int32_p)))
+    assert list(newt) == list(newt_r) and list(inner) == list(inner_r) and list(solved) == list(solved_r)
+    assert rel(un.numpy(), ur) < TOL_U
+
+
+def test_newton_host_buffers_entry_point(nk, ctx, oracle):
+    """ak_newton_solve_host: u in host memory (what a Julia Array caller passes)."""
+    d = P.bratu2d(48)
+    prob = nk.bratu2d_.problem(nk.DeviceVector(ctx, d["u0"].shape), (d["dx"], d["dy"], d["lam"]))
+    u = np.ascontiguousarray(d["u0"]).copy()
+    o = A.default_newton_opts()
+    st = A.ak_newton_stats()
+    hn, hi = np.zeros(64), np.zeros(64, dtype=np.int64)
+    nk._lib.check(ctx.lib.ak_newton_solve_host(ctx.h, C.byref(prob), u.ctypes.data_as(C.c_void_p), None, C.byref(o),
+                                               C.byref(st), hn.ctypes.data_as(A.c_double_p),
+                                               hi.ctypes.data_as(A.c_int64_p), 64))
+    po = P.oracle_problem(oracle, d)
+    ur, sr, hr = oracle.newton(po, d["u0"])
+    assert st.solved and st.outer_iterations == sr["outer_iterations"] and st.inner_iterations == sr["inner_iterations"]
+    assert rel(u, ur) < TOL_U
+
+
+def test_errors_are_loud(nk, ctx):
+    u = nk.DeviceVector.from_numpy(np.zeros(8), ctx)
+    with pytest.raises(nk.AriadneError):  # DG needs >= 2 elements of 4 nodes
+        nk.ImplicitResidual(nk.G_Euler_, nk.heat_1D_DG_)(u.zero(), nk.DeviceVector.from_numpy(np.zeros(6), ctx),
+                                                        (u, 0.1, u.zero(), (0.5,), 0.0))
+    with pytest.raises(nk.AriadneError):  # midpoint is not on the device path yet: fails, never falls back
+        nk.ImplicitResidual(nk.G_Midpoint_, nk.heat_1D_)(u.zero(), u, (u, 0.1, u.zero(), (0.2, 0.1, nk.bc_zero_), 0.0))
+    with pytest.raises(TypeError):
+        nk.JacobianOperator(lambda res, u, p: None, u, u, None)
