@@ -79,10 +79,28 @@ OK_EXPORT int64_t ok_problem_size(const ak_problem* p) {
 /* vector kernels: Krylov.k* as overloaded in examples/halovector.jl:51-147    */
 /* (interior only; on the compact slab that is simply the whole array)        */
 /* ------------------------------------------------------------------------- */
+/* Deterministic for any thread count: fixed 4096-element chunks are summed left to right,
+ * chunk sums are then added in chunk order (an OpenMP `reduction` combines thread partials in
+ * an unspecified order, which is enough to flip a GMRES iteration count at a knife edge). */
+#define OK_CHUNK 4096
 OK_EXPORT double ok_dot(int64_t n, const double* x, const double* y) {
+    const int64_t nchunk = (n + OK_CHUNK - 1) / OK_CHUNK;
+    if (nchunk <= 1) {
+        double s = 0.0;
+        for (int64_t i = 0; i < n; ++i) s += x[i] * y[i];
+        return s;
+    }
+    double* part = ok_alloc(nchunk);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < nchunk; ++c) {
+        const int64_t lo = c * OK_CHUNK, hi = (lo + OK_CHUNK < n) ? lo + OK_CHUNK : n;
+        double s = 0.0;
+        for (int64_t i = lo; i < hi; ++i) s += x[i] * y[i];
+        part[c] = s;
+    }
     double s = 0.0;
-#pragma omp parallel for reduction(+ : s) schedule(static)
-    for (int64_t i = 0; i < n; ++i) s += x[i] * y[i];
+    for (int64_t c = 0; c < nchunk; ++c) s += part[c];
+    free(part);
     return s;
 }
 OK_EXPORT double ok_nrm2(int64_t n, const double* x) { return sqrt(ok_dot(n, x, x)); }

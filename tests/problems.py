@@ -85,3 +85,21 @@ def ulp_diff(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     sp = np.spacing(np.maximum(np.abs(a), np.abs(b)))
     return float(np.max(np.abs(a - b) / sp)) if a.size else 0.0
+
+
+def generic(d):
+    """Same problem with a non-symmetric smooth perturbation of the initial guess.  The reference's
+    own IC (sin(pi x), sin(pi x) sin(pi y)) is an even function on a symmetric grid: the Krylov spaces
+    it generates are rank-deficient in exact arithmetic and late GMRES iterations are driven by
+    rounding noise, so histories are reproducible only to ~1e-2 there (measured on the oracle itself,
+    see tests/test_gpu_solvers.py::oracle_sensitivity)."""
+    d = dict(d)
+    if d["kind"] == A.AK_BRATU1D:
+        x = d["x"]
+        d["u0"] = d["u0"] + 1.2 * x * (1 - x) ** 2 * np.exp(x)
+    else:
+        nx, ny = d["nx"], d["ny"]
+        X = (d["dx"] * np.arange(1, nx + 1))[None, :]
+        Y = (d["dy"] * np.arange(1, ny + 1))[:, None]
+        d["u0"] = d["u0"] + 2.4 * X * (1 - X) ** 2 * Y**2 * (1 - Y) * np.exp(X + 0.5 * Y)
+    return d

@@ -1,0 +1,272 @@
+"""CPU tests of the oracle (oracle/nk_oracle.c): pinned to the reference's known answers
+(tests/golden/runtests_known_answers.json, transcribed from test/runtests.jl and the examples)
+and to mathematical properties of the restated algorithms."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from newtonkrylov_jl_b200 import _abi as A
+import problems as P
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "runtests_known_answers.json")))
+RNG = np.random.default_rng(7)
+
+
+def test_known_answer_jacobian(oracle):
+    g = GOLD["jacobian_2x2"]
+    p = oracle.make_problem(A.AK_SIMPLE2, 2)
+    out, _ = oracle.jvp(p, np.array(g["u"]), np.array(g["v"]))
+    assert list(out) == g["J_times_v"]  # exact ==, test/runtests.jl:36-38
+    outT = oracle.jvp_transpose_dense(p, np.array(g["u"]), np.array(g["v"]))
+    assert list(outT) == g["Jt_times_v"]  # test/runtests.jl:40-42
+    J = oracle.dense_jacobian(p, np.array(g["u"]))
+    assert J.shape == tuple(g["size"]) and J.size == g["length"]
+    v = RNG.random(2)
+    assert np.allclose(oracle.jvp(p, np.array(g["u"]), v)[0], J @ v, rtol=1e-15)  # :48-52
+
+
+def test_newton_2x2_solved(oracle):
+    p = oracle.make_problem(A.AK_SIMPLE2, 2)
+    pred = GOLD["survey_probe_predictions"]
+    for case, key in zip(GOLD["newton_2x2"]["cases"], ["newton_2x2_[2,0.5]", "newton_2x2_[3,5]"]):
+        u, st, hist = oracle.newton(p, np.array(case["x0"]))
+        assert st["solved"] == case["solved"]  # test/runtests.jl:15-23
+        assert st["outer_iterations"] == pred[key]["outer"]
+        assert [h["inner"] for h in hist[1:]] == pred[key]["inner"]
+    assert np.allclose(u, pred["newton_2x2_[3,5]"]["u"], atol=1e-5)
+
+
+def test_newton_defaults_match_reference(oracle):
+    g = GOLD["newton_defaults"]
+    o = A.default_newton_opts()
+    assert (o.tol_rel, o.tol_abs, o.max_niter, o.eta_max, o.gamma, o.eta) == (
+        g["tol_rel"], g["tol_abs"], g["max_niter"], g["eta_max"], g["gamma"], g["fixed_eta"])
+    assert o.krylov.atol == o.krylov.rtol == np.sqrt(np.finfo(float).eps)
+    assert o.memory == 20 and o.krylov.restart == 0 and o.krylov.itmax == 0
+
+
+def test_forcing_eisenstat_walker(oracle):
+    """src/Ariadne.jl:207-216 restated in pure Python vs the oracle."""
+    def ew(eta_max, g, eta, tol, nr, nrp):
+        eta_res = g * nr**2 / nrp**2
+        if g * eta**2 <= 1 / 10:
+            safe = min(eta_max, eta_res)
+        else:
+            safe = min(eta_max, max(eta_res, g * eta**2))
+        return min(eta_max, max(safe, 1 / 2 * tol / nr))
+    for _ in range(200):
+        eta, tol, nr, nrp = RNG.random(), 10 ** RNG.uniform(-12, -3), 10 ** RNG.uniform(-8, 2), 10 ** RNG.uniform(-8, 2)
+        assert oracle.forcing_ew(0.999, 0.9, eta, tol, nr, nrp) == pytest.approx(ew(0.999, 0.9, eta, tol, nr, nrp), rel=1e-15)
+    assert oracle.forcing_ew(0.999, 0.9, 0.999, 1e-9, 1.0, 1.0) == pytest.approx(0.9)
+
+
+def test_sym_givens(oracle):
+    """Krylov.jl sym_givens: [c s; s -c] [a; b] = [rho; 0], c^2 + s^2 = 1, plus the special cases."""
+    assert oracle.sym_givens(0.0, 0.0) == (1.0, 0.0, 0.0)
+    assert oracle.sym_givens(-2.0, 0.0) == (-1.0, 0.0, 2.0)
+    assert oracle.sym_givens(0.0, -3.0) == (0.0, -1.0, 3.0)
+    for _ in range(100):
+        a, b = RNG.standard_normal(2) * 10 ** RNG.uniform(-5, 5)
+        c, s, rho = oracle.sym_givens(a, b)
+        assert c * c + s * s == pytest.approx(1.0, rel=1e-14)
+        assert c * a + s * b == pytest.approx(rho, rel=1e-13)
+        assert abs(s * a - c * b) <= 1e-13 * abs(rho)
+
+
+@pytest.mark.parametrize("make", [lambda: P.bratu1d(50), lambda: P.bratu2d(9, 7), lambda: P.heat2d(8, dt_scale=32.0, ic="poly"),
+                                  lambda: P.heat1d_dg(6, dt=1e-3)], ids=["bratu1d", "bratu2d", "heat2d", "dg"])
+def test_gmres_iterates_are_minimum_residual(oracle, make):
+    """Property pin of the GMRES restatement: after k iterations x_k minimises ||b - J x|| over the
+    Krylov space K_k(J, b), and the recurrence residual equals the true residual."""
+    d = make()
+    po = P.oracle_problem(oracle, d, un=d["u0"] if d.get("scheme") else None)
+    Jd = oracle.dense_jacobian(po, d["u0"])
+    n = Jd.shape[0]
+    b = RNG.standard_normal(n)
+    for k in (1, 3, 7):
+        x, st, hist = oracle.krylov_solve(po, d["u0"], b.reshape(d["u0"].shape), itmax=k, rtol=0.0, atol=0.0, hist_cap=64)
+        assert st["niter"] == k
+        K = np.stack([np.linalg.matrix_power(Jd, i) @ b for i in range(k)], axis=1)
+        Q, _ = np.linalg.qr(K)
+        y, *_ = np.linalg.lstsq(Jd @ Q, b, rcond=None)
+        xm = Q @ y
+        r_true = np.linalg.norm(b - Jd @ x.reshape(-1))
+        assert r_true == pytest.approx(np.linalg.norm(b - Jd @ xm), rel=1e-8)
+        assert hist[-1] == pytest.approx(r_true, rel=1e-8)
+    # restart + reorthogonalization: the residual norm GMRES claims is the true one, pass after pass
+    x, st, hist = oracle.krylov_solve(po, d["u0"], b.reshape(d["u0"].shape), restart=True, reorthogonalization=True,
+                                      memory=5, rtol=1e-10, atol=0.0, itmax=60, hist_cap=10000)
+    assert st["niter"] <= 60 and st["npass"] == -(-st["niter"] // 5)
+    assert np.linalg.norm(b - Jd @ x.reshape(-1)) == pytest.approx(st["rnorm"], rel=1e-6, abs=1e-9 * np.linalg.norm(b))
+    assert np.all(np.diff(hist) <= 1e-12 * hist[0])  # monotone non-increasing
+
+
+def test_gmres_vs_scipy(oracle):
+    from scipy.sparse.linalg import gmres
+    d = P.bratu2d(10)
+    po = P.oracle_problem(oracle, d)
+    Jd = oracle.dense_jacobian(po, d["u0"])
+    b = RNG.standard_normal(Jd.shape[0])
+    x, st, _ = oracle.krylov_solve(po, d["u0"], b.reshape(10, 10), rtol=1e-12, atol=0.0)
+    xs, info = gmres(Jd, b, rtol=1e-13, atol=0.0, restart=200)
+    assert info == 0 and np.allclose(x.reshape(-1), xs, rtol=1e-8, atol=1e-10)
+
+
+def test_cg_matches_textbook(oracle):
+    d = P.bratu2d(8, lam=0.5)
+    po = P.oracle_problem(oracle, d)
+    Jd = oracle.dense_jacobian(po, d["u0"])
+    assert np.allclose(Jd, Jd.T)
+    b = RNG.standard_normal(64)
+    x, st, hist = oracle.krylov_solve(po, d["u0"], b.reshape(8, 8), algo=A.AK_ALGO_CG, rtol=1e-12, atol=0.0, hist_cap=1000)
+    assert st["solved"] and np.allclose(Jd @ x.reshape(-1), b, atol=1e-9)
+
+
+def test_jvp_is_exact_derivative(oracle):
+    """The tangent is the exact derivative (complex-step-free check with central differences at
+    several step sizes: error must shrink like h^2 until rounding)."""
+    for d in (P.bratu1d(40), P.bratu2d(12, 9)):
+        po = P.oracle_problem(oracle, d)
+        v = RNG.standard_normal(d["u0"].shape)
+        jv, _ = oracle.jvp(po, d["u0"], v)
+        errs = []
+        for h in (1e-2, 1e-3):
+            fp, _ = oracle.residual(po, d["u0"] + h * v)
+            fm, _ = oracle.residual(po, d["u0"] - h * v)
+            errs.append(np.max(np.abs((fp - fm) / (2 * h) - jv)) / np.max(np.abs(jv)))
+        assert errs[1] < errs[0] / 50 and errs[1] < 1e-6
+
+
+def test_linear_problems_jvp_equals_residual_difference(oracle):
+    """heat / DG residuals are affine in u: F(u+v) - F(u) == J v up to rounding."""
+    for d in (P.heat1d(30), P.heat2d(12, ic="poly"), P.heat2d(10, bc=A.AK_BC_PERIODIC, ic="poly"), P.heat1d_dg(8)):
+        po = P.oracle_problem(oracle, d, un=d["u0"])
+        v = RNG.standard_normal(d["u0"].shape)
+        if d["kind"] == A.AK_HEAT1D:
+            v[0] = v[-1] = 0.0
+        jv, _ = oracle.jvp(po, d["u0"], v)
+        f1, _ = oracle.residual(po, d["u0"] + v)
+        f0, _ = oracle.residual(po, d["u0"])
+        assert np.allclose(f1 - f0, jv, rtol=1e-9, atol=1e-9 * np.max(np.abs(jv)))
+
+
+def test_heat1d_boundary_side_effects(oracle):
+    """heat_1D.jl:16,34-37: bc!(u) zeroes u[1], u[end] in place; forward mode zeroes v's."""
+    d = P.heat1d(10)
+    po = P.oracle_problem(oracle, d, un=d["u0"])
+    u = d["u0"] + 1.0
+    res, u_after = oracle.residual(po, u)
+    assert u_after[0] == 0 and u_after[-1] == 0 and np.array_equal(u_after[1:-1], u[1:-1])
+    assert res[0] == d["u0"][0] and res[-1] == d["u0"][-1]  # un + dt*0 - 0
+    v = np.ones(12)
+    out, v_after = oracle.jvp(po, d["u0"], v)
+    assert v_after[0] == 0 and v_after[-1] == 0 and out[0] == 0 and out[-1] == 0
+    # Jacobian has zero boundary rows and columns (heat_1D.jl:57-66 rank inspection)
+    J = oracle.dense_jacobian(po, d["u0"])
+    assert np.all(J[0] == 0) and np.all(J[-1] == 0) and np.all(J[:, 0] == 0) and np.all(J[:, -1] == 0)
+    assert np.linalg.matrix_rank(J) == 10
+
+
+def test_dg_operator_invariants(oracle):
+    """SBP properties of the restated DG operators (SummationByPartsOperators.jl is not vendored):
+    M D+ + D-^T M = 0 ; M D- D+ symmetric negative semi-definite with constants in the null space;
+    derivative matrix matches the survey's literals; and the notebook's Jacobian identities
+    2*J_M + I == J_E, J_M == J_T (docs/src/notebooks/heat_1D_DG.jl:154,157)."""
+    D = np.zeros(16)
+    oracle.load().ok_dg_matrix(D.ctypes.data_as(A.c_double_p))
+    D = D.reshape(4, 4)
+    lit = np.array([[-3.0, 4.045084971874737, -1.545084971874737, 0.5],
+                    [-0.8090169943749473, 0.0, 1.118033988749895, -0.3090169943749475],
+                    [0.3090169943749475, -1.118033988749895, 0.0, 0.8090169943749473],
+                    [-0.5, 1.545084971874737, -4.045084971874737, 3.0]])
+    assert np.allclose(D, lit, rtol=0, atol=2e-15)
+    # exact differentiation of cubics on the LGL nodes
+    for k in range(4):
+        assert np.allclose(D @ P.LGL**k, k * P.LGL ** max(k - 1, 0) if k else 0.0, atol=1e-13)
+    ne, h = 7, 1.0 / 7
+    n = 4 * ne
+    lib = oracle.load()
+    Dp, Dm = np.zeros((n, n)), np.zeros((n, n))
+    for j in range(n):
+        e = np.zeros(n); e[j] = 1.0
+        o = np.zeros(n)
+        lib.ok_dg_plus(e.ctypes.data_as(A.c_double_p), o.ctypes.data_as(A.c_double_p), ne, h); Dp[:, j] = o
+        lib.ok_dg_minus(e.ctypes.data_as(A.c_double_p), o.ctypes.data_as(A.c_double_p), ne, h); Dm[:, j] = o
+    M = np.diag(np.tile(np.array([1, 5, 5, 1]) / 6.0 * h / 2, ne))
+    assert np.max(np.abs(M @ Dp + Dm.T @ M)) < 1e-12
+    L = M @ Dm @ Dp
+    assert np.allclose(L, L.T, atol=1e-10) and np.max(np.linalg.eigvalsh((L + L.T) / 2)) < 1e-9
+    assert np.max(np.abs(Dm @ Dp @ np.ones(n))) < 1e-9
+    d = P.heat1d_dg(ne, dt=0.1)
+    JE = oracle.dense_jacobian(P.oracle_problem(oracle, d, un=d["u0"]), d["u0"])
+    JM = oracle.dense_jacobian(P.oracle_problem(oracle, dict(d, scheme=A.AK_MIDPOINT), un=d["u0"]), d["u0"])
+    JT = oracle.dense_jacobian(P.oracle_problem(oracle, dict(d, scheme=A.AK_TRAPEZOID), un=d["u0"]), d["u0"])
+    assert np.allclose(2 * JM + np.eye(n), JE, atol=1e-10) and np.allclose(JM, JT, atol=1e-10)
+    assert np.allclose(JE, 0.1 * Dm @ Dp - np.eye(n), atol=1e-10)
+
+
+def test_bratu_analytic_solution(oracle):
+    """examples/bratu.jl:33-37 pins the converged u to O(dx^2).  At the example's lambda = 3.51382
+    (fold at 3.5138307) plain GMRES does not converge — the example says so (bratu.jl:110-118) — so
+    the check uses the same closed form at lambda = 3.0 with its own theta."""
+    from scipy.optimize import brentq
+    g = GOLD["bratu_analytic"]
+    # the example's (lambda, theta) pair satisfies theta = sqrt(2 lambda) cosh(theta/4)
+    assert g["theta"] == pytest.approx(np.sqrt(2 * g["lambda"]) * np.cosh(g["theta"] / 4), rel=2e-4)
+    lam, N = 3.0, 1000
+    theta = brentq(lambda t: t - np.sqrt(2 * lam) * np.cosh(t / 4), 0.1, 4.0)
+    d = P.bratu1d(N, lam=lam)
+    po = P.oracle_problem(oracle, d)
+    u, st, hist = oracle.newton(po, d["u0"])
+    assert st["solved"]
+    exact = -2.0 * np.log(np.cosh(theta * (d["x"] - 0.5) / 2) / np.cosh(theta / 4))
+    assert np.max(np.abs(u - exact)) < 5e-4
+
+
+def test_survey_probe_table(oracle):
+    """Independent restatement made during the survey (NumPy) predicted these histories."""
+    pred = GOLD["survey_probe_predictions"]
+    d = P.bratu1d(1000)
+    u, st, hist = oracle.newton(P.oracle_problem(oracle, d), d["u0"])
+    assert st["outer_iterations"] == pred["bratu1d_lambda3.5_N1000"]["outer"]
+    inner, want = [h["inner"] for h in hist[1:]], pred["bratu1d_lambda3.5_N1000"]["inner"]
+    # GMRES counts of ~500 flip by one when rNorm lands within rounding of the tolerance (a different
+    # summation order is enough), after which the Newton path differs slightly: exact for the first
+    # seven steps, within 3 % afterwards
+    assert inner[:7] == want[:7]
+    assert all(abs(a - b) <= 0.03 * b for a, b in zip(inner[7:], want[7:]))
+    for N, outer, tot in zip(*[pred["bratu2d_lambda3.5"][k] for k in ("N", "outer", "inner_total")]):
+        if N > 64:
+            continue
+        d = P.bratu2d(N)
+        u, st, hist = oracle.newton(P.oracle_problem(oracle, d), d["u0"])
+        assert (st["outer_iterations"], st["inner_iterations"]) == (outer, tot)
+    d = P.heat1d(100)
+    ur, newt, inner, solved = oracle.implicit_solve(P.oracle_problem(oracle, d, un=d["u0"]), d["u0"], 1)
+    assert newt[0] == pred["heat1d_M100"]["newton_per_step"] and inner[0] == sum(pred["heat1d_M100"]["inner_first_step"])
+
+
+def test_heat2d_reference_ic_is_eigenfunction(oracle):
+    """with the example's IC and dt the solve needs 1 Newton step of 1 GMRES iteration."""
+    d = P.heat2d(40)
+    ur, newt, inner, solved = oracle.implicit_solve(P.oracle_problem(oracle, d, un=d["u0"]), d["u0"], 2,
+                                                    A.default_newton_opts(tol_abs=6e-6))
+    assert list(newt) == [1, 1] and list(inner) == [1, 1] and all(solved)
+
+
+def test_halo_layout_roundtrip(oracle):
+    nx, ny = 5, 4
+    padded = RNG.standard_normal((ny + 2, nx + 2))
+    comp = np.zeros((ny, nx))
+    lib = oracle.load()
+    lib.ok_halo_pack(comp.ctypes.data_as(A.c_double_p), padded.ctypes.data_as(A.c_double_p), nx, ny)
+    assert np.array_equal(comp, padded[1:-1, 1:-1])
+    back = np.full((ny + 2, nx + 2), np.nan)
+    lib.ok_halo_unpack(back.ctypes.data_as(A.c_double_p), comp.ctypes.data_as(A.c_double_p), nx, ny, A.AK_BC_PERIODIC)
+    assert np.array_equal(back[1:-1, 1:-1], comp)
+    assert np.array_equal(back[1:-1, 0], comp[:, -1]) and np.array_equal(back[1:-1, -1], comp[:, 0])
+    assert np.array_equal(back[0, 1:-1], comp[-1]) and np.array_equal(back[-1, 1:-1], comp[0])
+    assert back[0, 0] == comp[-1, -1]
