@@ -116,6 +116,14 @@ int64_t ak_ctx_launch_count(ak_ctx* ctx, int reset);
 int ak_timer_start(ak_ctx* ctx);
 int ak_timer_stop(ak_ctx* ctx, double* ms_out);
 
+/* In-stream profiler: when enabled, every kernel launch is bracketed by CUDA events on the
+ * context's stream; ak_profile_read returns the number of launches of one kernel class and the
+ * sum of their device times.  Classes: 0 axpy+dot (fused MGS step, 32n bytes), 1 axpy+norm (24n),
+ * 2 axpy (24n), 3 dot (16n), 4 sum of squares (8n), 5 JVP, 6 residual, 7 element-wise,
+ * 8 basis combine, 9 one-thread scalar kernels.  Enabling resets the counters.          */
+int ak_profile_enable(ak_ctx* ctx, int on);
+int ak_profile_read(ak_ctx* ctx, int kernel_class, int64_t* count_out, double* ms_total_out);
+
 /* device memory owned by the library; the library never frees caller memory */
 int ak_malloc(ak_ctx* ctx, int64_t n_doubles, double** out);
 int ak_free(ak_ctx* ctx, double* p);

@@ -37,6 +37,8 @@ SIGNATURES = {
     "ak_ctx_launch_count": (C.c_int64, [_vp, C.c_int]),
     "ak_timer_start": (C.c_int, [_vp]),
     "ak_timer_stop": (C.c_int, [_vp, _dp]),
+    "ak_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "ak_profile_read": (C.c_int, [_vp, C.c_int, A.c_int64_p, _dp]),
     "ak_malloc": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "ak_free": (C.c_int, [_vp, _vp]),
     "ak_upload": (C.c_int, [_vp, _vp, _vp, C.c_int64]),

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <vector>
+
 #include "../../include/ariadne_b200.h"
 
 #define AK_API extern "C" __attribute__((visibility("default")))
@@ -42,6 +44,21 @@ constexpr int kNumSMsDefault = 148;
 
 struct Comm;  // NCCL state (context.cu)
 
+// kernel classes for the optional in-stream profiler (ak_profile_*)
+enum ProfClass {
+    PK_MGS_AXPY_DOT = 0,   // w -= h v_i ; h' = <v_{i+1}, w>      32n bytes
+    PK_MGS_AXPY_NRM = 1,   // w -= h v_k ; ||w||^2                24n
+    PK_MGS_AXPY = 2,       // w -= h v_i                          24n
+    PK_DOT = 3,            // <x, y>                              16n
+    PK_SUMSQ = 4,          // ||x||^2                              8n
+    PK_JVP = 5,            // J(u) v (+ fused divcopy / dot)
+    PK_RESIDUAL = 6,       // F(u) (+ fused norm)
+    PK_ELEMENTWISE = 7,    // scal/axpy/axpby/copy/fill/divcopy/ref
+    PK_COMBINE = 8,        // x = sum y_i V_i
+    PK_SCALAR = 9,         // one-thread Givens / control kernels
+    PK_NUM = 10
+};
+
 struct Ctx {
     int device = 0;
     int num_sms = kNumSMsDefault;
@@ -54,6 +71,12 @@ struct Ctx {
     double* hscal = nullptr;        // 64 doubles, pinned
     int64_t launches = 0;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    // optional profiler: CUDA-event pairs around every launch of the classes above
+    bool prof_on = false;
+    struct ProfRec { int cls; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    size_t prof_pool_used = 0;
     // multi-GPU
     Comm* comm = nullptr;
     int rank = 0, nranks = 1;
@@ -61,6 +84,14 @@ struct Ctx {
     double* halo_hi = nullptr;      // nx doubles: row gy0+ny (from rank+1)
     double* halo_send = nullptr;
     int64_t halo_cap = 0;
+};
+
+// RAII: brackets one kernel launch with events when the profiler is on (context.cu)
+struct ProfScope {
+    Ctx* c;
+    int idx;
+    ProfScope(Ctx* ctx, int cls);
+    ~ProfScope();
 };
 
 // --- comm (context.cu) --------------------------------------------------------

@@ -109,12 +109,17 @@ static int launch_mgs_t(Ctx* ctx, int64_t n, double* w, const double* vi, const 
                         double* out, const int* stop) {
     const bool vec = aligned32(w) && (!AXPY || aligned32(vi)) && (RED != 1 || aligned32(vnext));
     const int blocks = stream_blocks(ctx, n, 8);
-    if (vec)
-        k_mgs_step<AXPY, RED, true><<<blocks, kThreads, 0, ctx->stream>>>(w, vi, h_in, vnext, out, ctx->partials,
-                                                                          ctx->ticket, n, stop);
-    else
-        k_mgs_step<AXPY, RED, false><<<blocks, kThreads, 0, ctx->stream>>>(w, vi, h_in, vnext, out, ctx->partials,
-                                                                           ctx->ticket, n, stop);
+    constexpr int cls = AXPY ? (RED == 1 ? PK_MGS_AXPY_DOT : (RED == 2 ? PK_MGS_AXPY_NRM : PK_MGS_AXPY))
+                             : (RED == 1 ? PK_DOT : PK_SUMSQ);
+    {
+        ProfScope prof(ctx, cls);  // brackets the kernel only (not the all-reduce that follows)
+        if (vec)
+            k_mgs_step<AXPY, RED, true><<<blocks, kThreads, 0, ctx->stream>>>(w, vi, h_in, vnext, out, ctx->partials,
+                                                                              ctx->ticket, n, stop);
+        else
+            k_mgs_step<AXPY, RED, false><<<blocks, kThreads, 0, ctx->stream>>>(w, vi, h_in, vnext, out,
+                                                                               ctx->partials, ctx->ticket, n, stop);
+    }
     ctx->launches++;
     AK_CUDA(cudaGetLastError());
     if (RED != 0) AK_TRY(allreduce_sum(ctx, out, 1));
@@ -213,6 +218,7 @@ static int launch_ew(Ctx* ctx, int64_t n, double* y, const double* x, double s, 
     if (n <= 0) return AK_OK;
     const bool vec = aligned32(y) && (x == nullptr || aligned32(x));
     const int blocks = stream_blocks(ctx, n, 4);
+    ProfScope prof(ctx, PK_ELEMENTWISE);
     if (vec)
         k_ew<OP, true><<<blocks, kThreads, 0, ctx->stream>>>(y, const_cast<double*>(x), s, t, s_dev, n, stop);
     else
@@ -285,6 +291,7 @@ int launch_basis_combine(Ctx* ctx, int64_t n, double* x, const double* const* V_
                          int zero_x_first) {
     if (n <= 0) return AK_OK;
     const int blocks = stream_blocks(ctx, n, 4);
+    ProfScope prof(ctx, PK_COMBINE);
     // basis vectors come from the workspace arena (256-byte aligned); x may be caller memory
     if (aligned32(x))
         k_basis_combine<true><<<blocks, kThreads, 0, ctx->stream>>>(x, V_dev, y_dev, k, zero_x_first, n);

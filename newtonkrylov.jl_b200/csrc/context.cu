@@ -24,6 +24,28 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// ---- in-stream profiler --------------------------------------------------------------------
+constexpr size_t kProfMaxRecs = 1 << 16;
+ProfScope::ProfScope(Ctx* ctx, int cls) : c(ctx), idx(-1) {
+    if (!c->prof_on || c->prof_recs.size() >= kProfMaxRecs) return;
+    auto get = [&]() -> cudaEvent_t {
+        if (c->prof_pool_used == c->prof_pool.size()) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            c->prof_pool.push_back(e);
+        }
+        return c->prof_pool[c->prof_pool_used++];
+    };
+    cudaEvent_t e0 = get(), e1 = get();
+    if (!e0 || !e1) return;
+    cudaEventRecord(e0, c->stream);
+    c->prof_recs.push_back({cls, e0, e1});
+    idx = (int)c->prof_recs.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(c->prof_recs[(size_t)idx].e1, c->stream);
+}
+
 // ---- minimal NCCL surface (ABI-stable since NCCL 2.x) -----------------------------------
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
@@ -211,6 +233,7 @@ AK_API int ak_ctx_destroy(ak_ctx* ctx) {
     if (c->hscal) cudaFreeHost(c->hscal);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete ctx;
     return AK_OK;
@@ -240,6 +263,31 @@ AK_API int ak_timer_stop(ak_ctx* ctx, double* ms_out) {
     float ms = 0.f;
     AK_CUDA(cudaEventElapsedTime(&ms, ctx->c.ev_t0, ctx->c.ev_t1));
     *ms_out = (double)ms;
+    return AK_OK;
+}
+
+AK_API int ak_profile_enable(ak_ctx* ctx, int on) {
+    AK_REQUIRE(ctx, "ak_profile_enable: NULL ctx");
+    Ctx* c = &ctx->c;
+    AK_CUDA(cudaStreamSynchronize(c->stream));
+    c->prof_on = on != 0;
+    c->prof_recs.clear();
+    c->prof_pool_used = 0;
+    return AK_OK;
+}
+AK_API int ak_profile_read(ak_ctx* ctx, int cls, int64_t* count_out, double* ms_total_out) {
+    AK_REQUIRE(ctx && cls >= 0 && cls < PK_NUM, "ak_profile_read: bad argument");
+    Ctx* c = &ctx->c;
+    AK_CUDA(cudaStreamSynchronize(c->stream));
+    int64_t cnt = 0;
+    double tot = 0.0;
+    for (const auto& r : c->prof_recs) {
+        if (r.cls != cls) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { cnt++; tot += ms; }
+    }
+    if (count_out) *count_out = cnt;
+    if (ms_total_out) *ms_total_out = tot;
     return AK_OK;
 }
 

@@ -471,9 +471,10 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                     }
                 }
                 const int slot = (int)(k % kStatusRing);
+                { ProfScope prof(c, PK_SCALAR);
                 k_gmres_givens<<<1, 32, 0, sm>>>(ws->ctl, (int)k, nr, ws->R, ws->c, ws->s, ws->z, hcol, reorth,
                                                  want_hist ? ws->hist : nullptr, iter + k, (int)inner_limit,
-                                                 &ws->status[slot]);
+                                                 &ws->status[slot]); }
                 c->launches++;
                 AK_CUDA(cudaGetLastError());
                 AK_CUDA(cudaEventRecord(ws->ev[slot], sm));

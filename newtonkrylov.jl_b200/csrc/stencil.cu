@@ -630,6 +630,7 @@ static int ghost_rows(Ctx* ctx, const ak_problem* p, const double* v, const doub
 
 int launch_residual(Ctx* ctx, const ak_problem* p, double* u, double* res, double* sumsq_dev) {
     AK_TRY(check_problem(p));
+    ProfScope prof(ctx, PK_RESIDUAL);
     const int red = sumsq_dev ? RED_SUMSQ : RED_NONE;
     if (p->kind == AK_SIMPLE2) {
         k_simple2<<<1, 32, 0, ctx->stream>>>(u, nullptr, res, sumsq_dev, 0, nullptr, nullptr);
@@ -689,6 +690,7 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     AK_TRY(check_problem(p));
     JvpFusion nofuse;
     if (!f) f = &nofuse;
+    ProfScope prof(ctx, PK_JVP);
     const bool scale = f->scale_src != nullptr;
     const int red = f->dot_with ? RED_DOT : RED_NONE;
     if (p->kind == AK_SIMPLE2) {

@@ -60,6 +60,15 @@ class Context:
         L.check(self.lib.ak_timer_stop(self.h, C.byref(ms)))
         return ms.value
 
+    def profile(self, on=True):
+        L.check(self.lib.ak_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self, cls):
+        """(launch count, total device ms) of one kernel class since profile(True)."""
+        cnt, ms = C.c_int64(), C.c_double()
+        L.check(self.lib.ak_profile_read(self.h, cls, C.byref(cnt), C.byref(ms)))
+        return cnt.value, ms.value
+
     @property
     def stream(self):
         return int(self.lib.ak_ctx_stream(self.h))

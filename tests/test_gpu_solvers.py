@@ -243,7 +243,10 @@ def test_bratu1d_analytic_solution(nk, ctx):
 IMPLICIT_CASES = [
     ("heat1d", lambda: P.heat1d(100), 3, {}),
     ("heat2d_reference_ic", lambda: P.heat2d(40), 3, dict(reorthogonalization=True)),
-    ("heat2d_poly_stiff", lambda: P.heat2d(32, dt_scale=64.0, ic="poly"), 3, dict(reorthogonalization=True)),
+    # (N = 32 puts the last GMRES solve of step 3 within rounding of its tolerance: 41 vs 42 iterations
+    #  depending on summation order — N = 30 has no such knife edge)
+    ("heat2d_poly_stiff", lambda: P.heat2d(30, dt_scale=64.0, ic="poly"), 3, dict(reorthogonalization=True)),
+    ("heat2d_poly_stiff_rect_dt", lambda: P.heat2d(44, dt_scale=200.0, ic="poly"), 2, {}),
     ("heat2d_periodic", lambda: P.heat2d(24, dt_scale=16.0, bc=A.AK_BC_PERIODIC, ic="poly"), 2, {}),
     ("dg", lambda: P.heat1d_dg(40, dt=0.01), 2, {}),
 ]
@@ -259,7 +262,7 @@ def test_implicit_time_stepping_matches_oracle(nk, ctx, oracle, name, make, nste
     # reproducibility of the algorithm itself under a 1-ulp change of one entry of u0
     rng = np.random.default_rng(3)
     robust, du = np.ones(nsteps, dtype=bool), 0.0
-    for _ in range(2):
+    for _ in range(4):
         u1 = d["u0"].copy()
         i = rng.integers(1, u1.size - 1)
         u1.flat[i] = np.nextafter(u1.flat[i], np.inf)
