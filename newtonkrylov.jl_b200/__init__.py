@@ -12,6 +12,6 @@ library is missing (there is no CPU fallback).
 from . import _abi, _lib, build as _build  # noqa: F401
 from ._lib import AriadneError, LIB_PATH  # noqa: F401
 from .host import *  # noqa: F401,F403
-from . import host  # noqa: F401
+from . import host, dist  # noqa: F401
 
 __all__ = [n for n in dir(host) if not n.startswith("_")]

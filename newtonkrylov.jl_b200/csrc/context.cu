@@ -207,6 +207,15 @@ AK_API int ak_ctx_create(int device, ak_ctx** out) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     AK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        // Stream-ordered allocations from the device pool, never trimmed: a Krylov workspace
+        // (22+ vectors of n doubles) is re-created by every newton_krylov! call like in the
+        // reference (src/Ariadne.jl:317-318) but costs no cudaMalloc/cudaFree after the first.
+        cudaMemPool_t pool;
+        AK_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        AK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     AK_CUDA(cudaMalloc(&c->partials, sizeof(double) * kMaxPartials));
     AK_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned int)));
     AK_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
@@ -294,7 +303,7 @@ AK_API int ak_profile_read(ak_ctx* ctx, int cls, int64_t* count_out, double* ms_
 AK_API int ak_malloc(ak_ctx* ctx, int64_t n, double** out) {
     AK_REQUIRE(ctx && out && n >= 0, "ak_malloc: bad argument");
     AK_CUDA(cudaSetDevice(ctx->c.device));
-    cudaError_t e = cudaMalloc(out, sizeof(double) * (size_t)(n > 0 ? n : 1));
+    cudaError_t e = cudaMallocAsync((void**)out, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->c.stream);
     if (e != cudaSuccess) {
         set_error("ak_malloc: %lld doubles: %s", (long long)n, cudaGetErrorString(e));
         (void)cudaGetLastError();
@@ -305,8 +314,7 @@ AK_API int ak_malloc(ak_ctx* ctx, int64_t n, double** out) {
 AK_API int ak_free(ak_ctx* ctx, double* p) {
     AK_REQUIRE(ctx, "ak_free: NULL ctx");
     if (!p) return AK_OK;
-    AK_CUDA(cudaStreamSynchronize(ctx->c.stream));
-    AK_CUDA(cudaFree(p));
+    AK_CUDA(cudaFreeAsync(p, ctx->c.stream));  // stream-ordered: safe behind every kernel already enqueued
     return AK_OK;
 }
 AK_API int ak_upload(ak_ctx* ctx, double* dst_dev, const double* src_host, int64_t n) {

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) k_cg_update_p(double* __restrict__ p, con
 // ---------------------------------------------------------------------------------------
 static int ws_alloc_vec(ak_krylov* ws, double** out) {
     double* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, sizeof(double) * (size_t)(ws->n > 0 ? ws->n : 1));
+    cudaError_t e = cudaMallocAsync((void**)&p, sizeof(double) * (size_t)(ws->n > 0 ? ws->n : 1), ws->ctx->stream);
     if (e != cudaSuccess) {
         set_error("krylov workspace: cudaMalloc of %lld doubles failed: %s", (long long)ws->n, cudaGetErrorString(e));
         (void)cudaGetLastError();
@@ -253,12 +253,11 @@ static int ws_grow_scalars(ak_krylov* ws, int64_t kcap_new) {
     const int64_t nR = kcap_new * (kcap_new + 1) / 2;
     auto regrow = [&](double** arr, int64_t old_n, int64_t new_n) -> int {
         double* q = nullptr;
-        AK_CUDA(cudaMalloc(&q, sizeof(double) * (size_t)new_n));
+        AK_CUDA(cudaMallocAsync((void**)&q, sizeof(double) * (size_t)new_n, c->stream));
         AK_CUDA(cudaMemsetAsync(q, 0, sizeof(double) * (size_t)new_n, c->stream));
         if (*arr && old_n > 0)
             AK_CUDA(cudaMemcpyAsync(q, *arr, sizeof(double) * (size_t)old_n, cudaMemcpyDeviceToDevice, c->stream));
-        AK_CUDA(cudaStreamSynchronize(c->stream));
-        if (*arr) AK_CUDA(cudaFree(*arr));
+        if (*arr) AK_CUDA(cudaFreeAsync(*arr, c->stream));
         *arr = q;
         return AK_OK;
     };
@@ -279,10 +278,10 @@ static int ws_grow_hist(ak_krylov* ws, int64_t need) {
     if (nc < need) nc = need;
     AK_CUDA(cudaStreamSynchronize(c->stream));
     double* q = nullptr;
-    AK_CUDA(cudaMalloc(&q, sizeof(double) * (size_t)nc));
+    AK_CUDA(cudaMallocAsync((void**)&q, sizeof(double) * (size_t)nc, c->stream));
     if (ws->hist) {
-        AK_CUDA(cudaMemcpy(q, ws->hist, sizeof(double) * (size_t)ws->hist_cap, cudaMemcpyDeviceToDevice));
-        AK_CUDA(cudaFree(ws->hist));
+        AK_CUDA(cudaMemcpyAsync(q, ws->hist, sizeof(double) * (size_t)ws->hist_cap, cudaMemcpyDeviceToDevice, c->stream));
+        AK_CUDA(cudaFreeAsync(ws->hist, c->stream));
     }
     ws->hist = q;
     ws->hist_cap = nc;
@@ -316,10 +315,10 @@ static int ws_upload_basis_table(ak_krylov* ws, int64_t k) {
     Ctx* c = ws->ctx;
     if (k > ws->V_dev_cap) {
         AK_CUDA(cudaStreamSynchronize(c->stream));
-        if (ws->V_dev) AK_CUDA(cudaFree((void*)ws->V_dev));
+        if (ws->V_dev) AK_CUDA(cudaFreeAsync((void*)ws->V_dev, c->stream));
         int64_t cap = ws->V_dev_cap ? ws->V_dev_cap * 2 : 64;
         if (cap < k) cap = k;
-        AK_CUDA(cudaMalloc((void**)&ws->V_dev, sizeof(double*) * (size_t)cap));
+        AK_CUDA(cudaMallocAsync((void**)&ws->V_dev, sizeof(double*) * (size_t)cap, c->stream));
         ws->V_dev_cap = cap;
     }
     AK_CUDA(cudaMemcpyAsync((void*)ws->V_dev, ws->V.data(), sizeof(double*) * (size_t)k, cudaMemcpyHostToDevice,
@@ -684,8 +683,8 @@ AK_API int ak_krylov_create(ak_ctx* ctx, int32_t algo, int64_t n, int32_t memory
             if ((rc = ws_alloc_vec(ws, &ws->p)) != AK_OK) break;
             if ((rc = ws_alloc_vec(ws, &ws->Ap)) != AK_OK) break;
         }
-        if (cudaMalloc(&ws->ctl, sizeof(KrylovCtl)) != cudaSuccess) { rc = AK_ERR_NOMEM; break; }
-        cudaMemset(ws->ctl, 0, sizeof(KrylovCtl));
+        if (cudaMallocAsync((void**)&ws->ctl, sizeof(KrylovCtl), ctx->c.stream) != cudaSuccess) { rc = AK_ERR_NOMEM; break; }
+        cudaMemsetAsync(ws->ctl, 0, sizeof(KrylovCtl), ctx->c.stream);
         if (cudaHostAlloc((void**)&ws->status, sizeof(KrylovStatus) * kStatusSlots, cudaHostAllocMapped) != cudaSuccess) {
             rc = AK_ERR_NOMEM;
             break;
@@ -707,11 +706,13 @@ AK_API int ak_krylov_create(ak_ctx* ctx, int32_t algo, int64_t n, int32_t memory
 
 AK_API int ak_krylov_destroy(ak_krylov* ws) {
     if (!ws) return AK_OK;
-    if (ws->ctx && ws->ctx->stream) cudaStreamSynchronize(ws->ctx->stream);
-    for (double* p : ws->chunks) cudaFree(p);
-    if (ws->V_dev) cudaFree((void*)ws->V_dev);
-    cudaFree(ws->R); cudaFree(ws->c); cudaFree(ws->s); cudaFree(ws->z); cudaFree(ws->hcol); cudaFree(ws->hist);
-    cudaFree(ws->ctl);
+    cudaStream_t sm = ws->ctx ? ws->ctx->stream : nullptr;
+    if (sm) cudaStreamSynchronize(sm);
+    auto rel = [&](void* p) { if (p) cudaFreeAsync(p, sm); };
+    for (double* p : ws->chunks) rel(p);
+    rel((void*)ws->V_dev);
+    rel(ws->R); rel(ws->c); rel(ws->s); rel(ws->z); rel(ws->hcol); rel(ws->hist);
+    rel(ws->ctl);
     if (ws->status) cudaFreeHost(ws->status);
     for (int i = 0; i < kStatusSlots; ++i)
         if (ws->ev[i]) cudaEventDestroy(ws->ev[i]);

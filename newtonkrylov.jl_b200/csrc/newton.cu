@@ -134,7 +134,7 @@ AK_API int ak_newton_solve(ak_ctx* ctx, const ak_problem* p, double* u, double* 
         rc = newton_ws(c, p, u, res, opts, ws, rhs, stats_out, hist_nres_host, hist_inner_host, hist_eta_host,
                        hist_cap, cb, cb_user);
     cudaStreamSynchronize(c->stream);
-    if (rhs) cudaFree(rhs);
+    if (rhs) cudaFreeAsync(rhs, c->stream);
     ak_krylov_destroy(ws);
     return rc;
 }
@@ -170,7 +170,8 @@ AK_API int ak_newton_solve_host(ak_ctx* ctx, const ak_problem* p_in, double* u_h
     } while (0);
     if (rc == AK_ERR_CUDA) set_error("ak_newton_solve_host: CUDA copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     cudaStreamSynchronize(c->stream);
-    cudaFree(u); cudaFree(res); cudaFree(un); cudaFree(coef);
+    for (double* q : {u, res, un, coef})
+        if (q) cudaFreeAsync(q, c->stream);
     return rc;
 }
 
@@ -208,7 +209,8 @@ AK_API int ak_implicit_solve(ak_ctx* ctx, ak_problem* p, double* un_dev, int32_t
     } while (0);
     p->un = saved_un;
     cudaStreamSynchronize(c->stream);
-    cudaFree(u); cudaFree(res); cudaFree(rhs);
+    for (double* q : {u, res, rhs})
+        if (q) cudaFreeAsync(q, c->stream);
     ak_krylov_destroy(ws);
     return rc < 0 ? rc : AK_OK;
 }

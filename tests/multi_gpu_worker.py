@@ -1,0 +1,97 @@
+"""Run under torchrun with one rank per GPU: slab-decomposed kernels and solves through the C ABI
+(NCCL all-reduce + halo exchange issued by the library) against the single-domain oracle."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+import torch
+import torch.distributed as dist
+
+import newtonkrylov_jl_b200 as nk
+import oracle as O
+import problems as P
+from newtonkrylov_jl_b200 import _abi as A
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.ravel(a) - np.ravel(b)) / max(np.linalg.norm(np.ravel(b)), 1e-300))
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ctx = nk.dist.init_distributed(local)
+    assert (ctx.rank, ctx.nranks) == (rank, world)
+    rng = np.random.default_rng(0)
+
+    for name, d, bc in [("bratu2d", P.generic(P.bratu2d(48, 40)), nk.bc_zero_),
+                        ("bratu2d_ragged", P.generic(P.bratu2d(37, 29)), nk.bc_zero_),
+                        ("heat2d", P.heat2d(36, dt_scale=48.0, ic="poly"), nk.bc_zero_),
+                        ("heat2d_periodic", P.heat2d(32, dt_scale=16.0, bc=A.AK_BC_PERIODIC, ic="poly"), nk.bc_periodic_)]:
+        nx, gny = d["nx"], d["ny"]
+        gy0, ny = nk.dist.slab_partition(gny, world, rank)
+        sl = slice(gy0, gy0 + ny)
+        u = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
+        v0 = rng.standard_normal(d["u0"].shape)
+        v = nk.DeviceVector.from_numpy(v0[sl], ctx)
+        if d["kind"] == A.AK_BRATU2D:
+            F_, p = nk.bratu2d_, (d["dx"], d["dy"], d["lam"], gny, gy0)
+            po = P.oracle_problem(O, d)
+        else:
+            un = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
+            F_ = nk.ImplicitResidual(nk.G_Euler_, nk.diffusion_)
+            p = (un, d["dt"], un.zero(), (d["a"], d["dx"], d["dy"], bc, gny, gy0), 0.0)
+            po = P.oracle_problem(O, d, un=d["u0"])
+        # kernel level: residual, JVP, global reductions
+        res, out = u.zero(), u.zero()
+        F_(res, u, p)
+        ref, _ = O.residual(po, d["u0"])
+        assert rel(res.numpy(), ref[sl]) < 1e-14, name
+        nk.mul_(out, nk.JacobianOperator(F_, res, u, p), v)
+        refj, _ = O.jvp(po, d["u0"], v0)
+        assert rel(out.numpy(), refj[sl]) < 1e-14, name
+        assert abs(nk.kdot(u.n, u, v) - float(np.vdot(d["u0"], v0))) <= 1e-12 * np.linalg.norm(d["u0"]) * np.linalg.norm(v0)
+        assert abs(nk.knorm(v.n, v) - np.linalg.norm(v0)) <= 1e-13 * np.linalg.norm(v0)
+        # solver level
+        if d["kind"] == A.AK_BRATU2D:
+            for fuse in ("none", "mgs", "full"):
+                u = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
+                hist = []
+                _, r = nk.newton_krylov_native_(F_, u, p, None, history=hist, krylov_kwargs=dict(fuse=fuse))
+                ur, sr, hr = O.newton(po, d["u0"])
+                assert r.solved and r.stats.outer_iterations == sr["outer_iterations"], (name, fuse, r, sr)
+                assert [h["inner"] for h in hist] == [h["inner"] for h in hr], (name, fuse)
+                for a, b in zip(hist, hr):
+                    assert abs(a["n_res"] - b["n_res"]) <= 1e-8 * b["n_res"] + 1e-13 * hr[0]["n_res"], (name, fuse, a, b)
+                assert rel(u.numpy(), ur[sl]) < 1e-7, (name, fuse)
+        else:
+            prob = F_.problem(u, p)
+            import ctypes as C
+            o = nk.host._newton_opts(1e-6, 6e-6, 50, nk.EisenstatWalker(), "gmres", 20, 0, {})
+            nsteps = 2
+            newt, inner, solved = np.zeros(nsteps, np.int32), np.zeros(nsteps, np.int64), np.zeros(nsteps, np.int32)
+            un = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
+            nk._lib.check(ctx.lib.ak_implicit_solve(ctx.h, C.byref(prob), C.c_void_p(un.ptr), nsteps, C.byref(o),
+                                                    newt.ctypes.data_as(A.c_int32_p), inner.ctypes.data_as(A.c_int64_p),
+                                                    solved.ctypes.data_as(A.c_int32_p)))
+            ur, nr, ir, sr_ = O.implicit_solve(po, d["u0"], nsteps, o)
+            assert list(newt) == list(nr) and list(solved) == list(sr_), (name, newt, nr)
+            assert all(abs(int(a) - int(b)) <= 1 for a, b in zip(inner, ir)), (name, inner, ir)
+            assert rel(un.numpy(), ur[sl]) < 1e-7, name
+        if rank == 0:
+            print(f"[multi-gpu x{world}] {name}: ok", flush=True)
+    dist.barrier()
+    if rank == 0:
+        print("MULTI_GPU_OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
