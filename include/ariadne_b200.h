@@ -120,7 +120,8 @@ int ak_timer_stop(ak_ctx* ctx, double* ms_out);
  * context's stream; ak_profile_read returns the number of launches of one kernel class and the
  * sum of their device times.  Classes: 0 axpy+dot (fused MGS step, 32n bytes), 1 axpy+norm (24n),
  * 2 axpy (24n), 3 dot (16n), 4 sum of squares (8n), 5 JVP, 6 residual, 7 element-wise,
- * 8 basis combine, 9 one-thread scalar kernels.  Enabling resets the counters.          */
+ * 8 basis combine, 9 one-thread scalar kernels, 10 pair-wise MGS pass (48n), 11 first/odd
+ * passes of the pair-wise sweep.  Enabling resets the counters.                          */
 int ak_profile_enable(ak_ctx* ctx, int on);
 int ak_profile_read(ak_ctx* ctx, int kernel_class, int64_t* count_out, double* ms_total_out);
 
@@ -183,7 +184,12 @@ enum { AK_ALGO_GMRES = 0, AK_ALGO_CG = 1 };
 enum {
     AK_FUSE_NONE = 0,  /* reference op list: dot, axpy, ..., nrm2, divcopy        */
     AK_FUSE_MGS = 1,   /* axpy_i + dot_{i+1} in one pass, last axpy + nrm2 fused  */
-    AK_FUSE_FULL = 2   /* + (divcopy + JVP + first dot) in one pass               */
+    AK_FUSE_FULL = 2,  /* + (divcopy + JVP + first dot) in one pass               */
+    AK_FUSE_PAIR = 3   /* two Gram-Schmidt steps per sweep over w: the pass that subtracts
+                          h_a v_a + h_b v_b also accumulates <y_a,w>, <y_b,w>, <y_b,y_a>; the
+                          coefficient of y_b follows as <y_b,w> - <y_a,w><y_b,y_a>, which is
+                          algebraically the modified Gram-Schmidt value (24n bytes per step
+                          instead of 32n); falls back to FULL with reorthogonalization    */
 };
 
 typedef struct ak_krylov_opts {

@@ -56,7 +56,9 @@ enum ProfClass {
     PK_ELEMENTWISE = 7,    // scal/axpy/axpby/copy/fill/divcopy/ref
     PK_COMBINE = 8,        // x = sum y_i V_i
     PK_SCALAR = 9,         // one-thread Givens / control kernels
-    PK_NUM = 10
+    PK_MGS_PAIR = 10,      // w -= h_a v_a + h_b v_b ; 3 sums with the next pair   48n (24n per Gram-Schmidt step)
+    PK_MGS_PAIR_EDGE = 11, // first / odd passes of the pair-wise sweep
+    PK_NUM = 12
 };
 
 struct Ctx {
@@ -122,6 +124,9 @@ int launch_divcopy_dev(Ctx* ctx, int64_t n, double* y, const double* x, const do
 // `stop_flag` (device int, may be null): kernel is a no-op when *stop_flag != 0.
 int launch_mgs_step(Ctx* ctx, int64_t n, double* w, const double* vi, const double* h_in,
                     const double* vnext, int want_sumsq, double* out_dev, const int* stop_flag);
+// Pair-wise Gram-Schmidt pass (see blas1.cu)
+int launch_mgs_pair(Ctx* ctx, int64_t n, double* w, const double* va, const double* vb, const double* tin,
+                    const double* ya, const double* yb, int want_sumsq, double* out, const int* stop);
 // x <- x + sum_i y[i] V[i]  (sequential axpy order), optionally u <- u - x fused (single pass)
 int launch_basis_combine(Ctx* ctx, int64_t n, double* x, const double* const* V_dev, const double* y_dev,
                          int k, int zero_x_first);

@@ -139,6 +139,112 @@ int launch_mgs_step(Ctx* ctx, int64_t n, double* w, const double* vi, const doub
     return AK_OK;
 }
 
+// -----------------------------------------------------------------------------------
+// Pair-wise modified Gram-Schmidt pass (fuse level PAIR): two Gram-Schmidt steps per sweep over w.
+//   NAX  axpys : w <- w - h_a v_a [- h_b v_b]     with (h_a, h_b) = (t[0], t[1] - t[0] t[2]) from `tin`
+//   NRED = 1   : out[0] = <y_a, w_new>
+//   NRED = 2   : out = { <y_a,w_new>, <y_b,w_new>, <y_b,y_a> }   (h of y_b follows as d2 - d1 g: algebraically the
+//                modified Gram-Schmidt coefficient <y_b, w_new - d1 y_a>, without a second sweep over w)
+//   NRED = 3   : out[0] = <w_new, w_new>
+// Algorithmic bytes per launch: 8n (2 [w in/out] + NAX + number of y vectors); 48n for NAX = NRED = 2,
+// i.e. 24n per Gram-Schmidt step instead of 32n.
+// -----------------------------------------------------------------------------------
+template <int NAX, int NRED, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_mgs_pair(double* __restrict__ w, const double* __restrict__ va,
+                                                       const double* __restrict__ vb, const double* __restrict__ tin,
+                                                       const double* __restrict__ ya, const double* __restrict__ yb,
+                                                       double* __restrict__ out, double* __restrict__ partials,
+                                                       unsigned int* ticket, int64_t n, const int* __restrict__ stop) {
+    __shared__ double sh[32];
+    if (stop != nullptr && *stop != 0) return;
+    double ha = 0.0, hb = 0.0;
+    if (NAX >= 1) {
+        const double d1 = tin[0];
+        ha = -d1;
+        if (NAX == 2) hb = -pair_second_h(d1, tin[1], tin[2]);
+    }
+    double s0a = 0.0, s0b = 0.0, s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    auto body = [&](double& wj, double xa, double xb, double a, double b, double& t0, double& t1, double& t2) {
+        if (NAX >= 1) wj = fma(ha, xa, wj);   // same order as two successive kaxpy!
+        if (NAX == 2) wj = fma(hb, xb, wj);
+        if (NRED == 1) t0 = fma(a, wj, t0);
+        if (NRED == 2) { t0 = fma(a, wj, t0); t1 = fma(b, wj, t1); t2 = fma(b, a, t2); }
+        if (NRED == 3) t0 = fma(wj, wj, t0);
+    };
+    if (VEC) {
+        const int64_t n4 = n >> 2;
+        for (int64_t i = tid; i < n4; i += nth) {
+            const int64_t j = i << 2;
+            d4 wv = (NAX > 0) ? ld4(w + j) : ld4_stream(w + j);
+            d4 xa = {0, 0, 0, 0}, xb = {0, 0, 0, 0}, a = {0, 0, 0, 0}, b = {0, 0, 0, 0};
+            if (NAX >= 1) xa = ld4_stream(va + j);
+            if (NAX == 2) xb = ld4_stream(vb + j);
+            if (NRED == 1 || NRED == 2) a = ld4_stream(ya + j);
+            if (NRED == 2) b = ld4_stream(yb + j);
+            body(wv.x, xa.x, xb.x, a.x, b.x, s0a, s1a, s2a);
+            body(wv.y, xa.y, xb.y, a.y, b.y, s0b, s1b, s2b);
+            body(wv.z, xa.z, xb.z, a.z, b.z, s0a, s1a, s2a);
+            body(wv.w, xa.w, xb.w, a.w, b.w, s0b, s1b, s2b);
+            if (NAX > 0) st4(w + j, wv);
+        }
+        const int64_t j = (n4 << 2) + tid;
+        if (j < n) {
+            double wj = w[j];
+            body(wj, NAX >= 1 ? va[j] : 0.0, NAX == 2 ? vb[j] : 0.0, (NRED == 1 || NRED == 2) ? ya[j] : 0.0,
+                 NRED == 2 ? yb[j] : 0.0, s0a, s1a, s2a);
+            if (NAX > 0) w[j] = wj;
+        }
+    } else {
+        for (int64_t j = tid; j < n; j += nth) {
+            double wj = w[j];
+            body(wj, NAX >= 1 ? va[j] : 0.0, NAX == 2 ? vb[j] : 0.0, (NRED == 1 || NRED == 2) ? ya[j] : 0.0,
+                 NRED == 2 ? yb[j] : 0.0, s0a, s1a, s2a);
+            if (NAX > 0) w[j] = wj;
+        }
+    }
+    if (NRED == 2) {
+        const double r0 = block_sum(s0a + s0b, sh);
+        const double r1 = block_sum(s1a + s1b, sh);
+        const double r2 = block_sum(s2a + s2b, sh);
+        grid_sum_finish3(r0, r1, r2, partials, ticket, blockIdx.x, gridDim.x, out, sh);
+    } else if (NRED != 0) {
+        const double r0 = block_sum(s0a + s0b, sh);
+        grid_sum_finish(r0, partials, ticket, blockIdx.x, gridDim.x, out, sh);
+    }
+}
+
+// va/vb: vectors to subtract (0, 1 or 2 non-null), tin: raw triple of that pair; ya/yb: vectors to project on
+// (0, 1 or 2 non-null); want_sumsq: ||w_new||^2 instead.  out receives 3 doubles (NRED = 2) or 1.
+int launch_mgs_pair(Ctx* ctx, int64_t n, double* w, const double* va, const double* vb, const double* tin,
+                    const double* ya, const double* yb, int want_sumsq, double* out, const int* stop) {
+    if (n <= 0) return AK_OK;
+    const int nax = va ? (vb ? 2 : 1) : 0;
+    const int nred = want_sumsq ? 3 : (ya ? (yb ? 2 : 1) : 0);
+    const bool vec = aligned32(w) && aligned32(va) && aligned32(vb) && aligned32(ya) && aligned32(yb);
+    const int blocks = stream_blocks(ctx, n, 4);
+    const int cls = nax == 2 && nred == 2 ? PK_MGS_PAIR : (nax > 0 ? (nred == 3 ? PK_MGS_AXPY_NRM : PK_MGS_PAIR_EDGE)
+                                                                       : PK_MGS_PAIR_EDGE);
+#define AK_PAIR(A, R)                                                                                              \
+    if (nax == A && nred == R) {                                                                                   \
+        ProfScope prof(ctx, cls);                                                                                  \
+        if (vec)                                                                                                   \
+            k_mgs_pair<A, R, true><<<blocks, kThreads, 0, ctx->stream>>>(w, va, vb, tin, ya, yb, out, ctx->partials, \
+                                                                         ctx->ticket, n, stop);                    \
+        else                                                                                                       \
+            k_mgs_pair<A, R, false><<<blocks, kThreads, 0, ctx->stream>>>(w, va, vb, tin, ya, yb, out,             \
+                                                                          ctx->partials, ctx->ticket, n, stop);    \
+    }
+    AK_PAIR(0, 1) AK_PAIR(0, 2) AK_PAIR(1, 1) AK_PAIR(1, 2) AK_PAIR(1, 3) AK_PAIR(2, 1) AK_PAIR(2, 2) AK_PAIR(2, 3)
+#undef AK_PAIR
+    ctx->launches++;
+    AK_CUDA(cudaGetLastError());
+    if (nred == 2) AK_TRY(allreduce_sum(ctx, out, 3));
+    else if (nred != 0) AK_TRY(allreduce_sum(ctx, out, 1));
+    return AK_OK;
+}
+
 int launch_dot(Ctx* ctx, int64_t n, const double* x, const double* y, double* out_dev) {
     if (n <= 0) return launch_fill(ctx, 1, out_dev, 0.0);
     // <y, x>: w is only read when AXPY == false

@@ -108,4 +108,41 @@ AK_DEV void grid_sum_finish(double block_partial_in_t0, double* partials, unsign
     }
 }
 
+// Three sums at once (pair-wise Gram-Schmidt: <y_a,w>, <y_b,w>, <y_b,y_a>); same ordering rules.
+// partials layout: [3 * bid + c].
+AK_DEV void grid_sum_finish3(double s0, double s1, double s2, double* partials, unsigned int* ticket, int bid,
+                             int nblocks, double* out, double* sh) {
+    __shared__ bool is_last3;
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int nthreads = blockDim.x * blockDim.y;
+    if (tid == 0) {
+        partials[3 * bid + 0] = s0;
+        partials[3 * bid + 1] = s1;
+        partials[3 * bid + 2] = s2;
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last3 = (t == (unsigned int)(nblocks - 1));
+    }
+    __syncthreads();
+    if (is_last3) {
+        __threadfence();
+        double a[3] = {0.0, 0.0, 0.0};
+        for (int i = tid; i < nblocks; i += nthreads) {
+            a[0] += __ldcg(partials + 3 * i + 0);
+            a[1] += __ldcg(partials + 3 * i + 1);
+            a[2] += __ldcg(partials + 3 * i + 2);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double r = block_sum(a[c], sh);
+            if (tid == 0) out[c] = r;
+        }
+        if (tid == 0) *ticket = 0u;
+    }
+}
+
+// h of the second vector of a pair from the raw sums (d1 = <y_a,w>, d2 = <y_b,w>, g = <y_b,y_a>):
+// <y_b, w - d1 y_a> = d2 - d1 g.  One definition shared by the vector kernels and the Givens kernel.
+AK_DEV double pair_second_h(double d1, double d2, double g) { return __dsub_rn(d2, __dmul_rn(d1, g)); }
+
 }  // namespace ak

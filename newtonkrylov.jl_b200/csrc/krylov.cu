@@ -97,14 +97,24 @@ __device__ __forceinline__ double sgn(double x) { return (double)((x > 0.0) - (x
 
 // Krylov.jl sym_givens (real), then the update of iteration k (1-based) — gmres! steps 6-8
 __global__ void k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, double* c, double* s, double* z,
-                               const double* hcol, int reorth, double* hist, int64_t hist_pos, int inner_limit,
-                               KrylovStatus* st) {
+                               const double* hcol, int reorth, int pair, double* hist, int64_t hist_pos,
+                               int inner_limit, KrylovStatus* st) {
     if (threadIdx.x != 0) return;
     if (ctl->stop) return;
     // column k of H: h_1k..h_kk from the MGS sweep(s), h_{k+1,k} = ||q||
-    const double* h2 = hcol + (k + 1);
-    for (int i = 0; i < k; ++i) R[nr + i] = reorth ? hcol[i] + h2[i] : hcol[i];
-    const double Hbis = sqrt(reorth ? h2[k] : hcol[k]);
+    double hh;
+    if (pair) {  // raw triples {<y_a,w>, <y_b,w>, <y_b,y_a>} of the pair-wise sweep, then ||q||^2
+        for (int i = 0; i < k; ++i) {
+            const double* t = hcol + 3 * (i >> 1);
+            R[nr + i] = (i & 1) ? pair_second_h(t[0], t[1], t[2]) : t[0];
+        }
+        hh = hcol[3 * ((k + 1) >> 1)];
+    } else {
+        const double* h2 = hcol + (k + 1);
+        for (int i = 0; i < k; ++i) R[nr + i] = reorth ? hcol[i] + h2[i] : hcol[i];
+        hh = reorth ? h2[k] : hcol[k];
+    }
+    const double Hbis = sqrt(hh);
     for (int i = 0; i + 1 < k; ++i) {
         const double Rt = c[i] * R[nr + i] + s[i] * R[nr + i + 1];
         R[nr + i + 1] = s[i] * R[nr + i] - c[i] * R[nr + i + 1];
@@ -266,7 +276,7 @@ static int ws_grow_scalars(ak_krylov* ws, int64_t kcap_new) {
     AK_TRY(regrow(&ws->c, oldk, kcap_new));
     AK_TRY(regrow(&ws->s, oldk, kcap_new));
     AK_TRY(regrow(&ws->z, oldk ? oldk + 1 : 0, kcap_new + 1));
-    AK_TRY(regrow(&ws->hcol, oldk ? 2 * (oldk + 1) : 0, 2 * (kcap_new + 1)));
+    AK_TRY(regrow(&ws->hcol, oldk ? 2 * (oldk + 1) + 8 : 0, 2 * (kcap_new + 1) + 8));
     ws->kcap = kcap_new;
     return AK_OK;
 }
@@ -341,7 +351,9 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     const int64_t n = ws->n;
     const int mem = ws->mem;
     const int restart = o->restart, reorth = o->reorthogonalization;
-    const int fuse = o->fuse;
+    int fuse = o->fuse;
+    if (fuse == AK_FUSE_PAIR && reorth) fuse = AK_FUSE_FULL;  // the pair-wise sweep has no second-sweep variant
+    const bool pair = (fuse == AK_FUSE_PAIR);
     const bool want_hist = (hist_host != nullptr && hist_cap > 0) || o->history;
     cudaStream_t sm = c->stream;
 
@@ -352,7 +364,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
         if (!ws->dx) AK_TRY(ws_alloc_vec(ws, &ws->dx));
         xr = ws->dx;
     }
-    if (fuse == AK_FUSE_FULL && !ws->w[1]) AK_TRY(ws_alloc_vec(ws, &ws->w[1]));
+    if ((fuse == AK_FUSE_FULL || pair) && !ws->w[1]) AK_TRY(ws_alloc_vec(ws, &ws->w[1]));
     AK_TRY(ws_ensure_basis(ws, mem));
     AK_TRY(ws_grow_scalars(ws, mem));
     if (want_hist) AK_TRY(ws_grow_hist(ws, 257));
@@ -425,20 +437,33 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 JvpFusion jf;
                 jf.stop_flag = stop;
                 double* wout = w;
-                if (fuse == AK_FUSE_FULL) {
+                if (fuse == AK_FUSE_FULL || pair) {
                     if (scale_pending) {
                         jf.scale_src = w;
                         jf.denom_dev = &ws->ctl->Hbis;
                         wi ^= 1;
                         wout = ws->w[wi];
                     }
-                    jf.dot_with = ws->V[0];
-                    jf.dot_dev = hcol;
+                    if (!pair) {
+                        jf.dot_with = ws->V[0];
+                        jf.dot_dev = hcol;
+                    }
                 }
                 AK_TRY(launch_jvp(c, prob, u, ws->V[k - 1], wout, &jf));
                 w = wout;
                 // modified Gram-Schmidt
-                if (fuse == AK_FUSE_NONE) {
+                if (pair) {
+                    // two Gram-Schmidt steps per sweep over w: pass j subtracts pair j-1 and projects on pair j
+                    const int64_t P = (k + 1) / 2;
+                    auto va = [&](int64_t j) -> const double* { return ws->V[2 * j]; };
+                    auto vb = [&](int64_t j) -> const double* { return (2 * j + 1 < k) ? ws->V[2 * j + 1] : nullptr; };
+                    AK_TRY(launch_mgs_pair(c, n, w, nullptr, nullptr, nullptr, va(0), vb(0), 0, hcol, stop));
+                    for (int64_t j = 1; j < P; ++j)
+                        AK_TRY(launch_mgs_pair(c, n, w, va(j - 1), vb(j - 1), hcol + 3 * (j - 1), va(j), vb(j), 0,
+                                               hcol + 3 * j, stop));
+                    AK_TRY(launch_mgs_pair(c, n, w, va(P - 1), vb(P - 1), hcol + 3 * (P - 1), nullptr, nullptr, 1,
+                                           hcol + 3 * P, stop));
+                } else if (fuse == AK_FUSE_NONE) {
                     for (int64_t i = 0; i < k; ++i) {
                         AK_TRY(launch_mgs_step(c, n, w, nullptr, nullptr, ws->V[i], 0, hcol + i, stop));   // h = <V_i, w>
                         AK_TRY(launch_mgs_step(c, n, w, ws->V[i], hcol + i, nullptr, 0, nullptr, stop));   // w -= h V_i
@@ -471,7 +496,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 }
                 const int slot = (int)(k % kStatusRing);
                 { ProfScope prof(c, PK_SCALAR);
-                k_gmres_givens<<<1, 32, 0, sm>>>(ws->ctl, (int)k, nr, ws->R, ws->c, ws->s, ws->z, hcol, reorth,
+                k_gmres_givens<<<1, 32, 0, sm>>>(ws->ctl, (int)k, nr, ws->R, ws->c, ws->s, ws->z, hcol, reorth, pair ? 1 : 0,
                                                  want_hist ? ws->hist : nullptr, iter + k, (int)inner_limit,
                                                  &ws->status[slot]); }
                 c->launches++;
@@ -479,7 +504,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 AK_CUDA(cudaEventRecord(ws->ev[slot], sm));
                 // V[k] <- w / Hbis (skipped on the device when this iteration stopped the pass)
                 if (k < inner_limit) {
-                    if (fuse == AK_FUSE_FULL) scale_pending = true;
+                    if (fuse == AK_FUSE_FULL || pair) scale_pending = true;
                     else AK_TRY(launch_divcopy_dev(c, n, ws->V[k], w, &ws->ctl->Hbis, stop));
                 }
                 // look at the previous iteration's verdict while this one runs

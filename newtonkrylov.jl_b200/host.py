@@ -524,7 +524,7 @@ NewtonResult = namedtuple("NewtonResult", "solved stats t")
 # Krylov workspace: krylov_workspace / krylov_solve!  (src/Ariadne.jl:317-318,338-340,367)
 # ---------------------------------------------------------------------------------------------
 _ALGOS = {"gmres": A.AK_ALGO_GMRES, "cg": A.AK_ALGO_CG}
-_FUSE = {"none": A.AK_FUSE_NONE, "mgs": A.AK_FUSE_MGS, "full": A.AK_FUSE_FULL}
+_FUSE = {"none": A.AK_FUSE_NONE, "mgs": A.AK_FUSE_MGS, "full": A.AK_FUSE_FULL, "pair": A.AK_FUSE_PAIR}
 
 
 class KrylovConstructor:

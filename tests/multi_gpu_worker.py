@@ -61,7 +61,7 @@ def main():
         assert abs(nk.knorm(v.n, v) - np.linalg.norm(v0)) <= 1e-13 * np.linalg.norm(v0)
         # solver level
         if d["kind"] == A.AK_BRATU2D:
-            for fuse in ("none", "mgs", "full"):
+            for fuse in ("none", "mgs", "full", "pair"):
                 u = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
                 hist = []
                 _, r = nk.newton_krylov_native_(F_, u, p, None, history=hist, krylov_kwargs=dict(fuse=fuse))

@@ -44,7 +44,7 @@ ws = nk.krylov_workspace("gmres", nk.KrylovConstructor(res), memory=20)
 J = nk.JacobianOperator(nk.bratu2d_, res, u, (dx, dx, 3.5), coef=coef)
 lib.ak_residual(h, C.byref(prob), P(u), P(res), None)
 b = res.copy()
-for fuse in ("none", "mgs", "full"):
+for fuse in ("none", "mgs", "full", "pair"):
     for _ in range(2):
         ctx.sync(); ctx.launch_count(reset=True)
         ctx.timer_start()
@@ -54,3 +54,28 @@ for fuse in ("none", "mgs", "full"):
     ref_bytes = 2 * 8 * n * (5 * 20 * 21 / 2 + 6 * 20)
     print(f"gmres(20) fuse={fuse:5s} {it} its in {ms:8.2f} ms -> {it/ms*1e3:7.1f} it/s ; reference-op-list traffic {ref_bytes/ms/1e6:8.1f} GB/s "
           f"({ref_bytes/ms/1e6/6552.6*100:5.1f}% of peak); launches {ctx.launch_count()}")
+
+# ---- other BASELINE configs at full size: kernel GB/s (C2 heat 1-D 2^24, C3 heat 2-D 8192^2, C5 DG 2^22 elements)
+import gc
+del ws, J, b; gc.collect()
+un = nk.DeviceVector.from_numpy(u0, ctx)
+F2 = nk.ImplicitResidual(nk.G_Euler_, nk.diffusion_)
+p2 = (un, 1e-9, un.zero(), (0.01, dx, dx, nk.bc_zero_), 0.0)
+pr2 = F2.problem(u, p2)
+timeit("residual heat2d 8192^2", lambda: lib.ak_residual(h, C.byref(pr2), P(u), P(res), None), 24 * n)
+timeit("jvp heat2d 8192^2", lambda: lib.ak_jvp(h, C.byref(pr2), P(u), P(v), P(out)), 16 * n)
+N1 = 1 << 24
+x1 = np.linspace(0.0, 1.0, N1)
+u1 = nk.DeviceVector.from_numpy(4 * x1 * (1 - x1), ctx)
+un1, r1, v1, o1 = u1.copy(), u1.similar(), u1.copy(), u1.similar()
+F1 = nk.ImplicitResidual(nk.G_Euler_, nk.heat_1D_)
+pr1 = F1.problem(u1, (un1, 1e-12, un1.zero(), (0.2, 1.0 / (N1 - 1), nk.bc_zero_), 0.0))
+timeit("residual heat1d 2^24", lambda: lib.ak_residual(h, C.byref(pr1), P(u1), P(r1), None), 24 * N1)
+timeit("jvp heat1d 2^24", lambda: lib.ak_jvp(h, C.byref(pr1), P(u1), P(v1), P(o1)), 16 * N1)
+prb = nk.bratu_.problem(u1, (1.0 / (N1 + 1), 3.5))
+timeit("residual bratu1d 2^24", lambda: lib.ak_residual(h, C.byref(prb), P(u1), P(r1), None), 16 * N1)
+timeit("jvp bratu1d 2^24 (exp)", lambda: lib.ak_jvp(h, C.byref(prb), P(u1), P(v1), P(o1)), 24 * N1)
+Fd = nk.ImplicitResidual(nk.G_Euler_, nk.heat_1D_DG_)
+prd = Fd.problem(u1, (un1, 1e-12, un1.zero(), (4.0 / N1,), 0.0))
+timeit("residual DG 2^22 elements", lambda: lib.ak_residual(h, C.byref(prd), P(u1), P(r1), None), 24 * N1)
+timeit("jvp DG 2^22 elements", lambda: lib.ak_jvp(h, C.byref(prd), P(u1), P(v1), P(o1)), 16 * N1)
