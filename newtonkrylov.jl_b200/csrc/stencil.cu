@@ -23,7 +23,7 @@
 
 namespace ak {
 
-enum { OP_RES_BRATU = 0, OP_JVP_BRATU = 1, OP_RES_HEAT = 2, OP_JVP_HEAT = 3 };
+enum { OP_RES_BRATU = 0, OP_JVP_BRATU = 1, OP_RES_HEAT = 2, OP_JVP_HEAT = 3, OP_RHS_HEAT = 4, OP_JVP_BRATU_FD = 5 };  // RHS: du = f(u) only; FD: (F(u+eps v)-F(u))/eps
 enum { RED_NONE = 0, RED_SUMSQ = 1, RED_DOT = 2 };
 
 struct StencilArgs {
@@ -34,6 +34,7 @@ struct StencilArgs {
     int32_t scheme;      // AK_EULER / AK_MIDPOINT / AK_TRAPEZOID (heat)
     double dx2, dy2, lambda, a, dt;
     double c0, c1;       // JVP_HEAT: out = c1 * L(c0 * v) - v
+    double fd_eps;       // JVP_BRATU_FD
     const double* in;    // u (residual) or v (JVP) or scale_src (fused divcopy)
     const double* lo;    // ghost row y = -1  (nullptr -> 0)
     const double* hi;    // ghost row y = ny  (nullptr -> 0)
@@ -169,6 +170,35 @@ __global__ void __launch_bounds__(kTX) k_stencil2d(const StencilArgs p) {
         return v;
     };
 
+    // second window over u for the fused finite-difference JVP (u + eps v is never materialised)
+    constexpr bool FD = (OP == OP_JVP_BRATU_FD);
+    auto urow_ptr = [&](int64_t y) -> const double* {
+        if (y < 0) return p.aux_lo;
+        if (y >= ny) return p.aux_hi;
+        return p.aux + y * nx;
+    };
+    auto uload = [&](const double* src, double (&r)[VEC]) {
+        if (!active || src == nullptr) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) r[i] = 0.0;
+            return;
+        }
+        ldv<VEC>(src + x0, r);
+    };
+    auto uedge = [&](const double* src, int64_t x) -> double {
+        if (src == nullptr) return 0.0;
+        if (x < 0) { if (!p.wrap_x) return 0.0; x += nx; }
+        else if (x >= nx) { if (!p.wrap_x) return 0.0; x -= nx; }
+        return src[x];
+    };
+    double uprev[FD ? VEC : 1], ucur[FD ? VEC : 1], unext[FD ? VEC : 1];
+    const double* ucur_src = nullptr;
+    if (FD) {
+        ucur_src = urow_ptr(y0);
+        uload(urow_ptr(y0 - 1), reinterpret_cast<double(&)[VEC]>(uprev));
+        uload(ucur_src, reinterpret_cast<double(&)[VEC]>(ucur));
+    }
+
     double prev[VEC], cur[VEC], next[VEC];
     const double* cur_src = row_ptr(y0);
     load_row(row_ptr(y0 - 1), prev);
@@ -180,9 +210,21 @@ __global__ void __launch_bounds__(kTX) k_stencil2d(const StencilArgs p) {
         load_row(next_src, next);
         double left = __shfl_up_sync(0xffffffffu, cur[VEC - 1], 1);
         double right = __shfl_down_sync(0xffffffffu, cur[0], 1);
+        const double* unext_src = nullptr;
+        double uleft = 0.0, uright = 0.0;
+        if (FD) {
+            unext_src = urow_ptr(y + 1);
+            uload(unext_src, reinterpret_cast<double(&)[VEC]>(unext));
+            uleft = __shfl_up_sync(0xffffffffu, ucur[FD ? VEC - 1 : 0], 1);
+            uright = __shfl_down_sync(0xffffffffu, ucur[0], 1);
+        }
         if (active) {
             if (lane == 0) left = edge(cur_src, x0 - 1);
             if (lane == 31 || x0 + VEC >= nx) right = edge(cur_src, x0 + VEC);
+            if (FD) {
+                if (lane == 0) uleft = uedge(ucur_src, x0 - 1);
+                if (lane == 31 || x0 + VEC >= nx) uright = uedge(ucur_src, x0 + VEC);
+            }
             const int64_t off = y * nx + x0;
             double aux[VEC], o[VEC];
             if (OP == OP_JVP_BRATU || OP == OP_RES_HEAT) ldv_s<VEC>(p.aux + off, aux);
@@ -195,7 +237,22 @@ __global__ void __launch_bounds__(kTX) k_stencil2d(const StencilArgs p) {
                 const double xx = second_diff(e, c, w, dx2);
                 const double yy = second_diff(next[i], c, prev[i], dy2);
                 const double lap = __dadd_rn(xx, yy);
-                if (OP == OP_RES_BRATU) {
+                if (FD) {
+                    // J v ~ (F(u + eps v) - F(u)) / eps, both residuals evaluated at this point only
+                    const int iu = FD ? i : 0;
+                    const double eps = p.fd_eps;
+                    const double uc = ucur[iu];
+                    const double uw = (i == 0) ? uleft : ucur[FD ? i - 1 : 0];
+                    const double ue = (i == VEC - 1) ? uright : ucur[FD ? (i + 1) % VEC : 0];
+                    const double un_ = unext[iu], us = uprev[iu];
+                    const double f0 = __dadd_rn(__dadd_rn(second_diff(ue, uc, uw, dx2), second_diff(un_, uc, us, dy2)),
+                                                __dmul_rn(p.lambda, exp(uc)));
+                    const double pc = fma(eps, c, uc), pw = fma(eps, w, uw), pe = fma(eps, e, ue);
+                    const double pn = fma(eps, next[i], un_), ps = fma(eps, prev[i], us);
+                    const double f1 = __dadd_rn(__dadd_rn(second_diff(pe, pc, pw, dx2), second_diff(pn, pc, ps, dy2)),
+                                                __dmul_rn(p.lambda, exp(pc)));
+                    o[i] = __ddiv_rn(__dsub_rn(f1, f0), eps);
+                } else if (OP == OP_RES_BRATU) {
                     cf[i] = __dmul_rn(p.lambda, exp(c));
                     o[i] = __dadd_rn(lap, cf[i]);
                 } else if (OP == OP_JVP_BRATU) {
@@ -204,6 +261,8 @@ __global__ void __launch_bounds__(kTX) k_stencil2d(const StencilArgs p) {
                 } else if (OP == OP_RES_HEAT) {  // G_Euler!: (un + dt*du) - u
                     const double du = __dmul_rn(p.a, lap);
                     o[i] = __dsub_rn(__dadd_rn(aux[i], __dmul_rn(p.dt, du)), c);
+                } else if (OP == OP_RHS_HEAT) {  // du = a * lap (diffusion! alone: heat_2D.jl:53-60)
+                    o[i] = __dmul_rn(p.a, lap);
                 } else {  // OP_JVP_HEAT: c1 * dv - v
                     const double dv = __dmul_rn(p.a, lap);
                     o[i] = __dsub_rn(__dmul_rn(p.c1, dv), c);
@@ -225,6 +284,11 @@ __global__ void __launch_bounds__(kTX) k_stencil2d(const StencilArgs p) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) { prev[i] = cur[i]; cur[i] = next[i]; }
         cur_src = next_src;
+        if (FD) {
+#pragma unroll
+            for (int i = 0; i < (FD ? VEC : 1); ++i) { uprev[i] = ucur[i]; ucur[i] = unext[i]; }
+            ucur_src = unext_src;
+        }
     }
     if (RED != RED_NONE) {
         const double s = block_sum(acc, sh);
@@ -255,7 +319,7 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
     const bool active = x0 < n;
     const Divisor denom = make_divisor(SCALE ? *p.denom : 1.0);
     const Divisor dx2 = make_divisor(p.dx2);
-    constexpr bool HEAT = (OP == OP_RES_HEAT || OP == OP_JVP_HEAT);
+    constexpr bool HEAT = (OP == OP_RES_HEAT || OP == OP_JVP_HEAT || OP == OP_RHS_HEAT);
 
     auto value = [&](int64_t i) -> double {  // scalar access incl. boundary semantics
         double v;
@@ -309,6 +373,7 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
                 const double du =
                     bnd ? 0.0 : div_by(__dmul_rn(p.a, __dadd_rn(__dsub_rn(e, __dmul_rn(2.0, c)), w)), dx2);
                 if (OP == OP_RES_HEAT) o[i] = __dsub_rn(__dadd_rn(aux[i], __dmul_rn(p.dt, du)), c);
+                else if (OP == OP_RHS_HEAT) o[i] = du;
                 else o[i] = __dsub_rn(__dmul_rn(p.c1, du), c);
             }
         }
@@ -347,6 +412,7 @@ struct DgArgs {
     double jac;        // 2/h
     double mw;         // (h/2) * w_edge,  w_edge = 1/6
     double dt, c0, c1;
+    int rhs_only;      // out = D1m*(D1p*in) without the time-discretisation wrapper
     const double* in;
     const double* un;  // residual only
     double* out;
@@ -425,7 +491,10 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
         double du[4], o[4];
         dg_local(p.D, p.jac, t1, du);
         du[0] = __dadd_rn(du[0], div_by(__dsub_rn(t1[0], t_prev3), mw));
-        if (RESIDUAL) {
+        if (p.rhs_only) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = du[i];
+        } else if (RESIDUAL) {
             double un[4];
             ldv_s<4>(p.un + 4 * e, un);
 #pragma unroll
@@ -618,16 +687,16 @@ static int check_problem(const ak_problem* p) {
     if (p->kind == AK_HEAT1D_DG) AK_REQUIRE(p->nx % 4 == 0 && p->nx >= 8, "DG: nx must be 4 * elements, >= 2 elements");
     const bool timedep = (p->kind == AK_HEAT1D || p->kind == AK_HEAT2D || p->kind == AK_HEAT1D_DG);
     if (timedep) {
-        if (p->scheme != AK_EULER) {
-            set_error("scheme %d is not implemented on the device path yet (only AK_EULER)", p->scheme);
-            return AK_ERR_UNSUPPORTED;
-        }
+        AK_REQUIRE(p->scheme == AK_EULER || p->scheme == AK_MIDPOINT || p->scheme == AK_TRAPEZOID,
+                   "time-dependent problems need scheme AK_EULER, AK_MIDPOINT or AK_TRAPEZOID");
     } else {
         AK_REQUIRE(p->scheme == AK_STEADY, "Bratu problems are steady (scheme must be AK_STEADY)");
     }
     if (p->jvp_mode != AK_JVP_ANALYTIC) {
-        set_error("jvp_mode %d is not implemented (only AK_JVP_ANALYTIC)", p->jvp_mode);
-        return AK_ERR_UNSUPPORTED;
+        if (!(p->jvp_mode == AK_JVP_FD_FUSED && p->kind == AK_BRATU2D)) {
+            set_error("jvp_mode %d is only implemented as AK_JVP_FD_FUSED for AK_BRATU2D", p->jvp_mode);
+            return AK_ERR_UNSUPPORTED;
+        }
     }
     return AK_OK;
 }
@@ -645,7 +714,7 @@ static void base_args(Ctx* ctx, const ak_problem* p, StencilArgs& a) {
     a.a = p->a;
     a.dt = p->dt;
     a.c0 = 1.0;
-    a.c1 = p->dt;
+    a.c1 = (p->scheme == AK_TRAPEZOID) ? p->dt / 2.0 : p->dt;  // tangent of G_Trapezoid!: (dt/2) f'(v) - v
     a.partials = ctx->partials;
     a.ticket = ctx->ticket;
 }
@@ -663,9 +732,121 @@ static int ghost_rows(Ctx* ctx, const ak_problem* p, const double* v, const doub
     return AK_OK;
 }
 
+// ---- pieces of the Midpoint / Trapezoid wrappers (examples/implicit.jl:17-37), composed from
+//      the RHS stencil and two point-wise kernels; every rounding point of the Julia broadcasts is kept
+// y = a x + b z          (uu_n .= alpha .* u_n .+ (1 - alpha) .* u        implicit.jl:20)
+__global__ void __launch_bounds__(256) k_lincomb(double* __restrict__ y, double a, const double* __restrict__ x, double b,
+                                                 const double* __restrict__ z, int64_t n) {
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += nth)
+        y[j] = (x != nullptr) ? __dadd_rn(__dmul_rn(a, x[j]), __dmul_rn(b, z[j])) : __dmul_rn(b, z[j]);
+}
+// res = (un + c (d1 [+ d2])) - u     (res .= u_n .+ dt .* du .- u ; u_n .+ (dt/2) .* (du_n .+ du) .- u)
+// JVP form (un == nullptr): out = c d1 - v
+__global__ void __launch_bounds__(256) k_time_combine(double* __restrict__ res, const double* __restrict__ un, double c,
+                                                      const double* d1, const double* d2, const double* u,
+                                                      int64_t n) {
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += nth) {
+        const double d = (d2 != nullptr) ? __dadd_rn(d1[j], d2[j]) : d1[j];
+        const double t = __dmul_rn(c, d);
+        res[j] = (un != nullptr) ? __dsub_rn(__dadd_rn(un[j], t), u[j]) : __dsub_rn(t, u[j]);
+    }
+}
+static int ew_blocks(const Ctx* ctx, int64_t n) {
+    int64_t b = (n + 255) / 256, cap = (int64_t)ctx->num_sms * 8;
+    return (int)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+
+static void dg_constants(DgArgs& d, double h);
+static int launch_dg(Ctx* ctx, DgArgs& d, bool residual, bool scale, int red);
+template <int OP> static int launch1d(Ctx* ctx, StencilArgs& a, bool scale, int red);
+template <int OP> static int launch2d(Ctx* ctx, StencilArgs& a, bool scale, int red);
+static void base_args(Ctx* ctx, const ak_problem* p, StencilArgs& a);
+static int ghost_rows(Ctx* ctx, const ak_problem* p, const double* v, const double** lo, const double** hi);
+
+// du <- f(in): the bare right-hand side of heat_1D!, diffusion! or the DG heat_1D!; `in` may have its
+// boundary entries overwritten by the BC code (1-D heat), exactly like f!(du, u, p, t) in the reference.
+static int launch_rhs(Ctx* ctx, const ak_problem* p, double* in, double* du) {
+    if (p->kind == AK_HEAT1D_DG) {
+        DgArgs d{};
+        dg_constants(d, p->dx);
+        d.ne = p->nx / 4;
+        d.c0 = 1.0; d.c1 = 1.0; d.rhs_only = 1;
+        d.in = in; d.out = du;
+        d.partials = ctx->partials; d.ticket = ctx->ticket;
+        return launch_dg(ctx, d, false, false, RED_NONE);
+    }
+    StencilArgs a;
+    base_args(ctx, p, a);
+    a.in = in;
+    a.out = du;
+    if (p->kind == AK_HEAT1D) {
+        a.in_write = in;
+        return launch1d<OP_RHS_HEAT>(ctx, a, false, RED_NONE);
+    }
+    AK_TRY(ghost_rows(ctx, p, in, &a.lo, &a.hi));
+    return launch2d<OP_RHS_HEAT>(ctx, a, false, RED_NONE);
+}
+
+struct PoolVec {  // stream-ordered scratch vector
+    Ctx* c;
+    double* p = nullptr;
+    PoolVec(Ctx* ctx, int64_t n) : c(ctx) {
+        if (cudaMallocAsync((void**)&p, sizeof(double) * (size_t)(n > 0 ? n : 1), c->stream) != cudaSuccess) p = nullptr;
+    }
+    ~PoolVec() { if (p) cudaFreeAsync(p, c->stream); }
+};
+
+// G_Midpoint! / G_Trapezoid! residuals
+static int launch_residual_composite(Ctx* ctx, const ak_problem* p, double* u, double* res, double* sumsq_dev) {
+    const int64_t n = ak_problem_size(p);
+    AK_REQUIRE(p->un != nullptr, "time-dependent residual needs p->un");
+    PoolVec du(ctx, n), t2(ctx, n);
+    if (!du.p || !t2.p) { set_error("out of device memory for the Midpoint/Trapezoid scratch"); return AK_ERR_NOMEM; }
+    const int blocks = ew_blocks(ctx, n);
+    double* un = const_cast<double*>(p->un);
+    if (p->scheme == AK_MIDPOINT) {
+        const double al = 0.5;  // alpha default of G_Midpoint! (implicit.jl:17)
+        // the reference uses `res` as the temporary uu_n (implicit.jl:18-20); the BC code mutates it, not u
+        k_lincomb<<<blocks, 256, 0, ctx->stream>>>(res, al, un, 1.0 - al, u, n);
+        ctx->launches++;
+        AK_TRY(launch_rhs(ctx, p, res, du.p));
+        k_time_combine<<<blocks, 256, 0, ctx->stream>>>(res, un, p->dt, du.p, nullptr, u, n);
+        ctx->launches++;
+    } else {  // AK_TRAPEZOID (implicit.jl:29-37): f!(du_n, u_n) and f!(du, u) both run their BC code in place
+        AK_TRY(launch_rhs(ctx, p, un, t2.p));
+        AK_TRY(launch_rhs(ctx, p, u, du.p));
+        k_time_combine<<<blocks, 256, 0, ctx->stream>>>(res, un, p->dt / 2.0, t2.p, du.p, u, n);
+        ctx->launches++;
+    }
+    AK_CUDA(cudaGetLastError());
+    if (sumsq_dev) AK_TRY(launch_sumsq(ctx, n, res, sumsq_dev));
+    return AK_OK;
+}
+
+// tangent of G_Midpoint!: out = dt f'((1 - alpha) v) - v ; the BC code acts on the temporary, not on v
+static int launch_jvp_midpoint(Ctx* ctx, const ak_problem* p, double* v, double* out) {
+    const int64_t n = ak_problem_size(p);
+    PoolVec dv(ctx, n);
+    if (!dv.p) { set_error("out of device memory for the Midpoint scratch"); return AK_ERR_NOMEM; }
+    const int blocks = ew_blocks(ctx, n);
+    k_lincomb<<<blocks, 256, 0, ctx->stream>>>(out, 0.0, nullptr, 1.0 - 0.5, v, n);
+    ctx->launches++;
+    AK_TRY(launch_rhs(ctx, p, out, dv.p));
+    k_time_combine<<<blocks, 256, 0, ctx->stream>>>(out, nullptr, p->dt, dv.p, nullptr, v, n);
+    ctx->launches++;
+    AK_CUDA(cudaGetLastError());
+    return AK_OK;
+}
+
 int launch_residual(Ctx* ctx, const ak_problem* p, double* u, double* res, double* sumsq_dev) {
     AK_TRY(check_problem(p));
     ProfScope prof(ctx, PK_RESIDUAL);
+    if (p->scheme == AK_MIDPOINT || p->scheme == AK_TRAPEZOID) {
+        if (ctx->nranks > 1) { set_error("Midpoint/Trapezoid are single-GPU in this version"); return AK_ERR_UNSUPPORTED; }
+        return launch_residual_composite(ctx, p, u, res, sumsq_dev);
+    }
     const int red = sumsq_dev ? RED_SUMSQ : RED_NONE;
     if (p->kind == AK_SIMPLE2) {
         k_simple2<<<1, 32, 0, ctx->stream>>>(u, nullptr, res, sumsq_dev, 0, nullptr, nullptr);
@@ -726,6 +907,18 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     JvpFusion nofuse;
     if (!f) f = &nofuse;
     ProfScope prof(ctx, PK_JVP);
+    if (p->scheme == AK_MIDPOINT) {
+        // composed path: fused normalisation / dot are done as separate launches (same arithmetic)
+        if (ctx->nranks > 1) { set_error("Midpoint is single-GPU in this version"); return AK_ERR_UNSUPPORTED; }
+        const int64_t n = ak_problem_size(p);
+        if (f->stop_flag) {
+            // kernels of the composite path do not read the stop flag; results are discarded by the caller
+        }
+        if (f->scale_src) AK_TRY(launch_divcopy_dev(ctx, n, v, f->scale_src, f->denom_dev, f->stop_flag));
+        AK_TRY(launch_jvp_midpoint(ctx, p, v, out));
+        if (f->dot_with) AK_TRY(launch_mgs_step(ctx, n, out, nullptr, nullptr, f->dot_with, 0, f->dot_dev, f->stop_flag));
+        return AK_OK;
+    }
     const bool scale = f->scale_src != nullptr;
     const int red = f->dot_with ? RED_DOT : RED_NONE;
     if (p->kind == AK_SIMPLE2) {
@@ -739,7 +932,7 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
         DgArgs d{};
         dg_constants(d, p->dx);
         d.ne = p->nx / 4;
-        d.dt = p->dt; d.c0 = 1.0; d.c1 = p->dt;
+        d.dt = p->dt; d.c0 = 1.0; d.c1 = (p->scheme == AK_TRAPEZOID) ? p->dt / 2.0 : p->dt;
         d.in = scale ? f->scale_src : v;
         d.in_write = v; d.denom = f->denom_dev;
         d.out = out; d.dot_with = f->dot_with; d.red_out = f->dot_dev;
@@ -770,6 +963,17 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
             rc = launch1d<OP_JVP_HEAT>(ctx, a, scale, red);
             break;
         case AK_BRATU2D:
+            if (p->jvp_mode == AK_JVP_FD_FUSED) {
+                // north_star (2): one pass reads u and v and writes J v ~ (F(u + eps v) - F(u)) / eps
+                if (ctx->nranks > 1) { set_error("AK_JVP_FD_FUSED is single-GPU in this version"); return AK_ERR_UNSUPPORTED; }
+                AK_REQUIRE(u != nullptr, "AK_JVP_FD_FUSED needs u");
+                AK_TRY(ghost_rows(ctx, p, a.in, &a.lo, &a.hi));
+                a.aux = u;
+                AK_TRY(ghost_rows(ctx, p, u, &a.aux_lo, &a.aux_hi));
+                a.fd_eps = p->fd_eps > 0.0 ? p->fd_eps : 1.4901161193847656e-08;
+                rc = launch2d<OP_JVP_BRATU_FD>(ctx, a, scale, red);
+                break;
+            }
             AK_TRY(ghost_rows(ctx, p, a.in, &a.lo, &a.hi));
             a.aux = p->coef ? p->coef : u;
             a.coef_from_u = p->coef ? 0 : 1;

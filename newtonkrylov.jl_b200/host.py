@@ -406,11 +406,14 @@ class JacobianOperator:
     """Matrix-free J(u) of a native residual.  Aliases f, res, u, p (never copies) like the
     reference constructor (src/Ariadne.jl:39-41)."""
 
-    def __init__(self, f, res, u, p, coef=None):
+    def __init__(self, f, res, u, p, coef=None, jvp_mode="analytic", fd_eps=0.0):
         if not isinstance(f, NativeResidual):
             raise TypeError("JacobianOperator needs a native residual (no Enzyme / no CPU fallback on this path)")
         self.f, self.res, self.u, self.p = f, res, u, p
         self.coef = coef  # lambda*exp(u) cached by the last residual evaluation at this u (Bratu), or None
+        # "analytic": exact tangent (what the reference's Enzyme forward mode computes, default);
+        # "fd": fused (F(u + eps v) - F(u)) / eps in one pass (BASELINE north_star wording; O(1e-8) error)
+        self.jvp_mode, self.fd_eps = jvp_mode, float(fd_eps)
 
     def size(self):  # src/Ariadne.jl:44
         return (len(self.res), len(self.u))
@@ -427,7 +430,10 @@ class JacobianOperator:
         return m * n
 
     def problem(self):
-        return self.f.problem(self.u, self.p, coef=self.coef)
+        prob = self.f.problem(self.u, self.p, coef=self.coef)
+        if self.jvp_mode == "fd":
+            prob.jvp_mode, prob.fd_eps = A.AK_JVP_FD_FUSED, self.fd_eps
+        return prob
 
     @property
     def T(self):
@@ -600,7 +606,8 @@ def krylov_solve_(workspace, J, b, atol=A.SQRT_EPS, rtol=A.SQRT_EPS, itmax=0, re
 # ---------------------------------------------------------------------------------------------
 def newton_krylov_(F_, u, p=None, res=None, *, tol_rel=1.0e-6, tol_abs=1.0e-12, max_niter=50,
                    forcing=EisenstatWalker(), verbose=0, algo="gmres", M=None, N=None, krylov_kwargs=None,
-                   callback=lambda *args: None, memory=20, max_basis=0, history=None, workspace=None):
+                   callback=lambda *args: None, memory=20, max_basis=0, history=None, workspace=None,
+                   jvp_mode="analytic"):
     """Newton loop driven from the host language, one C-ABI call per arrowed line of
     src/Ariadne.jl:288-372.  Returns `(u, NewtonResult(solved, stats, t))`.
 
@@ -631,7 +638,7 @@ def newton_krylov_(F_, u, p=None, res=None, *, tol_rel=1.0e-6, tol_abs=1.0e-12, 
     eta = inital(forcing) if forcing is not None else None   # :308-310
     if verbose > 0:
         print(f"[ Info: Jacobian-Free Newton-Krylov algo={algo} res0={n_res} tol={tol} eta={eta}")
-    J = JacobianOperator(F_, res, u, p, coef=coef)           # :314
+    J = JacobianOperator(F_, res, u, p, coef=coef, jvp_mode=jvp_mode)  # :314
     if workspace is None:
         workspace = krylov_workspace(algo, KrylovConstructor(res), memory=memory, max_basis=max_basis)  # :317-318
     rhs = res.similar()

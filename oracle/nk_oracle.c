@@ -334,10 +334,8 @@ OK_EXPORT void ok_residual(const ak_problem* p, double* u, double* res) {
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < n; ++i) res[i] = (un[i] + dt * du[i]) - u[i];
     } else if (p->scheme == AK_TRAPEZOID) { /* G_Trapezoid!: implicit.jl:29-37 */
-        double* un_mut = ok_alloc(n); /* f!(du_n, u_n): BC mutation would land on u_n; values already satisfy it */
-        memcpy(un_mut, un, sizeof(double) * (size_t)n);
-        rhs_linear(p, res, un_mut, tmp);
-        free(un_mut);
+        /* f!(du_n, u_n, p, t) with du_n === res: the BC code of f! mutates u_n in place, like the reference */
+        rhs_linear(p, res, (double*)un, tmp);
         rhs_linear(p, du, u, tmp);
         const double h = dt / 2.0;
 #pragma omp parallel for schedule(static)

@@ -82,6 +82,38 @@ def test_jvp_matches_oracle(nk, ctx, oracle, name, make):
     assert np.array_equal(v.numpy(), v_after)
 
 
+SCHEME_CASES = [(nm, mk, sc) for nm, mk in [("heat1d", lambda: P.heat1d(50)), ("heat1d_periodic", lambda: P.heat1d(33, bc=A.AK_BC_PERIODIC)),
+                                              ("heat2d", lambda: P.heat2d(24, ic="poly")),
+                                              ("heat2d_periodic", lambda: P.heat2d(20, bc=A.AK_BC_PERIODIC, ic="poly")),
+                                              ("dg", lambda: P.heat1d_dg(19))]
+                for sc in (A.AK_MIDPOINT, A.AK_TRAPEZOID)]
+
+
+@pytest.mark.parametrize("name,make,scheme", SCHEME_CASES, ids=[f"{c[0]}-{'midpoint' if c[2] == A.AK_MIDPOINT else 'trapezoid'}" for c in SCHEME_CASES])
+def test_midpoint_trapezoid_match_oracle(nk, ctx, oracle, name, make, scheme):
+    """G_Midpoint! / G_Trapezoid! (examples/implicit.jl:17-37): residual, tangent and their BC side effects,
+    bit for bit (no transcendental functions involved)."""
+    d = dict(make(), scheme=scheme)
+    G_ = nk.G_Midpoint_ if scheme == A.AK_MIDPOINT else nk.G_Trapezoid_
+    u0 = d["u0"] + 0.01 * RNG.standard_normal(d["u0"].shape)
+    un0 = d["u0"] * 0.9 + 0.05
+    F_e, u, p, un = P.device_setup(nk, ctx, dict(d, u0=u0))
+    F_ = nk.ImplicitResidual(G_, F_e.f_)
+    un.set(un0)
+    res = u.zero()
+    F_(res, u, p)
+    po = P.oracle_problem(oracle, d, un=un0)
+    ref, u_after = oracle.residual(po, u0)
+    assert np.array_equal(res.numpy(), ref), P.ulp_diff(res.numpy(), ref)
+    assert np.array_equal(u.numpy(), u_after)
+    assert np.array_equal(un.numpy(), po._keep)  # Trapezoid: f!(du_n, u_n) runs its BC code on u_n in place
+    v0 = RNG.standard_normal(d["u0"].shape)
+    v, out = nk.DeviceVector.from_numpy(v0, ctx), u.zero()
+    nk.mul_(out, nk.JacobianOperator(F_, res, u, p), v)
+    refj, v_after = oracle.jvp(po, u0, v0)
+    assert np.array_equal(out.numpy(), refj) and np.array_equal(v.numpy(), v_after)
+
+
 def test_jvp_with_cached_coefficient_equals_recomputed(nk, ctx):
     """Bratu: JVP reading lambda*exp(u) cached by ak_residual == JVP recomputing exp(u)."""
     for d in (P.bratu1d(513), P.bratu2d(96, 40)):
@@ -198,3 +230,36 @@ def test_linearity_and_symmetry_large(nk, ctx):
     nk.mul_(Jw, J, w)
     a, b = nk.kdot(n, w, Jv), nk.kdot(n, v, Jw)
     assert a == pytest.approx(b, rel=1e-11)
+
+
+def test_fused_finite_difference_jvp(nk, ctx, oracle):
+    """AK_JVP_FD_FUSED (north_star item 2): (F(u + eps v) - F(u)) / eps in one pass that reads u and v and never
+    materialises u + eps v.  It approximates the exact tangent to O(eps |F''| + eps_mach |F| / eps) ~ 1e-7 relative
+    — which is why the analytic tangent, not this mode, is the parity path."""
+    for d in (P.bratu2d(64), P.bratu2d(130, 37), P.bratu2d(33, 31)):
+        F_, u, p, _ = P.device_setup(nk, ctx, d)
+        res = u.zero()
+        v0 = RNG.standard_normal(d["u0"].shape)
+        v0 /= np.linalg.norm(v0)
+        v = nk.DeviceVector.from_numpy(v0, ctx)
+        exact, fd = u.zero(), u.zero()
+        nk.mul_(exact, nk.JacobianOperator(F_, res, u, p), v)
+        nk.mul_(fd, nk.JacobianOperator(F_, res, u, p, jvp_mode="fd"), v)
+        e, f = exact.numpy(), fd.numpy()
+        assert 1e-12 < np.linalg.norm(f - e) / np.linalg.norm(e) < 1e-5
+        # the same finite difference formed from two oracle residuals agrees to rounding of the difference
+        po = P.oracle_problem(oracle, d)
+        eps = 1.4901161193847656e-08
+        f1, _ = oracle.residual(po, d["u0"] + eps * v0)
+        f0, _ = oracle.residual(po, d["u0"])
+        ref = (f1 - f0) / eps
+        assert np.linalg.norm(f - ref) / np.linalg.norm(ref) < 1e-6
+    # Newton with the FD operator converges in the same number of steps (histories agree to ~1e-6 only)
+    d = P.generic(P.bratu2d(32))
+    F_, u, p, _ = P.device_setup(nk, ctx, d)
+    h_fd, h_ex = [], []
+    _, r_fd = nk.newton_krylov_(F_, u, p, None, history=h_fd, jvp_mode="fd")
+    F_, u2, p, _ = P.device_setup(nk, ctx, d)
+    _, r_ex = nk.newton_krylov_(F_, u2, p, None, history=h_ex)
+    assert r_fd.solved and r_fd.stats.outer_iterations == r_ex.stats.outer_iterations
+    assert np.linalg.norm(u.numpy() - u2.numpy()) / np.linalg.norm(u2.numpy()) < 1e-6

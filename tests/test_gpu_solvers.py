@@ -242,6 +242,11 @@ def test_bratu1d_analytic_solution(nk, ctx):
 
 IMPLICIT_CASES = [
     ("heat1d", lambda: P.heat1d(100), 3, {}),
+    ("heat1d_midpoint", lambda: dict(P.heat1d(100), scheme=A.AK_MIDPOINT), 2, {}),
+    ("heat1d_trapezoid", lambda: dict(P.heat1d(100), scheme=A.AK_TRAPEZOID), 2, {}),
+    ("heat2d_midpoint", lambda: dict(P.heat2d(30, dt_scale=64.0, ic="poly"), scheme=A.AK_MIDPOINT), 2, {}),
+    ("heat2d_trapezoid", lambda: dict(P.heat2d(30, dt_scale=64.0, ic="poly"), scheme=A.AK_TRAPEZOID), 2, {}),
+    ("dg_trapezoid", lambda: dict(P.heat1d_dg(32, dt=1e-3), scheme=A.AK_TRAPEZOID), 2, {}),
     ("heat2d_reference_ic", lambda: P.heat2d(40), 3, dict(reorthogonalization=True)),
     # (N = 32 puts the last GMRES solve of step 3 within rounding of its tolerance: 41 vs 42 iterations
     #  depending on summation order — N = 30 has no such knife edge)
@@ -284,12 +289,13 @@ def test_implicit_time_stepping_matches_oracle(nk, ctx, oracle, name, make, nste
     F_, u, p, un = P.device_setup(nk, ctx, d)
     stats = []
     ts = [i * d["dt"] for i in range(nsteps + 1)]
-    nk.solve(nk.G_Euler_, F_.f_, un, p[3], d["dt"], ts, krylov_kwargs=kk, step_stats=stats)
+    G_ = {A.AK_EULER: nk.G_Euler_, A.AK_MIDPOINT: nk.G_Midpoint_, A.AK_TRAPEZOID: nk.G_Trapezoid_}[d["scheme"]]
+    nk.solve(G_, F_.f_, un, p[3], d["dt"], ts, krylov_kwargs=kk, step_stats=stats)
     check([s.stats.outer_iterations for s in stats], [s.stats.inner_iterations for s in stats],
           [s.solved for s in stats], un.numpy())
     # (b) the single C entry point ak_implicit_solve
     F_, u, p, un = P.device_setup(nk, ctx, d)
-    prob = F_.problem(u, p)
+    prob = nk.ImplicitResidual(G_, F_.f_).problem(u, p)
     newt = np.zeros(nsteps, dtype=np.int32)
     inner = np.zeros(nsteps, dtype=np.int64)
     solved = np.zeros(nsteps, dtype=np.int32)
@@ -322,7 +328,9 @@ def test_errors_are_loud(nk, ctx):
     with pytest.raises(nk.AriadneError):  # DG needs >= 2 elements of 4 nodes
         nk.ImplicitResidual(nk.G_Euler_, nk.heat_1D_DG_)(u.zero(), nk.DeviceVector.from_numpy(np.zeros(6), ctx),
                                                         (u, 0.1, u.zero(), (0.5,), 0.0))
-    with pytest.raises(nk.AriadneError):  # midpoint is not on the device path yet: fails, never falls back
-        nk.ImplicitResidual(nk.G_Midpoint_, nk.heat_1D_)(u.zero(), u, (u, 0.1, u.zero(), (0.2, 0.1, nk.bc_zero_), 0.0))
+    with pytest.raises(nk.AriadneError):  # Bratu problems are steady: a time scheme is a usage error, not a fallback
+        prob = nk.bratu_.problem(u, (0.1, 1.0))
+        prob.scheme = A.AK_EULER
+        nk._lib.check(ctx.lib.ak_residual(ctx.h, C.byref(prob), C.c_void_p(u.ptr), C.c_void_p(u.zero().ptr), None))
     with pytest.raises(TypeError):
         nk.JacobianOperator(lambda res, u, p: None, u, u, None)
