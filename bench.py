@@ -19,8 +19,9 @@ e2e    = the same metric through the host-buffer entry point ak_newton_solve_hos
          caller holding an Array{Float64} calls): every step copies u host->device from pinned
          memory, allocates the Krylov workspace like the reference does per newton_krylov! call,
          runs the same Newton step and copies u back.
-roofline = the dominant kernel (fused axpy_i + dot_{i+1} modified-Gram-Schmidt step, 32n bytes per
-         launch) timed live with CUDA events inside the timed region (library profiler).
+roofline = the dominant kernel (pair-wise modified-Gram-Schmidt pass, 48n bytes per launch = 24n per
+         Gram-Schmidt step; with --fuse mgs/full the axpy_i + dot_{i+1} kernel, 32n) timed live with CUDA events
+         inside the timed region (library profiler); traffic from the committed ncu --set full capture.
 cpu_baseline = the CPU oracle (oracle/nk_oracle.c, a port of the reference algorithm) on the host
          cores, one GMRES(20) restart cycle of the same solve.
 
@@ -299,13 +300,20 @@ def main():
         dom, dom_bytes = 0, 32 * n
         dom_name = "k_mgs_step<AXPY,DOT> (w -= h_i v_i ; h_{i+1} = <v_{i+1}, w>)"
     cnt, kms = prof[dom]
+    traffic = None  # dram bytes per launch of the dominant kernel from the committed ncu --set full capture
+    try:
+        kt = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json"))).get(args.fuse)
+        if kt and kt["n"] == n:
+            traffic = kt["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = None
     if cnt:
         achieved = dom_bytes / (kms / cnt * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom_name,
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-                    "avg_launch_ms": kms / cnt, "launches_timed": cnt, "traffic": None,
+                    "avg_launch_ms": kms / cnt, "launches_timed": cnt, "traffic": traffic,
                     "kernel_share_of_step": share}
     # per-iteration view against the reference op list  B(k) = 8n(5k+6)
     ref_bytes = sum(8.0 * n * (5 * k + 6) for k in range(1, MEMORY + 1)) * (ITMAX // MEMORY) * args.steps
