@@ -148,6 +148,13 @@ int ak_halo_unpack(ak_ctx* ctx, double* padded, const double* compact, int64_t n
  * stencil exchanges one halo row with rank-1 / rank+1 (slab decomposition along y). */
 int ak_comm_unique_id(char id_out[128]);
 int ak_comm_init(ak_ctx* ctx, int nranks, int rank, const char id[128]);
+/* NVLink peer memory for the fused compute + collective kernels of the pair-wise GMRES sweep:
+ * every rank exports one block through CUDA IPC (handles travel in an NCCL all-gather); the
+ * Gram-Schmidt kernels then deposit their partial sums directly in the peers' mailboxes and push
+ * their boundary rows into the neighbours' ghost rows (st.global over NVLink), so a restart cycle
+ * issues no NCCL call.  `halo_doubles` >= nx of the widest 2-D problem.  Collective call.     */
+int ak_comm_enable_p2p(ak_ctx* ctx, int64_t halo_doubles);
+int ak_comm_p2p_enabled(ak_ctx* ctx);
 int ak_comm_rank(ak_ctx* ctx, int* rank, int* nranks);
 int ak_comm_barrier(ak_ctx* ctx);
 /* ---- residual callback  F!(res,u,p): src/Ariadne.jl:250-256,302,349 --------- */

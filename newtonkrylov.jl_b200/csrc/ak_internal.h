@@ -38,6 +38,25 @@ void set_error(const char* fmt, ...);
         }                                                              \
     } while (0)
 
+// ---- NVLink peer memory (CUDA IPC) for the fused compute + collective kernels -----------------
+// One cudaMalloc'ed block per rank, mapped into every other rank of the node:
+//   mail : kMailSlots x nranks records {v0, v1, v2, tag}   — partial sums written by peer kernels
+//   halo : 2 parities x {lo, hi} x halo_cap doubles       — boundary rows pushed by the neighbours
+constexpr int kMaxPeers = 8;
+constexpr int kMailSlots = 8;
+struct P2PDev {           // passed by value to kernels
+    int nranks, rank;
+    double* mail_local;                 // this rank's mailbox
+    double* mail_peer[kMaxPeers];       // everybody's mailbox (index = rank; [rank] == mail_local)
+    int* err;                           // mapped host flag: set when a spin-wait times out
+    long long spin_cycles;              // time-out
+};
+struct P2PHalo {          // boundary-row push of the final Gram-Schmidt pass
+    double* down_hi;      // neighbour (rank-1)'s "hi" ghost row for this parity, or nullptr
+    double* up_lo;        // neighbour (rank+1)'s "lo" ghost row for this parity, or nullptr
+    int64_t nx;
+};
+
 // Upper bound on blocks of any reduction kernel (size of the partials buffer).
 constexpr int kMaxPartials = 1 << 16;
 constexpr int kNumSMsDefault = 148;
@@ -86,6 +105,16 @@ struct Ctx {
     double* halo_hi = nullptr;      // nx doubles: row gy0+ny (from rank+1)
     double* halo_send = nullptr;
     int64_t halo_cap = 0;
+    // peer memory (ak_comm_enable_p2p)
+    bool p2p_on = false;
+    double* p2p_block = nullptr;                 // local IPC-exported block
+    void* p2p_peer_block[kMaxPeers] = {};         // mapped blocks of the other ranks
+    int64_t p2p_halo_cap = 0;                    // doubles per ghost row
+    int* p2p_err = nullptr;                      // pinned, mapped
+    uint64_t p2p_seq = 0;                        // collective sequence number (identical on all ranks)
+    P2PDev p2p_dev() const;
+    double* p2p_halo_local(int parity, int hi) const;              // this rank's ghost rows
+    double* p2p_halo_of(int peer, int parity, int hi) const;       // a neighbour's ghost rows (mapped)
 };
 
 // RAII: brackets one kernel launch with events when the profiler is on (context.cu)
@@ -124,9 +153,16 @@ int launch_divcopy_dev(Ctx* ctx, int64_t n, double* y, const double* x, const do
 // `stop_flag` (device int, may be null): kernel is a no-op when *stop_flag != 0.
 int launch_mgs_step(Ctx* ctx, int64_t n, double* w, const double* vi, const double* h_in,
                     const double* vnext, int want_sumsq, double* out_dev, const int* stop_flag);
-// Pair-wise Gram-Schmidt pass (see blas1.cu)
+// Pair-wise Gram-Schmidt pass (see blas1.cu).  `pc` (may be null) routes the reduction through the peers'
+// mailboxes (NVLink) instead of NCCL and lets the final pass push its boundary rows to the neighbours.
+struct PairComm {
+    unsigned long long seq_in = 0, seq_out = 0;
+    double* tin_store = nullptr;
+    P2PHalo halo = {nullptr, nullptr, 0};
+};
 int launch_mgs_pair(Ctx* ctx, int64_t n, double* w, const double* va, const double* vb, const double* tin,
-                    const double* ya, const double* yb, int want_sumsq, double* out, const int* stop);
+                    const double* ya, const double* yb, int want_sumsq, double* out, const int* stop,
+                    const PairComm* pc);
 // x <- x + sum_i y[i] V[i]  (sequential axpy order), optionally u <- u - x fused (single pass)
 int launch_basis_combine(Ctx* ctx, int64_t n, double* x, const double* const* V_dev, const double* y_dev,
                          int k, int zero_x_first);
@@ -142,6 +178,10 @@ struct JvpFusion {
     const double* dot_with = nullptr;   // V[0]
     double* dot_dev = nullptr;
     const int* stop_flag = nullptr;
+    // ghost rows already delivered by the neighbours through peer memory (skips the NCCL exchange)
+    bool halo_given = false;
+    const double* halo_lo = nullptr;
+    const double* halo_hi = nullptr;
 };
 int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double* out, const JvpFusion* f);
 int launch_jvp_transpose(Ctx* ctx, const ak_problem* p, const double* u, double* v, double* out);

@@ -149,23 +149,43 @@ int launch_mgs_step(Ctx* ctx, int64_t n, double* w, const double* vi, const doub
 // Algorithmic bytes per launch: 8n (2 [w in/out] + NAX + number of y vectors); 48n for NAX = NRED = 2,
 // i.e. 24n per Gram-Schmidt step instead of 32n.
 // -----------------------------------------------------------------------------------
-template <int NAX, int NRED, bool VEC>
+struct PairP2P {      // fused collective of the pair-wise pass (all zero / null when not used)
+    P2PDev pd;
+    unsigned long long seq_in;   // record to wait for (reduced sums of the pair being subtracted), 0 = read `tin`
+    unsigned long long seq_out;  // record to post (this pass's sums), 0 = store to `out`
+    double* tin_store;           // where block 0 leaves the reduced incoming sums for the Givens kernel
+    P2PHalo halo;                // boundary-row push (final pass only)
+};
+
+template <int NAX, int NRED, bool VEC, bool P2P>
 __global__ void __launch_bounds__(kThreads) k_mgs_pair(double* __restrict__ w, const double* __restrict__ va,
                                                        const double* __restrict__ vb, const double* __restrict__ tin,
                                                        const double* __restrict__ ya, const double* __restrict__ yb,
                                                        double* __restrict__ out, double* __restrict__ partials,
-                                                       unsigned int* ticket, int64_t n, const int* __restrict__ stop) {
+                                                       unsigned int* ticket, int64_t n, const int* __restrict__ stop,
+                                                       const PairP2P pp) {
     __shared__ double sh[32];
+    __shared__ double sh4[4 * kMaxPeers];
     if (stop != nullptr && *stop != 0) return;
     double ha = 0.0, hb = 0.0;
     if (NAX >= 1) {
-        const double d1 = tin[0];
-        ha = -d1;
-        if (NAX == 2) hb = -pair_second_h(d1, tin[1], tin[2]);
+        double t[3];
+        if (P2P && pp.seq_in != 0) {
+            mail_wait_sum(pp.pd, pp.seq_in, t, sh4);
+            if (blockIdx.x == 0 && threadIdx.x == 0 && pp.tin_store != nullptr) {
+                pp.tin_store[0] = t[0]; pp.tin_store[1] = t[1]; pp.tin_store[2] = t[2];
+            }
+        } else {
+            t[0] = tin[0]; t[1] = (NAX == 2) ? tin[1] : 0.0; t[2] = (NAX == 2) ? tin[2] : 0.0;
+        }
+        ha = -t[0];
+        if (NAX == 2) hb = -pair_second_h(t[0], t[1], t[2]);
     }
     double s0a = 0.0, s0b = 0.0, s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    const bool push = P2P && NRED == 3 && (pp.halo.down_hi != nullptr || pp.halo.up_lo != nullptr);
+    const int64_t hnx = pp.halo.nx;
     auto body = [&](double& wj, double xa, double xb, double a, double b, double& t0, double& t1, double& t2) {
         if (NAX >= 1) wj = fma(ha, xa, wj);   // same order as two successive kaxpy!
         if (NAX == 2) wj = fma(hb, xb, wj);
@@ -188,6 +208,10 @@ __global__ void __launch_bounds__(kThreads) k_mgs_pair(double* __restrict__ w, c
             body(wv.z, xa.z, xb.z, a.z, b.z, s0a, s1a, s2a);
             body(wv.w, xa.w, xb.w, a.w, b.w, s0b, s1b, s2b);
             if (NAX > 0) st4(w + j, wv);
+            if (push) {  // boundary rows of the finished w go straight into the neighbours' ghost rows (NVLink)
+                if (pp.halo.down_hi != nullptr && j < hnx) st4(pp.halo.down_hi + j, wv);
+                if (pp.halo.up_lo != nullptr && j >= n - hnx) st4(pp.halo.up_lo + (j - (n - hnx)), wv);
+            }
         }
         const int64_t j = (n4 << 2) + tid;
         if (j < n) {
@@ -204,7 +228,14 @@ __global__ void __launch_bounds__(kThreads) k_mgs_pair(double* __restrict__ w, c
             if (NAX > 0) w[j] = wj;
         }
     }
-    if (NRED == 2) {
+    if (P2P && pp.seq_out != 0) {
+        const double r0 = block_sum(s0a + s0b, sh);
+        const double r1 = (NRED == 2) ? block_sum(s1a + s1b, sh) : 0.0;
+        const double r2 = (NRED == 2) ? block_sum(s2a + s2b, sh) : 0.0;
+        double tot[3];
+        if (grid_reduce3(r0, r1, r2, partials, ticket, blockIdx.x, gridDim.x, sh, tot, push))
+            mail_post(pp.pd, pp.seq_out, tot[0], tot[1], tot[2]);
+    } else if (NRED == 2) {
         const double r0 = block_sum(s0a + s0b, sh);
         const double r1 = block_sum(s1a + s1b, sh);
         const double r2 = block_sum(s2a + s2b, sh);
@@ -217,8 +248,10 @@ __global__ void __launch_bounds__(kThreads) k_mgs_pair(double* __restrict__ w, c
 
 // va/vb: vectors to subtract (0, 1 or 2 non-null), tin: raw triple of that pair; ya/yb: vectors to project on
 // (0, 1 or 2 non-null); want_sumsq: ||w_new||^2 instead.  out receives 3 doubles (NRED = 2) or 1.
+// With `p2p` (multi-GPU, peer memory enabled) the sums travel through the peers' mailboxes instead of NCCL.
 int launch_mgs_pair(Ctx* ctx, int64_t n, double* w, const double* va, const double* vb, const double* tin,
-                    const double* ya, const double* yb, int want_sumsq, double* out, const int* stop) {
+                    const double* ya, const double* yb, int want_sumsq, double* out, const int* stop,
+                    const PairComm* pc) {
     if (n <= 0) return AK_OK;
     const int nax = va ? (vb ? 2 : 1) : 0;
     const int nred = want_sumsq ? 3 : (ya ? (yb ? 2 : 1) : 0);
@@ -226,22 +259,41 @@ int launch_mgs_pair(Ctx* ctx, int64_t n, double* w, const double* va, const doub
     const int blocks = stream_blocks(ctx, n, 4);
     const int cls = nax == 2 && nred == 2 ? PK_MGS_PAIR : (nax > 0 ? (nred == 3 ? PK_MGS_AXPY_NRM : PK_MGS_PAIR_EDGE)
                                                                        : PK_MGS_PAIR_EDGE);
-#define AK_PAIR(A, R)                                                                                              \
-    if (nax == A && nred == R) {                                                                                   \
-        ProfScope prof(ctx, cls);                                                                                  \
-        if (vec)                                                                                                   \
-            k_mgs_pair<A, R, true><<<blocks, kThreads, 0, ctx->stream>>>(w, va, vb, tin, ya, yb, out, ctx->partials, \
-                                                                         ctx->ticket, n, stop);                    \
-        else                                                                                                       \
-            k_mgs_pair<A, R, false><<<blocks, kThreads, 0, ctx->stream>>>(w, va, vb, tin, ya, yb, out,             \
-                                                                          ctx->partials, ctx->ticket, n, stop);    \
+    const bool p2p = pc != nullptr && ctx->p2p_on && ctx->nranks > 1;
+    PairP2P pp{};
+    if (p2p) {
+        pp.pd = ctx->p2p_dev();
+        pp.seq_in = pc->seq_in;
+        pp.seq_out = pc->seq_out;
+        pp.tin_store = pc->tin_store;
+        pp.halo = pc->halo;
+        // the vector path pushes whole 256-bit words: rows must be 32-byte multiples
+        if (pp.halo.nx % 4 != 0 || n % 4 != 0 || !vec) pp.halo.down_hi = pp.halo.up_lo = nullptr;
+    }
+#define AK_PAIR(A, R)                                                                                               \
+    if (nax == A && nred == R) {                                                                                    \
+        ProfScope prof(ctx, cls);                                                                                   \
+        if (p2p && vec)                                                                                             \
+            k_mgs_pair<A, R, true, true><<<blocks, kThreads, 0, ctx->stream>>>(w, va, vb, tin, ya, yb, out,        \
+                                                                               ctx->partials, ctx->ticket, n, stop, pp); \
+        else if (p2p)                                                                                               \
+            k_mgs_pair<A, R, false, true><<<blocks, kThreads, 0, ctx->stream>>>(w, va, vb, tin, ya, yb, out,       \
+                                                                                ctx->partials, ctx->ticket, n, stop, pp); \
+        else if (vec)                                                                                               \
+            k_mgs_pair<A, R, true, false><<<blocks, kThreads, 0, ctx->stream>>>(w, va, vb, tin, ya, yb, out,       \
+                                                                                ctx->partials, ctx->ticket, n, stop, pp); \
+        else                                                                                                        \
+            k_mgs_pair<A, R, false, false><<<blocks, kThreads, 0, ctx->stream>>>(w, va, vb, tin, ya, yb, out,      \
+                                                                                 ctx->partials, ctx->ticket, n, stop, pp); \
     }
     AK_PAIR(0, 1) AK_PAIR(0, 2) AK_PAIR(1, 1) AK_PAIR(1, 2) AK_PAIR(1, 3) AK_PAIR(2, 1) AK_PAIR(2, 2) AK_PAIR(2, 3)
 #undef AK_PAIR
     ctx->launches++;
     AK_CUDA(cudaGetLastError());
-    if (nred == 2) AK_TRY(allreduce_sum(ctx, out, 3));
-    else if (nred != 0) AK_TRY(allreduce_sum(ctx, out, 1));
+    if (!p2p) {
+        if (nred == 2) AK_TRY(allreduce_sum(ctx, out, 3));
+        else if (nred != 0) AK_TRY(allreduce_sum(ctx, out, 1));
+    }
     return AK_OK;
 }
 

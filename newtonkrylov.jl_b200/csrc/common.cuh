@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ak_internal.h"
+
 #define AK_DEV __device__ __forceinline__
 
 namespace ak {
@@ -139,6 +141,93 @@ AK_DEV void grid_sum_finish3(double s0, double s1, double s2, double* partials, 
         }
         if (tid == 0) *ticket = 0u;
     }
+}
+
+// Same, but the three totals are handed back to flat thread 0 of the last block (returns true there only),
+// so that the caller decides where they go (device memory, or the peers' mailboxes over NVLink).
+// `sysfence`: the block also issued stores to peer memory that must be visible before the result is published.
+AK_DEV bool grid_reduce3(double s0, double s1, double s2, double* partials, unsigned int* ticket, int bid, int nblocks,
+                         double* sh, double (&r)[3], bool sysfence) {
+    __shared__ bool is_last_r;
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int nthreads = blockDim.x * blockDim.y;
+    __syncthreads();  // all stores of the block precede thread 0's fence
+    if (tid == 0) {
+        partials[3 * bid + 0] = s0;
+        partials[3 * bid + 1] = s1;
+        partials[3 * bid + 2] = s2;
+        if (sysfence) __threadfence_system(); else __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last_r = (t == (unsigned int)(nblocks - 1));
+    }
+    __syncthreads();
+    if (!is_last_r) return false;
+    __threadfence();
+    double a[3] = {0.0, 0.0, 0.0};
+    for (int i = tid; i < nblocks; i += nthreads) {
+        a[0] += __ldcg(partials + 3 * i + 0);
+        a[1] += __ldcg(partials + 3 * i + 1);
+        a[2] += __ldcg(partials + 3 * i + 2);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r[c] = block_sum(a[c], sh);
+    if (tid == 0) *ticket = 0u;
+    return tid == 0;
+}
+
+// ---- mailbox all-reduce over NVLink peer memory ---------------------------------------------------------
+// record (slot, src) = 4 doubles {v0, v1, v2, tag}; tag = sequence number of the collective (never reused)
+AK_DEV void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+AK_DEV unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// ONE thread: deposit this rank's partial sums in every rank's mailbox (own included)
+AK_DEV void mail_post(const P2PDev& pd, unsigned long long seq, double v0, double v1, double v2) {
+    const int slot = (int)(seq % kMailSlots);
+    __threadfence_system();  // halo rows pushed by this grid are visible before the record is
+    for (int q = 0; q < pd.nranks; ++q) {
+        double* rec = pd.mail_peer[q] + ((size_t)slot * pd.nranks + pd.rank) * 4;
+        rec[0] = v0;
+        rec[1] = v1;
+        rec[2] = v2;
+    }
+    __threadfence_system();
+    for (int q = 0; q < pd.nranks; ++q) {
+        double* rec = pd.mail_peer[q] + ((size_t)slot * pd.nranks + pd.rank) * 4;
+        st_release_sys_u64(reinterpret_cast<unsigned long long*>(rec + 3), seq);
+    }
+}
+// Whole block: wait until every rank's record `seq` has arrived in the local mailbox and add them in rank
+// order (bit-identical on every rank).  Result in out[0..2] for all threads.  `sh4` >= 4 * kMaxPeers doubles.
+AK_DEV void mail_wait_sum(const P2PDev& pd, unsigned long long seq, double (&out)[3], double* sh4) {
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int slot = (int)(seq % kMailSlots);
+    if (tid < pd.nranks) {
+        const double* rec = pd.mail_local + ((size_t)slot * pd.nranks + tid) * 4;
+        const unsigned long long* tag = reinterpret_cast<const unsigned long long*>(rec + 3);
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(tag) != seq) {
+            if (clock64() - t0 > pd.spin_cycles) {  // a peer never produced this record: flag it, do not hang
+                *pd.err = 1;
+                break;
+            }
+        }
+        sh4[4 * tid + 0] = __ldcv(rec + 0);
+        sh4[4 * tid + 1] = __ldcv(rec + 1);
+        sh4[4 * tid + 2] = __ldcv(rec + 2);
+    }
+    __syncthreads();
+    out[0] = out[1] = out[2] = 0.0;
+    for (int q = 0; q < pd.nranks; ++q) {
+        out[0] += sh4[4 * q + 0];
+        out[1] += sh4[4 * q + 1];
+        out[2] += sh4[4 * q + 2];
+    }
+    __syncthreads();
 }
 
 // h of the second vector of a pair from the raw sums (d1 = <y_a,w>, d2 = <y_b,w>, g = <y_b,y_a>):

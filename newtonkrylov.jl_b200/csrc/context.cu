@@ -58,6 +58,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -88,6 +89,7 @@ static int load_nccl() {
     AK_SYM(CommInitRank, "ncclCommInitRank");
     AK_SYM(CommDestroy, "ncclCommDestroy");
     AK_SYM(AllReduce, "ncclAllReduce");
+    AK_SYM(AllGather, "ncclAllGather");
     AK_SYM(Send, "ncclSend");
     AK_SYM(Recv, "ncclRecv");
     AK_SYM(GroupStart, "ncclGroupStart");
@@ -143,6 +145,25 @@ int exchange_halo_rows(Ctx* ctx, const double* v, int64_t nx, int64_t ny, int32_
     *lo = down >= 0 ? ctx->halo_lo : nullptr;
     *hi = up >= 0 ? ctx->halo_hi : nullptr;
     return AK_OK;
+}
+
+// ---- peer memory -------------------------------------------------------------------------
+static inline size_t p2p_mail_doubles(int nranks) { return (size_t)kMailSlots * nranks * 4; }
+P2PDev Ctx::p2p_dev() const {
+    P2PDev d{};
+    d.nranks = nranks;
+    d.rank = rank;
+    d.mail_local = p2p_block;
+    for (int q = 0; q < nranks && q < kMaxPeers; ++q) d.mail_peer[q] = (double*)p2p_peer_block[q];
+    d.err = p2p_err;
+    d.spin_cycles = 6000000000ll;  // ~3 s at 1.9 GHz: a peer that far behind means a bug, not load imbalance
+    return d;
+}
+double* Ctx::p2p_halo_local(int parity, int hi) const {
+    return p2p_block + p2p_mail_doubles(nranks) + ((size_t)parity * 2 + hi) * p2p_halo_cap;
+}
+double* Ctx::p2p_halo_of(int peer, int parity, int hi) const {
+    return (double*)p2p_peer_block[peer] + p2p_mail_doubles(nranks) + ((size_t)parity * 2 + hi) * p2p_halo_cap;
 }
 
 // ---- HaloVector layout bridge -----------------------------------------------------------
@@ -233,6 +254,12 @@ AK_API int ak_ctx_destroy(ak_ctx* ctx) {
     Ctx* c = &ctx->c;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->p2p_block) {
+        for (int q = 0; q < c->nranks && q < kMaxPeers; ++q)
+            if (q != c->rank && c->p2p_peer_block[q]) cudaIpcCloseMemHandle(c->p2p_peer_block[q]);
+        cudaFree(c->p2p_block);
+        if (c->p2p_err) cudaFreeHost(c->p2p_err);
+    }
     if (c->comm) {
         if (c->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm->comm);
         delete c->comm;
@@ -396,6 +423,59 @@ AK_API int ak_comm_init(ak_ctx* ctx, int nranks, int rank, const char id_in[128]
     ctx->c.nranks = nranks;
     return AK_OK;
 }
+AK_API int ak_comm_enable_p2p(ak_ctx* ctx, int64_t halo_doubles) {
+    AK_REQUIRE(ctx && halo_doubles >= 0, "ak_comm_enable_p2p: bad argument");
+    Ctx* c = &ctx->c;
+    if (c->nranks <= 1) return AK_OK;
+    AK_REQUIRE(c->comm != nullptr, "ak_comm_enable_p2p: call ak_comm_init first");
+    AK_REQUIRE(!c->p2p_on, "ak_comm_enable_p2p: already enabled");
+    if (c->nranks > kMaxPeers) {
+        set_error("ak_comm_enable_p2p: at most %d ranks per node", kMaxPeers);
+        return AK_ERR_UNSUPPORTED;
+    }
+    AK_CUDA(cudaSetDevice(c->device));
+    const int P = c->nranks;
+    const int64_t hcap = (halo_doubles + 3) & ~int64_t(3);
+    const size_t doubles = p2p_mail_doubles(P) + (size_t)4 * hcap;
+    // cudaMalloc (not the stream-ordered pool): IPC handles exist only for plain allocations
+    AK_CUDA(cudaMalloc(&c->p2p_block, sizeof(double) * doubles));
+    AK_CUDA(cudaMemset(c->p2p_block, 0, sizeof(double) * doubles));
+    AK_CUDA(cudaHostAlloc((void**)&c->p2p_err, sizeof(int), cudaHostAllocMapped));
+    *c->p2p_err = 0;
+    cudaIpcMemHandle_t mine;
+    AK_CUDA(cudaIpcGetMemHandle(&mine, c->p2p_block));
+    // exchange the 64-byte handles with an all-gather on the library's own communicator
+    char *dsend = nullptr, *drecv = nullptr;
+    AK_CUDA(cudaMalloc(&dsend, sizeof(mine)));
+    AK_CUDA(cudaMalloc(&drecv, sizeof(mine) * P));
+    AK_CUDA(cudaMemcpyAsync(dsend, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+    AK_NCCL(g_nccl.AllGather(dsend, drecv, sizeof(mine), /*ncclChar*/ 0, c->comm->comm, c->stream));
+    std::vector<cudaIpcMemHandle_t> all((size_t)P);
+    AK_CUDA(cudaMemcpyAsync(all.data(), drecv, sizeof(mine) * P, cudaMemcpyDeviceToHost, c->stream));
+    AK_CUDA(cudaStreamSynchronize(c->stream));
+    AK_CUDA(cudaFree(dsend));
+    AK_CUDA(cudaFree(drecv));
+    for (int q = 0; q < P; ++q) {
+        if (q == c->rank) { c->p2p_peer_block[q] = c->p2p_block; continue; }
+        cudaError_t e = cudaIpcOpenMemHandle(&c->p2p_peer_block[q], all[(size_t)q], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("cudaIpcOpenMemHandle(rank %d) failed: %s (peer access over NVLink is required)", q,
+                      cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            return AK_ERR_CUDA;
+        }
+    }
+    c->p2p_halo_cap = hcap;
+    c->p2p_seq = 0;
+    // nobody may write into a mailbox before its owner has zeroed it
+    AK_CUDA(cudaMemsetAsync(c->dscal + 62, 0, sizeof(double), c->stream));
+    AK_TRY(allreduce_sum(c, c->dscal + 62, 1));
+    AK_CUDA(cudaStreamSynchronize(c->stream));
+    c->p2p_on = true;
+    return AK_OK;
+}
+AK_API int ak_comm_p2p_enabled(ak_ctx* ctx) { return (ctx && ctx->c.p2p_on) ? 1 : 0; }
+
 AK_API int ak_comm_rank(ak_ctx* ctx, int* rank, int* nranks) {
     AK_REQUIRE(ctx, "ak_comm_rank: NULL ctx");
     if (rank) *rank = ctx->c.rank;

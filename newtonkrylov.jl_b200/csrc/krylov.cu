@@ -97,10 +97,26 @@ __device__ __forceinline__ double sgn(double x) { return (double)((x > 0.0) - (x
 
 // Krylov.jl sym_givens (real), then the update of iteration k (1-based) — gmres! steps 6-8
 __global__ void k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, double* c, double* s, double* z,
-                               const double* hcol, int reorth, int pair, double* hist, int64_t hist_pos,
-                               int inner_limit, KrylovStatus* st) {
+                               double* hcol, int reorth, int pair, double* hist, int64_t hist_pos,
+                               int inner_limit, KrylovStatus* st, const P2PDev pd, unsigned long long seq_in) {
     if (threadIdx.x != 0) return;
     if (ctl->stop) return;
+    if (seq_in != 0) {
+        // ||q||^2 arrives through the mailboxes (posted by the final Gram-Schmidt pass of every rank); adding
+        // in rank order gives the same bits on every rank, so all ranks take the same decisions below
+        const int slot = (int)(seq_in % kMailSlots);
+        double tot = 0.0;
+        for (int q = 0; q < pd.nranks; ++q) {
+            const double* rec = pd.mail_local + ((size_t)slot * pd.nranks + q) * 4;
+            const unsigned long long* tag = reinterpret_cast<const unsigned long long*>(rec + 3);
+            const long long t0 = clock64();
+            while (ld_acquire_sys_u64(tag) != seq_in) {
+                if (clock64() - t0 > pd.spin_cycles) { *pd.err = 1; break; }
+            }
+            tot += __ldcv(rec);
+        }
+        hcol[3 * ((k + 1) >> 1)] = tot;
+    }
     // column k of H: h_1k..h_kk from the MGS sweep(s), h_{k+1,k} = ||q||
     double hh;
     if (pair) {  // raw triples {<y_a,w>, <y_b,w>, <y_b,y_a>} of the pair-wise sweep, then ||q||^2
@@ -354,6 +370,16 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     int fuse = o->fuse;
     if (fuse == AK_FUSE_PAIR && reorth) fuse = AK_FUSE_FULL;  // the pair-wise sweep has no second-sweep variant
     const bool pair = (fuse == AK_FUSE_PAIR);
+    // multi-GPU with peer memory: reductions and ghost rows of the pair-wise sweep go over NVLink stores
+    const bool p2p = pair && c->p2p_on && c->nranks > 1;
+    const bool is2d = (prob->kind == AK_BRATU2D || prob->kind == AK_HEAT2D);
+    const bool p2p_halo = p2p && is2d && prob->nx % 4 == 0 && n % 4 == 0 && prob->nx <= c->p2p_halo_cap;
+    int nb_down = -1, nb_up = -1;  // owners of the ghost rows below / above this slab
+    if (p2p_halo) {
+        const bool per = (prob->bc == AK_BC_PERIODIC);
+        nb_down = c->rank > 0 ? c->rank - 1 : (per ? c->nranks - 1 : -1);
+        nb_up = c->rank < c->nranks - 1 ? c->rank + 1 : (per ? 0 : -1);
+    }
     const bool want_hist = (hist_host != nullptr && hist_cap > 0) || o->history;
     cudaStream_t sm = c->stream;
 
@@ -432,6 +458,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 const int64_t nr = k * (k - 1) / 2;
                 const int* stop = &ws->ctl->stop;
                 double* hcol = ws->hcol;
+                unsigned long long givens_seq = 0;
 
                 // w <- A V[k-1]  (+ fused divcopy of V[k-1], + fused first dot)
                 JvpFusion jf;
@@ -443,6 +470,12 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                         jf.denom_dev = &ws->ctl->Hbis;
                         wi ^= 1;
                         wout = ws->w[wi];
+                        if (p2p_halo) {  // ghost rows of w were pushed by the neighbours' final pass of iteration k-1
+                            const int par = (int)((k - 1) & 1);
+                            jf.halo_given = true;
+                            jf.halo_lo = nb_down >= 0 ? c->p2p_halo_local(par, 0) : nullptr;
+                            jf.halo_hi = nb_up >= 0 ? c->p2p_halo_local(par, 1) : nullptr;
+                        }
                     }
                     if (!pair) {
                         jf.dot_with = ws->V[0];
@@ -457,12 +490,35 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                     const int64_t P = (k + 1) / 2;
                     auto va = [&](int64_t j) -> const double* { return ws->V[2 * j]; };
                     auto vb = [&](int64_t j) -> const double* { return (2 * j + 1 < k) ? ws->V[2 * j + 1] : nullptr; };
-                    AK_TRY(launch_mgs_pair(c, n, w, nullptr, nullptr, nullptr, va(0), vb(0), 0, hcol, stop));
-                    for (int64_t j = 1; j < P; ++j)
+                    PairComm pc;
+                    unsigned long long prev_seq = 0;
+                    if (p2p) { pc.seq_out = ++c->p2p_seq; prev_seq = pc.seq_out; }
+                    AK_TRY(launch_mgs_pair(c, n, w, nullptr, nullptr, nullptr, va(0), vb(0), 0, hcol, stop,
+                                           p2p ? &pc : nullptr));
+                    for (int64_t j = 1; j < P; ++j) {
+                        if (p2p) {
+                            pc.seq_in = prev_seq;
+                            pc.seq_out = ++c->p2p_seq;
+                            pc.tin_store = hcol + 3 * (j - 1);
+                            prev_seq = pc.seq_out;
+                        }
                         AK_TRY(launch_mgs_pair(c, n, w, va(j - 1), vb(j - 1), hcol + 3 * (j - 1), va(j), vb(j), 0,
-                                               hcol + 3 * j, stop));
+                                               hcol + 3 * j, stop, p2p ? &pc : nullptr));
+                    }
+                    if (p2p) {
+                        pc.seq_in = prev_seq;
+                        pc.seq_out = ++c->p2p_seq;
+                        pc.tin_store = hcol + 3 * (P - 1);
+                        givens_seq = pc.seq_out;
+                        if (p2p_halo) {
+                            const int par = (int)(k & 1);
+                            pc.halo.nx = prob->nx;
+                            pc.halo.down_hi = nb_down >= 0 ? c->p2p_halo_of(nb_down, par, 1) : nullptr;
+                            pc.halo.up_lo = nb_up >= 0 ? c->p2p_halo_of(nb_up, par, 0) : nullptr;
+                        }
+                    }
                     AK_TRY(launch_mgs_pair(c, n, w, va(P - 1), vb(P - 1), hcol + 3 * (P - 1), nullptr, nullptr, 1,
-                                           hcol + 3 * P, stop));
+                                           hcol + 3 * P, stop, p2p ? &pc : nullptr));
                 } else if (fuse == AK_FUSE_NONE) {
                     for (int64_t i = 0; i < k; ++i) {
                         AK_TRY(launch_mgs_step(c, n, w, nullptr, nullptr, ws->V[i], 0, hcol + i, stop));   // h = <V_i, w>
@@ -498,7 +554,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 { ProfScope prof(c, PK_SCALAR);
                 k_gmres_givens<<<1, 32, 0, sm>>>(ws->ctl, (int)k, nr, ws->R, ws->c, ws->s, ws->z, hcol, reorth, pair ? 1 : 0,
                                                  want_hist ? ws->hist : nullptr, iter + k, (int)inner_limit,
-                                                 &ws->status[slot]); }
+                                                 &ws->status[slot], p2p ? c->p2p_dev() : P2PDev{}, givens_seq); }
                 c->launches++;
                 AK_CUDA(cudaGetLastError());
                 AK_CUDA(cudaEventRecord(ws->ev[slot], sm));
@@ -558,6 +614,10 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
         w = ws->w[wi];
     }
 
+    if (p2p && *c->p2p_err) {
+        set_error("peer-memory collective timed out (a rank fell out of step)");
+        return AK_ERR_NCCL;
+    }
     st->niter = iter;
     st->solved = solved ? 1 : 0;
     st->inconsistent = inconsistent ? 1 : 0;

@@ -967,20 +967,22 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
                 // north_star (2): one pass reads u and v and writes J v ~ (F(u + eps v) - F(u)) / eps
                 if (ctx->nranks > 1) { set_error("AK_JVP_FD_FUSED is single-GPU in this version"); return AK_ERR_UNSUPPORTED; }
                 AK_REQUIRE(u != nullptr, "AK_JVP_FD_FUSED needs u");
-                AK_TRY(ghost_rows(ctx, p, a.in, &a.lo, &a.hi));
+                AK_TRY(ghost_rows(ctx, p, a.in, &a.lo, &a.hi));  // (single GPU: no exchange)
                 a.aux = u;
                 AK_TRY(ghost_rows(ctx, p, u, &a.aux_lo, &a.aux_hi));
                 a.fd_eps = p->fd_eps > 0.0 ? p->fd_eps : 1.4901161193847656e-08;
                 rc = launch2d<OP_JVP_BRATU_FD>(ctx, a, scale, red);
                 break;
             }
-            AK_TRY(ghost_rows(ctx, p, a.in, &a.lo, &a.hi));
+            if (f->halo_given) { a.lo = f->halo_lo; a.hi = f->halo_hi; }
+            else AK_TRY(ghost_rows(ctx, p, a.in, &a.lo, &a.hi));
             a.aux = p->coef ? p->coef : u;
             a.coef_from_u = p->coef ? 0 : 1;
             rc = launch2d<OP_JVP_BRATU>(ctx, a, scale, red);
             break;
         case AK_HEAT2D:
-            AK_TRY(ghost_rows(ctx, p, a.in, &a.lo, &a.hi));
+            if (f->halo_given) { a.lo = f->halo_lo; a.hi = f->halo_hi; }
+            else AK_TRY(ghost_rows(ctx, p, a.in, &a.lo, &a.hi));
             rc = launch2d<OP_JVP_HEAT>(ctx, a, scale, red);
             break;
         default: break;

@@ -46,9 +46,11 @@ def halo_message_order(rank, world, periodic):
     return ops
 
 
-def init_distributed(device=None):
+def init_distributed(device=None, p2p_halo=None):
     """Create the context of this rank and its NCCL communicator.  Expects torch.distributed to be
-    initialised (any backend) and RANK / LOCAL_RANK / WORLD_SIZE in the environment."""
+    initialised (any backend) and RANK / LOCAL_RANK / WORLD_SIZE in the environment.
+    `p2p_halo` (row length of the widest 2-D grid) additionally maps the ranks' peer memory so that the
+    pair-wise GMRES sweep reduces and exchanges ghost rows with NVLink stores instead of NCCL calls."""
     import torch.distributed as dist
 
     rank = dist.get_rank() if dist.is_initialized() else 0
@@ -60,4 +62,6 @@ def init_distributed(device=None):
         ids = [host.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.init_comm(world, rank, ids[0])
+    if world > 1 and p2p_halo is not None and not ctx.p2p:
+        ctx.enable_p2p(p2p_halo)
     return ctx

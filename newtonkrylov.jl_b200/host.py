@@ -77,6 +77,14 @@ class Context:
         L.check(self.lib.ak_comm_init(self.h, nranks, rank, unique_id))
         self.rank, self.nranks = rank, nranks
 
+    def enable_p2p(self, halo_doubles):
+        """Map every rank's mailbox / ghost-row block over NVLink (CUDA IPC); collective call."""
+        L.check(self.lib.ak_comm_enable_p2p(self.h, int(halo_doubles)))
+
+    @property
+    def p2p(self):
+        return bool(self.lib.ak_comm_p2p_enabled(self.h))
+
     def barrier(self):
         L.check(self.lib.ak_comm_barrier(self.h))
 
