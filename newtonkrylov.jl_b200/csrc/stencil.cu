@@ -131,7 +131,7 @@ AK_DEV double second_diff(double e, double c, double w, const Divisor& d2) {
 constexpr int kTX = 128;  // threads per block, all along x
 
 template <int OP, int VEC, bool SCALE, int RED>
-__global__ void __launch_bounds__(kTX) k_stencil2d(const StencilArgs p) {
+__global__ void __launch_bounds__(kTX, OP == OP_JVP_BRATU_FD ? 4 : 8) k_stencil2d(const StencilArgs p) {
     __shared__ double sh[32];
     if (p.stop != nullptr && *p.stop != 0) return;
     const int lane = threadIdx.x & 31;
@@ -204,10 +204,20 @@ __global__ void __launch_bounds__(kTX) k_stencil2d(const StencilArgs p) {
     load_row(row_ptr(y0 - 1), prev);
     load_row(cur_src, cur);
     double acc = 0.0;
+    // x-neighbours outside the warp are fetched one row ahead so that their latency hides behind a row of work
+    const bool need_l = active && lane == 0;
+    const bool need_r = active && (lane == 31 || x0 + VEC >= nx);
+    double edge_l = need_l ? edge(cur_src, x0 - 1) : 0.0;
+    double edge_r = need_r ? edge(cur_src, x0 + VEC) : 0.0;
 
     for (int64_t y = y0; y < y1; ++y) {
         const double* next_src = row_ptr(y + 1);
         load_row(next_src, next);
+        double edge_l_next = 0.0, edge_r_next = 0.0;
+        if (y + 1 < y1) {
+            if (need_l) edge_l_next = edge(next_src, x0 - 1);
+            if (need_r) edge_r_next = edge(next_src, x0 + VEC);
+        }
         double left = __shfl_up_sync(0xffffffffu, cur[VEC - 1], 1);
         double right = __shfl_down_sync(0xffffffffu, cur[0], 1);
         const double* unext_src = nullptr;
@@ -219,8 +229,8 @@ __global__ void __launch_bounds__(kTX) k_stencil2d(const StencilArgs p) {
             uright = __shfl_down_sync(0xffffffffu, ucur[0], 1);
         }
         if (active) {
-            if (lane == 0) left = edge(cur_src, x0 - 1);
-            if (lane == 31 || x0 + VEC >= nx) right = edge(cur_src, x0 + VEC);
+            if (need_l) left = edge_l;
+            if (need_r) right = edge_r;
             if (FD) {
                 if (lane == 0) uleft = uedge(ucur_src, x0 - 1);
                 if (lane == 31 || x0 + VEC >= nx) uright = uedge(ucur_src, x0 + VEC);
@@ -284,6 +294,8 @@ __global__ void __launch_bounds__(kTX) k_stencil2d(const StencilArgs p) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) { prev[i] = cur[i]; cur[i] = next[i]; }
         cur_src = next_src;
+        edge_l = edge_l_next;
+        edge_r = edge_r_next;
         if (FD) {
 #pragma unroll
             for (int i = 0; i < (FD ? VEC : 1); ++i) { uprev[i] = ucur[i]; ucur[i] = unext[i]; }
