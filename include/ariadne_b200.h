@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AK_ABI_VERSION 1
+#define AK_ABI_VERSION 2
 
 /* ---- status / flags ------------------------------------------------------- */
 enum {
@@ -185,7 +185,13 @@ int ak_divcopy(ak_ctx* ctx, int64_t n, double* y, const double* x, double s);
 /* ---- whole linear solve: krylov_workspace / krylov_solve!, src/Ariadne.jl:317-318,338-340 */
 typedef struct ak_krylov ak_krylov;
 
-enum { AK_ALGO_GMRES = 0, AK_ALGO_CG = 1 };
+enum { AK_ALGO_GMRES = 0, AK_ALGO_CG = 1, AK_ALGO_FGMRES = 2 /* Krylov.jl fgmres!: examples/bratu.jl:131-157 */ };
+/* right preconditioner N of `newton_krylov!(...; N = (J) -> ...)` (src/Ariadne.jl:296-297,324-326) built natively */
+enum {
+    AK_PRECOND_NONE = 0,
+    AK_PRECOND_INNER_GMRES = 1 /* N = (J) -> GmresPreconditioner(J, itmax): y = gmres(J, x; itmax)
+                                  (examples/bratu.jl:141-157, bvp.jl:29-38)                      */
+};
 /* how aggressively the Arnoldi step is fused (all levels keep modified Gram-Schmidt
  * order, so they differ only by rounding of identical operations)               */
 enum {
@@ -207,6 +213,8 @@ typedef struct ak_krylov_opts {
     int32_t reorthogonalization; /* second MGS sweep (heat_2D.jl:131)              */
     int32_t history;        /* record rNorm per iteration                          */
     int32_t fuse;           /* AK_FUSE_*                                           */
+    int32_t precond_n;      /* AK_PRECOND_*: right preconditioner (kwarg N)        */
+    int32_t precond_itmax;  /* itmax of the inner GMRES (GmresPreconditioner.itmax) */
 } ak_krylov_opts;
 
 typedef struct ak_krylov_stats {

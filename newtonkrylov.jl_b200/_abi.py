@@ -5,7 +5,7 @@ struct layouts without touching the CUDA library.
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # status / flags
 AK_OK = 0
@@ -17,7 +17,8 @@ AK_SIMPLE2, AK_BRATU1D, AK_BRATU2D, AK_HEAT1D, AK_HEAT2D, AK_HEAT1D_DG = range(6
 AK_BC_ZERO, AK_BC_PERIODIC = 0, 1
 AK_STEADY, AK_EULER, AK_MIDPOINT, AK_TRAPEZOID = range(4)
 AK_JVP_ANALYTIC, AK_JVP_FD_FUSED = 0, 1
-AK_ALGO_GMRES, AK_ALGO_CG = 0, 1
+AK_ALGO_GMRES, AK_ALGO_CG, AK_ALGO_FGMRES = 0, 1, 2
+AK_PRECOND_NONE, AK_PRECOND_INNER_GMRES = 0, 1
 AK_FUSE_NONE, AK_FUSE_MGS, AK_FUSE_FULL, AK_FUSE_PAIR = 0, 1, 2, 3
 AK_FORCING_NONE, AK_FORCING_FIXED, AK_FORCING_EW = 0, 1, 2
 
@@ -57,6 +58,8 @@ class ak_krylov_opts(C.Structure):
         ("reorthogonalization", C.c_int32),
         ("history", C.c_int32),
         ("fuse", C.c_int32),
+        ("precond_n", C.c_int32),
+        ("precond_itmax", C.c_int32),
     ]
 
 
@@ -109,7 +112,7 @@ SQRT_EPS = 2.220446049250313e-16 ** 0.5
 
 def default_krylov_opts(**kw):
     """Krylov.jl gmres!/cg! keyword defaults (atol = rtol = sqrt(eps), itmax = 0 -> 2n)."""
-    o = ak_krylov_opts(SQRT_EPS, SQRT_EPS, 0, 0, 0, 0, AK_FUSE_MGS)
+    o = ak_krylov_opts(SQRT_EPS, SQRT_EPS, 0, 0, 0, 0, AK_FUSE_MGS, AK_PRECOND_NONE, 0)
     for k, v in kw.items():
         if not hasattr(o, k):
             raise TypeError(f"unknown krylov kwarg {k!r}")

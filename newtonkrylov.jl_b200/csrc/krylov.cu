@@ -47,6 +47,9 @@ struct ak_krylov {
     double* w[2] = {nullptr, nullptr};
     double* dx = nullptr;  // xr when restart
     std::vector<double*> V;          // basis vectors
+    std::vector<double*> Z;          // fgmres: z_k = N v_k
+    double* pbuf = nullptr;          // right-preconditioned gmres: p = N v_k
+    ak_krylov* inner = nullptr;      // workspace of the inner GMRES used as preconditioner
     std::vector<double*> chunks;     // cudaMalloc'ed blocks backing V / misc vectors
     const double** V_dev = nullptr;  // device table of basis pointers
     int64_t V_dev_cap = 0;
@@ -337,7 +340,7 @@ static int ws_ensure_basis(ak_krylov* ws, int64_t count) {
     return AK_OK;
 }
 
-static int ws_upload_basis_table(ak_krylov* ws, int64_t k) {
+static int ws_upload_basis_table(ak_krylov* ws, int64_t k, bool use_z = false) {
     Ctx* c = ws->ctx;
     if (k > ws->V_dev_cap) {
         AK_CUDA(cudaStreamSynchronize(c->stream));
@@ -347,8 +350,8 @@ static int ws_upload_basis_table(ak_krylov* ws, int64_t k) {
         AK_CUDA(cudaMallocAsync((void**)&ws->V_dev, sizeof(double*) * (size_t)cap, c->stream));
         ws->V_dev_cap = cap;
     }
-    AK_CUDA(cudaMemcpyAsync((void*)ws->V_dev, ws->V.data(), sizeof(double*) * (size_t)k, cudaMemcpyHostToDevice,
-                            c->stream));
+    AK_CUDA(cudaMemcpyAsync((void*)ws->V_dev, use_z ? ws->Z.data() : ws->V.data(), sizeof(double*) * (size_t)k,
+                            cudaMemcpyHostToDevice, c->stream));
     return AK_OK;
 }
 
@@ -362,6 +365,31 @@ static int wait_status(ak_krylov* ws, int slot, KrylovStatus* out) {
 }
 
 static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, const double* b,
+                       const ak_krylov_opts* o, ak_krylov_stats* st, double* hist_host, int64_t hist_cap);
+
+// out <- N in.  AK_PRECOND_INNER_GMRES: `copyto!(y, gmres(P.J, x; P.itmax)[1])` (examples/bratu.jl:146-149):
+// an inner GMRES with memory 20, default tolerances, x0 = 0 and at most precond_itmax iterations.
+static int apply_precond_n(ak_krylov* ws, const ak_problem* prob, const double* u, const ak_krylov_opts* o,
+                           const double* in, double* out) {
+    if (o->precond_n != AK_PRECOND_INNER_GMRES) {
+        set_error("unknown right preconditioner %d", o->precond_n);
+        return AK_ERR_UNSUPPORTED;
+    }
+    if (!ws->inner) {
+        ak_ctx* owner = reinterpret_cast<ak_ctx*>(ws->ctx);  // ak_ctx { Ctx c; } — c is its first member
+        AK_TRY(ak_krylov_create(owner, AK_ALGO_GMRES, ws->n, 20, 0, &ws->inner));
+    }
+    ak_krylov_opts io;
+    ak_krylov_default_opts(&io);
+    io.itmax = o->precond_itmax;
+    io.fuse = (o->fuse == AK_FUSE_NONE) ? AK_FUSE_NONE : AK_FUSE_MGS;
+    ak_krylov_stats ist;
+    int rc = gmres_solve(ws->inner, prob, u, in, &io, &ist, nullptr, 0);
+    if (rc < 0) return rc;
+    return launch_copy(ws->ctx, ws->n, out, ws->inner->x);
+}
+
+static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, const double* b,
                        const ak_krylov_opts* o, ak_krylov_stats* st, double* hist_host, int64_t hist_cap) {
     Ctx* c = ws->ctx;
     const int64_t n = ws->n;
@@ -369,6 +397,11 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     const int restart = o->restart, reorth = o->reorthogonalization;
     int fuse = o->fuse;
     if (fuse == AK_FUSE_PAIR && reorth) fuse = AK_FUSE_FULL;  // the pair-wise sweep has no second-sweep variant
+    const bool flexible = (ws->algo == AK_ALGO_FGMRES);
+    const bool precond = (o->precond_n != AK_PRECOND_NONE);
+    // z_k = N v_k needs v_k materialised before the JVP and a host decision per iteration: no JVP fusion
+    if ((flexible || precond) && fuse > AK_FUSE_MGS) fuse = AK_FUSE_MGS;
+    if ((flexible || precond) && !ws->pbuf) AK_TRY(ws_alloc_vec(ws, &ws->pbuf));
     const bool pair = (fuse == AK_FUSE_PAIR);
     // multi-GPU with peer memory: reductions and ghost rows of the pair-wise sweep go over NVLink stores
     const bool p2p = pair && c->p2p_on && c->nranks > 1;
@@ -460,6 +493,27 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 double* hcol = ws->hcol;
                 unsigned long long givens_seq = 0;
 
+                // fgmres / right preconditioning: z_k = N v_k (kept in Z for fgmres), then w <- A z_k
+                double* pv = ws->V[k - 1];
+                if (flexible || precond) {
+                    // the preconditioner solves with host-visible verdicts: this path is not speculative
+                    if (k > 1) {
+                        AK_TRY(wait_status(ws, (int)((k - 1) % kStatusRing), &hs));
+                        if (hs.stop) { K = k - 1; break; }
+                    }
+                    double* tgt = ws->pbuf;
+                    if (flexible) {
+                        while ((int64_t)ws->Z.size() < k) {
+                            double* z = nullptr;
+                            AK_TRY(ws_alloc_vec(ws, &z));
+                            ws->Z.push_back(z);
+                        }
+                        tgt = ws->Z[k - 1];
+                    }
+                    if (precond) AK_TRY(apply_precond_n(ws, prob, u, o, ws->V[k - 1], tgt));
+                    else AK_TRY(launch_copy(c, n, tgt, ws->V[k - 1]));
+                    pv = tgt;
+                }
                 // w <- A V[k-1]  (+ fused divcopy of V[k-1], + fused first dot)
                 JvpFusion jf;
                 jf.stop_flag = stop;
@@ -482,7 +536,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                         jf.dot_dev = hcol;
                     }
                 }
-                AK_TRY(launch_jvp(c, prob, u, ws->V[k - 1], wout, &jf));
+                AK_TRY(launch_jvp(c, prob, u, pv, wout, &jf));
                 w = wout;
                 // modified Gram-Schmidt
                 if (pair) {
@@ -600,8 +654,13 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 else y[i - 1] = y[i - 1] / Rh[(size_t)pos];
             }
             AK_CUDA(cudaMemcpyAsync(ws->hcol, y, sizeof(double) * (size_t)K, cudaMemcpyHostToDevice, sm));
-            AK_TRY(ws_upload_basis_table(ws, K));
+            // x_k = N V_k y_k (gmres) or Z_k y_k (fgmres)
+            AK_TRY(ws_upload_basis_table(ws, K, flexible));
             AK_TRY(launch_basis_combine(c, n, xr, ws->V_dev, ws->hcol, (int)K, /*zero_x_first=*/1));
+            if (!flexible && precond) {
+                AK_TRY(launch_copy(c, n, ws->pbuf, xr));
+                AK_TRY(apply_precond_n(ws, prob, u, o, ws->pbuf, xr));
+            }
             if (restart) AK_TRY(launch_axpy(c, n, 1.0, xr, x));
             // y lives in host memory that the async copy reads: drain before the vectors are reused
             AK_CUDA(cudaStreamSynchronize(sm));
@@ -731,7 +790,13 @@ static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, cons
 
 int krylov_solve_internal(ak_krylov* ws, const ak_problem* p, const double* u, const double* b,
                           const ak_krylov_opts* opts, ak_krylov_stats* st, double* hist_host, int64_t hist_cap) {
-    if (ws->algo == AK_ALGO_CG) return cg_solve(ws, p, u, b, opts, st, hist_host, hist_cap);
+    if (ws->algo == AK_ALGO_CG) {
+        if (opts->precond_n != AK_PRECOND_NONE) {
+            set_error("preconditioned CG is not implemented");
+            return AK_ERR_UNSUPPORTED;
+        }
+        return cg_solve(ws, p, u, b, opts, st, hist_host, hist_cap);
+    }
     return gmres_solve(ws, p, u, b, opts, st, hist_host, hist_cap);
 }
 
@@ -749,7 +814,7 @@ AK_API void ak_krylov_default_opts(ak_krylov_opts* o) {
 
 AK_API int ak_krylov_create(ak_ctx* ctx, int32_t algo, int64_t n, int32_t memory, int64_t max_basis, ak_krylov** out) {
     AK_REQUIRE(ctx && out && n >= 1, "ak_krylov_create: bad argument");
-    AK_REQUIRE(algo == AK_ALGO_GMRES || algo == AK_ALGO_CG, "ak_krylov_create: unknown algo");
+    AK_REQUIRE(algo == AK_ALGO_GMRES || algo == AK_ALGO_CG || algo == AK_ALGO_FGMRES, "ak_krylov_create: unknown algo");
     AK_REQUIRE(memory >= 1, "ak_krylov_create: memory must be >= 1");
     ak_krylov* ws = new ak_krylov();
     ws->ctx = &ctx->c;
@@ -760,7 +825,7 @@ AK_API int ak_krylov_create(ak_ctx* ctx, int32_t algo, int64_t n, int32_t memory
     int rc = AK_OK;
     do {
         if ((rc = ws_alloc_vec(ws, &ws->x)) != AK_OK) break;
-        if (algo == AK_ALGO_GMRES) {
+        if (algo == AK_ALGO_GMRES || algo == AK_ALGO_FGMRES) {
             if ((rc = ws_alloc_vec(ws, &ws->w[0])) != AK_OK) break;
             if ((rc = ws_ensure_basis(ws, memory)) != AK_OK) break;
         } else {
@@ -791,6 +856,7 @@ AK_API int ak_krylov_create(ak_ctx* ctx, int32_t algo, int64_t n, int32_t memory
 
 AK_API int ak_krylov_destroy(ak_krylov* ws) {
     if (!ws) return AK_OK;
+    if (ws->inner) ak_krylov_destroy(ws->inner);
     cudaStream_t sm = ws->ctx ? ws->ctx->stream : nullptr;
     if (sm) cudaStreamSynchronize(sm);
     auto rel = [&](void* p) { if (p) cudaFreeAsync(p, sm); };

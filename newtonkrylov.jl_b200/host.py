@@ -537,8 +537,17 @@ NewtonResult = namedtuple("NewtonResult", "solved stats t")
 # ---------------------------------------------------------------------------------------------
 # Krylov workspace: krylov_workspace / krylov_solve!  (src/Ariadne.jl:317-318,338-340,367)
 # ---------------------------------------------------------------------------------------------
-_ALGOS = {"gmres": A.AK_ALGO_GMRES, "cg": A.AK_ALGO_CG}
+_ALGOS = {"gmres": A.AK_ALGO_GMRES, "cg": A.AK_ALGO_CG, "fgmres": A.AK_ALGO_FGMRES}
 _FUSE = {"none": A.AK_FUSE_NONE, "mgs": A.AK_FUSE_MGS, "full": A.AK_FUSE_FULL, "pair": A.AK_FUSE_PAIR}
+
+
+class GmresPreconditioner:
+    """struct GmresPreconditioner{JOp}; J::JOp; itmax::Int  (examples/bratu.jl:141-149, bvp.jl:29-38):
+    `mul!(y, P, x) = copyto!(y, gmres(P.J, x; P.itmax)[1])`.  Passed as `N = J -> GmresPreconditioner(J, 5)`;
+    the library runs the inner GMRES natively (AK_PRECOND_INNER_GMRES)."""
+
+    def __init__(self, J, itmax):
+        self.J, self.itmax = J, int(itmax)
 
 
 class KrylovConstructor:
@@ -584,13 +593,21 @@ def krylov_workspace(algo, kc, memory=20, max_basis=0):
 
 
 def krylov_solve_(workspace, J, b, atol=A.SQRT_EPS, rtol=A.SQRT_EPS, itmax=0, restart=False,
-                  reorthogonalization=False, history=False, fuse="mgs", verbose=0, **unsupported):
-    """krylov_solve!(workspace, J, b; kwargs...) — solves J x = b from x0 = 0."""
+                  reorthogonalization=False, history=False, fuse="mgs", verbose=0, N=None, ldiv=False,
+                  **unsupported):
+    """krylov_solve!(workspace, J, b; kwargs...) — solves J x = b from x0 = 0.
+    `N`: right preconditioner object; only `GmresPreconditioner` is built natively."""
     if unsupported:
         raise TypeError(f"krylov kwargs not supported on the native path: {sorted(unsupported)}")
+    pn, pit = A.AK_PRECOND_NONE, 0
+    if N is not None:
+        if not isinstance(N, GmresPreconditioner) or ldiv:
+            raise NotImplementedError("only N = GmresPreconditioner(J, itmax) (ldiv = false) is built natively")
+        pn, pit = A.AK_PRECOND_INNER_GMRES, N.itmax
     o = A.default_krylov_opts(atol=atol, rtol=rtol, itmax=itmax, restart=int(bool(restart)),
                               reorthogonalization=int(bool(reorthogonalization)), history=int(bool(history)),
-                              fuse=_FUSE[fuse] if isinstance(fuse, str) else int(fuse))
+                              fuse=_FUSE[fuse] if isinstance(fuse, str) else int(fuse), precond_n=pn,
+                              precond_itmax=pit)
     st = A.ak_krylov_stats()
     prob = J.problem()
     ctx = workspace.ctx
@@ -621,8 +638,8 @@ def newton_krylov_(F_, u, p=None, res=None, *, tol_rel=1.0e-6, tol_abs=1.0e-12, 
 
     `history` (optional list) receives one dict per Newton iteration
     (n_res, inner iterations, eta used) — not in the reference; used by the parity tests."""
-    if M is not None or N is not None:
-        raise NotImplementedError("preconditioner hooks M / N are not on the native path yet")
+    if M is not None:
+        raise NotImplementedError("left preconditioner hook M is not on the native path yet")
     krylov_kwargs = dict(krylov_kwargs or {})
     if res is None:  # 3-argument form: res = similar(u0, M); make_zero!(res)   :259-263
         res = u.zero()
@@ -653,6 +670,8 @@ def newton_krylov_(F_, u, p=None, res=None, *, tol_rel=1.0e-6, tol_abs=1.0e-12, 
     stats = Stats(0, 0, n_res)                               # :320
     while n_res > tol and stats.outer_iterations <= max_niter:   # :321
         kwargs = dict(krylov_kwargs)
+        if N is not None:
+            kwargs = {"N": N(J), **kwargs}                   # kwargs = (; N = N(J), kwargs...)  :324-326
         if forcing is not None:
             kwargs = {"rtol": eta, **kwargs}                 # later keys win  :330-333
         kcopy_(len(res), rhs, res)                           # copy(res)      :338
@@ -685,10 +704,15 @@ def newton_krylov(F, u0, p=None, M=None, **kwargs):
     return newton_krylov_(F, u0, p, None, **kwargs)
 
 
-def _newton_opts(tol_rel, tol_abs, max_niter, forcing, algo, memory, max_basis, krylov_kwargs, verbose=0):
+def _newton_opts(tol_rel, tol_abs, max_niter, forcing, algo, memory, max_basis, krylov_kwargs, verbose=0, N=None):
     kk = dict(krylov_kwargs or {})
     override = "rtol" in kk
     fuse = kk.pop("fuse", "mgs")
+    if N is not None:
+        P = N(None)
+        if not isinstance(P, GmresPreconditioner):
+            raise NotImplementedError("only N = J -> GmresPreconditioner(J, itmax) is built natively")
+        kk["precond_n"], kk["precond_itmax"] = A.AK_PRECOND_INNER_GMRES, P.itmax
     ko = A.default_krylov_opts(fuse=_FUSE[fuse] if isinstance(fuse, str) else int(fuse),
                                **{k: (int(v) if isinstance(v, bool) else v) for k, v in kk.items()})
     o = A.default_newton_opts(tol_rel=tol_rel, tol_abs=tol_abs, max_niter=max_niter,
@@ -706,14 +730,14 @@ def _newton_opts(tol_rel, tol_abs, max_niter, forcing, algo, memory, max_basis, 
 
 def newton_krylov_native_(F_, u, p=None, res=None, *, tol_rel=1.0e-6, tol_abs=1.0e-12, max_niter=50,
                           forcing=EisenstatWalker(), algo="gmres", krylov_kwargs=None, memory=20, max_basis=0,
-                          history=None, verbose=0):
+                          history=None, verbose=0, N=None):
     """Same solve through the single C entry point ak_newton_solve (the loop runs in C++)."""
     if res is None:
         res = u.zero()
     ctx = u.ctx
     coef = u.similar() if F_.kind in (A.AK_BRATU1D, A.AK_BRATU2D) else None
     prob = F_.problem(u, p, coef=coef)
-    o = _newton_opts(tol_rel, tol_abs, max_niter, forcing, algo, memory, max_basis, krylov_kwargs, verbose)
+    o = _newton_opts(tol_rel, tol_abs, max_niter, forcing, algo, memory, max_basis, krylov_kwargs, verbose, N=N)
     st = A.ak_newton_stats()
     cap = max_niter + 3
     hn, hi, he = np.zeros(cap), np.zeros(cap, dtype=np.int64), np.zeros(cap)

@@ -462,6 +462,9 @@ typedef struct ok_krylov {
     int64_t nV;       /* allocated basis vectors (grows when restart == false) */
     double** V;
     double *x, *w, *dx; /* dx: xr when restart */
+    double** Z;         /* fgmres: z_k = N v_k */
+    int64_t nZ;
+    double* pbuf;       /* right-preconditioned gmres: p = N v_k */
     double *c, *s, *z, *R;
     int64_t cap_cs, cap_z, cap_R;
     /* cg */
@@ -474,8 +477,14 @@ OK_EXPORT ok_krylov* ok_krylov_create(int32_t algo, int64_t n, int32_t memory) {
     ws->n = n;
     ws->mem = memory;
     ws->x = ok_alloc(n);
-    if (algo == AK_ALGO_GMRES) {
+    if (algo == AK_ALGO_GMRES || algo == AK_ALGO_FGMRES) {
         ws->w = ok_alloc(n);
+        ws->pbuf = ok_alloc(n);
+        if (algo == AK_ALGO_FGMRES) {
+            ws->nZ = memory;
+            ws->Z = (double**)calloc((size_t)memory, sizeof(double*));
+            for (int i = 0; i < memory; ++i) ws->Z[i] = ok_alloc(n);
+        }
         ws->nV = memory;
         ws->V = (double**)calloc((size_t)memory, sizeof(double*));
         for (int i = 0; i < memory; ++i) ws->V[i] = ok_alloc(n);
@@ -496,6 +505,8 @@ OK_EXPORT ok_krylov* ok_krylov_create(int32_t algo, int64_t n, int32_t memory) {
 OK_EXPORT void ok_krylov_destroy(ok_krylov* ws) {
     if (!ws) return;
     for (int64_t i = 0; i < ws->nV; ++i) free(ws->V[i]);
+    for (int64_t i = 0; i < ws->nZ; ++i) free(ws->Z[i]);
+    free(ws->Z); free(ws->pbuf);
     free(ws->V); free(ws->x); free(ws->w); free(ws->dx);
     free(ws->c); free(ws->s); free(ws->z); free(ws->R);
     free(ws->r); free(ws->pp); free(ws->Ap);
@@ -514,13 +525,34 @@ static void grow(double** a, int64_t* cap, int64_t need) {
     *cap = nc;
 }
 
-/* GMRES, Krylov.jl gmres! with M = N = I.  Returns stats; x in ws->x.
- * `u` is the linearisation point of J = JacobianOperator(F!, res, u, p). */
+OK_EXPORT int ok_gmres(ok_krylov* ws, const ak_problem* p, const double* u, const double* b,
+                       const ak_krylov_opts* o, ak_krylov_stats* st, double* hist, int64_t hist_cap);
+OK_EXPORT void ok_krylov_default_opts(ak_krylov_opts* o);
+
+/* out <- N in, the right preconditioner.  AK_PRECOND_INNER_GMRES restates
+ *   mul!(y, P::GmresPreconditioner, x) = copyto!(y, gmres(P.J, x; P.itmax)[1])   examples/bratu.jl:146-149
+ * i.e. a fresh workspace (memory 20), default atol = rtol = sqrt(eps), x0 = 0, at most itmax iterations. */
+static void apply_precond_n(const ak_problem* p, const double* u, const ak_krylov_opts* o, int64_t n,
+                            const double* in, double* out) {
+    ok_krylov* in_ws = ok_krylov_create(AK_ALGO_GMRES, n, 20);
+    ak_krylov_opts io;
+    ok_krylov_default_opts(&io);
+    io.itmax = o->precond_itmax;
+    ak_krylov_stats ist;
+    ok_gmres(in_ws, p, u, in, &io, &ist, NULL, 0);
+    ok_copy(n, out, in_ws->x);
+    ok_krylov_destroy(in_ws);
+}
+
+/* GMRES / FGMRES, Krylov.jl gmres! and fgmres! with M = I and an optional right preconditioner N.
+ * Returns stats; x in ws->x.  `u` is the linearisation point of J = JacobianOperator(F!, res, u, p). */
 OK_EXPORT int ok_gmres(ok_krylov* ws, const ak_problem* p, const double* u, const double* b,
                        const ak_krylov_opts* o, ak_krylov_stats* st, double* hist, int64_t hist_cap) {
     const int64_t n = ws->n;
     const int32_t mem = ws->mem;
     const int restart = o->restart, reorth = o->reorthogonalization;
+    const int flexible = (ws->algo == AK_ALGO_FGMRES);
+    const int precond = (o->precond_n != AK_PRECOND_NONE);
     double* x = ws->x;
     double* w = ws->w;
     double* xr = x;
@@ -581,8 +613,23 @@ OK_EXPORT int ok_gmres(ok_krylov* ws, const ak_problem* p, const double* u, cons
                 grow(&ws->s, &cc, k + 1);
                 grow(&ws->c, &ws->cap_cs, k + 1);
             }
-            /* w <- A v_k */
-            ok_jvp(p, u, ws->V[k - 1], w);
+            /* w <- A N v_k   (fgmres keeps z_k = N v_k; gmres uses the scratch p) */
+            double* pv = ws->V[k - 1];
+            if (flexible || precond) {
+                double* tgt = ws->pbuf;
+                if (flexible) {
+                    if (k > ws->nZ) {
+                        ws->Z = (double**)realloc(ws->Z, sizeof(double*) * (size_t)k);
+                        ws->Z[k - 1] = ok_alloc(n);
+                        ws->nZ = k;
+                    }
+                    tgt = ws->Z[k - 1];
+                }
+                if (precond) apply_precond_n(p, u, o, n, ws->V[k - 1], tgt);
+                else ok_copy(n, tgt, ws->V[k - 1]);
+                pv = tgt;
+            }
+            ok_jvp(p, u, pv, w);
             double* q = w;
             for (int64_t i = 0; i < k; ++i) { /* modified Gram-Schmidt */
                 double h = ok_dot(n, ws->V[i], q);
@@ -638,7 +685,12 @@ OK_EXPORT int ok_gmres(ok_krylov* ws, const ak_problem* p, const double* u, cons
             if (fabs(ws->R[pos]) <= btol) { y[i - 1] = 0.0; inconsistent = 1; }
             else y[i - 1] = y[i - 1] / ws->R[pos];
         }
-        for (int64_t i = 0; i < inner_iter; ++i) ok_axpy(n, y[i], ws->V[i], xr);
+        /* x_k = N V_k y_k (gmres) or Z_k y_k (fgmres) */
+        for (int64_t i = 0; i < inner_iter; ++i) ok_axpy(n, y[i], flexible ? ws->Z[i] : ws->V[i], xr);
+        if (!flexible && precond) {
+            ok_copy(n, ws->pbuf, xr);
+            apply_precond_n(p, u, o, n, ws->pbuf, xr);
+        }
         if (restart) ok_axpy(n, 1.0, xr, x);
         inner_itmax -= inner_iter;
         iter += inner_iter;

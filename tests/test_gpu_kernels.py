@@ -20,6 +20,14 @@ CASES = [
     ("bratu1d", lambda: P.bratu1d(1000)),
     ("bratu1d_odd", lambda: P.bratu1d(1001)),
     ("bratu1d_tiny", lambda: P.bratu1d(3)),
+    ("bratu1d_single_point", lambda: P.bratu1d(1)),
+    ("bratu1d_two_points", lambda: P.bratu1d(2)),
+    ("bratu2d_1x1", lambda: P.bratu2d(1, 1)),
+    ("bratu2d_single_row", lambda: P.bratu2d(257, 1)),
+    ("bratu2d_single_column", lambda: P.bratu2d(1, 300)),
+    ("bratu2d_two_columns", lambda: P.bratu2d(2, 65)),
+    ("bratu2d_warp_edge", lambda: P.bratu2d(4 * 32 + 4, 19)),
+    ("bratu2d_block_edge", lambda: P.bratu2d(4 * 128 + 8, 11)),
     ("bratu2d", lambda: P.bratu2d(64)),
     ("bratu2d_rect", lambda: P.bratu2d(130, 37)),
     ("bratu2d_odd", lambda: P.bratu2d(33, 31)),
@@ -30,6 +38,9 @@ CASES = [
     ("heat2d", lambda: P.heat2d(40)),
     ("heat2d_periodic", lambda: P.heat2d(40, bc=A.AK_BC_PERIODIC, ic="poly")),
     ("heat2d_odd", lambda: P.heat2d(37, ic="poly")),
+    ("heat2d_1x1", lambda: P.heat2d(1, ic="poly")),
+    ("heat2d_2x2_periodic", lambda: P.heat2d(2, bc=A.AK_BC_PERIODIC, ic="poly")),
+    ("heat2d_block_edge_periodic", lambda: P.heat2d(516, bc=A.AK_BC_PERIODIC, ic="poly")),
     ("dg", lambda: P.heat1d_dg(40)),
     ("dg_unaligned_warp", lambda: P.heat1d_dg(77)),
     ("dg_min", lambda: P.heat1d_dg(2)),
@@ -146,6 +157,15 @@ def test_known_answer_jacobian_2x2(nk, ctx):
     v = RNG.random(2)
     nk.mul_(out, J, nk.DeviceVector.from_numpy(v, ctx))
     assert np.allclose(out.numpy(), Jd @ v, rtol=1e-15)
+
+
+def test_empty_vectors(nk, ctx):
+    """n = 0: reductions return 0, element-wise hooks are no-ops (Krylov.jl calls them with length(x))."""
+    x = nk.DeviceVector.from_numpy(np.array([1.0, 2.0]), ctx)
+    assert nk.kdot(0, x, x) == 0.0 and nk.knorm(0, x) == 0.0
+    nk.kaxpy_(0, 2.0, x, x)
+    nk.kscal_(0, 2.0, x)
+    assert np.array_equal(x.numpy(), np.array([1.0, 2.0]))
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 31, 1000, 4099, 1 << 20])

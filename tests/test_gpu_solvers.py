@@ -77,6 +77,35 @@ def test_gmres_options(nk, ctx, oracle, opts, fuse):
     assert np.max(np.abs(np.array(st.residuals) - hr)) <= 1e-9 * hr[0]
 
 
+@pytest.mark.parametrize("algo", ["gmres", "fgmres"])
+def test_right_preconditioned_krylov(nk, ctx, oracle, algo):
+    """kwarg N (src/Ariadne.jl:296-297,324-326) with the inner-GMRES preconditioner of examples/bratu.jl:141-149.
+    FGMRES keeps z_k = N v_k, so its recurrence residual is the true residual; plain GMRES applies N once more at
+    the end (x = N V y), which is only consistent for a linear N — both behaviours are the reference's."""
+    d = P.generic(P.bratu2d(28))
+    b0 = RNG.standard_normal(d["u0"].shape)
+    F_, u, p, _ = P.device_setup(nk, ctx, d)
+    res = u.zero()
+    J = nk.JacobianOperator(F_, res, u, p)
+    b = nk.DeviceVector.from_numpy(b0, ctx)
+    ws = nk.krylov_workspace(algo, nk.KrylovConstructor(res))
+    nk.krylov_solve_(ws, J, b, history=True, rtol=1e-9, N=nk.GmresPreconditioner(J, 5))
+    po = P.oracle_problem(oracle, d)
+    xr, sr, hr = oracle.krylov_solve(po, d["u0"], b0, algo=A.AK_ALGO_FGMRES if algo == "fgmres" else A.AK_ALGO_GMRES,
+                                     rtol=1e-9, hist_cap=1000, precond_n=A.AK_PRECOND_INNER_GMRES, precond_itmax=5)
+    st = ws.stats
+    assert (st.niter, st.solved) == (sr["niter"], sr["solved"])
+    assert np.max(np.abs(np.array(st.residuals) - hr)) <= 1e-9 * hr[0]
+    assert rel(ws.x.numpy(), xr) < 1e-7
+    if algo == "fgmres":
+        r = b.copy()
+        jx = u.zero()
+        nk.mul_(jx, J, ws.x)
+        nk.kaxpy_(u.n, -1.0, jx, r)
+        assert nk.knorm(u.n, r) == pytest.approx(st.residuals[-1], rel=1e-6)
+        assert st.niter < 20  # far fewer outer iterations than unpreconditioned GMRES
+
+
 def test_gmres_zero_rhs_and_basis_growth(nk, ctx, oracle):
     d = P.bratu1d(300)
     x, st = device_krylov(nk, ctx, d, np.zeros(300))
@@ -110,7 +139,8 @@ def newton_opts_for(nk, kw):
     kk = dict(kw.get("krylov_kwargs") or {})
     kk.pop("fuse", None)
     return nk.host._newton_opts(kw.get("tol_rel", 1e-6), kw.get("tol_abs", 1e-12), kw.get("max_niter", 50),
-                                kw.get("forcing", nk.EisenstatWalker()), kw.get("algo", "gmres"), 20, 0, kk)
+                                kw.get("forcing", nk.EisenstatWalker()), kw.get("algo", "gmres"), 20, 0, kk,
+                                N=kw.get("N"))
 
 
 def oracle_sensitivity(oracle, po, u0, o, ntrial=3):
@@ -195,6 +225,10 @@ NEWTON_CASES = [
     ("bratu2d_64_generic", lambda: P.generic(P.bratu2d(64)), {}),
     ("bratu2d_96x40_generic_fixed", lambda: P.generic(P.bratu2d(96, 40)), dict(forcing="fixed")),
     ("bratu1d_200_generic", lambda: P.generic(P.bratu1d(200)), {}),
+    # examples/bratu.jl:151-157: algo = :fgmres with N = (J) -> GmresPreconditioner(J, 5)
+    ("bratu1d_300_fgmres_inner_gmres", lambda: P.generic(P.bratu1d(300)), dict(algo="fgmres", N="gmres5")),
+    ("bratu2d_40_fgmres_inner_gmres", lambda: P.generic(P.bratu2d(40)), dict(algo="fgmres", N="gmres5")),
+    ("bratu2d_32_fgmres_unpreconditioned", lambda: P.generic(P.bratu2d(32)), dict(algo="fgmres")),
 ]
 
 
@@ -204,6 +238,8 @@ def test_newton_matches_oracle(nk, ctx, oracle, name, make, kw, native):
     kw = dict(kw)
     if kw.get("forcing") == "fixed":
         kw["forcing"] = nk.Fixed(0.1)
+    if kw.get("N") == "gmres5":
+        kw["N"] = lambda J: nk.GmresPreconditioner(J, 5)
     u, r, hist, sens = newton_both(nk, ctx, oracle, make(), native, **kw)
     assert r.solved
     assert_newton_parity(u, r, hist, sens)

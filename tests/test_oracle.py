@@ -270,3 +270,19 @@ def test_halo_layout_roundtrip(oracle):
     assert np.array_equal(back[1:-1, 0], comp[:, -1]) and np.array_equal(back[1:-1, -1], comp[:, 0])
     assert np.array_equal(back[0, 1:-1], comp[-1]) and np.array_equal(back[-1, 1:-1], comp[0])
     assert back[0, 0] == comp[-1, -1]
+
+
+def test_fgmres_restatement(oracle):
+    """fgmres! with N = I is gmres! bit for bit; with the inner-GMRES preconditioner of examples/bratu.jl:141-149
+    the recurrence residual of FGMRES equals the true residual (A Z_k = V_{k+1} H_k holds for any z_k)."""
+    d = P.bratu2d(12)
+    po = P.oracle_problem(oracle, d)
+    b = RNG.standard_normal(d["u0"].shape)
+    x0, s0, h0 = oracle.krylov_solve(po, d["u0"], b, rtol=1e-10, hist_cap=1000)
+    x1, s1, h1 = oracle.krylov_solve(po, d["u0"], b, algo=A.AK_ALGO_FGMRES, rtol=1e-10, hist_cap=1000)
+    assert s0["niter"] == s1["niter"] and np.array_equal(x0, x1) and np.array_equal(h0, h1)
+    x2, s2, h2 = oracle.krylov_solve(po, d["u0"], b, algo=A.AK_ALGO_FGMRES, rtol=1e-10, hist_cap=1000,
+                                     precond_n=A.AK_PRECOND_INNER_GMRES, precond_itmax=5)
+    Jd = oracle.dense_jacobian(po, d["u0"])
+    assert s2["solved"] and s2["niter"] < s0["niter"] / 3
+    assert np.linalg.norm(b.ravel() - Jd @ x2.ravel()) == pytest.approx(h2[-1], rel=1e-6)
