@@ -103,7 +103,7 @@ def test_right_preconditioned_krylov(nk, ctx, oracle, algo):
         nk.mul_(jx, J, ws.x)
         nk.kaxpy_(u.n, -1.0, jx, r)
         assert nk.knorm(u.n, r) == pytest.approx(st.residuals[-1], rel=1e-6)
-        assert st.niter < 20  # far fewer outer iterations than unpreconditioned GMRES
+        assert st.niter < 40  # far fewer outer iterations than unpreconditioned GMRES (~100)
 
 
 def test_gmres_zero_rhs_and_basis_growth(nk, ctx, oracle):
