@@ -132,6 +132,10 @@ int allreduce_sum(Ctx* ctx, double* dev, int count);
 // Returns pointers to use as ghost rows (nullptr => implicit zero).
 int exchange_halo_rows(Ctx* ctx, const double* v, int64_t nx, int64_t ny, int32_t bc,
                        const double** lo, const double** hi);
+// 1-D segments: receive the last `nlo` values of the left rank (-> *lo) and the first `nhi` values of the right
+// rank (-> *hi); nullptr at a physical (non-periodic) end.
+int exchange_halo_1d(Ctx* ctx, const double* v, int64_t n, int nlo, int nhi, bool periodic, const double** lo,
+                     const double** hi);
 
 // --- blas1.cu -------------------------------------------------------------------
 int launch_dot(Ctx* ctx, int64_t n, const double* x, const double* y, double* out_dev);

@@ -147,6 +147,32 @@ int exchange_halo_rows(Ctx* ctx, const double* v, int64_t nx, int64_t ny, int32_
     return AK_OK;
 }
 
+int exchange_halo_1d(Ctx* ctx, const double* v, int64_t n, int nlo, int nhi, bool periodic, const double** lo,
+                     const double** hi) {
+    const int P = ctx->nranks, r = ctx->rank;
+    if (ctx->halo_cap < 8) {
+        AK_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->halo_lo) AK_CUDA(cudaFree(ctx->halo_lo));
+        if (ctx->halo_hi) AK_CUDA(cudaFree(ctx->halo_hi));
+        AK_CUDA(cudaMalloc(&ctx->halo_lo, sizeof(double) * 8));
+        AK_CUDA(cudaMalloc(&ctx->halo_hi, sizeof(double) * 8));
+        ctx->halo_cap = 8;
+    }
+    AK_REQUIRE(nlo <= 8 && nhi <= 8 && n >= nlo && n >= nhi, "exchange_halo_1d: bad ghost width");
+    const int left = (r > 0) ? r - 1 : (periodic ? P - 1 : -1);
+    const int right = (r < P - 1) ? r + 1 : (periodic ? 0 : -1);
+    // posting order per peer as in exchange_halo_rows (P == 2 with wrap: both neighbours are the same rank)
+    AK_NCCL(g_nccl.GroupStart());
+    if (right >= 0) AK_NCCL(g_nccl.Send(v + (n - nlo), (size_t)nlo, ncclFloat64, right, ctx->comm->comm, ctx->stream));
+    if (left >= 0) AK_NCCL(g_nccl.Send(v, (size_t)nhi, ncclFloat64, left, ctx->comm->comm, ctx->stream));
+    if (left >= 0) AK_NCCL(g_nccl.Recv(ctx->halo_lo, (size_t)nlo, ncclFloat64, left, ctx->comm->comm, ctx->stream));
+    if (right >= 0) AK_NCCL(g_nccl.Recv(ctx->halo_hi, (size_t)nhi, ncclFloat64, right, ctx->comm->comm, ctx->stream));
+    AK_NCCL(g_nccl.GroupEnd());
+    *lo = left >= 0 ? ctx->halo_lo : nullptr;
+    *hi = right >= 0 ? ctx->halo_hi : nullptr;
+    return AK_OK;
+}
+
 // ---- peer memory -------------------------------------------------------------------------
 static inline size_t p2p_mail_doubles(int nranks) { return (size_t)kMailSlots * nranks * 4; }
 P2PDev Ctx::p2p_dev() const {

@@ -51,6 +51,7 @@ struct StencilArgs {
     unsigned int* ticket;
     const int* stop;
     int32_t coef_from_u;
+    int32_t seg_first, seg_last;  // 1-D slabs: this rank holds the global first / last point
 };
 
 // ---- vector row accessors --------------------------------------------------------------
@@ -335,10 +336,15 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
 
     auto value = [&](int64_t i) -> double {  // scalar access incl. boundary semantics
         double v;
-        if (HEAT) {
-            v = heat1d_bc_value(p.in, i, n, p.bc);
-        } else {  // Bratu: y_0 = y_{N+1} = 0 outside the array
-            if (i < 0 || i >= n) return 0.0;
+        if (i < 0) {  // left of this segment: neighbour rank's last point, or y_0 = 0 (Bratu: bratu.jl:17)
+            if (p.lo == nullptr) return 0.0;
+            v = p.lo[0];
+        } else if (i >= n) {
+            if (p.hi == nullptr) return 0.0;
+            v = p.hi[0];
+        } else if (HEAT && ((i == 0 && p.seg_first) || (i == n - 1 && p.seg_last))) {
+            v = heat1d_bc_value(p.in, i, n, p.bc);  // bc! / periodic_bc! act on the global end points only
+        } else {
             v = p.in[i];
         }
         if (SCALE) v = div_by(v, denom);
@@ -354,17 +360,17 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) cur[i] = div_by(cur[i], denom);
         }
-        if (HEAT) {  // boundary points take their BC value
-            if (x0 == 0) cur[0] = value(0);
-            if (x0 + VEC == n) cur[VEC - 1] = value(n - 1);
+        if (HEAT) {  // the global end points take their BC value
+            if (x0 == 0 && p.seg_first) cur[0] = value(0);
+            if (x0 + VEC == n && p.seg_last) cur[VEC - 1] = value(n - 1);
         }
     }
     double left = __shfl_up_sync(0xffffffffu, cur[VEC - 1], 1);
     double right = __shfl_down_sync(0xffffffffu, cur[0], 1);
     double acc = 0.0;
     if (active) {
-        if (lane == 0) left = (x0 == 0) ? 0.0 : value(x0 - 1);
-        if (lane == 31 || x0 + VEC >= n) right = (x0 + VEC >= n) ? 0.0 : value(x0 + VEC);
+        if (lane == 0) left = value(x0 - 1);
+        if (lane == 31 || x0 + VEC >= n) right = value(x0 + VEC);
         double aux[VEC], o[VEC], cf[VEC];
         if (OP == OP_JVP_BRATU || OP == OP_RES_HEAT) ldv_s<VEC>(p.aux + x0, aux);
 #pragma unroll
@@ -381,7 +387,7 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
             } else {
                 // heat_1D.jl:22: du[i] = a * (u[i+1] - 2u[i] + u[i-1]) / dx^2 ; du[1] = du[end] = 0
                 const int64_t gi = x0 + i;
-                const bool bnd = (gi == 0 || gi == n - 1);
+                const bool bnd = (gi == 0 && p.seg_first) || (gi == n - 1 && p.seg_last);
                 const double du =
                     bnd ? 0.0 : div_by(__dmul_rn(p.a, __dadd_rn(__dsub_rn(e, __dmul_rn(2.0, c)), w)), dx2);
                 if (OP == OP_RES_HEAT) o[i] = __dsub_rn(__dadd_rn(aux[i], __dmul_rn(p.dt, du)), c);
@@ -395,8 +401,8 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
             stv<VEC>(p.in_write + x0, cur);
         } else if (HEAT && p.in_write != nullptr) {
             // the reference's bc!(u) mutates the state / tangent seed in place (heat_1D.jl:16,34-42)
-            if (x0 == 0) p.in_write[0] = cur[0];
-            if (x0 + VEC == n) p.in_write[n - 1] = cur[VEC - 1];
+            if (x0 == 0 && p.seg_first) p.in_write[0] = cur[0];
+            if (x0 + VEC == n && p.seg_last) p.in_write[n - 1] = cur[VEC - 1];
         }
         if (RED == RED_SUMSQ) {
 #pragma unroll
@@ -425,6 +431,8 @@ struct DgArgs {
     double mw;         // (h/2) * w_edge,  w_edge = 1/6
     double dt, c0, c1;
     int rhs_only;      // out = D1m*(D1p*in) without the time-discretisation wrapper
+    const double* lo;  // slabs of elements: the 4 nodes of the left neighbour rank's last element (nullptr: wrap locally)
+    const double* hi;  // first node of the right neighbour rank's first element (nullptr: wrap locally)
     const double* in;
     const double* un;  // residual only
     double* out;
@@ -460,7 +468,7 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
     const Divisor mw = make_divisor(p.mw);
 
     auto load_elem = [&](int64_t el, double (&r)[4]) {
-        ldv<4>(p.in + 4 * el, r);
+        ldv<4>((el < 0) ? p.lo : p.in + 4 * el, r);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (SCALE) r[i] = div_by(r[i], denom);
@@ -480,7 +488,7 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
     double u_next0 = __shfl_down_sync(0xffffffffu, u[0], 1);
     if (active && (lane == 31 || e + 1 >= ne)) {
         const int64_t en = (e + 1 == ne) ? 0 : e + 1;
-        double t = p.in[4 * en];
+        double t = (e + 1 == ne && p.hi != nullptr) ? p.hi[0] : p.in[4 * en];
         if (SCALE) t = div_by(t, denom);
         u_next0 = RESIDUAL ? t : __dmul_rn(p.c0, t);
     }
@@ -492,7 +500,7 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
     // D1m: needs last node of (D1p u) of the element to the left
     double t_prev3 = __shfl_up_sync(0xffffffffu, t1[3], 1);
     if (active && lane == 0) {
-        const int64_t ep = (e == 0) ? ne - 1 : e - 1;
+        const int64_t ep = (e == 0) ? ((p.lo != nullptr) ? -1 : ne - 1) : e - 1;
         double up[4], tp[4];
         load_elem(ep, up);
         dg_local(p.D, p.jac, up, tp);
@@ -696,7 +704,7 @@ static int check_problem(const ak_problem* p) {
     const bool is2d = (p->kind == AK_BRATU2D || p->kind == AK_HEAT2D);
     if (is2d) AK_REQUIRE(p->ny >= 1, "ny must be >= 1");
     if (p->kind == AK_HEAT1D) AK_REQUIRE(p->nx >= 3, "heat 1-D needs >= 3 points (2 boundary points)");
-    if (p->kind == AK_HEAT1D_DG) AK_REQUIRE(p->nx % 4 == 0 && p->nx >= 8, "DG: nx must be 4 * elements, >= 2 elements");
+    if (p->kind == AK_HEAT1D_DG) AK_REQUIRE(p->nx % 4 == 0 && p->nx >= 8, "DG: nx must be 4 * elements, >= 2 elements per rank");
     const bool timedep = (p->kind == AK_HEAT1D || p->kind == AK_HEAT2D || p->kind == AK_HEAT1D_DG);
     if (timedep) {
         AK_REQUIRE(p->scheme == AK_EULER || p->scheme == AK_MIDPOINT || p->scheme == AK_TRAPEZOID,
@@ -709,6 +717,14 @@ static int check_problem(const ak_problem* p) {
             set_error("jvp_mode %d is only implemented as AK_JVP_FD_FUSED for AK_BRATU2D", p->jvp_mode);
             return AK_ERR_UNSUPPORTED;
         }
+    }
+    return AK_OK;
+}
+
+static int check_multi_gpu(const Ctx* ctx, const ak_problem* p) {
+    if (ctx->nranks > 1 && p->kind == AK_HEAT1D && p->bc == AK_BC_PERIODIC) {
+        set_error("periodic_bc! of the 1-D heat example couples the two global end points: single-GPU only");
+        return AK_ERR_UNSUPPORTED;
     }
     return AK_OK;
 }
@@ -729,6 +745,17 @@ static void base_args(Ctx* ctx, const ak_problem* p, StencilArgs& a) {
     a.c1 = (p->scheme == AK_TRAPEZOID) ? p->dt / 2.0 : p->dt;  // tangent of G_Trapezoid!: (dt/2) f'(v) - v
     a.partials = ctx->partials;
     a.ticket = ctx->ticket;
+    a.seg_first = (ctx->rank == 0);
+    a.seg_last = (ctx->rank == ctx->nranks - 1);
+}
+
+// ghost values of a 1-D segment (multi-GPU only): `nlo` values from the left rank's end, `nhi` from the right rank's start
+static int ghost_1d(Ctx* ctx, const double* v, int64_t n, int nlo, int nhi, bool periodic, const double** lo,
+                    const double** hi) {
+    *lo = nullptr;
+    *hi = nullptr;
+    if (ctx->nranks <= 1) return AK_OK;
+    return exchange_halo_1d(ctx, v, n, nlo, nhi, periodic, lo, hi);
 }
 
 // ghost rows for a 2-D slab: neighbours' rows (multi-GPU), own rows (periodic on one GPU) or zeros
@@ -854,6 +881,7 @@ static int launch_jvp_midpoint(Ctx* ctx, const ak_problem* p, double* v, double*
 
 int launch_residual(Ctx* ctx, const ak_problem* p, double* u, double* res, double* sumsq_dev) {
     AK_TRY(check_problem(p));
+    AK_TRY(check_multi_gpu(ctx, p));
     ProfScope prof(ctx, PK_RESIDUAL);
     if (p->scheme == AK_MIDPOINT || p->scheme == AK_TRAPEZOID) {
         if (ctx->nranks > 1) { set_error("Midpoint/Trapezoid are single-GPU in this version"); return AK_ERR_UNSUPPORTED; }
@@ -873,6 +901,7 @@ int launch_residual(Ctx* ctx, const ak_problem* p, double* u, double* res, doubl
         d.ne = p->nx / 4;
         d.dt = p->dt; d.c0 = 1.0; d.c1 = p->dt;
         d.in = u; d.un = p->un; d.out = res;
+        AK_TRY(ghost_1d(ctx, u, p->nx, 4, 1, true, &d.lo, &d.hi));
         d.red_out = sumsq_dev; d.partials = ctx->partials; d.ticket = ctx->ticket;
         AK_REQUIRE(al(u, 32) && al(res, 32) && al(p->un, 32), "DG vectors must be 32-byte aligned");
         AK_TRY(launch_dg(ctx, d, true, false, red));
@@ -887,11 +916,13 @@ int launch_residual(Ctx* ctx, const ak_problem* p, double* u, double* res, doubl
     int rc = AK_OK;
     switch (p->kind) {
         case AK_BRATU1D:
+            AK_TRY(ghost_1d(ctx, u, p->nx, 1, 1, false, &a.lo, &a.hi));
             a.aux_out = p->coef;
             rc = launch1d<OP_RES_BRATU>(ctx, a, false, red);
             break;
         case AK_HEAT1D:
             AK_REQUIRE(p->un != nullptr, "time-dependent residual needs p->un");
+            AK_TRY(ghost_1d(ctx, u, p->nx, 1, 1, false, &a.lo, &a.hi));
             a.aux = p->un;
             a.in_write = u;  // bc!(u) side effect
             rc = launch1d<OP_RES_HEAT>(ctx, a, false, red);
@@ -918,6 +949,7 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     AK_TRY(check_problem(p));
     JvpFusion nofuse;
     if (!f) f = &nofuse;
+    AK_TRY(check_multi_gpu(ctx, p));
     ProfScope prof(ctx, PK_JVP);
     if (p->scheme == AK_MIDPOINT) {
         // composed path: fused normalisation / dot are done as separate launches (same arithmetic)
@@ -946,6 +978,7 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
         d.ne = p->nx / 4;
         d.dt = p->dt; d.c0 = 1.0; d.c1 = (p->scheme == AK_TRAPEZOID) ? p->dt / 2.0 : p->dt;
         d.in = scale ? f->scale_src : v;
+        AK_TRY(ghost_1d(ctx, d.in, p->nx, 4, 1, true, &d.lo, &d.hi));
         d.in_write = v; d.denom = f->denom_dev;
         d.out = out; d.dot_with = f->dot_with; d.red_out = f->dot_dev;
         d.partials = ctx->partials; d.ticket = ctx->ticket; d.stop = f->stop_flag;
@@ -966,11 +999,13 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     int rc = AK_OK;
     switch (p->kind) {
         case AK_BRATU1D:
+            AK_TRY(ghost_1d(ctx, a.in, p->nx, 1, 1, false, &a.lo, &a.hi));
             a.aux = p->coef ? p->coef : u;
             a.coef_from_u = p->coef ? 0 : 1;
             rc = launch1d<OP_JVP_BRATU>(ctx, a, scale, red);
             break;
         case AK_HEAT1D:
+            AK_TRY(ghost_1d(ctx, a.in, p->nx, 1, 1, false, &a.lo, &a.hi));
             if (!scale) a.in_write = v;  // tangent of bc!(u): boundary entries of v are overwritten
             rc = launch1d<OP_JVP_HEAT>(ctx, a, scale, red);
             break;

@@ -42,7 +42,59 @@ def main():
     dist.destroy_process_group()
 
 
+def run_1d_cases(ctx, rank, world, rng, tag):
+    """1-D problems on segments (BASELINE config 5 runs the DG problem on 1 and 8 GPUs)."""
+    import ctypes as C
+    for name, d in [("bratu1d", P.generic(P.bratu1d(203))), ("heat1d", P.heat1d(98)),
+                    ("dg", P.heat1d_dg(max(26, 3 * world), dt=1e-4))]:
+        gn = d["nx"]
+        if d["kind"] == A.AK_HEAT1D_DG:  # whole elements per rank
+            e0, ne = nk.dist.slab_partition(gn // 4, world, rank)
+            g0, n = 4 * e0, 4 * ne
+        else:
+            g0, n = nk.dist.slab_partition(gn, world, rank)
+        sl = slice(g0, g0 + n)
+        u = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
+        v0 = rng.standard_normal(gn)
+        v = nk.DeviceVector.from_numpy(v0[sl], ctx)
+        if d["kind"] == A.AK_BRATU1D:
+            F_, p, po = nk.bratu_, (d["dx"], d["lam"]), P.oracle_problem(O, d)
+        else:
+            un = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
+            f_ = nk.heat_1D_ if d["kind"] == A.AK_HEAT1D else nk.heat_1D_DG_
+            pin = (d["a"], d["dx"], nk.bc_zero_) if d["kind"] == A.AK_HEAT1D else (d["dx"],)
+            F_ = nk.ImplicitResidual(nk.G_Euler_, f_)
+            p = (un, d["dt"], un.zero(), pin, 0.0)
+            po = P.oracle_problem(O, d, un=d["u0"])
+        res, out = u.zero(), u.zero()
+        F_(res, u, p)
+        ref, u_after = O.residual(po, d["u0"])
+        exact = d["kind"] != A.AK_BRATU1D
+        assert (np.array_equal(res.numpy(), ref[sl]) if exact else rel(res.numpy(), ref[sl]) < 1e-14), name
+        assert np.array_equal(u.numpy(), u_after[sl]), name
+        nk.mul_(out, nk.JacobianOperator(F_, res, u, p), v)
+        refj, v_after = O.jvp(po, d["u0"], v0)
+        assert (np.array_equal(out.numpy(), refj[sl]) if exact else rel(out.numpy(), refj[sl]) < 1e-14), name
+        assert np.array_equal(v.numpy(), v_after[sl]), name
+        # one linear solve with every fusion level
+        b0 = rng.standard_normal(gn)
+        if d["kind"] == A.AK_HEAT1D:
+            b0[0] = b0[-1] = 0.0
+        xr, sr, hr = O.krylov_solve(po, d["u0"], b0, rtol=1e-8, hist_cap=100000)
+        for fuse in ("none", "mgs", "full", "pair"):
+            u = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
+            ws = nk.krylov_workspace("gmres", nk.KrylovConstructor(res))
+            nk.krylov_solve_(ws, nk.JacobianOperator(F_, res, u, p), nk.DeviceVector.from_numpy(b0[sl], ctx),
+                             rtol=1e-8, history=True, fuse=fuse)
+            assert (ws.stats.niter, ws.stats.solved) == (sr["niter"], sr["solved"]), (name, fuse, ws.stats.niter, sr)
+            assert np.max(np.abs(np.array(ws.stats.residuals) - hr)) <= 1e-9 * hr[0], (name, fuse)
+            assert rel(ws.x.numpy(), xr[sl]) < 1e-7, (name, fuse)
+        if rank == 0:
+            print(f"[multi-gpu x{world} {tag}] {name}: ok", flush=True)
+
+
 def run_cases(ctx, rank, world, rng, tag):
+    run_1d_cases(ctx, rank, world, rng, tag)
     for name, d, bc in [("bratu2d", P.generic(P.bratu2d(48, 40)), nk.bc_zero_),
                         ("bratu2d_ragged", P.generic(P.bratu2d(37, 29)), nk.bc_zero_),
                         ("heat2d", P.heat2d(36, dt_scale=48.0, ic="poly"), nk.bc_zero_),
