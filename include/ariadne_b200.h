@@ -167,7 +167,9 @@ int ak_residual(ak_ctx* ctx, const ak_problem* p, double* u, double* res, double
 /* out <- J(u) v.  Exact tangent (AK_JVP_ANALYTIC).  `v` is non-const: forward mode
  * through bc!(u) zeroes v's boundary entries (heat_1D.jl:16,34-37).             */
 int ak_jvp(ak_ctx* ctx, const ak_problem* p, const double* u, double* v, double* out);
-/* out <- J(u)^T v  (src/Ariadne.jl:93-107); all shipped stencils have hand adjoints */
+/* out <- J(u)^T v  (src/Ariadne.jl:93-107).  Implemented for the operators that are symmetric in this
+ * layout (Bratu 1-D/2-D, heat 2-D, heat 1-D with bc!) and the 2x2 test system; DG and periodic 1-D heat
+ * return AK_ERR_UNSUPPORTED (GMRES/CG never need J^T).                                              */
 int ak_jvp_transpose(ak_ctx* ctx, const ak_problem* p, const double* u, double* v, double* out);
 
 /* ---- vector-kernel protocol: Krylov.k* hooks, examples/halovector.jl:51-147 -- */

@@ -11,7 +11,7 @@
 #     u, stats = newton_krylov!(Bratu2D(), u, (dx, dy, λ); krylov_kwargs = (; restart = true))
 module AriadneB200
 
-export B200Vector, newton_krylov!, newton_krylov, JacobianOperator, Fixed, EisenstatWalker,
+export B200Vector, newton_krylov!, newton_krylov, JacobianOperator, Fixed, EisenstatWalker, GmresPreconditioner,
        Bratu1D, Bratu2D, Heat1D, Diffusion2D, Heat1DDG, GEuler, solve
 
 using LinearAlgebra
@@ -36,6 +36,7 @@ end
 struct AkKrylovOpts
     atol::Float64; rtol::Float64; itmax::Int64
     restart::Int32; reorthogonalization::Int32; history::Int32; fuse::Int32
+    precond_n::Int32; precond_itmax::Int32
 end
 struct AkKrylovStats
     niter::Int64; solved::Int32; inconsistent::Int32; breakdown::Int32; npass::Int32
@@ -55,7 +56,13 @@ end
 
 const AK_SIMPLE2, AK_BRATU1D, AK_BRATU2D, AK_HEAT1D, AK_HEAT2D, AK_HEAT1D_DG = Int32.(0:5)
 const AK_STEADY, AK_EULER = Int32(0), Int32(1)
-const AK_ALGO = Dict(:gmres => Int32(0), :cg => Int32(1))
+const AK_ALGO = Dict(:gmres => Int32(0), :cg => Int32(1), :fgmres => Int32(2))
+
+"N = (J) -> GmresPreconditioner(J, itmax) of examples/bratu.jl:141-149; run natively as an inner GMRES"
+struct GmresPreconditioner{JOp}
+    J::JOp
+    itmax::Int
+end
 
 # ---- context and device vectors ------------------------------------------------------------------------------------
 mutable struct Context
@@ -192,8 +199,10 @@ function krylov_workspace(algo::Symbol, res::B200Vector; memory = 20, max_basis 
 end
 solution(ws::Workspace) = ccall((:ak_krylov_x, lib), Ptr{Float64}, (Ptr{Cvoid},), ws.h)
 function krylov_solve!(ws::Workspace, J::JacobianOperator, b::B200Vector; atol = √eps(Float64), rtol = √eps(Float64),
-                       itmax = 0, restart = false, reorthogonalization = false, history = false, fuse = 1)
-    o = Ref(AkKrylovOpts(atol, rtol, itmax, restart, reorthogonalization, history, fuse))
+                       itmax = 0, restart = false, reorthogonalization = false, history = false, fuse = 3,
+                       N::Union{Nothing, GmresPreconditioner} = nothing)
+    pn, pit = N === nothing ? (Int32(0), Int32(0)) : (Int32(1), Int32(N.itmax))
+    o = Ref(AkKrylovOpts(atol, rtol, itmax, restart, reorthogonalization, history, fuse, pn, pit))
     st = Ref(AkKrylovStats(0, 0, 0, 0, 0, 0.0, 0.0))
     prob = Ref(problem(J.f, J.u, J.p; coef = J.coef))
     check(ccall((:ak_krylov_solve, lib), Cint,
@@ -203,12 +212,19 @@ function krylov_solve!(ws::Workspace, J::JacobianOperator, b::B200Vector; atol =
     return ws
 end
 
+# ---- multi-GPU: one Julia process per GPU; `id` (128 bytes) comes from rank 0 through Distributed / MPI ------------------
+comm_unique_id() = (id = zeros(UInt8, 128); check(ccall((:ak_comm_unique_id, lib), Cint, (Ptr{UInt8},), id)); id)
+comm_init(ctx::Context, nranks, rank, id::Vector{UInt8}) =
+    check(ccall((:ak_comm_init, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx.h, nranks, rank, id))
+comm_enable_p2p(ctx::Context, halo_doubles) =
+    check(ccall((:ak_comm_enable_p2p, lib), Cint, (Ptr{Cvoid}, Int64), ctx.h, halo_doubles))
+
 # ---- newton_krylov! (src/Ariadne.jl:288-372): the loop is driven from Julia, one ccall per arrowed line ----------------------------
 function newton_krylov!(F!::NativeResidual, u::B200Vector, p = nothing, res::B200Vector = zero(u);
                         tol_rel = 1.0e-6, tol_abs = 1.0e-12, max_niter = 50,
                         forcing::Union{Forcing, Nothing} = EisenstatWalker(), verbose = 0, algo = :gmres,
                         M = nothing, N = nothing, krylov_kwargs = (;), callback = (args...) -> nothing)
-    (M === nothing && N === nothing) || error("preconditioner hooks are not on the native path yet")
+    M === nothing || error("the left preconditioner hook M is not on the native path yet")
     t₀ = time_ns()
     coef = F! isa Union{Bratu1D, Bratu2D} ? similar(u) : nothing      # λ·exp(u) cache shared by residual and JVPs
     cptr = coef === nothing ? Ptr{Float64}(C_NULL) : coef.ptr
@@ -226,6 +242,7 @@ function newton_krylov!(F!::NativeResidual, u::B200Vector, p = nothing, res::B20
     stats = Stats(0, 0, n_res)
     while n_res > tol && stats.outer_iterations <= max_niter
         kwargs = krylov_kwargs
+        N !== nothing && (kwargs = (; N = N(J), kwargs...))
         forcing !== nothing && (kwargs = (; rtol = η, kwargs...))
         Krylov_kcopy!(length(res), rhs, res)                       # copy(res)
         krylov_solve!(workspace, J, rhs; kwargs...)

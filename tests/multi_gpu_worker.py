@@ -80,12 +80,14 @@ def run_1d_cases(ctx, rank, world, rng, tag):
         b0 = rng.standard_normal(gn)
         if d["kind"] == A.AK_HEAT1D:
             b0[0] = b0[-1] = 0.0
-        xr, sr, hr = O.krylov_solve(po, d["u0"], b0, rtol=1e-8, hist_cap=100000)
+        # (a fixed number of iterations: 1-D Laplacians converge only when the Krylov space is exhausted, which
+        #  makes the final count a knife edge)
+        xr, sr, hr = O.krylov_solve(po, d["u0"], b0, rtol=1e-8, itmax=40, hist_cap=100000)
         for fuse in ("none", "mgs", "full", "pair"):
             u = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
             ws = nk.krylov_workspace("gmres", nk.KrylovConstructor(res))
             nk.krylov_solve_(ws, nk.JacobianOperator(F_, res, u, p), nk.DeviceVector.from_numpy(b0[sl], ctx),
-                             rtol=1e-8, history=True, fuse=fuse)
+                             rtol=1e-8, itmax=40, history=True, fuse=fuse)
             assert (ws.stats.niter, ws.stats.solved) == (sr["niter"], sr["solved"]), (name, fuse, ws.stats.niter, sr)
             assert np.max(np.abs(np.array(ws.stats.residuals) - hr)) <= 1e-9 * hr[0], (name, fuse)
             assert rel(ws.x.numpy(), xr[sl]) < 1e-7, (name, fuse)
