@@ -211,7 +211,18 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         ctx.init_comm(world, rank, ids[0])
         if not args.no_p2p:
-            ctx.enable_p2p(args.nx)  # NVLink peer memory: fused reductions + ghost-row push
+            # NVLink peer memory: fused reductions + ghost-row push; if any rank cannot map its
+            # peers (no IPC in this container) every rank falls back to the NCCL path together
+            try:
+                ctx.enable_p2p(args.nx)
+                ok = 1
+            except Exception as e:  # noqa: BLE001
+                print(f"[bench] rank {rank}: peer memory unavailable ({e}); using the NCCL path", file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag[0]) == 0 and ctx.p2p:
+                ctx.use_p2p(False)
 
     nx, ny = args.nx, args.ny
     n = nx * ny
@@ -391,7 +402,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world, nx, ny),
             "gmres_iters_per_sec_global": iters / (ms_max * 1e-3), "gmres_iterations_timed": iters,
-            "final_n_res": n_res, "fuse": args.fuse,
+            "final_n_res": n_res, "fuse": args.fuse, "peer_memory_path": bool(ctx.p2p),
             "clocks": sampler.summary() if sampler else None,
             "e2e": e2e, "gpu_launches": launches_total, "roofline": roofline, "per_iteration": per_iter,
             "cpu_baseline": cpu,

@@ -155,6 +155,8 @@ int ak_comm_init(ak_ctx* ctx, int nranks, int rank, const char id[128]);
  * issues no NCCL call.  `halo_doubles` >= nx of the widest 2-D problem.  Collective call.     */
 int ak_comm_enable_p2p(ak_ctx* ctx, int64_t halo_doubles);
 int ak_comm_p2p_enabled(ak_ctx* ctx);
+/* switch between the peer-memory path and the NCCL path (must be done on all ranks alike) */
+int ak_comm_use_p2p(ak_ctx* ctx, int on);
 int ak_comm_rank(ak_ctx* ctx, int* rank, int* nranks);
 int ak_comm_barrier(ak_ctx* ctx);
 /* ---- residual callback  F!(res,u,p): src/Ariadne.jl:250-256,302,349 --------- */

@@ -51,6 +51,7 @@ SIGNATURES = {
     "ak_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p]),
     "ak_comm_enable_p2p": (C.c_int, [_vp, C.c_int64]),
     "ak_comm_p2p_enabled": (C.c_int, [_vp]),
+    "ak_comm_use_p2p": (C.c_int, [_vp, C.c_int]),
     "ak_comm_rank": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ak_comm_barrier": (C.c_int, [_vp]),
     "ak_residual": (C.c_int, [_vp, C.POINTER(A.ak_problem), _vp, _vp, _dp]),

@@ -501,6 +501,13 @@ AK_API int ak_comm_enable_p2p(ak_ctx* ctx, int64_t halo_doubles) {
     return AK_OK;
 }
 AK_API int ak_comm_p2p_enabled(ak_ctx* ctx) { return (ctx && ctx->c.p2p_on) ? 1 : 0; }
+AK_API int ak_comm_use_p2p(ak_ctx* ctx, int on) {
+    AK_REQUIRE(ctx, "ak_comm_use_p2p: NULL ctx");
+    AK_REQUIRE(!on || ctx->c.p2p_block != nullptr, "ak_comm_use_p2p: peer memory was never mapped");
+    AK_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    ctx->c.p2p_on = (on != 0);
+    return AK_OK;
+}
 
 AK_API int ak_comm_rank(ak_ctx* ctx, int* rank, int* nranks) {
     AK_REQUIRE(ctx, "ak_comm_rank: NULL ctx");

@@ -85,6 +85,9 @@ class Context:
     def p2p(self):
         return bool(self.lib.ak_comm_p2p_enabled(self.h))
 
+    def use_p2p(self, on):
+        L.check(self.lib.ak_comm_use_p2p(self.h, 1 if on else 0))
+
     def barrier(self):
         L.check(self.lib.ak_comm_barrier(self.h))
 
