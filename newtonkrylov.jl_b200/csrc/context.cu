@@ -468,8 +468,18 @@ AK_API int ak_comm_enable_p2p(ak_ctx* ctx, int64_t halo_doubles) {
     AK_CUDA(cudaMemset(c->p2p_block, 0, sizeof(double) * doubles));
     AK_CUDA(cudaHostAlloc((void**)&c->p2p_err, sizeof(int), cudaHostAllocMapped));
     *c->p2p_err = 0;
+    // Every rank goes through the same collectives even when a local step fails, and the verdict is
+    // all-reduced, so that either all ranks switch to the peer-memory path or none does.
+    int failed = 0;
+    char why[256] = "";
     cudaIpcMemHandle_t mine;
-    AK_CUDA(cudaIpcGetMemHandle(&mine, c->p2p_block));
+    memset(&mine, 0, sizeof(mine));
+    cudaError_t e = cudaIpcGetMemHandle(&mine, c->p2p_block);
+    if (e != cudaSuccess) {
+        failed = 1;
+        snprintf(why, sizeof(why), "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+    }
     // exchange the 64-byte handles with an all-gather on the library's own communicator
     char *dsend = nullptr, *drecv = nullptr;
     AK_CUDA(cudaMalloc(&dsend, sizeof(mine)));
@@ -481,22 +491,30 @@ AK_API int ak_comm_enable_p2p(ak_ctx* ctx, int64_t halo_doubles) {
     AK_CUDA(cudaStreamSynchronize(c->stream));
     AK_CUDA(cudaFree(dsend));
     AK_CUDA(cudaFree(drecv));
-    for (int q = 0; q < P; ++q) {
+    for (int q = 0; q < P && !failed; ++q) {
         if (q == c->rank) { c->p2p_peer_block[q] = c->p2p_block; continue; }
-        cudaError_t e = cudaIpcOpenMemHandle(&c->p2p_peer_block[q], all[(size_t)q], cudaIpcMemLazyEnablePeerAccess);
+        e = cudaIpcOpenMemHandle(&c->p2p_peer_block[q], all[(size_t)q], cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
-            set_error("cudaIpcOpenMemHandle(rank %d) failed: %s (peer access over NVLink is required)", q,
-                      cudaGetErrorString(e));
+            failed = 1;
+            c->p2p_peer_block[q] = nullptr;
+            snprintf(why, sizeof(why), "cudaIpcOpenMemHandle(rank %d): %s (peer access over NVLink is required)", q,
+                     cudaGetErrorString(e));
             (void)cudaGetLastError();
-            return AK_ERR_CUDA;
         }
     }
     c->p2p_halo_cap = hcap;
     c->p2p_seq = 0;
-    // nobody may write into a mailbox before its owner has zeroed it
-    AK_CUDA(cudaMemsetAsync(c->dscal + 62, 0, sizeof(double), c->stream));
+    // verdict + barrier: nobody may write into a mailbox before its owner has zeroed it
+    const double mine_failed = failed ? 1.0 : 0.0;
+    AK_CUDA(cudaMemcpyAsync(c->dscal + 62, &mine_failed, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     AK_TRY(allreduce_sum(c, c->dscal + 62, 1));
+    double any_failed = 0.0;
+    AK_CUDA(cudaMemcpyAsync(&any_failed, c->dscal + 62, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     AK_CUDA(cudaStreamSynchronize(c->stream));
+    if (any_failed > 0.0) {
+        set_error("ak_comm_enable_p2p: %s", failed ? why : "another rank could not map its peers");
+        return AK_ERR_CUDA;
+    }
     c->p2p_on = true;
     return AK_OK;
 }
