@@ -202,11 +202,13 @@ enum {
     AK_FUSE_NONE = 0,  /* reference op list: dot, axpy, ..., nrm2, divcopy        */
     AK_FUSE_MGS = 1,   /* axpy_i + dot_{i+1} in one pass, last axpy + nrm2 fused  */
     AK_FUSE_FULL = 2,  /* + (divcopy + JVP + first dot) in one pass               */
-    AK_FUSE_PAIR = 3   /* two Gram-Schmidt steps per sweep over w: the pass that subtracts
+    AK_FUSE_PAIR = 3,  /* two Gram-Schmidt steps per sweep over w: the pass that subtracts
                           h_a v_a + h_b v_b also accumulates <y_a,w>, <y_b,w>, <y_b,y_a>; the
                           coefficient of y_b follows as <y_b,w> - <y_a,w><y_b,y_a>, which is
                           algebraically the modified Gram-Schmidt value (24n bytes per step
                           instead of 32n); falls back to FULL with reorthogonalization    */
+    AK_FUSE_BLOCK4 = 4 /* same with four steps per sweep: 4 projections + 6 Gram entries per
+                          pass, h_b = <y_b,w> - sum_{a<b} h_a <y_b,y_a> (20n bytes per step) */
 };
 
 typedef struct ak_krylov_opts {

@@ -140,73 +140,114 @@ int launch_mgs_step(Ctx* ctx, int64_t n, double* w, const double* vi, const doub
 }
 
 // -----------------------------------------------------------------------------------
-// Pair-wise modified Gram-Schmidt pass (fuse level PAIR): two Gram-Schmidt steps per sweep over w.
-//   NAX  axpys : w <- w - h_a v_a [- h_b v_b]     with (h_a, h_b) = (t[0], t[1] - t[0] t[2]) from `tin`
-//   NRED = 1   : out[0] = <y_a, w_new>
-//   NRED = 2   : out = { <y_a,w_new>, <y_b,w_new>, <y_b,y_a> }   (h of y_b follows as d2 - d1 g: algebraically the
-//                modified Gram-Schmidt coefficient <y_b, w_new - d1 y_a>, without a second sweep over w)
-//   NRED = 3   : out[0] = <w_new, w_new>
-// Algorithmic bytes per launch: 8n (2 [w in/out] + NAX + number of y vectors); 48n for NAX = NRED = 2,
-// i.e. 24n per Gram-Schmidt step instead of 32n.
+// Blocked modified Gram-Schmidt pass (fuse levels PAIR = blocks of 2, BLOCK4 = blocks of 4): up to kBlkMax
+// Gram-Schmidt steps per sweep over w.
+//   NAX axpys  : w <- w - sum_{b<NAX} h_b v_b, h = block_coefficients(raw sums of that block, `tin`)
+//   NRED 1..4  : raw sums of the next block: t[b] = <y_b, w_new>, t[gram_index(b,a)] = <y_b, y_a> (a < b).
+//                h_b = t[b] - sum_{a<b} h_a <y_b,y_a> is algebraically the modified Gram-Schmidt coefficient
+//                <y_b, w_new - sum_{a<b} h_a y_a>, obtained without another sweep over w.
+//   NRED 5     : out[0] = <w_new, w_new>
+// Algorithmic bytes per launch: 8n (2 [w in/out] + NAX + number of y vectors): 48n for blocks of 2 (24n per
+// Gram-Schmidt step), 80n for blocks of 4 (20n per step), instead of 32n per step for axpy_i + dot_{i+1}.
 // -----------------------------------------------------------------------------------
-struct PairP2P {      // fused collective of the pair-wise pass (all zero / null when not used)
+struct BlkPtrs {
+    const double* va[kBlkMax];  // vectors to subtract
+    const double* ya[kBlkMax];  // vectors to project on
+};
+struct BlockP2P {     // fused collective of the blocked pass (all zero / null when not used)
     P2PDev pd;
-    unsigned long long seq_in;   // record to wait for (reduced sums of the pair being subtracted), 0 = read `tin`
+    unsigned long long seq_in;   // record to wait for (reduced sums of the block being subtracted), 0 = read `tin`
     unsigned long long seq_out;  // record to post (this pass's sums), 0 = store to `out`
     double* tin_store;           // where block 0 leaves the reduced incoming sums for the Givens kernel
     P2PHalo halo;                // boundary-row push (final pass only)
 };
+constexpr int kRedSumsq = 5;
 
-template <int NAX, int NRED, bool VEC, bool P2P>
-__global__ void __launch_bounds__(kThreads) k_mgs_pair(double* __restrict__ w, const double* __restrict__ va,
-                                                       const double* __restrict__ vb, const double* __restrict__ tin,
-                                                       const double* __restrict__ ya, const double* __restrict__ yb,
-                                                       double* __restrict__ out, double* __restrict__ partials,
-                                                       unsigned int* ticket, int64_t n, const int* __restrict__ stop,
-                                                       const PairP2P pp) {
+template <int NAX, int NRED, bool P2P>
+__global__ void __launch_bounds__(kThreads, 2) k_mgs_block(double* __restrict__ w, const BlkPtrs bp,
+                                                           const double* __restrict__ tin, double* __restrict__ out,
+                                                           double* __restrict__ partials, unsigned int* ticket,
+                                                           int64_t n, const int* __restrict__ stop, const int vec,
+                                                           const BlockP2P pp) {
+    constexpr int NY = (NRED == kRedSumsq) ? 0 : NRED;
+    constexpr int NS = (NRED == kRedSumsq) ? 1 : sums_used(NRED);
     __shared__ double sh[32];
-    __shared__ double sh4[4 * kMaxPeers];
+    __shared__ double shm[kBlkSums * kMaxPeers];
     if (stop != nullptr && *stop != 0) return;
-    double ha = 0.0, hb = 0.0;
+    double h[kBlkMax] = {0.0, 0.0, 0.0, 0.0};  // negated coefficients of the block being subtracted
     if (NAX >= 1) {
-        double t[3];
+        constexpr int NIN = sums_used(NAX);
+        double t[kBlkSums];
         if (P2P && pp.seq_in != 0) {
-            mail_wait_sum(pp.pd, pp.seq_in, t, sh4);
+            mail_wait_sum(pp.pd, pp.seq_in, t, NIN, shm);
             if (blockIdx.x == 0 && threadIdx.x == 0 && pp.tin_store != nullptr) {
-                pp.tin_store[0] = t[0]; pp.tin_store[1] = t[1]; pp.tin_store[2] = t[2];
+#pragma unroll
+                for (int c = 0; c < NIN; ++c) pp.tin_store[c] = t[c];
             }
         } else {
-            t[0] = tin[0]; t[1] = (NAX == 2) ? tin[1] : 0.0; t[2] = (NAX == 2) ? tin[2] : 0.0;
+#pragma unroll
+            for (int c = 0; c < kBlkSums; ++c) t[c] = (c < NIN) ? tin[c] : 0.0;
         }
-        ha = -t[0];
-        if (NAX == 2) hb = -pair_second_h(t[0], t[1], t[2]);
+        block_coefficients(t, NAX, h);
+#pragma unroll
+        for (int b = 0; b < kBlkMax; ++b) h[b] = -h[b];
     }
-    double s0a = 0.0, s0b = 0.0, s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
+    double sA[NS], sB[NS];  // two accumulator sets (even / odd elements of a 256-bit word)
+#pragma unroll
+    for (int c = 0; c < NS; ++c) sA[c] = sB[c] = 0.0;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-    const bool push = P2P && NRED == 3 && (pp.halo.down_hi != nullptr || pp.halo.up_lo != nullptr);
+    const bool push = P2P && NRED == kRedSumsq && (pp.halo.down_hi != nullptr || pp.halo.up_lo != nullptr);
     const int64_t hnx = pp.halo.nx;
-    auto body = [&](double& wj, double xa, double xb, double a, double b, double& t0, double& t1, double& t2) {
-        if (NAX >= 1) wj = fma(ha, xa, wj);   // same order as two successive kaxpy!
-        if (NAX == 2) wj = fma(hb, xb, wj);
-        if (NRED == 1) t0 = fma(a, wj, t0);
-        if (NRED == 2) { t0 = fma(a, wj, t0); t1 = fma(b, wj, t1); t2 = fma(b, a, t2); }
-        if (NRED == 3) t0 = fma(wj, wj, t0);
+    auto body = [&](double& wj, const double (&x)[kBlkMax], const double (&y)[kBlkMax], double (&s)[NS]) {
+#pragma unroll
+        for (int b = 0; b < NAX; ++b) wj = fma(h[b], x[b], wj);  // same order as successive kaxpy!
+        if (NRED == kRedSumsq) {
+            s[0] = fma(wj, wj, s[0]);
+        } else {
+#pragma unroll
+            for (int b = 0; b < NY; ++b) {
+                s[b] = fma(y[b], wj, s[b]);
+#pragma unroll
+                for (int a = 0; a < b; ++a) s[gram_index(b, a)] = fma(y[b], y[a], s[gram_index(b, a)]);
+            }
+        }
     };
-    if (VEC) {
+    auto scalar_elem = [&](int64_t j) {
+        double wj = w[j];
+        double x[kBlkMax] = {0, 0, 0, 0}, y[kBlkMax] = {0, 0, 0, 0};
+#pragma unroll
+        for (int b = 0; b < NAX; ++b) x[b] = bp.va[b][j];
+#pragma unroll
+        for (int b = 0; b < NY; ++b) y[b] = bp.ya[b][j];
+        body(wj, x, y, sA);
+        if (NAX > 0) w[j] = wj;
+    };
+    if (vec) {
         const int64_t n4 = n >> 2;
         for (int64_t i = tid; i < n4; i += nth) {
             const int64_t j = i << 2;
             d4 wv = (NAX > 0) ? ld4(w + j) : ld4_stream(w + j);
-            d4 xa = {0, 0, 0, 0}, xb = {0, 0, 0, 0}, a = {0, 0, 0, 0}, b = {0, 0, 0, 0};
-            if (NAX >= 1) xa = ld4_stream(va + j);
-            if (NAX == 2) xb = ld4_stream(vb + j);
-            if (NRED == 1 || NRED == 2) a = ld4_stream(ya + j);
-            if (NRED == 2) b = ld4_stream(yb + j);
-            body(wv.x, xa.x, xb.x, a.x, b.x, s0a, s1a, s2a);
-            body(wv.y, xa.y, xb.y, a.y, b.y, s0b, s1b, s2b);
-            body(wv.z, xa.z, xb.z, a.z, b.z, s0a, s1a, s2a);
-            body(wv.w, xa.w, xb.w, a.w, b.w, s0b, s1b, s2b);
+            d4 xv[kBlkMax], yv[kBlkMax];
+#pragma unroll
+            for (int b = 0; b < kBlkMax; ++b) {
+                xv[b] = d4{0, 0, 0, 0};
+                yv[b] = d4{0, 0, 0, 0};
+            }
+#pragma unroll
+            for (int b = 0; b < NAX; ++b) xv[b] = ld4_stream(bp.va[b] + j);
+#pragma unroll
+            for (int b = 0; b < NY; ++b) yv[b] = ld4_stream(bp.ya[b] + j);
+            {
+                const double x0[kBlkMax] = {xv[0].x, xv[1].x, xv[2].x, xv[3].x}, y0[kBlkMax] = {yv[0].x, yv[1].x, yv[2].x, yv[3].x};
+                const double x1[kBlkMax] = {xv[0].y, xv[1].y, xv[2].y, xv[3].y}, y1[kBlkMax] = {yv[0].y, yv[1].y, yv[2].y, yv[3].y};
+                const double x2[kBlkMax] = {xv[0].z, xv[1].z, xv[2].z, xv[3].z}, y2[kBlkMax] = {yv[0].z, yv[1].z, yv[2].z, yv[3].z};
+                const double x3[kBlkMax] = {xv[0].w, xv[1].w, xv[2].w, xv[3].w}, y3[kBlkMax] = {yv[0].w, yv[1].w, yv[2].w, yv[3].w};
+                body(wv.x, x0, y0, sA);
+                body(wv.y, x1, y1, sB);
+                body(wv.z, x2, y2, sA);
+                body(wv.w, x3, y3, sB);
+            }
             if (NAX > 0) st4(w + j, wv);
             if (push) {  // boundary rows of the finished w go straight into the neighbours' ghost rows (NVLink)
                 if (pp.halo.down_hi != nullptr && j < hnx) st4(pp.halo.down_hi + j, wv);
@@ -214,53 +255,68 @@ __global__ void __launch_bounds__(kThreads) k_mgs_pair(double* __restrict__ w, c
             }
         }
         const int64_t j = (n4 << 2) + tid;
-        if (j < n) {
-            double wj = w[j];
-            body(wj, NAX >= 1 ? va[j] : 0.0, NAX == 2 ? vb[j] : 0.0, (NRED == 1 || NRED == 2) ? ya[j] : 0.0,
-                 NRED == 2 ? yb[j] : 0.0, s0a, s1a, s2a);
-            if (NAX > 0) w[j] = wj;
-        }
+        if (j < n) scalar_elem(j);
     } else {
-        for (int64_t j = tid; j < n; j += nth) {
-            double wj = w[j];
-            body(wj, NAX >= 1 ? va[j] : 0.0, NAX == 2 ? vb[j] : 0.0, (NRED == 1 || NRED == 2) ? ya[j] : 0.0,
-                 NRED == 2 ? yb[j] : 0.0, s0a, s1a, s2a);
-            if (NAX > 0) w[j] = wj;
-        }
+        for (int64_t j = tid; j < n; j += nth) scalar_elem(j);
     }
-    if (P2P && pp.seq_out != 0) {
-        const double r0 = block_sum(s0a + s0b, sh);
-        const double r1 = (NRED == 2) ? block_sum(s1a + s1b, sh) : 0.0;
-        const double r2 = (NRED == 2) ? block_sum(s2a + s2b, sh) : 0.0;
-        double tot[3];
-        if (grid_reduce3(r0, r1, r2, partials, ticket, blockIdx.x, gridDim.x, sh, tot, push))
-            mail_post(pp.pd, pp.seq_out, tot[0], tot[1], tot[2]);
-    } else if (NRED == 2) {
-        const double r0 = block_sum(s0a + s0b, sh);
-        const double r1 = block_sum(s1a + s1b, sh);
-        const double r2 = block_sum(s2a + s2b, sh);
-        grid_sum_finish3(r0, r1, r2, partials, ticket, blockIdx.x, gridDim.x, out, sh);
-    } else if (NRED != 0) {
-        const double r0 = block_sum(s0a + s0b, sh);
-        grid_sum_finish(r0, partials, ticket, blockIdx.x, gridDim.x, out, sh);
+    double r[NS];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) r[c] = sA[c] + sB[c];
+    double tot[NS];
+    if (grid_reduce_n<NS>(r, partials, ticket, blockIdx.x, gridDim.x, sh, tot, push)) {
+        if (P2P && pp.seq_out != 0) {
+            mail_post(pp.pd, pp.seq_out, tot, NS);
+        } else {
+#pragma unroll
+            for (int c = 0; c < NS; ++c) out[c] = tot[c];
+        }
     }
 }
 
-// va/vb: vectors to subtract (0, 1 or 2 non-null), tin: raw triple of that pair; ya/yb: vectors to project on
-// (0, 1 or 2 non-null); want_sumsq: ||w_new||^2 instead.  out receives 3 doubles (NRED = 2) or 1.
-// With `p2p` (multi-GPU, peer memory enabled) the sums travel through the peers' mailboxes instead of NCCL.
-int launch_mgs_pair(Ctx* ctx, int64_t n, double* w, const double* va, const double* vb, const double* tin,
-                    const double* ya, const double* yb, int want_sumsq, double* out, const int* stop,
-                    const PairComm* pc) {
+template <int NAX, int NRED>
+static int launch_mgs_block_t(Ctx* ctx, int64_t n, double* w, const BlkPtrs& bp, const double* tin, double* out,
+                              const int* stop, bool vec, bool p2p, const BlockP2P& pp, int cls) {
+    static int occ[2] = {0, 0};  // resident blocks per SM of this instantiation (queried once)
+    if (occ[p2p] == 0) {
+        int nb = 0;
+        cudaError_t e = p2p ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mgs_block<NAX, NRED, true>, kThreads, 0)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mgs_block<NAX, NRED, false>, kThreads, 0);
+        AK_CUDA(e);
+        occ[p2p] = nb < 1 ? 1 : (nb > 4 ? 4 : nb);
+    }
+    int64_t need = (n + (int64_t)kThreads * 4 - 1) / ((int64_t)kThreads * 4);
+    const int64_t cap = (int64_t)ctx->num_sms * occ[p2p];  // one wave of resident blocks, grid-stride
+    const int blocks = (int)(need < 1 ? 1 : (need < cap ? need : cap));
+    ProfScope prof(ctx, cls);
+    if (p2p)
+        k_mgs_block<NAX, NRED, true><<<blocks, kThreads, 0, ctx->stream>>>(w, bp, tin, out, ctx->partials, ctx->ticket,
+                                                                           n, stop, vec ? 1 : 0, pp);
+    else
+        k_mgs_block<NAX, NRED, false><<<blocks, kThreads, 0, ctx->stream>>>(w, bp, tin, out, ctx->partials, ctx->ticket,
+                                                                            n, stop, vec ? 1 : 0, pp);
+    return AK_OK;
+}
+
+// va[0..nax): vectors to subtract, tin: raw sums of that block; ya[0..ny): vectors to project on;
+// want_sumsq: ||w_new||^2 instead.  out receives sums_used(ny) doubles, or 1.
+// With `pc` (multi-GPU, peer memory enabled) the sums travel through the peers' mailboxes instead of NCCL.
+int launch_mgs_block(Ctx* ctx, int64_t n, double* w, const double* const* va, int nax, const double* tin,
+                     const double* const* ya, int ny, int want_sumsq, double* out, const int* stop,
+                     const BlockComm* pc) {
     if (n <= 0) return AK_OK;
-    const int nax = va ? (vb ? 2 : 1) : 0;
-    const int nred = want_sumsq ? 3 : (ya ? (yb ? 2 : 1) : 0);
-    const bool vec = aligned32(w) && aligned32(va) && aligned32(vb) && aligned32(ya) && aligned32(yb);
-    const int blocks = stream_blocks(ctx, n, 4);
-    const int cls = nax == 2 && nred == 2 ? PK_MGS_PAIR : (nax > 0 ? (nred == 3 ? PK_MGS_AXPY_NRM : PK_MGS_PAIR_EDGE)
-                                                                       : PK_MGS_PAIR_EDGE);
+    if (nax < 0 || nax > kBlkMax || ny < 0 || ny > kBlkMax || (ny == 0 && !want_sumsq) || (ny > 0 && want_sumsq)) {
+        set_error("launch_mgs_block: bad block shape (nax = %d, ny = %d, sumsq = %d)", nax, ny, want_sumsq);
+        return AK_ERR_ARG;
+    }
+    const int nred = want_sumsq ? kRedSumsq : ny;
+    BlkPtrs bp{};
+    bool vec = aligned32(w);
+    for (int b = 0; b < nax; ++b) { bp.va[b] = va[b]; vec = vec && aligned32(va[b]); }
+    for (int b = 0; b < ny; ++b) { bp.ya[b] = ya[b]; vec = vec && aligned32(ya[b]); }
+    const int cls = (nax >= 2 && nax == ny) ? PK_MGS_PAIR
+                                            : ((nax > 0 && nred == kRedSumsq) ? PK_MGS_AXPY_NRM : PK_MGS_PAIR_EDGE);
     const bool p2p = pc != nullptr && ctx->p2p_on && ctx->nranks > 1;
-    PairP2P pp{};
+    BlockP2P pp{};
     if (p2p) {
         pp.pd = ctx->p2p_dev();
         pp.seq_in = pc->seq_in;
@@ -270,30 +326,19 @@ int launch_mgs_pair(Ctx* ctx, int64_t n, double* w, const double* va, const doub
         // the vector path pushes whole 256-bit words: rows must be 32-byte multiples
         if (pp.halo.nx % 4 != 0 || n % 4 != 0 || !vec) pp.halo.down_hi = pp.halo.up_lo = nullptr;
     }
-#define AK_PAIR(A, R)                                                                                               \
-    if (nax == A && nred == R) {                                                                                    \
-        ProfScope prof(ctx, cls);                                                                                   \
-        if (p2p && vec)                                                                                             \
-            k_mgs_pair<A, R, true, true><<<blocks, kThreads, 0, ctx->stream>>>(w, va, vb, tin, ya, yb, out,        \
-                                                                               ctx->partials, ctx->ticket, n, stop, pp); \
-        else if (p2p)                                                                                               \
-            k_mgs_pair<A, R, false, true><<<blocks, kThreads, 0, ctx->stream>>>(w, va, vb, tin, ya, yb, out,       \
-                                                                                ctx->partials, ctx->ticket, n, stop, pp); \
-        else if (vec)                                                                                               \
-            k_mgs_pair<A, R, true, false><<<blocks, kThreads, 0, ctx->stream>>>(w, va, vb, tin, ya, yb, out,       \
-                                                                                ctx->partials, ctx->ticket, n, stop, pp); \
-        else                                                                                                        \
-            k_mgs_pair<A, R, false, false><<<blocks, kThreads, 0, ctx->stream>>>(w, va, vb, tin, ya, yb, out,      \
-                                                                                 ctx->partials, ctx->ticket, n, stop, pp); \
-    }
-    AK_PAIR(0, 1) AK_PAIR(0, 2) AK_PAIR(1, 1) AK_PAIR(1, 2) AK_PAIR(1, 3) AK_PAIR(2, 1) AK_PAIR(2, 2) AK_PAIR(2, 3)
-#undef AK_PAIR
+    int rc = AK_ERR_ARG;
+#define AK_BLK(A, R) \
+    if (nax == A && nred == R) rc = launch_mgs_block_t<A, R>(ctx, n, w, bp, tin, out, stop, vec, p2p, pp, cls);
+    AK_BLK(0, 1) AK_BLK(0, 2) AK_BLK(0, 3) AK_BLK(0, 4)
+    AK_BLK(1, 1) AK_BLK(1, 2) AK_BLK(1, 3) AK_BLK(1, 4) AK_BLK(1, 5)
+    AK_BLK(2, 1) AK_BLK(2, 2) AK_BLK(2, 3) AK_BLK(2, 4) AK_BLK(2, 5)
+    AK_BLK(3, 1) AK_BLK(3, 2) AK_BLK(3, 3) AK_BLK(3, 4) AK_BLK(3, 5)
+    AK_BLK(4, 1) AK_BLK(4, 2) AK_BLK(4, 3) AK_BLK(4, 4) AK_BLK(4, 5)
+#undef AK_BLK
+    AK_TRY(rc);
     ctx->launches++;
     AK_CUDA(cudaGetLastError());
-    if (!p2p) {
-        if (nred == 2) AK_TRY(allreduce_sum(ctx, out, 3));
-        else if (nred != 0) AK_TRY(allreduce_sum(ctx, out, 1));
-    }
+    if (!p2p) AK_TRY(allreduce_sum(ctx, out, want_sumsq ? 1 : sums_used(ny)));
     return AK_OK;
 }
 

@@ -110,52 +110,22 @@ AK_DEV void grid_sum_finish(double block_partial_in_t0, double* partials, unsign
     }
 }
 
-// Three sums at once (pair-wise Gram-Schmidt: <y_a,w>, <y_b,w>, <y_b,y_a>); same ordering rules.
-// partials layout: [3 * bid + c].
-AK_DEV void grid_sum_finish3(double s0, double s1, double s2, double* partials, unsigned int* ticket, int bid,
-                             int nblocks, double* out, double* sh) {
-    __shared__ bool is_last3;
-    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
-    const int nthreads = blockDim.x * blockDim.y;
-    if (tid == 0) {
-        partials[3 * bid + 0] = s0;
-        partials[3 * bid + 1] = s1;
-        partials[3 * bid + 2] = s2;
-        __threadfence();
-        unsigned int t = atomicAdd(ticket, 1u);
-        is_last3 = (t == (unsigned int)(nblocks - 1));
-    }
-    __syncthreads();
-    if (is_last3) {
-        __threadfence();
-        double a[3] = {0.0, 0.0, 0.0};
-        for (int i = tid; i < nblocks; i += nthreads) {
-            a[0] += __ldcg(partials + 3 * i + 0);
-            a[1] += __ldcg(partials + 3 * i + 1);
-            a[2] += __ldcg(partials + 3 * i + 2);
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const double r = block_sum(a[c], sh);
-            if (tid == 0) out[c] = r;
-        }
-        if (tid == 0) *ticket = 0u;
-    }
-}
-
-// Same, but the three totals are handed back to flat thread 0 of the last block (returns true there only),
-// so that the caller decides where they go (device memory, or the peers' mailboxes over NVLink).
+// NS sums at once, handed back to flat thread 0 of the last block (returns true there only), so that the caller
+// decides where they go (device memory, or the peers' mailboxes over NVLink).  partials layout [NS * bid + c].
 // `sysfence`: the block also issued stores to peer memory that must be visible before the result is published.
-AK_DEV bool grid_reduce3(double s0, double s1, double s2, double* partials, unsigned int* ticket, int bid, int nblocks,
-                         double* sh, double (&r)[3], bool sysfence) {
+template <int NS>
+AK_DEV bool grid_reduce_n(const double (&v)[NS], double* partials, unsigned int* ticket, int bid, int nblocks,
+                          double* sh, double (&r)[NS], bool sysfence) {
     __shared__ bool is_last_r;
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
     const int nthreads = blockDim.x * blockDim.y;
+    double b[NS];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) b[c] = block_sum(v[c], sh);
     __syncthreads();  // all stores of the block precede thread 0's fence
     if (tid == 0) {
-        partials[3 * bid + 0] = s0;
-        partials[3 * bid + 1] = s1;
-        partials[3 * bid + 2] = s2;
+#pragma unroll
+        for (int c = 0; c < NS; ++c) partials[NS * bid + c] = b[c];
         if (sysfence) __threadfence_system(); else __threadfence();
         unsigned int t = atomicAdd(ticket, 1u);
         is_last_r = (t == (unsigned int)(nblocks - 1));
@@ -163,20 +133,21 @@ AK_DEV bool grid_reduce3(double s0, double s1, double s2, double* partials, unsi
     __syncthreads();
     if (!is_last_r) return false;
     __threadfence();
-    double a[3] = {0.0, 0.0, 0.0};
+    double a[NS];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) a[c] = 0.0;
     for (int i = tid; i < nblocks; i += nthreads) {
-        a[0] += __ldcg(partials + 3 * i + 0);
-        a[1] += __ldcg(partials + 3 * i + 1);
-        a[2] += __ldcg(partials + 3 * i + 2);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) a[c] += __ldcg(partials + NS * i + c);
     }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) r[c] = block_sum(a[c], sh);
+    for (int c = 0; c < NS; ++c) r[c] = block_sum(a[c], sh);
     if (tid == 0) *ticket = 0u;
     return tid == 0;
 }
 
 // ---- mailbox all-reduce over NVLink peer memory ---------------------------------------------------------
-// record (slot, src) = 4 doubles {v0, v1, v2, tag}; tag = sequence number of the collective (never reused)
+// record (slot, src) = kMailRec doubles {kBlkSums sums, tag, pad}; tag = sequence number of the collective
 AK_DEV void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -185,30 +156,28 @@ AK_DEV unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// ONE thread: deposit this rank's partial sums in every rank's mailbox (own included)
-AK_DEV void mail_post(const P2PDev& pd, unsigned long long seq, double v0, double v1, double v2) {
+// ONE thread: deposit this rank's `ns` partial sums in every rank's mailbox (own included)
+AK_DEV void mail_post(const P2PDev& pd, unsigned long long seq, const double* vals, int ns) {
     const int slot = (int)(seq % kMailSlots);
-    __threadfence_system();  // halo rows pushed by this grid are visible before the record is
+    __threadfence_system();  // ghost rows pushed by this grid are visible before the record is
     for (int q = 0; q < pd.nranks; ++q) {
-        double* rec = pd.mail_peer[q] + ((size_t)slot * pd.nranks + pd.rank) * 4;
-        rec[0] = v0;
-        rec[1] = v1;
-        rec[2] = v2;
+        double* rec = pd.mail_peer[q] + ((size_t)slot * pd.nranks + pd.rank) * kMailRec;
+        for (int c = 0; c < ns; ++c) rec[c] = vals[c];
     }
     __threadfence_system();
     for (int q = 0; q < pd.nranks; ++q) {
-        double* rec = pd.mail_peer[q] + ((size_t)slot * pd.nranks + pd.rank) * 4;
-        st_release_sys_u64(reinterpret_cast<unsigned long long*>(rec + 3), seq);
+        double* rec = pd.mail_peer[q] + ((size_t)slot * pd.nranks + pd.rank) * kMailRec;
+        st_release_sys_u64(reinterpret_cast<unsigned long long*>(rec + kBlkSums), seq);
     }
 }
 // Whole block: wait until every rank's record `seq` has arrived in the local mailbox and add them in rank
-// order (bit-identical on every rank).  Result in out[0..2] for all threads.  `sh4` >= 4 * kMaxPeers doubles.
-AK_DEV void mail_wait_sum(const P2PDev& pd, unsigned long long seq, double (&out)[3], double* sh4) {
+// order (bit-identical on every rank).  Result in out[0..ns) for all threads.  `shm` >= kMaxPeers * kBlkSums doubles.
+AK_DEV void mail_wait_sum(const P2PDev& pd, unsigned long long seq, double (&out)[kBlkSums], int ns, double* shm) {
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
     const int slot = (int)(seq % kMailSlots);
     if (tid < pd.nranks) {
-        const double* rec = pd.mail_local + ((size_t)slot * pd.nranks + tid) * 4;
-        const unsigned long long* tag = reinterpret_cast<const unsigned long long*>(rec + 3);
+        const double* rec = pd.mail_local + ((size_t)slot * pd.nranks + tid) * kMailRec;
+        const unsigned long long* tag = reinterpret_cast<const unsigned long long*>(rec + kBlkSums);
         const long long t0 = clock64();
         while (ld_acquire_sys_u64(tag) != seq) {
             if (clock64() - t0 > pd.spin_cycles) {  // a peer never produced this record: flag it, do not hang
@@ -216,22 +185,31 @@ AK_DEV void mail_wait_sum(const P2PDev& pd, unsigned long long seq, double (&out
                 break;
             }
         }
-        sh4[4 * tid + 0] = __ldcv(rec + 0);
-        sh4[4 * tid + 1] = __ldcv(rec + 1);
-        sh4[4 * tid + 2] = __ldcv(rec + 2);
+        for (int c = 0; c < ns; ++c) shm[kBlkSums * tid + c] = __ldcv(rec + c);
     }
     __syncthreads();
-    out[0] = out[1] = out[2] = 0.0;
-    for (int q = 0; q < pd.nranks; ++q) {
-        out[0] += sh4[4 * q + 0];
-        out[1] += sh4[4 * q + 1];
-        out[2] += sh4[4 * q + 2];
-    }
+#pragma unroll
+    for (int c = 0; c < kBlkSums; ++c) out[c] = 0.0;
+    for (int q = 0; q < pd.nranks; ++q)
+        for (int c = 0; c < ns; ++c) out[c] += shm[kBlkSums * q + c];
     __syncthreads();
 }
 
-// h of the second vector of a pair from the raw sums (d1 = <y_a,w>, d2 = <y_b,w>, g = <y_b,y_a>):
-// <y_b, w - d1 y_a> = d2 - d1 g.  One definition shared by the vector kernels and the Givens kernel.
-AK_DEV double pair_second_h(double d1, double d2, double g) { return __dsub_rn(d2, __dmul_rn(d1, g)); }
+// Raw sums of a blocked pass, fixed layout: t[b] = <y_b, w> (b < 4), t[4 + b(b-1)/2 + a] = <y_b, y_a> (a < b).
+// Modified Gram-Schmidt coefficients of the block:  h_b = <y_b, w - sum_{a<b} h_a y_a> = t[b] - sum_{a<b} h_a <y_b,y_a>.
+// One definition shared by the vector kernels and the Givens kernel so that both see the same bits.
+AK_DEV int gram_index(int b, int a) { return kBlkMax + b * (b - 1) / 2 + a; }
+AK_DEV void block_coefficients(const double* t, int m, double (&h)[kBlkMax]) {
+#pragma unroll
+    for (int b = 0; b < kBlkMax; ++b) {
+        double acc = 0.0;
+        if (b < m) {
+            acc = t[b];
+            for (int a = 0; a < b; ++a) acc = __dsub_rn(acc, __dmul_rn(h[a], t[gram_index(b, a)]));
+        }
+        h[b] = acc;
+    }
+}
+__host__ __device__ constexpr int sums_used(int m) { return m <= 1 ? 1 : kBlkMax + m * (m - 1) / 2; }  // prefix of the record that is live
 
 }  // namespace ak

@@ -174,7 +174,7 @@ int exchange_halo_1d(Ctx* ctx, const double* v, int64_t n, int nlo, int nhi, boo
 }
 
 // ---- peer memory -------------------------------------------------------------------------
-static inline size_t p2p_mail_doubles(int nranks) { return (size_t)kMailSlots * nranks * 4; }
+static inline size_t p2p_mail_doubles(int nranks) { return (size_t)kMailSlots * nranks * kMailRec; }
 P2PDev Ctx::p2p_dev() const {
     P2PDev d{};
     d.nranks = nranks;

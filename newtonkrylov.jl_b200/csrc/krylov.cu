@@ -37,6 +37,7 @@ constexpr int kStatusSlots = kStatusRing + 1;
 }  // namespace ak
 
 struct ak_krylov {
+    ak_ctx* owner = nullptr;
     ak::Ctx* ctx = nullptr;
     int32_t algo = AK_ALGO_GMRES;
     int64_t n = 0;
@@ -100,34 +101,37 @@ __device__ __forceinline__ double sgn(double x) { return (double)((x > 0.0) - (x
 
 // Krylov.jl sym_givens (real), then the update of iteration k (1-based) — gmres! steps 6-8
 __global__ void k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, double* c, double* s, double* z,
-                               double* hcol, int reorth, int pair, double* hist, int64_t hist_pos,
+                               double* hcol, int reorth, int blk, double* hist, int64_t hist_pos,
                                int inner_limit, KrylovStatus* st, const P2PDev pd, unsigned long long seq_in) {
     if (threadIdx.x != 0) return;
     if (ctl->stop) return;
+    const int nblk = blk > 0 ? (k + blk - 1) / blk : 0;  // blocks of the blocked Gram-Schmidt sweep
     if (seq_in != 0) {
         // ||q||^2 arrives through the mailboxes (posted by the final Gram-Schmidt pass of every rank); adding
         // in rank order gives the same bits on every rank, so all ranks take the same decisions below
         const int slot = (int)(seq_in % kMailSlots);
         double tot = 0.0;
         for (int q = 0; q < pd.nranks; ++q) {
-            const double* rec = pd.mail_local + ((size_t)slot * pd.nranks + q) * 4;
-            const unsigned long long* tag = reinterpret_cast<const unsigned long long*>(rec + 3);
+            const double* rec = pd.mail_local + ((size_t)slot * pd.nranks + q) * kMailRec;
+            const unsigned long long* tag = reinterpret_cast<const unsigned long long*>(rec + kBlkSums);
             const long long t0 = clock64();
             while (ld_acquire_sys_u64(tag) != seq_in) {
                 if (clock64() - t0 > pd.spin_cycles) { *pd.err = 1; break; }
             }
             tot += __ldcv(rec);
         }
-        hcol[3 * ((k + 1) >> 1)] = tot;
+        hcol[kBlkSums * nblk] = tot;
     }
     // column k of H: h_1k..h_kk from the MGS sweep(s), h_{k+1,k} = ||q||
     double hh;
-    if (pair) {  // raw triples {<y_a,w>, <y_b,w>, <y_b,y_a>} of the pair-wise sweep, then ||q||^2
-        for (int i = 0; i < k; ++i) {
-            const double* t = hcol + 3 * (i >> 1);
-            R[nr + i] = (i & 1) ? pair_second_h(t[0], t[1], t[2]) : t[0];
+    if (blk > 0) {  // raw sums of the blocked sweep (one record of kBlkSums per block), then ||q||^2
+        for (int j = 0; j < nblk; ++j) {
+            const int m = (k - j * blk) < blk ? (k - j * blk) : blk;
+            double hb[kBlkMax];
+            block_coefficients(hcol + kBlkSums * j, m, hb);
+            for (int b = 0; b < m; ++b) R[nr + j * blk + b] = hb[b];
         }
-        hh = hcol[3 * ((k + 1) >> 1)];
+        hh = hcol[kBlkSums * nblk];
     } else {
         const double* h2 = hcol + (k + 1);
         for (int i = 0; i < k; ++i) R[nr + i] = reorth ? hcol[i] + h2[i] : hcol[i];
@@ -275,6 +279,13 @@ static int ws_alloc_vec(ak_krylov* ws, double** out) {
     return AK_OK;
 }
 
+// doubles of the device column `hcol`: two sweeps of k + 1 sums, or one record of kBlkSums per block of the
+// blocked sweep (blocks of >= 2) plus the final ||q||^2 record
+static inline int64_t hcol_len(int64_t k) {
+    const int64_t a = 2 * (k + 1) + 8, b = (int64_t)kBlkSums * ((k + 1) / 2 + 2);
+    return a > b ? a : b;
+}
+
 static int ws_grow_scalars(ak_krylov* ws, int64_t kcap_new) {
     Ctx* c = ws->ctx;
     if (kcap_new <= ws->kcap) return AK_OK;
@@ -295,7 +306,7 @@ static int ws_grow_scalars(ak_krylov* ws, int64_t kcap_new) {
     AK_TRY(regrow(&ws->c, oldk, kcap_new));
     AK_TRY(regrow(&ws->s, oldk, kcap_new));
     AK_TRY(regrow(&ws->z, oldk ? oldk + 1 : 0, kcap_new + 1));
-    AK_TRY(regrow(&ws->hcol, oldk ? 2 * (oldk + 1) + 8 : 0, 2 * (kcap_new + 1) + 8));
+    AK_TRY(regrow(&ws->hcol, oldk ? hcol_len(oldk) : 0, hcol_len(kcap_new)));
     ws->kcap = kcap_new;
     return AK_OK;
 }
@@ -376,8 +387,7 @@ static int apply_precond_n(ak_krylov* ws, const ak_problem* prob, const double* 
         return AK_ERR_UNSUPPORTED;
     }
     if (!ws->inner) {
-        ak_ctx* owner = reinterpret_cast<ak_ctx*>(ws->ctx);  // ak_ctx { Ctx c; } — c is its first member
-        AK_TRY(ak_krylov_create(owner, AK_ALGO_GMRES, ws->n, 20, 0, &ws->inner));
+        AK_TRY(ak_krylov_create(ws->owner, AK_ALGO_GMRES, ws->n, 20, 0, &ws->inner));
     }
     ak_krylov_opts io;
     ak_krylov_default_opts(&io);
@@ -396,14 +406,16 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     const int mem = ws->mem;
     const int restart = o->restart, reorth = o->reorthogonalization;
     int fuse = o->fuse;
-    if (fuse == AK_FUSE_PAIR && reorth) fuse = AK_FUSE_FULL;  // the pair-wise sweep has no second-sweep variant
+    // the blocked sweeps have no second-sweep variant
+    if ((fuse == AK_FUSE_PAIR || fuse == AK_FUSE_BLOCK4) && reorth) fuse = AK_FUSE_FULL;
     const bool flexible = (ws->algo == AK_ALGO_FGMRES);
     const bool precond = (o->precond_n != AK_PRECOND_NONE);
     // z_k = N v_k needs v_k materialised before the JVP and a host decision per iteration: no JVP fusion
     if ((flexible || precond) && fuse > AK_FUSE_MGS) fuse = AK_FUSE_MGS;
     if ((flexible || precond) && !ws->pbuf) AK_TRY(ws_alloc_vec(ws, &ws->pbuf));
-    const bool pair = (fuse == AK_FUSE_PAIR);
-    // multi-GPU with peer memory: reductions and ghost rows of the pair-wise sweep go over NVLink stores
+    const int blk = fuse == AK_FUSE_PAIR ? 2 : (fuse == AK_FUSE_BLOCK4 ? kBlkMax : 0);  // Gram-Schmidt steps per sweep
+    const bool pair = blk > 0;
+    // multi-GPU with peer memory: reductions and ghost rows of the blocked sweep go over NVLink stores
     const bool p2p = pair && c->p2p_on && c->nranks > 1;
     const bool is2d = (prob->kind == AK_BRATU2D || prob->kind == AK_HEAT2D);
     const bool p2p_halo = p2p && is2d && prob->nx % 4 == 0 && n % 4 == 0 && prob->nx <= c->p2p_halo_cap;
@@ -540,29 +552,29 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 w = wout;
                 // modified Gram-Schmidt
                 if (pair) {
-                    // two Gram-Schmidt steps per sweep over w: pass j subtracts pair j-1 and projects on pair j
-                    const int64_t P = (k + 1) / 2;
-                    auto va = [&](int64_t j) -> const double* { return ws->V[2 * j]; };
-                    auto vb = [&](int64_t j) -> const double* { return (2 * j + 1 < k) ? ws->V[2 * j + 1] : nullptr; };
-                    PairComm pc;
+                    // `blk` Gram-Schmidt steps per sweep over w: pass j subtracts block j-1 and projects on block j
+                    const int64_t P = (k + blk - 1) / blk;
+                    auto blk_ptr = [&](int64_t j) -> const double* const* { return ws->V.data() + blk * j; };
+                    auto blk_len = [&](int64_t j) -> int { return (int)((k - blk * j) < blk ? (k - blk * j) : blk); };
+                    BlockComm pc;
                     unsigned long long prev_seq = 0;
                     if (p2p) { pc.seq_out = ++c->p2p_seq; prev_seq = pc.seq_out; }
-                    AK_TRY(launch_mgs_pair(c, n, w, nullptr, nullptr, nullptr, va(0), vb(0), 0, hcol, stop,
-                                           p2p ? &pc : nullptr));
+                    AK_TRY(launch_mgs_block(c, n, w, nullptr, 0, nullptr, blk_ptr(0), blk_len(0), 0, hcol, stop,
+                                            p2p ? &pc : nullptr));
                     for (int64_t j = 1; j < P; ++j) {
                         if (p2p) {
                             pc.seq_in = prev_seq;
                             pc.seq_out = ++c->p2p_seq;
-                            pc.tin_store = hcol + 3 * (j - 1);
+                            pc.tin_store = hcol + kBlkSums * (j - 1);
                             prev_seq = pc.seq_out;
                         }
-                        AK_TRY(launch_mgs_pair(c, n, w, va(j - 1), vb(j - 1), hcol + 3 * (j - 1), va(j), vb(j), 0,
-                                               hcol + 3 * j, stop, p2p ? &pc : nullptr));
+                        AK_TRY(launch_mgs_block(c, n, w, blk_ptr(j - 1), blk, hcol + kBlkSums * (j - 1), blk_ptr(j),
+                                                blk_len(j), 0, hcol + kBlkSums * j, stop, p2p ? &pc : nullptr));
                     }
                     if (p2p) {
                         pc.seq_in = prev_seq;
                         pc.seq_out = ++c->p2p_seq;
-                        pc.tin_store = hcol + 3 * (P - 1);
+                        pc.tin_store = hcol + kBlkSums * (P - 1);
                         givens_seq = pc.seq_out;
                         if (p2p_halo) {
                             const int par = (int)(k & 1);
@@ -571,8 +583,8 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                             pc.halo.up_lo = nb_up >= 0 ? c->p2p_halo_of(nb_up, par, 0) : nullptr;
                         }
                     }
-                    AK_TRY(launch_mgs_pair(c, n, w, va(P - 1), vb(P - 1), hcol + 3 * (P - 1), nullptr, nullptr, 1,
-                                           hcol + 3 * P, stop, p2p ? &pc : nullptr));
+                    AK_TRY(launch_mgs_block(c, n, w, blk_ptr(P - 1), blk_len(P - 1), hcol + kBlkSums * (P - 1), nullptr,
+                                            0, 1, hcol + kBlkSums * P, stop, p2p ? &pc : nullptr));
                 } else if (fuse == AK_FUSE_NONE) {
                     for (int64_t i = 0; i < k; ++i) {
                         AK_TRY(launch_mgs_step(c, n, w, nullptr, nullptr, ws->V[i], 0, hcol + i, stop));   // h = <V_i, w>
@@ -606,7 +618,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 }
                 const int slot = (int)(k % kStatusRing);
                 { ProfScope prof(c, PK_SCALAR);
-                k_gmres_givens<<<1, 32, 0, sm>>>(ws->ctl, (int)k, nr, ws->R, ws->c, ws->s, ws->z, hcol, reorth, pair ? 1 : 0,
+                k_gmres_givens<<<1, 32, 0, sm>>>(ws->ctl, (int)k, nr, ws->R, ws->c, ws->s, ws->z, hcol, reorth, blk,
                                                  want_hist ? ws->hist : nullptr, iter + k, (int)inner_limit,
                                                  &ws->status[slot], p2p ? c->p2p_dev() : P2PDev{}, givens_seq); }
                 c->launches++;
@@ -817,6 +829,7 @@ AK_API int ak_krylov_create(ak_ctx* ctx, int32_t algo, int64_t n, int32_t memory
     AK_REQUIRE(algo == AK_ALGO_GMRES || algo == AK_ALGO_CG || algo == AK_ALGO_FGMRES, "ak_krylov_create: unknown algo");
     AK_REQUIRE(memory >= 1, "ak_krylov_create: memory must be >= 1");
     ak_krylov* ws = new ak_krylov();
+    ws->owner = ctx;
     ws->ctx = &ctx->c;
     ws->algo = algo;
     ws->n = n;

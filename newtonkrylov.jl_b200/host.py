@@ -541,7 +541,8 @@ NewtonResult = namedtuple("NewtonResult", "solved stats t")
 # Krylov workspace: krylov_workspace / krylov_solve!  (src/Ariadne.jl:317-318,338-340,367)
 # ---------------------------------------------------------------------------------------------
 _ALGOS = {"gmres": A.AK_ALGO_GMRES, "cg": A.AK_ALGO_CG, "fgmres": A.AK_ALGO_FGMRES}
-_FUSE = {"none": A.AK_FUSE_NONE, "mgs": A.AK_FUSE_MGS, "full": A.AK_FUSE_FULL, "pair": A.AK_FUSE_PAIR}
+_FUSE = {"none": A.AK_FUSE_NONE, "mgs": A.AK_FUSE_MGS, "full": A.AK_FUSE_FULL, "pair": A.AK_FUSE_PAIR,
+         "block4": A.AK_FUSE_BLOCK4}
 
 
 class GmresPreconditioner:
