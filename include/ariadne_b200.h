@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AK_ABI_VERSION 2
+#define AK_ABI_VERSION 3
 
 /* ---- status / flags ------------------------------------------------------- */
 enum {
@@ -40,7 +40,8 @@ enum {
     AK_ERR_ARG = -2,
     AK_ERR_NCCL = -3,
     AK_ERR_NOMEM = -4,
-    AK_ERR_UNSUPPORTED = -5
+    AK_ERR_UNSUPPORTED = -5,
+    AK_ERR_USER = -6           /* a caller-supplied callback returned non-zero */
 };
 /* positive numerical flags (bit set) */
 enum {
@@ -58,7 +59,9 @@ enum {
     AK_BRATU2D = 2,   /* tensor extension of bratu.jl on heat_2D's grid (defined here) */
     AK_HEAT1D = 3,    /* examples/heat_1D.jl:12-25 (+ bc! :34-37, periodic_bc! :39-42) */
     AK_HEAT2D = 4,    /* examples/heat_2D.jl:45-62 (+ bc_zero! :28-38, bc_periodic! :15-26) */
-    AK_HEAT1D_DG = 5  /* examples/heat_1D_DG.jl:17-36, DG/SBP polydeg 3, periodic */
+    AK_HEAT1D_DG = 5, /* examples/heat_1D_DG.jl:17-36, DG/SBP polydeg 3, periodic */
+    AK_USER = 6       /* caller-supplied F!(res,u,p) (src/Ariadne.jl:250-256) and, optionally, its tangent:
+                         the generic seam of newton_krylov!(F!, u, p, res), e.g. examples/bvp.jl:10-23 */
 };
 enum { AK_BC_ZERO = 0, AK_BC_PERIODIC = 1 };
 /* time discretisation wrapper around the RHS f!: examples/implicit.jl */
@@ -71,9 +74,20 @@ enum {
 enum {
     AK_JVP_ANALYTIC = 0, /* exact tangent-linear stencil == what Enzyme forward mode
                             yields at src/Ariadne.jl:48-57 (parity path)          */
-    AK_JVP_FD_FUSED = 1  /* (F(u+eps v)-F(u))/eps evaluated point-wise in one pass,
+    AK_JVP_FD_FUSED = 1, /* (F(u+eps v)-F(u))/eps evaluated point-wise in one pass,
                             u+eps v never materialised (bandwidth study only)     */
+    AK_JVP_FD = 2        /* generic two-evaluation finite difference (F(u+eps v)-F(u))/eps through the
+                            residual itself; eps = fd_eps, or sqrt(eps_mach)(1+||u||)/||v|| when 0.
+                            Default of AK_USER problems without a tangent callback               */
 };
+
+/* AK_USER callbacks.  `stream` is the context's cudaStream_t: the callback ENQUEUES device work on it
+ * (or synchronises it before touching the data any other way) and returns 0; all pointers are device
+ * pointers to ak_problem_size(p) doubles.  Non-zero return aborts the solve with AK_ERR_USER.       */
+/* res <- F(u):  F!(res, u, p), src/Ariadne.jl:252,302,349.  May mutate u like the reference's BC code. */
+typedef int (*ak_user_residual_fn)(void* user, uint64_t stream, double* u, double* res);
+/* out <- J(u) v: what `mul!(out, J::JacobianOperator, v)` (src/Ariadne.jl:48-57) computes by forward-mode AD */
+typedef int (*ak_user_jvp_fn)(void* user, uint64_t stream, const double* u, double* v, double* out);
 
 typedef struct ak_problem {
     int32_t kind;      /* AK_BRATU1D ...                                           */
@@ -93,8 +107,14 @@ typedef struct ak_problem {
     const double* un;  /* device: previous time level u_n (scheme != AK_STEADY)    */
     double* coef;      /* device scratch, n doubles, or NULL.  Bratu: ak_residual
                           stores lambda*exp(u) here so that every JVP of the same
-                          Newton step is a pure 24n-byte stencil                   */
+                          Newton step is a pure 24n-byte stencil.  AK_JVP_FD: ak_residual
+                          keeps a copy of F(u) here so that a JVP costs one residual
+                          evaluation instead of two                                */
     double* work;      /* device scratch, n doubles, or NULL (midpoint/trapezoid)  */
+    /* AK_USER only (n = nx unknowns on this rank; reductions stay global over the communicator) */
+    ak_user_residual_fn user_residual;
+    ak_user_jvp_fn user_jvp;     /* NULL => AK_JVP_FD                                        */
+    void* user_data;             /* the closure `p` of F!(res, u, p)                         */
 } ak_problem;
 
 /* number of LOCAL unknowns of a problem (length of u, res, v on this rank) */

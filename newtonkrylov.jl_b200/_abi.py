@@ -5,18 +5,18 @@ struct layouts without touching the CUDA library.
 """
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # status / flags
 AK_OK = 0
-AK_ERR_CUDA, AK_ERR_ARG, AK_ERR_NCCL, AK_ERR_NOMEM, AK_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
+AK_ERR_CUDA, AK_ERR_ARG, AK_ERR_NCCL, AK_ERR_NOMEM, AK_ERR_UNSUPPORTED, AK_ERR_USER = -1, -2, -3, -4, -5, -6
 AK_FLAG_NOT_SOLVED, AK_FLAG_BREAKDOWN, AK_FLAG_INCONSISTENT, AK_FLAG_NAN = 1, 2, 4, 8
 
 # problem kinds
-AK_SIMPLE2, AK_BRATU1D, AK_BRATU2D, AK_HEAT1D, AK_HEAT2D, AK_HEAT1D_DG = range(6)
+AK_SIMPLE2, AK_BRATU1D, AK_BRATU2D, AK_HEAT1D, AK_HEAT2D, AK_HEAT1D_DG, AK_USER = range(7)
 AK_BC_ZERO, AK_BC_PERIODIC = 0, 1
 AK_STEADY, AK_EULER, AK_MIDPOINT, AK_TRAPEZOID = range(4)
-AK_JVP_ANALYTIC, AK_JVP_FD_FUSED = 0, 1
+AK_JVP_ANALYTIC, AK_JVP_FD_FUSED, AK_JVP_FD = 0, 1, 2
 AK_ALGO_GMRES, AK_ALGO_CG, AK_ALGO_FGMRES = 0, 1, 2
 AK_PRECOND_NONE, AK_PRECOND_INNER_GMRES = 0, 1
 AK_FUSE_NONE, AK_FUSE_MGS, AK_FUSE_FULL, AK_FUSE_PAIR, AK_FUSE_BLOCK4 = 0, 1, 2, 3, 4
@@ -46,6 +46,9 @@ class ak_problem(C.Structure):
         ("un", C.c_void_p),
         ("coef", C.c_void_p),
         ("work", C.c_void_p),
+        ("user_residual", C.c_void_p),
+        ("user_jvp", C.c_void_p),
+        ("user_data", C.c_void_p),
     ]
 
 
@@ -104,6 +107,10 @@ class ak_newton_stats(C.Structure):
         ("flags", C.c_int32),
     ]
 
+
+# AK_USER callbacks: int (*)(void* user, uint64_t stream, double* u, double* res) / (..., const double* u, double* v, double* out)
+USER_RESIDUAL = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p)
+USER_JVP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p)
 
 NEWTON_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double)
 

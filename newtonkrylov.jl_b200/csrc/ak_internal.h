@@ -140,6 +140,11 @@ int exchange_halo_rows(Ctx* ctx, const double* v, int64_t nx, int64_t ny, int32_
 int exchange_halo_1d(Ctx* ctx, const double* v, int64_t n, int nlo, int nhi, bool periodic, const double** lo,
                      const double** hi);
 
+// --- user.cu: caller-supplied residual / tangent callbacks, generic finite-difference JVP -------
+int user_residual(Ctx* ctx, const ak_problem* p, double* u, double* res);
+int user_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double* out);
+int launch_jvp_fd(Ctx* ctx, const ak_problem* p, const double* u, double* v, double* out);
+
 // --- blas1.cu -------------------------------------------------------------------
 int launch_dot(Ctx* ctx, int64_t n, const double* x, const double* y, double* out_dev);
 int launch_sumsq(Ctx* ctx, int64_t n, const double* x, double* out_dev);

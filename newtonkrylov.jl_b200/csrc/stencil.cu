@@ -698,7 +698,13 @@ static int launch_dg(Ctx* ctx, DgArgs& d, bool residual, bool scale, int red) {
 
 static int check_problem(const ak_problem* p) {
     AK_REQUIRE(p != nullptr, "problem is NULL");
-    AK_REQUIRE(p->kind >= AK_SIMPLE2 && p->kind <= AK_HEAT1D_DG, "unknown problem kind");
+    AK_REQUIRE(p->kind >= AK_SIMPLE2 && p->kind <= AK_USER, "unknown problem kind");
+    if (p->kind == AK_USER) {
+        AK_REQUIRE(p->nx >= 1, "AK_USER: nx (number of unknowns) must be >= 1");
+        AK_REQUIRE(p->user_residual != nullptr, "AK_USER: user_residual is NULL");
+        AK_REQUIRE(p->jvp_mode == AK_JVP_ANALYTIC || p->jvp_mode == AK_JVP_FD, "AK_USER: jvp_mode must be AK_JVP_ANALYTIC or AK_JVP_FD");
+        return AK_OK;
+    }
     if (p->kind == AK_SIMPLE2) return AK_OK;
     AK_REQUIRE(p->nx >= 1, "nx must be >= 1");
     const bool is2d = (p->kind == AK_BRATU2D || p->kind == AK_HEAT2D);
@@ -712,9 +718,9 @@ static int check_problem(const ak_problem* p) {
     } else {
         AK_REQUIRE(p->scheme == AK_STEADY, "Bratu problems are steady (scheme must be AK_STEADY)");
     }
-    if (p->jvp_mode != AK_JVP_ANALYTIC) {
+    if (p->jvp_mode != AK_JVP_ANALYTIC && p->jvp_mode != AK_JVP_FD) {
         if (!(p->jvp_mode == AK_JVP_FD_FUSED && p->kind == AK_BRATU2D)) {
-            set_error("jvp_mode %d is only implemented as AK_JVP_FD_FUSED for AK_BRATU2D", p->jvp_mode);
+            set_error("jvp_mode %d: AK_JVP_FD_FUSED is only implemented for AK_BRATU2D", p->jvp_mode);
             return AK_ERR_UNSUPPORTED;
         }
     }
@@ -879,10 +885,27 @@ static int launch_jvp_midpoint(Ctx* ctx, const ak_problem* p, double* v, double*
     return AK_OK;
 }
 
+// true when J v is the generic finite difference of the residual (AK_JVP_FD, or AK_USER without a tangent)
+static inline bool fd_generic(const ak_problem* p) {
+    return p->jvp_mode == AK_JVP_FD || (p->kind == AK_USER && p->user_jvp == nullptr);
+}
+
 int launch_residual(Ctx* ctx, const ak_problem* p, double* u, double* res, double* sumsq_dev) {
     AK_TRY(check_problem(p));
     AK_TRY(check_multi_gpu(ctx, p));
+    if (fd_generic(p) && p->coef != nullptr) {
+        // p->coef caches F(u) for the finite-difference JVPs of this Newton step (not lambda e^u)
+        ak_problem q = *p;
+        q.coef = nullptr;
+        AK_TRY(launch_residual(ctx, &q, u, res, sumsq_dev));
+        return launch_copy(ctx, ak_problem_size(p), p->coef, res);
+    }
     ProfScope prof(ctx, PK_RESIDUAL);
+    if (p->kind == AK_USER) {
+        AK_TRY(user_residual(ctx, p, u, res));
+        if (sumsq_dev) AK_TRY(launch_sumsq(ctx, p->nx, res, sumsq_dev));
+        return AK_OK;
+    }
     if (p->scheme == AK_MIDPOINT || p->scheme == AK_TRAPEZOID) {
         if (ctx->nranks > 1) { set_error("Midpoint/Trapezoid are single-GPU in this version"); return AK_ERR_UNSUPPORTED; }
         return launch_residual_composite(ctx, p, u, res, sumsq_dev);
@@ -951,6 +974,16 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     if (!f) f = &nofuse;
     AK_TRY(check_multi_gpu(ctx, p));
     ProfScope prof(ctx, PK_JVP);
+    if (p->kind == AK_USER || fd_generic(p)) {
+        // caller-supplied tangent, or (F(u + eps v) - F(u)) / eps through the residual; the fused normalisation
+        // and first dot of the Arnoldi step run as separate launches (same arithmetic)
+        const int64_t n = ak_problem_size(p);
+        if (f->scale_src) AK_TRY(launch_divcopy_dev(ctx, n, v, f->scale_src, f->denom_dev, f->stop_flag));
+        if (fd_generic(p)) AK_TRY(launch_jvp_fd(ctx, p, u, v, out));
+        else AK_TRY(user_jvp(ctx, p, u, v, out));
+        if (f->dot_with) AK_TRY(launch_mgs_step(ctx, n, out, nullptr, nullptr, f->dot_with, 0, f->dot_dev, f->stop_flag));
+        return AK_OK;
+    }
     if (p->scheme == AK_MIDPOINT) {
         // composed path: fused normalisation / dot are done as separate launches (same arithmetic)
         if (ctx->nranks > 1) { set_error("Midpoint is single-GPU in this version"); return AK_ERR_UNSUPPORTED; }
@@ -1069,7 +1102,7 @@ AK_API int64_t ak_problem_size(const ak_problem* p) {
     if (!p) return 0;
     switch (p->kind) {
         case AK_SIMPLE2: return 2;
-        case AK_BRATU1D: case AK_HEAT1D: case AK_HEAT1D_DG: return p->nx;
+        case AK_BRATU1D: case AK_HEAT1D: case AK_HEAT1D_DG: case AK_USER: return p->nx;
         default: return p->nx * p->ny;
     }
 }

@@ -70,7 +70,7 @@ OK_EXPORT int ok_num_threads(void) {
 OK_EXPORT int64_t ok_problem_size(const ak_problem* p) {
     switch (p->kind) {
         case AK_SIMPLE2: return 2;
-        case AK_BRATU1D: case AK_HEAT1D: case AK_HEAT1D_DG: return p->nx;
+        case AK_BRATU1D: case AK_HEAT1D: case AK_HEAT1D_DG: case AK_USER: return p->nx;
         default: return p->nx * p->ny;
     }
 }
@@ -287,6 +287,10 @@ static void rhs_linear(const ak_problem* p, double* du, double* u, double* tmp) 
 /* ------------------------------------------------------------------------- */
 OK_EXPORT void ok_residual(const ak_problem* p, double* u, double* res) {
     const int64_t n = ok_problem_size(p);
+    if (p->kind == AK_USER) { /* any F!(res, u, p): src/Ariadne.jl:250-256 (host pointers, stream 0) */
+        if (p->user_residual(p->user_data, 0, u, res) != 0) { fprintf(stderr, "oracle: user residual failed\n"); abort(); }
+        return;
+    }
     if (p->kind == AK_SIMPLE2) { /* test/runtests.jl:4-7 */
         res[0] = u[0] * u[0] + u[1] * u[1] - 2.0;
         res[1] = exp(u[0] - 1.0) + u[1] * u[1] - 2.0;
@@ -350,8 +354,37 @@ OK_EXPORT void ok_residual(const ak_problem* p, double* u, double* res) {
 /* ------------------------------------------------------------------------- */
 /* JVP: out = J(u) v, exact tangent (src/Ariadne.jl:48-57)                      */
 /* ------------------------------------------------------------------------- */
+static double ok_nrm2_plain(const double* x, int64_t n) {
+    double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) s += x[i] * x[i];
+    return sqrt(s);
+}
+
 OK_EXPORT void ok_jvp(const ak_problem* p, const double* u, double* v, double* out) {
     const int64_t n = ok_problem_size(p);
+    if (p->jvp_mode == AK_JVP_FD || (p->kind == AK_USER && p->user_jvp == NULL)) {
+        /* BASELINE north_star wording: J v ~ (F(u + eps v) - F(u)) / eps, two residual evaluations;
+         * eps = fd_eps, or sqrt(eps_mach) (1 + ||u||) / ||v|| */
+        ak_problem q = *p;
+        q.jvp_mode = AK_JVP_ANALYTIC;
+        double* t = ok_alloc(n);
+        double* f0 = ok_alloc(n);
+        const double vn = ok_nrm2_plain(v, n);
+        double e = 0.0;
+        if (vn > 0.0) e = p->fd_eps > 0.0 ? p->fd_eps : 1.4901161193847656e-08 * (1.0 + ok_nrm2_plain(u, n)) / vn;
+        for (int64_t i = 0; i < n; ++i) t[i] = u[i] + e * v[i];
+        ok_residual(&q, t, out);
+        for (int64_t i = 0; i < n; ++i) t[i] = u[i];
+        ok_residual(&q, t, f0);
+        for (int64_t i = 0; i < n; ++i) out[i] = (e > 0.0) ? (out[i] - f0[i]) / e : 0.0;
+        free(t);
+        free(f0);
+        return;
+    }
+    if (p->kind == AK_USER) { /* caller-supplied exact tangent (what Enzyme forward mode yields, src/Ariadne.jl:48-57) */
+        if (p->user_jvp(p->user_data, 0, u, v, out) != 0) { fprintf(stderr, "oracle: user tangent failed\n"); abort(); }
+        return;
+    }
     if (p->kind == AK_SIMPLE2) {
         out[0] = 2.0 * u[0] * v[0] + 2.0 * u[1] * v[1];
         out[1] = exp(u[0] - 1.0) * v[0] + 2.0 * u[1] * v[1];
