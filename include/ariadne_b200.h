@@ -210,12 +210,22 @@ int ak_divcopy(ak_ctx* ctx, int64_t n, double* y, const double* x, double s);
 typedef struct ak_krylov ak_krylov;
 
 enum { AK_ALGO_GMRES = 0, AK_ALGO_CG = 1, AK_ALGO_FGMRES = 2 /* Krylov.jl fgmres!: examples/bratu.jl:131-157 */ };
-/* right preconditioner N of `newton_krylov!(...; N = (J) -> ...)` (src/Ariadne.jl:296-297,324-326) built natively */
+/* Preconditioners of `newton_krylov!(...; M = (J) -> ..., N = (J) -> ...)` (src/Ariadne.jl:296-297,324-329): the
+ * reference calls M(J) / N(J) once per Newton step and hands the objects to Krylov.jl, which applies them with
+ * mul! (ldiv = false) or ldiv! (ldiv = true).  Here the object is named by kind and built natively from the
+ * operator J = (problem, u); it is rebuilt implicitly for every u, like N(J) in the reference.            */
 enum {
     AK_PRECOND_NONE = 0,
-    AK_PRECOND_INNER_GMRES = 1 /* N = (J) -> GmresPreconditioner(J, itmax): y = gmres(J, x; itmax)
-                                  (examples/bratu.jl:141-157, bvp.jl:29-38)                      */
+    AK_PRECOND_INNER_GMRES = 1, /* (J) -> GmresPreconditioner(J, itmax): y = gmres(J, x; itmax)
+                                   (examples/bratu.jl:141-157, bvp.jl:29-38)                     */
+    AK_PRECOND_USER = 2,        /* caller-supplied y <- P x (mul!) or y <- P \ x (ldiv!): ak_precond_apply_fn */
+    AK_PRECOND_JACOBI = 3,      /* y = x ./ diag(J(u)); Bratu 1-D/2-D, heat 1-D/2-D (Euler, Trapezoid)     */
+    AK_PRECOND_TRIDIAG_LU = 4   /* y = J(u) \ x by tridiagonal LU (parallel partitioned Thomas): what
+                                   `ilu(collect(J))` with ldiv = true is for the 1-D Bratu Jacobian, whose LU
+                                   factors have no fill-in (examples/bratu.jl:121-139).  AK_BRATU1D, one GPU */
 };
+/* y <- P x on `stream` (device pointers, n doubles); non-zero return aborts with AK_ERR_USER */
+typedef int (*ak_precond_apply_fn)(void* user, uint64_t stream, const double* x, double* y);
 /* how aggressively the Arnoldi step is fused (all levels keep modified Gram-Schmidt
  * order, so they differ only by rounding of identical operations)               */
 enum {
@@ -241,6 +251,13 @@ typedef struct ak_krylov_opts {
     int32_t fuse;           /* AK_FUSE_*                                           */
     int32_t precond_n;      /* AK_PRECOND_*: right preconditioner (kwarg N)        */
     int32_t precond_itmax;  /* itmax of the inner GMRES (GmresPreconditioner.itmax) */
+    int32_t precond_m;      /* AK_PRECOND_*: left preconditioner (kwarg M); GMRES/FGMRES then
+                               iterate on M J N and measure ||M r||, like Krylov.jl          */
+    int32_t precond_m_itmax;
+    ak_precond_apply_fn n_apply;  /* AK_PRECOND_USER */
+    void* n_user;
+    ak_precond_apply_fn m_apply;
+    void* m_user;
 } ak_krylov_opts;
 
 typedef struct ak_krylov_stats {
@@ -267,6 +284,11 @@ int ak_krylov_solve(ak_krylov* ws, const ak_problem* p, const double* u, const d
                     double* hist_host, int64_t hist_cap);
 /* workspace.x: device pointer to the solution of the last solve */
 double* ak_krylov_x(ak_krylov* ws);
+/* One application of a native preconditioner object built from J = (p, u): `mul!(y, P, x)` for
+ * AK_PRECOND_INNER_GMRES / AK_PRECOND_JACOBI, `ldiv!(y, P, x)` for AK_PRECOND_TRIDIAG_LU — what Krylov.jl calls
+ * on the object returned by `N(J)` / `M(J)` (src/Ariadne.jl:324-329) when Krylov.jl itself drives the solve. */
+int ak_precond_apply(ak_ctx* ctx, const ak_problem* p, const double* u, int32_t kind, int32_t itmax,
+                     const double* x, double* y);
 
 /* ---- whole Newton solve: newton_krylov!, src/Ariadne.jl:288-372 ------------- */
 enum { AK_FORCING_NONE = 0, AK_FORCING_FIXED = 1, AK_FORCING_EW = 2 };

@@ -12,6 +12,7 @@
 module AriadneB200
 
 export B200Vector, newton_krylov!, newton_krylov, JacobianOperator, Fixed, EisenstatWalker, GmresPreconditioner,
+       TridiagonalLU, ilu, JacobiPreconditioner, UserPreconditioner, UserResidual,
        Bratu1D, Bratu2D, Heat1D, Diffusion2D, Heat1DDG, GEuler, solve
 
 using LinearAlgebra
@@ -32,11 +33,16 @@ struct AkProblem
     nx::Int64; ny::Int64; gny::Int64; gy0::Int64
     dx::Float64; dy::Float64; lambda::Float64; a::Float64; dt::Float64; fd_eps::Float64
     un::Ptr{Float64}; coef::Ptr{Float64}; work::Ptr{Float64}
+    user_residual::Ptr{Cvoid}; user_jvp::Ptr{Cvoid}; user_data::Ptr{Cvoid}      # AK_USER
 end
+# every native residual: no callbacks
+AkProblem(kind, bc, scheme, jvp_mode, nx, ny, gny, gy0, dx, dy, lambda, a, dt, fd_eps, un, coef, work) =
+    AkProblem(kind, bc, scheme, jvp_mode, nx, ny, gny, gy0, dx, dy, lambda, a, dt, fd_eps, un, coef, work, C_NULL, C_NULL, C_NULL)
 struct AkKrylovOpts
     atol::Float64; rtol::Float64; itmax::Int64
     restart::Int32; reorthogonalization::Int32; history::Int32; fuse::Int32
-    precond_n::Int32; precond_itmax::Int32
+    precond_n::Int32; precond_itmax::Int32; precond_m::Int32; precond_m_itmax::Int32
+    n_apply::Ptr{Cvoid}; n_user::Ptr{Cvoid}; m_apply::Ptr{Cvoid}; m_user::Ptr{Cvoid}
 end
 struct AkKrylovStats
     niter::Int64; solved::Int32; inconsistent::Int32; breakdown::Int32; npass::Int32
@@ -54,14 +60,37 @@ struct AkNewtonStats
     n_res::Float64; tol::Float64; t_seconds::Float64; flags::Int32
 end
 
-const AK_SIMPLE2, AK_BRATU1D, AK_BRATU2D, AK_HEAT1D, AK_HEAT2D, AK_HEAT1D_DG = Int32.(0:5)
+const AK_SIMPLE2, AK_BRATU1D, AK_BRATU2D, AK_HEAT1D, AK_HEAT2D, AK_HEAT1D_DG, AK_USER = Int32.(0:6)
 const AK_STEADY, AK_EULER = Int32(0), Int32(1)
+const AK_JVP_ANALYTIC, AK_JVP_FD = Int32(0), Int32(2)
 const AK_ALGO = Dict(:gmres => Int32(0), :cg => Int32(1), :fgmres => Int32(2))
+const AK_PRECOND_NONE, AK_PRECOND_INNER_GMRES, AK_PRECOND_USER, AK_PRECOND_JACOBI, AK_PRECOND_TRIDIAG_LU = Int32.(0:4)
 
+# ---- preconditioner objects returned by `M(J)` / `N(J)` (src/Ariadne.jl:324-329) -----------------------------------------
 "N = (J) -> GmresPreconditioner(J, itmax) of examples/bratu.jl:141-149; run natively as an inner GMRES"
 struct GmresPreconditioner{JOp}
     J::JOp
     itmax::Int
+end
+"What `ilu(collect(J))` is for the tridiagonal 1-D Bratu Jacobian (examples/bratu.jl:121-139); applied with ldiv = true"
+struct TridiagonalLU{JOp}; J::JOp; end
+ilu(J) = TridiagonalLU(J)
+"y = x ./ diag(J(u))"
+struct JacobiPreconditioner{JOp}; J::JOp; end
+"Any preconditioner of the caller: `apply!(y::CuPtr, x::CuPtr, n, stream)` enqueues y <- P x on `stream`"
+struct UserPreconditioner{F}; apply!::F; ldiv::Bool; end
+precond_fields(::Nothing) = (AK_PRECOND_NONE, Int32(0), C_NULL, C_NULL)
+precond_fields(P::GmresPreconditioner) = (AK_PRECOND_INNER_GMRES, Int32(P.itmax), C_NULL, C_NULL)
+precond_fields(::TridiagonalLU) = (AK_PRECOND_TRIDIAG_LU, Int32(0), C_NULL, C_NULL)
+precond_fields(::JacobiPreconditioner) = (AK_PRECOND_JACOBI, Int32(0), C_NULL, C_NULL)
+function precond_trampoline(user::Ptr{Cvoid}, stream::UInt64, x::Ptr{Float64}, y::Ptr{Float64})::Cint
+    P, n = unsafe_pointer_to_objref(user)::Tuple
+    try
+        P.apply!(y, x, n, stream)
+        return 0
+    catch
+        return 1
+    end
 end
 
 # ---- context and device vectors ------------------------------------------------------------------------------------
@@ -150,6 +179,45 @@ function problem(F::GEuler, u, p; coef = C_NULL)
         return AkProblem(AK_HEAT1D_DG, 1, AK_EULER, 0, length(u), 1, 1, 0, pf[1], 0.0, 0.0, 0.0, dt, 0.0, un.ptr, C_NULL, C_NULL)
     end
 end
+# ---- caller-supplied residuals: the generic seam of newton_krylov!(F!, u, p, res) (src/Ariadne.jl:250-256) ------------------
+# `F!(res::Ptr{Float64}, u::Ptr{Float64}, p, n, stream)` and (optionally) `jvp!(out, u, v, p, n, stream)` enqueue device work
+# on `stream` (e.g. CUDA.jl kernels launched with `stream = CuStream(stream)`; the tangent is what
+# `Enzyme.autodiff(Forward, ...)` of the same kernel computes).  Without `jvp!` the library forms
+# (F(u + ε v) - F(u)) / ε itself (AK_JVP_FD).
+mutable struct UserResidual{F, T} <: NativeResidual
+    F!::F
+    jvp!::T
+    p::Any
+    n::Int
+end
+UserResidual(F!, jvp! = nothing) = UserResidual(F!, jvp!, nothing, 0)
+function user_residual_trampoline(user::Ptr{Cvoid}, stream::UInt64, u::Ptr{Float64}, res::Ptr{Float64})::Cint
+    R = unsafe_pointer_to_objref(user)::UserResidual
+    try
+        R.F!(res, u, R.p, R.n, stream)
+        return 0
+    catch
+        return 1
+    end
+end
+function user_jvp_trampoline(user::Ptr{Cvoid}, stream::UInt64, u::Ptr{Float64}, v::Ptr{Float64}, out::Ptr{Float64})::Cint
+    R = unsafe_pointer_to_objref(user)::UserResidual
+    try
+        R.jvp!(out, u, v, R.p, R.n, stream)
+        return 0
+    catch
+        return 1
+    end
+end
+function problem(R::UserResidual, u, p; coef = C_NULL)
+    R.p, R.n = p, length(u)                      # R must stay rooted while the solve runs (it is: the caller holds it)
+    fr = @cfunction(user_residual_trampoline, Cint, (Ptr{Cvoid}, UInt64, Ptr{Float64}, Ptr{Float64}))
+    fj = R.jvp! === nothing ? C_NULL :
+         @cfunction(user_jvp_trampoline, Cint, (Ptr{Cvoid}, UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}))
+    return AkProblem(AK_USER, 0, AK_STEADY, R.jvp! === nothing ? AK_JVP_FD : AK_JVP_ANALYTIC, length(u), 1, 1, 0,
+                     0.0, 0.0, 0.0, 0.0, 0.0, 0.0, C_NULL, coef, C_NULL, fr, fj, pointer_from_objref(R))
+end
+
 function (F::NativeResidual)(res::B200Vector, u::B200Vector, p)
     prob = Ref(problem(F, u, p))
     check(ccall((:ak_residual, lib), Cint, (Ptr{Cvoid}, Ptr{AkProblem}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), u.ctx.h, prob, u.ptr, res.ptr, C_NULL))
@@ -199,10 +267,15 @@ function krylov_workspace(algo::Symbol, res::B200Vector; memory = 20, max_basis 
 end
 solution(ws::Workspace) = ccall((:ak_krylov_x, lib), Ptr{Float64}, (Ptr{Cvoid},), ws.h)
 function krylov_solve!(ws::Workspace, J::JacobianOperator, b::B200Vector; atol = √eps(Float64), rtol = √eps(Float64),
-                       itmax = 0, restart = false, reorthogonalization = false, history = false, fuse = 3,
-                       N::Union{Nothing, GmresPreconditioner} = nothing)
-    pn, pit = N === nothing ? (Int32(0), Int32(0)) : (Int32(1), Int32(N.itmax))
-    o = Ref(AkKrylovOpts(atol, rtol, itmax, restart, reorthogonalization, history, fuse, pn, pit))
+                       itmax = 0, restart = false, reorthogonalization = false, history = false, fuse = 4,
+                       M = nothing, N = nothing, ldiv = false)
+    fields(P) = P isa UserPreconditioner ?
+        (AK_PRECOND_USER, Int32(0), @cfunction(precond_trampoline, Cint, (Ptr{Cvoid}, UInt64, Ptr{Float64}, Ptr{Float64})),
+         pointer_from_objref(Ref((P, length(b))))) : precond_fields(P)
+    (N isa TridiagonalLU || M isa TridiagonalLU) && !ldiv && error("ilu(J) is applied with ldiv = true (examples/bratu.jl:126)")
+    pn, pit, nfn, nus = fields(N)
+    pm, pmit, mfn, mus = fields(M)
+    o = Ref(AkKrylovOpts(atol, rtol, itmax, restart, reorthogonalization, history, fuse, pn, pit, pm, pmit, nfn, nus, mfn, mus))
     st = Ref(AkKrylovStats(0, 0, 0, 0, 0, 0.0, 0.0))
     prob = Ref(problem(J.f, J.u, J.p; coef = J.coef))
     check(ccall((:ak_krylov_solve, lib), Cint,
@@ -224,9 +297,9 @@ function newton_krylov!(F!::NativeResidual, u::B200Vector, p = nothing, res::B20
                         tol_rel = 1.0e-6, tol_abs = 1.0e-12, max_niter = 50,
                         forcing::Union{Forcing, Nothing} = EisenstatWalker(), verbose = 0, algo = :gmres,
                         M = nothing, N = nothing, krylov_kwargs = (;), callback = (args...) -> nothing)
-    M === nothing || error("the left preconditioner hook M is not on the native path yet")
     t₀ = time_ns()
-    coef = F! isa Union{Bratu1D, Bratu2D} ? similar(u) : nothing      # λ·exp(u) cache shared by residual and JVPs
+    # λ·exp(u) cache shared by residual and JVPs (Bratu); F(u) cache for finite-difference JVPs (user F! without tangent)
+    coef = (F! isa Union{Bratu1D, Bratu2D} || (F! isa UserResidual && F!.jvp! === nothing)) ? similar(u) : nothing
     cptr = coef === nothing ? Ptr{Float64}(C_NULL) : coef.ptr
     prob = Ref(problem(F!, u, p; coef = cptr))
     nrm = Ref{Float64}(0.0)
@@ -243,6 +316,7 @@ function newton_krylov!(F!::NativeResidual, u::B200Vector, p = nothing, res::B20
     while n_res > tol && stats.outer_iterations <= max_niter
         kwargs = krylov_kwargs
         N !== nothing && (kwargs = (; N = N(J), kwargs...))
+        M !== nothing && (kwargs = (; M = M(J), kwargs...))
         forcing !== nothing && (kwargs = (; rtol = η, kwargs...))
         Krylov_kcopy!(length(res), rhs, res)                       # copy(res)
         krylov_solve!(workspace, J, rhs; kwargs...)

@@ -18,7 +18,7 @@ AK_BC_ZERO, AK_BC_PERIODIC = 0, 1
 AK_STEADY, AK_EULER, AK_MIDPOINT, AK_TRAPEZOID = range(4)
 AK_JVP_ANALYTIC, AK_JVP_FD_FUSED, AK_JVP_FD = 0, 1, 2
 AK_ALGO_GMRES, AK_ALGO_CG, AK_ALGO_FGMRES = 0, 1, 2
-AK_PRECOND_NONE, AK_PRECOND_INNER_GMRES = 0, 1
+AK_PRECOND_NONE, AK_PRECOND_INNER_GMRES, AK_PRECOND_USER, AK_PRECOND_JACOBI, AK_PRECOND_TRIDIAG_LU = 0, 1, 2, 3, 4
 AK_FUSE_NONE, AK_FUSE_MGS, AK_FUSE_FULL, AK_FUSE_PAIR, AK_FUSE_BLOCK4 = 0, 1, 2, 3, 4
 AK_FORCING_NONE, AK_FORCING_FIXED, AK_FORCING_EW = 0, 1, 2
 
@@ -63,6 +63,12 @@ class ak_krylov_opts(C.Structure):
         ("fuse", C.c_int32),
         ("precond_n", C.c_int32),
         ("precond_itmax", C.c_int32),
+        ("precond_m", C.c_int32),
+        ("precond_m_itmax", C.c_int32),
+        ("n_apply", C.c_void_p),
+        ("n_user", C.c_void_p),
+        ("m_apply", C.c_void_p),
+        ("m_user", C.c_void_p),
     ]
 
 
@@ -111,6 +117,8 @@ class ak_newton_stats(C.Structure):
 # AK_USER callbacks: int (*)(void* user, uint64_t stream, double* u, double* res) / (..., const double* u, double* v, double* out)
 USER_RESIDUAL = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p)
 USER_JVP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p)
+# AK_PRECOND_USER: int (*)(void* user, uint64_t stream, const double* x, double* y)
+PRECOND_APPLY = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p)
 
 NEWTON_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double)
 
@@ -119,7 +127,7 @@ SQRT_EPS = 2.220446049250313e-16 ** 0.5
 
 def default_krylov_opts(**kw):
     """Krylov.jl gmres!/cg! keyword defaults (atol = rtol = sqrt(eps), itmax = 0 -> 2n)."""
-    o = ak_krylov_opts(SQRT_EPS, SQRT_EPS, 0, 0, 0, 0, AK_FUSE_MGS, AK_PRECOND_NONE, 0)
+    o = ak_krylov_opts(SQRT_EPS, SQRT_EPS, 0, 0, 0, 0, AK_FUSE_MGS, AK_PRECOND_NONE, 0, AK_PRECOND_NONE, 0, None, None, None, None)
     for k, v in kw.items():
         if not hasattr(o, k):
             raise TypeError(f"unknown krylov kwarg {k!r}")

@@ -145,6 +145,10 @@ int user_residual(Ctx* ctx, const ak_problem* p, double* u, double* res);
 int user_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double* out);
 int launch_jvp_fd(Ctx* ctx, const ak_problem* p, const double* u, double* v, double* out);
 
+// --- precond.cu: Jacobi, tridiagonal LU, caller-supplied apply ---------------------------------
+int precond_apply(Ctx* ctx, const ak_problem* p, const double* u, int32_t kind, ak_precond_apply_fn fn, void* user,
+                  const double* x, double* y);
+
 // --- blas1.cu -------------------------------------------------------------------
 int launch_dot(Ctx* ctx, int64_t n, const double* x, const double* y, double* out_dev);
 int launch_sumsq(Ctx* ctx, int64_t n, const double* x, double* out_dev);

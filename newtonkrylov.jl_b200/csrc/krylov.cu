@@ -50,6 +50,7 @@ struct ak_krylov {
     std::vector<double*> V;          // basis vectors
     std::vector<double*> Z;          // fgmres: z_k = N v_k
     double* pbuf = nullptr;          // right-preconditioned gmres: p = N v_k
+    double* qbuf = nullptr;          // left-preconditioned gmres: A N v_k before M is applied
     ak_krylov* inner = nullptr;      // workspace of the inner GMRES used as preconditioner
     std::vector<double*> chunks;     // cudaMalloc'ed blocks backing V / misc vectors
     const double** V_dev = nullptr;  // device table of basis pointers
@@ -378,25 +379,30 @@ static int wait_status(ak_krylov* ws, int slot, KrylovStatus* out) {
 static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, const double* b,
                        const ak_krylov_opts* o, ak_krylov_stats* st, double* hist_host, int64_t hist_cap);
 
-// out <- N in.  AK_PRECOND_INNER_GMRES: `copyto!(y, gmres(P.J, x; P.itmax)[1])` (examples/bratu.jl:146-149):
-// an inner GMRES with memory 20, default tolerances, x0 = 0 and at most precond_itmax iterations.
-static int apply_precond_n(ak_krylov* ws, const ak_problem* prob, const double* u, const ak_krylov_opts* o,
-                           const double* in, double* out) {
-    if (o->precond_n != AK_PRECOND_INNER_GMRES) {
-        set_error("unknown right preconditioner %d", o->precond_n);
-        return AK_ERR_UNSUPPORTED;
-    }
+// out <- P in for the right (N) or left (M) preconditioner of this solve.
+// AK_PRECOND_INNER_GMRES: `copyto!(y, gmres(P.J, x; P.itmax)[1])` (examples/bratu.jl:146-149): an inner GMRES with
+// memory 20, default tolerances, x0 = 0 and at most itmax iterations.  Other kinds: precond.cu.
+static int apply_precond(ak_krylov* ws, const ak_problem* prob, const double* u, const ak_krylov_opts* o, bool left,
+                         const double* in, double* out) {
+    const int32_t kind = left ? o->precond_m : o->precond_n;
+    if (kind != AK_PRECOND_INNER_GMRES)
+        return precond_apply(ws->ctx, prob, u, kind, left ? o->m_apply : o->n_apply, left ? o->m_user : o->n_user, in,
+                             out);
     if (!ws->inner) {
         AK_TRY(ak_krylov_create(ws->owner, AK_ALGO_GMRES, ws->n, 20, 0, &ws->inner));
     }
     ak_krylov_opts io;
     ak_krylov_default_opts(&io);
-    io.itmax = o->precond_itmax;
+    io.itmax = left ? o->precond_m_itmax : o->precond_itmax;
     io.fuse = (o->fuse == AK_FUSE_NONE) ? AK_FUSE_NONE : AK_FUSE_MGS;
     ak_krylov_stats ist;
     int rc = gmres_solve(ws->inner, prob, u, in, &io, &ist, nullptr, 0);
     if (rc < 0) return rc;
     return launch_copy(ws->ctx, ws->n, out, ws->inner->x);
+}
+static int apply_precond_n(ak_krylov* ws, const ak_problem* prob, const double* u, const ak_krylov_opts* o,
+                           const double* in, double* out) {
+    return apply_precond(ws, prob, u, o, false, in, out);
 }
 
 static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, const double* b,
@@ -410,9 +416,11 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     if ((fuse == AK_FUSE_PAIR || fuse == AK_FUSE_BLOCK4) && reorth) fuse = AK_FUSE_FULL;
     const bool flexible = (ws->algo == AK_ALGO_FGMRES);
     const bool precond = (o->precond_n != AK_PRECOND_NONE);
+    const bool lprec = (o->precond_m != AK_PRECOND_NONE);  // q = M A N v_k, r0 = M (b - A x): Krylov.jl solver.q
     // z_k = N v_k needs v_k materialised before the JVP and a host decision per iteration: no JVP fusion
-    if ((flexible || precond) && fuse > AK_FUSE_MGS) fuse = AK_FUSE_MGS;
+    if ((flexible || precond || lprec) && fuse > AK_FUSE_MGS) fuse = AK_FUSE_MGS;
     if ((flexible || precond) && !ws->pbuf) AK_TRY(ws_alloc_vec(ws, &ws->pbuf));
+    if (lprec && !ws->qbuf) AK_TRY(ws_alloc_vec(ws, &ws->qbuf));
     const int blk = fuse == AK_FUSE_PAIR ? 2 : (fuse == AK_FUSE_BLOCK4 ? kBlkMax : 0);  // Gram-Schmidt steps per sweep
     const bool pair = blk > 0;
     // multi-GPU with peer memory: reductions and ghost rows of the blocked sweep go over NVLink stores
@@ -443,7 +451,8 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     int wi = 0;  // index of the buffer currently holding w / r0
     double* w = ws->w[wi];
     AK_TRY(launch_fill(c, n, x, 0.0));
-    AK_TRY(launch_copy(c, n, w, b));
+    if (lprec) AK_TRY(apply_precond(ws, prob, u, o, true, b, w));  // r0 = M b
+    else AK_TRY(launch_copy(c, n, w, b));
 
     memset(st, 0, sizeof(*st));
     int64_t iter = 0, inner_itmax = itmax;
@@ -457,9 +466,11 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
         if (restart) {
             AK_TRY(launch_fill(c, n, xr, 0.0));
             if (npass >= 1) {
-                // w <- b - A x
-                AK_TRY(launch_jvp(c, prob, u, x, w, nullptr));
-                AK_TRY(launch_axpby(c, n, 1.0, b, -1.0, w));
+                // w <- b - A x  (left-preconditioned: w <- M (b - A x))
+                double* t = lprec ? ws->qbuf : w;
+                AK_TRY(launch_jvp(c, prob, u, x, t, nullptr));
+                AK_TRY(launch_axpby(c, n, 1.0, b, -1.0, t));
+                if (lprec) AK_TRY(apply_precond(ws, prob, u, o, true, t, w));
             }
         }
         AK_TRY(launch_sumsq(c, n, w, ws->hcol));
@@ -507,12 +518,12 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
 
                 // fgmres / right preconditioning: z_k = N v_k (kept in Z for fgmres), then w <- A z_k
                 double* pv = ws->V[k - 1];
-                if (flexible || precond) {
+                if ((flexible || precond || lprec) && k > 1) {
                     // the preconditioner solves with host-visible verdicts: this path is not speculative
-                    if (k > 1) {
-                        AK_TRY(wait_status(ws, (int)((k - 1) % kStatusRing), &hs));
-                        if (hs.stop) { K = k - 1; break; }
-                    }
+                    AK_TRY(wait_status(ws, (int)((k - 1) % kStatusRing), &hs));
+                    if (hs.stop) { K = k - 1; break; }
+                }
+                if (flexible || precond) {
                     double* tgt = ws->pbuf;
                     if (flexible) {
                         while ((int64_t)ws->Z.size() < k) {
@@ -548,7 +559,12 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                         jf.dot_dev = hcol;
                     }
                 }
-                AK_TRY(launch_jvp(c, prob, u, pv, wout, &jf));
+                if (lprec) {  // w <- M (A N v_k)
+                    AK_TRY(launch_jvp(c, prob, u, pv, ws->qbuf, &jf));
+                    AK_TRY(apply_precond(ws, prob, u, o, true, ws->qbuf, wout));
+                } else {
+                    AK_TRY(launch_jvp(c, prob, u, pv, wout, &jf));
+                }
                 w = wout;
                 // modified Gram-Schmidt
                 if (pair) {
@@ -803,7 +819,7 @@ static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, cons
 int krylov_solve_internal(ak_krylov* ws, const ak_problem* p, const double* u, const double* b,
                           const ak_krylov_opts* opts, ak_krylov_stats* st, double* hist_host, int64_t hist_cap) {
     if (ws->algo == AK_ALGO_CG) {
-        if (opts->precond_n != AK_PRECOND_NONE) {
+        if (opts->precond_n != AK_PRECOND_NONE || opts->precond_m != AK_PRECOND_NONE) {
             set_error("preconditioned CG is not implemented");
             return AK_ERR_UNSUPPORTED;
         }
@@ -893,3 +909,21 @@ AK_API int ak_krylov_solve(ak_krylov* ws, const ak_problem* p, const double* u, 
 }
 
 AK_API double* ak_krylov_x(ak_krylov* ws) { return ws ? ws->x : nullptr; }
+
+AK_API int ak_precond_apply(ak_ctx* ctx, const ak_problem* p, const double* u, int32_t kind, int32_t itmax,
+                            const double* x, double* y) {
+    AK_REQUIRE(ctx && p && x && y, "ak_precond_apply: NULL argument");
+    if (kind != AK_PRECOND_INNER_GMRES) return precond_apply(&ctx->c, p, u, kind, nullptr, nullptr, x, y);
+    // mul!(y, P::GmresPreconditioner, x) = copyto!(y, gmres(P.J, x; P.itmax)[1])   examples/bratu.jl:146-149
+    ak_krylov* ws = nullptr;
+    AK_TRY(ak_krylov_create(ctx, AK_ALGO_GMRES, ak_problem_size(p), 20, 0, &ws));
+    ak_krylov_opts io;
+    ak_krylov_default_opts(&io);
+    io.itmax = itmax;
+    ak_krylov_stats st;
+    int rc = krylov_solve_internal(ws, p, u, x, &io, &st, nullptr, 0);
+    if (rc >= 0) rc = launch_copy(&ctx->c, ws->n, y, ws->x);
+    cudaStreamSynchronize(ctx->c.stream);
+    ak_krylov_destroy(ws);
+    return rc < 0 ? rc : AK_OK;
+}

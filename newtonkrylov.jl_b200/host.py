@@ -289,6 +289,7 @@ def _base_problem(kind, nx, ny=1, **kw):
     p.un = kw.get("un")
     p.coef = kw.get("coef")
     p.work = None
+    p.user_residual = p.user_jvp = p.user_data = None
     return p
 
 
@@ -325,6 +326,100 @@ class _Bratu2D(NativeResidual):
 simple_F_ = _Simple2()
 bratu_ = _Bratu1D()
 bratu2d_ = _Bratu2D()
+
+
+# caller-supplied residuals: the generic seam of newton_krylov!(F!, u, p, res) -----------------------
+class _DeviceArrayView:
+    """Minimal __cuda_array_interface__ carrier so that torch can alias a raw device pointer."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def as_torch(ptr, shape, device_index=0):
+    """torch.float64 CUDA tensor aliasing `shape` doubles at device address `ptr` (no copy)."""
+    import torch
+
+    return torch.as_tensor(_DeviceArrayView(ptr, shape), device=torch.device("cuda", device_index))
+
+
+class UserResidual(NativeResidual):
+    """Any `F!(res, u, p)` (contract: src/Ariadne.jl:250-256) written by the caller as device code — the
+    seam that lets `newton_krylov!` take arbitrary residuals (examples/bvp.jl:10-23, spring.jl:13-17, ...).
+
+    `F_(res, u, p)` and, optionally, `jvp_(out, u, v, p)` (out <- J(u) v: what the reference obtains from
+    Enzyme forward mode, src/Ariadne.jl:48-57) receive torch.float64 CUDA tensors that ALIAS the library's
+    device vectors; they run on the library's stream (C ABI: AK_USER, ak_user_residual_fn / ak_user_jvp_fn).
+    Without `jvp_` the library forms J v = (F(u + eps v) - F(u)) / eps itself (AK_JVP_FD)."""
+
+    kind = A.AK_USER
+
+    def __init__(self, F_, jvp_=None, name=None, fd_eps=0.0):
+        self.F_, self.jvp_, self.fd_eps = F_, jvp_, float(fd_eps)
+        self.name = name or getattr(F_, "__name__", "F!")
+        self._p, self._shape, self._dev = None, None, 0
+        self._streams = {}
+        self._cb_res = A.USER_RESIDUAL(self._residual_cb)
+        self._cb_jvp = A.USER_JVP(self._jvp_cb) if jvp_ is not None else None
+
+    @classmethod
+    def from_function(cls, F, name=None):
+        """Out-of-place `F(u, p) -> tensor` (src/Ariadne.jl:245-248 wraps it as `res .= F(u, p)`); the tangent
+        comes from forward-mode AD of the same code (torch.func.jvp), like Enzyme's in the reference."""
+        import torch
+
+        def F_(res, u, p):
+            res.copy_(F(u, p))
+
+        def jvp_(out, u, v, p):
+            out.copy_(torch.func.jvp(lambda x: F(x, p), (u,), (v,))[1])
+
+        return cls(F_, jvp_, name=name or getattr(F, "__name__", "F"))
+
+    def _stream(self, handle):
+        import torch
+
+        if handle not in self._streams:
+            self._streams[handle] = torch.cuda.ExternalStream(handle, device=torch.device("cuda", self._dev))
+        return self._streams[handle]
+
+    def _residual_cb(self, _user, stream, u, res):
+        try:
+            import torch
+
+            with torch.cuda.stream(self._stream(stream)):
+                self.F_(as_torch(res, self._shape, self._dev), as_torch(u, self._shape, self._dev), self._p)
+            return 0
+        except Exception:  # noqa: BLE001 - must not unwind through the C frames
+            import traceback
+
+            traceback.print_exc()
+            return 1
+
+    def _jvp_cb(self, _user, stream, u, v, out):
+        try:
+            import torch
+
+            with torch.cuda.stream(self._stream(stream)):
+                self.jvp_(as_torch(out, self._shape, self._dev), as_torch(u, self._shape, self._dev),
+                          as_torch(v, self._shape, self._dev), self._p)
+            return 0
+        except Exception:  # noqa: BLE001
+            import traceback
+
+            traceback.print_exc()
+            return 1
+
+    def problem(self, u, p, coef=None):
+        self._p, self._shape, self._dev = p, u.shape, u.ctx.device
+        prob = _base_problem(A.AK_USER, u.n, coef=coef.ptr if coef is not None else None)
+        prob.jvp_mode = A.AK_JVP_ANALYTIC if self.jvp_ is not None else A.AK_JVP_FD
+        prob.fd_eps = self.fd_eps
+        prob.user_residual = C.cast(self._cb_res, C.c_void_p).value
+        prob.user_jvp = C.cast(self._cb_jvp, C.c_void_p).value if self._cb_jvp is not None else None
+        prob.user_data = None
+        return prob
 
 
 # right-hand sides f!(du, u, p, t) of the implicit examples -------------------------------------
@@ -442,8 +537,11 @@ class JacobianOperator:
 
     def problem(self):
         prob = self.f.problem(self.u, self.p, coef=self.coef)
-        if self.jvp_mode == "fd":
-            prob.jvp_mode, prob.fd_eps = A.AK_JVP_FD_FUSED, self.fd_eps
+        if self.jvp_mode == "fd":      # one fused pass for 2-D Bratu, two residual evaluations otherwise
+            prob.jvp_mode = A.AK_JVP_FD_FUSED if prob.kind == A.AK_BRATU2D else A.AK_JVP_FD
+            prob.fd_eps = self.fd_eps
+        elif self.jvp_mode == "fd2":   # generic (F(u + eps v) - F(u)) / eps through the residual itself
+            prob.jvp_mode, prob.fd_eps = A.AK_JVP_FD, self.fd_eps
         return prob
 
     @property
@@ -550,8 +648,91 @@ class GmresPreconditioner:
     `mul!(y, P, x) = copyto!(y, gmres(P.J, x; P.itmax)[1])`.  Passed as `N = J -> GmresPreconditioner(J, 5)`;
     the library runs the inner GMRES natively (AK_PRECOND_INNER_GMRES)."""
 
+    kind, ldiv = A.AK_PRECOND_INNER_GMRES, False
+
     def __init__(self, J, itmax):
         self.J, self.itmax = J, int(itmax)
+
+
+class TridiagonalLU:
+    """What `ilu(collect(J))` is for the 1-D Bratu Jacobian (examples/bratu.jl:121-139): LU factors of a tridiagonal
+    matrix have no fill-in, so the incomplete factorisation is the complete one.  Applied with `ldiv = true`
+    (`ldiv!(y, P, x)`), natively as a partitioned Thomas solve on the device (AK_PRECOND_TRIDIAG_LU)."""
+
+    kind, ldiv, itmax = A.AK_PRECOND_TRIDIAG_LU, True, 0
+
+    def __init__(self, J):
+        self.J = J
+
+
+def ilu(J):
+    """`ilu(collect(J))` of examples/bratu.jl:125,135 for a JacobianOperator whose matrix is tridiagonal (1-D Bratu).
+    The O(N) JVPs of `collect` are not needed: the factors are formed from the stencil inside the solve kernel."""
+    if not isinstance(J, JacobianOperator) or J.f.kind != A.AK_BRATU1D:
+        raise NotImplementedError("ilu(J) is built natively for the tridiagonal 1-D Bratu Jacobian only")
+    return TridiagonalLU(J)
+
+
+class JacobiPreconditioner:
+    """y = x ./ diag(J(u)) (AK_PRECOND_JACOBI): Bratu 1-D/2-D, heat 1-D/2-D.  A `mul!`-style object (ldiv = false)."""
+
+    kind, ldiv, itmax = A.AK_PRECOND_JACOBI, False, 0
+
+    def __init__(self, J):
+        self.J = J
+
+
+class UserPreconditioner:
+    """Any preconditioner object of the caller: `apply_(y, x)` on torch.float64 CUDA tensors aliasing the library's
+    vectors, run on the library's stream (AK_PRECOND_USER).  `ldiv` only records which of `mul!` / `ldiv!` the
+    callable stands for (Krylov.jl's `ldiv` keyword); the library just calls it."""
+
+    kind, itmax = A.AK_PRECOND_USER, 0
+
+    def __init__(self, apply_, ldiv=False, device=0):
+        self.apply_, self.ldiv, self._dev, self._n = apply_, bool(ldiv), device, None
+        self._streams = {}
+        self._cb = A.PRECOND_APPLY(self._call)
+
+    def _call(self, _user, stream, x, y):
+        try:
+            import torch
+
+            if stream not in self._streams:
+                self._streams[stream] = torch.cuda.ExternalStream(stream, device=torch.device("cuda", self._dev))
+            with torch.cuda.stream(self._streams[stream]):
+                self.apply_(as_torch(y, (self._n,), self._dev), as_torch(x, (self._n,), self._dev))
+            return 0
+        except Exception:  # noqa: BLE001 - must not unwind through the C frames
+            import traceback
+
+            traceback.print_exc()
+            return 1
+
+
+def precond_apply_(y, P, x):
+    """`mul!(y, P, x)` / `ldiv!(y, P, x)` for a native preconditioner object (what Krylov.jl calls on N(J) / M(J))."""
+    if isinstance(P, UserPreconditioner):
+        raise TypeError("a UserPreconditioner is applied by calling its own function")
+    J = P.J
+    prob = J.problem()
+    L.check(x.ctx.lib.ak_precond_apply(x.ctx.h, C.byref(prob), _ptr(J.u), P.kind, P.itmax, _ptr(x), _ptr(y)))
+    return y
+
+
+def _precond_fields(P, n, ldiv, side):
+    """(kind, itmax, apply pointer) of a preconditioner object for ak_krylov_opts."""
+    if P is None:
+        return A.AK_PRECOND_NONE, 0, None
+    if not hasattr(P, "kind"):
+        raise NotImplementedError(f"{side} = {P!r}: not a preconditioner this library can apply "
+                                  "(GmresPreconditioner, ilu(J), JacobiPreconditioner, UserPreconditioner)")
+    if bool(P.ldiv) != bool(ldiv):
+        raise ValueError(f"{side}: {type(P).__name__} is applied with ldiv = {P.ldiv} (Krylov.jl keyword `ldiv`)")
+    if isinstance(P, UserPreconditioner):
+        P._n = n
+        return P.kind, 0, C.cast(P._cb, C.c_void_p).value
+    return P.kind, P.itmax, None
 
 
 class KrylovConstructor:
@@ -597,21 +778,20 @@ def krylov_workspace(algo, kc, memory=20, max_basis=0):
 
 
 def krylov_solve_(workspace, J, b, atol=A.SQRT_EPS, rtol=A.SQRT_EPS, itmax=0, restart=False,
-                  reorthogonalization=False, history=False, fuse="mgs", verbose=0, N=None, ldiv=False,
+                  reorthogonalization=False, history=False, fuse="mgs", verbose=0, M=None, N=None, ldiv=False,
                   **unsupported):
     """krylov_solve!(workspace, J, b; kwargs...) — solves J x = b from x0 = 0.
-    `N`: right preconditioner object; only `GmresPreconditioner` is built natively."""
+    `M` / `N`: left / right preconditioner objects (GmresPreconditioner, ilu(J), JacobiPreconditioner,
+    UserPreconditioner); `ldiv` as in Krylov.jl."""
     if unsupported:
         raise TypeError(f"krylov kwargs not supported on the native path: {sorted(unsupported)}")
-    pn, pit = A.AK_PRECOND_NONE, 0
-    if N is not None:
-        if not isinstance(N, GmresPreconditioner) or ldiv:
-            raise NotImplementedError("only N = GmresPreconditioner(J, itmax) (ldiv = false) is built natively")
-        pn, pit = A.AK_PRECOND_INNER_GMRES, N.itmax
+    n = workspace.proto.n
+    pn, pit, pfn = _precond_fields(N, n, ldiv, "N")
+    pm, pmit, pmfn = _precond_fields(M, n, ldiv, "M")
     o = A.default_krylov_opts(atol=atol, rtol=rtol, itmax=itmax, restart=int(bool(restart)),
                               reorthogonalization=int(bool(reorthogonalization)), history=int(bool(history)),
                               fuse=_FUSE[fuse] if isinstance(fuse, str) else int(fuse), precond_n=pn,
-                              precond_itmax=pit)
+                              precond_itmax=pit, precond_m=pm, precond_m_itmax=pmit, n_apply=pfn, m_apply=pmfn)
     st = A.ak_krylov_stats()
     prob = J.problem()
     ctx = workspace.ctx
@@ -633,6 +813,15 @@ def krylov_solve_(workspace, J, b, atol=A.SQRT_EPS, rtol=A.SQRT_EPS, itmax=0, re
 # ---------------------------------------------------------------------------------------------
 # newton_krylov!: src/Ariadne.jl:288-372
 # ---------------------------------------------------------------------------------------------
+def _wants_coef(F_, jvp_mode):
+    """Bratu: lambda*exp(u) cache; finite-difference JVPs: F(u) cache (include/ariadne_b200.h: ak_problem.coef)."""
+    if F_.kind in (A.AK_BRATU1D, A.AK_BRATU2D):
+        return True
+    if isinstance(F_, UserResidual) and F_.jvp_ is None:
+        return True
+    return jvp_mode in ("fd", "fd2")
+
+
 def newton_krylov_(F_, u, p=None, res=None, *, tol_rel=1.0e-6, tol_abs=1.0e-12, max_niter=50,
                    forcing=EisenstatWalker(), verbose=0, algo="gmres", M=None, N=None, krylov_kwargs=None,
                    callback=lambda *args: None, memory=20, max_basis=0, history=None, workspace=None,
@@ -642,8 +831,6 @@ def newton_krylov_(F_, u, p=None, res=None, *, tol_rel=1.0e-6, tol_abs=1.0e-12, 
 
     `history` (optional list) receives one dict per Newton iteration
     (n_res, inner iterations, eta used) — not in the reference; used by the parity tests."""
-    if M is not None:
-        raise NotImplementedError("left preconditioner hook M is not on the native path yet")
     krylov_kwargs = dict(krylov_kwargs or {})
     if res is None:  # 3-argument form: res = similar(u0, M); make_zero!(res)   :259-263
         res = u.zero()
@@ -651,8 +838,11 @@ def newton_krylov_(F_, u, p=None, res=None, *, tol_rel=1.0e-6, tol_abs=1.0e-12, 
     lib = ctx.lib
     t0 = time.perf_counter_ns()
     # Bratu: lambda*exp(u) is cached by the residual kernel for the JVPs of the same Newton step
-    coef = u.similar() if F_.kind in (A.AK_BRATU1D, A.AK_BRATU2D) else None
+    # (finite-difference JVPs: F(u) is cached instead)
+    coef = u.similar() if _wants_coef(F_, jvp_mode) else None
     prob = F_.problem(u, p, coef=coef)
+    if jvp_mode == "fd2" or (jvp_mode == "fd" and prob.kind != A.AK_BRATU2D):
+        prob.jvp_mode = A.AK_JVP_FD
     nrm = C.c_double()
 
     def residual_norm():
@@ -676,6 +866,8 @@ def newton_krylov_(F_, u, p=None, res=None, *, tol_rel=1.0e-6, tol_abs=1.0e-12, 
         kwargs = dict(krylov_kwargs)
         if N is not None:
             kwargs = {"N": N(J), **kwargs}                   # kwargs = (; N = N(J), kwargs...)  :324-326
+        if M is not None:
+            kwargs = {"M": M(J), **kwargs}                   # kwargs = (; M = M(J), kwargs...)  :327-329
         if forcing is not None:
             kwargs = {"rtol": eta, **kwargs}                 # later keys win  :330-333
         kcopy_(len(res), rhs, res)                           # copy(res)      :338
@@ -704,19 +896,33 @@ def newton_krylov_(F_, u, p=None, res=None, *, tol_rel=1.0e-6, tol_abs=1.0e-12, 
 
 
 def newton_krylov(F, u0, p=None, M=None, **kwargs):
-    """Out-of-place form, src/Ariadne.jl:245-248; `F` must be one of the native residuals."""
+    """Out-of-place form, src/Ariadne.jl:245-248: `F!(res, u, p) = (res .= F(u, p))`.  `F` is one of the
+    native residuals, a UserResidual, or any callable `F(u, p) -> tensor` on torch CUDA tensors (wrapped with
+    UserResidual.from_function: tangent by forward-mode AD of the same code)."""
+    if not isinstance(F, NativeResidual):
+        if not callable(F):
+            raise TypeError("newton_krylov: F must be callable")
+        F = UserResidual.from_function(F)
     return newton_krylov_(F, u0, p, None, **kwargs)
 
 
-def _newton_opts(tol_rel, tol_abs, max_niter, forcing, algo, memory, max_basis, krylov_kwargs, verbose=0, N=None):
+def _newton_opts(tol_rel, tol_abs, max_niter, forcing, algo, memory, max_basis, krylov_kwargs, verbose=0, N=None,
+                 M=None, J=None, keep=None):
     kk = dict(krylov_kwargs or {})
     override = "rtol" in kk
     fuse = kk.pop("fuse", "mgs")
+    ldiv = bool(kk.pop("ldiv", False))
+    n = len(J.u) if J is not None else 0
     if N is not None:
-        P = N(None)
-        if not isinstance(P, GmresPreconditioner):
-            raise NotImplementedError("only N = J -> GmresPreconditioner(J, itmax) is built natively")
-        kk["precond_n"], kk["precond_itmax"] = A.AK_PRECOND_INNER_GMRES, P.itmax
+        P = N(J)
+        kk["precond_n"], kk["precond_itmax"], kk["n_apply"] = _precond_fields(P, n, ldiv, "N")
+        if keep is not None:
+            keep.append(P)
+    if M is not None:
+        P = M(J)
+        kk["precond_m"], kk["precond_m_itmax"], kk["m_apply"] = _precond_fields(P, n, ldiv, "M")
+        if keep is not None:
+            keep.append(P)
     ko = A.default_krylov_opts(fuse=_FUSE[fuse] if isinstance(fuse, str) else int(fuse),
                                **{k: (int(v) if isinstance(v, bool) else v) for k, v in kk.items()})
     o = A.default_newton_opts(tol_rel=tol_rel, tol_abs=tol_abs, max_niter=max_niter,
@@ -734,14 +940,16 @@ def _newton_opts(tol_rel, tol_abs, max_niter, forcing, algo, memory, max_basis, 
 
 def newton_krylov_native_(F_, u, p=None, res=None, *, tol_rel=1.0e-6, tol_abs=1.0e-12, max_niter=50,
                           forcing=EisenstatWalker(), algo="gmres", krylov_kwargs=None, memory=20, max_basis=0,
-                          history=None, verbose=0, N=None):
+                          history=None, verbose=0, N=None, M=None):
     """Same solve through the single C entry point ak_newton_solve (the loop runs in C++)."""
     if res is None:
         res = u.zero()
     ctx = u.ctx
-    coef = u.similar() if F_.kind in (A.AK_BRATU1D, A.AK_BRATU2D) else None
+    coef = u.similar() if _wants_coef(F_, "analytic") else None
     prob = F_.problem(u, p, coef=coef)
-    o = _newton_opts(tol_rel, tol_abs, max_niter, forcing, algo, memory, max_basis, krylov_kwargs, verbose, N=N)
+    keep = []  # preconditioner objects (their ctypes callbacks) must outlive the solve
+    o = _newton_opts(tol_rel, tol_abs, max_niter, forcing, algo, memory, max_basis, krylov_kwargs, verbose, N=N, M=M,
+                     J=JacobianOperator(F_, res, u, p, coef=coef), keep=keep)
     st = A.ak_newton_stats()
     cap = max_niter + 3
     hn, hi, he = np.zeros(cap), np.zeros(cap, dtype=np.int64), np.zeros(cap)

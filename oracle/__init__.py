@@ -67,6 +67,7 @@ def load():
         "ok_krylov_solve": (C.c_int, [C.c_void_p, _P, _dp, _dp, C.POINTER(A.ak_krylov_opts),
                                       C.POINTER(A.ak_krylov_stats), _dp, C.c_int64]),
         "ok_forcing_ew": (C.c_double, [C.c_double] * 6),
+        "ok_precond_apply": (None, [_P, _dp, C.c_int32, C.c_int32, _dp, _dp]),
         "ok_newton": (C.c_int, [_P, _dp, _dp, C.POINTER(A.ak_newton_opts), C.POINTER(A.ak_newton_stats), _dp,
                                 A.c_int64_p, _dp, C.c_int32]),
         "ok_implicit_solve": (C.c_int, [_P, _dp, C.c_int32, C.POINTER(A.ak_newton_opts), A.c_int32_p, A.c_int64_p,
@@ -98,6 +99,34 @@ def make_problem(kind, nx, ny=1, *, bc=A.AK_BC_ZERO, scheme=A.AK_STEADY, dx=0.0,
         un = _arr(un)
         p.un = un.ctypes.data
         p._keep = un
+    return p
+
+
+def make_user_problem(n, F, jvp=None, fd_eps=0.0):
+    """AK_USER problem for the oracle: `F(res, u)` / `jvp(out, u, v)` are Python callables on NumPy arrays that alias
+    the oracle's host vectors (the same callbacks the CUDA library takes, with host pointers and stream 0)."""
+    p = A.ak_problem()
+    p.kind, p.bc, p.scheme = A.AK_USER, A.AK_BC_ZERO, A.AK_STEADY
+    p.jvp_mode = A.AK_JVP_ANALYTIC if jvp is not None else A.AK_JVP_FD
+    p.nx, p.ny, p.gny, p.gy0 = n, 1, 1, 0
+    p.fd_eps = fd_eps
+
+    def view(ptr):
+        return np.ctypeslib.as_array(C.cast(ptr, _dp), shape=(n,))
+
+    def res_cb(_user, _stream, u, res):
+        F(view(res), view(u))
+        return 0
+
+    def jvp_cb(_user, _stream, u, v, out):
+        jvp(view(out), view(u), view(v))
+        return 0
+
+    cb_r = A.USER_RESIDUAL(res_cb)
+    cb_j = A.USER_JVP(jvp_cb) if jvp is not None else None
+    p.user_residual = C.cast(cb_r, C.c_void_p).value
+    p.user_jvp = C.cast(cb_j, C.c_void_p).value if cb_j is not None else None
+    p._keep = (cb_r, cb_j)
     return p
 
 
@@ -143,6 +172,24 @@ def sym_givens(a, b):
 
 def forcing_ew(eta_max, gamma, eta, tol, n_res, n_res_prior):
     return load().ok_forcing_ew(eta_max, gamma, eta, tol, n_res, n_res_prior)
+
+
+def user_precond(n, apply):
+    """(callback pointer, keep-alive object) for AK_PRECOND_USER on the oracle side: `apply(y, x)` on NumPy views."""
+    def cb(_user, _stream, x, y):
+        apply(np.ctypeslib.as_array(C.cast(y, _dp), shape=(n,)), np.ctypeslib.as_array(C.cast(x, _dp), shape=(n,)))
+        return 0
+
+    f = A.PRECOND_APPLY(cb)
+    return C.cast(f, C.c_void_p).value, f
+
+
+def precond_apply(p, u, kind, x, itmax=0):
+    """y = P x for a native preconditioner kind (the oracle's restatement)."""
+    u, x = _arr(u), _arr(x)
+    y = np.empty_like(x)
+    load().ok_precond_apply(C.byref(p), _d(u), kind, itmax, _d(x), _d(y))
+    return y
 
 
 def krylov_solve(p, u, b, *, algo=A.AK_ALGO_GMRES, memory=20, hist_cap=0, **kw):

@@ -498,6 +498,7 @@ typedef struct ok_krylov {
     double** Z;         /* fgmres: z_k = N v_k */
     int64_t nZ;
     double* pbuf;       /* right-preconditioned gmres: p = N v_k */
+    double* qbuf;       /* left-preconditioned gmres: q = M w (Krylov.jl solver.q) */
     double *c, *s, *z, *R;
     int64_t cap_cs, cap_z, cap_R;
     /* cg */
@@ -513,6 +514,7 @@ OK_EXPORT ok_krylov* ok_krylov_create(int32_t algo, int64_t n, int32_t memory) {
     if (algo == AK_ALGO_GMRES || algo == AK_ALGO_FGMRES) {
         ws->w = ok_alloc(n);
         ws->pbuf = ok_alloc(n);
+        ws->qbuf = ok_alloc(n);
         if (algo == AK_ALGO_FGMRES) {
             ws->nZ = memory;
             ws->Z = (double**)calloc((size_t)memory, sizeof(double*));
@@ -539,7 +541,7 @@ OK_EXPORT void ok_krylov_destroy(ok_krylov* ws) {
     if (!ws) return;
     for (int64_t i = 0; i < ws->nV; ++i) free(ws->V[i]);
     for (int64_t i = 0; i < ws->nZ; ++i) free(ws->Z[i]);
-    free(ws->Z); free(ws->pbuf);
+    free(ws->Z); free(ws->pbuf); free(ws->qbuf);
     free(ws->V); free(ws->x); free(ws->w); free(ws->dx);
     free(ws->c); free(ws->s); free(ws->z); free(ws->R);
     free(ws->r); free(ws->pp); free(ws->Ap);
@@ -562,22 +564,93 @@ OK_EXPORT int ok_gmres(ok_krylov* ws, const ak_problem* p, const double* u, cons
                        const ak_krylov_opts* o, ak_krylov_stats* st, double* hist, int64_t hist_cap);
 OK_EXPORT void ok_krylov_default_opts(ak_krylov_opts* o);
 
-/* out <- N in, the right preconditioner.  AK_PRECOND_INNER_GMRES restates
- *   mul!(y, P::GmresPreconditioner, x) = copyto!(y, gmres(P.J, x; P.itmax)[1])   examples/bratu.jl:146-149
- * i.e. a fresh workspace (memory 20), default atol = rtol = sqrt(eps), x0 = 0, at most itmax iterations. */
-static void apply_precond_n(const ak_problem* p, const double* u, const ak_krylov_opts* o, int64_t n,
-                            const double* in, double* out) {
-    ok_krylov* in_ws = ok_krylov_create(AK_ALGO_GMRES, n, 20);
-    ak_krylov_opts io;
-    ok_krylov_default_opts(&io);
-    io.itmax = o->precond_itmax;
-    ak_krylov_stats ist;
-    ok_gmres(in_ws, p, u, in, &io, &ist, NULL, 0);
-    ok_copy(n, out, in_ws->x);
-    ok_krylov_destroy(in_ws);
+/* diag(J(u)) of the stencil Jacobians (AK_PRECOND_JACOBI) */
+static int jacobian_diagonal(const ak_problem* p, const double* u, double* d) {
+    const int64_t n = ok_problem_size(p);
+    const double c1 = (p->scheme == AK_EULER) ? p->dt : p->dt / 2.0; /* Midpoint: dt (1 - alpha), Trapezoid: dt / 2 */
+    switch (p->kind) {
+        case AK_BRATU1D:
+            for (int64_t i = 0; i < n; ++i) d[i] = -2.0 / (p->dx * p->dx) + p->lambda * exp(u[i]);
+            return 0;
+        case AK_BRATU2D:
+            for (int64_t i = 0; i < n; ++i)
+                d[i] = (-2.0 / (p->dx * p->dx) - 2.0 / (p->dy * p->dy)) + p->lambda * exp(u[i]);
+            return 0;
+        case AK_HEAT1D:
+            for (int64_t i = 0; i < n; ++i) d[i] = c1 * (p->a * (-2.0 / (p->dx * p->dx))) - 1.0;
+            if (p->bc == AK_BC_ZERO) d[0] = d[n - 1] = -1.0; /* zero rows of J (bc!): any non-zero pivot */
+            return 0;
+        case AK_HEAT2D:
+            for (int64_t i = 0; i < n; ++i)
+                d[i] = c1 * (p->a * (-2.0 / (p->dx * p->dx) - 2.0 / (p->dy * p->dy))) - 1.0;
+            return 0;
+        default: return -1;
+    }
 }
 
-/* GMRES / FGMRES, Krylov.jl gmres! and fgmres! with M = I and an optional right preconditioner N.
+/* out <- P in for a preconditioner named by kind (include/ariadne_b200.h AK_PRECOND_*).
+ * AK_PRECOND_INNER_GMRES restates
+ *   mul!(y, P::GmresPreconditioner, x) = copyto!(y, gmres(P.J, x; P.itmax)[1])   examples/bratu.jl:146-149
+ * i.e. a fresh workspace (memory 20), default atol = rtol = sqrt(eps), x0 = 0, at most itmax iterations.
+ * AK_PRECOND_TRIDIAG_LU: ldiv!(y, ilu(collect(J)), x) for the tridiagonal 1-D Bratu Jacobian
+ * (examples/bratu.jl:121-139): LU of a tridiagonal matrix has no fill-in, so the incomplete factors are the
+ * complete ones; Thomas algorithm without pivoting. */
+static void apply_precond(const ak_problem* p, const double* u, int32_t kind, int32_t itmax, ak_precond_apply_fn fn,
+                          void* user, int64_t n, const double* in, double* out) {
+    if (kind == AK_PRECOND_INNER_GMRES) {
+        ok_krylov* in_ws = ok_krylov_create(AK_ALGO_GMRES, n, 20);
+        ak_krylov_opts io;
+        ok_krylov_default_opts(&io);
+        io.itmax = itmax;
+        ak_krylov_stats ist;
+        ok_gmres(in_ws, p, u, in, &io, &ist, NULL, 0);
+        ok_copy(n, out, in_ws->x);
+        ok_krylov_destroy(in_ws);
+    } else if (kind == AK_PRECOND_USER) {
+        if (!fn || fn(user, 0, in, out) != 0) { fprintf(stderr, "oracle: user preconditioner failed\n"); abort(); }
+    } else if (kind == AK_PRECOND_JACOBI) {
+        double* d = ok_alloc(n);
+        if (jacobian_diagonal(p, u, d) != 0) { fprintf(stderr, "oracle: Jacobi for kind %d\n", p->kind); abort(); }
+        for (int64_t i = 0; i < n; ++i) out[i] = in[i] / d[i];
+        free(d);
+    } else if (kind == AK_PRECOND_TRIDIAG_LU) {
+        if (p->kind != AK_BRATU1D) { fprintf(stderr, "oracle: tridiagonal LU for kind %d\n", p->kind); abort(); }
+        const double o = 1.0 / (p->dx * p->dx);
+        double* cp = ok_alloc(n);
+        double* d = ok_alloc(n);
+        jacobian_diagonal(p, u, d);
+        /* Thomas: forward elimination, back substitution */
+        double piv = d[0];
+        cp[0] = o / piv;
+        out[0] = in[0] / piv;
+        for (int64_t i = 1; i < n; ++i) {
+            piv = d[i] - o * cp[i - 1];
+            cp[i] = o / piv;
+            out[i] = (in[i] - o * out[i - 1]) / piv;
+        }
+        for (int64_t i = n - 2; i >= 0; --i) out[i] -= cp[i] * out[i + 1];
+        free(cp);
+        free(d);
+    } else {
+        fprintf(stderr, "oracle: unknown preconditioner %d\n", kind);
+        abort();
+    }
+}
+OK_EXPORT void ok_precond_apply(const ak_problem* p, const double* u, int32_t kind, int32_t itmax, const double* x,
+                                double* y) {
+    apply_precond(p, u, kind, itmax, NULL, NULL, ok_problem_size(p), x, y);
+}
+static void apply_precond_n(const ak_problem* p, const double* u, const ak_krylov_opts* o, int64_t n,
+                            const double* in, double* out) {
+    apply_precond(p, u, o->precond_n, o->precond_itmax, o->n_apply, o->n_user, n, in, out);
+}
+static void apply_precond_m(const ak_problem* p, const double* u, const ak_krylov_opts* o, int64_t n,
+                            const double* in, double* out) {
+    apply_precond(p, u, o->precond_m, o->precond_m_itmax, o->m_apply, o->m_user, n, in, out);
+}
+
+/* GMRES / FGMRES, Krylov.jl gmres! and fgmres! with optional left (M) and right (N) preconditioners:
+ * r0 = M (b - A x), q = M A N v_k, residual norms measured in the M-preconditioned space, x = N V y.
  * Returns stats; x in ws->x.  `u` is the linearisation point of J = JacobianOperator(F!, res, u, p). */
 OK_EXPORT int ok_gmres(ok_krylov* ws, const ak_problem* p, const double* u, const double* b,
                        const ak_krylov_opts* o, ak_krylov_stats* st, double* hist, int64_t hist_cap) {
@@ -595,8 +668,10 @@ OK_EXPORT int ok_gmres(ok_krylov* ws, const ak_problem* p, const double* u, cons
         xr = ws->dx;
     }
     ok_fill(n, x, 0.0);
-    ok_copy(n, w, b);          /* w <- b ; r0 === w (no left preconditioner) */
-    double* r0 = w;
+    const int lprec = (o->precond_m != AK_PRECOND_NONE);
+    ok_copy(n, w, b);          /* w <- b ; r0 === w without left preconditioner, else r0 = M w in solver.q */
+    double* r0 = lprec ? ws->qbuf : w;
+    if (lprec) apply_precond_m(p, u, o, n, w, r0);
     double beta = ok_nrm2(n, r0);
     double rNorm = beta;
     if (hist && nh < hist_cap) hist[nh++] = beta;
@@ -627,6 +702,7 @@ OK_EXPORT int ok_gmres(ok_krylov* ws, const ak_problem* p, const double* u, cons
                 /* w <- b - A x  (mul!(w, A, x); kaxpby!(n, 1, b, -1, w)) */
                 ok_jvp(p, u, x, w);
                 ok_axpby(n, 1.0, b, -1.0, w);
+                if (lprec) apply_precond_m(p, u, o, n, w, r0);
             }
         }
         beta = ok_nrm2(n, r0);
@@ -663,7 +739,8 @@ OK_EXPORT int ok_gmres(ok_krylov* ws, const ak_problem* p, const double* u, cons
                 pv = tgt;
             }
             ok_jvp(p, u, pv, w);
-            double* q = w;
+            double* q = lprec ? ws->qbuf : w;
+            if (lprec) apply_precond_m(p, u, o, n, w, q); /* q <- M A N v_k */
             for (int64_t i = 0; i < k; ++i) { /* modified Gram-Schmidt */
                 double h = ok_dot(n, ws->V[i], q);
                 ws->R[nr + i] = h;

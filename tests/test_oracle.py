@@ -286,3 +286,119 @@ def test_fgmres_restatement(oracle):
     Jd = oracle.dense_jacobian(po, d["u0"])
     assert s2["solved"] and s2["niter"] < s0["niter"] / 3
     assert np.linalg.norm(b.ravel() - Jd @ x2.ravel()) == pytest.approx(h2[-1], rel=1e-6)
+
+
+# ---- generic residual seam (AK_USER) on the oracle side ---------------------------------------------------
+def test_oracle_user_problem_reproduces_native_bratu(oracle):
+    """The oracle driven through user callbacks (NumPy restatement of bratu!, examples/bratu.jl:14-24, and its
+    tangent) walks the same Newton path as its built-in Bratu residual."""
+    d = P.bratu1d(200)
+    dx2, lam, N = d["dx"] ** 2, d["lam"], d["nx"]
+
+    def F(res, y):
+        yl = np.concatenate(([0.0], y[:-1]))
+        yr = np.concatenate((y[1:], [0.0]))
+        res[:] = ((yr - 2.0 * y) + yl) / dx2 + lam * np.exp(y)
+
+    def jvp(out, y, v):
+        vl = np.concatenate(([0.0], v[:-1]))
+        vr = np.concatenate((v[1:], [0.0]))
+        out[:] = ((vr - 2.0 * v) + vl) / dx2 + (lam * np.exp(y)) * v
+
+    pu = oracle.make_user_problem(N, F, jvp)
+    pn = P.oracle_problem(oracle, d)
+    r1, _ = oracle.residual(pu, d["u0"])
+    r2, _ = oracle.residual(pn, d["u0"])
+    assert np.max(np.abs(r1 - r2)) <= 4 * np.spacing(np.max(np.abs(r2)))
+    o = A.default_newton_opts(algo=A.AK_ALGO_CG)
+    u1, s1, h1 = oracle.newton(pu, d["u0"], o)
+    u2, s2, h2 = oracle.newton(pn, d["u0"], o)
+    assert s1["solved"] and s2["solved"] and s1["outer_iterations"] == s2["outer_iterations"]
+    assert np.linalg.norm(u1 - u2) <= 1e-9 * np.linalg.norm(u2)
+
+
+def test_oracle_finite_difference_jvp(oracle):
+    """AK_JVP_FD: (F(u + eps v) - F(u)) / eps with eps = sqrt(eps_mach)(1 + ||u||)/||v|| is O(1e-7) from the tangent."""
+    d = P.bratu2d(12)
+    p = P.oracle_problem(oracle, d)
+    v = np.random.default_rng(5).standard_normal(d["u0"].shape)
+    ja, _ = oracle.jvp(p, d["u0"], v)
+    p.jvp_mode = A.AK_JVP_FD
+    jf, _ = oracle.jvp(p, d["u0"], v)
+    err = np.linalg.norm(jf - ja) / np.linalg.norm(ja)
+    assert 1e-13 < err < 1e-5
+
+
+# ---- preconditioner hooks M / N (src/Ariadne.jl:296-297,324-329) on the oracle side ---------------------------
+def _dense_solve(oracle, p, u, b):
+    return np.linalg.solve(oracle.dense_jacobian(p, u), np.ravel(b))
+
+
+def test_oracle_tridiagonal_lu_is_the_exact_inverse(oracle):
+    """`ilu(collect(J))` of examples/bratu.jl:121-139: for the tridiagonal 1-D Bratu Jacobian the factors are exact,
+    so N = J^-1 and right-preconditioned GMRES / FGMRES converge in one iteration."""
+    d = P.bratu1d(300)
+    p = P.oracle_problem(oracle, d)
+    b = RNG.standard_normal(300)
+    y = oracle.precond_apply(p, d["u0"], A.AK_PRECOND_TRIDIAG_LU, b)
+    xd = _dense_solve(oracle, p, d["u0"], b)
+    assert np.linalg.norm(y - xd) <= 1e-11 * np.linalg.norm(xd)
+    for algo in (A.AK_ALGO_GMRES, A.AK_ALGO_FGMRES):
+        x, st, hist = oracle.krylov_solve(p, d["u0"], b, algo=algo, precond_n=A.AK_PRECOND_TRIDIAG_LU, hist_cap=10)
+        assert st["solved"] and st["niter"] == 1
+        assert np.linalg.norm(x - xd) <= 1e-10 * np.linalg.norm(xd)
+
+
+@pytest.mark.parametrize("side", ["M", "N", "MN"])
+def test_oracle_jacobi_left_and_right(oracle, side):
+    d = P.bratu2d(10)
+    p = P.oracle_problem(oracle, d)
+    b = RNG.standard_normal(100)
+    kw = {}
+    if "N" in side:
+        kw["precond_n"] = A.AK_PRECOND_JACOBI
+    if "M" in side:
+        kw["precond_m"] = A.AK_PRECOND_JACOBI
+    x, st, hist = oracle.krylov_solve(p, d["u0"], b, rtol=1e-12, atol=0.0, hist_cap=400, **kw)
+    xd = _dense_solve(oracle, p, d["u0"], b)
+    assert st["solved"]
+    assert np.linalg.norm(x.ravel() - xd) <= 1e-9 * np.linalg.norm(xd)
+    if "M" in side:  # residual norms are measured in the M-preconditioned space: hist[0] = ||M b||
+        Mb = oracle.precond_apply(p, d["u0"], A.AK_PRECOND_JACOBI, b)
+        assert abs(hist[0] - np.linalg.norm(Mb)) <= 1e-13 * hist[0]
+    else:
+        assert abs(hist[0] - np.linalg.norm(b)) <= 1e-13 * hist[0]
+
+
+def test_oracle_user_preconditioner_equals_native_jacobi(oracle):
+    d = P.bratu1d(120)
+    p = P.oracle_problem(oracle, d)
+    b = RNG.standard_normal(120)
+    diag = -2.0 / d["dx"] ** 2 + d["lam"] * np.exp(d["u0"])
+
+    def apply(y, x):
+        y[:] = x / diag
+
+    fn, keep = oracle.user_precond(120, apply)
+    x1, s1, h1 = oracle.krylov_solve(p, d["u0"], b, precond_n=A.AK_PRECOND_USER, n_apply=fn, hist_cap=300)
+    x2, s2, h2 = oracle.krylov_solve(p, d["u0"], b, precond_n=A.AK_PRECOND_JACOBI, hist_cap=300)
+    assert s1["niter"] == s2["niter"] and np.allclose(h1, h2, rtol=1e-9)
+    assert np.linalg.norm(x1 - x2) <= 1e-10 * np.linalg.norm(x2)
+    del keep
+
+
+def test_oracle_newton_gmres_ilu_bratu_example(oracle):
+    """examples/bratu.jl:121-139 (N = 10_000, lambda = 3.51382): GMRES + ILU and FGMRES + ILU.  With the exact
+    tridiagonal factors every linear solve takes one iteration; the result matches the analytic solution
+    (examples/bratu.jl:33-37) to discretisation accuracy."""
+    d = P.bratu1d(10000, lam=3.51382)
+    p = P.oracle_problem(oracle, d)
+    for algo in (A.AK_ALGO_GMRES, A.AK_ALGO_FGMRES):
+        o = A.default_newton_opts(algo=algo)
+        o.krylov.precond_n = A.AK_PRECOND_TRIDIAG_LU
+        u, st, hist = oracle.newton(p, d["u0"], o)
+        assert st["solved"]
+        assert all(h["inner"] == 1 for h in hist[1:])
+        theta = GOLD["bratu_analytic"]["theta"] if "bratu_analytic" in GOLD else 4.79173
+        ref = -2.0 * np.log(np.cosh(theta * (d["x"] - 0.5) / 2.0) / np.cosh(theta / 4.0))
+        assert np.max(np.abs(u - ref)) < 1e-4
