@@ -57,6 +57,7 @@ SIGNATURES = {
     "ak_residual": (C.c_int, [_vp, C.POINTER(A.ak_problem), _vp, _vp, _dp]),
     "ak_jvp": (C.c_int, [_vp, C.POINTER(A.ak_problem), _vp, _vp, _vp]),
     "ak_jvp_transpose": (C.c_int, [_vp, C.POINTER(A.ak_problem), _vp, _vp, _vp]),
+    "ak_jvp_batched": (C.c_int, [_vp, C.POINTER(A.ak_problem), _vp, _vp, C.c_int64, _vp, C.c_int64, C.c_int32]),
     "ak_dot": (C.c_int, [_vp, C.c_int64, _vp, _vp, _dp]),
     "ak_nrm2": (C.c_int, [_vp, C.c_int64, _vp, _dp]),
     "ak_scal": (C.c_int, [_vp, C.c_int64, C.c_double, _vp]),

@@ -1072,8 +1072,33 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     return AK_OK;
 }
 
+// y[j] = x[j] * s[j % 4]   (node-wise scaling of a DG vector: 4 LGL nodes per element)
+__global__ void __launch_bounds__(256) k_scale_nodes4(double* __restrict__ y, const double* __restrict__ x, double s0,
+                                                      double s1, double s2, double s3, int64_t n) {
+    const double s[4] = {s0, s1, s2, s3};
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += nth) y[j] = __dmul_rn(x[j], s[j & 3]);
+}
+
 int launch_jvp_transpose(Ctx* ctx, const ak_problem* p, const double* u, double* v, double* out) {
     AK_TRY(check_problem(p));
+    if (p->kind == AK_HEAT1D_DG) {
+        // Upwind SBP duality  M D+ + D-^T M = 0  (M = (h/2) diag(w), w = LGL weights 1/6, 5/6, 5/6, 1/6) gives
+        // (D- D+)^T = M D- D+ M^-1, hence J^T = W J W^-1 for every time discretisation (J = c D- D+ - I):
+        // two node-wise scalings around the forward tangent kernel.
+        const int64_t n = p->nx;
+        PoolVec t(ctx, n);
+        if (!t.p) { set_error("out of device memory for the DG transpose scratch"); return AK_ERR_NOMEM; }
+        const int blocks = ew_blocks(ctx, n);
+        const double w0 = 1.0 / 6.0, w1 = 5.0 / 6.0;
+        k_scale_nodes4<<<blocks, 256, 0, ctx->stream>>>(t.p, v, 1.0 / w0, 1.0 / w1, 1.0 / w1, 1.0 / w0, n);
+        ctx->launches++;
+        AK_TRY(launch_jvp(ctx, p, u, t.p, out, nullptr));
+        k_scale_nodes4<<<blocks, 256, 0, ctx->stream>>>(out, out, w0, w1, w1, w0, n);
+        ctx->launches++;
+        AK_CUDA(cudaGetLastError());
+        return AK_OK;
+    }
     switch (p->kind) {
         case AK_SIMPLE2:
             k_simple2<<<1, 32, 0, ctx->stream>>>(u, v, out, nullptr, 2, nullptr, nullptr);
@@ -1122,6 +1147,15 @@ AK_API int ak_residual(ak_ctx* ctx, const ak_problem* p, double* u, double* res,
 AK_API int ak_jvp(ak_ctx* ctx, const ak_problem* p, const double* u, double* v, double* out) {
     AK_REQUIRE(ctx && p && v && out, "ak_jvp: NULL argument");
     return launch_jvp(&ctx->c, p, u, v, out, nullptr);
+}
+
+AK_API int ak_jvp_batched(ak_ctx* ctx, const ak_problem* p, const double* u, double* V, int64_t ldv, double* Out,
+                          int64_t ldo, int32_t ncols) {
+    AK_REQUIRE(ctx && p && V && Out && ncols >= 0, "ak_jvp_batched: bad argument");
+    const int64_t n = ak_problem_size(p);
+    AK_REQUIRE(ldv >= n && ldo >= n, "ak_jvp_batched: leading dimensions must be >= n");
+    for (int32_t c = 0; c < ncols; ++c) AK_TRY(launch_jvp(&ctx->c, p, u, V + (int64_t)c * ldv, Out + (int64_t)c * ldo, nullptr));
+    return AK_OK;
 }
 
 AK_API int ak_jvp_transpose(ak_ctx* ctx, const ak_problem* p, const double* u, double* v, double* out) {

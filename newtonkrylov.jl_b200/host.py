@@ -580,8 +580,100 @@ def mul_(out, J, v):
     return None
 
 
-def collect(JOp):
-    """Base.collect(J): src/Ariadne.jl:140-162 — one JVP per column; dense ndarray (small n only)."""
+def mul_batched_(Out, J, V):
+    """mul!(Out, J, V) for matrices (src/Ariadne.jl:69-83).  `V`, `Out`: DeviceVectors of shape (ncols, n) — the
+    column-major n x ncols matrices of the reference, one column per row of the C-ordered array."""
+    ncols, n = V.shape[0], int(np.prod(V.shape[1:]))
+    prob = J.problem()
+    L.check(V.ctx.lib.ak_jvp_batched(V.ctx.h, C.byref(prob), _ptr(J.u), _ptr(V), n, _ptr(Out), n, ncols))
+    return None
+
+
+def _ring_colours(N, s):
+    """Colours of N columns on a ring such that equal colours are >= s apart: j mod s on the main range, one
+    colour of their own for the N mod s trailing columns.  Returns (colour array, number of colours)."""
+    if N <= s:
+        return np.arange(N), N
+    main = N - (N % s)
+    col = np.arange(N) % s
+    col[main:] = s + np.arange(N - main)
+    return col, s + (N - main)
+
+
+def collect(JOp, sparse=False, bandwidth=None):
+    """Base.collect(J): src/Ariadne.jl:140-162.
+
+    sparse = False: one JVP per column, dense ndarray (small n only).
+    sparse = True:  the reference assembles a SparseMatrixCSC with N JVPs; here the stencil structure is used
+    (SURVEY §8f-4): columns that cannot share a row are probed together (ring colouring, 3-15 colours in 1-D,
+    9-25 on the 2-D five-point grid), so the whole Jacobian costs a handful of JVPs.  Returns scipy.sparse CSR.
+    `bandwidth`: half-width for AK_USER operators (|i - j| <= bandwidth on the ring)."""
+    if not sparse:
+        return _collect_dense(JOp)
+    tr = isinstance(JOp, TransposeOperator)
+    J = JOp.parent if tr else JOp
+    prob = J.problem()
+    u = J.u
+    n = u.n
+    colour, ncol, offsets = probe_plan(prob.kind, prob.bc, u.shape, bandwidth)
+    probes = np.zeros((ncol, n))
+    probes[colour, np.arange(n)] = 1.0
+    V = DeviceVector.from_numpy(probes, u.ctx)
+    Out = DeviceVector(u.ctx, (ncol, n))
+    kfill_(Out, 0.0)
+    mul_batched_(Out, J, V)
+    M = assemble_probed(Out.numpy(), colour, offsets, n)
+    return M.T.tocsr() if tr else M
+
+
+def probe_plan(kind, bc, shape, bandwidth=None):
+    """(colour of every column, number of colours, candidate column of every row per stencil offset) — pure host logic."""
+    n = int(np.prod(shape))
+    if kind in (A.AK_BRATU2D, A.AK_HEAT2D):
+        ny, nx = shape
+        cx, ncx = _ring_colours(nx, 3)
+        cy, ncy = _ring_colours(ny, 3)
+        colour = (cy[:, None] * ncx + cx[None, :]).reshape(-1)
+        ii, jj = np.meshgrid(np.arange(nx), np.arange(ny))
+        offsets = [(((jj + dy_) % ny) * nx + (ii + dx_) % nx).reshape(-1)
+                   for dx_, dy_ in ((0, 0), (1, 0), (-1, 0), (0, 1), (0, -1))]
+        return colour, ncx * ncy, offsets
+    w = bandwidth
+    if w is None:
+        if kind == A.AK_BRATU1D:
+            w = 1
+        elif kind == A.AK_HEAT1D:
+            w = 3 if bc == A.AK_BC_PERIODIC else 1   # periodic_bc! copies u[end-1] into u[1]: ring distance 3
+        elif kind == A.AK_HEAT1D_DG:
+            w = 7                                     # D1m * D1p couples an element with both neighbours
+        else:
+            raise NotImplementedError("collect(J, sparse=True): pass bandwidth= for this operator")
+    colour, ncol = _ring_colours(n, 2 * w + 1)
+    rows = np.arange(n)
+    offsets = [(rows + d) % n for d in range(-w, w + 1)] if n > 2 * w + 1 else [np.full(n, j) for j in range(n)]
+    return colour, ncol, offsets
+
+
+def assemble_probed(Y, colour, offsets, n):
+    """CSR matrix from the probe products Y[c] = J * (sum of the unit vectors of colour c)."""
+    import scipy.sparse as sp
+
+    rows = np.arange(n)
+    R, Cc, D = [], [], []
+    done = np.zeros((0, n), dtype=np.int64)
+    for cols in offsets:
+        fresh = np.ones(n, dtype=bool)
+        for prev in done:            # tiny grids: two offsets can wrap onto the same column of a row
+            fresh &= prev != cols
+        done = np.vstack([done, cols[None, :]])
+        vals = Y[colour[cols], rows]
+        nz = (vals != 0.0) & fresh
+        R.append(rows[nz]); Cc.append(cols[nz]); D.append(vals[nz])
+    return sp.csr_matrix((np.concatenate(D), (np.concatenate(R), np.concatenate(Cc))), shape=(n, n))
+
+
+def _collect_dense(JOp):
+    """One JVP per column (the literal algorithm of src/Ariadne.jl:140-162)."""
     J = JOp.parent if isinstance(JOp, TransposeOperator) else JOp
     N, M = JOp.size()
     v = (J.res if isinstance(JOp, TransposeOperator) else J.u).zero()

@@ -283,3 +283,64 @@ def test_fused_finite_difference_jvp(nk, ctx, oracle):
     _, r_ex = nk.newton_krylov_(F_, u2, p, None, history=h_ex)
     assert r_fd.solved and r_fd.stats.outer_iterations == r_ex.stats.outer_iterations
     assert np.linalg.norm(u.numpy() - u2.numpy()) / np.linalg.norm(u2.numpy()) < 1e-6
+
+
+# ---- collect(J) by probing, J^T for the DG operator, batched mul! ----------------------------------
+COLLECT_CASES = [
+    ("bratu1d", lambda: P.bratu1d(50)), ("bratu1d_tiny", lambda: P.bratu1d(3)),
+    ("heat1d_zero", lambda: P.heat1d(40)), ("heat1d_periodic", lambda: P.heat1d(41, bc=A.AK_BC_PERIODIC)),
+    ("dg", lambda: P.heat1d_dg(13)), ("dg_min", lambda: P.heat1d_dg(3)),
+    ("bratu2d", lambda: P.bratu2d(7, 5)), ("bratu2d_thin", lambda: P.bratu2d(9, 2)),
+    ("heat2d_zero", lambda: P.heat2d(8, dt_scale=16.0)), ("heat2d_periodic", lambda: P.heat2d(7, dt_scale=16.0, bc=A.AK_BC_PERIODIC)),
+]
+
+
+@pytest.mark.parametrize("name,make", COLLECT_CASES, ids=[c[0] for c in COLLECT_CASES])
+def test_sparse_collect_equals_column_by_column_collect(nk, ctx, name, make):
+    """`collect(J)` (src/Ariadne.jl:140-162) assembled from a handful of colour-probe JVPs equals the literal
+    one-JVP-per-column algorithm entry for entry."""
+    d = make()
+    F_, u, p, _ = P.device_setup(nk, ctx, d)
+    J = nk.JacobianOperator(F_, u.zero(), u, p)
+    dense = nk.collect(J)
+    sparse = nk.collect(J, sparse=True)
+    assert sparse.shape == dense.shape
+    assert np.array_equal(sparse.toarray(), dense)
+    assert sparse.nnz <= 5 * dense.shape[0] if d["kind"] != A.AK_HEAT1D_DG else sparse.nnz <= 12 * dense.shape[0]
+
+
+@pytest.mark.parametrize("scheme", ["euler", "midpoint", "trapezoid"])
+def test_dg_transpose_product(nk, ctx, oracle, scheme):
+    """J^T v for the DG operator (src/Ariadne.jl:93-107): J^T = W J W^-1 by upwind-SBP duality, against the
+    transpose of the collected Jacobian and the oracle's dense probe."""
+    d = P.heat1d_dg(16, dt=1e-3)
+    d["scheme"] = {"euler": A.AK_EULER, "midpoint": A.AK_MIDPOINT, "trapezoid": A.AK_TRAPEZOID}[scheme]
+    G_ = {"euler": nk.G_Euler_, "midpoint": nk.G_Midpoint_, "trapezoid": nk.G_Trapezoid_}[scheme]
+    u = nk.DeviceVector.from_numpy(d["u0"], ctx)
+    un = nk.DeviceVector.from_numpy(d["u0"], ctx)
+    F_ = nk.ImplicitResidual(G_, nk.heat_1D_DG_)
+    J = nk.JacobianOperator(F_, u.zero(), u, (un, d["dt"], un.zero(), (d["dx"],), 0.0))
+    v0 = RNG.standard_normal(d["nx"])
+    out = u.zero()
+    nk.mul_(out, nk.transpose(J), nk.DeviceVector.from_numpy(v0, ctx))
+    Jd = nk.collect(J)
+    ref = Jd.T @ v0
+    assert np.linalg.norm(out.numpy() - ref) <= 1e-12 * np.linalg.norm(ref)
+    po = P.oracle_problem(oracle, d, un=d["u0"])
+    ro = oracle.jvp_transpose_dense(po, d["u0"], v0)
+    assert np.linalg.norm(out.numpy() - ro) <= 1e-12 * np.linalg.norm(ro)
+
+
+def test_batched_jvp(nk, ctx):
+    """mul!(Out, J, V) for a matrix V (src/Ariadne.jl:69-83, test/runtests.jl:57-66) == column-wise mul!."""
+    d = P.bratu2d(20, 12)
+    F_, u, p, _ = P.device_setup(nk, ctx, d)
+    J = nk.JacobianOperator(F_, u.zero(), u, p)
+    V0 = RNG.standard_normal((5, 12 * 20))
+    V = nk.DeviceVector.from_numpy(V0, ctx)
+    Out = nk.DeviceVector(ctx, (5, 12 * 20))
+    nk.mul_batched_(Out, J, V)
+    for c in range(5):
+        o = u.zero()
+        nk.mul_(o, J, nk.DeviceVector.from_numpy(V0[c].reshape(12, 20), ctx))
+        assert np.array_equal(Out.numpy()[c], o.numpy().reshape(-1))

@@ -402,3 +402,28 @@ def test_oracle_newton_gmres_ilu_bratu_example(oracle):
         theta = GOLD["bratu_analytic"]["theta"] if "bratu_analytic" in GOLD else 4.79173
         ref = -2.0 * np.log(np.cosh(theta * (d["x"] - 0.5) / 2.0) / np.cosh(theta / 4.0))
         assert np.max(np.abs(u - ref)) < 1e-4
+
+
+# ---- collect(J) by colour probing: the host-side plan of newtonkrylov.jl_b200.host.collect(sparse=True) -------------
+@pytest.mark.parametrize("make", [lambda: P.bratu1d(50), lambda: P.bratu1d(3), lambda: P.heat1d(40),
+                                  lambda: P.heat1d(41, bc=A.AK_BC_PERIODIC), lambda: P.heat1d_dg(13),
+                                  lambda: P.heat1d_dg(3), lambda: P.bratu2d(7, 5), lambda: P.bratu2d(9, 2),
+                                  lambda: P.bratu2d(2, 2), lambda: P.heat2d(8, dt_scale=16.0),
+                                  lambda: P.heat2d(7, dt_scale=16.0, bc=A.AK_BC_PERIODIC),
+                                  lambda: P.heat2d(3, dt_scale=16.0, bc=A.AK_BC_PERIODIC)])
+def test_probe_plan_recovers_the_dense_jacobian(oracle, make):
+    """Ring colouring + per-offset attribution (pure host logic of the product) on the oracle's JVP: the matrix
+    assembled from ncolours products equals the one-JVP-per-column Jacobian (src/Ariadne.jl:140-162) exactly."""
+    import newtonkrylov_jl_b200 as nk
+
+    d = make()
+    p = P.oracle_problem(oracle, d, un=d["u0"] if d.get("scheme") else None)
+    n = d["u0"].size
+    colour, ncol, offsets = nk.probe_plan(d["kind"], d.get("bc", A.AK_BC_ZERO), d["u0"].shape)
+    Y = np.zeros((ncol, n))
+    for c in range(ncol):
+        e = (colour == c).astype(np.float64).reshape(d["u0"].shape)
+        Y[c] = oracle.jvp(p, d["u0"], e)[0].reshape(-1)
+    M = nk.assemble_probed(Y, colour, offsets, n)
+    assert np.array_equal(M.toarray(), oracle.dense_jacobian(p, d["u0"]))
+    assert ncol <= 25
