@@ -180,8 +180,8 @@ struct BlockComm {
     P2PHalo halo = {nullptr, nullptr, 0};
 };
 int launch_mgs_block(Ctx* ctx, int64_t n, double* w, const double* const* va, int nax, const double* tin,
-                     const double* const* ya, int ny, int want_sumsq, double* out, const int* stop,
-                     const BlockComm* pc);
+                     const double* rho_in, const double* const* ya, int ny, int want_sumsq, double* out,
+                     const int* stop, const BlockComm* pc);
 // x <- x + sum_i y[i] V[i]  (sequential axpy order), optionally u <- u - x fused (single pass)
 int launch_basis_combine(Ctx* ctx, int64_t n, double* x, const double* const* V_dev, const double* y_dev,
                          int k, int zero_x_first);
@@ -194,6 +194,10 @@ int launch_residual(Ctx* ctx, const ak_problem* p, double* u, double* res, doubl
 struct JvpFusion {
     const double* scale_src = nullptr;  // w_prev: v <- scale_src / denom, written to v
     const double* denom_dev = nullptr;  // device scalar
+    // un-normalised basis: scale_src stays the stored basis vector and out = J(scale_src) / denom (J is linear; the
+    // stencil kernels scale at the store).  `v` is then scratch (n doubles) for the problem kinds that go through a
+    // normalised copy (2x2 system, Midpoint, caller-supplied tangents, finite differences), unused otherwise.
+    bool raw = false;
     const double* dot_with = nullptr;   // V[0]
     double* dot_dev = nullptr;
     const int* stop_flag = nullptr;

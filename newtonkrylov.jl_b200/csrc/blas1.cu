@@ -165,7 +165,8 @@ constexpr int kRedSumsq = 5;
 
 template <int NAX, int NRED, bool P2P>
 __global__ void __launch_bounds__(kThreads, 2) k_mgs_block(double* __restrict__ w, const BlkPtrs bp,
-                                                           const double* __restrict__ tin, double* __restrict__ out,
+                                                           const double* __restrict__ tin,
+                                                           const double* __restrict__ rho_in, double* __restrict__ out,
                                                            double* __restrict__ partials, unsigned int* ticket,
                                                            int64_t n, const int* __restrict__ stop, const int vec,
                                                            const BlockP2P pp) {
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_mgs_block(double* __restrict__ 
     __shared__ double sh[32];
     __shared__ double shm[kBlkSums * kMaxPeers];
     if (stop != nullptr && *stop != 0) return;
-    double h[kBlkMax] = {0.0, 0.0, 0.0, 0.0};  // negated coefficients of the block being subtracted
+    double h[kBlkMax] = {0.0, 0.0, 0.0, 0.0};  // negated multipliers of the stored vectors of the block being subtracted
     if (NAX >= 1) {
         constexpr int NIN = sums_used(NAX);
         double t[kBlkSums];
@@ -188,7 +189,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_mgs_block(double* __restrict__ 
 #pragma unroll
             for (int c = 0; c < kBlkSums; ++c) t[c] = (c < NIN) ? tin[c] : 0.0;
         }
-        block_coefficients(t, NAX, h);
+        double hc[kBlkMax];
+        block_coefficients(t, rho_in, NAX, hc, h);
 #pragma unroll
         for (int b = 0; b < kBlkMax; ++b) h[b] = -h[b];
     }
@@ -274,8 +276,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_mgs_block(double* __restrict__ 
 }
 
 template <int NAX, int NRED>
-static int launch_mgs_block_t(Ctx* ctx, int64_t n, double* w, const BlkPtrs& bp, const double* tin, double* out,
-                              const int* stop, bool vec, bool p2p, const BlockP2P& pp, int cls) {
+static int launch_mgs_block_t(Ctx* ctx, int64_t n, double* w, const BlkPtrs& bp, const double* tin,
+                              const double* rho_in, double* out, const int* stop, bool vec, bool p2p,
+                              const BlockP2P& pp, int cls) {
     static int occ[2] = {0, 0};  // resident blocks per SM of this instantiation (queried once)
     if (occ[p2p] == 0) {
         int nb = 0;
@@ -289,20 +292,20 @@ static int launch_mgs_block_t(Ctx* ctx, int64_t n, double* w, const BlkPtrs& bp,
     const int blocks = (int)(need < 1 ? 1 : (need < cap ? need : cap));
     ProfScope prof(ctx, cls);
     if (p2p)
-        k_mgs_block<NAX, NRED, true><<<blocks, kThreads, 0, ctx->stream>>>(w, bp, tin, out, ctx->partials, ctx->ticket,
-                                                                           n, stop, vec ? 1 : 0, pp);
+        k_mgs_block<NAX, NRED, true><<<blocks, kThreads, 0, ctx->stream>>>(w, bp, tin, rho_in, out, ctx->partials,
+                                                                           ctx->ticket, n, stop, vec ? 1 : 0, pp);
     else
-        k_mgs_block<NAX, NRED, false><<<blocks, kThreads, 0, ctx->stream>>>(w, bp, tin, out, ctx->partials, ctx->ticket,
-                                                                            n, stop, vec ? 1 : 0, pp);
+        k_mgs_block<NAX, NRED, false><<<blocks, kThreads, 0, ctx->stream>>>(w, bp, tin, rho_in, out, ctx->partials,
+                                                                            ctx->ticket, n, stop, vec ? 1 : 0, pp);
     return AK_OK;
 }
 
-// va[0..nax): vectors to subtract, tin: raw sums of that block; ya[0..ny): vectors to project on;
-// want_sumsq: ||w_new||^2 instead.  out receives sums_used(ny) doubles, or 1.
+// va[0..nax): stored vectors to subtract, tin: raw sums of that block, rho_in (may be null): their scales (un-normalised
+// basis); ya[0..ny): vectors to project on; want_sumsq: ||w_new||^2 instead.  out receives sums_used(ny) doubles, or 1.
 // With `pc` (multi-GPU, peer memory enabled) the sums travel through the peers' mailboxes instead of NCCL.
 int launch_mgs_block(Ctx* ctx, int64_t n, double* w, const double* const* va, int nax, const double* tin,
-                     const double* const* ya, int ny, int want_sumsq, double* out, const int* stop,
-                     const BlockComm* pc) {
+                     const double* rho_in, const double* const* ya, int ny, int want_sumsq, double* out,
+                     const int* stop, const BlockComm* pc) {
     if (n <= 0) return AK_OK;
     if (nax < 0 || nax > kBlkMax || ny < 0 || ny > kBlkMax || (ny == 0 && !want_sumsq) || (ny > 0 && want_sumsq)) {
         set_error("launch_mgs_block: bad block shape (nax = %d, ny = %d, sumsq = %d)", nax, ny, want_sumsq);
@@ -328,7 +331,7 @@ int launch_mgs_block(Ctx* ctx, int64_t n, double* w, const double* const* va, in
     }
     int rc = AK_ERR_ARG;
 #define AK_BLK(A, R) \
-    if (nax == A && nred == R) rc = launch_mgs_block_t<A, R>(ctx, n, w, bp, tin, out, stop, vec, p2p, pp, cls);
+    if (nax == A && nred == R) rc = launch_mgs_block_t<A, R>(ctx, n, w, bp, tin, rho_in, out, stop, vec, p2p, pp, cls);
     AK_BLK(0, 1) AK_BLK(0, 2) AK_BLK(0, 3) AK_BLK(0, 4)
     AK_BLK(1, 1) AK_BLK(1, 2) AK_BLK(1, 3) AK_BLK(1, 4) AK_BLK(1, 5)
     AK_BLK(2, 1) AK_BLK(2, 2) AK_BLK(2, 3) AK_BLK(2, 4) AK_BLK(2, 5)

@@ -58,6 +58,7 @@ struct ak_krylov {
     // scalars (device)
     int64_t kcap = 0;  // columns of R that fit
     double *R = nullptr, *c = nullptr, *s = nullptr, *z = nullptr, *hcol = nullptr, *hist = nullptr;
+    double* rho = nullptr;  // un-normalised basis (blocked sweeps): stored V[i] = rho[i] * v_i
     int64_t hist_cap = 0;
     ak::KrylovCtl* ctl = nullptr;
     ak::KrylovStatus* status = nullptr;  // pinned
@@ -73,7 +74,7 @@ namespace ak {
 // ---------------------------------------------------------------------------------------
 // start of a solve / of a restart pass: beta = ||r0||, z[0] = beta, stopping tolerance
 __global__ void k_gmres_begin(KrylovCtl* ctl, const double* sumsq, double* z, double* hist, int first_pass,
-                              double atol, double rtol, KrylovStatus* st) {
+                              double atol, double rtol, KrylovStatus* st, double* rho) {
     if (threadIdx.x != 0) return;
     const double beta = sqrt(*sumsq);
     if (first_pass) {
@@ -86,6 +87,7 @@ __global__ void k_gmres_begin(KrylovCtl* ctl, const double* sumsq, double* z, do
         if (hist) hist[0] = beta;
     }
     z[0] = beta;
+    if (rho) rho[0] = ctl->rNorm;  // un-normalised basis: V[0] stays r0, v_0 = r0 / rNorm
     ctl->solved = (ctl->rNorm <= ctl->eps) || (beta == 0.0);
     ctl->stop = ctl->solved;
     ctl->inner_iter = 0;
@@ -103,7 +105,8 @@ __device__ __forceinline__ double sgn(double x) { return (double)((x > 0.0) - (x
 // Krylov.jl sym_givens (real), then the update of iteration k (1-based) — gmres! steps 6-8
 __global__ void k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, double* c, double* s, double* z,
                                double* hcol, int reorth, int blk, double* hist, int64_t hist_pos,
-                               int inner_limit, KrylovStatus* st, const P2PDev pd, unsigned long long seq_in) {
+                               int inner_limit, KrylovStatus* st, const P2PDev pd, unsigned long long seq_in,
+                               double* rho_vec) {
     if (threadIdx.x != 0) return;
     if (ctl->stop) return;
     const int nblk = blk > 0 ? (k + blk - 1) / blk : 0;  // blocks of the blocked Gram-Schmidt sweep
@@ -128,8 +131,8 @@ __global__ void k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, dou
     if (blk > 0) {  // raw sums of the blocked sweep (one record of kBlkSums per block), then ||q||^2
         for (int j = 0; j < nblk; ++j) {
             const int m = (k - j * blk) < blk ? (k - j * blk) : blk;
-            double hb[kBlkMax];
-            block_coefficients(hcol + kBlkSums * j, m, hb);
+            double hb[kBlkMax], cb[kBlkMax];
+            block_coefficients(hcol + kBlkSums * j, rho_vec ? rho_vec + j * blk : nullptr, m, hb, cb);
             for (int b = 0; b < m; ++b) R[nr + j * blk + b] = hb[b];
         }
         hh = hcol[kBlkSums * nblk];
@@ -139,6 +142,7 @@ __global__ void k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, dou
         hh = reorth ? h2[k] : hcol[k];
     }
     const double Hbis = sqrt(hh);
+    if (rho_vec) rho_vec[k] = Hbis;  // the finished w of this iteration IS the stored basis vector k
     for (int i = 0; i + 1 < k; ++i) {
         const double Rt = c[i] * R[nr + i] + s[i] * R[nr + i + 1];
         R[nr + i + 1] = s[i] * R[nr + i] - c[i] * R[nr + i + 1];
@@ -307,6 +311,7 @@ static int ws_grow_scalars(ak_krylov* ws, int64_t kcap_new) {
     AK_TRY(regrow(&ws->c, oldk, kcap_new));
     AK_TRY(regrow(&ws->s, oldk, kcap_new));
     AK_TRY(regrow(&ws->z, oldk ? oldk + 1 : 0, kcap_new + 1));
+    AK_TRY(regrow(&ws->rho, oldk ? oldk + 1 : 0, kcap_new + 1));
     AK_TRY(regrow(&ws->hcol, oldk ? hcol_len(oldk) : 0, hcol_len(kcap_new)));
     ws->kcap = kcap_new;
     return AK_OK;
@@ -330,14 +335,14 @@ static int ws_grow_hist(ak_krylov* ws, int64_t need) {
 }
 
 // make sure basis vectors V[0..count) exist
-static int ws_ensure_basis(ak_krylov* ws, int64_t count) {
+static int ws_ensure_basis(ak_krylov* ws, int64_t count, bool exact = false) {
     if ((int64_t)ws->V.size() >= count) return AK_OK;
     if (ws->max_basis > 0 && count > ws->max_basis) {
         set_error("krylov workspace: basis would grow past max_basis = %lld", (long long)ws->max_basis);
         return AK_ERR_NOMEM;
     }
     // grow in steps of `mem` vectors (Krylov.jl pushes one at a time; chunking amortises cudaMalloc)
-    int64_t target = (int64_t)ws->V.size() + ws->mem;
+    int64_t target = exact ? count : (int64_t)ws->V.size() + ws->mem;
     if (target < count) target = count;
     if (ws->max_basis > 0 && target > ws->max_basis) target = ws->max_basis;
     while ((int64_t)ws->V.size() < target) {
@@ -423,6 +428,10 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     if (lprec && !ws->qbuf) AK_TRY(ws_alloc_vec(ws, &ws->qbuf));
     const int blk = fuse == AK_FUSE_PAIR ? 2 : (fuse == AK_FUSE_BLOCK4 ? kBlkMax : 0);  // Gram-Schmidt steps per sweep
     const bool pair = blk > 0;
+    // Blocked sweeps keep the basis un-normalised: iteration k works in place on basis slot k, whose finished content
+    // IS the stored vector (scale rho[k] = Hbis); the JVP divides by rho[k-1] in registers.  No w buffers, no
+    // normalised copy: 24n instead of 32n bytes per JVP.
+    const bool raw = pair;
     // multi-GPU with peer memory: reductions and ghost rows of the blocked sweep go over NVLink stores
     const bool p2p = pair && c->p2p_on && c->nranks > 1;
     const bool is2d = (prob->kind == AK_BRATU2D || prob->kind == AK_HEAT2D);
@@ -443,13 +452,17 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
         if (!ws->dx) AK_TRY(ws_alloc_vec(ws, &ws->dx));
         xr = ws->dx;
     }
-    if ((fuse == AK_FUSE_FULL || pair) && !ws->w[1]) AK_TRY(ws_alloc_vec(ws, &ws->w[1]));
-    AK_TRY(ws_ensure_basis(ws, mem));
+    if (fuse == AK_FUSE_FULL && !ws->w[1]) AK_TRY(ws_alloc_vec(ws, &ws->w[1]));
+    AK_TRY(ws_ensure_basis(ws, raw && restart ? mem + 1 : mem, raw));
+    // problem kinds without a fused normalise + JVP kernel get the normalised seed in a scratch vector
+    const bool raw_needs_seed = raw && (prob->kind == AK_SIMPLE2 || prob->kind == AK_USER || prob->scheme == AK_MIDPOINT ||
+                                        prob->jvp_mode == AK_JVP_FD);
+    if (raw_needs_seed && !ws->pbuf) AK_TRY(ws_alloc_vec(ws, &ws->pbuf));
     AK_TRY(ws_grow_scalars(ws, mem));
     if (want_hist) AK_TRY(ws_grow_hist(ws, 257));
 
     int wi = 0;  // index of the buffer currently holding w / r0
-    double* w = ws->w[wi];
+    double* w = raw ? ws->V[0] : ws->w[wi];
     AK_TRY(launch_fill(c, n, x, 0.0));
     if (lprec) AK_TRY(apply_precond(ws, prob, u, o, true, b, w));  // r0 = M b
     else AK_TRY(launch_copy(c, n, w, b));
@@ -459,7 +472,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     int npass = 0;
     bool solved = false, tired = false, breakdown = false, inconsistent = false;
     double rNorm = 0.0, beta0 = 0.0;
-    std::vector<double> Rh, zh;
+    std::vector<double> Rh, zh, rhoh;
 
     while (true) {
         // ---- pass prologue -------------------------------------------------------------
@@ -475,12 +488,12 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
         }
         AK_TRY(launch_sumsq(c, n, w, ws->hcol));
         k_gmres_begin<<<1, 32, 0, sm>>>(ws->ctl, ws->hcol, ws->z, want_hist ? ws->hist : nullptr, npass == 0, o->atol,
-                                        o->rtol, &ws->status[kStatusRing]);
+                                        o->rtol, &ws->status[kStatusRing], raw ? ws->rho : nullptr);
         c->launches++;
         AK_CUDA(cudaGetLastError());
         AK_CUDA(cudaEventRecord(ws->ev[kStatusRing], sm));
-        // V[0] <- r0 / rNorm   (no-op when already converged / zero residual)
-        AK_TRY(launch_divcopy_dev(c, n, ws->V[0], w, &ws->ctl->rNorm, &ws->ctl->stop));
+        // V[0] <- r0 / rNorm   (no-op when already converged / zero residual; un-normalised basis: V[0] is r0)
+        if (!raw) AK_TRY(launch_divcopy_dev(c, n, ws->V[0], w, &ws->ctl->rNorm, &ws->ctl->stop));
         npass += 1;
 
         const int64_t inner_limit = restart ? (mem < inner_itmax ? mem : inner_itmax) : inner_itmax;
@@ -497,7 +510,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
             while (true) {
                 k += 1;
                 // storage for this iteration (basis vector k receives q/Hbis, 0-based)
-                if (!restart || k < mem) {
+                if (!restart || k < mem || raw) {
                     if (k + 1 > (int64_t)ws->V.size()) {
                         int rc = ws_ensure_basis(ws, k + 1);
                         if (rc != AK_OK) {
@@ -541,7 +554,21 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 JvpFusion jf;
                 jf.stop_flag = stop;
                 double* wout = w;
-                if (fuse == AK_FUSE_FULL || pair) {
+                double* seed = pv;
+                if (raw) {
+                    // w <- J (V[k-1] / rho[k-1]), straight into basis slot k
+                    jf.scale_src = ws->V[k - 1];
+                    jf.denom_dev = ws->rho + (k - 1);
+                    jf.raw = true;
+                    seed = raw_needs_seed ? ws->pbuf : nullptr;
+                    wout = ws->V[k];
+                    if (p2p_halo && k > 1) {  // ghost rows of V[k-1] were pushed by the neighbours' final pass of iteration k-1
+                        const int par = (int)((k - 1) & 1);
+                        jf.halo_given = true;
+                        jf.halo_lo = nb_down >= 0 ? c->p2p_halo_local(par, 0) : nullptr;
+                        jf.halo_hi = nb_up >= 0 ? c->p2p_halo_local(par, 1) : nullptr;
+                    }
+                } else if (fuse == AK_FUSE_FULL) {
                     if (scale_pending) {
                         jf.scale_src = w;
                         jf.denom_dev = &ws->ctl->Hbis;
@@ -554,16 +581,14 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                             jf.halo_hi = nb_up >= 0 ? c->p2p_halo_local(par, 1) : nullptr;
                         }
                     }
-                    if (!pair) {
-                        jf.dot_with = ws->V[0];
-                        jf.dot_dev = hcol;
-                    }
+                    jf.dot_with = ws->V[0];
+                    jf.dot_dev = hcol;
                 }
                 if (lprec) {  // w <- M (A N v_k)
-                    AK_TRY(launch_jvp(c, prob, u, pv, ws->qbuf, &jf));
+                    AK_TRY(launch_jvp(c, prob, u, seed, ws->qbuf, &jf));
                     AK_TRY(apply_precond(ws, prob, u, o, true, ws->qbuf, wout));
                 } else {
-                    AK_TRY(launch_jvp(c, prob, u, pv, wout, &jf));
+                    AK_TRY(launch_jvp(c, prob, u, seed, wout, &jf));
                 }
                 w = wout;
                 // modified Gram-Schmidt
@@ -575,7 +600,8 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                     BlockComm pc;
                     unsigned long long prev_seq = 0;
                     if (p2p) { pc.seq_out = ++c->p2p_seq; prev_seq = pc.seq_out; }
-                    AK_TRY(launch_mgs_block(c, n, w, nullptr, 0, nullptr, blk_ptr(0), blk_len(0), 0, hcol, stop,
+                    auto blk_rho = [&](int64_t j) -> const double* { return ws->rho + blk * j; };
+                    AK_TRY(launch_mgs_block(c, n, w, nullptr, 0, nullptr, nullptr, blk_ptr(0), blk_len(0), 0, hcol, stop,
                                             p2p ? &pc : nullptr));
                     for (int64_t j = 1; j < P; ++j) {
                         if (p2p) {
@@ -584,8 +610,9 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                             pc.tin_store = hcol + kBlkSums * (j - 1);
                             prev_seq = pc.seq_out;
                         }
-                        AK_TRY(launch_mgs_block(c, n, w, blk_ptr(j - 1), blk, hcol + kBlkSums * (j - 1), blk_ptr(j),
-                                                blk_len(j), 0, hcol + kBlkSums * j, stop, p2p ? &pc : nullptr));
+                        AK_TRY(launch_mgs_block(c, n, w, blk_ptr(j - 1), blk, hcol + kBlkSums * (j - 1), blk_rho(j - 1),
+                                                blk_ptr(j), blk_len(j), 0, hcol + kBlkSums * j, stop,
+                                                p2p ? &pc : nullptr));
                     }
                     if (p2p) {
                         pc.seq_in = prev_seq;
@@ -599,8 +626,9 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                             pc.halo.up_lo = nb_up >= 0 ? c->p2p_halo_of(nb_up, par, 0) : nullptr;
                         }
                     }
-                    AK_TRY(launch_mgs_block(c, n, w, blk_ptr(P - 1), blk_len(P - 1), hcol + kBlkSums * (P - 1), nullptr,
-                                            0, 1, hcol + kBlkSums * P, stop, p2p ? &pc : nullptr));
+                    AK_TRY(launch_mgs_block(c, n, w, blk_ptr(P - 1), blk_len(P - 1), hcol + kBlkSums * (P - 1),
+                                            blk_rho(P - 1), nullptr, 0, 1, hcol + kBlkSums * P, stop,
+                                            p2p ? &pc : nullptr));
                 } else if (fuse == AK_FUSE_NONE) {
                     for (int64_t i = 0; i < k; ++i) {
                         AK_TRY(launch_mgs_step(c, n, w, nullptr, nullptr, ws->V[i], 0, hcol + i, stop));   // h = <V_i, w>
@@ -636,13 +664,14 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 { ProfScope prof(c, PK_SCALAR);
                 k_gmres_givens<<<1, 32, 0, sm>>>(ws->ctl, (int)k, nr, ws->R, ws->c, ws->s, ws->z, hcol, reorth, blk,
                                                  want_hist ? ws->hist : nullptr, iter + k, (int)inner_limit,
-                                                 &ws->status[slot], p2p ? c->p2p_dev() : P2PDev{}, givens_seq); }
+                                                 &ws->status[slot], p2p ? c->p2p_dev() : P2PDev{}, givens_seq,
+                                                 raw ? ws->rho : nullptr); }
                 c->launches++;
                 AK_CUDA(cudaGetLastError());
                 AK_CUDA(cudaEventRecord(ws->ev[slot], sm));
                 // V[k] <- w / Hbis (skipped on the device when this iteration stopped the pass)
-                if (k < inner_limit) {
-                    if (fuse == AK_FUSE_FULL || pair) scale_pending = true;
+                if (k < inner_limit && !raw) {
+                    if (fuse == AK_FUSE_FULL) scale_pending = true;
                     else AK_TRY(launch_divcopy_dev(c, n, ws->V[k], w, &ws->ctl->Hbis, stop));
                 }
                 // look at the previous iteration's verdict while this one runs
@@ -669,6 +698,10 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
             zh.resize((size_t)K);
             AK_CUDA(cudaMemcpyAsync(Rh.data(), ws->R, sizeof(double) * (size_t)nR, cudaMemcpyDeviceToHost, sm));
             AK_CUDA(cudaMemcpyAsync(zh.data(), ws->z, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost, sm));
+            if (raw) {
+                rhoh.resize((size_t)K);
+                AK_CUDA(cudaMemcpyAsync(rhoh.data(), ws->rho, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost, sm));
+            }
             AK_CUDA(cudaStreamSynchronize(sm));
             const double btol = pow(2.220446049250313e-16, 0.75);
             double* y = zh.data();
@@ -681,6 +714,8 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 if (fabs(Rh[(size_t)pos]) <= btol) { y[i - 1] = 0.0; inconsistent = true; }
                 else y[i - 1] = y[i - 1] / Rh[(size_t)pos];
             }
+            if (raw)  // x = sum y_i v_i = sum (y_i / rho_i) V[i]
+                for (int64_t i = 0; i < K; ++i) y[i] = y[i] / rhoh[(size_t)i];
             AK_CUDA(cudaMemcpyAsync(ws->hcol, y, sizeof(double) * (size_t)K, cudaMemcpyHostToDevice, sm));
             // x_k = N V_k y_k (gmres) or Z_k y_k (fgmres)
             AK_TRY(ws_upload_basis_table(ws, K, flexible));
@@ -698,7 +733,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
         if (iter >= itmax) tired = true;
         if (solved || tired || breakdown) break;
         // FUSE_FULL leaves the last residual candidate in w[wi]; the restart recomputes w anyway
-        w = ws->w[wi];
+        w = raw ? ws->V[0] : ws->w[wi];
     }
 
     if (p2p && *c->p2p_err) {
@@ -891,7 +926,7 @@ AK_API int ak_krylov_destroy(ak_krylov* ws) {
     auto rel = [&](void* p) { if (p) cudaFreeAsync(p, sm); };
     for (double* p : ws->chunks) rel(p);
     rel((void*)ws->V_dev);
-    rel(ws->R); rel(ws->c); rel(ws->s); rel(ws->z); rel(ws->hcol); rel(ws->hist);
+    rel(ws->R); rel(ws->c); rel(ws->s); rel(ws->z); rel(ws->hcol); rel(ws->hist); rel(ws->rho);
     rel(ws->ctl);
     if (ws->status) cudaFreeHost(ws->status);
     for (int i = 0; i < kStatusSlots; ++i)

@@ -44,6 +44,7 @@ struct StencilArgs {
     double* aux_out;     // RES_BRATU: coef out (may be null)
     double* out;
     double* in_write;    // fused divcopy: scaled `in` is stored here (own rows) ; 1-D heat: BC write-back target
+    const double* out_scale;  // tangent kernels, un-normalised Krylov basis: out = J(in) / *out_scale (device scalar)
     const double* denom; // fused divcopy: device scalar
     const double* dot_with;
     double* red_out;
@@ -143,6 +144,9 @@ __global__ void __launch_bounds__(kTX, OP == OP_JVP_BRATU_FD ? 4 : 8) k_stencil2
     const int64_t y1 = (y0 + p.ry < ny) ? y0 + p.ry : ny;
     const Divisor denom = make_divisor(SCALE ? *p.denom : 1.0);
     const Divisor dx2 = make_divisor(p.dx2), dy2 = make_divisor(p.dy2);
+    // un-normalised Krylov basis: J is linear, so J(v / rho) is formed as J(v) * (1 / rho) at the store
+    const bool oscale_on = (OP == OP_JVP_BRATU || OP == OP_JVP_HEAT || OP == OP_JVP_BRATU_FD) && p.out_scale != nullptr;
+    const double oscale = oscale_on ? __ddiv_rn(1.0, *p.out_scale) : 1.0;
 
     auto row_ptr = [&](int64_t y) -> const double* {
         if (y < 0) return p.lo;
@@ -279,6 +283,10 @@ __global__ void __launch_bounds__(kTX, OP == OP_JVP_BRATU_FD ? 4 : 8) k_stencil2
                     o[i] = __dsub_rn(__dmul_rn(p.c1, dv), c);
                 }
             }
+            if (oscale_on) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) o[i] = __dmul_rn(o[i], oscale);
+            }
             stv<VEC>(p.out + off, o);
             if (OP == OP_RES_BRATU && p.aux_out != nullptr) stv<VEC>(p.aux_out + off, cf);
             if (SCALE) stv<VEC>(p.in_write + off, cur);
@@ -333,6 +341,8 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
     const Divisor denom = make_divisor(SCALE ? *p.denom : 1.0);
     const Divisor dx2 = make_divisor(p.dx2);
     constexpr bool HEAT = (OP == OP_RES_HEAT || OP == OP_JVP_HEAT || OP == OP_RHS_HEAT);
+    const bool oscale_on = (OP == OP_JVP_BRATU || OP == OP_JVP_HEAT) && p.out_scale != nullptr;
+    const double oscale = oscale_on ? __ddiv_rn(1.0, *p.out_scale) : 1.0;
 
     auto value = [&](int64_t i) -> double {  // scalar access incl. boundary semantics
         double v;
@@ -395,6 +405,10 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
                 else o[i] = __dsub_rn(__dmul_rn(p.c1, du), c);
             }
         }
+        if (oscale_on) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] = __dmul_rn(o[i], oscale);
+        }
         stv<VEC>(p.out + x0, o);
         if (OP == OP_RES_BRATU && p.aux_out != nullptr) stv<VEC>(p.aux_out + x0, cf);
         if (SCALE) {
@@ -438,6 +452,7 @@ struct DgArgs {
     double* out;
     double* in_write;
     const double* denom;
+    const double* out_scale;  // tangent with an un-normalised Krylov basis: out = J(in) / *out_scale
     const double* dot_with;
     double* red_out;
     double* partials;
@@ -522,6 +537,11 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dmul_rn(p.c1, du[i]), raw[i]);
+            if (p.out_scale != nullptr) {
+                const double oscale = __ddiv_rn(1.0, *p.out_scale);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = __dmul_rn(o[i], oscale);
+            }
         }
         stv<4>(p.out + 4 * e, o);
         if (SCALE) stv<4>(p.in_write + 4 * e, raw);
@@ -996,8 +1016,12 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
         if (f->dot_with) AK_TRY(launch_mgs_step(ctx, n, out, nullptr, nullptr, f->dot_with, 0, f->dot_dev, f->stop_flag));
         return AK_OK;
     }
-    const bool scale = f->scale_src != nullptr;
+    // un-normalised Krylov basis (f->raw): the stored vector scale_src is the seed, J(scale_src) / denom the result
+    const bool raw = f->raw && f->scale_src != nullptr;
+    const bool native = !(p->kind == AK_SIMPLE2);
+    const bool scale = f->scale_src != nullptr && !(raw && native);
     const int red = f->dot_with ? RED_DOT : RED_NONE;
+    if (raw && native) v = const_cast<double*>(f->scale_src);
     if (p->kind == AK_SIMPLE2) {
         if (scale) AK_TRY(launch_divcopy_dev(ctx, 2, v, f->scale_src, f->denom_dev, f->stop_flag));
         k_simple2<<<1, 32, 0, ctx->stream>>>(u, v, out, f->dot_dev, 1, f->dot_with, f->stop_flag);
@@ -1012,7 +1036,7 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
         d.dt = p->dt; d.c0 = 1.0; d.c1 = (p->scheme == AK_TRAPEZOID) ? p->dt / 2.0 : p->dt;
         d.in = scale ? f->scale_src : v;
         AK_TRY(ghost_1d(ctx, d.in, p->nx, 4, 1, true, &d.lo, &d.hi));
-        d.in_write = v; d.denom = f->denom_dev;
+        d.in_write = v; d.denom = f->denom_dev; d.out_scale = raw ? f->denom_dev : nullptr;
         d.out = out; d.dot_with = f->dot_with; d.red_out = f->dot_dev;
         d.partials = ctx->partials; d.ticket = ctx->ticket; d.stop = f->stop_flag;
         AK_REQUIRE(al(d.in, 32) && al(v, 32) && al(out, 32) && al(f->dot_with, 32), "DG vectors must be 32-byte aligned");
@@ -1025,6 +1049,7 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     a.in = scale ? f->scale_src : v;
     a.in_write = scale ? v : nullptr;
     a.denom = f->denom_dev;
+    a.out_scale = raw ? f->denom_dev : nullptr;
     a.out = out;
     a.dot_with = f->dot_with;
     a.red_out = f->dot_dev;

@@ -344,3 +344,88 @@ def test_batched_jvp(nk, ctx):
         o = u.zero()
         nk.mul_(o, J, nk.DeviceVector.from_numpy(V0[c].reshape(12, 20), ctx))
         assert np.array_equal(Out.numpy()[c], o.numpy().reshape(-1))
+
+
+# ---- guard bands: compute-sanitizer is not available on the GPU pool, so out-of-bounds accesses are caught here -----
+GUARD = 64
+
+
+def _guarded(nk, ctx, arrays):
+    """Place the arrays back to back in ONE device buffer, separated and surrounded by NaN guard bands; vectors start
+    32-byte aligned.  An out-of-bounds read poisons the result with NaN, an out-of-bounds write clears a guard."""
+    sizes = [int(np.asarray(a).size) for a in arrays]
+    padded = [(s + 3) // 4 * 4 for s in sizes]
+    total = GUARD + sum(p + GUARD for p in padded)
+    host = np.full(total, np.nan)
+    offs, o = [], GUARD
+    for a, s, p in zip(arrays, sizes, padded):
+        host[o:o + s] = np.ravel(a)
+        offs.append(o)
+        o += p + GUARD
+    base = nk.DeviceVector.from_numpy(host, ctx)
+    vecs = [nk.DeviceVector(ctx, np.asarray(a).shape, ptr=base.ptr + 8 * off, owner=base) for a, off in zip(arrays, offs)]
+    mask = np.ones(total, dtype=bool)
+    for off, s in zip(offs, sizes):
+        mask[off:off + s] = False
+    return base, vecs, mask
+
+
+GUARD_CASES = [("bratu1d", lambda: P.bratu1d(1001)), ("bratu2d", lambda: P.bratu2d(36, 27)), ("bratu2d_odd", lambda: P.bratu2d(33, 5)),
+               ("heat1d", lambda: P.heat1d(99)), ("heat1d_periodic", lambda: P.heat1d(100, bc=A.AK_BC_PERIODIC)),
+               ("heat2d", lambda: P.heat2d(20, dt_scale=8.0)), ("heat2d_periodic", lambda: P.heat2d(12, dt_scale=8.0, bc=A.AK_BC_PERIODIC)),
+               ("dg", lambda: P.heat1d_dg(9))]
+
+
+@pytest.mark.parametrize("name,make", GUARD_CASES, ids=[c[0] for c in GUARD_CASES])
+def test_stencil_kernels_stay_inside_their_vectors(nk, ctx, oracle, name, make):
+    """Residual, JVP (plain and with the fused first dot of the Arnoldi step) and the vector hooks on vectors
+    surrounded by NaN guard bands: results equal the oracle's (no NaN leaked in) and every guard is still NaN."""
+    d = make()
+    v0 = RNG.standard_normal(d["u0"].shape)
+    zeros = np.zeros_like(d["u0"])
+    base, (u, un, v, res, out), mask = _guarded(nk, ctx, [d["u0"], d["u0"], v0, zeros, zeros])
+    k = d["kind"]
+    bc = nk.bc_zero_ if d.get("bc", A.AK_BC_ZERO) == A.AK_BC_ZERO else nk.bc_periodic_
+    if k == A.AK_BRATU1D:
+        F_, p = nk.bratu_, (d["dx"], d["lam"])
+    elif k == A.AK_BRATU2D:
+        F_, p = nk.bratu2d_, (d["dx"], d["dy"], d["lam"])
+    elif k == A.AK_HEAT1D:
+        F_, p = nk.ImplicitResidual(nk.G_Euler_, nk.heat_1D_), (un, d["dt"], None, (d["a"], d["dx"], bc), 0.0)
+    elif k == A.AK_HEAT2D:
+        F_, p = nk.ImplicitResidual(nk.G_Euler_, nk.diffusion_), (un, d["dt"], None, (d["a"], d["dx"], d["dy"], bc), 0.0)
+    else:
+        F_, p = nk.ImplicitResidual(nk.G_Euler_, nk.heat_1D_DG_), (un, d["dt"], None, (d["dx"],), 0.0)
+    po = P.oracle_problem(oracle, d, un=d["u0"] if d.get("scheme") else None)
+    F_(res, u, p)
+    rr, _ = oracle.residual(po, d["u0"])
+    assert np.allclose(res.numpy(), rr, rtol=1e-12, atol=1e-12 * np.max(np.abs(rr)))
+    nk.mul_(out, nk.JacobianOperator(F_, res, u, p), v)
+    jr, _ = oracle.jvp(po, d["u0"], v0)
+    assert np.allclose(out.numpy(), jr, rtol=1e-12, atol=1e-12 * np.max(np.abs(jr)))
+    n = u.n
+    assert np.isfinite(nk.kdot(n, out, res)) and np.isfinite(nk.knorm(n, out))
+    nk.kaxpy_(n, 0.5, out, res)
+    nk.kaxpby_(n, 2.0, out, -1.0, res)
+    nk.kscal_(n, 0.25, res)
+    nk.kcopy_(n, out, res)
+    nk.kref_(n, out, res, 0.6, 0.8)
+    assert np.all(np.isfinite(res.numpy())) and np.all(np.isfinite(out.numpy()))
+    h = base.numpy()
+    assert np.all(np.isnan(h[mask])), "a kernel wrote outside its vector"
+
+
+@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4"])
+def test_gmres_reads_only_its_operands(nk, ctx, oracle, fuse):
+    """A whole GMRES solve (7 iterations: ragged blocks of the blocked sweep) with u and b inside NaN guard bands."""
+    d = P.bratu2d(33, 19)
+    b0 = RNG.standard_normal(d["u0"].shape)
+    base, (u, b, res), mask = _guarded(nk, ctx, [d["u0"], b0, np.zeros_like(b0)])
+    J = nk.JacobianOperator(nk.bratu2d_, res, u, (d["dx"], d["dy"], d["lam"]))
+    ws = nk.krylov_workspace("gmres", nk.KrylovConstructor(res), memory=5)
+    nk.krylov_solve_(ws, J, b, itmax=7, restart=True, history=True, fuse=fuse)
+    po = P.oracle_problem(oracle, d)
+    xr, sr, hr = oracle.krylov_solve(po, d["u0"], b0, memory=5, itmax=7, restart=True, hist_cap=16)
+    assert ws.stats.niter == sr["niter"] == 7
+    assert np.linalg.norm(ws.x.numpy() - xr) <= 1e-9 * np.linalg.norm(xr)
+    assert np.all(np.isnan(base.numpy()[mask]))
