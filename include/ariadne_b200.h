@@ -140,8 +140,9 @@ int ak_timer_stop(ak_ctx* ctx, double* ms_out);
  * context's stream; ak_profile_read returns the number of launches of one kernel class and the
  * sum of their device times.  Classes: 0 axpy+dot (fused MGS step, 32n bytes), 1 axpy+norm (24n),
  * 2 axpy (24n), 3 dot (16n), 4 sum of squares (8n), 5 JVP, 6 residual, 7 element-wise,
- * 8 basis combine, 9 one-thread scalar kernels, 10 pair-wise MGS pass (48n), 11 first/odd
- * passes of the pair-wise sweep.  Enabling resets the counters.                          */
+ * 8 basis combine, 9 one-thread scalar kernels, 10 full pass of the blocked Gram-Schmidt sweep (48n for
+ * blocks of 2, 80n for blocks of 4), 11 first / ragged passes of the blocked sweep.  Enabling resets the
+ * counters.                                                                                           */
 int ak_profile_enable(ak_ctx* ctx, int on);
 int ak_profile_read(ak_ctx* ctx, int kernel_class, int64_t* count_out, double* ms_total_out);
 
@@ -244,6 +245,10 @@ enum {
                           instead of 32n); falls back to FULL with reorthogonalization    */
     AK_FUSE_BLOCK4 = 4 /* same with four steps per sweep: 4 projections + 6 Gram entries per
                           pass, h_b = <y_b,w> - sum_{a<b} h_a <y_b,y_a> (20n bytes per step) */
+    /* PAIR and BLOCK4 keep the Krylov basis UN-NORMALISED: iteration k works in place on basis slot k, whose
+     * finished content is the stored vector rho_k v_k (rho_k = Hbis); gmres!'s `V[k+1] = w / Hbis` is never
+     * materialised, the scales enter the Gram-Schmidt coefficients and the JVP divides its result by rho_k
+     * (J is linear).  Same algebra, rounding differs in the last bits.                                     */
 };
 
 typedef struct ak_krylov_opts {

@@ -119,3 +119,25 @@ def test_c5_dg_2pow22_elements(nk, ctx):
     nk.kaxpy_(4 * ne, 1.0, v, out)
     s = nk.kdot(4 * ne, mw, out)
     assert abs(s) <= 1e-9 * nk.knorm(4 * ne, out) * np.sqrt(4 * ne)
+
+
+@pytest.mark.parametrize("lam", [3.5, 3.51382], ids=["baseline_lambda", "example_lambda"])
+def test_c1_bratu1d_10000_newton_cg(nk, ctx, oracle, lam):
+    """BASELINE config 1 at full size, through the solver the reference's own script uses at this size
+    (examples/bratu.jl:40-46,59-63: N = 10_000, `algo = :cg`; plain GMRES "doesn't converge", :110-118):
+    ~20-60 thousand CG iterations, compared with the oracle to the oracle's own 1-ulp reproducibility."""
+    from test_gpu_solvers import assert_newton_parity, oracle_sensitivity
+
+    d = P.bratu1d(10000, lam=lam)
+    po = P.oracle_problem(oracle, d)
+    o = A.default_newton_opts(algo=A.AK_ALGO_CG)
+    sens = oracle_sensitivity(oracle, po, d["u0"], o, ntrial=2)
+    F_, u, p, _ = P.device_setup(nk, ctx, d)
+    hist = []
+    _, r = nk.newton_krylov_native_(F_, u, p, None, algo="cg", history=hist)
+    assert r.solved
+    assert_newton_parity(u.numpy(), r, hist, sens)
+    if lam == 3.51382:  # analytic solution of the continuous problem, examples/bratu.jl:33-37
+        theta = 4.79173
+        ref = -2.0 * np.log(np.cosh(theta * (d["x"] - 0.5) / 2.0) / np.cosh(theta / 4.0))
+        assert np.max(np.abs(u.numpy() - ref)) < 1e-4
