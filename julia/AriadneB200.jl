@@ -84,7 +84,7 @@ precond_fields(P::GmresPreconditioner) = (AK_PRECOND_INNER_GMRES, Int32(P.itmax)
 precond_fields(::TridiagonalLU) = (AK_PRECOND_TRIDIAG_LU, Int32(0), C_NULL, C_NULL)
 precond_fields(::JacobiPreconditioner) = (AK_PRECOND_JACOBI, Int32(0), C_NULL, C_NULL)
 function precond_trampoline(user::Ptr{Cvoid}, stream::UInt64, x::Ptr{Float64}, y::Ptr{Float64})::Cint
-    P, n = unsafe_pointer_to_objref(user)::Tuple
+    P, n = (unsafe_pointer_to_objref(user)::Base.RefValue{Any})[]
     try
         P.apply!(y, x, n, stream)
         return 0
@@ -269,18 +269,22 @@ solution(ws::Workspace) = ccall((:ak_krylov_x, lib), Ptr{Float64}, (Ptr{Cvoid},)
 function krylov_solve!(ws::Workspace, J::JacobianOperator, b::B200Vector; atol = √eps(Float64), rtol = √eps(Float64),
                        itmax = 0, restart = false, reorthogonalization = false, history = false, fuse = 4,
                        M = nothing, N = nothing, ldiv = false)
-    fields(P) = P isa UserPreconditioner ?
-        (AK_PRECOND_USER, Int32(0), @cfunction(precond_trampoline, Cint, (Ptr{Cvoid}, UInt64, Ptr{Float64}, Ptr{Float64})),
-         pointer_from_objref(Ref((P, length(b))))) : precond_fields(P)
     (N isa TridiagonalLU || M isa TridiagonalLU) && !ldiv && error("ilu(J) is applied with ldiv = true (examples/bratu.jl:126)")
-    pn, pit, nfn, nus = fields(N)
-    pm, pmit, mfn, mus = fields(M)
+    # caller-supplied preconditioners travel as (object, n) behind a rooted Ref for the duration of the solve
+    nref = N isa UserPreconditioner ? Ref{Any}((N, length(b))) : nothing
+    mref = M isa UserPreconditioner ? Ref{Any}((M, length(b))) : nothing
+    tramp = @cfunction(precond_trampoline, Cint, (Ptr{Cvoid}, UInt64, Ptr{Float64}, Ptr{Float64}))
+    fields(P, r) = r === nothing ? precond_fields(P) : (AK_PRECOND_USER, Int32(0), tramp, pointer_from_objref(r))
+    pn, pit, nfn, nus = fields(N, nref)
+    pm, pmit, mfn, mus = fields(M, mref)
     o = Ref(AkKrylovOpts(atol, rtol, itmax, restart, reorthogonalization, history, fuse, pn, pit, pm, pmit, nfn, nus, mfn, mus))
     st = Ref(AkKrylovStats(0, 0, 0, 0, 0, 0.0, 0.0))
     prob = Ref(problem(J.f, J.u, J.p; coef = J.coef))
-    check(ccall((:ak_krylov_solve, lib), Cint,
-                (Ptr{Cvoid}, Ptr{AkProblem}, Ptr{Float64}, Ptr{Float64}, Ptr{AkKrylovOpts}, Ptr{AkKrylovStats}, Ptr{Float64}, Int64),
-                ws.h, prob, J.u.ptr, b.ptr, o, st, C_NULL, 0))
+    GC.@preserve nref mref J begin
+        check(ccall((:ak_krylov_solve, lib), Cint,
+                    (Ptr{Cvoid}, Ptr{AkProblem}, Ptr{Float64}, Ptr{Float64}, Ptr{AkKrylovOpts}, Ptr{AkKrylovStats}, Ptr{Float64}, Int64),
+                    ws.h, prob, J.u.ptr, b.ptr, o, st, C_NULL, 0))
+    end
     ws.niter, ws.solved = st[].niter, st[].solved != 0
     return ws
 end
