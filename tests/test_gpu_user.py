@@ -157,7 +157,7 @@ def test_bvp_first_newton_step(nk, ctx, oracle):
     Only the first Newton step is compared.  This operator is so far from normal that GMRES itself is not
     reproducible beyond it: two IEEE-correct implementations of Fbvp!'s tangent (NumPy / torch, equal to 1e-14)
     give GMRES histories that differ by 2.5e-4 after 60 iterations and inner-GMRES preconditioner outputs that
-    differ by 8e-7 (measured, tools/dbg_user.py); the full solve takes 34 Newton steps / 3095 FGMRES iterations at
+    differ by 8e-7 (measured, tests/debug/dbg_user.py); the full solve takes 34 Newton steps / 3095 FGMRES iterations at
     n = 101 in the oracle and 23 / 2012 after a 1-ulp change of U0."""
     n, h, tv, tvdag, U0 = bvp_setup(101)
     Fn, Jn = bvp_np(n, h, tv, tvdag)
