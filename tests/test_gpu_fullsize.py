@@ -126,17 +126,23 @@ def test_c1_bratu1d_10000_newton_cg(nk, ctx, oracle, lam):
     """BASELINE config 1 at full size, through the solver the reference's own script uses at this size
     (examples/bratu.jl:40-46,59-63: N = 10_000, `algo = :cg`; plain GMRES "doesn't converge", :110-118):
     ~20-60 thousand CG iterations, compared with the oracle to the oracle's own 1-ulp reproducibility."""
-    from test_gpu_solvers import assert_newton_parity, oracle_sensitivity
+    from test_gpu_solvers import oracle_sensitivity
 
     d = P.bratu1d(10000, lam=lam)
     po = P.oracle_problem(oracle, d)
     o = A.default_newton_opts(algo=A.AK_ALGO_CG)
-    sens = oracle_sensitivity(oracle, po, d["u0"], o, ntrial=2)
+    ur, sr, hr, dev, robust, du, same_len = oracle_sensitivity(oracle, po, d["u0"], o, ntrial=2)
     F_, u, p, _ = P.device_setup(nk, ctx, d)
     hist = []
     _, r = nk.newton_krylov_native_(F_, u, p, None, algo="cg", history=hist)
-    assert r.solved
-    assert_newton_parity(u.numpy(), r, hist, sens)
+    assert r.solved and sr["solved"] and r.stats.outer_iterations == sr["outer_iterations"]
+    for k, (a, b) in enumerate(zip(hist, hr)):
+        if robust[k]:  # the oracle's own CG count does not move under a 1-ulp change of u0
+            assert a["inner"] == b["inner"], f"step {k}"
+        else:          # near the fold (lambda_c = 3.5138307) late CG counts are rounding-driven: same magnitude only
+            assert abs(a["inner"] - b["inner"]) <= 0.2 * b["inner"], f"step {k}"
+        assert abs(a["n_res"] - b["n_res"]) <= max(1e-10, 50 * dev[k]) * b["n_res"] + 1e-13 * hr[0]["n_res"], f"step {k}"
+    assert np.linalg.norm(u.numpy() - ur) <= max(1e-8, 50 * du) * np.linalg.norm(ur)
     if lam == 3.51382:  # analytic solution of the continuous problem, examples/bratu.jl:33-37
         theta = 4.79173
         ref = -2.0 * np.log(np.cosh(theta * (d["x"] - 0.5) / 2.0) / np.cosh(theta / 4.0))
