@@ -125,6 +125,18 @@ def run_cases(ctx, rank, world, rng, tag):
         assert rel(out.numpy(), refj[sl]) < 1e-14, name
         assert abs(nk.kdot(u.n, u, v) - float(np.vdot(d["u0"], v0))) <= 1e-12 * np.linalg.norm(d["u0"]) * np.linalg.norm(v0)
         assert abs(nk.knorm(v.n, v) - np.linalg.norm(v0)) <= 1e-13 * np.linalg.norm(v0)
+        # Jacobi as right and as left preconditioner (hooks N / M): local kernel, global reductions
+        b0 = rng.standard_normal(d["u0"].shape)
+        for side, kw, okw in (("N", "N", dict(precond_n=A.AK_PRECOND_JACOBI)), ("M", "M", dict(precond_m=A.AK_PRECOND_JACOBI))):
+            xr, sr, hr = O.krylov_solve(po, d["u0"], b0, rtol=1e-8, itmax=60, hist_cap=100, **okw)
+            uu = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
+            J = nk.JacobianOperator(F_, res, uu, p)
+            ws = nk.krylov_workspace("gmres", nk.KrylovConstructor(res))
+            nk.krylov_solve_(ws, J, nk.DeviceVector.from_numpy(b0[sl], ctx), rtol=1e-8, itmax=60, history=True,
+                             **{kw: nk.JacobiPreconditioner(J)})
+            assert (ws.stats.niter, ws.stats.solved) == (sr["niter"], sr["solved"]), (name, side, ws.stats.niter, sr)
+            assert np.max(np.abs(np.array(ws.stats.residuals) - hr)) <= 1e-9 * hr[0], (name, side)
+            assert rel(ws.x.numpy(), xr[sl]) < 1e-7, (name, side)
         # solver level
         if d["kind"] == A.AK_BRATU2D:
             for fuse in ("none", "mgs", "full", "pair", "block4"):
