@@ -75,7 +75,7 @@ enum {
     AK_JVP_ANALYTIC = 0, /* exact tangent-linear stencil == what Enzyme forward mode
                             yields at src/Ariadne.jl:48-57 (parity path)          */
     AK_JVP_FD_FUSED = 1, /* (F(u+eps v)-F(u))/eps evaluated point-wise in one pass,
-                            u+eps v never materialised (bandwidth study only)     */
+                            u+eps v never materialised; the Bratu problems (1-D, 2-D) */
     AK_JVP_FD = 2        /* generic two-evaluation finite difference (F(u+eps v)-F(u))/eps through the
                             residual itself; eps = fd_eps, or sqrt(eps_mach)(1+||u||)/||v|| when 0.
                             Default of AK_USER problems without a tangent callback               */

@@ -341,8 +341,15 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
     const Divisor denom = make_divisor(SCALE ? *p.denom : 1.0);
     const Divisor dx2 = make_divisor(p.dx2);
     constexpr bool HEAT = (OP == OP_RES_HEAT || OP == OP_JVP_HEAT || OP == OP_RHS_HEAT);
-    const bool oscale_on = (OP == OP_JVP_BRATU || OP == OP_JVP_HEAT) && p.out_scale != nullptr;
+    constexpr bool FD = (OP == OP_JVP_BRATU_FD);
+    const bool oscale_on = (OP == OP_JVP_BRATU || OP == OP_JVP_HEAT || FD) && p.out_scale != nullptr;
     const double oscale = oscale_on ? __ddiv_rn(1.0, *p.out_scale) : 1.0;
+    // fused finite-difference JVP: second window over u (p.aux, ghosts p.aux_lo / p.aux_hi); u + eps v is never stored
+    auto uvalue = [&](int64_t i) -> double {
+        if (i < 0) return p.aux_lo ? p.aux_lo[0] : 0.0;
+        if (i >= n) return p.aux_hi ? p.aux_hi[0] : 0.0;
+        return p.aux[i];
+    };
 
     auto value = [&](int64_t i) -> double {  // scalar access incl. boundary semantics
         double v;
@@ -377,10 +384,23 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
     }
     double left = __shfl_up_sync(0xffffffffu, cur[VEC - 1], 1);
     double right = __shfl_down_sync(0xffffffffu, cur[0], 1);
+    double ucur[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) ucur[i] = 0.0;
+    if (FD && active) ldv<VEC>(p.aux + x0, ucur);
+    double uleft = 0.0, uright = 0.0;
+    if (FD) {
+        uleft = __shfl_up_sync(0xffffffffu, ucur[VEC - 1], 1);
+        uright = __shfl_down_sync(0xffffffffu, ucur[0], 1);
+    }
     double acc = 0.0;
     if (active) {
         if (lane == 0) left = value(x0 - 1);
         if (lane == 31 || x0 + VEC >= n) right = value(x0 + VEC);
+        if (FD) {
+            if (lane == 0) uleft = uvalue(x0 - 1);
+            if (lane == 31 || x0 + VEC >= n) uright = uvalue(x0 + VEC);
+        }
         double aux[VEC], o[VEC], cf[VEC];
         if (OP == OP_JVP_BRATU || OP == OP_RES_HEAT) ldv_s<VEC>(p.aux + x0, aux);
 #pragma unroll
@@ -394,6 +414,16 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
             } else if (OP == OP_JVP_BRATU) {
                 const double k = p.coef_from_u ? __dmul_rn(p.lambda, exp(aux[i])) : aux[i];
                 o[i] = __dadd_rn(second_diff(e, c, w, dx2), __dmul_rn(k, c));
+            } else if (FD) {
+                // J v ~ (F(u + eps v) - F(u)) / eps, both residuals of bratu! (bratu.jl:14-24) evaluated at this point
+                const double eps = p.fd_eps;
+                const double uc = ucur[i];
+                const double uw = (i == 0) ? uleft : ucur[i > 0 ? i - 1 : 0];
+                const double ue = (i == VEC - 1) ? uright : ucur[(i + 1) % VEC];
+                const double f0 = __dadd_rn(second_diff(ue, uc, uw, dx2), __dmul_rn(p.lambda, exp(uc)));
+                const double pc = fma(eps, c, uc), pw = fma(eps, w, uw), pe = fma(eps, e, ue);
+                const double f1 = __dadd_rn(second_diff(pe, pc, pw, dx2), __dmul_rn(p.lambda, exp(pc)));
+                o[i] = __ddiv_rn(__dsub_rn(f1, f0), eps);
             } else {
                 // heat_1D.jl:22: du[i] = a * (u[i+1] - 2u[i] + u[i-1]) / dx^2 ; du[1] = du[end] = 0
                 const int64_t gi = x0 + i;
@@ -739,8 +769,8 @@ static int check_problem(const ak_problem* p) {
         AK_REQUIRE(p->scheme == AK_STEADY, "Bratu problems are steady (scheme must be AK_STEADY)");
     }
     if (p->jvp_mode != AK_JVP_ANALYTIC && p->jvp_mode != AK_JVP_FD) {
-        if (!(p->jvp_mode == AK_JVP_FD_FUSED && p->kind == AK_BRATU2D)) {
-            set_error("jvp_mode %d: AK_JVP_FD_FUSED is only implemented for AK_BRATU2D", p->jvp_mode);
+        if (!(p->jvp_mode == AK_JVP_FD_FUSED && (p->kind == AK_BRATU2D || p->kind == AK_BRATU1D))) {
+            set_error("jvp_mode %d: AK_JVP_FD_FUSED is implemented for the Bratu problems (heat/DG are linear: use AK_JVP_FD)", p->jvp_mode);
             return AK_ERR_UNSUPPORTED;
         }
     }
@@ -1057,6 +1087,15 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     int rc = AK_OK;
     switch (p->kind) {
         case AK_BRATU1D:
+            if (p->jvp_mode == AK_JVP_FD_FUSED) {
+                // north_star (2) in 1-D: one pass reads u and v and writes J v ~ (F(u + eps v) - F(u)) / eps
+                if (ctx->nranks > 1) { set_error("AK_JVP_FD_FUSED is single-GPU in this version"); return AK_ERR_UNSUPPORTED; }
+                AK_REQUIRE(u != nullptr, "AK_JVP_FD_FUSED needs u");
+                a.aux = u;
+                a.fd_eps = p->fd_eps > 0.0 ? p->fd_eps : 1.4901161193847656e-08;
+                rc = launch1d<OP_JVP_BRATU_FD>(ctx, a, scale, red);
+                break;
+            }
             AK_TRY(ghost_1d(ctx, a.in, p->nx, 1, 1, false, &a.lo, &a.hi));
             a.aux = p->coef ? p->coef : u;
             a.coef_from_u = p->coef ? 0 : 1;

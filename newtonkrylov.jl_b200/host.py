@@ -538,7 +538,7 @@ class JacobianOperator:
     def problem(self):
         prob = self.f.problem(self.u, self.p, coef=self.coef)
         if self.jvp_mode == "fd":      # one fused pass for 2-D Bratu, two residual evaluations otherwise
-            prob.jvp_mode = A.AK_JVP_FD_FUSED if prob.kind == A.AK_BRATU2D else A.AK_JVP_FD
+            prob.jvp_mode = A.AK_JVP_FD_FUSED if prob.kind in (A.AK_BRATU1D, A.AK_BRATU2D) else A.AK_JVP_FD
             prob.fd_eps = self.fd_eps
         elif self.jvp_mode == "fd2":   # generic (F(u + eps v) - F(u)) / eps through the residual itself
             prob.jvp_mode, prob.fd_eps = A.AK_JVP_FD, self.fd_eps
@@ -933,7 +933,7 @@ def newton_krylov_(F_, u, p=None, res=None, *, tol_rel=1.0e-6, tol_abs=1.0e-12, 
     # (finite-difference JVPs: F(u) is cached instead)
     coef = u.similar() if _wants_coef(F_, jvp_mode) else None
     prob = F_.problem(u, p, coef=coef)
-    if jvp_mode == "fd2" or (jvp_mode == "fd" and prob.kind != A.AK_BRATU2D):
+    if jvp_mode == "fd2" or (jvp_mode == "fd" and prob.kind not in (A.AK_BRATU1D, A.AK_BRATU2D)):
         prob.jvp_mode = A.AK_JVP_FD
     nrm = C.c_double()
 

@@ -256,7 +256,7 @@ def test_fused_finite_difference_jvp(nk, ctx, oracle):
     """AK_JVP_FD_FUSED (north_star item 2): (F(u + eps v) - F(u)) / eps in one pass that reads u and v and never
     materialises u + eps v.  It approximates the exact tangent to O(eps |F''| + eps_mach |F| / eps) ~ 1e-7 relative
     — which is why the analytic tangent, not this mode, is the parity path."""
-    for d in (P.bratu2d(64), P.bratu2d(130, 37), P.bratu2d(33, 31)):
+    for d in (P.bratu2d(64), P.bratu2d(130, 37), P.bratu2d(33, 31), P.bratu1d(1000), P.bratu1d(1001), P.bratu1d(5)):
         F_, u, p, _ = P.device_setup(nk, ctx, d)
         res = u.zero()
         v0 = RNG.standard_normal(d["u0"].shape)
