@@ -32,6 +32,11 @@ struct KrylovStatus {  // pinned host ring, written by the scalar kernels
     int iter, stop, solved, breakdown, zerocurv, pad;
 };
 constexpr int kStatusRing = 8;   // per-iteration records; slot kStatusRing is the pass prologue
+// How many iterations the host launches ahead of the last verdict it has read.  Kernels of iterations after a stop
+// are no-ops on the device, so depth only costs a few empty launches at the end of a pass; with short kernels
+// (vectors that fit in L2) a depth of 1 leaves the stream empty while the host wakes up from the event.
+constexpr int kSpecDepth = 3;
+static_assert(kSpecDepth < kStatusRing, "the status ring must outlive the speculation window");
 constexpr int kStatusSlots = kStatusRing + 1;
 
 }  // namespace ak
@@ -507,6 +512,18 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
         } else {
             int64_t k = 0;
             bool scale_pending = false;  // FUSE_FULL: V[k] = w/Hbis is folded into the next JVP
+            int64_t next_read = 1;       // oldest iteration whose verdict the host has not looked at yet
+            // read the verdicts of iterations next_read..upto in order; true as soon as one of them stopped the pass
+            auto verdicts_until = [&](int64_t upto, bool* stopped) -> int {
+                *stopped = false;
+                while (next_read <= upto) {
+                    AK_TRY(wait_status(ws, (int)(next_read % kStatusRing), &hs));
+                    next_read += 1;
+                    if (hs.stop) { *stopped = true; break; }
+                }
+                return AK_OK;
+            };
+            bool stopped = false;
             while (true) {
                 k += 1;
                 // storage for this iteration (basis vector k receives q/Hbis, 0-based)
@@ -515,7 +532,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                         int rc = ws_ensure_basis(ws, k + 1);
                         if (rc != AK_OK) {
                             // cannot grow further: treat as out of iterations (reference would keep growing)
-                            if (k > 1) AK_TRY(wait_status(ws, (int)((k - 1) % kStatusRing), &hs));
+                            AK_TRY(verdicts_until(k - 1, &stopped));
                             K = k - 1;
                             tired = true;
                             break;
@@ -533,8 +550,8 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 double* pv = ws->V[k - 1];
                 if ((flexible || precond || lprec) && k > 1) {
                     // the preconditioner solves with host-visible verdicts: this path is not speculative
-                    AK_TRY(wait_status(ws, (int)((k - 1) % kStatusRing), &hs));
-                    if (hs.stop) { K = k - 1; break; }
+                    AK_TRY(verdicts_until(k - 1, &stopped));
+                    if (stopped) { K = k - 1; break; }
                 }
                 if (flexible || precond) {
                     double* tgt = ws->pbuf;
@@ -674,14 +691,11 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                     if (fuse == AK_FUSE_FULL) scale_pending = true;
                     else AK_TRY(launch_divcopy_dev(c, n, ws->V[k], w, &ws->ctl->Hbis, stop));
                 }
-                // look at the previous iteration's verdict while this one runs
-                if (k > 1) {
-                    AK_TRY(wait_status(ws, (int)((k - 1) % kStatusRing), &hs));
-                    if (hs.stop) { K = k - 1; break; }
-                }
-                if (k >= inner_limit) {
-                    AK_TRY(wait_status(ws, slot, &hs));
-                    K = hs.stop && hs.iter == k ? k : hs.iter;
+                // look at an older iteration's verdict while the newer ones run
+                AK_TRY(verdicts_until(k - kSpecDepth, &stopped));
+                if (stopped) break;
+                if (k >= inner_limit) {  // last iteration of the pass: drain the window (its own record has stop = tired)
+                    AK_TRY(verdicts_until(k, &stopped));
                     break;
                 }
             }
@@ -789,7 +803,7 @@ static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, cons
     bool solved = hs.solved != 0, zerocurv = false;
     double rNorm = hs.rNorm;
     if (!hs.stop && itmax > 0) {
-        int64_t k = 0;
+        int64_t k = 0, next_read = 1;
         while (true) {
             k += 1;
             if (want_hist) AK_TRY(ws_grow_hist(ws, k + 1));
@@ -820,12 +834,19 @@ static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, cons
                 c->launches++;
                 AK_CUDA(cudaGetLastError());
             }
-            if (k > 1) {
-                AK_TRY(wait_status(ws, (int)((k - 1) % kStatusRing), &hs));
-                if (hs.stop) break;
+            bool stopped = false;
+            while (next_read <= k - kSpecDepth && !stopped) {  // verdicts of older iterations, in order
+                AK_TRY(wait_status(ws, (int)(next_read % kStatusRing), &hs));
+                next_read += 1;
+                stopped = hs.stop != 0;
             }
-            if (k >= itmax) {
-                AK_TRY(wait_status(ws, slot, &hs));
+            if (stopped) break;
+            if (k >= itmax) {  // drain the window; the record of iteration itmax has stop set
+                while (next_read <= k) {
+                    AK_TRY(wait_status(ws, (int)(next_read % kStatusRing), &hs));
+                    next_read += 1;
+                    if (hs.stop) break;
+                }
                 break;
             }
         }
