@@ -268,3 +268,33 @@ def test_failing_user_callback_is_reported(nk, ctx):
     with pytest.raises(nk.AriadneError) as e:
         F_(u.zero(), u, None)
     assert e.value.code == A.AK_ERR_USER
+
+
+def test_blow_up_guard(nk, ctx, oracle, capsys):
+    """`isinf(n_res) || isnan(n_res)` -> `@error "Inner solver blew up"; break` (src/Ariadne.jl:353-356): the full Newton
+    step of F(u) = sqrt(u) - 1 from u0 = (9, 16, 25, 36) lands on negative values, the next residual is NaN, and the
+    loop stops before the step is counted — in the host-driven loop, in ak_newton_solve and in the oracle alike."""
+    import torch
+
+    u0 = np.array([9.0, 16.0, 25.0, 36.0])
+
+    def F_np(res, u):
+        with np.errstate(all="ignore"):
+            res[:] = np.sqrt(u) - 1.0
+
+    def J_np(out, u, v):
+        with np.errstate(all="ignore"):
+            out[:] = v / (2.0 * np.sqrt(u))
+
+    o = A.default_newton_opts(forcing=A.AK_FORCING_NONE)
+    ur, sr, hr = oracle.newton(oracle.make_user_problem(4, F_np, J_np), u0, o)
+    assert sr["flags"] & A.AK_FLAG_NAN and not sr["solved"] and sr["outer_iterations"] == 0
+
+    F_ = nk.UserResidual(lambda res, u, p: res.copy_(torch.sqrt(u) - 1.0),
+                         lambda out, u, v, p: out.copy_(v / (2.0 * torch.sqrt(u))))
+    for drive in (nk.newton_krylov_, nk.newton_krylov_native_):
+        u = nk.DeviceVector.from_numpy(u0, ctx)
+        _, r = drive(F_, u, None, u.zero(), forcing=None)
+        assert not r.solved and r.stats.outer_iterations == 0
+        assert np.allclose(u.numpy(), ur, rtol=1e-9)      # the overshot iterate (-3, -8, -15, -24)
+    assert "Inner solver blew up" in capsys.readouterr().out
