@@ -202,6 +202,21 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # one process per GPU: run (and allocate the pinned staging buffer of the e2e leg) on the CPUs next to this
+        # GPU, so that eight simultaneous 512 MiB host<->device copies do not all go through one socket's memory
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            try:  # NVML numbers physical devices; go through the UUID in case CUDA_VISIBLE_DEVICES remaps them
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:  # noqa: BLE001
+                handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            pynvml.nvmlDeviceSetCpuAffinity(handle)
+        except Exception as e:  # noqa: BLE001 - affinity is an optimisation only
+            print(f"[bench] rank {rank}: CPU affinity not set ({e})", file=sys.stderr)
+    if world > 1:
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
