@@ -159,3 +159,52 @@ def test_newton_with_ilu_bratu_example(nk, ctx, oracle, algo, drive):
     theta = 4.79173  # examples/bratu.jl:33-37
     ref = -2.0 * np.log(np.cosh(theta * (d["x"] - 0.5) / 2.0) / np.cosh(theta / 4.0))
     assert np.max(np.abs(u.numpy() - ref)) < 1e-4
+
+
+def test_full_bratu2d_solve_with_caller_supplied_fast_poisson_preconditioner(nk, ctx, oracle):
+    """The `N` hook with user code (AK_PRECOND_USER): y = (Laplacian + mean(lambda e^u))^-1 x by sine transforms
+    (examples/python/bratu2d_fast_poisson.py).  With it the 2-D Bratu solve converges in a handful of GMRES
+    iterations per Newton step at any grid size; against the oracle driven with the same preconditioner (scipy DST)."""
+    import importlib.util
+    import os
+
+    import scipy.fft as sfft
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("bratu2d_fast_poisson",
+                                                  os.path.join(here, "..", "examples", "python", "bratu2d_fast_poisson.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    N, lam = 192, 3.5
+    u, r, hist, _ = ex.solve(N, lam, verbose=False, ctx=ctx)
+    assert r.solved and all(h["inner"] <= 12 for h in hist)
+
+    # oracle: same Newton loop, the preconditioner rebuilt per Newton step like N(J)  (src/Ariadne.jl:324-326)
+    d = P.bratu2d(N, lam=lam)
+    po = P.oracle_problem(oracle, d)
+    k = np.arange(1, N + 1)
+    mu = -4.0 * np.sin(np.pi * k / (2 * (N + 1))) ** 2 / d["dx"] ** 2
+    eig = mu[:, None] + mu[None, :]
+    state = {"shift": 0.0}
+
+    def apply(y, x):
+        X = sfft.dstn(x.reshape(N, N), type=1) / (eig + state["shift"])
+        y[:] = (sfft.idstn(X, type=1)).reshape(-1)
+
+    fn, keep = oracle.user_precond(N * N, apply)
+    uo = d["u0"].copy()
+    n_res = np.linalg.norm(oracle.residual(po, uo)[0])
+    tol, eta, hist_o = 1e-6 * n_res + 1e-12, 0.999, []
+    while n_res > tol and len(hist_o) <= 50:
+        state["shift"] = lam * float(np.mean(np.exp(uo)))
+        res, _ = oracle.residual(po, uo)
+        x, st, _ = oracle.krylov_solve(po, uo, res, rtol=eta, precond_n=A.AK_PRECOND_USER, n_apply=fn)
+        uo = uo - x.reshape(uo.shape)
+        prior, n_res = n_res, np.linalg.norm(oracle.residual(po, uo)[0])
+        eta = oracle.forcing_ew(0.999, 0.9, eta, tol, n_res, prior)
+        hist_o.append(dict(n_res=n_res, inner=st["niter"]))
+    assert [h["inner"] for h in hist[1:]] == [h["inner"] for h in hist_o]
+    for a, b in zip(hist[1:], hist_o):
+        assert abs(a["n_res"] - b["n_res"]) <= 1e-7 * b["n_res"] + 1e-11 * hist[0]["n_res"]
+    assert rel(u.numpy(), uo) < 1e-8
+    del keep
