@@ -869,6 +869,7 @@ static int launch_rhs(Ctx* ctx, const ak_problem* p, double* in, double* du) {
         d.ne = p->nx / 4;
         d.c0 = 1.0; d.c1 = 1.0; d.rhs_only = 1;
         d.in = in; d.out = du;
+        AK_TRY(ghost_1d(ctx, in, p->nx, 4, 1, true, &d.lo, &d.hi));
         d.partials = ctx->partials; d.ticket = ctx->ticket;
         return launch_dg(ctx, d, false, false, RED_NONE);
     }
@@ -877,6 +878,7 @@ static int launch_rhs(Ctx* ctx, const ak_problem* p, double* in, double* du) {
     a.in = in;
     a.out = du;
     if (p->kind == AK_HEAT1D) {
+        AK_TRY(ghost_1d(ctx, in, p->nx, 1, 1, false, &a.lo, &a.hi));
         a.in_write = in;
         return launch1d<OP_RHS_HEAT>(ctx, a, false, RED_NONE);
     }
@@ -957,7 +959,6 @@ int launch_residual(Ctx* ctx, const ak_problem* p, double* u, double* res, doubl
         return AK_OK;
     }
     if (p->scheme == AK_MIDPOINT || p->scheme == AK_TRAPEZOID) {
-        if (ctx->nranks > 1) { set_error("Midpoint/Trapezoid are single-GPU in this version"); return AK_ERR_UNSUPPORTED; }
         return launch_residual_composite(ctx, p, u, res, sumsq_dev);
     }
     const int red = sumsq_dev ? RED_SUMSQ : RED_NONE;
@@ -1036,7 +1037,6 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     }
     if (p->scheme == AK_MIDPOINT) {
         // composed path: fused normalisation / dot are done as separate launches (same arithmetic)
-        if (ctx->nranks > 1) { set_error("Midpoint is single-GPU in this version"); return AK_ERR_UNSUPPORTED; }
         const int64_t n = ak_problem_size(p);
         if (f->stop_flag) {
             // kernels of the composite path do not read the stop flag; results are discarded by the caller

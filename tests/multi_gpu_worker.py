@@ -95,8 +95,66 @@ def run_1d_cases(ctx, rank, world, rng, tag):
             print(f"[multi-gpu x{world} {tag}] {name}: ok", flush=True)
 
 
+def run_scheme_cases(ctx, rank, world, rng, tag):
+    """G_Midpoint! / G_Trapezoid! (examples/implicit.jl:17-37) on slabs / segments: residual, tangent, two time steps."""
+    import ctypes as C
+    cases = [("heat1d", P.heat1d(98), nk.heat_1D_), ("dg", P.heat1d_dg(max(26, 3 * world), dt=1e-4), nk.heat_1D_DG_),
+             ("heat2d", P.heat2d(36, dt_scale=48.0, ic="poly"), nk.diffusion_)]
+    for name, d0, f_ in cases:
+        for G_, code in ((nk.G_Midpoint_, A.AK_MIDPOINT), (nk.G_Trapezoid_, A.AK_TRAPEZOID)):
+            d = dict(d0)
+            d["scheme"] = code
+            if d["kind"] == A.AK_HEAT2D:
+                gy0, ny = nk.dist.slab_partition(d["ny"], world, rank)
+                sl = slice(gy0, gy0 + ny)
+                pin = (d["a"], d["dx"], d["dy"], nk.bc_zero_, d["ny"], gy0)
+            elif d["kind"] == A.AK_HEAT1D_DG:
+                e0, ne = nk.dist.slab_partition(d["nx"] // 4, world, rank)
+                sl = slice(4 * e0, 4 * (e0 + ne))
+                pin = (d["dx"],)
+            else:
+                g0, n = nk.dist.slab_partition(d["nx"], world, rank)
+                sl = slice(g0, g0 + n)
+                pin = (d["a"], d["dx"], nk.bc_zero_)
+            # a state that differs from u_n, so that both halves of the schemes are exercised
+            ustate = d["u0"] * (1.0 + 0.1 * np.cos(np.arange(d["u0"].size).reshape(d["u0"].shape) * 0.37))
+            u = nk.DeviceVector.from_numpy(ustate[sl], ctx)
+            un = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
+            F_ = nk.ImplicitResidual(G_, f_)
+            p = (un, d["dt"], un.zero(), pin, 0.0)
+            po = P.oracle_problem(O, d, un=d["u0"].copy())
+            res, out = u.zero(), u.zero()
+            F_(res, u, p)
+            ref, _ = O.residual(po, ustate)
+            assert rel(res.numpy(), ref[sl]) < 1e-13, (name, code)
+            v0 = rng.standard_normal(d["u0"].shape)
+            if d["kind"] == A.AK_HEAT1D:
+                v0[0] = v0[-1] = 0.0
+            nk.mul_(out, nk.JacobianOperator(F_, res, u, p), nk.DeviceVector.from_numpy(v0[sl], ctx))
+            refj, _ = O.jvp(po, ustate, v0)
+            assert rel(out.numpy(), refj[sl]) < 1e-13, (name, code)
+            # two time steps through ak_implicit_solve
+            prob = F_.problem(u, p)
+            o = nk.host._newton_opts(1e-6, 6e-6, 50, nk.EisenstatWalker(), "gmres", 20, 0, {})
+            nsteps = 2
+            newt, inner, solved = np.zeros(nsteps, np.int32), np.zeros(nsteps, np.int64), np.zeros(nsteps, np.int32)
+            un2 = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
+            nk._lib.check(ctx.lib.ak_implicit_solve(ctx.h, C.byref(prob), C.c_void_p(un2.ptr), nsteps, C.byref(o),
+                                                    newt.ctypes.data_as(A.c_int32_p), inner.ctypes.data_as(A.c_int64_p),
+                                                    solved.ctypes.data_as(A.c_int32_p)))
+            po2 = P.oracle_problem(O, d, un=d["u0"].copy())
+            ur, nr, ir, sr_ = O.implicit_solve(po2, d["u0"], nsteps, o)
+            assert list(newt) == list(nr) and list(solved) == list(sr_), (name, code, newt, nr)
+            assert all(abs(int(a) - int(b)) <= 1 for a, b in zip(inner, ir)), (name, code, inner, ir)
+            assert rel(un2.numpy(), ur[sl]) < 1e-7, (name, code)
+        if rank == 0:
+            print(f"[multi-gpu x{world} {tag}] {name} midpoint/trapezoid: ok", flush=True)
+
+
 def run_cases(ctx, rank, world, rng, tag):
     run_1d_cases(ctx, rank, world, rng, tag)
+    if tag == "nccl":
+        run_scheme_cases(ctx, rank, world, rng, tag)
     for name, d, bc in [("bratu2d", P.generic(P.bratu2d(48, 40)), nk.bc_zero_),
                         ("bratu2d_ragged", P.generic(P.bratu2d(37, 29)), nk.bc_zero_),
                         ("heat2d", P.heat2d(36, dt_scale=48.0, ic="poly"), nk.bc_zero_),
