@@ -40,13 +40,15 @@ void set_error(const char* fmt, ...);
 
 // ---- NVLink peer memory (CUDA IPC) for the fused compute + collective kernels -----------------
 // One cudaMalloc'ed block per rank, mapped into every other rank of the node:
-//   mail : kMailSlots x nranks records {10 sums, tag, pad}  — partial sums written by peer kernels
+//   mail : kMailSlots x nranks records {kBlkSums sums, tag, pad}  — partial sums written by peer kernels
 //   halo : 2 parities x {lo, hi} x halo_cap doubles       — boundary rows pushed by the neighbours
 constexpr int kMaxPeers = 8;
 constexpr int kMailSlots = 8;
 constexpr int kBlkMax = 4;    // Gram-Schmidt steps per sweep over w (block size of the blocked sweep)
-constexpr int kBlkSums = 10;  // sums of one pass: 4 projections <y_b,w> + 6 Gram entries <y_b,y_a>, a < b
-constexpr int kMailRec = 12;  // doubles per mailbox record: kBlkSums sums, tag, pad
+// sums of one pass: up to kBlkMax projections <S_b, w>; final pass: ||w||^2 and the Gram entries <S_a, w_new> of the
+// vector it finishes with the vectors of its own block (cached: they do not change in later iterations)
+constexpr int kBlkSums = kBlkMax + 1;
+constexpr int kMailRec = kBlkSums + 2;  // doubles per mailbox record: kBlkSums sums, tag, pad
 struct P2PDev {           // passed by value to kernels
     int nranks, rank;
     double* mail_local;                 // this rank's mailbox
@@ -78,7 +80,7 @@ enum ProfClass {
     PK_ELEMENTWISE = 7,    // scal/axpy/axpby/copy/fill/divcopy/ref
     PK_COMBINE = 8,        // x = sum y_i V_i
     PK_SCALAR = 9,         // one-thread Givens / control kernels
-    PK_MGS_PAIR = 10,      // full blocked pass: w -= sum_b h_b v_b ; sums with the next block   8n(2+2R): 48n (R=2), 80n (R=4)
+    PK_MGS_PAIR = 10,      // full blocked pass: w -= sum_b h_b v_b ; projections on the next block   8n(2+2R): 48n (R=2), 80n (R=4)
     PK_MGS_PAIR_EDGE = 11, // first / ragged passes of the blocked sweep
     PK_NUM = 12
 };
@@ -170,8 +172,9 @@ int launch_divcopy_dev(Ctx* ctx, int64_t n, double* y, const double* x, const do
 int launch_mgs_step(Ctx* ctx, int64_t n, double* w, const double* vi, const double* h_in,
                     const double* vnext, int want_sumsq, double* out_dev, const int* stop_flag);
 // Blocked Gram-Schmidt pass (see blas1.cu): subtracts up to kBlkMax basis vectors `va[0..nax)` with the
-// coefficients recovered from the raw sums `tin` (kBlkSums doubles) and projects the result on up to kBlkMax
-// vectors `ya[0..ny)` (raw sums -> out, kBlkSums doubles), or returns ||w||^2 in out[0] (want_sumsq).
+// coefficients recovered from the raw projections `tin`, the cached Gram entries `gram_in` of that block and the
+// scales `rho_in`, and projects the result on up to kBlkMax vectors `ya[0..ny)` (raw sums -> out), or (want_sumsq)
+// returns ||w||^2 in out[0] and <va[a], w_new> in out[1 + a].
 // `pc` (may be null) routes the reduction through the peers' mailboxes (NVLink) instead of NCCL and lets the
 // final pass push its boundary rows to the neighbours.
 struct BlockComm {
@@ -180,8 +183,8 @@ struct BlockComm {
     P2PHalo halo = {nullptr, nullptr, 0};
 };
 int launch_mgs_block(Ctx* ctx, int64_t n, double* w, const double* const* va, int nax, const double* tin,
-                     const double* rho_in, const double* const* ya, int ny, int want_sumsq, double* out,
-                     const int* stop, const BlockComm* pc);
+                     const double* gram_in, const double* rho_in, const double* const* ya, int ny, int want_sumsq,
+                     double* out, const int* stop, const BlockComm* pc);
 // x <- x + sum_i y[i] V[i]  (sequential axpy order), optionally u <- u - x fused (single pass)
 int launch_basis_combine(Ctx* ctx, int64_t n, double* x, const double* const* V_dev, const double* y_dev,
                          int k, int zero_x_first);

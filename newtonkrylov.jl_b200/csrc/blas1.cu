@@ -140,19 +140,23 @@ int launch_mgs_step(Ctx* ctx, int64_t n, double* w, const double* vi, const doub
 }
 
 // -----------------------------------------------------------------------------------
-// Blocked modified Gram-Schmidt pass (fuse levels PAIR = blocks of 2, BLOCK4 = blocks of 4): up to kBlkMax
+// Blocked modified Gram-Schmidt pass (fuse levels PAIR = blocks of 2, BLOCK4 = blocks of kBlkMax): several
 // Gram-Schmidt steps per sweep over w.
-//   NAX axpys  : w <- w - sum_{b<NAX} h_b v_b, h = block_coefficients(raw sums of that block, `tin`)
-//   NRED 1..4  : raw sums of the next block: t[b] = <y_b, w_new>, t[gram_index(b,a)] = <y_b, y_a> (a < b).
-//                h_b = t[b] - sum_{a<b} h_a <y_b,y_a> is algebraically the modified Gram-Schmidt coefficient
-//                <y_b, w_new - sum_{a<b} h_a y_a>, obtained without another sweep over w.
-//   NRED 5     : out[0] = <w_new, w_new>
-// Algorithmic bytes per launch: 8n (2 [w in/out] + NAX + number of y vectors): 48n for blocks of 2 (24n per
+//   NAX axpys      : w <- w - sum_{b<NAX} c_b S_b, (h, c) = block_coefficients(projections `tin` of that block,
+//                    its cached Gram entries `gram_in`, its scales `rho_in`)
+//   NRED 1..kBlkMax: projections on the next block, t[b] = <S'_b, w_new>.  With the cached Gram entries
+//                    h_b = <v_b,w> - sum_{a<b} h_a <v_b,v_a> is algebraically the modified Gram-Schmidt coefficient
+//                    <v_b, w_new - sum_{a<b} h_a v_a>, obtained without another sweep over w.
+//   NRED = final   : out[0] = <w_new, w_new>, out[1 + a] = <S_a, w_new> for the NAX vectors just subtracted: w_new is the
+//                    stored basis vector this iteration produces, and these are its Gram entries with the earlier
+//                    vectors of its own block (rounding-level numbers: the loss of orthogonality that the
+//                    coefficients of later iterations correct for).  They come for free: S_a is in registers.
+// Algorithmic bytes per launch: 8n (2 [w in/out] + NAX + number of projection vectors): 48n for blocks of 2 (24n per
 // Gram-Schmidt step), 80n for blocks of 4 (20n per step), instead of 32n per step for axpy_i + dot_{i+1}.
 // -----------------------------------------------------------------------------------
 struct BlkPtrs {
-    const double* va[kBlkMax];  // vectors to subtract
-    const double* ya[kBlkMax];  // vectors to project on
+    const double* va[kBlkMax];  // stored vectors to subtract
+    const double* ya[kBlkMax];  // stored vectors to project on
 };
 struct BlockP2P {     // fused collective of the blocked pass (all zero / null when not used)
     P2PDev pd;
@@ -161,36 +165,39 @@ struct BlockP2P {     // fused collective of the blocked pass (all zero / null w
     double* tin_store;           // where block 0 leaves the reduced incoming sums for the Givens kernel
     P2PHalo halo;                // boundary-row push (final pass only)
 };
-constexpr int kRedSumsq = 5;
+constexpr int kRedFinal = kBlkMax + 1;
 
 template <int NAX, int NRED, bool P2P>
 __global__ void __launch_bounds__(kThreads, 2) k_mgs_block(double* __restrict__ w, const BlkPtrs bp,
                                                            const double* __restrict__ tin,
+                                                           const double* __restrict__ gram_in,
                                                            const double* __restrict__ rho_in, double* __restrict__ out,
                                                            double* __restrict__ partials, unsigned int* ticket,
                                                            int64_t n, const int* __restrict__ stop, const int vec,
                                                            const BlockP2P pp) {
-    constexpr int NY = (NRED == kRedSumsq) ? 0 : NRED;
-    constexpr int NS = (NRED == kRedSumsq) ? 1 : sums_used(NRED);
+    constexpr bool FINAL = (NRED == kRedFinal);
+    constexpr int NY = FINAL ? 0 : NRED;
+    constexpr int NS = FINAL ? 1 + NAX : NRED;
     __shared__ double sh[32];
     __shared__ double shm[kBlkSums * kMaxPeers];
     if (stop != nullptr && *stop != 0) return;
-    double h[kBlkMax] = {0.0, 0.0, 0.0, 0.0};  // negated multipliers of the stored vectors of the block being subtracted
+    double h[kBlkMax];  // negated multipliers of the stored vectors of the block being subtracted
+#pragma unroll
+    for (int b = 0; b < kBlkMax; ++b) h[b] = 0.0;
     if (NAX >= 1) {
-        constexpr int NIN = sums_used(NAX);
         double t[kBlkSums];
         if (P2P && pp.seq_in != 0) {
-            mail_wait_sum(pp.pd, pp.seq_in, t, NIN, shm);
+            mail_wait_sum(pp.pd, pp.seq_in, t, NAX, shm);
             if (blockIdx.x == 0 && threadIdx.x == 0 && pp.tin_store != nullptr) {
 #pragma unroll
-                for (int c = 0; c < NIN; ++c) pp.tin_store[c] = t[c];
+                for (int c = 0; c < NAX; ++c) pp.tin_store[c] = t[c];
             }
         } else {
 #pragma unroll
-            for (int c = 0; c < kBlkSums; ++c) t[c] = (c < NIN) ? tin[c] : 0.0;
+            for (int c = 0; c < kBlkSums; ++c) t[c] = (c < NAX) ? tin[c] : 0.0;
         }
         double hc[kBlkMax];
-        block_coefficients(t, rho_in, NAX, hc, h);
+        block_coefficients(t, gram_in, rho_in, NAX, hc, h);
 #pragma unroll
         for (int b = 0; b < kBlkMax; ++b) h[b] = -h[b];
     }
@@ -199,25 +206,25 @@ __global__ void __launch_bounds__(kThreads, 2) k_mgs_block(double* __restrict__ 
     for (int c = 0; c < NS; ++c) sA[c] = sB[c] = 0.0;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-    const bool push = P2P && NRED == kRedSumsq && (pp.halo.down_hi != nullptr || pp.halo.up_lo != nullptr);
+    const bool push = P2P && FINAL && (pp.halo.down_hi != nullptr || pp.halo.up_lo != nullptr);
     const int64_t hnx = pp.halo.nx;
     auto body = [&](double& wj, const double (&x)[kBlkMax], const double (&y)[kBlkMax], double (&s)[NS]) {
 #pragma unroll
         for (int b = 0; b < NAX; ++b) wj = fma(h[b], x[b], wj);  // same order as successive kaxpy!
-        if (NRED == kRedSumsq) {
+        if (FINAL) {
             s[0] = fma(wj, wj, s[0]);
+#pragma unroll
+            for (int a = 0; a < NAX; ++a) s[1 + a] = fma(x[a], wj, s[1 + a]);
         } else {
 #pragma unroll
-            for (int b = 0; b < NY; ++b) {
-                s[b] = fma(y[b], wj, s[b]);
-#pragma unroll
-                for (int a = 0; a < b; ++a) s[gram_index(b, a)] = fma(y[b], y[a], s[gram_index(b, a)]);
-            }
+            for (int b = 0; b < NY; ++b) s[b] = fma(y[b], wj, s[b]);
         }
     };
     auto scalar_elem = [&](int64_t j) {
         double wj = w[j];
-        double x[kBlkMax] = {0, 0, 0, 0}, y[kBlkMax] = {0, 0, 0, 0};
+        double x[kBlkMax], y[kBlkMax];
+#pragma unroll
+        for (int b = 0; b < kBlkMax; ++b) x[b] = y[b] = 0.0;
 #pragma unroll
         for (int b = 0; b < NAX; ++b) x[b] = bp.va[b][j];
 #pragma unroll
@@ -241,10 +248,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_mgs_block(double* __restrict__ 
 #pragma unroll
             for (int b = 0; b < NY; ++b) yv[b] = ld4_stream(bp.ya[b] + j);
             {
-                const double x0[kBlkMax] = {xv[0].x, xv[1].x, xv[2].x, xv[3].x}, y0[kBlkMax] = {yv[0].x, yv[1].x, yv[2].x, yv[3].x};
-                const double x1[kBlkMax] = {xv[0].y, xv[1].y, xv[2].y, xv[3].y}, y1[kBlkMax] = {yv[0].y, yv[1].y, yv[2].y, yv[3].y};
-                const double x2[kBlkMax] = {xv[0].z, xv[1].z, xv[2].z, xv[3].z}, y2[kBlkMax] = {yv[0].z, yv[1].z, yv[2].z, yv[3].z};
-                const double x3[kBlkMax] = {xv[0].w, xv[1].w, xv[2].w, xv[3].w}, y3[kBlkMax] = {yv[0].w, yv[1].w, yv[2].w, yv[3].w};
+                double x0[kBlkMax], x1[kBlkMax], x2[kBlkMax], x3[kBlkMax], y0[kBlkMax], y1[kBlkMax], y2[kBlkMax], y3[kBlkMax];
+#pragma unroll
+                for (int b = 0; b < kBlkMax; ++b) {
+                    x0[b] = xv[b].x; x1[b] = xv[b].y; x2[b] = xv[b].z; x3[b] = xv[b].w;
+                    y0[b] = yv[b].x; y1[b] = yv[b].y; y2[b] = yv[b].z; y3[b] = yv[b].w;
+                }
                 body(wv.x, x0, y0, sA);
                 body(wv.y, x1, y1, sB);
                 body(wv.z, x2, y2, sA);
@@ -277,8 +286,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_mgs_block(double* __restrict__ 
 
 template <int NAX, int NRED>
 static int launch_mgs_block_t(Ctx* ctx, int64_t n, double* w, const BlkPtrs& bp, const double* tin,
-                              const double* rho_in, double* out, const int* stop, bool vec, bool p2p,
-                              const BlockP2P& pp, int cls) {
+                              const double* gram_in, const double* rho_in, double* out, const int* stop, bool vec,
+                              bool p2p, const BlockP2P& pp, int cls) {
     static int occ[2] = {0, 0};  // resident blocks per SM of this instantiation (queried once)
     if (occ[p2p] == 0) {
         int nb = 0;
@@ -292,32 +301,56 @@ static int launch_mgs_block_t(Ctx* ctx, int64_t n, double* w, const BlkPtrs& bp,
     const int blocks = (int)(need < 1 ? 1 : (need < cap ? need : cap));
     ProfScope prof(ctx, cls);
     if (p2p)
-        k_mgs_block<NAX, NRED, true><<<blocks, kThreads, 0, ctx->stream>>>(w, bp, tin, rho_in, out, ctx->partials,
-                                                                           ctx->ticket, n, stop, vec ? 1 : 0, pp);
+        k_mgs_block<NAX, NRED, true><<<blocks, kThreads, 0, ctx->stream>>>(w, bp, tin, gram_in, rho_in, out,
+                                                                           ctx->partials, ctx->ticket, n, stop,
+                                                                           vec ? 1 : 0, pp);
     else
-        k_mgs_block<NAX, NRED, false><<<blocks, kThreads, 0, ctx->stream>>>(w, bp, tin, rho_in, out, ctx->partials,
-                                                                            ctx->ticket, n, stop, vec ? 1 : 0, pp);
+        k_mgs_block<NAX, NRED, false><<<blocks, kThreads, 0, ctx->stream>>>(w, bp, tin, gram_in, rho_in, out,
+                                                                            ctx->partials, ctx->ticket, n, stop,
+                                                                            vec ? 1 : 0, pp);
     return AK_OK;
 }
 
-// va[0..nax): stored vectors to subtract, tin: raw sums of that block, rho_in (may be null): their scales (un-normalised
-// basis); ya[0..ny): vectors to project on; want_sumsq: ||w_new||^2 instead.  out receives sums_used(ny) doubles, or 1.
+// compile-time enumeration of the (NAX, NRED) shapes the sweep uses
+template <int A, int R>
+static int dispatch_block(int nax, int nred, Ctx* ctx, int64_t n, double* w, const BlkPtrs& bp, const double* tin,
+                          const double* gram_in, const double* rho_in, double* out, const int* stop, bool vec, bool p2p,
+                          const BlockP2P& pp, int cls) {
+    if (nax == A && nred == R) {
+        // a pass either projects (first pass: nothing to subtract; later passes: any block) or is the final one
+        // (projection passes subtract nothing, a full pair or a full block; the final pass subtracts 1..kBlkMax)
+        if constexpr (R == kRedFinal ? (A >= 1) : (A == 0 || A == 2 || A == kBlkMax))
+            return launch_mgs_block_t<A, R>(ctx, n, w, bp, tin, gram_in, rho_in, out, stop, vec, p2p, pp, cls);
+    }
+    if constexpr (R < kRedFinal) {
+        return dispatch_block<A, R + 1>(nax, nred, ctx, n, w, bp, tin, gram_in, rho_in, out, stop, vec, p2p, pp, cls);
+    } else if constexpr (A < kBlkMax) {
+        return dispatch_block<A + 1, 1>(nax, nred, ctx, n, w, bp, tin, gram_in, rho_in, out, stop, vec, p2p, pp, cls);
+    } else {
+        set_error("launch_mgs_block: no kernel for nax = %d, nred = %d", nax, nred);
+        return AK_ERR_ARG;
+    }
+}
+
+// va[0..nax): stored vectors to subtract, tin: raw projections on that block, gram_in: its cached Gram entries, rho_in
+// (may be null): its scales; ya[0..ny): vectors to project on; want_sumsq: final pass instead (||w_new||^2 and the Gram
+// entries of w_new with va).  out receives ny doubles, or 1 + nax.
 // With `pc` (multi-GPU, peer memory enabled) the sums travel through the peers' mailboxes instead of NCCL.
 int launch_mgs_block(Ctx* ctx, int64_t n, double* w, const double* const* va, int nax, const double* tin,
-                     const double* rho_in, const double* const* ya, int ny, int want_sumsq, double* out,
-                     const int* stop, const BlockComm* pc) {
+                     const double* gram_in, const double* rho_in, const double* const* ya, int ny, int want_sumsq,
+                     double* out, const int* stop, const BlockComm* pc) {
     if (n <= 0) return AK_OK;
     if (nax < 0 || nax > kBlkMax || ny < 0 || ny > kBlkMax || (ny == 0 && !want_sumsq) || (ny > 0 && want_sumsq)) {
         set_error("launch_mgs_block: bad block shape (nax = %d, ny = %d, sumsq = %d)", nax, ny, want_sumsq);
         return AK_ERR_ARG;
     }
-    const int nred = want_sumsq ? kRedSumsq : ny;
+    const int nred = want_sumsq ? kRedFinal : ny;
     BlkPtrs bp{};
     bool vec = aligned32(w);
     for (int b = 0; b < nax; ++b) { bp.va[b] = va[b]; vec = vec && aligned32(va[b]); }
     for (int b = 0; b < ny; ++b) { bp.ya[b] = ya[b]; vec = vec && aligned32(ya[b]); }
     const int cls = (nax >= 2 && nax == ny) ? PK_MGS_PAIR
-                                            : ((nax > 0 && nred == kRedSumsq) ? PK_MGS_AXPY_NRM : PK_MGS_PAIR_EDGE);
+                                            : ((nax > 0 && want_sumsq) ? PK_MGS_AXPY_NRM : PK_MGS_PAIR_EDGE);
     const bool p2p = pc != nullptr && ctx->p2p_on && ctx->nranks > 1;
     BlockP2P pp{};
     if (p2p) {
@@ -329,19 +362,10 @@ int launch_mgs_block(Ctx* ctx, int64_t n, double* w, const double* const* va, in
         // the vector path pushes whole 256-bit words: rows must be 32-byte multiples
         if (pp.halo.nx % 4 != 0 || n % 4 != 0 || !vec) pp.halo.down_hi = pp.halo.up_lo = nullptr;
     }
-    int rc = AK_ERR_ARG;
-#define AK_BLK(A, R) \
-    if (nax == A && nred == R) rc = launch_mgs_block_t<A, R>(ctx, n, w, bp, tin, rho_in, out, stop, vec, p2p, pp, cls);
-    AK_BLK(0, 1) AK_BLK(0, 2) AK_BLK(0, 3) AK_BLK(0, 4)
-    AK_BLK(1, 1) AK_BLK(1, 2) AK_BLK(1, 3) AK_BLK(1, 4) AK_BLK(1, 5)
-    AK_BLK(2, 1) AK_BLK(2, 2) AK_BLK(2, 3) AK_BLK(2, 4) AK_BLK(2, 5)
-    AK_BLK(3, 1) AK_BLK(3, 2) AK_BLK(3, 3) AK_BLK(3, 4) AK_BLK(3, 5)
-    AK_BLK(4, 1) AK_BLK(4, 2) AK_BLK(4, 3) AK_BLK(4, 4) AK_BLK(4, 5)
-#undef AK_BLK
-    AK_TRY(rc);
+    AK_TRY((dispatch_block<0, 1>(nax, nred, ctx, n, w, bp, tin, gram_in, rho_in, out, stop, vec, p2p, pp, cls)));
     ctx->launches++;
     AK_CUDA(cudaGetLastError());
-    if (!p2p) AK_TRY(allreduce_sum(ctx, out, want_sumsq ? 1 : sums_used(ny)));
+    if (!p2p) AK_TRY(allreduce_sum(ctx, out, want_sumsq ? 1 + nax : ny));
     return AK_OK;
 }
 

@@ -195,16 +195,17 @@ AK_DEV void mail_wait_sum(const P2PDev& pd, unsigned long long seq, double (&out
     __syncthreads();
 }
 
-// Raw sums of a blocked pass, fixed layout: t[b] = <S_b, w> (b < 4), t[4 + b(b-1)/2 + a] = <S_b, S_a> (a < b), where
-// S_b is the STORED vector of basis vector v_b.
-//   rho == nullptr: the stored vectors are the normalised basis vectors (S_b = v_b);
-//   otherwise      S_b = rho[b] v_b — the un-normalised basis: V_k is the finished w of iteration k, rho_k = ||w||
-//                  (gmres! step 8, V[k+1] = w / Hbis, is never materialised).
-// Modified Gram-Schmidt coefficients of the block:  h_b = <v_b, w - sum_{a<b} h_a v_a> = <v_b,w> - sum_{a<b} h_a <v_b,v_a>,
-// and c_b = h_b / rho[b] is what multiplies the stored vector in the update w -= sum_b c_b S_b.
+// Coefficients of one block of the blocked Gram-Schmidt sweep.
+//   t[b]            = <S_b, w>            raw projections of this pass (b < m), S_b = stored vector of basis vector v_b
+//   gram[b * kBlkMax + a] = <S_b, S_a>    for a < b in the same block — measured once, by the final pass of the
+//                                         iteration that finished S_b, and cached (they never change afterwards)
+//   rho[b]          : S_b = rho[b] v_b    (un-normalised basis: V_k is the finished w of iteration k, rho_k = ||w||;
+//                                         gmres! step 8, V[k+1] = w / Hbis, is never materialised); nullptr: rho = 1
+// Modified Gram-Schmidt coefficients:  h_b = <v_b, w - sum_{a<b} h_a v_a> = <v_b,w> - sum_{a<b} h_a <v_b,v_a>, and
+// c_b = h_b / rho[b] is what multiplies the stored vector in the update w -= sum_b c_b S_b.
 // One definition shared by the vector kernels and the Givens kernel so that both see the same bits.
-AK_DEV int gram_index(int b, int a) { return kBlkMax + b * (b - 1) / 2 + a; }
-AK_DEV void block_coefficients(const double* t, const double* rho, int m, double (&h)[kBlkMax], double (&c)[kBlkMax]) {
+AK_DEV void block_coefficients(const double* t, const double* gram, const double* rho, int m, double (&h)[kBlkMax],
+                               double (&c)[kBlkMax]) {
 #pragma unroll
     for (int b = 0; b < kBlkMax; ++b) {
         double acc = 0.0, cb = 0.0;
@@ -212,7 +213,7 @@ AK_DEV void block_coefficients(const double* t, const double* rho, int m, double
             const double rb = rho ? rho[b] : 1.0;
             acc = rho ? __ddiv_rn(t[b], rb) : t[b];
             for (int a = 0; a < b; ++a) {
-                double g = t[gram_index(b, a)];
+                double g = gram[b * kBlkMax + a];
                 if (rho) g = __ddiv_rn(__ddiv_rn(g, rb), rho[a]);
                 acc = __dsub_rn(acc, __dmul_rn(h[a], g));
             }
@@ -222,6 +223,5 @@ AK_DEV void block_coefficients(const double* t, const double* rho, int m, double
         c[b] = cb;
     }
 }
-__host__ __device__ constexpr int sums_used(int m) { return m <= 1 ? 1 : kBlkMax + m * (m - 1) / 2; }  // prefix of the record that is live
 
 }  // namespace ak

@@ -64,6 +64,7 @@ struct ak_krylov {
     int64_t kcap = 0;  // columns of R that fit
     double *R = nullptr, *c = nullptr, *s = nullptr, *z = nullptr, *hcol = nullptr, *hist = nullptr;
     double* rho = nullptr;  // un-normalised basis (blocked sweeps): stored V[i] = rho[i] * v_i
+    double* gram = nullptr; // blocked sweeps: <V[i], V[a]> for the earlier vectors a of V[i]'s own block (kBlkMax per i)
     int64_t hist_cap = 0;
     ak::KrylovCtl* ctl = nullptr;
     ak::KrylovStatus* status = nullptr;  // pinned
@@ -111,15 +112,17 @@ __device__ __forceinline__ double sgn(double x) { return (double)((x > 0.0) - (x
 __global__ void k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, double* c, double* s, double* z,
                                double* hcol, int reorth, int blk, double* hist, int64_t hist_pos,
                                int inner_limit, KrylovStatus* st, const P2PDev pd, unsigned long long seq_in,
-                               double* rho_vec) {
+                               double* rho_vec, double* gram) {
     if (threadIdx.x != 0) return;
     if (ctl->stop) return;
     const int nblk = blk > 0 ? (k + blk - 1) / blk : 0;  // blocks of the blocked Gram-Schmidt sweep
+    const int mlast = blk > 0 ? k - (nblk - 1) * blk : 0;  // vectors in the last block = subtracted by the final pass
     if (seq_in != 0) {
         // ||q||^2 arrives through the mailboxes (posted by the final Gram-Schmidt pass of every rank); adding
         // in rank order gives the same bits on every rank, so all ranks take the same decisions below
         const int slot = (int)(seq_in % kMailSlots);
-        double tot = 0.0;
+        double tot[kBlkSums];
+        for (int c = 0; c < kBlkSums; ++c) tot[c] = 0.0;
         for (int q = 0; q < pd.nranks; ++q) {
             const double* rec = pd.mail_local + ((size_t)slot * pd.nranks + q) * kMailRec;
             const unsigned long long* tag = reinterpret_cast<const unsigned long long*>(rec + kBlkSums);
@@ -127,9 +130,9 @@ __global__ void k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, dou
             while (ld_acquire_sys_u64(tag) != seq_in) {
                 if (clock64() - t0 > pd.spin_cycles) { *pd.err = 1; break; }
             }
-            tot += __ldcv(rec);
+            for (int c = 0; c <= mlast; ++c) tot[c] += __ldcv(rec + c);  // ||q||^2 and the new Gram entries
         }
-        hcol[kBlkSums * nblk] = tot;
+        for (int c = 0; c <= mlast; ++c) hcol[kBlkSums * nblk + c] = tot[c];
     }
     // column k of H: h_1k..h_kk from the MGS sweep(s), h_{k+1,k} = ||q||
     double hh;
@@ -137,10 +140,15 @@ __global__ void k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, dou
         for (int j = 0; j < nblk; ++j) {
             const int m = (k - j * blk) < blk ? (k - j * blk) : blk;
             double hb[kBlkMax], cb[kBlkMax];
-            block_coefficients(hcol + kBlkSums * j, rho_vec ? rho_vec + j * blk : nullptr, m, hb, cb);
+            block_coefficients(hcol + kBlkSums * j, gram + (size_t)j * blk * kBlkMax, rho_vec ? rho_vec + j * blk : nullptr,
+                               m, hb, cb);
             for (int b = 0; b < m; ++b) R[nr + j * blk + b] = hb[b];
         }
         hh = hcol[kBlkSums * nblk];
+        // the vector finished by this iteration is stored as basis vector k; when it joins the last block (block not
+        // full yet) its Gram entries with that block's vectors were measured by the final pass: cache them
+        if (mlast < blk)
+            for (int a = 0; a < mlast; ++a) gram[(size_t)k * kBlkMax + a] = hcol[kBlkSums * nblk + 1 + a];
     } else {
         const double* h2 = hcol + (k + 1);
         for (int i = 0; i < k; ++i) R[nr + i] = reorth ? hcol[i] + h2[i] : hcol[i];
@@ -292,7 +300,7 @@ static int ws_alloc_vec(ak_krylov* ws, double** out) {
 // doubles of the device column `hcol`: two sweeps of k + 1 sums, or one record of kBlkSums per block of the
 // blocked sweep (blocks of >= 2) plus the final ||q||^2 record
 static inline int64_t hcol_len(int64_t k) {
-    const int64_t a = 2 * (k + 1) + 8, b = (int64_t)kBlkSums * ((k + 1) / 2 + 2);
+    const int64_t a = 2 * (k + 1) + 8, b = (int64_t)kBlkSums * ((k + 1) / 2 + 3);
     return a > b ? a : b;
 }
 
@@ -317,6 +325,7 @@ static int ws_grow_scalars(ak_krylov* ws, int64_t kcap_new) {
     AK_TRY(regrow(&ws->s, oldk, kcap_new));
     AK_TRY(regrow(&ws->z, oldk ? oldk + 1 : 0, kcap_new + 1));
     AK_TRY(regrow(&ws->rho, oldk ? oldk + 1 : 0, kcap_new + 1));
+    AK_TRY(regrow(&ws->gram, oldk ? (oldk + 1) * kBlkMax : 0, (kcap_new + 1) * kBlkMax));
     AK_TRY(regrow(&ws->hcol, oldk ? hcol_len(oldk) : 0, hcol_len(kcap_new)));
     ws->kcap = kcap_new;
     return AK_OK;
@@ -618,8 +627,9 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                     unsigned long long prev_seq = 0;
                     if (p2p) { pc.seq_out = ++c->p2p_seq; prev_seq = pc.seq_out; }
                     auto blk_rho = [&](int64_t j) -> const double* { return ws->rho + blk * j; };
-                    AK_TRY(launch_mgs_block(c, n, w, nullptr, 0, nullptr, nullptr, blk_ptr(0), blk_len(0), 0, hcol, stop,
-                                            p2p ? &pc : nullptr));
+                    auto blk_gram = [&](int64_t j) -> const double* { return ws->gram + blk * j * kBlkMax; };
+                    AK_TRY(launch_mgs_block(c, n, w, nullptr, 0, nullptr, nullptr, nullptr, blk_ptr(0), blk_len(0), 0, hcol,
+                                            stop, p2p ? &pc : nullptr));
                     for (int64_t j = 1; j < P; ++j) {
                         if (p2p) {
                             pc.seq_in = prev_seq;
@@ -627,8 +637,8 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                             pc.tin_store = hcol + kBlkSums * (j - 1);
                             prev_seq = pc.seq_out;
                         }
-                        AK_TRY(launch_mgs_block(c, n, w, blk_ptr(j - 1), blk, hcol + kBlkSums * (j - 1), blk_rho(j - 1),
-                                                blk_ptr(j), blk_len(j), 0, hcol + kBlkSums * j, stop,
+                        AK_TRY(launch_mgs_block(c, n, w, blk_ptr(j - 1), blk, hcol + kBlkSums * (j - 1), blk_gram(j - 1),
+                                                blk_rho(j - 1), blk_ptr(j), blk_len(j), 0, hcol + kBlkSums * j, stop,
                                                 p2p ? &pc : nullptr));
                     }
                     if (p2p) {
@@ -644,7 +654,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                         }
                     }
                     AK_TRY(launch_mgs_block(c, n, w, blk_ptr(P - 1), blk_len(P - 1), hcol + kBlkSums * (P - 1),
-                                            blk_rho(P - 1), nullptr, 0, 1, hcol + kBlkSums * P, stop,
+                                            blk_gram(P - 1), blk_rho(P - 1), nullptr, 0, 1, hcol + kBlkSums * P, stop,
                                             p2p ? &pc : nullptr));
                 } else if (fuse == AK_FUSE_NONE) {
                     for (int64_t i = 0; i < k; ++i) {
@@ -682,7 +692,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 k_gmres_givens<<<1, 32, 0, sm>>>(ws->ctl, (int)k, nr, ws->R, ws->c, ws->s, ws->z, hcol, reorth, blk,
                                                  want_hist ? ws->hist : nullptr, iter + k, (int)inner_limit,
                                                  &ws->status[slot], p2p ? c->p2p_dev() : P2PDev{}, givens_seq,
-                                                 raw ? ws->rho : nullptr); }
+                                                 raw ? ws->rho : nullptr, ws->gram); }
                 c->launches++;
                 AK_CUDA(cudaGetLastError());
                 AK_CUDA(cudaEventRecord(ws->ev[slot], sm));
@@ -947,7 +957,7 @@ AK_API int ak_krylov_destroy(ak_krylov* ws) {
     auto rel = [&](void* p) { if (p) cudaFreeAsync(p, sm); };
     for (double* p : ws->chunks) rel(p);
     rel((void*)ws->V_dev);
-    rel(ws->R); rel(ws->c); rel(ws->s); rel(ws->z); rel(ws->hcol); rel(ws->hist); rel(ws->rho);
+    rel(ws->R); rel(ws->c); rel(ws->s); rel(ws->z); rel(ws->hcol); rel(ws->hist); rel(ws->rho); rel(ws->gram);
     rel(ws->ctl);
     if (ws->status) cudaFreeHost(ws->status);
     for (int i = 0; i < kStatusSlots; ++i)
