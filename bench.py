@@ -178,7 +178,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=NX)
     ap.add_argument("--ny", type=int, default=NY_PER_GPU, help="rows per GPU")
-    ap.add_argument("--fuse", default="block4", choices=["none", "mgs", "full", "pair", "block4"])
+    ap.add_argument("--fuse", default="block4", choices=["none", "mgs", "full", "pair", "block4", "block8"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-reduce / send-recv instead of peer memory")
@@ -326,6 +326,9 @@ def main():
         dom, dom_bytes = 10, 80 * n
         dom_name = ("k_mgs_block<4,4> (w -= sum_b h_b v_b ; 4 projections <y_b,w> + 6 Gram entries <y_b,y_a>): "
                     "four Gram-Schmidt steps per pass")
+    elif args.fuse == "block8":
+        dom, dom_bytes = 10, 144 * n
+        dom_name = "k_mgs_block<8,8> (w -= sum_b c_b S_b ; 8 projections <S'_b,w>): eight Gram-Schmidt steps per pass"
     elif args.fuse == "none":
         dom, dom_bytes = 2, 24 * n
         dom_name = "k_mgs_step<AXPY> (w -= h_i v_i)"
@@ -362,7 +365,7 @@ def main():
         ubuf = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_double)), shape=(n,))
         o = A.default_newton_opts(max_niter=0)  # `outer <= max_niter` admits exactly one Newton step
         o.krylov = A.default_krylov_opts(restart=1, itmax=ITMAX, rtol=1e-30, atol=0.0,
-                                         fuse={"none": 0, "mgs": 1, "full": 2, "pair": 3, "block4": 4}[args.fuse])
+                                         fuse={"none": 0, "mgs": 1, "full": 2, "pair": 3, "block4": 4, "block8": 5}[args.fuse])
         o.krylov_rtol_override = 1
         st = A.ak_newton_stats()
         prob_h = nk.bratu2d_.problem(u, (dx, dy, LAMBDA, gny, gy0))  # coef is allocated by the entry point

@@ -243,8 +243,10 @@ enum {
                           coefficient of y_b follows as <y_b,w> - <y_a,w><y_b,y_a>, which is
                           algebraically the modified Gram-Schmidt value (24n bytes per step
                           instead of 32n); falls back to FULL with reorthogonalization    */
-    AK_FUSE_BLOCK4 = 4 /* same with four steps per sweep: 4 projections + 6 Gram entries per
-                          pass, h_b = <y_b,w> - sum_{a<b} h_a <y_b,y_a> (20n bytes per step) */
+    AK_FUSE_BLOCK4 = 4,/* same with four steps per sweep: h_b = <y_b,w> - sum_{a<b} h_a <y_b,y_a>
+                          (20n bytes per step); the Gram entries <y_b,y_a> of a block are measured once,
+                          by the final pass of the iteration that finishes y_b, and cached          */
+    AK_FUSE_BLOCK8 = 5 /* eight steps per sweep (18n bytes per step)                                */
     /* PAIR and BLOCK4 keep the Krylov basis UN-NORMALISED: iteration k works in place on basis slot k, whose
      * finished content is the stored vector rho_k v_k (rho_k = Hbis); gmres!'s `V[k+1] = w / Hbis` is never
      * materialised, the scales enter the Gram-Schmidt coefficients and the JVP divides its result by rho_k

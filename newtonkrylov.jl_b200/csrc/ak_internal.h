@@ -44,7 +44,7 @@ void set_error(const char* fmt, ...);
 //   halo : 2 parities x {lo, hi} x halo_cap doubles       — boundary rows pushed by the neighbours
 constexpr int kMaxPeers = 8;
 constexpr int kMailSlots = 8;
-constexpr int kBlkMax = 4;    // Gram-Schmidt steps per sweep over w (block size of the blocked sweep)
+constexpr int kBlkMax = 8;    // most Gram-Schmidt steps per sweep over w (largest block of the blocked sweep)
 // sums of one pass: up to kBlkMax projections <S_b, w>; final pass: ||w||^2 and the Gram entries <S_a, w_new> of the
 // vector it finishes with the vectors of its own block (cached: they do not change in later iterations)
 constexpr int kBlkSums = kBlkMax + 1;

@@ -167,8 +167,13 @@ struct BlockP2P {     // fused collective of the blocked pass (all zero / null w
 };
 constexpr int kRedFinal = kBlkMax + 1;
 
+// resident blocks per SM the register budget is sized for: wide passes hold up to 16 vectors of 4 doubles per thread
+constexpr int mgs_block_min_blocks(int nax, int nred) {
+    return (nred == kBlkMax + 1) ? (nax > 4 ? 1 : 2) : ((nax + nred > 8 || nred > 6) ? 1 : 2);
+}
+
 template <int NAX, int NRED, bool P2P>
-__global__ void __launch_bounds__(kThreads, 2) k_mgs_block(double* __restrict__ w, const BlkPtrs bp,
+__global__ void __launch_bounds__(kThreads, mgs_block_min_blocks(NAX, NRED)) k_mgs_block(double* __restrict__ w, const BlkPtrs bp,
                                                            const double* __restrict__ tin,
                                                            const double* __restrict__ gram_in,
                                                            const double* __restrict__ rho_in, double* __restrict__ out,
@@ -319,7 +324,7 @@ static int dispatch_block(int nax, int nred, Ctx* ctx, int64_t n, double* w, con
     if (nax == A && nred == R) {
         // a pass either projects (first pass: nothing to subtract; later passes: any block) or is the final one
         // (projection passes subtract nothing, a full pair or a full block; the final pass subtracts 1..kBlkMax)
-        if constexpr (R == kRedFinal ? (A >= 1) : (A == 0 || A == 2 || A == kBlkMax))
+        if constexpr (R == kRedFinal ? (A >= 1) : (A == 0 || A == 2 || A == 4 || A == kBlkMax))
             return launch_mgs_block_t<A, R>(ctx, n, w, bp, tin, gram_in, rho_in, out, stop, vec, p2p, pp, cls);
     }
     if constexpr (R < kRedFinal) {

@@ -432,7 +432,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     const int restart = o->restart, reorth = o->reorthogonalization;
     int fuse = o->fuse;
     // the blocked sweeps have no second-sweep variant
-    if ((fuse == AK_FUSE_PAIR || fuse == AK_FUSE_BLOCK4) && reorth) fuse = AK_FUSE_FULL;
+    if ((fuse == AK_FUSE_PAIR || fuse == AK_FUSE_BLOCK4 || fuse == AK_FUSE_BLOCK8) && reorth) fuse = AK_FUSE_FULL;
     const bool flexible = (ws->algo == AK_ALGO_FGMRES);
     const bool precond = (o->precond_n != AK_PRECOND_NONE);
     const bool lprec = (o->precond_m != AK_PRECOND_NONE);  // q = M A N v_k, r0 = M (b - A x): Krylov.jl solver.q
@@ -440,7 +440,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     if ((flexible || precond || lprec) && fuse > AK_FUSE_MGS) fuse = AK_FUSE_MGS;
     if ((flexible || precond) && !ws->pbuf) AK_TRY(ws_alloc_vec(ws, &ws->pbuf));
     if (lprec && !ws->qbuf) AK_TRY(ws_alloc_vec(ws, &ws->qbuf));
-    const int blk = fuse == AK_FUSE_PAIR ? 2 : (fuse == AK_FUSE_BLOCK4 ? kBlkMax : 0);  // Gram-Schmidt steps per sweep
+    const int blk = fuse == AK_FUSE_PAIR ? 2 : (fuse == AK_FUSE_BLOCK4 ? 4 : (fuse == AK_FUSE_BLOCK8 ? 8 : 0));  // steps per sweep
     const bool pair = blk > 0;
     // Blocked sweeps keep the basis un-normalised: iteration k works in place on basis slot k, whose finished content
     // IS the stored vector (scale rho[k] = Hbis); the JVP divides by rho[k-1] in registers.  No w buffers, no

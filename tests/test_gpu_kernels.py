@@ -415,7 +415,7 @@ def test_stencil_kernels_stay_inside_their_vectors(nk, ctx, oracle, name, make):
     assert np.all(np.isnan(h[mask])), "a kernel wrote outside its vector"
 
 
-@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4"])
+@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4", "block8"])
 def test_gmres_reads_only_its_operands(nk, ctx, oracle, fuse):
     """A whole GMRES solve (7 iterations: ragged blocks of the blocked sweep) with u and b inside NaN guard bands."""
     d = P.bratu2d(33, 19)

@@ -43,7 +43,7 @@ LIN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4"])
+@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4", "block8"])
 @pytest.mark.parametrize("name,make,kw", LIN_CASES, ids=[c[0] for c in LIN_CASES])
 def test_gmres_matches_oracle(nk, ctx, oracle, name, make, kw, fuse):
     d = make()
@@ -61,7 +61,7 @@ def test_gmres_matches_oracle(nk, ctx, oracle, name, make, kw, fuse):
     assert np.max(np.abs(h - hr)) <= 1e-10 * hr[0]
 
 
-@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4"])
+@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4", "block8"])
 @pytest.mark.parametrize("opts", [dict(restart=True, itmax=45), dict(restart=True, reorthogonalization=True, itmax=33),
                                   dict(reorthogonalization=True), dict(itmax=7), dict(restart=True)],
                          ids=["restart45", "restart_reorth33", "reorth", "itmax7", "restart_conv"])
@@ -245,7 +245,7 @@ def test_newton_matches_oracle(nk, ctx, oracle, name, make, kw, native):
     assert_newton_parity(u, r, hist, sens)
 
 
-@pytest.mark.parametrize("fuse", ["none", "full", "pair", "block4"])
+@pytest.mark.parametrize("fuse", ["none", "full", "pair", "block4", "block8"])
 def test_newton_fusion_levels_agree(nk, ctx, oracle, fuse):
     d = P.generic(P.bratu2d(40))
     u, r, hist, sens = newton_both(nk, ctx, oracle, d, True, krylov_kwargs=dict(fuse=fuse))

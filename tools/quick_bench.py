@@ -44,7 +44,7 @@ ws = nk.krylov_workspace("gmres", nk.KrylovConstructor(res), memory=20)
 J = nk.JacobianOperator(nk.bratu2d_, res, u, (dx, dx, 3.5), coef=coef)
 lib.ak_residual(h, C.byref(prob), P(u), P(res), None)
 b = res.copy()
-for fuse in ("none", "mgs", "full", "pair", "block4"):
+for fuse in ("none", "mgs", "full", "pair", "block4", "block8"):
     for _ in range(2):
         ctx.sync(); ctx.launch_count(reset=True)
         ctx.timer_start()
