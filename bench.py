@@ -178,7 +178,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=NX)
     ap.add_argument("--ny", type=int, default=NY_PER_GPU, help="rows per GPU")
-    ap.add_argument("--fuse", default="block4", choices=["none", "mgs", "full", "pair", "block4", "block8"])
+    ap.add_argument("--fuse", default="block8", choices=["none", "mgs", "full", "pair", "block4", "block8"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-reduce / send-recv instead of peer memory")

@@ -267,7 +267,7 @@ function krylov_workspace(algo::Symbol, res::B200Vector; memory = 20, max_basis 
 end
 solution(ws::Workspace) = ccall((:ak_krylov_x, lib), Ptr{Float64}, (Ptr{Cvoid},), ws.h)
 function krylov_solve!(ws::Workspace, J::JacobianOperator, b::B200Vector; atol = √eps(Float64), rtol = √eps(Float64),
-                       itmax = 0, restart = false, reorthogonalization = false, history = false, fuse = 4,
+                       itmax = 0, restart = false, reorthogonalization = false, history = false, fuse = 5,
                        M = nothing, N = nothing, ldiv = false)
     (N isa TridiagonalLU || M isa TridiagonalLU) && !ldiv && error("ilu(J) is applied with ldiv = true (examples/bratu.jl:126)")
     # caller-supplied preconditioners travel as (object, n) behind a rooted Ref for the duration of the solve
