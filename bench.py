@@ -19,8 +19,9 @@ e2e    = the same metric through the host-buffer entry point ak_newton_solve_hos
          caller holding an Array{Float64} calls): every step copies u host->device from pinned
          memory, allocates the Krylov workspace like the reference does per newton_krylov! call,
          runs the same Newton step and copies u back.
-roofline = the dominant kernel (pair-wise modified-Gram-Schmidt pass, 48n bytes per launch = 24n per
-         Gram-Schmidt step; with --fuse mgs/full the axpy_i + dot_{i+1} kernel, 32n) timed live with CUDA events
+roofline = the dominant kernel (full pass of the blocked modified-Gram-Schmidt sweep: 144n bytes per launch = 18n per
+         Gram-Schmidt step with --fuse block8; 80n / 48n with block4 / pair; with --fuse mgs/full the axpy_i + dot_{i+1}
+         kernel, 32n) timed live with CUDA events
          inside the timed region (library profiler); traffic from the committed ncu --set full capture.
 cpu_baseline = the CPU oracle (oracle/nk_oracle.c, a port of the reference algorithm) on the host
          cores, one GMRES(20) restart cycle of the same solve.
