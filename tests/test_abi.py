@@ -43,6 +43,9 @@ int main(void) {
          sizeof(ak_newton_opts), sizeof(ak_newton_stats));
   printf("%zu %zu %zu %zu\n", offsetof(ak_problem, dx), offsetof(ak_problem, un), offsetof(ak_newton_opts, krylov),
          offsetof(ak_newton_stats, t_seconds));
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", offsetof(ak_problem, user_residual), offsetof(ak_problem, user_data),
+         offsetof(ak_krylov_opts, precond_m), offsetof(ak_krylov_opts, n_apply), offsetof(ak_krylov_opts, m_user),
+         offsetof(ak_newton_opts, krylov_rtol_override), offsetof(ak_newton_opts, verbose));
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as td:
@@ -54,8 +57,13 @@ int main(void) {
     sizes = [int(x) for x in out]
     assert sizes[:5] == [C.sizeof(A.ak_problem), C.sizeof(A.ak_krylov_opts), C.sizeof(A.ak_krylov_stats),
                          C.sizeof(A.ak_newton_opts), C.sizeof(A.ak_newton_stats)]
-    assert sizes[5:] == [A.ak_problem.dx.offset, A.ak_problem.un.offset, A.ak_newton_opts.krylov.offset,
-                         A.ak_newton_stats.t_seconds.offset]
+    assert sizes[5:9] == [A.ak_problem.dx.offset, A.ak_problem.un.offset, A.ak_newton_opts.krylov.offset,
+                          A.ak_newton_stats.t_seconds.offset]
+    # ABI 3: caller-supplied residual / tangent callbacks and the preconditioner hooks
+    assert sizes[9:] == [A.ak_problem.user_residual.offset, A.ak_problem.user_data.offset,
+                         A.ak_krylov_opts.precond_m.offset, A.ak_krylov_opts.n_apply.offset,
+                         A.ak_krylov_opts.m_user.offset, A.ak_newton_opts.krylov_rtol_override.offset,
+                         A.ak_newton_opts.verbose.offset]
 
 
 def test_header_is_plain_c_and_cites_the_reference():
