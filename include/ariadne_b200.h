@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AK_ABI_VERSION 3
+#define AK_ABI_VERSION 4
 
 /* ---- status / flags ------------------------------------------------------- */
 enum {
@@ -41,7 +41,10 @@ enum {
     AK_ERR_NCCL = -3,
     AK_ERR_NOMEM = -4,
     AK_ERR_UNSUPPORTED = -5,
-    AK_ERR_USER = -6           /* a caller-supplied callback returned non-zero */
+    AK_ERR_USER = -6,          /* a caller-supplied callback returned non-zero */
+    AK_ERR_PEER = -7           /* a peer-memory (NVLink mailbox) wait timed out: a rank fell out of step.  The peer path
+                                  of the context stays latched off (every solve returns this code) until
+                                  ak_comm_use_p2p is called again on every rank                                        */
 };
 /* positive numerical flags (bit set) */
 enum {
@@ -298,6 +301,11 @@ int ak_krylov_solve(ak_krylov* ws, const ak_problem* p, const double* u, const d
                     double* hist_host, int64_t hist_cap);
 /* workspace.x: device pointer to the solution of the last solve */
 double* ak_krylov_x(ak_krylov* ws);
+/* Inspection of the Krylov basis after a GMRES solve (diagnostics; the loss-of-orthogonality tests): the STORED vector
+ * of basis vector i (device pointer, n doubles) and its scale, v_i = stored / scale.  scale = 1 when the basis is kept
+ * normalised like Krylov.jl's V[i]; the blocked sweeps keep rho_i v_i.  count_out: vectors the workspace holds.
+ * stored_dev / scale_host / count_out may each be NULL.                                                            */
+int ak_krylov_basis(ak_krylov* ws, int64_t i, double** stored_dev, double* scale_host, int64_t* count_out);
 /* One application of a native preconditioner object built from J = (p, u): `mul!(y, P, x)` for
  * AK_PRECOND_INNER_GMRES / AK_PRECOND_JACOBI, `ldiv!(y, P, x)` for AK_PRECOND_TRIDIAG_LU — what Krylov.jl calls
  * on the object returned by `N(J)` / `M(J)` (src/Ariadne.jl:324-329) when Krylov.jl itself drives the solve. */

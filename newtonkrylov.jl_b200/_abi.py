@@ -5,11 +5,11 @@ struct layouts without touching the CUDA library.
 """
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # status / flags
 AK_OK = 0
-AK_ERR_CUDA, AK_ERR_ARG, AK_ERR_NCCL, AK_ERR_NOMEM, AK_ERR_UNSUPPORTED, AK_ERR_USER = -1, -2, -3, -4, -5, -6
+AK_ERR_CUDA, AK_ERR_ARG, AK_ERR_NCCL, AK_ERR_NOMEM, AK_ERR_UNSUPPORTED, AK_ERR_USER, AK_ERR_PEER = -1, -2, -3, -4, -5, -6, -7
 AK_FLAG_NOT_SOLVED, AK_FLAG_BREAKDOWN, AK_FLAG_INCONSISTENT, AK_FLAG_NAN = 1, 2, 4, 8
 
 # problem kinds

@@ -73,6 +73,7 @@ SIGNATURES = {
     "ak_krylov_solve": (C.c_int, [_vp, C.POINTER(A.ak_problem), _vp, _vp, C.POINTER(A.ak_krylov_opts),
                                   C.POINTER(A.ak_krylov_stats), _dp, C.c_int64]),
     "ak_krylov_x": (_vp, [_vp]),
+    "ak_krylov_basis": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp), _dp, A.c_int64_p]),
     "ak_precond_apply": (C.c_int, [_vp, C.POINTER(A.ak_problem), _vp, C.c_int32, C.c_int32, _vp, _vp]),
     "ak_newton_default_opts": (None, [C.POINTER(A.ak_newton_opts)]),
     "ak_newton_solve": (C.c_int, [_vp, C.POINTER(A.ak_problem), _vp, _vp, C.POINTER(A.ak_newton_opts),

@@ -133,6 +133,9 @@ struct ProfScope {
 // --- comm (context.cu) --------------------------------------------------------
 // In-stream sum all-reduce of `count` device doubles (no-op on one rank).
 int allreduce_sum(Ctx* ctx, double* dev, int count);
+// Make a local success/failure verdict collective: *rc becomes an error on every rank when it is one on any rank
+// (host-synchronising; used where ranks must take the same control-flow branch, e.g. basis growth).  No-op on one rank.
+int collective_verdict(Ctx* ctx, int* rc);
 // Fill ctx->halo_lo / halo_hi with the neighbours' boundary rows of `v` (nx*ny slab).
 // Returns pointers to use as ghost rows (nullptr => implicit zero).
 int exchange_halo_rows(Ctx* ctx, const double* v, int64_t nx, int64_t ny, int32_t bc,
@@ -185,9 +188,10 @@ struct BlockComm {
 int launch_mgs_block(Ctx* ctx, int64_t n, double* w, const double* const* va, int nax, const double* tin,
                      const double* gram_in, const double* rho_in, const double* const* ya, int ny, int want_sumsq,
                      double* out, const int* stop, const BlockComm* pc);
-// x <- x + sum_i y[i] V[i]  (sequential axpy order), optionally u <- u - x fused (single pass)
+// x <- [x +] sum_{i<k} y[i] V[i]  (sum formed from zero in the sequential axpy order of gmres!, then stored or
+// added to x); k = *k_dev when k_dev != null (device-resident pass length), else k_host
 int launch_basis_combine(Ctx* ctx, int64_t n, double* x, const double* const* V_dev, const double* y_dev,
-                         int k, int zero_x_first);
+                         const int* k_dev, int k_host, int accumulate);
 
 // --- stencil.cu -----------------------------------------------------------------
 // res <- F(u); if sumsq_dev != null also *sumsq_dev = ||res||^2 (global when comm is set)
@@ -203,6 +207,10 @@ struct JvpFusion {
     bool raw = false;
     const double* dot_with = nullptr;   // V[0]
     double* dot_dev = nullptr;
+    // restart residual of gmres! (w <- b - A x: mul!(w, A, x); kaxpby!(n, one, b, -one, w)) in the same pass:
+    // out = rhs_minus - J v, and (sumsq_dev != null, exclusive with dot_with) *sumsq_dev = ||out||^2
+    const double* rhs_minus = nullptr;
+    double* sumsq_dev = nullptr;
     const int* stop_flag = nullptr;
     // ghost rows already delivered by the neighbours through peer memory (skips the NCCL exchange)
     bool halo_given = false;

@@ -9,6 +9,8 @@
 // All kernels stream 256-bit vectors (LDG.E.256) when the operands are 32-byte aligned
 // and fall back to scalar accesses otherwise.  Reductions are deterministic: warp
 // butterflies, per-block partials, last block sums partials in index order.
+#include <atomic>
+
 #include "ak_internal.h"
 #include "common.cuh"
 
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, mgs_block_min_blocks(NAX, NRED)) k_m
     if (NAX >= 1) {
         double t[kBlkSums];
         if (P2P && pp.seq_in != 0) {
-            mail_wait_sum(pp.pd, pp.seq_in, t, NAX, shm);
+            mail_wait_sum(pp.pd, pp.seq_in, t, NAX, shm, const_cast<int*>(stop));
             if (blockIdx.x == 0 && threadIdx.x == 0 && pp.tin_store != nullptr) {
 #pragma unroll
                 for (int c = 0; c < NAX; ++c) pp.tin_store[c] = t[c];
@@ -293,13 +295,17 @@ template <int NAX, int NRED>
 static int launch_mgs_block_t(Ctx* ctx, int64_t n, double* w, const BlkPtrs& bp, const double* tin,
                               const double* gram_in, const double* rho_in, double* out, const int* stop, bool vec,
                               bool p2p, const BlockP2P& pp, int cls) {
-    static int occ[2] = {0, 0};  // resident blocks per SM of this instantiation (queried once)
+    // resident blocks per SM of this instantiation (a property of the sm_100a binary: the same on every B200 of
+    // the box, so one process-wide cache per instantiation is enough; atomic because contexts may live on threads)
+    static std::atomic<int> occ_cache[2] = {{0}, {0}};
+    int occ[2] = {occ_cache[0].load(std::memory_order_relaxed), occ_cache[1].load(std::memory_order_relaxed)};
     if (occ[p2p] == 0) {
         int nb = 0;
         cudaError_t e = p2p ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mgs_block<NAX, NRED, true>, kThreads, 0)
                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mgs_block<NAX, NRED, false>, kThreads, 0);
         AK_CUDA(e);
         occ[p2p] = nb < 1 ? 1 : (nb > 4 ? 4 : nb);
+        occ_cache[p2p].store(occ[p2p], std::memory_order_relaxed);
     }
     int64_t need = (n + (int64_t)kThreads * 4 - 1) / ((int64_t)kThreads * 4);
     const int64_t cap = (int64_t)ctx->num_sms * occ[p2p];  // one wave of resident blocks, grid-stride
@@ -324,7 +330,11 @@ static int dispatch_block(int nax, int nred, Ctx* ctx, int64_t n, double* w, con
     if (nax == A && nred == R) {
         // a pass either projects (first pass: nothing to subtract; later passes: any block) or is the final one
         // (projection passes subtract nothing, a full pair or a full block; the final pass subtracts 1..kBlkMax)
-        if constexpr (R == kRedFinal ? (A >= 1) : (A == 0 || A == 2 || A == 4 || A == kBlkMax))
+        // a second (re-orthogonalisation) sweep also subtracts a ragged last block while it projects on block 0 again:
+        // (A, A) when the whole basis is one block, (A <= R, R = 2, 4, kBlkMax) otherwise
+        if constexpr (R == kRedFinal ? (A >= 1)
+                                     : (A == 0 || A == 2 || A == 4 || A == kBlkMax || R == A ||
+                                        ((R == 2 || R == 4 || R == kBlkMax) && A <= R)))
             return launch_mgs_block_t<A, R>(ctx, n, w, bp, tin, gram_in, rho_in, out, stop, vec, p2p, pp, cls);
     }
     if constexpr (R < kRedFinal) {
@@ -478,13 +488,18 @@ int launch_divcopy_dev(Ctx* ctx, int64_t n, double* y, const double* x, const do
 }
 
 // -----------------------------------------------------------------------------------
-// x <- [x +] sum_{i<k} y[i] V[i]   in the sequential axpy order of gmres! step 10
-// (for i = 1:k  kaxpy!(n, y[i], V[i], xr)).  Algorithmic bytes 8n(k+1) (+8n when accumulating).
+// xr = sum_{i<k} y[i] V[i] in the sequential axpy order of gmres! step 10 (for i = 1:k kaxpy!(n, y[i], V[i], xr)),
+// formed in registers from zero; then  x <- xr  (accumulate = 0)  or  x <- x + xr  (accumulate = 1: the restart
+// update `kaxpy!(n, one, xr, x)` without materialising xr).  k and y live in device memory (k_dev may be null: k_host),
+// so the launch needs no host knowledge of how far the pass got.
+// Algorithmic bytes 8n(k+1), +8n when accumulating.
 // -----------------------------------------------------------------------------------
 template <bool VEC>
 __global__ void __launch_bounds__(kThreads) k_basis_combine(double* __restrict__ x, const double* const* __restrict__ V,
-                                                            const double* __restrict__ y, int k, int zero_first,
-                                                            int64_t n) {
+                                                            const double* __restrict__ y, const int* __restrict__ k_dev,
+                                                            int k_host, int accumulate, int64_t n) {
+    const int k = k_dev != nullptr ? *k_dev : k_host;
+    if (k <= 0 && accumulate) return;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
     if (VEC) {
@@ -492,7 +507,6 @@ __global__ void __launch_bounds__(kThreads) k_basis_combine(double* __restrict__
         for (int64_t i = tid; i < n4; i += nth) {
             const int64_t j = i << 2;
             d4 acc = {0, 0, 0, 0};
-            if (!zero_first) acc = ld4(x + j);
             int c = 0;
             for (; c + 1 < k; c += 2) {  // two basis vectors in flight
                 const d4 v0 = ld4_stream(V[c] + j), v1 = ld4_stream(V[c + 1] + j);
@@ -505,33 +519,37 @@ __global__ void __launch_bounds__(kThreads) k_basis_combine(double* __restrict__
                 const double y0 = y[c];
                 acc.x = fma(y0, v0.x, acc.x); acc.y = fma(y0, v0.y, acc.y); acc.z = fma(y0, v0.z, acc.z); acc.w = fma(y0, v0.w, acc.w);
             }
+            if (accumulate) {
+                const d4 xo = ld4(x + j);
+                acc.x = xo.x + acc.x; acc.y = xo.y + acc.y; acc.z = xo.z + acc.z; acc.w = xo.w + acc.w;
+            }
             st4(x + j, acc);
         }
         const int64_t j = (n4 << 2) + tid;
         if (j < n) {
-            double acc = zero_first ? 0.0 : x[j];
+            double acc = 0.0;
             for (int c = 0; c < k; ++c) acc = fma(y[c], V[c][j], acc);
-            x[j] = acc;
+            x[j] = accumulate ? x[j] + acc : acc;
         }
     } else {
         for (int64_t j = tid; j < n; j += nth) {
-            double acc = zero_first ? 0.0 : x[j];
+            double acc = 0.0;
             for (int c = 0; c < k; ++c) acc = fma(y[c], V[c][j], acc);
-            x[j] = acc;
+            x[j] = accumulate ? x[j] + acc : acc;
         }
     }
 }
 
-int launch_basis_combine(Ctx* ctx, int64_t n, double* x, const double* const* V_dev, const double* y_dev, int k,
-                         int zero_x_first) {
+int launch_basis_combine(Ctx* ctx, int64_t n, double* x, const double* const* V_dev, const double* y_dev,
+                         const int* k_dev, int k_host, int accumulate) {
     if (n <= 0) return AK_OK;
     const int blocks = stream_blocks(ctx, n, 4);
     ProfScope prof(ctx, PK_COMBINE);
     // basis vectors come from the workspace arena (256-byte aligned); x may be caller memory
     if (aligned32(x))
-        k_basis_combine<true><<<blocks, kThreads, 0, ctx->stream>>>(x, V_dev, y_dev, k, zero_x_first, n);
+        k_basis_combine<true><<<blocks, kThreads, 0, ctx->stream>>>(x, V_dev, y_dev, k_dev, k_host, accumulate, n);
     else
-        k_basis_combine<false><<<blocks, kThreads, 0, ctx->stream>>>(x, V_dev, y_dev, k, zero_x_first, n);
+        k_basis_combine<false><<<blocks, kThreads, 0, ctx->stream>>>(x, V_dev, y_dev, k_dev, k_host, accumulate, n);
     ctx->launches++;
     AK_CUDA(cudaGetLastError());
     return AK_OK;

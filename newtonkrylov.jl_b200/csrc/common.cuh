@@ -172,7 +172,10 @@ AK_DEV void mail_post(const P2PDev& pd, unsigned long long seq, const double* va
 }
 // Whole block: wait until every rank's record `seq` has arrived in the local mailbox and add them in rank
 // order (bit-identical on every rank).  Result in out[0..ns) for all threads.  `shm` >= kMaxPeers * kBlkSums doubles.
-AK_DEV void mail_wait_sum(const P2PDev& pd, unsigned long long seq, double (&out)[kBlkSums], int ns, double* shm) {
+// A record that never arrives (a peer fell out of step) raises the mapped error flag AND the device `stop` flag of the
+// solve (`stop_w`, may be null), so that every later kernel of the solve is a no-op instead of spinning again.
+AK_DEV void mail_wait_sum(const P2PDev& pd, unsigned long long seq, double (&out)[kBlkSums], int ns, double* shm,
+                          int* stop_w = nullptr) {
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
     const int slot = (int)(seq % kMailSlots);
     if (tid < pd.nranks) {
@@ -182,6 +185,7 @@ AK_DEV void mail_wait_sum(const P2PDev& pd, unsigned long long seq, double (&out
         while (ld_acquire_sys_u64(tag) != seq) {
             if (clock64() - t0 > pd.spin_cycles) {  // a peer never produced this record: flag it, do not hang
                 *pd.err = 1;
+                if (stop_w != nullptr) *stop_w = 1;
                 break;
             }
         }

@@ -119,6 +119,21 @@ int allreduce_sum(Ctx* ctx, double* dev, int count) {
     return AK_OK;
 }
 
+int collective_verdict(Ctx* ctx, int* rc) {
+    if (ctx->nranks <= 1) return AK_OK;
+    const double mine = (*rc != AK_OK) ? 1.0 : 0.0;
+    double any = 0.0;
+    AK_CUDA(cudaMemcpyAsync(ctx->dscal + 61, &mine, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    AK_TRY(allreduce_sum(ctx, ctx->dscal + 61, 1));
+    AK_CUDA(cudaMemcpyAsync(&any, ctx->dscal + 61, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    AK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (any > 0.0 && *rc == AK_OK) {
+        set_error("another rank could not grow its Krylov basis");
+        *rc = AK_ERR_NOMEM;
+    }
+    return AK_OK;
+}
+
 int exchange_halo_rows(Ctx* ctx, const double* v, int64_t nx, int64_t ny, int32_t bc, const double** lo,
                        const double** hi) {
     const int P = ctx->nranks, r = ctx->rank;
@@ -524,6 +539,7 @@ AK_API int ak_comm_use_p2p(ak_ctx* ctx, int on) {
     AK_REQUIRE(!on || ctx->c.p2p_block != nullptr, "ak_comm_use_p2p: peer memory was never mapped");
     AK_CUDA(cudaStreamSynchronize(ctx->c.stream));
     ctx->c.p2p_on = (on != 0);
+    if (ctx->c.p2p_err) *ctx->c.p2p_err = 0;  // clears the time-out latch (collective by contract: all ranks call this)
     return AK_OK;
 }
 

@@ -29,15 +29,16 @@ struct KrylovCtl {  // device-resident control block
 };
 struct KrylovStatus {  // pinned host ring, written by the scalar kernels
     double rNorm, Hbis, beta;
-    int iter, stop, solved, breakdown, zerocurv, pad;
+    int iter, stop, solved, breakdown, zerocurv, inconsistent;
 };
-constexpr int kStatusRing = 8;   // per-iteration records; slot kStatusRing is the pass prologue
+constexpr int kStatusRing = 8;   // per-iteration records; slot kStatusRing is the pass prologue, kStatusRing + 1 the
+                                 // record of the back-substitution (inconsistent flag, read once at the end of a solve)
 // How many iterations the host launches ahead of the last verdict it has read.  Kernels of iterations after a stop
 // are no-ops on the device, so depth only costs a few empty launches at the end of a pass; with short kernels
 // (vectors that fit in L2) a depth of 1 leaves the stream empty while the host wakes up from the event.
 constexpr int kSpecDepth = 3;
 static_assert(kSpecDepth < kStatusRing, "the status ring must outlive the speculation window");
-constexpr int kStatusSlots = kStatusRing + 1;
+constexpr int kStatusSlots = kStatusRing + 2;
 
 }  // namespace ak
 
@@ -63,6 +64,8 @@ struct ak_krylov {
     // scalars (device)
     int64_t kcap = 0;  // columns of R that fit
     double *R = nullptr, *c = nullptr, *s = nullptr, *z = nullptr, *hcol = nullptr, *hist = nullptr;
+    bool last_raw = false;    // the last GMRES solve kept the basis un-normalised (stored V[i] = rho[i] v_i)
+    double* ycoef = nullptr;  // solution of R y = z (device back-substitution), already divided by rho for the combine
     double* rho = nullptr;  // un-normalised basis (blocked sweeps): stored V[i] = rho[i] * v_i
     double* gram = nullptr; // blocked sweeps: <V[i], V[a]> for the earlier vectors a of V[i]'s own block (kBlkMax per i)
     int64_t hist_cap = 0;
@@ -114,9 +117,21 @@ __global__ void k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, dou
                                int inner_limit, KrylovStatus* st, const P2PDev pd, unsigned long long seq_in,
                                double* rho_vec, double* gram) {
     if (threadIdx.x != 0) return;
-    if (ctl->stop) return;
+    if (ctl->stop) {
+        // iterations queued behind the verdict that ended the pass repeat that verdict, so that the host can never read
+        // a stale record of an earlier lap of the ring as "keep going" (it reads the records in order)
+        st->rNorm = ctl->rNorm;
+        st->Hbis = ctl->Hbis;
+        st->iter = ctl->inner_iter;
+        st->solved = ctl->solved;
+        st->breakdown = ctl->breakdown;
+        st->stop = 1;
+        return;
+    }
     const int nblk = blk > 0 ? (k + blk - 1) / blk : 0;  // blocks of the blocked Gram-Schmidt sweep
     const int mlast = blk > 0 ? k - (nblk - 1) * blk : 0;  // vectors in the last block = subtracted by the final pass
+    const int nsweep = reorth ? 2 : 1;
+    const int rec_final = nsweep * nblk;  // record of the final pass: ||q||^2 and the new Gram entries
     if (seq_in != 0) {
         // ||q||^2 arrives through the mailboxes (posted by the final Gram-Schmidt pass of every rank); adding
         // in rank order gives the same bits on every rank, so all ranks take the same decisions below
@@ -127,28 +142,38 @@ __global__ void k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, dou
             const double* rec = pd.mail_local + ((size_t)slot * pd.nranks + q) * kMailRec;
             const unsigned long long* tag = reinterpret_cast<const unsigned long long*>(rec + kBlkSums);
             const long long t0 = clock64();
+            bool timed_out = false;
             while (ld_acquire_sys_u64(tag) != seq_in) {
-                if (clock64() - t0 > pd.spin_cycles) { *pd.err = 1; break; }
+                if (clock64() - t0 > pd.spin_cycles) { *pd.err = 1; timed_out = true; break; }
+            }
+            if (timed_out) {  // a peer fell out of step: end the pass here, the host reports the error
+                ctl->stop = 1;
+                st->rNorm = ctl->rNorm; st->Hbis = ctl->Hbis; st->iter = ctl->inner_iter;
+                st->solved = 0; st->breakdown = 0; st->stop = 1;
+                return;
             }
             for (int c = 0; c <= mlast; ++c) tot[c] += __ldcv(rec + c);  // ||q||^2 and the new Gram entries
         }
-        for (int c = 0; c <= mlast; ++c) hcol[kBlkSums * nblk + c] = tot[c];
+        for (int c = 0; c <= mlast; ++c) hcol[kBlkSums * rec_final + c] = tot[c];
     }
     // column k of H: h_1k..h_kk from the MGS sweep(s), h_{k+1,k} = ||q||
     double hh;
-    if (blk > 0) {  // raw sums of the blocked sweep (one record of kBlkSums per block), then ||q||^2
-        for (int j = 0; j < nblk; ++j) {
-            const int m = (k - j * blk) < blk ? (k - j * blk) : blk;
-            double hb[kBlkMax], cb[kBlkMax];
-            block_coefficients(hcol + kBlkSums * j, gram + (size_t)j * blk * kBlkMax, rho_vec ? rho_vec + j * blk : nullptr,
-                               m, hb, cb);
-            for (int b = 0; b < m; ++b) R[nr + j * blk + b] = hb[b];
+    if (blk > 0) {  // raw sums of the blocked sweep(s) (one record of kBlkSums per block and sweep), then ||q||^2
+        for (int sw = 0; sw < nsweep; ++sw) {
+            for (int j = 0; j < nblk; ++j) {
+                const int m = (k - j * blk) < blk ? (k - j * blk) : blk;
+                double hb[kBlkMax], cb[kBlkMax];
+                block_coefficients(hcol + kBlkSums * (sw * nblk + j), gram + (size_t)j * blk * kBlkMax,
+                                   rho_vec ? rho_vec + j * blk : nullptr, m, hb, cb);
+                // second sweep: R[nr+i] += Htmp (gmres! step 5)
+                for (int b = 0; b < m; ++b) R[nr + j * blk + b] = sw == 0 ? hb[b] : R[nr + j * blk + b] + hb[b];
+            }
         }
-        hh = hcol[kBlkSums * nblk];
+        hh = hcol[kBlkSums * rec_final];
         // the vector finished by this iteration is stored as basis vector k; when it joins the last block (block not
         // full yet) its Gram entries with that block's vectors were measured by the final pass: cache them
         if (mlast < blk)
-            for (int a = 0; a < mlast; ++a) gram[(size_t)k * kBlkMax + a] = hcol[kBlkSums * nblk + 1 + a];
+            for (int a = 0; a < mlast; ++a) gram[(size_t)k * kBlkMax + a] = hcol[kBlkSums * rec_final + 1 + a];
     } else {
         const double* h2 = hcol + (k + 1);
         for (int i = 0; i < k; ++i) R[nr + i] = reorth ? hcol[i] + h2[i] : hcol[i];
@@ -207,6 +232,41 @@ __global__ void k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, dou
     st->stop = stop;
     st->solved = solved;
     st->breakdown = breakdown;
+}
+
+// gmres! step 9: solve R y = z (K x K packed column-major upper triangle, K = inner iterations of the pass, read from
+// the control block so that the host can queue this kernel before it knows how far the pass got).  Column-oriented
+// back-substitution: y_j = z_j / R_jj, then z_i -= R_ij y_j for all i < j in parallel.  Every y_i therefore sees the
+// subtractions in the order j = K, K-1, ..., i+1 with one multiplication and one subtraction each: the same operations
+// in the same order as the row-oriented loop of Krylov.jl, |R_ii| <= btol  =>  y_i = 0 and `inconsistent`.
+// use_rho: un-normalised basis, the combine kernel multiplies the STORED vectors: y_i <- y_i / rho_i.
+__global__ void __launch_bounds__(256) k_gmres_backsolve(KrylovCtl* ctl, const double* __restrict__ R,
+                                                         const double* __restrict__ z, const double* __restrict__ rho,
+                                                         double* y, int use_rho, KrylovStatus* st) {
+    __shared__ double s_yj;
+    const int K = ctl->inner_iter;
+    const int tid = threadIdx.x;
+    const double btol = ctl->btol;
+    for (int i = tid; i < K; i += blockDim.x) y[i] = z[i];
+    __syncthreads();
+    for (int j = K - 1; j >= 0; --j) {
+        const int64_t col = (int64_t)j * (j + 1) / 2;  // column j holds R[0..j, j]
+        if (tid == 0) {
+            const double diag = R[col + j];
+            double yj;
+            if (fabs(diag) <= btol) { yj = 0.0; ctl->inconsistent = 1; }
+            else yj = y[j] / diag;
+            y[j] = yj;
+            s_yj = yj;
+        }
+        __syncthreads();
+        const double yj = s_yj;
+        for (int i = tid; i < j; i += blockDim.x) y[i] = __dsub_rn(y[i], __dmul_rn(R[col + i], yj));
+        __syncthreads();
+    }
+    if (use_rho)
+        for (int i = tid; i < K; i += blockDim.x) y[i] = y[i] / rho[i];
+    if (tid == 0) st->inconsistent = ctl->inconsistent;
 }
 
 // CG scalar updates (Krylov.jl cg!, M = I, radius = 0, linesearch = false)
@@ -300,7 +360,8 @@ static int ws_alloc_vec(ak_krylov* ws, double** out) {
 // doubles of the device column `hcol`: two sweeps of k + 1 sums, or one record of kBlkSums per block of the
 // blocked sweep (blocks of >= 2) plus the final ||q||^2 record
 static inline int64_t hcol_len(int64_t k) {
-    const int64_t a = 2 * (k + 1) + 8, b = (int64_t)kBlkSums * ((k + 1) / 2 + 3);
+    // blocks of 2, two sweeps (re-orthogonalisation): 2 ceil(k/2) records + the final one
+    const int64_t a = 2 * (k + 1) + 8, b = (int64_t)kBlkSums * (2 * ((k + 1) / 2) + 4);
     return a > b ? a : b;
 }
 
@@ -325,6 +386,7 @@ static int ws_grow_scalars(ak_krylov* ws, int64_t kcap_new) {
     AK_TRY(regrow(&ws->s, oldk, kcap_new));
     AK_TRY(regrow(&ws->z, oldk ? oldk + 1 : 0, kcap_new + 1));
     AK_TRY(regrow(&ws->rho, oldk ? oldk + 1 : 0, kcap_new + 1));
+    AK_TRY(regrow(&ws->ycoef, oldk ? oldk + 1 : 0, kcap_new + 1));
     AK_TRY(regrow(&ws->gram, oldk ? (oldk + 1) * kBlkMax : 0, (kcap_new + 1) * kBlkMax));
     AK_TRY(regrow(&ws->hcol, oldk ? hcol_len(oldk) : 0, hcol_len(kcap_new)));
     ws->kcap = kcap_new;
@@ -413,7 +475,7 @@ static int apply_precond(ak_krylov* ws, const ak_problem* prob, const double* u,
     ak_krylov_opts io;
     ak_krylov_default_opts(&io);
     io.itmax = left ? o->precond_m_itmax : o->precond_itmax;
-    io.fuse = (o->fuse == AK_FUSE_NONE) ? AK_FUSE_NONE : AK_FUSE_MGS;
+    io.fuse = (o->fuse == AK_FUSE_FULL) ? AK_FUSE_MGS : o->fuse;  // the inner solve runs at the outer solve's fusion level
     ak_krylov_stats ist;
     int rc = gmres_solve(ws->inner, prob, u, in, &io, &ist, nullptr, 0);
     if (rc < 0) return rc;
@@ -431,13 +493,14 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     const int mem = ws->mem;
     const int restart = o->restart, reorth = o->reorthogonalization;
     int fuse = o->fuse;
-    // the blocked sweeps have no second-sweep variant
-    if ((fuse == AK_FUSE_PAIR || fuse == AK_FUSE_BLOCK4 || fuse == AK_FUSE_BLOCK8) && reorth) fuse = AK_FUSE_FULL;
     const bool flexible = (ws->algo == AK_ALGO_FGMRES);
     const bool precond = (o->precond_n != AK_PRECOND_NONE);
     const bool lprec = (o->precond_m != AK_PRECOND_NONE);  // q = M A N v_k, r0 = M (b - A x): Krylov.jl solver.q
-    // z_k = N v_k needs v_k materialised before the JVP and a host decision per iteration: no JVP fusion
-    if ((flexible || precond || lprec) && fuse > AK_FUSE_MGS) fuse = AK_FUSE_MGS;
+    // z_k = N v_k needs v_k materialised before the JVP and a host decision per iteration (the preconditioner may be
+    // an inner solve with its own verdicts): no JVP fusion.  The blocked sweeps still apply: they orthogonalise
+    // against the stored (un-normalised) vectors, only the seed of the preconditioner is a normalised copy.
+    const bool hosted = flexible || precond || lprec;
+    if (hosted && fuse == AK_FUSE_FULL) fuse = AK_FUSE_MGS;
     if ((flexible || precond) && !ws->pbuf) AK_TRY(ws_alloc_vec(ws, &ws->pbuf));
     if (lprec && !ws->qbuf) AK_TRY(ws_alloc_vec(ws, &ws->qbuf));
     const int blk = fuse == AK_FUSE_PAIR ? 2 : (fuse == AK_FUSE_BLOCK4 ? 4 : (fuse == AK_FUSE_BLOCK8 ? 8 : 0));  // steps per sweep
@@ -446,10 +509,11 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     // IS the stored vector (scale rho[k] = Hbis); the JVP divides by rho[k-1] in registers.  No w buffers, no
     // normalised copy: 24n instead of 32n bytes per JVP.
     const bool raw = pair;
+    ws->last_raw = raw;
     // multi-GPU with peer memory: reductions and ghost rows of the blocked sweep go over NVLink stores
     const bool p2p = pair && c->p2p_on && c->nranks > 1;
     const bool is2d = (prob->kind == AK_BRATU2D || prob->kind == AK_HEAT2D);
-    const bool p2p_halo = p2p && is2d && prob->nx % 4 == 0 && n % 4 == 0 && prob->nx <= c->p2p_halo_cap;
+    const bool p2p_halo = p2p && !hosted && is2d && prob->nx % 4 == 0 && n % 4 == 0 && prob->nx <= c->p2p_halo_cap;
     int nb_down = -1, nb_up = -1;  // owners of the ghost rows below / above this slab
     if (p2p_halo) {
         const bool per = (prob->bc == AK_BC_PERIODIC);
@@ -461,46 +525,56 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
 
     int64_t itmax = o->itmax == 0 ? 2 * n : o->itmax;
     double* x = ws->x;
+    // right-preconditioned gmres!: x += N (V y) goes through a separate xr; otherwise the combine kernel adds to x directly
+    const bool xr_separate = precond && !flexible;
     double* xr = x;
-    if (restart) {
+    if (restart && xr_separate) {
         if (!ws->dx) AK_TRY(ws_alloc_vec(ws, &ws->dx));
         xr = ws->dx;
     }
     if (fuse == AK_FUSE_FULL && !ws->w[1]) AK_TRY(ws_alloc_vec(ws, &ws->w[1]));
     AK_TRY(ws_ensure_basis(ws, raw && restart ? mem + 1 : mem, raw));
     // problem kinds without a fused normalise + JVP kernel get the normalised seed in a scratch vector
-    const bool raw_needs_seed = raw && (prob->kind == AK_SIMPLE2 || prob->kind == AK_USER || prob->scheme == AK_MIDPOINT ||
-                                        prob->jvp_mode == AK_JVP_FD);
+    const bool raw_needs_seed = raw && !hosted && (prob->kind == AK_SIMPLE2 || prob->kind == AK_USER ||
+                                                   prob->scheme == AK_MIDPOINT || prob->jvp_mode == AK_JVP_FD);
     if (raw_needs_seed && !ws->pbuf) AK_TRY(ws_alloc_vec(ws, &ws->pbuf));
     AK_TRY(ws_grow_scalars(ws, mem));
     if (want_hist) AK_TRY(ws_grow_hist(ws, 257));
 
+    if (p2p && *c->p2p_err) {
+        set_error("the peer-memory path of this context is latched off after a time-out; call ak_comm_use_p2p on every rank");
+        return AK_ERR_PEER;
+    }
     int wi = 0;  // index of the buffer currently holding w / r0
     double* w = raw ? ws->V[0] : ws->w[wi];
-    AK_TRY(launch_fill(c, n, x, 0.0));
+    if (xr_separate) AK_TRY(launch_fill(c, n, x, 0.0));
     if (lprec) AK_TRY(apply_precond(ws, prob, u, o, true, b, w));  // r0 = M b
     else AK_TRY(launch_copy(c, n, w, b));
+    AK_TRY(launch_sumsq(c, n, w, ws->hcol));
 
     memset(st, 0, sizeof(*st));
     int64_t iter = 0, inner_itmax = itmax;
     int npass = 0;
     bool solved = false, tired = false, breakdown = false, inconsistent = false;
+    bool x_written = false;  // x holds the sum of the passes so far (false: still conceptually zero)
     double rNorm = 0.0, beta0 = 0.0;
-    std::vector<double> Rh, zh, rhoh;
+    ws->status[kStatusRing + 1].inconsistent = 0;
 
     while (true) {
         // ---- pass prologue -------------------------------------------------------------
-        if (restart) {
-            AK_TRY(launch_fill(c, n, xr, 0.0));
-            if (npass >= 1) {
-                // w <- b - A x  (left-preconditioned: w <- M (b - A x))
-                double* t = lprec ? ws->qbuf : w;
-                AK_TRY(launch_jvp(c, prob, u, x, t, nullptr));
-                AK_TRY(launch_axpby(c, n, 1.0, b, -1.0, t));
-                if (lprec) AK_TRY(apply_precond(ws, prob, u, o, true, t, w));
+        if (restart && npass >= 1) {
+            // w <- b - A x with ||w||^2 in the same pass (left-preconditioned: w <- M (b - A x))
+            JvpFusion rf;
+            rf.rhs_minus = b;
+            if (lprec) {
+                AK_TRY(launch_jvp(c, prob, u, x, ws->qbuf, &rf));
+                AK_TRY(apply_precond(ws, prob, u, o, true, ws->qbuf, w));
+                AK_TRY(launch_sumsq(c, n, w, ws->hcol));
+            } else {
+                rf.sumsq_dev = ws->hcol;
+                AK_TRY(launch_jvp(c, prob, u, x, w, &rf));
             }
         }
-        AK_TRY(launch_sumsq(c, n, w, ws->hcol));
         k_gmres_begin<<<1, 32, 0, sm>>>(ws->ctl, ws->hcol, ws->z, want_hist ? ws->hist : nullptr, npass == 0, o->atol,
                                         o->rtol, &ws->status[kStatusRing], raw ? ws->rho : nullptr);
         c->launches++;
@@ -513,6 +587,34 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
         const int64_t inner_limit = restart ? (mem < inner_itmax ? mem : inner_itmax) : inner_itmax;
         int64_t K = 0;  // completed inner iterations of this pass
         KrylovStatus hs;
+        bool update_queued = false;
+        // x (+)= sum_i y_i V_i with y from the device back-substitution; the pass length is read on the device, so this
+        // can be queued before the host has seen the last verdict (no stream drain at the cycle boundary)
+        auto queue_solution_update = [&](int64_t k_launched) -> int {
+            int64_t cnt = k_launched;
+            const int64_t have = flexible ? (int64_t)ws->Z.size() : (int64_t)ws->V.size();
+            if (cnt > have) cnt = have;
+            if (cnt < 1) return AK_OK;
+            AK_TRY(ws_upload_basis_table(ws, cnt, flexible));
+            { ProfScope prof(c, PK_SCALAR);
+            k_gmres_backsolve<<<1, 256, 0, sm>>>(ws->ctl, ws->R, ws->z, ws->rho, ws->ycoef, (raw && !flexible) ? 1 : 0,
+                                                 &ws->status[kStatusRing + 1]); }
+            c->launches++;
+            AK_CUDA(cudaGetLastError());
+            const int* kdev = &ws->ctl->inner_iter;
+            if (xr_separate) {
+                // x_k = N V_k y_k: xr <- V y ; xr <- N xr ; x += xr
+                AK_TRY(launch_basis_combine(c, n, xr, ws->V_dev, ws->ycoef, kdev, 0, 0));
+                AK_TRY(launch_copy(c, n, ws->pbuf, xr));
+                AK_TRY(apply_precond_n(ws, prob, u, o, ws->pbuf, xr));
+                if (restart) AK_TRY(launch_axpy(c, n, 1.0, xr, x));
+            } else {
+                // gmres: V y, fgmres: Z y; first pass stores, restart passes add (kaxpy!(n, one, xr, x))
+                AK_TRY(launch_basis_combine(c, n, x, ws->V_dev, ws->ycoef, kdev, 0, x_written ? 1 : 0));
+            }
+            update_queued = true;
+            return AK_OK;
+        };
         AK_TRY(wait_status(ws, kStatusRing, &hs));
         if (npass == 1) { beta0 = hs.beta; rNorm = hs.rNorm; }
         if (hs.stop) {
@@ -539,10 +641,11 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 if (!restart || k < mem || raw) {
                     if (k + 1 > (int64_t)ws->V.size()) {
                         int rc = ws_ensure_basis(ws, k + 1);
+                        // every rank must take the same branch (the peer-memory kernels wait for one another)
+                        AK_TRY(collective_verdict(c, &rc));
                         if (rc != AK_OK) {
                             // cannot grow further: treat as out of iterations (reference would keep growing)
                             AK_TRY(verdicts_until(k - 1, &stopped));
-                            K = k - 1;
                             tired = true;
                             break;
                         }
@@ -557,10 +660,15 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
 
                 // fgmres / right preconditioning: z_k = N v_k (kept in Z for fgmres), then w <- A z_k
                 double* pv = ws->V[k - 1];
-                if ((flexible || precond || lprec) && k > 1) {
+                if (hosted && k > 1) {
                     // the preconditioner solves with host-visible verdicts: this path is not speculative
                     AK_TRY(verdicts_until(k - 1, &stopped));
-                    if (stopped) { K = k - 1; break; }
+                    if (stopped) break;
+                }
+                if (hosted && raw) {
+                    // normalised copy of the stored vector: v_k = V[k-1] / rho[k-1] (what gmres! holds in V[k])
+                    AK_TRY(launch_divcopy_dev(c, n, ws->w[0], ws->V[k - 1], ws->rho + (k - 1), stop));
+                    pv = ws->w[0];
                 }
                 if (flexible || precond) {
                     double* tgt = ws->pbuf;
@@ -572,8 +680,8 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                         }
                         tgt = ws->Z[k - 1];
                     }
-                    if (precond) AK_TRY(apply_precond_n(ws, prob, u, o, ws->V[k - 1], tgt));
-                    else AK_TRY(launch_copy(c, n, tgt, ws->V[k - 1]));
+                    if (precond) AK_TRY(apply_precond_n(ws, prob, u, o, pv, tgt));
+                    else AK_TRY(launch_copy(c, n, tgt, pv));
                     pv = tgt;
                 }
                 // w <- A V[k-1]  (+ fused divcopy of V[k-1], + fused first dot)
@@ -581,7 +689,9 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 jf.stop_flag = stop;
                 double* wout = w;
                 double* seed = pv;
-                if (raw) {
+                if (raw && hosted) {
+                    wout = ws->V[k];  // plain tangent of the (preconditioned) normalised seed, straight into basis slot k
+                } else if (raw) {
                     // w <- J (V[k-1] / rho[k-1]), straight into basis slot k
                     jf.scale_src = ws->V[k - 1];
                     jf.denom_dev = ws->rho + (k - 1);
@@ -600,12 +710,6 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                         jf.denom_dev = &ws->ctl->Hbis;
                         wi ^= 1;
                         wout = ws->w[wi];
-                        if (p2p_halo) {  // ghost rows of w were pushed by the neighbours' final pass of iteration k-1
-                            const int par = (int)((k - 1) & 1);
-                            jf.halo_given = true;
-                            jf.halo_lo = nb_down >= 0 ? c->p2p_halo_local(par, 0) : nullptr;
-                            jf.halo_hi = nb_up >= 0 ? c->p2p_halo_local(par, 1) : nullptr;
-                        }
                     }
                     jf.dot_with = ws->V[0];
                     jf.dot_dev = hcol;
@@ -619,32 +723,37 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 w = wout;
                 // modified Gram-Schmidt
                 if (pair) {
-                    // `blk` Gram-Schmidt steps per sweep over w: pass j subtracts block j-1 and projects on block j
+                    // `blk` Gram-Schmidt steps per sweep over w.  Pass list of one iteration: project on block 0; then
+                    // every pass subtracts the block the previous pass projected on and projects on the next one
+                    // (re-orthogonalisation: the blocks are visited a second time, gmres! step 5); the final pass
+                    // subtracts the last block and measures ||w||^2.  Record r of hcol holds the sums of pass r.
                     const int64_t P = (k + blk - 1) / blk;
+                    const int64_t npj = (reorth ? 2 : 1) * P;  // projection passes
                     auto blk_ptr = [&](int64_t j) -> const double* const* { return ws->V.data() + blk * j; };
                     auto blk_len = [&](int64_t j) -> int { return (int)((k - blk * j) < blk ? (k - blk * j) : blk); };
+                    auto blk_rho = [&](int64_t j) -> const double* { return ws->rho + blk * j; };
+                    auto blk_gram = [&](int64_t j) -> const double* { return ws->gram + blk * j * kBlkMax; };
                     BlockComm pc;
                     unsigned long long prev_seq = 0;
                     if (p2p) { pc.seq_out = ++c->p2p_seq; prev_seq = pc.seq_out; }
-                    auto blk_rho = [&](int64_t j) -> const double* { return ws->rho + blk * j; };
-                    auto blk_gram = [&](int64_t j) -> const double* { return ws->gram + blk * j * kBlkMax; };
                     AK_TRY(launch_mgs_block(c, n, w, nullptr, 0, nullptr, nullptr, nullptr, blk_ptr(0), blk_len(0), 0, hcol,
                                             stop, p2p ? &pc : nullptr));
-                    for (int64_t j = 1; j < P; ++j) {
+                    for (int64_t r = 1; r < npj; ++r) {
+                        const int64_t js = (r - 1) % P, jp = r % P;  // block subtracted / block projected on
                         if (p2p) {
                             pc.seq_in = prev_seq;
                             pc.seq_out = ++c->p2p_seq;
-                            pc.tin_store = hcol + kBlkSums * (j - 1);
+                            pc.tin_store = hcol + kBlkSums * (r - 1);
                             prev_seq = pc.seq_out;
                         }
-                        AK_TRY(launch_mgs_block(c, n, w, blk_ptr(j - 1), blk, hcol + kBlkSums * (j - 1), blk_gram(j - 1),
-                                                blk_rho(j - 1), blk_ptr(j), blk_len(j), 0, hcol + kBlkSums * j, stop,
+                        AK_TRY(launch_mgs_block(c, n, w, blk_ptr(js), blk_len(js), hcol + kBlkSums * (r - 1), blk_gram(js),
+                                                blk_rho(js), blk_ptr(jp), blk_len(jp), 0, hcol + kBlkSums * r, stop,
                                                 p2p ? &pc : nullptr));
                     }
                     if (p2p) {
                         pc.seq_in = prev_seq;
                         pc.seq_out = ++c->p2p_seq;
-                        pc.tin_store = hcol + kBlkSums * (P - 1);
+                        pc.tin_store = hcol + kBlkSums * (npj - 1);
                         givens_seq = pc.seq_out;
                         if (p2p_halo) {
                             const int par = (int)(k & 1);
@@ -653,8 +762,8 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                             pc.halo.up_lo = nb_up >= 0 ? c->p2p_halo_of(nb_up, par, 0) : nullptr;
                         }
                     }
-                    AK_TRY(launch_mgs_block(c, n, w, blk_ptr(P - 1), blk_len(P - 1), hcol + kBlkSums * (P - 1),
-                                            blk_gram(P - 1), blk_rho(P - 1), nullptr, 0, 1, hcol + kBlkSums * P, stop,
+                    AK_TRY(launch_mgs_block(c, n, w, blk_ptr(P - 1), blk_len(P - 1), hcol + kBlkSums * (npj - 1),
+                                            blk_gram(P - 1), blk_rho(P - 1), nullptr, 0, 1, hcol + kBlkSums * npj, stop,
                                             p2p ? &pc : nullptr));
                 } else if (fuse == AK_FUSE_NONE) {
                     for (int64_t i = 0; i < k; ++i) {
@@ -701,57 +810,26 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                     if (fuse == AK_FUSE_FULL) scale_pending = true;
                     else AK_TRY(launch_divcopy_dev(c, n, ws->V[k], w, &ws->ctl->Hbis, stop));
                 }
-                // look at an older iteration's verdict while the newer ones run
-                AK_TRY(verdicts_until(k - kSpecDepth, &stopped));
-                if (stopped) break;
-                if (k >= inner_limit) {  // last iteration of the pass: drain the window (its own record has stop = tired)
+                if (k >= inner_limit) {
+                    // last iteration of the pass: queue the solution update behind it, then drain the window (the
+                    // record of iteration inner_limit has stop = tired)
+                    AK_TRY(queue_solution_update(k));
                     AK_TRY(verdicts_until(k, &stopped));
                     break;
                 }
+                // look at an older iteration's verdict while the newer ones run
+                AK_TRY(verdicts_until(k - kSpecDepth, &stopped));
+                if (stopped) break;
             }
+            // hs is the record the pass ended on: the stop verdict, or (basis could not grow) the last complete iteration
             solved = hs.solved != 0;
             breakdown = hs.breakdown != 0;
             rNorm = hs.rNorm;
             K = hs.iter;
+            if (K > 0 && !update_queued) AK_TRY(queue_solution_update(k));
         }
-
-        // ---- solve R y = z on the host (K x K packed upper triangle), x += V y ------------
-        if (K > 0) {
-            const int64_t nR = K * (K + 1) / 2;
-            Rh.resize((size_t)nR);
-            zh.resize((size_t)K);
-            AK_CUDA(cudaMemcpyAsync(Rh.data(), ws->R, sizeof(double) * (size_t)nR, cudaMemcpyDeviceToHost, sm));
-            AK_CUDA(cudaMemcpyAsync(zh.data(), ws->z, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost, sm));
-            if (raw) {
-                rhoh.resize((size_t)K);
-                AK_CUDA(cudaMemcpyAsync(rhoh.data(), ws->rho, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost, sm));
-            }
-            AK_CUDA(cudaStreamSynchronize(sm));
-            const double btol = pow(2.220446049250313e-16, 0.75);
-            double* y = zh.data();
-            for (int64_t i = K; i >= 1; --i) {
-                int64_t pos = nR + i - K - 1;
-                for (int64_t j = K; j >= i + 1; --j) {
-                    y[i - 1] = y[i - 1] - Rh[(size_t)pos] * y[j - 1];
-                    pos = pos - j + 1;
-                }
-                if (fabs(Rh[(size_t)pos]) <= btol) { y[i - 1] = 0.0; inconsistent = true; }
-                else y[i - 1] = y[i - 1] / Rh[(size_t)pos];
-            }
-            if (raw)  // x = sum y_i v_i = sum (y_i / rho_i) V[i]
-                for (int64_t i = 0; i < K; ++i) y[i] = y[i] / rhoh[(size_t)i];
-            AK_CUDA(cudaMemcpyAsync(ws->hcol, y, sizeof(double) * (size_t)K, cudaMemcpyHostToDevice, sm));
-            // x_k = N V_k y_k (gmres) or Z_k y_k (fgmres)
-            AK_TRY(ws_upload_basis_table(ws, K, flexible));
-            AK_TRY(launch_basis_combine(c, n, xr, ws->V_dev, ws->hcol, (int)K, /*zero_x_first=*/1));
-            if (!flexible && precond) {
-                AK_TRY(launch_copy(c, n, ws->pbuf, xr));
-                AK_TRY(apply_precond_n(ws, prob, u, o, ws->pbuf, xr));
-            }
-            if (restart) AK_TRY(launch_axpy(c, n, 1.0, xr, x));
-            // y lives in host memory that the async copy reads: drain before the vectors are reused
-            AK_CUDA(cudaStreamSynchronize(sm));
-        }
+        if (K > 0) x_written = true;
+        if (p2p && *c->p2p_err) break;  // a peer fell out of step: reported below
         inner_itmax -= K;
         iter += K;
         if (iter >= itmax) tired = true;
@@ -759,10 +837,19 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
         // FUSE_FULL leaves the last residual candidate in w[wi]; the restart recomputes w anyway
         w = raw ? ws->V[0] : ws->w[wi];
     }
+    if (!x_written && !xr_separate) AK_TRY(launch_fill(c, n, x, 0.0));  // x0 = 0 and no iteration ran
 
+    // one drain per solve: the verdict of the back-substitution(s) and the history
+    if (hist_host && hist_cap > 0 && ws->hist) {
+        int64_t m = iter + 1 < hist_cap ? iter + 1 : hist_cap;
+        AK_CUDA(cudaMemcpyAsync(hist_host, ws->hist, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, sm));
+    }
+    AK_CUDA(cudaStreamSynchronize(sm));
+    inconsistent = ws->status[kStatusRing + 1].inconsistent != 0;
     if (p2p && *c->p2p_err) {
-        set_error("peer-memory collective timed out (a rank fell out of step)");
-        return AK_ERR_NCCL;
+        set_error("peer-memory collective timed out (a rank fell out of step); the peer path of this context is "
+                  "latched off until ak_comm_use_p2p is called again on every rank");
+        return AK_ERR_PEER;
     }
     st->niter = iter;
     st->solved = solved ? 1 : 0;
@@ -771,11 +858,6 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     st->npass = npass;
     st->rnorm = rNorm;
     st->beta = beta0;
-    if (hist_host && hist_cap > 0 && ws->hist) {
-        int64_t m = iter + 1 < hist_cap ? iter + 1 : hist_cap;
-        AK_CUDA(cudaMemcpyAsync(hist_host, ws->hist, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, sm));
-        AK_CUDA(cudaStreamSynchronize(sm));
-    }
     int flags = 0;
     if (!solved) flags |= AK_FLAG_NOT_SOLVED;
     if (breakdown) flags |= AK_FLAG_BREAKDOWN;
@@ -958,6 +1040,7 @@ AK_API int ak_krylov_destroy(ak_krylov* ws) {
     for (double* p : ws->chunks) rel(p);
     rel((void*)ws->V_dev);
     rel(ws->R); rel(ws->c); rel(ws->s); rel(ws->z); rel(ws->hcol); rel(ws->hist); rel(ws->rho); rel(ws->gram);
+    rel(ws->ycoef);
     rel(ws->ctl);
     if (ws->status) cudaFreeHost(ws->status);
     for (int i = 0; i < kStatusSlots; ++i)
@@ -975,6 +1058,22 @@ AK_API int ak_krylov_solve(ak_krylov* ws, const ak_problem* p, const double* u, 
 }
 
 AK_API double* ak_krylov_x(ak_krylov* ws) { return ws ? ws->x : nullptr; }
+
+AK_API int ak_krylov_basis(ak_krylov* ws, int64_t i, double** stored_dev, double* scale_host, int64_t* count_out) {
+    AK_REQUIRE(ws, "ak_krylov_basis: NULL workspace");
+    if (count_out) *count_out = (int64_t)ws->V.size();
+    if (stored_dev == nullptr && scale_host == nullptr) return AK_OK;
+    AK_REQUIRE(i >= 0 && i < (int64_t)ws->V.size(), "ak_krylov_basis: index out of range");
+    if (stored_dev) *stored_dev = ws->V[(size_t)i];
+    if (scale_host) {
+        *scale_host = 1.0;
+        if (ws->last_raw && ws->rho && i <= ws->kcap) {
+            AK_CUDA(cudaMemcpyAsync(scale_host, ws->rho + i, sizeof(double), cudaMemcpyDeviceToHost, ws->ctx->stream));
+            AK_CUDA(cudaStreamSynchronize(ws->ctx->stream));
+        }
+    }
+    return AK_OK;
+}
 
 AK_API int ak_precond_apply(ak_ctx* ctx, const ak_problem* p, const double* u, int32_t kind, int32_t itmax,
                             const double* x, double* y) {

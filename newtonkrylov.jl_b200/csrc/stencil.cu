@@ -45,6 +45,7 @@ struct StencilArgs {
     double* out;
     double* in_write;    // fused divcopy: scaled `in` is stored here (own rows) ; 1-D heat: BC write-back target
     const double* out_scale;  // tangent kernels, un-normalised Krylov basis: out = J(in) / *out_scale (device scalar)
+    const double* bminus;     // tangent kernels: out = bminus - J(in)  (restart residual b - A x of gmres!)
     const double* denom; // fused divcopy: device scalar
     const double* dot_with;
     double* red_out;
@@ -287,6 +288,12 @@ __global__ void __launch_bounds__(kTX, OP == OP_JVP_BRATU_FD ? 4 : 8) k_stencil2
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) o[i] = __dmul_rn(o[i], oscale);
             }
+            if (p.bminus != nullptr) {
+                double bb[VEC];
+                ldv_s<VEC>(p.bminus + off, bb);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) o[i] = __dsub_rn(bb[i], o[i]);
+            }
             stv<VEC>(p.out + off, o);
             if (OP == OP_RES_BRATU && p.aux_out != nullptr) stv<VEC>(p.aux_out + off, cf);
             if (SCALE) stv<VEC>(p.in_write + off, cur);
@@ -439,6 +446,12 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) o[i] = __dmul_rn(o[i], oscale);
         }
+        if (p.bminus != nullptr) {
+            double bb[VEC];
+            ldv_s<VEC>(p.bminus + x0, bb);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] = __dsub_rn(bb[i], o[i]);
+        }
         stv<VEC>(p.out + x0, o);
         if (OP == OP_RES_BRATU && p.aux_out != nullptr) stv<VEC>(p.aux_out + x0, cf);
         if (SCALE) {
@@ -483,6 +496,7 @@ struct DgArgs {
     double* in_write;
     const double* denom;
     const double* out_scale;  // tangent with an un-normalised Krylov basis: out = J(in) / *out_scale
+    const double* bminus;     // tangent: out = bminus - J(in)  (restart residual of gmres!)
     const double* dot_with;
     double* red_out;
     double* partials;
@@ -572,6 +586,12 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) o[i] = __dmul_rn(o[i], oscale);
             }
+            if (p.bminus != nullptr) {
+                double bb[4];
+                ldv_s<4>(p.bminus + 4 * e, bb);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(bb[i], o[i]);
+            }
         }
         stv<4>(p.out + 4 * e, o);
         if (SCALE) stv<4>(p.in_write + 4 * e, raw);
@@ -640,7 +660,7 @@ template <int OP>
 static int launch2d(Ctx* ctx, StencilArgs& a, bool scale, int red) {
     // widest vector the row pitch and every operand allow
     int vec = 1;
-    const void* ptrs[] = {a.in, a.lo, a.hi, a.aux, a.aux_out, a.out, a.in_write, a.dot_with};
+    const void* ptrs[] = {a.in, a.lo, a.hi, a.aux, a.aux_out, a.out, a.in_write, a.dot_with, a.bminus};
     auto ok = [&](int v) {
         if (a.nx % v) return false;
         for (const void* q : ptrs)
@@ -690,7 +710,7 @@ static void launch1d_v(Ctx* ctx, const StencilArgs& a, bool scale, int red, int 
 template <int OP>
 static int launch1d(Ctx* ctx, StencilArgs& a, bool scale, int red) {
     int vec = 1;
-    const void* ptrs[] = {a.in, a.aux, a.aux_out, a.out, a.in_write, a.dot_with};
+    const void* ptrs[] = {a.in, a.aux, a.aux_out, a.out, a.in_write, a.dot_with, a.bminus};
     auto ok = [&](int v) {
         if (a.nx % v) return false;
         for (const void* q : ptrs)
@@ -738,6 +758,7 @@ static int launch_dg(Ctx* ctx, DgArgs& d, bool residual, bool scale, int red) {
         else AK_LDG(false, true, RED_NONE);
     } else {
         if (red == RED_DOT) AK_LDG(false, false, RED_DOT);
+        else if (red == RED_SUMSQ) AK_LDG(false, false, RED_SUMSQ);
         else AK_LDG(false, false, RED_NONE);
     }
 #undef AK_LDG
@@ -1032,7 +1053,9 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
         if (f->scale_src) AK_TRY(launch_divcopy_dev(ctx, n, v, f->scale_src, f->denom_dev, f->stop_flag));
         if (fd_generic(p)) AK_TRY(launch_jvp_fd(ctx, p, u, v, out));
         else AK_TRY(user_jvp(ctx, p, u, v, out));
+        if (f->rhs_minus) AK_TRY(launch_axpby(ctx, n, 1.0, f->rhs_minus, -1.0, out));
         if (f->dot_with) AK_TRY(launch_mgs_step(ctx, n, out, nullptr, nullptr, f->dot_with, 0, f->dot_dev, f->stop_flag));
+        else if (f->sumsq_dev) AK_TRY(launch_sumsq(ctx, n, out, f->sumsq_dev));
         return AK_OK;
     }
     if (p->scheme == AK_MIDPOINT) {
@@ -1043,20 +1066,28 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
         }
         if (f->scale_src) AK_TRY(launch_divcopy_dev(ctx, n, v, f->scale_src, f->denom_dev, f->stop_flag));
         AK_TRY(launch_jvp_midpoint(ctx, p, v, out));
+        if (f->rhs_minus) AK_TRY(launch_axpby(ctx, n, 1.0, f->rhs_minus, -1.0, out));
         if (f->dot_with) AK_TRY(launch_mgs_step(ctx, n, out, nullptr, nullptr, f->dot_with, 0, f->dot_dev, f->stop_flag));
+        else if (f->sumsq_dev) AK_TRY(launch_sumsq(ctx, n, out, f->sumsq_dev));
         return AK_OK;
     }
     // un-normalised Krylov basis (f->raw): the stored vector scale_src is the seed, J(scale_src) / denom the result
     const bool raw = f->raw && f->scale_src != nullptr;
     const bool native = !(p->kind == AK_SIMPLE2);
     const bool scale = f->scale_src != nullptr && !(raw && native);
-    const int red = f->dot_with ? RED_DOT : RED_NONE;
+    const int red = f->dot_with ? RED_DOT : (f->sumsq_dev ? RED_SUMSQ : RED_NONE);
+    double* red_out = f->dot_with ? f->dot_dev : f->sumsq_dev;
     if (raw && native) v = const_cast<double*>(f->scale_src);
     if (p->kind == AK_SIMPLE2) {
         if (scale) AK_TRY(launch_divcopy_dev(ctx, 2, v, f->scale_src, f->denom_dev, f->stop_flag));
-        k_simple2<<<1, 32, 0, ctx->stream>>>(u, v, out, f->dot_dev, 1, f->dot_with, f->stop_flag);
+        k_simple2<<<1, 32, 0, ctx->stream>>>(u, v, out, f->rhs_minus ? nullptr : red_out, 1, f->dot_with, f->stop_flag);
         ctx->launches++;
         AK_CUDA(cudaGetLastError());
+        if (f->rhs_minus) {
+            AK_TRY(launch_axpby(ctx, 2, 1.0, f->rhs_minus, -1.0, out));
+            if (f->dot_with) AK_TRY(launch_mgs_step(ctx, 2, out, nullptr, nullptr, f->dot_with, 0, f->dot_dev, f->stop_flag));
+            else if (f->sumsq_dev) AK_TRY(launch_sumsq(ctx, 2, out, f->sumsq_dev));
+        }
         return AK_OK;
     }
     if (p->kind == AK_HEAT1D_DG) {
@@ -1067,11 +1098,12 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
         d.in = scale ? f->scale_src : v;
         AK_TRY(ghost_1d(ctx, d.in, p->nx, 4, 1, true, &d.lo, &d.hi));
         d.in_write = v; d.denom = f->denom_dev; d.out_scale = raw ? f->denom_dev : nullptr;
-        d.out = out; d.dot_with = f->dot_with; d.red_out = f->dot_dev;
+        d.out = out; d.dot_with = f->dot_with; d.red_out = red_out; d.bminus = f->rhs_minus;
         d.partials = ctx->partials; d.ticket = ctx->ticket; d.stop = f->stop_flag;
-        AK_REQUIRE(al(d.in, 32) && al(v, 32) && al(out, 32) && al(f->dot_with, 32), "DG vectors must be 32-byte aligned");
+        AK_REQUIRE(al(d.in, 32) && al(v, 32) && al(out, 32) && al(f->dot_with, 32) && al(f->rhs_minus, 32),
+                   "DG vectors must be 32-byte aligned");
         AK_TRY(launch_dg(ctx, d, false, scale, red));
-        if (red) AK_TRY(allreduce_sum(ctx, f->dot_dev, 1));
+        if (red) AK_TRY(allreduce_sum(ctx, red_out, 1));
         return AK_OK;
     }
     StencilArgs a;
@@ -1082,7 +1114,8 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     a.out_scale = raw ? f->denom_dev : nullptr;
     a.out = out;
     a.dot_with = f->dot_with;
-    a.red_out = f->dot_dev;
+    a.red_out = red_out;
+    a.bminus = f->rhs_minus;
     a.stop = f->stop_flag;
     int rc = AK_OK;
     switch (p->kind) {
@@ -1132,7 +1165,7 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
         default: break;
     }
     AK_TRY(rc);
-    if (red) AK_TRY(allreduce_sum(ctx, f->dot_dev, 1));
+    if (red) AK_TRY(allreduce_sum(ctx, red_out, 1));
     return AK_OK;
 }
 

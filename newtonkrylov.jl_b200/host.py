@@ -857,6 +857,12 @@ class KrylovWorkspace:
         p = self.ctx.lib.ak_krylov_x(self.h)
         return DeviceVector(self.ctx, self.proto.shape, ptr=p, owner=self)
 
+    def basis(self, i):
+        """(stored basis vector i as a DeviceVector view, its scale): v_i = stored / scale (ak_krylov_basis)."""
+        p, sc = C.c_void_p(), C.c_double()
+        L.check(self.ctx.lib.ak_krylov_basis(self.h, int(i), C.byref(p), C.byref(sc), None))
+        return DeviceVector(self.ctx, self.proto.shape, ptr=p.value, owner=self), sc.value
+
     def __del__(self):
         try:
             if self.h and self.ctx.h:

@@ -1,15 +1,107 @@
-"""Parity at BASELINE.json's full sizes through size-independent properties (the oracle is not asked to
-run at these sizes): C2 heat 1-D N = 2^24, C3 heat 2-D 8192^2, C4 2-D Bratu 8192^2, C5 DG 2^22 elements."""
+"""Parity at BASELINE.json's full sizes: C2 heat 1-D N = 2^24, C3 heat 2-D 8192^2, C4 2-D Bratu 8192^2,
+C5 DG 2^22 elements.  Every config is compared with the ORACLE at its stated size (a GMRES(20) cycle / a Newton step
+of the oracle takes seconds on the box's host cores) and, in addition, through size-independent properties.
+Observed deviations go to the parity ledger (tests/ledger.py -> profiles/parity_ledger.json)."""
 import ctypes as C
 
 import numpy as np
 import pytest
 
 from newtonkrylov_jl_b200 import _abi as A
+import ledger
 import problems as P
 
 pytestmark = pytest.mark.gpu
 RNG = np.random.default_rng(4)
+FUSE_LEVELS = ("none", "mgs", "full", "pair", "block4", "block8")
+
+
+def rel(a, b):
+    a, b = np.ravel(a), np.ravel(b)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def test_c4_bratu2d_8192_gmres_cycle_matches_oracle(nk, ctx, oracle):
+    """BASELINE config 4 at its stated size, the bench.py workload: one GMRES(20) restart cycle of the first Newton
+    step of 2-D Bratu 8192^2, all six fusion levels against the oracle's cycle on the same inputs.
+    Bar: recurrence residual history within 1e-10 * beta, x within 1e-8 relative, same iteration count."""
+    N = 8192
+    d = P.bratu2d(N)
+    po = P.oracle_problem(oracle, d)
+    r0, _ = oracle.residual(po, d["u0"])
+    kw = dict(rtol=1e-30, atol=0.0, restart=True, itmax=20)
+    xr, sr, hr = oracle.krylov_solve(po, d["u0"], r0, memory=20, hist_cap=32, **kw)
+    assert sr["niter"] == 20 and len(hr) == 21
+    F_, u, p, _ = P.device_setup(nk, ctx, d)
+    res, coef = u.zero(), u.similar()
+    prob = F_.problem(u, p, coef=coef)
+    nrm = C.c_double()
+    nk._lib.check(ctx.lib.ak_residual(ctx.h, C.byref(prob), C.c_void_p(u.ptr), C.c_void_p(res.ptr), C.byref(nrm)))
+    res_dev = rel(res.numpy(), r0)
+    assert res_dev < 1e-14  # exp differs by <= 1 ulp between libdevice and glibc
+    J = nk.JacobianOperator(F_, res, u, p, coef=coef)
+    ws = nk.krylov_workspace("gmres", nk.KrylovConstructor(res), memory=20)
+    b = nk.DeviceVector.from_numpy(r0, ctx)  # the oracle's right-hand side, bit for bit
+    failures = []
+    for fuse in FUSE_LEVELS:
+        nk.krylov_solve_(ws, J, b, history=True, fuse=fuse, **kw)
+        st = ws.stats
+        h = np.array(st.residuals)
+        hdev = float(np.max(np.abs(h - hr)) / hr[0]) if len(h) == len(hr) else float("inf")
+        xdev = rel(ws.x.numpy(), xr)
+        ok = st.niter == 20 and st.npass == 1 and hdev <= 1e-10 and xdev <= 1e-8
+        ledger.record("fullsize_vs_oracle", f"C4_bratu2d_8192_gmres20_cycle/{fuse}", niter_gpu=st.niter,
+                      niter_oracle=sr["niter"], max_hist_dev_rel_beta=hdev, x_rel_dev=xdev, residual_rel_dev=res_dev,
+                      beta=float(hr[0]), rnorm_after_cycle_gpu=float(h[-1]), rnorm_after_cycle_oracle=float(hr[-1]),
+                      **{"met_1e-10_1e-8": bool(ok)})
+        if not ok:
+            failures.append((fuse, st.niter, hdev, xdev))
+    assert not failures, failures
+
+
+def _newton_fullsize(nk, ctx, oracle, d, label, fuses, **kw):
+    """One newton_krylov! call at full size on the GPU (per fusion level) and on the oracle, plus one oracle run from a
+    1-ulp perturbed u0 (the reproducibility of the algorithm itself)."""
+    from test_gpu_solvers import newton_opts_for, oracle_sensitivity, assert_newton_parity
+
+    po = P.oracle_problem(oracle, d, un=d["u0"] if d.get("scheme") else None)
+    sens = oracle_sensitivity(oracle, po, d["u0"], newton_opts_for(nk, kw), ntrial=1)
+    for fuse in fuses:
+        F_, u, p, _ = P.device_setup(nk, ctx, d)
+        hist = []
+        kk = dict(kw.get("krylov_kwargs") or {}, fuse=fuse)
+        _, r = nk.newton_krylov_native_(F_, u, p, None, history=hist, **dict(kw, krylov_kwargs=kk))
+        assert_newton_parity(u.numpy(), r, hist, sens, label=f"{label}/{fuse}")
+        del u, F_, p
+    return sens
+
+
+def test_c3_heat2d_8192_implicit_euler_step_matches_oracle(nk, ctx, oracle):
+    """BASELINE config 3 at its stated size: one implicit-Euler step of 2-D heat 8192^2 (non-eigenfunction IC, dt rule
+    of examples/heat_2D.jl:72 x 16, tol_abs = 6e-6 of implicit.jl:69) with `reorthogonalization = true`
+    (examples/heat_2D.jl:131), solved to tolerance: Newton count, GMRES count per step, ||F|| history, final u."""
+    d = P.heat2d(8192, dt_scale=16.0, ic="poly")
+    sens = _newton_fullsize(nk, ctx, oracle, d, "C3_heat2d_8192_euler_step_reorth", ("none", "block8"), tol_abs=6e-6,
+                            krylov_kwargs=dict(reorthogonalization=True))
+    assert sens[1]["solved"] and sens[1]["outer_iterations"] >= 3
+
+
+def test_c2_heat1d_2pow24_newton_step_matches_oracle(nk, ctx, oracle):
+    """BASELINE config 2 at its stated size with the example's dt = 0.1 (a dt / dx^2 = 5.6e12: GMRES cannot converge,
+    SURVEY 8d C2 (i)): one Newton step of 20 GMRES iterations (`max_niter = 0` admits exactly one step; the user rtol
+    overrides eta), then u .-= d and the new residual norm."""
+    N = 1 << 24
+    d = P.heat1d(N - 2, dt=0.1)
+    _newton_fullsize(nk, ctx, oracle, d, "C2_heat1d_2pow24_newton_step_gmres20", ("none", "block8"), tol_abs=6e-6,
+                     max_niter=0, krylov_kwargs=dict(itmax=20, rtol=1e-12))
+
+
+def test_c5_dg_2pow22_newton_step_matches_oracle(nk, ctx, oracle):
+    """BASELINE config 5 at its stated size with the example's dt = 0.01 (examples/heat_1D_DG.jl:81): one Newton step
+    of 20 GMRES iterations."""
+    d = P.heat1d_dg(1 << 22, dt=0.01)
+    _newton_fullsize(nk, ctx, oracle, d, "C5_dg_2pow22_newton_step_gmres20", ("none", "block8"), tol_abs=6e-6,
+                     max_niter=0, krylov_kwargs=dict(itmax=20, rtol=1e-12))
 
 
 def affine_check(nk, ctx, F_, u, p, v, tol=1e-11):
