@@ -41,6 +41,7 @@ def load():
     lib = C.CDLL(LIB_PATH)
     sig = {
         "ok_num_threads": (C.c_int, []),
+        "ok_set_num_threads": (C.c_int, [C.c_int]),
         "ok_problem_size": (C.c_int64, [_P]),
         "ok_dot": (C.c_double, [C.c_int64, _dp, _dp]),
         "ok_nrm2": (C.c_double, [C.c_int64, _dp]),
@@ -242,3 +243,12 @@ def implicit_solve(p, un0, nsteps, opts=None):
 
 def num_threads():
     return int(load().ok_num_threads())
+
+
+def use_all_cores():
+    """OpenMP team = the cores this process may run on, whatever OMP_NUM_THREADS says (torchrun exports 1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return int(load().ok_set_num_threads(n))

@@ -66,6 +66,17 @@ OK_EXPORT int ok_num_threads(void) {
     return 1;
 #endif
 }
+/* Set the OpenMP team size explicitly (launchers such as torchrun export OMP_NUM_THREADS=1, which would silently
+ * time the "all host cores" column on one core).  n <= 0: leave as is.  Returns the team size in effect. */
+OK_EXPORT int ok_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 OK_EXPORT int64_t ok_problem_size(const ak_problem* p) {
     switch (p->kind) {

@@ -44,3 +44,27 @@ def test_our_arm_refuses_to_run_without_a_gpu():
         return
     r = run(["--steps", "1", "--warmup", "1", "--nx", "64", "--ny", "64"])
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_uses_all_host_cores_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU column must still be timed on the host's cores and say how many,
+    on the same sample (one full GMRES(20) restart cycle) at every N (SCALE vs_reference was void)."""
+    env = {"RANK": "0", "LOCAL_RANK": "0", "WORLD_SIZE": "4", "OMP_NUM_THREADS": "1"}
+    r = run(["--impl", "reference", "--nx", "128", "--ny", "96", "--steps", "1", "--warmup", "1", "--gpus", "4"], env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count()
+    assert d["cpu_baseline"]["cores"] == ncores and d["n_gpus"] == 4
+    assert "20 iterations" in d["cpu_baseline"]["sample"]
+    assert d["config"]["grid_per_gpu"] == [128, 96]  # the per-GPU workload, whatever N is
+
+
+def test_reference_arm_covers_every_baseline_config():
+    for cfg, key in (("c2", "1D implicit-Euler heat"), ("c3", "reorthogonalization=true"), ("c5", "DG 1D heat")):
+        r = run(["--impl", "reference", "--config", cfg, "--nx", "1024", "--ny", "48", "--steps", "1", "--warmup", "1"])
+        assert r.returncode == 0, r.stderr[-2000:]
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        assert key in d["config"]["workload"] and d["config"]["baseline_config"] == cfg and d["value"] > 0
