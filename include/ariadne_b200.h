@@ -194,12 +194,15 @@ int ak_residual(ak_ctx* ctx, const ak_problem* p, double* u, double* res, double
  * through bc!(u) zeroes v's boundary entries (heat_1D.jl:16,34-37).             */
 int ak_jvp(ak_ctx* ctx, const ak_problem* p, const double* u, double* v, double* out);
 /* out <- J(u)^T v  (src/Ariadne.jl:93-107).  Implemented for the operators that are symmetric in this
- * layout (Bratu 1-D/2-D, heat 2-D, heat 1-D with bc!), the 2x2 test system and the DG operator (J^T = W J W^-1
- * by upwind-SBP duality); periodic 1-D heat and AK_USER return AK_ERR_UNSUPPORTED (GMRES/CG never need J^T). */
+ * layout (Bratu 1-D/2-D, heat 2-D, heat 1-D with bc!), the 2x2 test system, the DG operator (J^T = W J W^-1
+ * by upwind-SBP duality) and 1-D heat with periodic_bc! (Euler / Trapezoid, one GPU: J = (c1 a L - I) B with the
+ * boundary copy B, adjoint kernel B^T (c1 a L^T - I)); AK_USER returns AK_ERR_UNSUPPORTED (GMRES/CG never need J^T). */
 int ak_jvp_transpose(ak_ctx* ctx, const ak_problem* p, const double* u, double* v, double* out);
 /* Out[:, c] <- J(u) V[:, c], c < ncols: the batched `mul!(Out, J, V)` of src/Ariadne.jl:69-83 for column-major
- * matrices with leading dimensions ldv, ldo >= n (one tangent sweep per column; V's boundary entries may be
- * overwritten like in ak_jvp).                                                                            */
+ * matrices with leading dimensions ldv, ldo >= n.  Bratu 1-D/2-D (the operators that depend on u): ONE multi-RHS
+ * launch, lambda e^u read (or computed) once for all columns, (16 + 8/ncols) n bytes per column; the u-independent
+ * heat / DG tangents and AK_USER: one tangent sweep per column (V's boundary entries may be overwritten like in
+ * ak_jvp).  Every column equals ak_jvp's result bit for bit.                                                  */
 int ak_jvp_batched(ak_ctx* ctx, const ak_problem* p, const double* u, double* V, int64_t ldv, double* Out,
                    int64_t ldo, int32_t ncols);
 

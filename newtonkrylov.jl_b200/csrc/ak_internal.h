@@ -219,6 +219,9 @@ struct JvpFusion {
 };
 int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double* out, const JvpFusion* f);
 int launch_jvp_transpose(Ctx* ctx, const ak_problem* p, const double* u, double* v, double* out);
+// Out[:, c] = J(u) V[:, c] for the Bratu problems with lambda e^u read once for all columns (single GPU)
+int launch_jvp_batched_bratu(Ctx* ctx, const ak_problem* p, const double* u, const double* V, int64_t ldv, double* Out,
+                             int64_t ldo, int32_t ncols);
 
 // --- krylov.cu ------------------------------------------------------------------
 }  // namespace ak

@@ -332,13 +332,47 @@ __global__ void k_cg_beta(KrylovCtl* ctl, const double* gnext_dev, int iter, int
     ctl->stop = stop;
     st->rNorm = rNorm; st->iter = iter; st->stop = stop; st->solved = solved; st->zerocurv = 0;
 }
-// p <- r + beta p  with beta from the control block
-__global__ void __launch_bounds__(256) k_cg_update_p(double* __restrict__ p, const double* __restrict__ r,
-                                                     const KrylovCtl* __restrict__ ctl, int64_t n) {
-    if (ctl->stop) return;
-    const double beta = ctl->cg_beta;
+// Tail of one CG iteration in one pass (cg!: x += alpha p ... p = r + beta p):
+//   x <- x + alpha p      for the iteration that has just been judged (also when it was the last one)
+//   p <- r + beta p       unless the solve stopped
+// 40n bytes (x and p read + written, r read) instead of 24n + 24n for the two separate updates; 256-bit accesses.
+// `k`: the iteration this launch belongs to; when the control block did not advance to k (zero curvature, or a launch
+// queued behind the stop) the kernel is a no-op.
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_cg_update_xp(double* __restrict__ x, double* __restrict__ p,
+                                                      const double* __restrict__ r, const KrylovCtl* __restrict__ ctl,
+                                                      int k, int64_t n) {
+    if (ctl->inner_iter != k) return;
+    const bool upd_p = ctl->stop == 0;
+    const double alpha = ctl->alpha, beta = ctl->cg_beta;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += nth) p[j] = fma(beta, p[j], r[j]);
+    if (VEC) {
+        const int64_t n4 = n >> 2;
+        for (int64_t i = tid; i < n4; i += nth) {
+            const int64_t j = i << 2;
+            d4 xv = ld4(x + j), pv = ld4(p + j);
+            xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y); xv.z = fma(alpha, pv.z, xv.z); xv.w = fma(alpha, pv.w, xv.w);
+            st4(x + j, xv);
+            if (upd_p) {
+                const d4 rv = ld4_stream(r + j);
+                pv.x = fma(beta, pv.x, rv.x); pv.y = fma(beta, pv.y, rv.y); pv.z = fma(beta, pv.z, rv.z); pv.w = fma(beta, pv.w, rv.w);
+                st4(p + j, pv);
+            }
+        }
+        const int64_t j = (n4 << 2) + tid;
+        if (j < n) {
+            const double pj = p[j];
+            x[j] = fma(alpha, pj, x[j]);
+            if (upd_p) p[j] = fma(beta, pj, r[j]);
+        }
+    } else {
+        for (int64_t j = tid; j < n; j += nth) {
+            const double pj = p[j];
+            x[j] = fma(alpha, pj, x[j]);
+            if (upd_p) p[j] = fma(beta, pj, r[j]);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -907,22 +941,24 @@ static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, cons
             const int slot = (int)(k % kStatusRing);
             k_cg_alpha<<<1, 32, 0, sm>>>(ws->ctl, ws->hcol + 1, &ws->status[slot]);
             c->launches++;
-            // x += alpha p ; r -= alpha Ap (+ gamma_next = <r, r>)
-            {
-                // y += s_dev * x  kernels honour the stop flag through launch_mgs_step / k_ew
-                AK_TRY(launch_mgs_step(c, n, x, p, &ws->ctl->neg_alpha, nullptr, 0, nullptr, stop));
-                AK_TRY(launch_mgs_step(c, n, r, Ap, &ws->ctl->alpha, nullptr, 1, ws->hcol + 2, stop));
-            }
+            // r -= alpha Ap (+ gamma_next = <r, r>); the x update rides with the p update below (same values:
+            // x += alpha p uses the p of this iteration, which is only overwritten afterwards)
+            AK_TRY(launch_mgs_step(c, n, r, Ap, &ws->ctl->alpha, nullptr, 1, ws->hcol + 2, stop));
             k_cg_beta<<<1, 32, 0, sm>>>(ws->ctl, ws->hcol + 2, (int)k, itmax, want_hist ? ws->hist : nullptr,
                                         &ws->status[slot]);
             c->launches++;
             AK_CUDA(cudaGetLastError());
             AK_CUDA(cudaEventRecord(ws->ev[slot], sm));
-            // p <- r + beta p
+            // x += alpha p ; p <- r + beta p   (one pass)
             {
-                int blocks = (int)((n + 255) / 256);
-                if (blocks > c->num_sms * 8) blocks = c->num_sms * 8;
-                k_cg_update_p<<<blocks, 256, 0, sm>>>(p, r, ws->ctl, n);
+                int64_t blocks = (n + 1023) / 1024;
+                if (blocks > (int64_t)c->num_sms * 4) blocks = (int64_t)c->num_sms * 4;
+                if (blocks < 1) blocks = 1;
+                const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(p) |
+                                   reinterpret_cast<uintptr_t>(r)) & 31u) == 0;
+                ProfScope prof(c, PK_ELEMENTWISE);
+                if (vec) k_cg_update_xp<true><<<(int)blocks, 256, 0, sm>>>(x, p, r, ws->ctl, (int)k, n);
+                else k_cg_update_xp<false><<<(int)blocks, 256, 0, sm>>>(x, p, r, ws->ctl, (int)k, n);
                 c->launches++;
                 AK_CUDA(cudaGetLastError());
             }

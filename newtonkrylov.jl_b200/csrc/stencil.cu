@@ -337,18 +337,21 @@ AK_DEV double heat1d_bc_value(const double* src, int64_t i, int64_t n, int bc) {
     return src[i];
 }
 
+// One wave of resident blocks walks the array (grid-stride over chunks of VEC points); every thread keeps TWO chunks
+// in flight per trip: all vector loads of both chunks are issued before either is finished, so each operand stream has
+// two independent 256-bit requests outstanding per thread (the launch-per-chunk version sat at 74-83 % of the copy
+// bandwidth at N = 2^24: one request per thread and 16 K blocks to schedule).
 template <int OP, int VEC, bool SCALE, int RED>
-__global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
+__global__ void __launch_bounds__(kT1, 2) k_stencil1d(const StencilArgs p) {
     __shared__ double sh[32];
     if (p.stop != nullptr && *p.stop != 0) return;
     const int lane = threadIdx.x & 31;
     const int64_t n = p.nx;
-    const int64_t x0 = ((int64_t)blockIdx.x * kT1 + threadIdx.x) * VEC;
-    const bool active = x0 < n;
     const Divisor denom = make_divisor(SCALE ? *p.denom : 1.0);
     const Divisor dx2 = make_divisor(p.dx2);
     constexpr bool HEAT = (OP == OP_RES_HEAT || OP == OP_JVP_HEAT || OP == OP_RHS_HEAT);
     constexpr bool FD = (OP == OP_JVP_BRATU_FD);
+    constexpr bool AUX = (OP == OP_JVP_BRATU || OP == OP_RES_HEAT);
     const bool oscale_on = (OP == OP_JVP_BRATU || OP == OP_JVP_HEAT || FD) && p.out_scale != nullptr;
     const double oscale = oscale_on ? __ddiv_rn(1.0, *p.out_scale) : 1.0;
     // fused finite-difference JVP: second window over u (p.aux, ghosts p.aux_lo / p.aux_hi); u + eps v is never stored
@@ -357,7 +360,6 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
         if (i >= n) return p.aux_hi ? p.aux_hi[0] : 0.0;
         return p.aux[i];
     };
-
     auto value = [&](int64_t i) -> double {  // scalar access incl. boundary semantics
         double v;
         if (i < 0) {  // left of this segment: neighbour rank's last point, or y_0 = 0 (Bratu: bratu.jl:17)
@@ -375,60 +377,72 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
         return v;
     };
 
-    double cur[VEC];
+    struct Chunk {
+        int64_t x0;
+        bool active;
+        double cur[VEC], aux[VEC], ucur[VEC], bb[VEC], dw[VEC];
+    };
+    // phase 1: every global vector load of the chunk
+    auto load_chunk = [&](Chunk& c, int64_t x0) {
+        c.x0 = x0;
+        c.active = x0 < n;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) cur[i] = 0.0;
-    if (active) {
-        ldv<VEC>(p.in + x0, cur);
-        if (SCALE) {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) cur[i] = div_by(cur[i], denom);
-        }
-        if (HEAT) {  // the global end points take their BC value
-            if (x0 == 0 && p.seg_first) cur[0] = value(0);
-            if (x0 + VEC == n && p.seg_last) cur[VEC - 1] = value(n - 1);
-        }
-    }
-    double left = __shfl_up_sync(0xffffffffu, cur[VEC - 1], 1);
-    double right = __shfl_down_sync(0xffffffffu, cur[0], 1);
-    double ucur[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) ucur[i] = 0.0;
-    if (FD && active) ldv<VEC>(p.aux + x0, ucur);
-    double uleft = 0.0, uright = 0.0;
-    if (FD) {
-        uleft = __shfl_up_sync(0xffffffffu, ucur[VEC - 1], 1);
-        uright = __shfl_down_sync(0xffffffffu, ucur[0], 1);
-    }
+        for (int i = 0; i < VEC; ++i) c.cur[i] = c.aux[i] = c.ucur[i] = c.bb[i] = c.dw[i] = 0.0;
+        if (!c.active) return;
+        ldv<VEC>(p.in + x0, c.cur);
+        if (AUX) ldv_s<VEC>(p.aux + x0, c.aux);
+        if (FD) ldv<VEC>(p.aux + x0, c.ucur);
+        if (p.bminus != nullptr) ldv_s<VEC>(p.bminus + x0, c.bb);
+        if (RED == RED_DOT) ldv_s<VEC>(p.dot_with + x0, c.dw);
+    };
     double acc = 0.0;
-    if (active) {
+    // phase 2: boundary semantics, neighbours (shuffles; warp-edge lanes load one scalar), arithmetic, stores
+    auto finish_chunk = [&](Chunk& c) {
+        const int64_t x0 = c.x0;
+        if (c.active) {
+            if (SCALE) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) c.cur[i] = div_by(c.cur[i], denom);
+            }
+            if (HEAT) {  // the global end points take their BC value
+                if (x0 == 0 && p.seg_first) c.cur[0] = value(0);
+                if (x0 + VEC == n && p.seg_last) c.cur[VEC - 1] = value(n - 1);
+            }
+        }
+        double left = __shfl_up_sync(0xffffffffu, c.cur[VEC - 1], 1);
+        double right = __shfl_down_sync(0xffffffffu, c.cur[0], 1);
+        double uleft = 0.0, uright = 0.0;
+        if (FD) {
+            uleft = __shfl_up_sync(0xffffffffu, c.ucur[VEC - 1], 1);
+            uright = __shfl_down_sync(0xffffffffu, c.ucur[0], 1);
+        }
+        if (!c.active) return;
         if (lane == 0) left = value(x0 - 1);
         if (lane == 31 || x0 + VEC >= n) right = value(x0 + VEC);
         if (FD) {
             if (lane == 0) uleft = uvalue(x0 - 1);
             if (lane == 31 || x0 + VEC >= n) uright = uvalue(x0 + VEC);
         }
-        double aux[VEC], o[VEC], cf[VEC];
-        if (OP == OP_JVP_BRATU || OP == OP_RES_HEAT) ldv_s<VEC>(p.aux + x0, aux);
+        double o[VEC], cf[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const double w = (i == 0) ? left : cur[i - 1];
-            const double e = (i == VEC - 1) ? right : cur[(i + 1) % VEC];
-            const double c = cur[i];
+            const double w = (i == 0) ? left : c.cur[i > 0 ? i - 1 : 0];
+            const double e = (i == VEC - 1) ? right : c.cur[(i + 1) % VEC];
+            const double cc = c.cur[i];
             if (OP == OP_RES_BRATU) {
-                cf[i] = __dmul_rn(p.lambda, exp(c));
-                o[i] = __dadd_rn(second_diff(e, c, w, dx2), cf[i]);
+                cf[i] = __dmul_rn(p.lambda, exp(cc));
+                o[i] = __dadd_rn(second_diff(e, cc, w, dx2), cf[i]);
             } else if (OP == OP_JVP_BRATU) {
-                const double k = p.coef_from_u ? __dmul_rn(p.lambda, exp(aux[i])) : aux[i];
-                o[i] = __dadd_rn(second_diff(e, c, w, dx2), __dmul_rn(k, c));
+                const double k = p.coef_from_u ? __dmul_rn(p.lambda, exp(c.aux[i])) : c.aux[i];
+                o[i] = __dadd_rn(second_diff(e, cc, w, dx2), __dmul_rn(k, cc));
             } else if (FD) {
                 // J v ~ (F(u + eps v) - F(u)) / eps, both residuals of bratu! (bratu.jl:14-24) evaluated at this point
                 const double eps = p.fd_eps;
-                const double uc = ucur[i];
-                const double uw = (i == 0) ? uleft : ucur[i > 0 ? i - 1 : 0];
-                const double ue = (i == VEC - 1) ? uright : ucur[(i + 1) % VEC];
+                const double uc = c.ucur[i];
+                const double uw = (i == 0) ? uleft : c.ucur[i > 0 ? i - 1 : 0];
+                const double ue = (i == VEC - 1) ? uright : c.ucur[(i + 1) % VEC];
                 const double f0 = __dadd_rn(second_diff(ue, uc, uw, dx2), __dmul_rn(p.lambda, exp(uc)));
-                const double pc = fma(eps, c, uc), pw = fma(eps, w, uw), pe = fma(eps, e, ue);
+                const double pc = fma(eps, cc, uc), pw = fma(eps, w, uw), pe = fma(eps, e, ue);
                 const double f1 = __dadd_rn(second_diff(pe, pc, pw, dx2), __dmul_rn(p.lambda, exp(pc)));
                 o[i] = __ddiv_rn(__dsub_rn(f1, f0), eps);
             } else {
@@ -436,10 +450,10 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
                 const int64_t gi = x0 + i;
                 const bool bnd = (gi == 0 && p.seg_first) || (gi == n - 1 && p.seg_last);
                 const double du =
-                    bnd ? 0.0 : div_by(__dmul_rn(p.a, __dadd_rn(__dsub_rn(e, __dmul_rn(2.0, c)), w)), dx2);
-                if (OP == OP_RES_HEAT) o[i] = __dsub_rn(__dadd_rn(aux[i], __dmul_rn(p.dt, du)), c);
+                    bnd ? 0.0 : div_by(__dmul_rn(p.a, __dadd_rn(__dsub_rn(e, __dmul_rn(2.0, cc)), w)), dx2);
+                if (OP == OP_RES_HEAT) o[i] = __dsub_rn(__dadd_rn(c.aux[i], __dmul_rn(p.dt, du)), cc);
                 else if (OP == OP_RHS_HEAT) o[i] = du;
-                else o[i] = __dsub_rn(__dmul_rn(p.c1, du), c);
+                else o[i] = __dsub_rn(__dmul_rn(p.c1, du), cc);
             }
         }
         if (oscale_on) {
@@ -447,29 +461,37 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
             for (int i = 0; i < VEC; ++i) o[i] = __dmul_rn(o[i], oscale);
         }
         if (p.bminus != nullptr) {
-            double bb[VEC];
-            ldv_s<VEC>(p.bminus + x0, bb);
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) o[i] = __dsub_rn(bb[i], o[i]);
+            for (int i = 0; i < VEC; ++i) o[i] = __dsub_rn(c.bb[i], o[i]);
         }
         stv<VEC>(p.out + x0, o);
         if (OP == OP_RES_BRATU && p.aux_out != nullptr) stv<VEC>(p.aux_out + x0, cf);
         if (SCALE) {
-            stv<VEC>(p.in_write + x0, cur);
+            stv<VEC>(p.in_write + x0, c.cur);
         } else if (HEAT && p.in_write != nullptr) {
             // the reference's bc!(u) mutates the state / tangent seed in place (heat_1D.jl:16,34-42)
-            if (x0 == 0 && p.seg_first) p.in_write[0] = cur[0];
-            if (x0 + VEC == n && p.seg_last) p.in_write[n - 1] = cur[VEC - 1];
+            if (x0 == 0 && p.seg_first) p.in_write[0] = c.cur[0];
+            if (x0 + VEC == n && p.seg_last) p.in_write[n - 1] = c.cur[VEC - 1];
         }
         if (RED == RED_SUMSQ) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc = fma(o[i], o[i], acc);
         } else if (RED == RED_DOT) {
-            double dw[VEC];
-            ldv_s<VEC>(p.dot_with + x0, dw);
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc = fma(dw[i], o[i], acc);
+            for (int i = 0; i < VEC; ++i) acc = fma(c.dw[i], o[i], acc);
         }
+    };
+
+    const int64_t nchunks = (n + VEC - 1) / VEC;
+    const int64_t nth = (int64_t)gridDim.x * kT1;
+    // warp-uniform trip count (the shuffles need whole warps): the warp stays in the loop while its first lane has work
+    for (int64_t ch = (int64_t)blockIdx.x * kT1 + threadIdx.x; ch - lane < nchunks; ch += 2 * nth) {
+        Chunk a, b;
+        const bool second = (ch + nth - lane) < nchunks;
+        load_chunk(a, ch * VEC);
+        if (second) load_chunk(b, (ch + nth) * VEC);
+        finish_chunk(a);
+        if (second) finish_chunk(b);
     }
     if (RED != RED_NONE) {
         const double s = block_sum(acc, sh);
@@ -515,16 +537,18 @@ AK_DEV void dg_local(const double (&D)[4][4], double jac, const double (&u)[4], 
     }
 }
 
+// One thread per element and trip; one wave of resident blocks walks the mesh with two elements in flight per thread
+// (all vector loads of both elements are issued before either is finished).
 template <bool RESIDUAL, bool SCALE, int RED>
-__global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
+__global__ void __launch_bounds__(kT1, 2) k_dg(const DgArgs p) {
     __shared__ double sh[32];
     if (p.stop != nullptr && *p.stop != 0) return;
     const int lane = threadIdx.x & 31;
     const int64_t ne = p.ne;
-    const int64_t e = (int64_t)blockIdx.x * kT1 + threadIdx.x;
-    const bool active = e < ne;
     const Divisor denom = make_divisor(SCALE ? *p.denom : 1.0);
     const Divisor mw = make_divisor(p.mw);
+    const bool oscale_on = !RESIDUAL && !p.rhs_only && p.out_scale != nullptr;
+    const double oscale = oscale_on ? __ddiv_rn(1.0, *p.out_scale) : 1.0;
 
     auto load_elem = [&](int64_t el, double (&r)[4]) {
         ldv<4>((el < 0) ? p.lo : p.in + 4 * el, r);
@@ -534,39 +558,57 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
             if (!RESIDUAL) r[i] = __dmul_rn(p.c0, r[i]);
         }
     };
-    double u[4] = {0, 0, 0, 0}, raw[4] = {0, 0, 0, 0};
-    if (active) {
-        ldv<4>(p.in + 4 * e, raw);
+    struct Elem {
+        int64_t e;
+        bool active;
+        double raw[4], un[4], bb[4], dw[4];
+    };
+    auto load = [&](Elem& c, int64_t e) {
+        c.e = e;
+        c.active = e < ne;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (SCALE) raw[i] = div_by(raw[i], denom);
-            u[i] = RESIDUAL ? raw[i] : __dmul_rn(p.c0, raw[i]);
-        }
-    }
-    // D1p: needs first node of the element to the right
-    double u_next0 = __shfl_down_sync(0xffffffffu, u[0], 1);
-    if (active && (lane == 31 || e + 1 >= ne)) {
-        const int64_t en = (e + 1 == ne) ? 0 : e + 1;
-        double t = (e + 1 == ne && p.hi != nullptr) ? p.hi[0] : p.in[4 * en];
-        if (SCALE) t = div_by(t, denom);
-        u_next0 = RESIDUAL ? t : __dmul_rn(p.c0, t);
-    }
-    double t1[4] = {0, 0, 0, 0};
-    if (active) {
-        dg_local(p.D, p.jac, u, t1);
-        t1[3] = __dadd_rn(t1[3], div_by(__dsub_rn(u_next0, u[3]), mw));
-    }
-    // D1m: needs last node of (D1p u) of the element to the left
-    double t_prev3 = __shfl_up_sync(0xffffffffu, t1[3], 1);
-    if (active && lane == 0) {
-        const int64_t ep = (e == 0) ? ((p.lo != nullptr) ? -1 : ne - 1) : e - 1;
-        double up[4], tp[4];
-        load_elem(ep, up);
-        dg_local(p.D, p.jac, up, tp);
-        t_prev3 = __dadd_rn(tp[3], div_by(__dsub_rn(u[0], up[3]), mw));
-    }
+        for (int i = 0; i < 4; ++i) c.raw[i] = c.un[i] = c.bb[i] = c.dw[i] = 0.0;
+        if (!c.active) return;
+        ldv<4>(p.in + 4 * e, c.raw);
+        if (RESIDUAL && !p.rhs_only) ldv_s<4>(p.un + 4 * e, c.un);
+        if (!RESIDUAL && p.bminus != nullptr) ldv_s<4>(p.bminus + 4 * e, c.bb);
+        if (RED == RED_DOT) ldv_s<4>(p.dot_with + 4 * e, c.dw);
+    };
     double acc = 0.0;
-    if (active) {
+    auto finish = [&](Elem& c) {
+        const int64_t e = c.e;
+        const bool active = c.active;
+        double u[4] = {0, 0, 0, 0};
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (SCALE) c.raw[i] = div_by(c.raw[i], denom);
+                u[i] = RESIDUAL ? c.raw[i] : __dmul_rn(p.c0, c.raw[i]);
+            }
+        }
+        // D1p: needs first node of the element to the right
+        double u_next0 = __shfl_down_sync(0xffffffffu, u[0], 1);
+        if (active && (lane == 31 || e + 1 >= ne)) {
+            const int64_t en = (e + 1 == ne) ? 0 : e + 1;
+            double t = (e + 1 == ne && p.hi != nullptr) ? p.hi[0] : p.in[4 * en];
+            if (SCALE) t = div_by(t, denom);
+            u_next0 = RESIDUAL ? t : __dmul_rn(p.c0, t);
+        }
+        double t1[4] = {0, 0, 0, 0};
+        if (active) {
+            dg_local(p.D, p.jac, u, t1);
+            t1[3] = __dadd_rn(t1[3], div_by(__dsub_rn(u_next0, u[3]), mw));
+        }
+        // D1m: needs last node of (D1p u) of the element to the left
+        double t_prev3 = __shfl_up_sync(0xffffffffu, t1[3], 1);
+        if (active && lane == 0) {
+            const int64_t ep = (e == 0) ? ((p.lo != nullptr) ? -1 : ne - 1) : e - 1;
+            double up[4], tp[4];
+            load_elem(ep, up);
+            dg_local(p.D, p.jac, up, tp);
+            t_prev3 = __dadd_rn(tp[3], div_by(__dsub_rn(u[0], up[3]), mw));
+        }
+        if (!active) return;
         double du[4], o[4];
         dg_local(p.D, p.jac, t1, du);
         du[0] = __dadd_rn(du[0], div_by(__dsub_rn(t1[0], t_prev3), mw));
@@ -574,36 +616,38 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] = du[i];
         } else if (RESIDUAL) {
-            double un[4];
-            ldv_s<4>(p.un + 4 * e, un);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dadd_rn(un[i], __dmul_rn(p.dt, du[i])), raw[i]);
+            for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dadd_rn(c.un[i], __dmul_rn(p.dt, du[i])), c.raw[i]);
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dmul_rn(p.c1, du[i]), raw[i]);
-            if (p.out_scale != nullptr) {
-                const double oscale = __ddiv_rn(1.0, *p.out_scale);
+            for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dmul_rn(p.c1, du[i]), c.raw[i]);
+            if (oscale_on) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) o[i] = __dmul_rn(o[i], oscale);
             }
             if (p.bminus != nullptr) {
-                double bb[4];
-                ldv_s<4>(p.bminus + 4 * e, bb);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(bb[i], o[i]);
+                for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(c.bb[i], o[i]);
             }
         }
         stv<4>(p.out + 4 * e, o);
-        if (SCALE) stv<4>(p.in_write + 4 * e, raw);
+        if (SCALE) stv<4>(p.in_write + 4 * e, c.raw);
         if (RED == RED_SUMSQ) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc = fma(o[i], o[i], acc);
         } else if (RED == RED_DOT) {
-            double dw[4];
-            ldv_s<4>(p.dot_with + 4 * e, dw);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc = fma(dw[i], o[i], acc);
+            for (int i = 0; i < 4; ++i) acc = fma(c.dw[i], o[i], acc);
         }
+    };
+    const int64_t nth = (int64_t)gridDim.x * kT1;
+    for (int64_t e = (int64_t)blockIdx.x * kT1 + threadIdx.x; e - lane < ne; e += 2 * nth) {
+        Elem a, b;
+        const bool second = (e + nth - lane) < ne;
+        load(a, e);
+        if (second) load(b, e + nth);
+        finish(a);
+        if (second) finish(b);
     }
     if (RED != RED_NONE) {
         const double s = block_sum(acc, sh);
@@ -635,6 +679,164 @@ __global__ void k_simple2(const double* u, const double* v, double* out, double*
     if (red_out != nullptr) {
         if (dot_with != nullptr) *red_out = fma(dot_with[1], o1, dot_with[0] * o0);
         else *red_out = fma(o1, o1, o0 * o0);
+    }
+}
+
+// ========================================================================================
+// Multi-RHS tangent: Out[:, c] = J(u) V[:, c], c < ncols  —  `mul!(Out, J, V)` of src/Ariadne.jl:69-83 and the probe
+// products of `collect(J)` (:140-162).  The operand every column shares, lambda e^u, is read (or computed: one `exp`
+// per point) ONCE per tile and kept in registers while the columns stream through: (16 + 8/ncols) n bytes per column
+// instead of 24n, and one launch instead of ncols.  Arithmetic per column is the single-column kernel's, bit for bit.
+// (The heat and DG tangents do not depend on u: their columns share nothing and stay a loop of single launches.)
+// ========================================================================================
+struct BatchArgs {
+    int64_t nx, ny;
+    double dx2, dy2, lambda;
+    const double* aux;   // cached lambda e^u, or u when coef_from_u
+    int32_t coef_from_u;
+    const double* V;
+    int64_t ldv;
+    double* Out;
+    int64_t ldo;
+    int32_t ncols;
+};
+constexpr int kBatchRY = 8;  // rows per tile of the 2-D batched kernel (tile of lambda e^u: kBatchRY x VEC registers)
+
+template <int VEC>
+__global__ void __launch_bounds__(kTX, 4) k_bratu2d_jvp_batched(const BatchArgs p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nx = p.nx, ny = p.ny;
+    const int64_t x0 = ((int64_t)blockIdx.x * kTX + threadIdx.x) * VEC;
+    const bool active = x0 < nx;
+    const int64_t y0 = (int64_t)blockIdx.y * kBatchRY;
+    const int64_t y1 = (y0 + kBatchRY < ny) ? y0 + kBatchRY : ny;
+    const Divisor dx2 = make_divisor(p.dx2), dy2 = make_divisor(p.dy2);
+    double kc[kBatchRY][VEC];
+#pragma unroll
+    for (int r = 0; r < kBatchRY; ++r) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) kc[r][i] = 0.0;
+        if (active && y0 + r < y1) {
+            ldv_s<VEC>(p.aux + (y0 + r) * nx + x0, kc[r]);
+            if (p.coef_from_u) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) kc[r][i] = __dmul_rn(p.lambda, exp(kc[r][i]));
+            }
+        }
+    }
+    const bool need_l = active && lane == 0;
+    const bool need_r = active && (lane == 31 || x0 + VEC >= nx);
+    for (int c = 0; c < p.ncols; ++c) {
+        const double* in = p.V + (int64_t)c * p.ldv;
+        double* out = p.Out + (int64_t)c * p.ldo;
+        auto load_row = [&](int64_t y, double (&r)[VEC]) {
+            if (!active || y < 0 || y >= ny) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) r[i] = 0.0;
+                return;
+            }
+            ldv<VEC>(in + y * nx + x0, r);
+        };
+        auto edge = [&](int64_t y, int64_t x) -> double { return (x < 0 || x >= nx) ? 0.0 : in[y * nx + x]; };
+        double prev[VEC], cur[VEC], next[VEC];
+        load_row(y0 - 1, prev);
+        load_row(y0, cur);
+#pragma unroll
+        for (int r = 0; r < kBatchRY; ++r) {
+            const int64_t y = y0 + r;
+            if (y < y1) {  // block-uniform
+                load_row(y + 1, next);
+                double left = __shfl_up_sync(0xffffffffu, cur[VEC - 1], 1);
+                double right = __shfl_down_sync(0xffffffffu, cur[0], 1);
+                if (active) {
+                    if (need_l) left = edge(y, x0 - 1);
+                    if (need_r) right = edge(y, x0 + VEC);
+                    double o[VEC];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        const double w = (i == 0) ? left : cur[i > 0 ? i - 1 : 0];
+                        const double e = (i == VEC - 1) ? right : cur[(i + 1) % VEC];
+                        const double cc = cur[i];
+                        const double lap = __dadd_rn(second_diff(e, cc, w, dx2), second_diff(next[i], cc, prev[i], dy2));
+                        o[i] = __dadd_rn(lap, __dmul_rn(kc[r][i], cc));
+                    }
+                    stv<VEC>(out + y * nx + x0, o);
+                }
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) { prev[i] = cur[i]; cur[i] = next[i]; }
+            }
+        }
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kT1, 2) k_bratu1d_jvp_batched(const BatchArgs p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = p.nx;
+    const Divisor dx2 = make_divisor(p.dx2);
+    const int64_t nchunks = (n + VEC - 1) / VEC;
+    const int64_t nth = (int64_t)gridDim.x * kT1;
+    for (int64_t ch = (int64_t)blockIdx.x * kT1 + threadIdx.x; ch - lane < nchunks; ch += nth) {
+        const int64_t x0 = ch * VEC;
+        const bool active = x0 < n;
+        double kc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) kc[i] = 0.0;
+        if (active) {
+            ldv_s<VEC>(p.aux + x0, kc);
+            if (p.coef_from_u) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) kc[i] = __dmul_rn(p.lambda, exp(kc[i]));
+            }
+        }
+        for (int c = 0; c < p.ncols; ++c) {
+            const double* in = p.V + (int64_t)c * p.ldv;
+            double cur[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) cur[i] = 0.0;
+            if (active) ldv<VEC>(in + x0, cur);
+            double left = __shfl_up_sync(0xffffffffu, cur[VEC - 1], 1);
+            double right = __shfl_down_sync(0xffffffffu, cur[0], 1);
+            if (active) {
+                if (lane == 0) left = x0 > 0 ? in[x0 - 1] : 0.0;
+                if (lane == 31 || x0 + VEC >= n) right = x0 + VEC < n ? in[x0 + VEC] : 0.0;
+                double o[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const double w = (i == 0) ? left : cur[i > 0 ? i - 1 : 0];
+                    const double e = (i == VEC - 1) ? right : cur[(i + 1) % VEC];
+                    o[i] = __dadd_rn(second_diff(e, cur[i], w, dx2), __dmul_rn(kc[i], cur[i]));
+                }
+                stv<VEC>(p.Out + (int64_t)c * p.ldo + x0, o);
+            }
+        }
+    }
+}
+
+// out <- J^T v for the 1-D heat operator with periodic_bc! (heat_1D.jl:39-42).  The forward tangent is
+// J = (c1 a L - I) B: B copies v[n-2] -> v[0], v[1] -> v[n-1] (the BC code), L is the three-point row
+// a (e - 2c + w) / dx^2 on the interior rows and zero on rows 0 and n-1.  Hence J^T = B^T (c1 a L^T - I):
+//   y[j]   = c1 * (a * ((wt[j+1] - 2 wt[j]) + wt[j-1]) / dx^2) - v[j],  wt = v with wt[0] = wt[n-1] = 0
+//   out[j] = y[j] (interior), out[1] += y[n-1], out[n-2] += y[0], out[0] = out[n-1] = 0.
+// Applied to a unit vector this reproduces the entries of the forward kernel bit for bit (same formula per entry).
+__global__ void __launch_bounds__(256) k_heat1d_periodic_transpose(const double* __restrict__ v, double* __restrict__ out,
+                                                                   int64_t n, double a, double dx2v, double c1) {
+    const Divisor dx2 = make_divisor(dx2v);
+    auto wt = [&](int64_t i) -> double { return (i <= 0 || i >= n - 1) ? 0.0 : v[i]; };
+    auto y = [&](int64_t j) -> double {
+        const double du = div_by(__dmul_rn(a, __dadd_rn(__dsub_rn(wt(j + 1), __dmul_rn(2.0, wt(j))), wt(j - 1))), dx2);
+        return __dsub_rn(__dmul_rn(c1, du), v[j]);
+    };
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += nth) {
+        double o;
+        if (j == 0 || j == n - 1) o = 0.0;
+        else {
+            o = y(j);
+            if (j == 1) o = __dadd_rn(o, y(n - 1));
+            if (j == n - 2) o = __dadd_rn(o, y(0));
+        }
+        out[j] = o;
     }
 }
 
@@ -719,11 +921,11 @@ static int launch1d(Ctx* ctx, StencilArgs& a, bool scale, int red) {
     };
     if (ok(4)) vec = 4;
     else if (ok(2)) vec = 2;
+    // one wave of resident blocks (2 x 256 threads per SM: the register budget of the launch bounds), grid-stride
     int64_t grid = (a.nx + (int64_t)kT1 * vec - 1) / ((int64_t)kT1 * vec);
-    if (grid > kMaxPartials && red != RED_NONE) {
-        set_error("1-D stencil with fused reduction: n too large for the partials buffer");
-        return AK_ERR_UNSUPPORTED;
-    }
+    const int64_t cap = (int64_t)ctx->num_sms * 2;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
     if (vec == 4) launch1d_v<OP, 4>(ctx, a, scale, red, (int)grid);
     else if (vec == 2) launch1d_v<OP, 2>(ctx, a, scale, red, (int)grid);
     else launch1d_v<OP, 1>(ctx, a, scale, red, (int)grid);
@@ -744,11 +946,10 @@ static void dg_constants(DgArgs& d, double h) {
 }
 
 static int launch_dg(Ctx* ctx, DgArgs& d, bool residual, bool scale, int red) {
-    const int64_t grid = (d.ne + kT1 - 1) / kT1;
-    if (grid > kMaxPartials && red != RED_NONE) {
-        set_error("DG stencil with fused reduction: n too large for the partials buffer");
-        return AK_ERR_UNSUPPORTED;
-    }
+    int64_t grid = (d.ne + kT1 - 1) / kT1;  // one wave of resident blocks (2 per SM), grid-stride over the elements
+    const int64_t cap = (int64_t)ctx->num_sms * 2;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
 #define AK_LDG(RS, S, R) k_dg<RS, S, R><<<(int)grid, kT1, 0, ctx->stream>>>(d)
     if (residual) {
         if (red == RED_SUMSQ) AK_LDG(true, false, RED_SUMSQ);
@@ -1169,6 +1370,46 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     return AK_OK;
 }
 
+int launch_jvp_batched_bratu(Ctx* ctx, const ak_problem* p, const double* u, const double* V, int64_t ldv, double* Out,
+                             int64_t ldo, int32_t ncols) {
+    AK_TRY(check_problem(p));
+    BatchArgs a{};
+    a.nx = p->nx;
+    a.ny = p->kind == AK_BRATU2D ? p->ny : 1;
+    a.dx2 = p->dx * p->dx;
+    a.dy2 = p->dy * p->dy;
+    a.lambda = p->lambda;
+    a.aux = p->coef ? p->coef : u;
+    a.coef_from_u = p->coef ? 0 : 1;
+    a.V = V; a.ldv = ldv; a.Out = Out; a.ldo = ldo; a.ncols = ncols;
+    int vec = 1;
+    auto ok = [&](int v) {
+        return a.nx % v == 0 && ldv % v == 0 && ldo % v == 0 && al(a.aux, 8 * v) && al(V, 8 * v) && al(Out, 8 * v);
+    };
+    if (ok(4)) vec = 4;
+    else if (ok(2)) vec = 2;
+    ProfScope prof(ctx, PK_JVP);
+    if (p->kind == AK_BRATU2D) {
+        const int64_t gx = (a.nx + (int64_t)kTX * vec - 1) / ((int64_t)kTX * vec);
+        const int64_t gy = (a.ny + kBatchRY - 1) / kBatchRY;
+        if (gy > 65535) { set_error("ak_jvp_batched: more than 65535 row tiles"); return AK_ERR_UNSUPPORTED; }
+        dim3 grid((unsigned)gx, (unsigned)gy);
+        if (vec == 4) k_bratu2d_jvp_batched<4><<<grid, kTX, 0, ctx->stream>>>(a);
+        else if (vec == 2) k_bratu2d_jvp_batched<2><<<grid, kTX, 0, ctx->stream>>>(a);
+        else k_bratu2d_jvp_batched<1><<<grid, kTX, 0, ctx->stream>>>(a);
+    } else {
+        int64_t grid = (a.nx + (int64_t)kT1 * vec - 1) / ((int64_t)kT1 * vec);
+        const int64_t cap = (int64_t)ctx->num_sms * 2;
+        if (grid > cap) grid = cap;
+        if (vec == 4) k_bratu1d_jvp_batched<4><<<(int)grid, kT1, 0, ctx->stream>>>(a);
+        else if (vec == 2) k_bratu1d_jvp_batched<2><<<(int)grid, kT1, 0, ctx->stream>>>(a);
+        else k_bratu1d_jvp_batched<1><<<(int)grid, kT1, 0, ctx->stream>>>(a);
+    }
+    ctx->launches++;
+    AK_CUDA(cudaGetLastError());
+    return AK_OK;
+}
+
 // y[j] = x[j] * s[j % 4]   (node-wise scaling of a DG vector: 4 LGL nodes per element)
 __global__ void __launch_bounds__(256) k_scale_nodes4(double* __restrict__ y, const double* __restrict__ x, double s0,
                                                       double s1, double s2, double s3, int64_t n) {
@@ -1209,6 +1450,15 @@ int launch_jvp_transpose(Ctx* ctx, const ak_problem* p, const double* u, double*
             return launch_jvp(ctx, p, u, v, out, nullptr);
         case AK_HEAT1D:
             if (p->bc == AK_BC_ZERO) return launch_jvp(ctx, p, u, v, out, nullptr);  // zero boundary rows/cols: symmetric
+            if (p->scheme != AK_MIDPOINT && ctx->nranks == 1 && p->nx >= 4) {
+                // periodic_bc! makes J = (c1 a L - I) B non-symmetric: dedicated adjoint kernel
+                const double c1 = (p->scheme == AK_TRAPEZOID) ? p->dt / 2.0 : p->dt;
+                k_heat1d_periodic_transpose<<<ew_blocks(ctx, p->nx), 256, 0, ctx->stream>>>(v, out, p->nx, p->a,
+                                                                                          p->dx * p->dx, c1);
+                ctx->launches++;
+                AK_CUDA(cudaGetLastError());
+                return AK_OK;
+            }
             break;
         default: break;
     }
@@ -1251,7 +1501,15 @@ AK_API int ak_jvp_batched(ak_ctx* ctx, const ak_problem* p, const double* u, dou
     AK_REQUIRE(ctx && p && V && Out && ncols >= 0, "ak_jvp_batched: bad argument");
     const int64_t n = ak_problem_size(p);
     AK_REQUIRE(ldv >= n && ldo >= n, "ak_jvp_batched: leading dimensions must be >= n");
-    for (int32_t c = 0; c < ncols; ++c) AK_TRY(launch_jvp(&ctx->c, p, u, V + (int64_t)c * ldv, Out + (int64_t)c * ldo, nullptr));
+    Ctx* c_ = &ctx->c;
+    // Bratu tangents share lambda e^u between the columns: multi-RHS kernels (one launch, the shared operand read once)
+    const bool bratu = (p->kind == AK_BRATU2D || p->kind == AK_BRATU1D) && p->jvp_mode == AK_JVP_ANALYTIC &&
+                       c_->nranks == 1 && ncols >= 2 && (p->coef != nullptr || u != nullptr);
+    if (bratu) {
+        AK_TRY(launch_jvp_batched_bratu(c_, p, u, V, ldv, Out, ldo, ncols));
+        return AK_OK;
+    }
+    for (int32_t c = 0; c < ncols; ++c) AK_TRY(launch_jvp(c_, p, u, V + (int64_t)c * ldv, Out + (int64_t)c * ldo, nullptr));
     return AK_OK;
 }
 

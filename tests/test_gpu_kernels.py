@@ -6,6 +6,8 @@ Bratu involves exp(): CUDA libdevice and glibc each stay within 1 ulp of the tru
 coefficient lambda*exp(u) may differ by a few ulp -> compared relative to the row scale.
 Reductions differ in summation order -> 1e-13 relative.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -344,6 +346,60 @@ def test_batched_jvp(nk, ctx):
         o = u.zero()
         nk.mul_(o, J, nk.DeviceVector.from_numpy(V0[c].reshape(12, 20), ctx))
         assert np.array_equal(Out.numpy()[c], o.numpy().reshape(-1))
+
+
+BATCH_CASES = [("bratu2d", lambda: P.bratu2d(20, 12)), ("bratu2d_odd", lambda: P.bratu2d(33, 7)),
+               ("bratu2d_tall", lambda: P.bratu2d(8, 37)), ("bratu2d_wide", lambda: P.bratu2d(1030, 9)),
+               ("bratu1d", lambda: P.bratu1d(1000)), ("bratu1d_odd", lambda: P.bratu1d(37)),
+               ("heat2d", lambda: P.heat2d(12, dt_scale=8.0)), ("dg", lambda: P.heat1d_dg(9))]
+
+
+@pytest.mark.parametrize("cached", [False, True], ids=["exp_from_u", "cached_coef"])
+@pytest.mark.parametrize("name,make", BATCH_CASES, ids=[c[0] for c in BATCH_CASES])
+def test_multi_rhs_jvp_equals_columnwise_bit_for_bit(nk, ctx, name, make, cached):
+    """The multi-RHS tangent kernels (lambda e^u read once for all columns of `mul!(Out, J, V)`, src/Ariadne.jl:69-83)
+    give every column exactly what the single-column kernel gives; guard bands around V and Out stay intact."""
+    d = make()
+    F_, u, p, _ = P.device_setup(nk, ctx, d)
+    n, ncols = u.n, 6
+    coef = None
+    if cached and d["kind"] in (A.AK_BRATU1D, A.AK_BRATU2D):
+        coef = u.similar()
+        prob = F_.problem(u, p, coef=coef)
+        nk._lib.check(ctx.lib.ak_residual(ctx.h, C.byref(prob), C.c_void_p(u.ptr), C.c_void_p(u.zero().ptr), None))
+    J = nk.JacobianOperator(F_, u.zero(), u, p, coef=coef)
+    V0 = RNG.standard_normal((ncols, n))
+    base, (V, Out), mask = _guarded(nk, ctx, [V0, np.zeros((ncols, n))])
+    guards_before = base.numpy()[mask]
+    nk.mul_batched_(Out, J, V)
+    got = Out.numpy()
+    assert np.array_equal(np.isnan(base.numpy()[mask]), np.isnan(guards_before)) and not np.isnan(got).any()
+    for c in range(ncols):
+        o = u.zero()
+        nk.mul_(o, J, nk.DeviceVector.from_numpy(V0[c].reshape(u.shape), ctx))
+        assert np.array_equal(got[c], o.numpy().reshape(-1)), (name, c)
+
+
+@pytest.mark.parametrize("scheme", ["euler", "trapezoid"])
+def test_periodic_heat1d_transpose_product(nk, ctx, scheme):
+    """J^T v (src/Ariadne.jl:93-107) for heat_1D! with periodic_bc! (heat_1D.jl:39-42), whose Jacobian is not
+    symmetric: `collect(transpose(J)) == transpose(collect(J))` exactly (the reference's own test, runtests.jl:54)
+    and a random product against the dense transpose."""
+    d = P.heat1d(41, bc=A.AK_BC_PERIODIC)
+    d["scheme"] = {"euler": A.AK_EULER, "trapezoid": A.AK_TRAPEZOID}[scheme]
+    G_ = {"euler": nk.G_Euler_, "trapezoid": nk.G_Trapezoid_}[scheme]
+    u = nk.DeviceVector.from_numpy(d["u0"], ctx)
+    un = nk.DeviceVector.from_numpy(d["u0"], ctx)
+    F_ = nk.ImplicitResidual(G_, nk.heat_1D_)
+    J = nk.JacobianOperator(F_, u.zero(), u, (un, d["dt"], un.zero(), (d["a"], d["dx"], nk.bc_periodic_), 0.0))
+    Jd = nk.collect(J)
+    assert not np.array_equal(Jd, Jd.T)
+    assert np.array_equal(nk.collect(nk.transpose(J)), Jd.T)
+    v0 = RNG.standard_normal(d["nx"])
+    out = u.zero()
+    nk.mul_(out, nk.transpose(J), nk.DeviceVector.from_numpy(v0, ctx))
+    ref = Jd.T @ v0
+    assert np.linalg.norm(out.numpy() - ref) <= 1e-13 * np.linalg.norm(ref)
 
 
 # ---- guard bands: compute-sanitizer is not available on the GPU pool, so out-of-bounds accesses are caught here -----

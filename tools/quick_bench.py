@@ -69,13 +69,34 @@ x1 = np.linspace(0.0, 1.0, N1)
 u1 = nk.DeviceVector.from_numpy(4 * x1 * (1 - x1), ctx)
 un1, r1, v1, o1 = u1.copy(), u1.similar(), u1.copy(), u1.similar()
 F1 = nk.ImplicitResidual(nk.G_Euler_, nk.heat_1D_)
-pr1 = F1.problem(u1, (un1, 1e-12, un1.zero(), (0.2, 1.0 / (N1 - 1), nk.bc_zero_), 0.0))
+pr1 = F1.problem(u1, (un1, 1e-12, None, (0.2, 1.0 / (N1 - 1), nk.bc_zero_), 0.0))
 timeit("residual heat1d 2^24", lambda: lib.ak_residual(h, C.byref(pr1), P(u1), P(r1), None), 24 * N1)
 timeit("jvp heat1d 2^24", lambda: lib.ak_jvp(h, C.byref(pr1), P(u1), P(v1), P(o1)), 16 * N1)
 prb = nk.bratu_.problem(u1, (1.0 / (N1 + 1), 3.5))
 timeit("residual bratu1d 2^24", lambda: lib.ak_residual(h, C.byref(prb), P(u1), P(r1), None), 16 * N1)
 timeit("jvp bratu1d 2^24 (exp)", lambda: lib.ak_jvp(h, C.byref(prb), P(u1), P(v1), P(o1)), 24 * N1)
 Fd = nk.ImplicitResidual(nk.G_Euler_, nk.heat_1D_DG_)
-prd = Fd.problem(u1, (un1, 1e-12, un1.zero(), (4.0 / N1,), 0.0))
+prd = Fd.problem(u1, (un1, 1e-12, None, (4.0 / N1,), 0.0))
 timeit("residual DG 2^22 elements", lambda: lib.ak_residual(h, C.byref(prd), P(u1), P(r1), None), 24 * N1)
 timeit("jvp DG 2^22 elements", lambda: lib.ak_jvp(h, C.byref(prd), P(u1), P(v1), P(o1)), 16 * N1)
+
+# ---- CG (algo = :cg of examples/bratu.jl:59-108) on 1-D Bratu N = 2^24, lambda = 1: bytes per iteration 88n
+#      (tangent + <p,Ap> 24n, r -= alpha Ap + <r,r> 24n, x += alpha p ; p = r + beta p 40n)
+prc = nk.bratu_.problem(u1, (1.0 / (N1 + 1), 1.0))
+wsc = nk.krylov_workspace("cg", nk.KrylovConstructor(r1))
+Jc = nk.JacobianOperator(nk.bratu_, r1, u1, (1.0 / (N1 + 1), 1.0))
+lib.ak_residual(h, C.byref(prc), P(u1), P(r1), None)
+bc = r1.copy()
+for _ in range(2):
+    ctx.sync(); ctx.launch_count(reset=True); ctx.timer_start()
+    nk.krylov_solve_(wsc, Jc, bc, rtol=1e-30, atol=0.0, itmax=100)
+    ms = ctx.timer_stop()
+it = wsc.stats.niter
+print(f"cg bratu1d 2^24 {it} its in {ms:8.2f} ms -> {it/ms*1e3:7.1f} it/s ; 88n bytes/it -> {88*N1*it/ms/1e6:8.1f} GB/s "
+      f"({88*N1*it/ms/1e6/6552.6*100:5.1f}% of peak); launches {ctx.launch_count()}")
+# multi-RHS tangent (mul!(Out, J, V), 8 columns) at 8192^2 vs 8 single launches
+ncol = 8
+Vb = nk.DeviceVector(ctx, (ncol, n)); Ob = nk.DeviceVector(ctx, (ncol, n))
+nk.kfill_(Vb, 1.0)
+timeit("jvp bratu2d x8 multi-RHS (exp)", lambda: lib.ak_jvp_batched(h, C.byref(prob2), P(u), P(Vb), n, P(Ob), n, ncol), (16 * ncol + 8) * n, reps=5)
+timeit("jvp bratu2d x8 single launches", lambda: [lib.ak_jvp(h, C.byref(prob2), P(u), C.c_void_p(Vb.ptr + 8 * n * c), C.c_void_p(Ob.ptr + 8 * n * c)) for c in range(ncol)], 24 * ncol * n, reps=5)
