@@ -200,7 +200,7 @@ int ak_jvp(ak_ctx* ctx, const ak_problem* p, const double* u, double* v, double*
 int ak_jvp_transpose(ak_ctx* ctx, const ak_problem* p, const double* u, double* v, double* out);
 /* Out[:, c] <- J(u) V[:, c], c < ncols: the batched `mul!(Out, J, V)` of src/Ariadne.jl:69-83 for column-major
  * matrices with leading dimensions ldv, ldo >= n.  Bratu 1-D/2-D (the operators that depend on u): ONE multi-RHS
- * launch, lambda e^u read (or computed) once for all columns, (16 + 8/ncols) n bytes per column; the u-independent
+ * launch, lambda e^u read (or computed) once per group of four columns, 18n instead of 24n bytes per column; the u-independent
  * heat / DG tangents and AK_USER: one tangent sweep per column (V's boundary entries may be overwritten like in
  * ak_jvp).  Every column equals ak_jvp's result bit for bit.                                                  */
 int ak_jvp_batched(ak_ctx* ctx, const ak_problem* p, const double* u, double* V, int64_t ldv, double* Out,

@@ -337,10 +337,14 @@ AK_DEV double heat1d_bc_value(const double* src, int64_t i, int64_t n, int bc) {
     return src[i];
 }
 
-// One wave of resident blocks walks the array (grid-stride over chunks of VEC points); every thread keeps TWO chunks
-// in flight per trip: all vector loads of both chunks are issued before either is finished, so each operand stream has
-// two independent 256-bit requests outstanding per thread (the launch-per-chunk version sat at 74-83 % of the copy
-// bandwidth at N = 2^24: one request per thread and 16 K blocks to schedule).
+// One wave of resident blocks (2 x 256 threads per SM) walks the array, grid-stride over chunks of VEC points.  Every
+// thread keeps kU1 (2-4) chunks in flight per trip: ALL global loads of the trip — the vector operands and, for the warp-edge
+// lanes, the one scalar neighbour a shuffle cannot provide — are issued before any of them is consumed.  (History: the
+// launch-per-chunk version sat at 74-83 % of the copy bandwidth at N = 2^24 — one request per thread and 16 K blocks to
+// schedule; a first persistent version with two chunks in flight and the edge loads issued late had only 16 warps per
+// SM with ~1.5 requests outstanding each and was slower, 55-78 %: profiles/r02_ncu_1d_two_chunks.txt.)
+// (fewer chunks for the variants with more operand streams per chunk: the register file holds all of them at once)
+
 template <int OP, int VEC, bool SCALE, int RED>
 __global__ void __launch_bounds__(kT1, 2) k_stencil1d(const StencilArgs p) {
     __shared__ double sh[32];
@@ -352,77 +356,78 @@ __global__ void __launch_bounds__(kT1, 2) k_stencil1d(const StencilArgs p) {
     constexpr bool HEAT = (OP == OP_RES_HEAT || OP == OP_JVP_HEAT || OP == OP_RHS_HEAT);
     constexpr bool FD = (OP == OP_JVP_BRATU_FD);
     constexpr bool AUX = (OP == OP_JVP_BRATU || OP == OP_RES_HEAT);
+    constexpr int kU1 = OP == OP_JVP_BRATU_FD ? 2 : (RED == RED_DOT ? 3 : 4);
     const bool oscale_on = (OP == OP_JVP_BRATU || OP == OP_JVP_HEAT || FD) && p.out_scale != nullptr;
     const double oscale = oscale_on ? __ddiv_rn(1.0, *p.out_scale) : 1.0;
+    // raw value at index i incl. the boundary semantics (before the SCALE division): one load or a constant.
+    //   i < 0 / i >= n : the neighbour rank's end point, or y_0 = y_{N+1} = 0 (Bratu: bratu.jl:17)
+    //   heat, global end points: their bc! / periodic_bc! value (heat_1D.jl:34-42)
+    auto raw_value = [&](int64_t i) -> double {
+        if (i < 0) return p.lo != nullptr ? p.lo[0] : 0.0;
+        if (i >= n) return p.hi != nullptr ? p.hi[0] : 0.0;
+        if (HEAT && ((i == 0 && p.seg_first) || (i == n - 1 && p.seg_last))) return heat1d_bc_value(p.in, i, n, p.bc);
+        return p.in[i];
+    };
     // fused finite-difference JVP: second window over u (p.aux, ghosts p.aux_lo / p.aux_hi); u + eps v is never stored
     auto uvalue = [&](int64_t i) -> double {
         if (i < 0) return p.aux_lo ? p.aux_lo[0] : 0.0;
         if (i >= n) return p.aux_hi ? p.aux_hi[0] : 0.0;
         return p.aux[i];
     };
-    auto value = [&](int64_t i) -> double {  // scalar access incl. boundary semantics
-        double v;
-        if (i < 0) {  // left of this segment: neighbour rank's last point, or y_0 = 0 (Bratu: bratu.jl:17)
-            if (p.lo == nullptr) return 0.0;
-            v = p.lo[0];
-        } else if (i >= n) {
-            if (p.hi == nullptr) return 0.0;
-            v = p.hi[0];
-        } else if (HEAT && ((i == 0 && p.seg_first) || (i == n - 1 && p.seg_last))) {
-            v = heat1d_bc_value(p.in, i, n, p.bc);  // bc! / periodic_bc! act on the global end points only
-        } else {
-            v = p.in[i];
-        }
-        if (SCALE) v = div_by(v, denom);
-        return v;
-    };
 
     struct Chunk {
         int64_t x0;
         bool active;
-        double cur[VEC], aux[VEC], ucur[VEC], bb[VEC], dw[VEC];
+        double cur[VEC], aux[AUX ? VEC : 1], ucur[FD ? VEC : 1], dw[RED == RED_DOT ? VEC : 1];
+        double el, er, uel, uer;  // neighbours outside the warp (edge lanes only), raw
     };
-    // phase 1: every global vector load of the chunk
+    // phase 1: every global load of the chunk, nothing consumed
     auto load_chunk = [&](Chunk& c, int64_t x0) {
         c.x0 = x0;
         c.active = x0 < n;
+        c.el = c.er = c.uel = c.uer = 0.0;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) c.cur[i] = c.aux[i] = c.ucur[i] = c.bb[i] = c.dw[i] = 0.0;
+        for (int i = 0; i < VEC; ++i) c.cur[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < (FD ? VEC : 1); ++i) c.ucur[i] = 0.0;
         if (!c.active) return;
         ldv<VEC>(p.in + x0, c.cur);
-        if (AUX) ldv_s<VEC>(p.aux + x0, c.aux);
-        if (FD) ldv<VEC>(p.aux + x0, c.ucur);
-        if (p.bminus != nullptr) ldv_s<VEC>(p.bminus + x0, c.bb);
-        if (RED == RED_DOT) ldv_s<VEC>(p.dot_with + x0, c.dw);
+        if (AUX) ldv_s<VEC>(p.aux + x0, reinterpret_cast<double(&)[VEC]>(c.aux));
+        if (FD) ldv<VEC>(p.aux + x0, reinterpret_cast<double(&)[VEC]>(c.ucur));
+        if (RED == RED_DOT) ldv_s<VEC>(p.dot_with + x0, reinterpret_cast<double(&)[VEC]>(c.dw));
+        const bool last = lane == 31 || x0 + VEC >= n;
+        if (lane == 0) c.el = raw_value(x0 - 1);
+        if (last) c.er = raw_value(x0 + VEC);
+        if (FD) {
+            if (lane == 0) c.uel = uvalue(x0 - 1);
+            if (last) c.uer = uvalue(x0 + VEC);
+        }
+        if (HEAT) {  // the global end points take their BC value (raw; scaled with the rest below)
+            if (x0 == 0 && p.seg_first) c.cur[0] = raw_value(0);
+            if (x0 + VEC == n && p.seg_last) c.cur[VEC - 1] = raw_value(n - 1);
+        }
     };
     double acc = 0.0;
-    // phase 2: boundary semantics, neighbours (shuffles; warp-edge lanes load one scalar), arithmetic, stores
+    // phase 2: neighbours (shuffles; warp-edge lanes use their prefetched scalar), arithmetic, stores
     auto finish_chunk = [&](Chunk& c) {
         const int64_t x0 = c.x0;
-        if (c.active) {
-            if (SCALE) {
+        if (SCALE) {
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) c.cur[i] = div_by(c.cur[i], denom);
-            }
-            if (HEAT) {  // the global end points take their BC value
-                if (x0 == 0 && p.seg_first) c.cur[0] = value(0);
-                if (x0 + VEC == n && p.seg_last) c.cur[VEC - 1] = value(n - 1);
-            }
+            for (int i = 0; i < VEC; ++i) c.cur[i] = div_by(c.cur[i], denom);
+            c.el = div_by(c.el, denom);
+            c.er = div_by(c.er, denom);
         }
         double left = __shfl_up_sync(0xffffffffu, c.cur[VEC - 1], 1);
         double right = __shfl_down_sync(0xffffffffu, c.cur[0], 1);
         double uleft = 0.0, uright = 0.0;
         if (FD) {
-            uleft = __shfl_up_sync(0xffffffffu, c.ucur[VEC - 1], 1);
+            uleft = __shfl_up_sync(0xffffffffu, c.ucur[FD ? VEC - 1 : 0], 1);
             uright = __shfl_down_sync(0xffffffffu, c.ucur[0], 1);
         }
         if (!c.active) return;
-        if (lane == 0) left = value(x0 - 1);
-        if (lane == 31 || x0 + VEC >= n) right = value(x0 + VEC);
-        if (FD) {
-            if (lane == 0) uleft = uvalue(x0 - 1);
-            if (lane == 31 || x0 + VEC >= n) uright = uvalue(x0 + VEC);
-        }
+        const bool last = lane == 31 || x0 + VEC >= n;
+        if (lane == 0) { left = c.el; uleft = c.uel; }
+        if (last) { right = c.er; uright = c.uer; }
         double o[VEC], cf[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
@@ -433,14 +438,15 @@ __global__ void __launch_bounds__(kT1, 2) k_stencil1d(const StencilArgs p) {
                 cf[i] = __dmul_rn(p.lambda, exp(cc));
                 o[i] = __dadd_rn(second_diff(e, cc, w, dx2), cf[i]);
             } else if (OP == OP_JVP_BRATU) {
-                const double k = p.coef_from_u ? __dmul_rn(p.lambda, exp(c.aux[i])) : c.aux[i];
+                const double a_ = c.aux[AUX ? i : 0];
+                const double k = p.coef_from_u ? __dmul_rn(p.lambda, exp(a_)) : a_;
                 o[i] = __dadd_rn(second_diff(e, cc, w, dx2), __dmul_rn(k, cc));
             } else if (FD) {
                 // J v ~ (F(u + eps v) - F(u)) / eps, both residuals of bratu! (bratu.jl:14-24) evaluated at this point
                 const double eps = p.fd_eps;
-                const double uc = c.ucur[i];
-                const double uw = (i == 0) ? uleft : c.ucur[i > 0 ? i - 1 : 0];
-                const double ue = (i == VEC - 1) ? uright : c.ucur[(i + 1) % VEC];
+                const double uc = c.ucur[FD ? i : 0];
+                const double uw = (i == 0) ? uleft : c.ucur[(FD && i > 0) ? i - 1 : 0];
+                const double ue = (i == VEC - 1) ? uright : c.ucur[FD ? (i + 1) % VEC : 0];
                 const double f0 = __dadd_rn(second_diff(ue, uc, uw, dx2), __dmul_rn(p.lambda, exp(uc)));
                 const double pc = fma(eps, cc, uc), pw = fma(eps, w, uw), pe = fma(eps, e, ue);
                 const double f1 = __dadd_rn(second_diff(pe, pc, pw, dx2), __dmul_rn(p.lambda, exp(pc)));
@@ -451,7 +457,7 @@ __global__ void __launch_bounds__(kT1, 2) k_stencil1d(const StencilArgs p) {
                 const bool bnd = (gi == 0 && p.seg_first) || (gi == n - 1 && p.seg_last);
                 const double du =
                     bnd ? 0.0 : div_by(__dmul_rn(p.a, __dadd_rn(__dsub_rn(e, __dmul_rn(2.0, cc)), w)), dx2);
-                if (OP == OP_RES_HEAT) o[i] = __dsub_rn(__dadd_rn(c.aux[i], __dmul_rn(p.dt, du)), cc);
+                if (OP == OP_RES_HEAT) o[i] = __dsub_rn(__dadd_rn(c.aux[AUX ? i : 0], __dmul_rn(p.dt, du)), cc);
                 else if (OP == OP_RHS_HEAT) o[i] = du;
                 else o[i] = __dsub_rn(__dmul_rn(p.c1, du), cc);
             }
@@ -459,10 +465,6 @@ __global__ void __launch_bounds__(kT1, 2) k_stencil1d(const StencilArgs p) {
         if (oscale_on) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) o[i] = __dmul_rn(o[i], oscale);
-        }
-        if (p.bminus != nullptr) {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) o[i] = __dsub_rn(c.bb[i], o[i]);
         }
         stv<VEC>(p.out + x0, o);
         if (OP == OP_RES_BRATU && p.aux_out != nullptr) stv<VEC>(p.aux_out + x0, cf);
@@ -478,20 +480,21 @@ __global__ void __launch_bounds__(kT1, 2) k_stencil1d(const StencilArgs p) {
             for (int i = 0; i < VEC; ++i) acc = fma(o[i], o[i], acc);
         } else if (RED == RED_DOT) {
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc = fma(c.dw[i], o[i], acc);
+            for (int i = 0; i < VEC; ++i) acc = fma(c.dw[RED == RED_DOT ? i : 0], o[i], acc);
         }
     };
 
     const int64_t nchunks = (n + VEC - 1) / VEC;
     const int64_t nth = (int64_t)gridDim.x * kT1;
-    // warp-uniform trip count (the shuffles need whole warps): the warp stays in the loop while its first lane has work
-    for (int64_t ch = (int64_t)blockIdx.x * kT1 + threadIdx.x; ch - lane < nchunks; ch += 2 * nth) {
-        Chunk a, b;
-        const bool second = (ch + nth - lane) < nchunks;
-        load_chunk(a, ch * VEC);
-        if (second) load_chunk(b, (ch + nth) * VEC);
-        finish_chunk(a);
-        if (second) finish_chunk(b);
+    // warp-uniform trip count (the shuffles need whole warps): a chunk slot is live while its warp's first lane has work
+    for (int64_t ch = (int64_t)blockIdx.x * kT1 + threadIdx.x; ch - lane < nchunks; ch += kU1 * nth) {
+        Chunk c[kU1];
+#pragma unroll
+        for (int q = 0; q < kU1; ++q)
+            if ((ch + q * nth - lane) < nchunks) load_chunk(c[q], (ch + q * nth) * VEC);
+#pragma unroll
+        for (int q = 0; q < kU1; ++q)
+            if ((ch + q * nth - lane) < nchunks) finish_chunk(c[q]);
     }
     if (RED != RED_NONE) {
         const double s = block_sum(acc, sh);
@@ -518,7 +521,6 @@ struct DgArgs {
     double* in_write;
     const double* denom;
     const double* out_scale;  // tangent with an un-normalised Krylov basis: out = J(in) / *out_scale
-    const double* bminus;     // tangent: out = bminus - J(in)  (restart residual of gmres!)
     const double* dot_with;
     double* red_out;
     double* partials;
@@ -537,8 +539,10 @@ AK_DEV void dg_local(const double (&D)[4][4], double jac, const double (&u)[4], 
     }
 }
 
-// One thread per element and trip; one wave of resident blocks walks the mesh with two elements in flight per thread
-// (all vector loads of both elements are issued before either is finished).
+// One thread per element and trip; one wave of resident blocks (2 x 256 threads per SM) walks the mesh with kUdg
+// elements in flight per thread: all global loads of the trip (the element itself, u_n, and for the warp-edge lanes the
+// neighbour element / node a shuffle cannot provide) are issued before any is consumed (kUdg = 2-4).
+
 template <bool RESIDUAL, bool SCALE, int RED>
 __global__ void __launch_bounds__(kT1, 2) k_dg(const DgArgs p) {
     __shared__ double sh[32];
@@ -549,30 +553,33 @@ __global__ void __launch_bounds__(kT1, 2) k_dg(const DgArgs p) {
     const Divisor mw = make_divisor(p.mw);
     const bool oscale_on = !RESIDUAL && !p.rhs_only && p.out_scale != nullptr;
     const double oscale = oscale_on ? __ddiv_rn(1.0, *p.out_scale) : 1.0;
+    constexpr int kUdg = RESIDUAL ? 3 : (RED == RED_DOT ? 2 : 4);  // what the register file holds without spilling
 
-    auto load_elem = [&](int64_t el, double (&r)[4]) {
-        ldv<4>((el < 0) ? p.lo : p.in + 4 * el, r);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (SCALE) r[i] = div_by(r[i], denom);
-            if (!RESIDUAL) r[i] = __dmul_rn(p.c0, r[i]);
-        }
-    };
     struct Elem {
         int64_t e;
         bool active;
-        double raw[4], un[4], bb[4], dw[4];
+        double raw[4], un[RESIDUAL ? 4 : 1], dw[RED == RED_DOT ? 4 : 1];
+        double prev[4];  // lane 0: the element to the left (raw)
+        double next0;    // last lane: first node of the element to the right (raw)
     };
     auto load = [&](Elem& c, int64_t e) {
         c.e = e;
         c.active = e < ne;
+        c.next0 = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c.raw[i] = c.un[i] = c.bb[i] = c.dw[i] = 0.0;
+        for (int i = 0; i < 4; ++i) c.raw[i] = c.prev[i] = 0.0;
         if (!c.active) return;
         ldv<4>(p.in + 4 * e, c.raw);
-        if (RESIDUAL && !p.rhs_only) ldv_s<4>(p.un + 4 * e, c.un);
-        if (!RESIDUAL && p.bminus != nullptr) ldv_s<4>(p.bminus + 4 * e, c.bb);
-        if (RED == RED_DOT) ldv_s<4>(p.dot_with + 4 * e, c.dw);
+        if (RESIDUAL && !p.rhs_only) ldv_s<4>(p.un + 4 * e, reinterpret_cast<double(&)[4]>(c.un));
+        if (RED == RED_DOT) ldv_s<4>(p.dot_with + 4 * e, reinterpret_cast<double(&)[4]>(c.dw));
+        if (lane == 31 || e + 1 >= ne) {
+            const int64_t en = (e + 1 == ne) ? 0 : e + 1;
+            c.next0 = (e + 1 == ne && p.hi != nullptr) ? p.hi[0] : p.in[4 * en];
+        }
+        if (lane == 0) {
+            const int64_t ep = (e == 0) ? ((p.lo != nullptr) ? -1 : ne - 1) : e - 1;
+            ldv<4>((ep < 0) ? p.lo : p.in + 4 * ep, c.prev);
+        }
     };
     double acc = 0.0;
     auto finish = [&](Elem& c) {
@@ -589,8 +596,7 @@ __global__ void __launch_bounds__(kT1, 2) k_dg(const DgArgs p) {
         // D1p: needs first node of the element to the right
         double u_next0 = __shfl_down_sync(0xffffffffu, u[0], 1);
         if (active && (lane == 31 || e + 1 >= ne)) {
-            const int64_t en = (e + 1 == ne) ? 0 : e + 1;
-            double t = (e + 1 == ne && p.hi != nullptr) ? p.hi[0] : p.in[4 * en];
+            double t = c.next0;
             if (SCALE) t = div_by(t, denom);
             u_next0 = RESIDUAL ? t : __dmul_rn(p.c0, t);
         }
@@ -602,9 +608,13 @@ __global__ void __launch_bounds__(kT1, 2) k_dg(const DgArgs p) {
         // D1m: needs last node of (D1p u) of the element to the left
         double t_prev3 = __shfl_up_sync(0xffffffffu, t1[3], 1);
         if (active && lane == 0) {
-            const int64_t ep = (e == 0) ? ((p.lo != nullptr) ? -1 : ne - 1) : e - 1;
             double up[4], tp[4];
-            load_elem(ep, up);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                up[i] = c.prev[i];
+                if (SCALE) up[i] = div_by(up[i], denom);
+                if (!RESIDUAL) up[i] = __dmul_rn(p.c0, up[i]);
+            }
             dg_local(p.D, p.jac, up, tp);
             t_prev3 = __dadd_rn(tp[3], div_by(__dsub_rn(u[0], up[3]), mw));
         }
@@ -617,17 +627,13 @@ __global__ void __launch_bounds__(kT1, 2) k_dg(const DgArgs p) {
             for (int i = 0; i < 4; ++i) o[i] = du[i];
         } else if (RESIDUAL) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dadd_rn(c.un[i], __dmul_rn(p.dt, du[i])), c.raw[i]);
+            for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dadd_rn(c.un[RESIDUAL ? i : 0], __dmul_rn(p.dt, du[i])), c.raw[i]);
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dmul_rn(p.c1, du[i]), c.raw[i]);
             if (oscale_on) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) o[i] = __dmul_rn(o[i], oscale);
-            }
-            if (p.bminus != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(c.bb[i], o[i]);
             }
         }
         stv<4>(p.out + 4 * e, o);
@@ -637,17 +643,18 @@ __global__ void __launch_bounds__(kT1, 2) k_dg(const DgArgs p) {
             for (int i = 0; i < 4; ++i) acc = fma(o[i], o[i], acc);
         } else if (RED == RED_DOT) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc = fma(c.dw[i], o[i], acc);
+            for (int i = 0; i < 4; ++i) acc = fma(c.dw[RED == RED_DOT ? i : 0], o[i], acc);
         }
     };
     const int64_t nth = (int64_t)gridDim.x * kT1;
-    for (int64_t e = (int64_t)blockIdx.x * kT1 + threadIdx.x; e - lane < ne; e += 2 * nth) {
-        Elem a, b;
-        const bool second = (e + nth - lane) < ne;
-        load(a, e);
-        if (second) load(b, e + nth);
-        finish(a);
-        if (second) finish(b);
+    for (int64_t e = (int64_t)blockIdx.x * kT1 + threadIdx.x; e - lane < ne; e += kUdg * nth) {
+        Elem c[kUdg];
+#pragma unroll
+        for (int q = 0; q < kUdg; ++q)
+            if ((e + q * nth - lane) < ne) load(c[q], e + q * nth);
+#pragma unroll
+        for (int q = 0; q < kUdg; ++q)
+            if ((e + q * nth - lane) < ne) finish(c[q]);
     }
     if (RED != RED_NONE) {
         const double s = block_sum(acc, sh);
@@ -685,8 +692,8 @@ __global__ void k_simple2(const double* u, const double* v, double* out, double*
 // ========================================================================================
 // Multi-RHS tangent: Out[:, c] = J(u) V[:, c], c < ncols  —  `mul!(Out, J, V)` of src/Ariadne.jl:69-83 and the probe
 // products of `collect(J)` (:140-162).  The operand every column shares, lambda e^u, is read (or computed: one `exp`
-// per point) ONCE per tile and kept in registers while the columns stream through: (16 + 8/ncols) n bytes per column
-// instead of 24n, and one launch instead of ncols.  Arithmetic per column is the single-column kernel's, bit for bit.
+// per point) once per group of kCB = 4 columns: (16 + 8/4) n = 18n bytes per column instead of 24n, one `exp` per
+// point and group instead of one per column, and one launch instead of ncols.  Arithmetic per column is the single-column kernel's, bit for bit.
 // (The heat and DG tangents do not depend on u: their columns share nothing and stay a loop of single launches.)
 // ========================================================================================
 struct BatchArgs {
@@ -700,71 +707,82 @@ struct BatchArgs {
     int64_t ldo;
     int32_t ncols;
 };
-constexpr int kBatchRY = 8;  // rows per tile of the 2-D batched kernel (tile of lambda e^u: kBatchRY x VEC registers)
+constexpr int kBatchRY = 16;  // rows per tile of the 2-D multi-RHS kernel
+constexpr int kCB = 4;        // columns that share one read of lambda e^u (and are in flight together)
 
+// grid = (x tiles, row tiles, column groups of kCB).  Per row step every thread issues the loads of the next row of all
+// kCB columns plus the lambda e^u row before it consumes anything (kCB + 1 requests in flight, 3-row register windows of
+// kCB columns): (16 + 8/kCB) n bytes per column.
 template <int VEC>
-__global__ void __launch_bounds__(kTX, 4) k_bratu2d_jvp_batched(const BatchArgs p) {
+__global__ void __launch_bounds__(kTX, 3) k_bratu2d_jvp_batched(const BatchArgs p) {
     const int lane = threadIdx.x & 31;
     const int64_t nx = p.nx, ny = p.ny;
     const int64_t x0 = ((int64_t)blockIdx.x * kTX + threadIdx.x) * VEC;
     const bool active = x0 < nx;
     const int64_t y0 = (int64_t)blockIdx.y * kBatchRY;
     const int64_t y1 = (y0 + kBatchRY < ny) ? y0 + kBatchRY : ny;
+    const int c0 = blockIdx.z * kCB;
     const Divisor dx2 = make_divisor(p.dx2), dy2 = make_divisor(p.dy2);
-    double kc[kBatchRY][VEC];
-#pragma unroll
-    for (int r = 0; r < kBatchRY; ++r) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) kc[r][i] = 0.0;
-        if (active && y0 + r < y1) {
-            ldv_s<VEC>(p.aux + (y0 + r) * nx + x0, kc[r]);
-            if (p.coef_from_u) {
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) kc[r][i] = __dmul_rn(p.lambda, exp(kc[r][i]));
-            }
-        }
-    }
     const bool need_l = active && lane == 0;
     const bool need_r = active && (lane == 31 || x0 + VEC >= nx);
-    for (int c = 0; c < p.ncols; ++c) {
-        const double* in = p.V + (int64_t)c * p.ldv;
-        double* out = p.Out + (int64_t)c * p.ldo;
-        auto load_row = [&](int64_t y, double (&r)[VEC]) {
-            if (!active || y < 0 || y >= ny) {
+    auto col_in = [&](int c) -> const double* { return p.V + (int64_t)(c0 + c) * p.ldv; };
+    auto load_row = [&](int c, int64_t y, double (&r)[VEC]) {
+        if (!active || y < 0 || y >= ny || c0 + c >= p.ncols) {
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) r[i] = 0.0;
-                return;
-            }
-            ldv<VEC>(in + y * nx + x0, r);
-        };
-        auto edge = [&](int64_t y, int64_t x) -> double { return (x < 0 || x >= nx) ? 0.0 : in[y * nx + x]; };
-        double prev[VEC], cur[VEC], next[VEC];
-        load_row(y0 - 1, prev);
-        load_row(y0, cur);
+            for (int i = 0; i < VEC; ++i) r[i] = 0.0;
+            return;
+        }
+        ldv<VEC>(col_in(c) + y * nx + x0, r);
+    };
+    auto edge = [&](int c, int64_t y, int64_t x) -> double {
+        return (x < 0 || x >= nx || c0 + c >= p.ncols) ? 0.0 : col_in(c)[y * nx + x];
+    };
+    double prev[kCB][VEC], cur[kCB][VEC], next[kCB][VEC], el[kCB], er[kCB];
 #pragma unroll
-        for (int r = 0; r < kBatchRY; ++r) {
-            const int64_t y = y0 + r;
-            if (y < y1) {  // block-uniform
-                load_row(y + 1, next);
-                double left = __shfl_up_sync(0xffffffffu, cur[VEC - 1], 1);
-                double right = __shfl_down_sync(0xffffffffu, cur[0], 1);
-                if (active) {
-                    if (need_l) left = edge(y, x0 - 1);
-                    if (need_r) right = edge(y, x0 + VEC);
-                    double o[VEC];
+    for (int c = 0; c < kCB; ++c) {
+        load_row(c, y0 - 1, prev[c]);
+        load_row(c, y0, cur[c]);
+        el[c] = need_l ? edge(c, y0, x0 - 1) : 0.0;
+        er[c] = need_r ? edge(c, y0, x0 + VEC) : 0.0;
+    }
+    for (int64_t y = y0; y < y1; ++y) {
+        double kc[VEC], eln[kCB], ern[kCB];
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        const double w = (i == 0) ? left : cur[i > 0 ? i - 1 : 0];
-                        const double e = (i == VEC - 1) ? right : cur[(i + 1) % VEC];
-                        const double cc = cur[i];
-                        const double lap = __dadd_rn(second_diff(e, cc, w, dx2), second_diff(next[i], cc, prev[i], dy2));
-                        o[i] = __dadd_rn(lap, __dmul_rn(kc[r][i], cc));
-                    }
-                    stv<VEC>(out + y * nx + x0, o);
+        for (int i = 0; i < VEC; ++i) kc[i] = 0.0;
+        // every load of this row step first
+#pragma unroll
+        for (int c = 0; c < kCB; ++c) {
+            load_row(c, y + 1, next[c]);
+            eln[c] = (need_l && y + 1 < y1) ? edge(c, y + 1, x0 - 1) : 0.0;
+            ern[c] = (need_r && y + 1 < y1) ? edge(c, y + 1, x0 + VEC) : 0.0;
+        }
+        if (active) ldv_s<VEC>(p.aux + y * nx + x0, kc);
+        if (p.coef_from_u) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) kc[i] = __dmul_rn(p.lambda, exp(kc[i]));
+        }
+#pragma unroll
+        for (int c = 0; c < kCB; ++c) {
+            double left = __shfl_up_sync(0xffffffffu, cur[c][VEC - 1], 1);
+            double right = __shfl_down_sync(0xffffffffu, cur[c][0], 1);
+            if (active && c0 + c < p.ncols) {
+                if (need_l) left = el[c];
+                if (need_r) right = er[c];
+                double o[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const double w = (i == 0) ? left : cur[c][i > 0 ? i - 1 : 0];
+                    const double e = (i == VEC - 1) ? right : cur[c][(i + 1) % VEC];
+                    const double cc = cur[c][i];
+                    const double lap = __dadd_rn(second_diff(e, cc, w, dx2), second_diff(next[c][i], cc, prev[c][i], dy2));
+                    o[i] = __dadd_rn(lap, __dmul_rn(kc[i], cc));
                 }
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) { prev[i] = cur[i]; cur[i] = next[i]; }
+                stv<VEC>(p.Out + (int64_t)(c0 + c) * p.ldo + y * nx + x0, o);
             }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) { prev[c][i] = cur[c][i]; cur[c][i] = next[c][i]; }
+            el[c] = eln[c];
+            er[c] = ern[c];
         }
     }
 }
@@ -779,35 +797,46 @@ __global__ void __launch_bounds__(kT1, 2) k_bratu1d_jvp_batched(const BatchArgs 
     for (int64_t ch = (int64_t)blockIdx.x * kT1 + threadIdx.x; ch - lane < nchunks; ch += nth) {
         const int64_t x0 = ch * VEC;
         const bool active = x0 < n;
+        const bool last = lane == 31 || x0 + VEC >= n;
         double kc[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) kc[i] = 0.0;
-        if (active) {
-            ldv_s<VEC>(p.aux + x0, kc);
-            if (p.coef_from_u) {
+        if (active) ldv_s<VEC>(p.aux + x0, kc);
+        for (int cg = 0; cg < p.ncols; cg += kCB) {  // kCB columns in flight together
+            double cur[kCB][VEC], el[kCB], er[kCB];
+#pragma unroll
+            for (int c = 0; c < kCB; ++c) {
+                const double* in = p.V + (int64_t)(cg + c) * p.ldv;
+                const bool on = active && cg + c < p.ncols;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) cur[c][i] = 0.0;
+                el[c] = er[c] = 0.0;
+                if (on) {
+                    ldv<VEC>(in + x0, cur[c]);
+                    if (lane == 0 && x0 > 0) el[c] = in[x0 - 1];
+                    if (last && x0 + VEC < n) er[c] = in[x0 + VEC];
+                }
+            }
+            if (cg == 0 && p.coef_from_u) {
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) kc[i] = __dmul_rn(p.lambda, exp(kc[i]));
             }
-        }
-        for (int c = 0; c < p.ncols; ++c) {
-            const double* in = p.V + (int64_t)c * p.ldv;
-            double cur[VEC];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) cur[i] = 0.0;
-            if (active) ldv<VEC>(in + x0, cur);
-            double left = __shfl_up_sync(0xffffffffu, cur[VEC - 1], 1);
-            double right = __shfl_down_sync(0xffffffffu, cur[0], 1);
-            if (active) {
-                if (lane == 0) left = x0 > 0 ? in[x0 - 1] : 0.0;
-                if (lane == 31 || x0 + VEC >= n) right = x0 + VEC < n ? in[x0 + VEC] : 0.0;
-                double o[VEC];
+            for (int c = 0; c < kCB; ++c) {
+                double left = __shfl_up_sync(0xffffffffu, cur[c][VEC - 1], 1);
+                double right = __shfl_down_sync(0xffffffffu, cur[c][0], 1);
+                if (active && cg + c < p.ncols) {
+                    if (lane == 0) left = el[c];
+                    if (last) right = er[c];
+                    double o[VEC];
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    const double w = (i == 0) ? left : cur[i > 0 ? i - 1 : 0];
-                    const double e = (i == VEC - 1) ? right : cur[(i + 1) % VEC];
-                    o[i] = __dadd_rn(second_diff(e, cur[i], w, dx2), __dmul_rn(kc[i], cur[i]));
+                    for (int i = 0; i < VEC; ++i) {
+                        const double w = (i == 0) ? left : cur[c][i > 0 ? i - 1 : 0];
+                        const double e = (i == VEC - 1) ? right : cur[c][(i + 1) % VEC];
+                        o[i] = __dadd_rn(second_diff(e, cur[c][i], w, dx2), __dmul_rn(kc[i], cur[c][i]));
+                    }
+                    stv<VEC>(p.Out + (int64_t)(cg + c) * p.ldo + x0, o);
                 }
-                stv<VEC>(p.Out + (int64_t)c * p.ldo + x0, o);
             }
         }
     }
@@ -912,7 +941,7 @@ static void launch1d_v(Ctx* ctx, const StencilArgs& a, bool scale, int red, int 
 template <int OP>
 static int launch1d(Ctx* ctx, StencilArgs& a, bool scale, int red) {
     int vec = 1;
-    const void* ptrs[] = {a.in, a.aux, a.aux_out, a.out, a.in_write, a.dot_with, a.bminus};
+    const void* ptrs[] = {a.in, a.aux, a.aux_out, a.out, a.in_write, a.dot_with};
     auto ok = [&](int v) {
         if (a.nx % v) return false;
         for (const void* q : ptrs)
@@ -1246,6 +1275,22 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     JvpFusion nofuse;
     if (!f) f = &nofuse;
     AK_TRY(check_multi_gpu(ctx, p));
+    if (f->rhs_minus != nullptr || f->sumsq_dev != nullptr) {
+        // restart residual b - J v (+ its norm): fused into the store of the 2-D tangent stencils (the 512 MiB vectors of
+        // the benchmark configs); everywhere else the reference's three operations (mul!, kaxpby!, knorm)
+        const bool fused2d = (p->kind == AK_BRATU2D || p->kind == AK_HEAT2D) && p->scheme != AK_MIDPOINT &&
+                             p->jvp_mode == AK_JVP_ANALYTIC;
+        if (!fused2d) {
+            const int64_t n = ak_problem_size(p);
+            JvpFusion g = *f;
+            g.rhs_minus = nullptr;
+            g.sumsq_dev = nullptr;
+            AK_TRY(launch_jvp(ctx, p, u, v, out, &g));
+            if (f->rhs_minus) AK_TRY(launch_axpby(ctx, n, 1.0, f->rhs_minus, -1.0, out));
+            if (f->sumsq_dev) AK_TRY(launch_sumsq(ctx, n, out, f->sumsq_dev));
+            return AK_OK;
+        }
+    }
     ProfScope prof(ctx, PK_JVP);
     if (p->kind == AK_USER || fd_generic(p)) {
         // caller-supplied tangent, or (F(u + eps v) - F(u)) / eps through the residual; the fused normalisation
@@ -1254,9 +1299,7 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
         if (f->scale_src) AK_TRY(launch_divcopy_dev(ctx, n, v, f->scale_src, f->denom_dev, f->stop_flag));
         if (fd_generic(p)) AK_TRY(launch_jvp_fd(ctx, p, u, v, out));
         else AK_TRY(user_jvp(ctx, p, u, v, out));
-        if (f->rhs_minus) AK_TRY(launch_axpby(ctx, n, 1.0, f->rhs_minus, -1.0, out));
         if (f->dot_with) AK_TRY(launch_mgs_step(ctx, n, out, nullptr, nullptr, f->dot_with, 0, f->dot_dev, f->stop_flag));
-        else if (f->sumsq_dev) AK_TRY(launch_sumsq(ctx, n, out, f->sumsq_dev));
         return AK_OK;
     }
     if (p->scheme == AK_MIDPOINT) {
@@ -1267,9 +1310,7 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
         }
         if (f->scale_src) AK_TRY(launch_divcopy_dev(ctx, n, v, f->scale_src, f->denom_dev, f->stop_flag));
         AK_TRY(launch_jvp_midpoint(ctx, p, v, out));
-        if (f->rhs_minus) AK_TRY(launch_axpby(ctx, n, 1.0, f->rhs_minus, -1.0, out));
         if (f->dot_with) AK_TRY(launch_mgs_step(ctx, n, out, nullptr, nullptr, f->dot_with, 0, f->dot_dev, f->stop_flag));
-        else if (f->sumsq_dev) AK_TRY(launch_sumsq(ctx, n, out, f->sumsq_dev));
         return AK_OK;
     }
     // un-normalised Krylov basis (f->raw): the stored vector scale_src is the seed, J(scale_src) / denom the result
@@ -1281,14 +1322,9 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     if (raw && native) v = const_cast<double*>(f->scale_src);
     if (p->kind == AK_SIMPLE2) {
         if (scale) AK_TRY(launch_divcopy_dev(ctx, 2, v, f->scale_src, f->denom_dev, f->stop_flag));
-        k_simple2<<<1, 32, 0, ctx->stream>>>(u, v, out, f->rhs_minus ? nullptr : red_out, 1, f->dot_with, f->stop_flag);
+        k_simple2<<<1, 32, 0, ctx->stream>>>(u, v, out, red_out, 1, f->dot_with, f->stop_flag);
         ctx->launches++;
         AK_CUDA(cudaGetLastError());
-        if (f->rhs_minus) {
-            AK_TRY(launch_axpby(ctx, 2, 1.0, f->rhs_minus, -1.0, out));
-            if (f->dot_with) AK_TRY(launch_mgs_step(ctx, 2, out, nullptr, nullptr, f->dot_with, 0, f->dot_dev, f->stop_flag));
-            else if (f->sumsq_dev) AK_TRY(launch_sumsq(ctx, 2, out, f->sumsq_dev));
-        }
         return AK_OK;
     }
     if (p->kind == AK_HEAT1D_DG) {
@@ -1299,10 +1335,9 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
         d.in = scale ? f->scale_src : v;
         AK_TRY(ghost_1d(ctx, d.in, p->nx, 4, 1, true, &d.lo, &d.hi));
         d.in_write = v; d.denom = f->denom_dev; d.out_scale = raw ? f->denom_dev : nullptr;
-        d.out = out; d.dot_with = f->dot_with; d.red_out = red_out; d.bminus = f->rhs_minus;
+        d.out = out; d.dot_with = f->dot_with; d.red_out = red_out;
         d.partials = ctx->partials; d.ticket = ctx->ticket; d.stop = f->stop_flag;
-        AK_REQUIRE(al(d.in, 32) && al(v, 32) && al(out, 32) && al(f->dot_with, 32) && al(f->rhs_minus, 32),
-                   "DG vectors must be 32-byte aligned");
+        AK_REQUIRE(al(d.in, 32) && al(v, 32) && al(out, 32) && al(f->dot_with, 32), "DG vectors must be 32-byte aligned");
         AK_TRY(launch_dg(ctx, d, false, scale, red));
         if (red) AK_TRY(allreduce_sum(ctx, red_out, 1));
         return AK_OK;
@@ -1393,7 +1428,9 @@ int launch_jvp_batched_bratu(Ctx* ctx, const ak_problem* p, const double* u, con
         const int64_t gx = (a.nx + (int64_t)kTX * vec - 1) / ((int64_t)kTX * vec);
         const int64_t gy = (a.ny + kBatchRY - 1) / kBatchRY;
         if (gy > 65535) { set_error("ak_jvp_batched: more than 65535 row tiles"); return AK_ERR_UNSUPPORTED; }
-        dim3 grid((unsigned)gx, (unsigned)gy);
+        const int64_t gz = (ncols + kCB - 1) / kCB;
+        if (gz > 65535) { set_error("ak_jvp_batched: more than 65535 column groups"); return AK_ERR_UNSUPPORTED; }
+        dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz);
         if (vec == 4) k_bratu2d_jvp_batched<4><<<grid, kTX, 0, ctx->stream>>>(a);
         else if (vec == 2) k_bratu2d_jvp_batched<2><<<grid, kTX, 0, ctx->stream>>>(a);
         else k_bratu2d_jvp_batched<1><<<grid, kTX, 0, ctx->stream>>>(a);

@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, session C: GPU tests, kernel GB/s table, short bench, ncu of the reworked 1-D / DG kernels
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q --maxfail=30 --deselect tests/test_gpu_multi.py > gpurun_out/r2c_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2c_pytest.log
+tail -4 gpurun_out/r2c_pytest.log
+python tools/quick_bench.py > gpurun_out/r2c_quick_bench.txt 2>&1; echo "quick rc=$?"
+cat gpurun_out/r2c_quick_bench.txt
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2c_bench.json 2> gpurun_out/r2c_bench.err; echo "bench rc=$?"
+tail -c 600 gpurun_out/r2c_bench.err
+python tools/ncu_1d_driver.py 4 > gpurun_out/r2c_ncu1d_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'k_stencil1d|k_dg' -s 6 -c 6 -o gpurun_out/r02_ncu_1d_v2 python tools/ncu_1d_driver.py 4 > gpurun_out/r2c_ncu1d.log 2>&1
+echo "ncu rc=$?"
