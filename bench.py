@@ -193,7 +193,8 @@ class Workload:
                     P = -(-k // blk)
                     blen = [min(blk, k - blk * j) for j in range(P)]
                     seq = [blen[r % P] for r in range(sweeps * P)]
-                    units += 1 + seq[0]                                   # first pass: w, block 0
+                    # first pass: block 0 (+ w, unless the 2-D tangent kernel does the projections while w is in registers)
+                    units += seq[0] + (0 if cfg["kind"] in ("bratu2d", "heat2d") else 1)
                     for r in range(1, len(seq)):
                         units += 2 + seq[r - 1] + seq[r]                  # subtract one block, project on the next
                     units += 2 + seq[-1]                                  # final pass

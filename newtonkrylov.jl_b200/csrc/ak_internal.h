@@ -41,7 +41,8 @@ void set_error(const char* fmt, ...);
 // ---- NVLink peer memory (CUDA IPC) for the fused compute + collective kernels -----------------
 // One cudaMalloc'ed block per rank, mapped into every other rank of the node:
 //   mail : kMailSlots x nranks records {kBlkSums sums, tag, pad}  — partial sums written by peer kernels
-//   halo : 2 parities x {lo, hi} x halo_cap doubles       — boundary rows pushed by the neighbours
+//   halo : 2 parities x {lo, hi} x halo_cap doubles       — boundary rows pushed by the neighbours' final Gram-Schmidt pass
+//   ghost: 2 parities x {lo, hi} x halo_cap doubles       — ghost values pushed by the stand-alone exchange kernel
 constexpr int kMaxPeers = 8;
 constexpr int kMailSlots = 8;
 constexpr int kBlkMax = 8;    // most Gram-Schmidt steps per sweep over w (largest block of the blocked sweep)
@@ -118,8 +119,12 @@ struct Ctx {
     int* p2p_err = nullptr;                      // pinned, mapped
     uint64_t p2p_seq = 0;                        // collective sequence number (identical on all ranks)
     P2PDev p2p_dev() const;
+    uint64_t p2p_xchg = 0;                       // count of stand-alone ghost exchanges (parity of their slots)
     double* p2p_halo_local(int parity, int hi) const;              // this rank's ghost rows
     double* p2p_halo_of(int peer, int parity, int hi) const;       // a neighbour's ghost rows (mapped)
+    // second set of ghost slots, used by the stand-alone exchanges (residuals, tangents outside the blocked sweep)
+    double* p2p_ghost_local(int parity, int hi) const;
+    double* p2p_ghost_of(int peer, int parity, int hi) const;
 };
 
 // RAII: brackets one kernel launch with events when the profiler is on (context.cu)
@@ -211,6 +216,12 @@ struct JvpFusion {
     // out = rhs_minus - J v, and (sumsq_dev != null, exclusive with dot_with) *sumsq_dev = ||out||^2
     const double* rhs_minus = nullptr;
     double* sumsq_dev = nullptr;
+    // first projection pass of the blocked Gram-Schmidt sweep folded into the tangent kernel (2-D analytic tangents):
+    // proj_out[b] = <proj[b], out>, b < nproj; with proj_comm (peer memory) the sums go to the ranks' mailboxes
+    const double* const* proj = nullptr;
+    int nproj = 0;
+    double* proj_out = nullptr;
+    const struct BlockComm* proj_comm = nullptr;
     const int* stop_flag = nullptr;
     // ghost rows already delivered by the neighbours through peer memory (skips the NCCL exchange)
     bool halo_given = false;

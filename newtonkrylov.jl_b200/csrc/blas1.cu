@@ -187,26 +187,24 @@ __global__ void __launch_bounds__(kThreads, mgs_block_min_blocks(NAX, NRED)) k_m
     constexpr int NS = FINAL ? 1 + NAX : NRED;
     __shared__ double sh[32];
     __shared__ double shm[kBlkSums * kMaxPeers];
+    __shared__ double s_t[kBlkSums], s_g[kBlkMax * kBlkMax], s_h[kBlkMax], s_c[kBlkMax];
     if (stop != nullptr && *stop != 0) return;
     double h[kBlkMax];  // negated multipliers of the stored vectors of the block being subtracted
 #pragma unroll
     for (int b = 0; b < kBlkMax; ++b) h[b] = 0.0;
     if (NAX >= 1) {
-        double t[kBlkSums];
         if (P2P && pp.seq_in != 0) {
-            mail_wait_sum(pp.pd, pp.seq_in, t, NAX, shm, const_cast<int*>(stop));
-            if (blockIdx.x == 0 && threadIdx.x == 0 && pp.tin_store != nullptr) {
-#pragma unroll
-                for (int c = 0; c < NAX; ++c) pp.tin_store[c] = t[c];
-            }
+            mail_wait_sum(pp.pd, pp.seq_in, s_t, NAX, shm, const_cast<int*>(stop));
+            if (blockIdx.x == 0 && threadIdx.x < NAX && pp.tin_store != nullptr) pp.tin_store[threadIdx.x] = s_t[threadIdx.x];
         } else {
-#pragma unroll
-            for (int c = 0; c < kBlkSums; ++c) t[c] = (c < NAX) ? tin[c] : 0.0;
+            if (threadIdx.x < NAX) s_t[threadIdx.x] = tin[threadIdx.x];
+            __syncthreads();
         }
-        double hc[kBlkMax];
-        block_coefficients(t, gram_in, rho_in, NAX, hc, h);
+        // one warp turns the raw projections into the Gram-Schmidt multipliers, the block reads them from shared memory
+        if (threadIdx.x < 32) block_coefficients_warp(threadIdx.x, s_t, gram_in, rho_in, NAX, s_g, s_h, s_c);
+        __syncthreads();
 #pragma unroll
-        for (int b = 0; b < kBlkMax; ++b) h[b] = -h[b];
+        for (int b = 0; b < NAX; ++b) h[b] = -s_c[b];
     }
     double sA[NS], sB[NS];  // two accumulator sets (even / odd elements of a 256-bit word)
 #pragma unroll

@@ -171,10 +171,11 @@ AK_DEV void mail_post(const P2PDev& pd, unsigned long long seq, const double* va
     }
 }
 // Whole block: wait until every rank's record `seq` has arrived in the local mailbox and add them in rank
-// order (bit-identical on every rank).  Result in out[0..ns) for all threads.  `shm` >= kMaxPeers * kBlkSums doubles.
+// order (bit-identical on every rank).  Result in out_s[0..ns) (SHARED memory, visible to the whole block on return).
+// `shm` >= kMaxPeers * kBlkSums doubles.
 // A record that never arrives (a peer fell out of step) raises the mapped error flag AND the device `stop` flag of the
 // solve (`stop_w`, may be null), so that every later kernel of the solve is a no-op instead of spinning again.
-AK_DEV void mail_wait_sum(const P2PDev& pd, unsigned long long seq, double (&out)[kBlkSums], int ns, double* shm,
+AK_DEV void mail_wait_sum(const P2PDev& pd, unsigned long long seq, double* out_s, int ns, double* shm,
                           int* stop_w = nullptr) {
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
     const int slot = (int)(seq % kMailSlots);
@@ -192,10 +193,11 @@ AK_DEV void mail_wait_sum(const P2PDev& pd, unsigned long long seq, double (&out
         for (int c = 0; c < ns; ++c) shm[kBlkSums * tid + c] = __ldcv(rec + c);
     }
     __syncthreads();
-#pragma unroll
-    for (int c = 0; c < kBlkSums; ++c) out[c] = 0.0;
-    for (int q = 0; q < pd.nranks; ++q)
-        for (int c = 0; c < ns; ++c) out[c] += shm[kBlkSums * q + c];
+    if (tid < ns) {
+        double a = 0.0;
+        for (int q = 0; q < pd.nranks; ++q) a += shm[kBlkSums * q + tid];
+        out_s[tid] = a;
+    }
     __syncthreads();
 }
 
@@ -208,24 +210,34 @@ AK_DEV void mail_wait_sum(const P2PDev& pd, unsigned long long seq, double (&out
 // Modified Gram-Schmidt coefficients:  h_b = <v_b, w - sum_{a<b} h_a v_a> = <v_b,w> - sum_{a<b} h_a <v_b,v_a>, and
 // c_b = h_b / rho[b] is what multiplies the stored vector in the update w -= sum_b c_b S_b.
 // One definition shared by the vector kernels and the Givens kernel so that both see the same bits.
-AK_DEV void block_coefficients(const double* t, const double* gram, const double* rho, int m, double (&h)[kBlkMax],
-                               double (&c)[kBlkMax]) {
-#pragma unroll
-    for (int b = 0; b < kBlkMax; ++b) {
-        double acc = 0.0, cb = 0.0;
-        if (b < m) {
-            const double rb = rho ? rho[b] : 1.0;
-            acc = rho ? __ddiv_rn(t[b], rb) : t[b];
-            for (int a = 0; a < b; ++a) {
-                double g = gram[b * kBlkMax + a];
-                if (rho) g = __ddiv_rn(__ddiv_rn(g, rb), rho[a]);
-                acc = __dsub_rn(acc, __dmul_rn(h[a], g));
-            }
-            cb = rho ? __ddiv_rn(acc, rb) : acc;
+// Executed by ONE WARP: the scalings <v_b,v_a> = <S_b,S_a> / rho_b / rho_a (two IEEE divisions per entry, up to 28
+// entries) are independent and go to the lanes; only the forward substitution (m(m-1)/2 multiply-subtract pairs in the
+// serial order) runs on lane 0.  A single thread doing all of it — what every thread of every pass used to do at kernel
+// start — took ~12 000 cycles per block: 6 us in front of each of the ~200 passes of a step, 19 us per Givens kernel.
+// Results: s_h[b] = h_b, s_c[b] = c_b (zero for b >= m), in shared memory; the caller synchronises the block.
+AK_DEV void block_coefficients_warp(int lane, const double* t, const double* gram, const double* rho, int m,
+                                    double* s_g /* kBlkMax * kBlkMax */, double* s_h /* kBlkMax */,
+                                    double* s_c /* kBlkMax */) {
+    for (int q = lane; q < m * kBlkMax; q += 32) {
+        const int b = q / kBlkMax, a = q % kBlkMax;
+        if (a < b) {
+            double g = gram[q];
+            if (rho) g = __ddiv_rn(__ddiv_rn(g, rho[b]), rho[a]);
+            s_g[q] = g;
         }
-        h[b] = acc;
-        c[b] = cb;
     }
+    if (lane < kBlkMax) s_h[lane] = lane < m ? (rho ? __ddiv_rn(t[lane], rho[lane]) : t[lane]) : 0.0;
+    __syncwarp();
+    if (lane == 0) {
+        for (int b = 1; b < m; ++b) {
+            double acc = s_h[b];
+            for (int a = 0; a < b; ++a) acc = __dsub_rn(acc, __dmul_rn(s_h[a], s_g[b * kBlkMax + a]));
+            s_h[b] = acc;
+        }
+    }
+    __syncwarp();
+    if (lane < kBlkMax) s_c[lane] = lane < m ? (rho ? __ddiv_rn(s_h[lane], rho[lane]) : s_h[lane]) : 0.0;
+    __syncwarp();
 }
 
 }  // namespace ak

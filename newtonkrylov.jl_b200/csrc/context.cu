@@ -113,9 +113,65 @@ struct Comm {
     ncclComm_t comm = nullptr;
 };
 
+// ---- stand-alone collectives over NVLink peer memory -----------------------------------------------------------
+// All-reduce of up to kBlkSums doubles through the mailboxes: thread 0 deposits this rank's values in every rank's
+// mailbox (st.global over NVLink + release of the sequence tag), then the block waits for every rank's record and adds
+// them in rank order (bit-identical on all ranks).  Replaces an in-stream ncclAllReduce (a kernel launch of its own
+// plus the proxy/LL protocol latency) by ~2 us of peer stores for the scalars of CG, the step-wise Gram-Schmidt kernels
+// and the norms at the cycle boundaries.
+__global__ void __launch_bounds__(32) k_mail_allreduce(double* vals, int count, const P2PDev pd, unsigned long long seq) {
+    __shared__ double shm[kBlkSums * kMaxPeers];
+    __shared__ double tot[kBlkSums];
+    if (threadIdx.x == 0) mail_post(pd, seq, vals, count);
+    __syncwarp();
+    mail_wait_sum(pd, seq, tot, count, shm);
+    if ((int)threadIdx.x < count) vals[threadIdx.x] = tot[threadIdx.x];
+}
+
+// Ghost exchange of a slab / segment: the last `cnt_up` values of v go into the up (right) neighbour's "lo" slot, the
+// first `cnt_down` values into the down (left) neighbour's "hi" slot (peer stores), then an all-to-all signal through
+// the mailboxes: when the kernel ends, this rank's own slots hold its neighbours' values.
+__global__ void __launch_bounds__(1024) k_push_ghost(const double* __restrict__ v, int64_t n, int cnt_up, int cnt_down,
+                                                     double* up_lo, double* down_hi, const P2PDev pd,
+                                                     unsigned long long seq) {
+    __shared__ double shm[kBlkSums * kMaxPeers];
+    if (up_lo != nullptr)
+        for (int i = threadIdx.x; i < cnt_up; i += blockDim.x) up_lo[i] = v[n - cnt_up + i];
+    if (down_hi != nullptr)
+        for (int i = threadIdx.x; i < cnt_down; i += blockDim.x) down_hi[i] = v[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) mail_post(pd, seq, nullptr, 0);
+    mail_wait_sum(pd, seq, nullptr, 0, shm);
+}
+
+static int p2p_allreduce(Ctx* ctx, double* dev, int count) {
+    const unsigned long long seq = ++ctx->p2p_seq;
+    ProfScope prof(ctx, PK_SCALAR);
+    k_mail_allreduce<<<1, 32, 0, ctx->stream>>>(dev, count, ctx->p2p_dev(), seq);
+    ctx->launches++;
+    AK_CUDA(cudaGetLastError());
+    return AK_OK;
+}
+
 int allreduce_sum(Ctx* ctx, double* dev, int count) {
     if (ctx->nranks <= 1) return AK_OK;
+    if (ctx->p2p_on && count <= kBlkSums) return p2p_allreduce(ctx, dev, count);
     AK_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclFloat64, ncclSum, ctx->comm->comm, ctx->stream));
+    return AK_OK;
+}
+
+// peer-memory form of the two exchanges below; cnt_* <= p2p_halo_cap
+static int p2p_exchange(Ctx* ctx, const double* v, int64_t n, int cnt_up, int cnt_down, int up, int down,
+                        const double** lo, const double** hi) {
+    const int par = (int)(ctx->p2p_xchg++ & 1);
+    const unsigned long long seq = ++ctx->p2p_seq;
+    k_push_ghost<<<1, 1024, 0, ctx->stream>>>(v, n, cnt_up, cnt_down, up >= 0 ? ctx->p2p_ghost_of(up, par, 0) : nullptr,
+                                              down >= 0 ? ctx->p2p_ghost_of(down, par, 1) : nullptr, ctx->p2p_dev(), seq);
+    ctx->launches++;
+    AK_CUDA(cudaGetLastError());
+    *lo = down >= 0 ? ctx->p2p_ghost_local(par, 0) : nullptr;
+    *hi = up >= 0 ? ctx->p2p_ghost_local(par, 1) : nullptr;
     return AK_OK;
 }
 
@@ -137,6 +193,11 @@ int collective_verdict(Ctx* ctx, int* rc) {
 int exchange_halo_rows(Ctx* ctx, const double* v, int64_t nx, int64_t ny, int32_t bc, const double** lo,
                        const double** hi) {
     const int P = ctx->nranks, r = ctx->rank;
+    const bool periodic = (bc == AK_BC_PERIODIC);
+    const int down = (r > 0) ? r - 1 : (periodic ? P - 1 : -1);  // owner of row gy0-1
+    const int up = (r < P - 1) ? r + 1 : (periodic ? 0 : -1);    // owner of row gy0+ny
+    if (ctx->p2p_on && nx <= ctx->p2p_halo_cap)  // boundary rows pushed into the neighbours' ghost slots over NVLink
+        return p2p_exchange(ctx, v, nx * ny, (int)nx, (int)nx, up, down, lo, hi);
     if (ctx->halo_cap < nx) {
         AK_CUDA(cudaStreamSynchronize(ctx->stream));
         if (ctx->halo_lo) AK_CUDA(cudaFree(ctx->halo_lo));
@@ -145,9 +206,6 @@ int exchange_halo_rows(Ctx* ctx, const double* v, int64_t nx, int64_t ny, int32_
         AK_CUDA(cudaMalloc(&ctx->halo_hi, sizeof(double) * (size_t)nx));
         ctx->halo_cap = nx;
     }
-    const bool periodic = (bc == AK_BC_PERIODIC);
-    const int down = (r > 0) ? r - 1 : (periodic ? P - 1 : -1);  // owner of row gy0-1
-    const int up = (r < P - 1) ? r + 1 : (periodic ? 0 : -1);    // owner of row gy0+ny
     // Per peer, NCCL matches sends and receives in posting order; with P == 2 and periodic
     // wrap both neighbours are the same rank, so "last row up" is posted before "first row down"
     // and "lo from down" before "hi from up".
@@ -176,6 +234,8 @@ int exchange_halo_1d(Ctx* ctx, const double* v, int64_t n, int nlo, int nhi, boo
     AK_REQUIRE(nlo <= 8 && nhi <= 8 && n >= nlo && n >= nhi, "exchange_halo_1d: bad ghost width");
     const int left = (r > 0) ? r - 1 : (periodic ? P - 1 : -1);
     const int right = (r < P - 1) ? r + 1 : (periodic ? 0 : -1);
+    if (ctx->p2p_on && ctx->p2p_halo_cap >= 8)  // this rank's last nlo values -> right neighbour's lo, first nhi -> left's hi
+        return p2p_exchange(ctx, v, n, nlo, nhi, right, left, lo, hi);
     // posting order per peer as in exchange_halo_rows (P == 2 with wrap: both neighbours are the same rank)
     AK_NCCL(g_nccl.GroupStart());
     if (right >= 0) AK_NCCL(g_nccl.Send(v + (n - nlo), (size_t)nlo, ncclFloat64, right, ctx->comm->comm, ctx->stream));
@@ -206,6 +266,8 @@ double* Ctx::p2p_halo_local(int parity, int hi) const {
 double* Ctx::p2p_halo_of(int peer, int parity, int hi) const {
     return (double*)p2p_peer_block[peer] + p2p_mail_doubles(nranks) + ((size_t)parity * 2 + hi) * p2p_halo_cap;
 }
+double* Ctx::p2p_ghost_local(int parity, int hi) const { return p2p_halo_local(parity, hi) + (size_t)4 * p2p_halo_cap; }
+double* Ctx::p2p_ghost_of(int peer, int parity, int hi) const { return p2p_halo_of(peer, parity, hi) + (size_t)4 * p2p_halo_cap; }
 
 // ---- HaloVector layout bridge -----------------------------------------------------------
 __global__ void k_halo_pack(double* __restrict__ compact, const double* __restrict__ padded, int64_t nx, int64_t ny) {
@@ -476,8 +538,9 @@ AK_API int ak_comm_enable_p2p(ak_ctx* ctx, int64_t halo_doubles) {
     }
     AK_CUDA(cudaSetDevice(c->device));
     const int P = c->nranks;
-    const int64_t hcap = (halo_doubles + 3) & ~int64_t(3);
-    const size_t doubles = p2p_mail_doubles(P) + (size_t)4 * hcap;
+    int64_t hcap = (halo_doubles + 3) & ~int64_t(3);
+    if (hcap < 8) hcap = 8;  // the 1-D ghost exchanges move up to 8 values
+    const size_t doubles = p2p_mail_doubles(P) + (size_t)8 * hcap;  // mailboxes, 4 halo rows, 4 stand-alone ghost slots
     // cudaMalloc (not the stream-ordered pool): IPC handles exist only for plain allocations
     AK_CUDA(cudaMalloc(&c->p2p_block, sizeof(double) * doubles));
     AK_CUDA(cudaMemset(c->p2p_block, 0, sizeof(double) * doubles));
@@ -487,28 +550,45 @@ AK_API int ak_comm_enable_p2p(ak_ctx* ctx, int64_t halo_doubles) {
     // all-reduced, so that either all ranks switch to the peer-memory path or none does.
     int failed = 0;
     char why[256] = "";
-    cudaIpcMemHandle_t mine;
+    struct Card {  // what every rank tells the others: the IPC handle of its block and which physical GPU it sits on
+        cudaIpcMemHandle_t handle;
+        char busid[32];
+    } mine;
     memset(&mine, 0, sizeof(mine));
-    cudaError_t e = cudaIpcGetMemHandle(&mine, c->p2p_block);
+    cudaError_t e = cudaIpcGetMemHandle(&mine.handle, c->p2p_block);
     if (e != cudaSuccess) {
         failed = 1;
         snprintf(why, sizeof(why), "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
         (void)cudaGetLastError();
     }
-    // exchange the 64-byte handles with an all-gather on the library's own communicator
+    if (cudaDeviceGetPCIBusId(mine.busid, (int)sizeof(mine.busid), c->device) != cudaSuccess) {
+        (void)cudaGetLastError();
+        snprintf(mine.busid, sizeof(mine.busid), "unknown-%d", c->rank);
+    }
+    // exchange the cards with an all-gather on the library's own communicator
     char *dsend = nullptr, *drecv = nullptr;
     AK_CUDA(cudaMalloc(&dsend, sizeof(mine)));
     AK_CUDA(cudaMalloc(&drecv, sizeof(mine) * P));
     AK_CUDA(cudaMemcpyAsync(dsend, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
     AK_NCCL(g_nccl.AllGather(dsend, drecv, sizeof(mine), /*ncclChar*/ 0, c->comm->comm, c->stream));
-    std::vector<cudaIpcMemHandle_t> all((size_t)P);
+    std::vector<Card> all((size_t)P);
     AK_CUDA(cudaMemcpyAsync(all.data(), drecv, sizeof(mine) * P, cudaMemcpyDeviceToHost, c->stream));
     AK_CUDA(cudaStreamSynchronize(c->stream));
     AK_CUDA(cudaFree(dsend));
     AK_CUDA(cudaFree(drecv));
+    // The mailbox kernels of different ranks wait for one another.  Two ranks on ONE GPU would be kernels that spin on
+    // each other's flags on the same device: nothing guarantees that they run at the same time (Xid 109, context-switch
+    // time-out).  Every rank sees the same cards, so every rank refuses alike.
+    for (int q = 0; q < P && !failed; ++q)
+        for (int q2 = q + 1; q2 < P && !failed; ++q2)
+            if (strncmp(all[(size_t)q].busid, all[(size_t)q2].busid, sizeof(mine.busid)) == 0) {
+                failed = 1;
+                snprintf(why, sizeof(why), "ranks %d and %d share the GPU %s: the peer-memory path needs one GPU per rank "
+                         "(use the NCCL path)", q, q2, all[(size_t)q].busid);
+            }
     for (int q = 0; q < P && !failed; ++q) {
         if (q == c->rank) { c->p2p_peer_block[q] = c->p2p_block; continue; }
-        e = cudaIpcOpenMemHandle(&c->p2p_peer_block[q], all[(size_t)q], cudaIpcMemLazyEnablePeerAccess);
+        e = cudaIpcOpenMemHandle(&c->p2p_peer_block[q], all[(size_t)q].handle, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             failed = 1;
             c->p2p_peer_block[q] = nullptr;

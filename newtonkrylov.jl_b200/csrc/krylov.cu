@@ -12,6 +12,7 @@
 // k+1 before it knows the outcome of iteration k (it reads a pinned status record one iteration
 // late), so the stream never drains inside a pass.  The Krylov basis stays resident in HBM.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(32) k_gmres_givens(KrylovCtl* ctl, int k, int6
                                                      double* z, double* hcol, int reorth, int blk, double* hist,
                                                      int64_t hist_pos, int inner_limit, KrylovStatus* st, const P2PDev pd,
                                                      unsigned long long seq_in, double* rho_vec, double* gram) {
-    __shared__ double s_t[kBlkSums], s_g[kBlkMax * kBlkMax], s_rho[kBlkMax];
+    __shared__ double s_t[kBlkSums], s_g[kBlkMax * kBlkMax], s_hb[kBlkMax], s_cb[kBlkMax];
     __shared__ double s_c[32], s_s[32], s_r[33];
     __shared__ int s_abort;
     const int lane = threadIdx.x;
@@ -174,17 +175,13 @@ __global__ void __launch_bounds__(32) k_gmres_givens(KrylovCtl* ctl, int k, int6
         for (int sw = 0; sw < nsweep; ++sw) {
             for (int j = 0; j < nblk; ++j) {
                 const int m = (k - j * blk) < blk ? (k - j * blk) : blk;
-                // warp-wide prefetch of the block's sums, Gram entries and scales
+                // the same warp-cooperative routine the vector kernels ran on these sums (same bits)
                 if (lane < kBlkSums) s_t[lane] = hcol[kBlkSums * (sw * nblk + j) + lane];
-                for (int q = lane; q < m * kBlkMax; q += 32) s_g[q] = gram[(size_t)j * blk * kBlkMax + q];  // rows b < m
-                if (lane < kBlkMax && rho_vec != nullptr && lane < m) s_rho[lane] = rho_vec[j * blk + lane];
                 __syncwarp();
-                if (lane == 0) {
-                    double hb[kBlkMax], cb[kBlkMax];
-                    block_coefficients(s_t, s_g, rho_vec ? s_rho : nullptr, m, hb, cb);
-                    // second sweep: R[nr+i] += Htmp (gmres! step 5)
-                    for (int b = 0; b < m; ++b) R[nr + j * blk + b] = sw == 0 ? hb[b] : R[nr + j * blk + b] + hb[b];
-                }
+                block_coefficients_warp(lane, s_t, gram + (size_t)j * blk * kBlkMax, rho_vec ? rho_vec + j * blk : nullptr, m,
+                                        s_g, s_hb, s_cb);
+                // second sweep: R[nr+i] += Htmp (gmres! step 5)
+                if (lane < m) R[nr + j * blk + lane] = sw == 0 ? s_hb[lane] : R[nr + j * blk + lane] + s_hb[lane];
                 __syncwarp();
             }
         }
@@ -612,11 +609,17 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     // problem kinds without a fused normalise + JVP kernel get the normalised seed in a scratch vector
     const bool raw_needs_seed = raw && !hosted && (prob->kind == AK_SIMPLE2 || prob->kind == AK_USER ||
                                                    prob->scheme == AK_MIDPOINT || prob->jvp_mode == AK_JVP_FD);
+    // 2-D analytic tangents: the first projection pass of every iteration is folded into the tangent kernel
+    // (AK_NO_PROJ_FUSION=1 keeps the separate pass: a developer switch for A/B timing)
+    static const bool no_proj_fusion = getenv("AK_NO_PROJ_FUSION") != nullptr;
+    const bool proj_in_jvp = raw && !hosted && is2d && prob->scheme != AK_MIDPOINT && prob->jvp_mode == AK_JVP_ANALYTIC &&
+                             !no_proj_fusion;
     if (raw_needs_seed && !ws->pbuf) AK_TRY(ws_alloc_vec(ws, &ws->pbuf));
     AK_TRY(ws_grow_scalars(ws, mem));
     if (want_hist) AK_TRY(ws_grow_hist(ws, 257));
 
-    if (p2p && *c->p2p_err) {
+    const bool peer = c->p2p_on && c->nranks > 1;  // some collective of this solve goes through the mailboxes
+    if (peer && *c->p2p_err) {
         set_error("the peer-memory path of this context is latched off after a time-out; call ak_comm_use_p2p on every rank");
         return AK_ERR_PEER;
     }
@@ -789,6 +792,28 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                     jf.dot_with = ws->V[0];
                     jf.dot_dev = hcol;
                 }
+                // `blk` Gram-Schmidt steps per sweep over w.  Pass list of one iteration: project on block 0; then
+                // every pass subtracts the block the previous pass projected on and projects on the next one
+                // (re-orthogonalisation: the blocks are visited a second time, gmres! step 5); the final pass
+                // subtracts the last block and measures ||w||^2.  Record r of hcol holds the sums of pass r.
+                const int64_t P = pair ? (k + blk - 1) / blk : 0;
+                const int64_t npj = (reorth ? 2 : 1) * P;  // projection passes
+                auto blk_ptr = [&](int64_t j) -> const double* const* { return ws->V.data() + blk * j; };
+                auto blk_len = [&](int64_t j) -> int { return (int)((k - blk * j) < blk ? (k - blk * j) : blk); };
+                auto blk_rho = [&](int64_t j) -> const double* { return ws->rho + blk * j; };
+                auto blk_gram = [&](int64_t j) -> const double* { return ws->gram + blk * j * kBlkMax; };
+                BlockComm pc;
+                unsigned long long prev_seq = 0;
+                if (pair) {
+                    if (p2p) { pc.seq_out = ++c->p2p_seq; prev_seq = pc.seq_out; }
+                    if (proj_in_jvp) {
+                        // the first projection pass rides in the tangent kernel: <S_b, w> for block 0 while w is in registers
+                        jf.proj = blk_ptr(0);
+                        jf.nproj = blk_len(0);
+                        jf.proj_out = hcol;
+                        jf.proj_comm = p2p ? &pc : nullptr;
+                    }
+                }
                 if (lprec) {  // w <- M (A N v_k)
                     AK_TRY(launch_jvp(c, prob, u, seed, ws->qbuf, &jf));
                     AK_TRY(apply_precond(ws, prob, u, o, true, ws->qbuf, wout));
@@ -798,21 +823,9 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 w = wout;
                 // modified Gram-Schmidt
                 if (pair) {
-                    // `blk` Gram-Schmidt steps per sweep over w.  Pass list of one iteration: project on block 0; then
-                    // every pass subtracts the block the previous pass projected on and projects on the next one
-                    // (re-orthogonalisation: the blocks are visited a second time, gmres! step 5); the final pass
-                    // subtracts the last block and measures ||w||^2.  Record r of hcol holds the sums of pass r.
-                    const int64_t P = (k + blk - 1) / blk;
-                    const int64_t npj = (reorth ? 2 : 1) * P;  // projection passes
-                    auto blk_ptr = [&](int64_t j) -> const double* const* { return ws->V.data() + blk * j; };
-                    auto blk_len = [&](int64_t j) -> int { return (int)((k - blk * j) < blk ? (k - blk * j) : blk); };
-                    auto blk_rho = [&](int64_t j) -> const double* { return ws->rho + blk * j; };
-                    auto blk_gram = [&](int64_t j) -> const double* { return ws->gram + blk * j * kBlkMax; };
-                    BlockComm pc;
-                    unsigned long long prev_seq = 0;
-                    if (p2p) { pc.seq_out = ++c->p2p_seq; prev_seq = pc.seq_out; }
-                    AK_TRY(launch_mgs_block(c, n, w, nullptr, 0, nullptr, nullptr, nullptr, blk_ptr(0), blk_len(0), 0, hcol,
-                                            stop, p2p ? &pc : nullptr));
+                    if (!proj_in_jvp)
+                        AK_TRY(launch_mgs_block(c, n, w, nullptr, 0, nullptr, nullptr, nullptr, blk_ptr(0), blk_len(0), 0, hcol,
+                                                stop, p2p ? &pc : nullptr));
                     for (int64_t r = 1; r < npj; ++r) {
                         const int64_t js = (r - 1) % P, jp = r % P;  // block subtracted / block projected on
                         if (p2p) {
@@ -904,7 +917,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
             if (K > 0 && !update_queued) AK_TRY(queue_solution_update(k));
         }
         if (K > 0) x_written = true;
-        if (p2p && *c->p2p_err) break;  // a peer fell out of step: reported below
+        if (peer && *c->p2p_err) break;  // a peer fell out of step: reported below
         inner_itmax -= K;
         iter += K;
         if (iter >= itmax) tired = true;
@@ -921,7 +934,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     }
     AK_CUDA(cudaStreamSynchronize(sm));
     inconsistent = ws->status[kStatusRing + 1].inconsistent != 0;
-    if (p2p && *c->p2p_err) {
+    if (peer && *c->p2p_err) {
         set_error("peer-memory collective timed out (a rank fell out of step); the peer path of this context is "
                   "latched off until ak_comm_use_p2p is called again on every rank");
         return AK_ERR_PEER;
@@ -1026,6 +1039,11 @@ static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, cons
         rNorm = hs.rNorm;
     }
     AK_CUDA(cudaStreamSynchronize(sm));
+    if (c->p2p_on && c->nranks > 1 && *c->p2p_err) {
+        set_error("peer-memory collective timed out (a rank fell out of step); the peer path of this context is "
+                  "latched off until ak_comm_use_p2p is called again on every rank");
+        return AK_ERR_PEER;
+    }
     st->niter = iter;
     st->solved = solved;
     st->inconsistent = zerocurv;

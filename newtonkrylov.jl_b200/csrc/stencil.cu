@@ -24,7 +24,7 @@
 namespace ak {
 
 enum { OP_RES_BRATU = 0, OP_JVP_BRATU = 1, OP_RES_HEAT = 2, OP_JVP_HEAT = 3, OP_RHS_HEAT = 4, OP_JVP_BRATU_FD = 5 };  // RHS: du = f(u) only; FD: (F(u+eps v)-F(u))/eps
-enum { RED_NONE = 0, RED_SUMSQ = 1, RED_DOT = 2 };
+enum { RED_NONE = 0, RED_SUMSQ = 1, RED_DOT = 2, RED_PROJ = 3 };  // PROJ: <proj[b], out> for up to kBlkMax vectors (2-D tangents)
 
 struct StencilArgs {
     int64_t nx, ny;
@@ -46,6 +46,13 @@ struct StencilArgs {
     double* in_write;    // fused divcopy: scaled `in` is stored here (own rows) ; 1-D heat: BC write-back target
     const double* out_scale;  // tangent kernels, un-normalised Krylov basis: out = J(in) / *out_scale (device scalar)
     const double* bminus;     // tangent kernels: out = bminus - J(in)  (restart residual b - A x of gmres!)
+    // RED_PROJ: the first projection pass of the blocked Gram-Schmidt sweep folded into the tangent kernel: raw sums
+    // <proj[b], out>, b < nproj, of the vector the kernel has just formed (saves re-reading it: 8n bytes per iteration)
+    const double* proj[kBlkMax];
+    int32_t nproj;
+    double* proj_out;
+    P2PDev pd;                    // multi-GPU with peer memory: the sums go to the ranks' mailboxes (seq_out != 0)
+    unsigned long long seq_out;
     const double* denom; // fused divcopy: device scalar
     const double* dot_with;
     double* red_out;
@@ -134,8 +141,12 @@ AK_DEV double second_diff(double e, double c, double w, const Divisor& d2) {
 constexpr int kTX = 128;  // threads per block, all along x
 
 template <int OP, int VEC, bool SCALE, int RED>
-__global__ void __launch_bounds__(kTX, OP == OP_JVP_BRATU_FD ? 4 : 8) k_stencil2d(const StencilArgs p) {
+__global__ void __launch_bounds__(kTX, OP == OP_JVP_BRATU_FD ? 4 : (RED == RED_PROJ ? 3 : 8)) k_stencil2d(const StencilArgs p) {
     __shared__ double sh[32];
+    constexpr bool PROJ = (RED == RED_PROJ);
+    double accp[PROJ ? kBlkMax : 1];
+#pragma unroll
+    for (int b = 0; b < (PROJ ? kBlkMax : 1); ++b) accp[b] = 0.0;
     if (p.stop != nullptr && *p.stop != 0) return;
     const int lane = threadIdx.x & 31;
     const int64_t nx = p.nx, ny = p.ny;
@@ -242,6 +253,15 @@ __global__ void __launch_bounds__(kTX, OP == OP_JVP_BRATU_FD ? 4 : 8) k_stencil2
                 if (lane == 31 || x0 + VEC >= nx) uright = uedge(ucur_src, x0 + VEC);
             }
             const int64_t off = y * nx + x0;
+            double pv[PROJ ? kBlkMax : 1][VEC];  // the block to project on: loads issued before the row's arithmetic
+            if (PROJ) {
+#pragma unroll
+                for (int b = 0; b < (PROJ ? kBlkMax : 1); ++b) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) pv[b][i] = 0.0;
+                    if (b < p.nproj) ldv_s<VEC>(p.proj[b] + off, pv[b]);
+                }
+            }
             double aux[VEC], o[VEC];
             if (OP == OP_JVP_BRATU || OP == OP_RES_HEAT) ldv_s<VEC>(p.aux + off, aux);
             double cf[VEC];
@@ -305,6 +325,12 @@ __global__ void __launch_bounds__(kTX, OP == OP_JVP_BRATU_FD ? 4 : 8) k_stencil2
                 ldv_s<VEC>(p.dot_with + off, dw);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) acc = fma(dw[i], o[i], acc);
+            } else if (PROJ) {
+#pragma unroll
+                for (int b = 0; b < (PROJ ? kBlkMax : 1); ++b) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) accp[b] = fma(pv[b][i], o[i], accp[b]);
+                }
             }
         }
 #pragma unroll
@@ -318,7 +344,19 @@ __global__ void __launch_bounds__(kTX, OP == OP_JVP_BRATU_FD ? 4 : 8) k_stencil2
             ucur_src = unext_src;
         }
     }
-    if (RED != RED_NONE) {
+    if (PROJ) {
+        double tot[PROJ ? kBlkMax : 1];
+        const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+        if (grid_reduce_n<(PROJ ? kBlkMax : 1)>(accp, p.partials, p.ticket, bid, gridDim.x * gridDim.y, sh, tot, false)) {
+            if (p.seq_out != 0) {
+                mail_post(p.pd, p.seq_out, tot, p.nproj);
+            } else {
+#pragma unroll
+                for (int b = 0; b < (PROJ ? kBlkMax : 1); ++b)
+                    if (b < p.nproj) p.proj_out[b] = tot[b];
+            }
+        }
+    } else if (RED != RED_NONE) {
         const double s = block_sum(acc, sh);
         const int bid = blockIdx.y * gridDim.x + blockIdx.x;
         grid_sum_finish(s, p.partials, p.ticket, bid, gridDim.x * gridDim.y, p.red_out, sh);
@@ -337,37 +375,26 @@ AK_DEV double heat1d_bc_value(const double* src, int64_t i, int64_t n, int bc) {
     return src[i];
 }
 
-// One wave of resident blocks (2 x 256 threads per SM) walks the array, grid-stride over chunks of VEC points.  Every
-// thread keeps kU1 (2-4) chunks in flight per trip: ALL global loads of the trip — the vector operands and, for the warp-edge
-// lanes, the one scalar neighbour a shuffle cannot provide — are issued before any of them is consumed.  (History: the
-// launch-per-chunk version sat at 74-83 % of the copy bandwidth at N = 2^24 — one request per thread and 16 K blocks to
-// schedule; a first persistent version with two chunks in flight and the edge loads issued late had only 16 warps per
-// SM with ~1.5 requests outstanding each and was slower, 55-78 %: profiles/r02_ncu_1d_two_chunks.txt.)
-// (fewer chunks for the variants with more operand streams per chunk: the register file holds all of them at once)
-
+// One chunk of VEC points per thread, one launch-wide wave of small blocks (44-64 registers, 32 warps per SM).
+// Two persistent variants were tried in round 2 and dropped (profiles/r02_ncu_1d_two_chunks.txt, r02_ncu_1d_v2_summary.txt):
+// with 2-4 chunks in flight per thread they need ~120 registers (16 warps per SM) and, although they execute fewer
+// instructions per point, the kernels are instruction-issue bound, not DRAM bound (~50 SASS instructions per point of
+// index arithmetic, boundary predicates and the exact-division fix-up around ~12 fp64 operations): half the warps
+// issued at 45-60 % and ran 55-78 % of the copy bandwidth, this version 74-91 %.
 template <int OP, int VEC, bool SCALE, int RED>
-__global__ void __launch_bounds__(kT1, 2) k_stencil1d(const StencilArgs p) {
+__global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
     __shared__ double sh[32];
     if (p.stop != nullptr && *p.stop != 0) return;
     const int lane = threadIdx.x & 31;
     const int64_t n = p.nx;
+    const int64_t x0 = ((int64_t)blockIdx.x * kT1 + threadIdx.x) * VEC;
+    const bool active = x0 < n;
     const Divisor denom = make_divisor(SCALE ? *p.denom : 1.0);
     const Divisor dx2 = make_divisor(p.dx2);
     constexpr bool HEAT = (OP == OP_RES_HEAT || OP == OP_JVP_HEAT || OP == OP_RHS_HEAT);
     constexpr bool FD = (OP == OP_JVP_BRATU_FD);
-    constexpr bool AUX = (OP == OP_JVP_BRATU || OP == OP_RES_HEAT);
-    constexpr int kU1 = OP == OP_JVP_BRATU_FD ? 2 : (RED == RED_DOT ? 3 : 4);
     const bool oscale_on = (OP == OP_JVP_BRATU || OP == OP_JVP_HEAT || FD) && p.out_scale != nullptr;
     const double oscale = oscale_on ? __ddiv_rn(1.0, *p.out_scale) : 1.0;
-    // raw value at index i incl. the boundary semantics (before the SCALE division): one load or a constant.
-    //   i < 0 / i >= n : the neighbour rank's end point, or y_0 = y_{N+1} = 0 (Bratu: bratu.jl:17)
-    //   heat, global end points: their bc! / periodic_bc! value (heat_1D.jl:34-42)
-    auto raw_value = [&](int64_t i) -> double {
-        if (i < 0) return p.lo != nullptr ? p.lo[0] : 0.0;
-        if (i >= n) return p.hi != nullptr ? p.hi[0] : 0.0;
-        if (HEAT && ((i == 0 && p.seg_first) || (i == n - 1 && p.seg_last))) return heat1d_bc_value(p.in, i, n, p.bc);
-        return p.in[i];
-    };
     // fused finite-difference JVP: second window over u (p.aux, ghosts p.aux_lo / p.aux_hi); u + eps v is never stored
     auto uvalue = [&](int64_t i) -> double {
         if (i < 0) return p.aux_lo ? p.aux_lo[0] : 0.0;
@@ -375,80 +402,77 @@ __global__ void __launch_bounds__(kT1, 2) k_stencil1d(const StencilArgs p) {
         return p.aux[i];
     };
 
-    struct Chunk {
-        int64_t x0;
-        bool active;
-        double cur[VEC], aux[AUX ? VEC : 1], ucur[FD ? VEC : 1], dw[RED == RED_DOT ? VEC : 1];
-        double el, er, uel, uer;  // neighbours outside the warp (edge lanes only), raw
-    };
-    // phase 1: every global load of the chunk, nothing consumed
-    auto load_chunk = [&](Chunk& c, int64_t x0) {
-        c.x0 = x0;
-        c.active = x0 < n;
-        c.el = c.er = c.uel = c.uer = 0.0;
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) c.cur[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < (FD ? VEC : 1); ++i) c.ucur[i] = 0.0;
-        if (!c.active) return;
-        ldv<VEC>(p.in + x0, c.cur);
-        if (AUX) ldv_s<VEC>(p.aux + x0, reinterpret_cast<double(&)[VEC]>(c.aux));
-        if (FD) ldv<VEC>(p.aux + x0, reinterpret_cast<double(&)[VEC]>(c.ucur));
-        if (RED == RED_DOT) ldv_s<VEC>(p.dot_with + x0, reinterpret_cast<double(&)[VEC]>(c.dw));
-        const bool last = lane == 31 || x0 + VEC >= n;
-        if (lane == 0) c.el = raw_value(x0 - 1);
-        if (last) c.er = raw_value(x0 + VEC);
-        if (FD) {
-            if (lane == 0) c.uel = uvalue(x0 - 1);
-            if (last) c.uer = uvalue(x0 + VEC);
+    auto value = [&](int64_t i) -> double {  // scalar access incl. boundary semantics
+        double v;
+        if (i < 0) {  // left of this segment: neighbour rank's last point, or y_0 = 0 (Bratu: bratu.jl:17)
+            if (p.lo == nullptr) return 0.0;
+            v = p.lo[0];
+        } else if (i >= n) {
+            if (p.hi == nullptr) return 0.0;
+            v = p.hi[0];
+        } else if (HEAT && ((i == 0 && p.seg_first) || (i == n - 1 && p.seg_last))) {
+            v = heat1d_bc_value(p.in, i, n, p.bc);  // bc! / periodic_bc! act on the global end points only
+        } else {
+            v = p.in[i];
         }
-        if (HEAT) {  // the global end points take their BC value (raw; scaled with the rest below)
-            if (x0 == 0 && p.seg_first) c.cur[0] = raw_value(0);
-            if (x0 + VEC == n && p.seg_last) c.cur[VEC - 1] = raw_value(n - 1);
-        }
+        if (SCALE) v = div_by(v, denom);
+        return v;
     };
-    double acc = 0.0;
-    // phase 2: neighbours (shuffles; warp-edge lanes use their prefetched scalar), arithmetic, stores
-    auto finish_chunk = [&](Chunk& c) {
-        const int64_t x0 = c.x0;
+
+    double cur[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) cur[i] = 0.0;
+    if (active) {
+        ldv<VEC>(p.in + x0, cur);
         if (SCALE) {
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) c.cur[i] = div_by(c.cur[i], denom);
-            c.el = div_by(c.el, denom);
-            c.er = div_by(c.er, denom);
+            for (int i = 0; i < VEC; ++i) cur[i] = div_by(cur[i], denom);
         }
-        double left = __shfl_up_sync(0xffffffffu, c.cur[VEC - 1], 1);
-        double right = __shfl_down_sync(0xffffffffu, c.cur[0], 1);
-        double uleft = 0.0, uright = 0.0;
+        if (HEAT) {  // the global end points take their BC value
+            if (x0 == 0 && p.seg_first) cur[0] = value(0);
+            if (x0 + VEC == n && p.seg_last) cur[VEC - 1] = value(n - 1);
+        }
+    }
+    double left = __shfl_up_sync(0xffffffffu, cur[VEC - 1], 1);
+    double right = __shfl_down_sync(0xffffffffu, cur[0], 1);
+    double ucur[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) ucur[i] = 0.0;
+    if (FD && active) ldv<VEC>(p.aux + x0, ucur);
+    double uleft = 0.0, uright = 0.0;
+    if (FD) {
+        uleft = __shfl_up_sync(0xffffffffu, ucur[VEC - 1], 1);
+        uright = __shfl_down_sync(0xffffffffu, ucur[0], 1);
+    }
+    double acc = 0.0;
+    if (active) {
+        if (lane == 0) left = value(x0 - 1);
+        if (lane == 31 || x0 + VEC >= n) right = value(x0 + VEC);
         if (FD) {
-            uleft = __shfl_up_sync(0xffffffffu, c.ucur[FD ? VEC - 1 : 0], 1);
-            uright = __shfl_down_sync(0xffffffffu, c.ucur[0], 1);
+            if (lane == 0) uleft = uvalue(x0 - 1);
+            if (lane == 31 || x0 + VEC >= n) uright = uvalue(x0 + VEC);
         }
-        if (!c.active) return;
-        const bool last = lane == 31 || x0 + VEC >= n;
-        if (lane == 0) { left = c.el; uleft = c.uel; }
-        if (last) { right = c.er; uright = c.uer; }
-        double o[VEC], cf[VEC];
+        double aux[VEC], o[VEC], cf[VEC];
+        if (OP == OP_JVP_BRATU || OP == OP_RES_HEAT) ldv_s<VEC>(p.aux + x0, aux);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const double w = (i == 0) ? left : c.cur[i > 0 ? i - 1 : 0];
-            const double e = (i == VEC - 1) ? right : c.cur[(i + 1) % VEC];
-            const double cc = c.cur[i];
+            const double w = (i == 0) ? left : cur[i - 1];
+            const double e = (i == VEC - 1) ? right : cur[(i + 1) % VEC];
+            const double c = cur[i];
             if (OP == OP_RES_BRATU) {
-                cf[i] = __dmul_rn(p.lambda, exp(cc));
-                o[i] = __dadd_rn(second_diff(e, cc, w, dx2), cf[i]);
+                cf[i] = __dmul_rn(p.lambda, exp(c));
+                o[i] = __dadd_rn(second_diff(e, c, w, dx2), cf[i]);
             } else if (OP == OP_JVP_BRATU) {
-                const double a_ = c.aux[AUX ? i : 0];
-                const double k = p.coef_from_u ? __dmul_rn(p.lambda, exp(a_)) : a_;
-                o[i] = __dadd_rn(second_diff(e, cc, w, dx2), __dmul_rn(k, cc));
+                const double k = p.coef_from_u ? __dmul_rn(p.lambda, exp(aux[i])) : aux[i];
+                o[i] = __dadd_rn(second_diff(e, c, w, dx2), __dmul_rn(k, c));
             } else if (FD) {
                 // J v ~ (F(u + eps v) - F(u)) / eps, both residuals of bratu! (bratu.jl:14-24) evaluated at this point
                 const double eps = p.fd_eps;
-                const double uc = c.ucur[FD ? i : 0];
-                const double uw = (i == 0) ? uleft : c.ucur[(FD && i > 0) ? i - 1 : 0];
-                const double ue = (i == VEC - 1) ? uright : c.ucur[FD ? (i + 1) % VEC : 0];
+                const double uc = ucur[i];
+                const double uw = (i == 0) ? uleft : ucur[i > 0 ? i - 1 : 0];
+                const double ue = (i == VEC - 1) ? uright : ucur[(i + 1) % VEC];
                 const double f0 = __dadd_rn(second_diff(ue, uc, uw, dx2), __dmul_rn(p.lambda, exp(uc)));
-                const double pc = fma(eps, cc, uc), pw = fma(eps, w, uw), pe = fma(eps, e, ue);
+                const double pc = fma(eps, c, uc), pw = fma(eps, w, uw), pe = fma(eps, e, ue);
                 const double f1 = __dadd_rn(second_diff(pe, pc, pw, dx2), __dmul_rn(p.lambda, exp(pc)));
                 o[i] = __ddiv_rn(__dsub_rn(f1, f0), eps);
             } else {
@@ -456,10 +480,10 @@ __global__ void __launch_bounds__(kT1, 2) k_stencil1d(const StencilArgs p) {
                 const int64_t gi = x0 + i;
                 const bool bnd = (gi == 0 && p.seg_first) || (gi == n - 1 && p.seg_last);
                 const double du =
-                    bnd ? 0.0 : div_by(__dmul_rn(p.a, __dadd_rn(__dsub_rn(e, __dmul_rn(2.0, cc)), w)), dx2);
-                if (OP == OP_RES_HEAT) o[i] = __dsub_rn(__dadd_rn(c.aux[AUX ? i : 0], __dmul_rn(p.dt, du)), cc);
+                    bnd ? 0.0 : div_by(__dmul_rn(p.a, __dadd_rn(__dsub_rn(e, __dmul_rn(2.0, c)), w)), dx2);
+                if (OP == OP_RES_HEAT) o[i] = __dsub_rn(__dadd_rn(aux[i], __dmul_rn(p.dt, du)), c);
                 else if (OP == OP_RHS_HEAT) o[i] = du;
-                else o[i] = __dsub_rn(__dmul_rn(p.c1, du), cc);
+                else o[i] = __dsub_rn(__dmul_rn(p.c1, du), c);
             }
         }
         if (oscale_on) {
@@ -469,32 +493,21 @@ __global__ void __launch_bounds__(kT1, 2) k_stencil1d(const StencilArgs p) {
         stv<VEC>(p.out + x0, o);
         if (OP == OP_RES_BRATU && p.aux_out != nullptr) stv<VEC>(p.aux_out + x0, cf);
         if (SCALE) {
-            stv<VEC>(p.in_write + x0, c.cur);
+            stv<VEC>(p.in_write + x0, cur);
         } else if (HEAT && p.in_write != nullptr) {
             // the reference's bc!(u) mutates the state / tangent seed in place (heat_1D.jl:16,34-42)
-            if (x0 == 0 && p.seg_first) p.in_write[0] = c.cur[0];
-            if (x0 + VEC == n && p.seg_last) p.in_write[n - 1] = c.cur[VEC - 1];
+            if (x0 == 0 && p.seg_first) p.in_write[0] = cur[0];
+            if (x0 + VEC == n && p.seg_last) p.in_write[n - 1] = cur[VEC - 1];
         }
         if (RED == RED_SUMSQ) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc = fma(o[i], o[i], acc);
         } else if (RED == RED_DOT) {
+            double dw[VEC];
+            ldv_s<VEC>(p.dot_with + x0, dw);
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc = fma(c.dw[RED == RED_DOT ? i : 0], o[i], acc);
+            for (int i = 0; i < VEC; ++i) acc = fma(dw[i], o[i], acc);
         }
-    };
-
-    const int64_t nchunks = (n + VEC - 1) / VEC;
-    const int64_t nth = (int64_t)gridDim.x * kT1;
-    // warp-uniform trip count (the shuffles need whole warps): a chunk slot is live while its warp's first lane has work
-    for (int64_t ch = (int64_t)blockIdx.x * kT1 + threadIdx.x; ch - lane < nchunks; ch += kU1 * nth) {
-        Chunk c[kU1];
-#pragma unroll
-        for (int q = 0; q < kU1; ++q)
-            if ((ch + q * nth - lane) < nchunks) load_chunk(c[q], (ch + q * nth) * VEC);
-#pragma unroll
-        for (int q = 0; q < kU1; ++q)
-            if ((ch + q * nth - lane) < nchunks) finish_chunk(c[q]);
     }
     if (RED != RED_NONE) {
         const double s = block_sum(acc, sh);
@@ -539,86 +552,58 @@ AK_DEV void dg_local(const double (&D)[4][4], double jac, const double (&u)[4], 
     }
 }
 
-// One thread per element and trip; one wave of resident blocks (2 x 256 threads per SM) walks the mesh with kUdg
-// elements in flight per thread: all global loads of the trip (the element itself, u_n, and for the warp-edge lanes the
-// neighbour element / node a shuffle cannot provide) are issued before any is consumed (kUdg = 2-4).
-
 template <bool RESIDUAL, bool SCALE, int RED>
-__global__ void __launch_bounds__(kT1, 2) k_dg(const DgArgs p) {
+__global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
     __shared__ double sh[32];
     if (p.stop != nullptr && *p.stop != 0) return;
     const int lane = threadIdx.x & 31;
     const int64_t ne = p.ne;
+    const int64_t e = (int64_t)blockIdx.x * kT1 + threadIdx.x;
+    const bool active = e < ne;
     const Divisor denom = make_divisor(SCALE ? *p.denom : 1.0);
     const Divisor mw = make_divisor(p.mw);
-    const bool oscale_on = !RESIDUAL && !p.rhs_only && p.out_scale != nullptr;
-    const double oscale = oscale_on ? __ddiv_rn(1.0, *p.out_scale) : 1.0;
-    constexpr int kUdg = RESIDUAL ? 3 : (RED == RED_DOT ? 2 : 4);  // what the register file holds without spilling
 
-    struct Elem {
-        int64_t e;
-        bool active;
-        double raw[4], un[RESIDUAL ? 4 : 1], dw[RED == RED_DOT ? 4 : 1];
-        double prev[4];  // lane 0: the element to the left (raw)
-        double next0;    // last lane: first node of the element to the right (raw)
-    };
-    auto load = [&](Elem& c, int64_t e) {
-        c.e = e;
-        c.active = e < ne;
-        c.next0 = 0.0;
+    auto load_elem = [&](int64_t el, double (&r)[4]) {
+        ldv<4>((el < 0) ? p.lo : p.in + 4 * el, r);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c.raw[i] = c.prev[i] = 0.0;
-        if (!c.active) return;
-        ldv<4>(p.in + 4 * e, c.raw);
-        if (RESIDUAL && !p.rhs_only) ldv_s<4>(p.un + 4 * e, reinterpret_cast<double(&)[4]>(c.un));
-        if (RED == RED_DOT) ldv_s<4>(p.dot_with + 4 * e, reinterpret_cast<double(&)[4]>(c.dw));
-        if (lane == 31 || e + 1 >= ne) {
-            const int64_t en = (e + 1 == ne) ? 0 : e + 1;
-            c.next0 = (e + 1 == ne && p.hi != nullptr) ? p.hi[0] : p.in[4 * en];
-        }
-        if (lane == 0) {
-            const int64_t ep = (e == 0) ? ((p.lo != nullptr) ? -1 : ne - 1) : e - 1;
-            ldv<4>((ep < 0) ? p.lo : p.in + 4 * ep, c.prev);
+        for (int i = 0; i < 4; ++i) {
+            if (SCALE) r[i] = div_by(r[i], denom);
+            if (!RESIDUAL) r[i] = __dmul_rn(p.c0, r[i]);
         }
     };
+    double u[4] = {0, 0, 0, 0}, raw[4] = {0, 0, 0, 0};
+    if (active) {
+        ldv<4>(p.in + 4 * e, raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (SCALE) raw[i] = div_by(raw[i], denom);
+            u[i] = RESIDUAL ? raw[i] : __dmul_rn(p.c0, raw[i]);
+        }
+    }
+    // D1p: needs first node of the element to the right
+    double u_next0 = __shfl_down_sync(0xffffffffu, u[0], 1);
+    if (active && (lane == 31 || e + 1 >= ne)) {
+        const int64_t en = (e + 1 == ne) ? 0 : e + 1;
+        double t = (e + 1 == ne && p.hi != nullptr) ? p.hi[0] : p.in[4 * en];
+        if (SCALE) t = div_by(t, denom);
+        u_next0 = RESIDUAL ? t : __dmul_rn(p.c0, t);
+    }
+    double t1[4] = {0, 0, 0, 0};
+    if (active) {
+        dg_local(p.D, p.jac, u, t1);
+        t1[3] = __dadd_rn(t1[3], div_by(__dsub_rn(u_next0, u[3]), mw));
+    }
+    // D1m: needs last node of (D1p u) of the element to the left
+    double t_prev3 = __shfl_up_sync(0xffffffffu, t1[3], 1);
+    if (active && lane == 0) {
+        const int64_t ep = (e == 0) ? ((p.lo != nullptr) ? -1 : ne - 1) : e - 1;
+        double up[4], tp[4];
+        load_elem(ep, up);
+        dg_local(p.D, p.jac, up, tp);
+        t_prev3 = __dadd_rn(tp[3], div_by(__dsub_rn(u[0], up[3]), mw));
+    }
     double acc = 0.0;
-    auto finish = [&](Elem& c) {
-        const int64_t e = c.e;
-        const bool active = c.active;
-        double u[4] = {0, 0, 0, 0};
-        if (active) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (SCALE) c.raw[i] = div_by(c.raw[i], denom);
-                u[i] = RESIDUAL ? c.raw[i] : __dmul_rn(p.c0, c.raw[i]);
-            }
-        }
-        // D1p: needs first node of the element to the right
-        double u_next0 = __shfl_down_sync(0xffffffffu, u[0], 1);
-        if (active && (lane == 31 || e + 1 >= ne)) {
-            double t = c.next0;
-            if (SCALE) t = div_by(t, denom);
-            u_next0 = RESIDUAL ? t : __dmul_rn(p.c0, t);
-        }
-        double t1[4] = {0, 0, 0, 0};
-        if (active) {
-            dg_local(p.D, p.jac, u, t1);
-            t1[3] = __dadd_rn(t1[3], div_by(__dsub_rn(u_next0, u[3]), mw));
-        }
-        // D1m: needs last node of (D1p u) of the element to the left
-        double t_prev3 = __shfl_up_sync(0xffffffffu, t1[3], 1);
-        if (active && lane == 0) {
-            double up[4], tp[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                up[i] = c.prev[i];
-                if (SCALE) up[i] = div_by(up[i], denom);
-                if (!RESIDUAL) up[i] = __dmul_rn(p.c0, up[i]);
-            }
-            dg_local(p.D, p.jac, up, tp);
-            t_prev3 = __dadd_rn(tp[3], div_by(__dsub_rn(u[0], up[3]), mw));
-        }
-        if (!active) return;
+    if (active) {
         double du[4], o[4];
         dg_local(p.D, p.jac, t1, du);
         du[0] = __dadd_rn(du[0], div_by(__dsub_rn(t1[0], t_prev3), mw));
@@ -626,35 +611,30 @@ __global__ void __launch_bounds__(kT1, 2) k_dg(const DgArgs p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] = du[i];
         } else if (RESIDUAL) {
+            double un[4];
+            ldv_s<4>(p.un + 4 * e, un);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dadd_rn(c.un[RESIDUAL ? i : 0], __dmul_rn(p.dt, du[i])), c.raw[i]);
+            for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dadd_rn(un[i], __dmul_rn(p.dt, du[i])), raw[i]);
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dmul_rn(p.c1, du[i]), c.raw[i]);
-            if (oscale_on) {
+            for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dmul_rn(p.c1, du[i]), raw[i]);
+            if (p.out_scale != nullptr) {
+                const double oscale = __ddiv_rn(1.0, *p.out_scale);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) o[i] = __dmul_rn(o[i], oscale);
             }
         }
         stv<4>(p.out + 4 * e, o);
-        if (SCALE) stv<4>(p.in_write + 4 * e, c.raw);
+        if (SCALE) stv<4>(p.in_write + 4 * e, raw);
         if (RED == RED_SUMSQ) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc = fma(o[i], o[i], acc);
         } else if (RED == RED_DOT) {
+            double dw[4];
+            ldv_s<4>(p.dot_with + 4 * e, dw);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc = fma(c.dw[RED == RED_DOT ? i : 0], o[i], acc);
+            for (int i = 0; i < 4; ++i) acc = fma(dw[i], o[i], acc);
         }
-    };
-    const int64_t nth = (int64_t)gridDim.x * kT1;
-    for (int64_t e = (int64_t)blockIdx.x * kT1 + threadIdx.x; e - lane < ne; e += kUdg * nth) {
-        Elem c[kUdg];
-#pragma unroll
-        for (int q = 0; q < kUdg; ++q)
-            if ((e + q * nth - lane) < ne) load(c[q], e + q * nth);
-#pragma unroll
-        for (int q = 0; q < kUdg; ++q)
-            if ((e + q * nth - lane) < ne) finish(c[q]);
     }
     if (RED != RED_NONE) {
         const double s = block_sum(acc, sh);
@@ -883,7 +863,9 @@ static void launch2d_v(Ctx* ctx, const StencilArgs& a, bool scale, int red, dim3
     } else {
         if (red == RED_DOT) AK_L2D(false, RED_DOT);
         else if (red == RED_SUMSQ) AK_L2D(false, RED_SUMSQ);
-        else AK_L2D(false, RED_NONE);
+        else if (red == RED_PROJ) {
+            if constexpr (OP == OP_JVP_BRATU || OP == OP_JVP_HEAT) AK_L2D(false, RED_PROJ);
+        } else AK_L2D(false, RED_NONE);
     }
 #undef AK_L2D
 }
@@ -896,6 +878,8 @@ static int launch2d(Ctx* ctx, StencilArgs& a, bool scale, int red) {
         if (a.nx % v) return false;
         for (const void* q : ptrs)
             if (!al(q, 8 * v)) return false;
+        for (int b = 0; b < a.nproj; ++b)
+            if (!al(a.proj[b], 8 * v)) return false;
         return true;
     };
     if (ok(4)) vec = 4;
@@ -910,8 +894,9 @@ static int launch2d(Ctx* ctx, StencilArgs& a, bool scale, int red) {
     }
     a.ry = ry;
     int64_t gy = (a.ny + ry - 1) / ry;
-    if (gx * gy > kMaxPartials && red != RED_NONE) {  // keep the partials buffer in bounds
-        ry = (int)((a.ny * gx + kMaxPartials - 1) / kMaxPartials);
+    const int64_t max_blocks = red == RED_PROJ ? kMaxPartials / kBlkMax : kMaxPartials;  // partials per block: 8 or 1
+    if (gx * gy > max_blocks && red != RED_NONE) {  // keep the partials buffer in bounds
+        ry = (int)((a.ny * gx + max_blocks - 1) / max_blocks);
         a.ry = ry;
         gy = (a.ny + ry - 1) / ry;
     }
@@ -950,11 +935,11 @@ static int launch1d(Ctx* ctx, StencilArgs& a, bool scale, int red) {
     };
     if (ok(4)) vec = 4;
     else if (ok(2)) vec = 2;
-    // one wave of resident blocks (2 x 256 threads per SM: the register budget of the launch bounds), grid-stride
     int64_t grid = (a.nx + (int64_t)kT1 * vec - 1) / ((int64_t)kT1 * vec);
-    const int64_t cap = (int64_t)ctx->num_sms * 2;
-    if (grid > cap) grid = cap;
-    if (grid < 1) grid = 1;
+    if (grid > kMaxPartials && red != RED_NONE) {
+        set_error("1-D stencil with fused reduction: n too large for the partials buffer");
+        return AK_ERR_UNSUPPORTED;
+    }
     if (vec == 4) launch1d_v<OP, 4>(ctx, a, scale, red, (int)grid);
     else if (vec == 2) launch1d_v<OP, 2>(ctx, a, scale, red, (int)grid);
     else launch1d_v<OP, 1>(ctx, a, scale, red, (int)grid);
@@ -975,10 +960,11 @@ static void dg_constants(DgArgs& d, double h) {
 }
 
 static int launch_dg(Ctx* ctx, DgArgs& d, bool residual, bool scale, int red) {
-    int64_t grid = (d.ne + kT1 - 1) / kT1;  // one wave of resident blocks (2 per SM), grid-stride over the elements
-    const int64_t cap = (int64_t)ctx->num_sms * 2;
-    if (grid > cap) grid = cap;
-    if (grid < 1) grid = 1;
+    const int64_t grid = (d.ne + kT1 - 1) / kT1;
+    if (grid > kMaxPartials && red != RED_NONE) {
+        set_error("DG stencil with fused reduction: n too large for the partials buffer");
+        return AK_ERR_UNSUPPORTED;
+    }
 #define AK_LDG(RS, S, R) k_dg<RS, S, R><<<(int)grid, kT1, 0, ctx->stream>>>(d)
     if (residual) {
         if (red == RED_SUMSQ) AK_LDG(true, false, RED_SUMSQ);
@@ -1317,7 +1303,10 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     const bool raw = f->raw && f->scale_src != nullptr;
     const bool native = !(p->kind == AK_SIMPLE2);
     const bool scale = f->scale_src != nullptr && !(raw && native);
-    const int red = f->dot_with ? RED_DOT : (f->sumsq_dev ? RED_SUMSQ : RED_NONE);
+    const bool is2d = (p->kind == AK_BRATU2D || p->kind == AK_HEAT2D);
+    AK_REQUIRE(f->nproj == 0 || (is2d && p->jvp_mode == AK_JVP_ANALYTIC && f->nproj <= kBlkMax && !f->dot_with && !f->sumsq_dev),
+               "launch_jvp: the projection fusion belongs to the 2-D analytic tangents");
+    const int red = f->nproj > 0 ? RED_PROJ : (f->dot_with ? RED_DOT : (f->sumsq_dev ? RED_SUMSQ : RED_NONE));
     double* red_out = f->dot_with ? f->dot_dev : f->sumsq_dev;
     if (raw && native) v = const_cast<double*>(f->scale_src);
     if (p->kind == AK_SIMPLE2) {
@@ -1353,6 +1342,17 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     a.red_out = red_out;
     a.bminus = f->rhs_minus;
     a.stop = f->stop_flag;
+    bool proj_p2p = false;
+    if (f->nproj > 0) {
+        a.nproj = f->nproj;
+        for (int b = 0; b < f->nproj; ++b) a.proj[b] = f->proj[b];
+        a.proj_out = f->proj_out;
+        proj_p2p = f->proj_comm != nullptr && ctx->p2p_on && ctx->nranks > 1;
+        if (proj_p2p) {
+            a.pd = ctx->p2p_dev();
+            a.seq_out = f->proj_comm->seq_out;
+        }
+    }
     int rc = AK_OK;
     switch (p->kind) {
         case AK_BRATU1D:
@@ -1401,7 +1401,11 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
         default: break;
     }
     AK_TRY(rc);
-    if (red) AK_TRY(allreduce_sum(ctx, red_out, 1));
+    if (red == RED_PROJ) {
+        if (!proj_p2p) AK_TRY(allreduce_sum(ctx, f->proj_out, f->nproj));
+    } else if (red) {
+        AK_TRY(allreduce_sum(ctx, red_out, 1));
+    }
     return AK_OK;
 }
 
