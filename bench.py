@@ -341,7 +341,8 @@ def cpu_baseline_leg(name, cfg):
 
 # ---------------------------------------------------------------------------------------------
 PROF_NAMES = ["mgs_axpy_dot", "mgs_axpy_norm", "mgs_axpy", "dot", "sumsq", "jvp", "residual", "elementwise",
-              "basis_combine", "scalar", "mgs_pair", "mgs_pair_edge"]
+              "basis_combine", "scalar", "mgs_pair", "mgs_pair_edge", "mgs_block_final"]
+NPROF = len(PROF_NAMES)
 
 
 def timed_run(W, steps, warmup, barrier, sampler=None):
@@ -365,7 +366,7 @@ def timed_run(W, steps, warmup, barrier, sampler=None):
     ms = ctx.timer_stop()
     barrier()
     launches = ctx.launch_count()
-    prof = {c: ctx.profile_read(c) for c in range(12)}
+    prof = {c: ctx.profile_read(c) for c in range(NPROF)}
     ctx.profile(False)
     if sampler:
         sampler.stop()
@@ -377,17 +378,60 @@ def kernel_table(W, prof, ms, peak):
     n = W.n
     fixed = {"jvp": W.cfg["jvp_bytes"] * n, "residual": W.cfg["res_bytes"] * n}
     out = {}
-    for c in range(12):
+    for c in range(NPROF):
         cnt, kms = prof[c]
         if not cnt:
             continue
         e = {"launches": cnt, "ms": round(kms, 3), "share_of_step_time": round(kms / ms, 4)}
         b = fixed.get(PROF_NAMES[c])  # (restart residuals b - J x read one more vector: counted at the plain JVP's bytes)
+        if PROF_NAMES[c] == "jvp" and W.cfg["kind"] in ("bratu2d", "heat2d") and W.fuse in ("pair", "block4", "block8"):
+            b = None  # the 2-D tangent launches also carry the first projection pass: bytes per launch vary with k
         if b:
             e["GBs"] = round(b / (kms / cnt * 1e-3) / 1e9, 1)
             e["frac_of_peak"] = round(e["GBs"] / peak, 4)
         out[PROF_NAMES[c]] = e
     return out
+
+
+def c1_small_regime(nk, ctx):
+    """BASELINE config 1 (examples/bratu.jl: 1-D Bratu, N = 10 000, the CPU-runnable case): CG iterations/s of one linear
+    solve of the first Newton step, GPU (one persistent block: the whole of cg! without a launch inside) against the CPU
+    oracle on the host cores.  80 KB per vector: a launch-latency regime, not a bandwidth one."""
+    import oracle as O
+    from newtonkrylov_jl_b200 import _abi as A
+
+    N, lam, its = 10_000, LAMBDA, 2000
+    dx = 1.0 / (N + 1)
+    x = np.linspace(dx, 1.0 - dx, N)
+    u0 = np.sin(np.pi * x)
+    u = nk.DeviceVector.from_numpy(u0, ctx)
+    res, coef = u.similar(), u.similar()
+    prob = nk.bratu_.problem(u, (dx, lam), coef=coef)
+    nk._lib.check(ctx.lib.ak_residual(ctx.h, C.byref(prob), C.c_void_p(u.ptr), C.c_void_p(res.ptr), None))
+    J = nk.JacobianOperator(nk.bratu_, res, u, (dx, lam), coef=coef)
+    ws = nk.krylov_workspace("cg", nk.KrylovConstructor(res))
+    b = res.copy()
+    best = None
+    for _ in range(4):
+        ctx.sync()
+        t0 = time.perf_counter()
+        nk.krylov_solve_(ws, J, b, rtol=1e-30, atol=0.0, itmax=its)
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    gpu_its = ws.stats.niter
+    O.build()
+    cores = O.use_all_cores()
+    po = O.make_problem(A.AK_BRATU1D, N, 1, dx=dx, lam=lam)
+    r0, _ = O.residual(po, u0)
+    t0 = time.perf_counter()
+    _, stc, _ = O.krylov_solve(po, u0, r0, algo=A.AK_ALGO_CG, rtol=1e-30, atol=0.0, itmax=its)
+    dtc = time.perf_counter() - t0
+    return {"workload": f"1D Bratu N={N} (examples/bratu.jl:40-46), algo=:cg, {its} iterations of one linear solve",
+            "gpu_cg_iters_per_sec": gpu_its / best, "gpu_iterations": gpu_its, "gpu_seconds": best,
+            "gpu_path": "k_cg_small_bratu1d: one persistent 1024-thread block, p and r in shared memory, no launch inside the solve",
+            "cpu_cg_iters_per_sec": stc["niter"] / dtc, "cpu_cores": cores, "cpu_kind": "port (oracle/nk_oracle.c)",
+            "wall_clock": "host perf_counter around the blocking solve call (one launch + one sync)"}
 
 
 def main():
@@ -524,10 +568,10 @@ def main():
         pass
     step_bytes = W.step_bytes()
     step_gbs = step_bytes * args.steps / (ms * 1e-3) / 1e9
-    gs_ms = sum(prof[c][1] for c in (0, 1, 2, 10, 11))
+    gs_ms = sum(prof[c][1] for c in (0, 1, 2, 10, 11, 12))
     family = {
         "gram_schmidt_passes (k_mgs_block / k_mgs_step, all instantiations)": round(gs_ms / ms, 4),
-        "jvp (k_stencil*/k_dg tangent)": round(prof[5][1] / ms, 4),
+        "jvp (k_stencil*/k_dg tangent; 2-D: with the first projection pass folded in)": round(prof[5][1] / ms, 4),
         "cycle_boundary (basis_combine + element-wise + norms)": round((prof[8][1] + prof[7][1] + prof[4][1] + prof[3][1]) / ms, 4),
         "residual": round(prof[6][1] / ms, 4),
         "scalar (Givens / back-substitution, one block)": round(prof[9][1] / ms, 4),
@@ -620,6 +664,8 @@ def main():
                 "kernels": kernel_table(Wo, oprof, oms, peak),
             }
             del Wo
+        if world == 1:
+            others["c1"] = c1_small_regime(nk, ctx)
 
     # ---- CPU baseline (rank 0): one restart cycle on all host cores, at every N -------------------------
     cpu = None

@@ -144,8 +144,8 @@ int ak_timer_stop(ak_ctx* ctx, double* ms_out);
  * sum of their device times.  Classes: 0 axpy+dot (fused MGS step, 32n bytes), 1 axpy+norm (24n),
  * 2 axpy (24n), 3 dot (16n), 4 sum of squares (8n), 5 JVP, 6 residual, 7 element-wise,
  * 8 basis combine, 9 one-thread scalar kernels, 10 full pass of the blocked Gram-Schmidt sweep (48n for
- * blocks of 2, 80n for blocks of 4), 11 first / ragged passes of the blocked sweep.  Enabling resets the
- * counters.                                                                                           */
+ * blocks of 2, 80n for blocks of 4, 144n for blocks of 8), 11 first / ragged passes of the blocked sweep, 12 final
+ * pass of the blocked sweep (last update + norm + new Gram entries).  Enabling resets the counters.    */
 int ak_profile_enable(ak_ctx* ctx, int on);
 int ak_profile_read(ak_ctx* ctx, int kernel_class, int64_t* count_out, double* ms_total_out);
 

@@ -83,7 +83,8 @@ enum ProfClass {
     PK_SCALAR = 9,         // one-thread Givens / control kernels
     PK_MGS_PAIR = 10,      // full blocked pass: w -= sum_b h_b v_b ; projections on the next block   8n(2+2R): 48n (R=2), 80n (R=4)
     PK_MGS_PAIR_EDGE = 11, // first / ragged passes of the blocked sweep
-    PK_NUM = 12
+    PK_MGS_BLOCK_FINAL = 12, // final pass of the blocked sweep: w -= sum_b c_b S_b ; ||w||^2 and the new Gram entries
+    PK_NUM = 13
 };
 
 struct Ctx {

@@ -363,7 +363,7 @@ int launch_mgs_block(Ctx* ctx, int64_t n, double* w, const double* const* va, in
     for (int b = 0; b < nax; ++b) { bp.va[b] = va[b]; vec = vec && aligned32(va[b]); }
     for (int b = 0; b < ny; ++b) { bp.ya[b] = ya[b]; vec = vec && aligned32(ya[b]); }
     const int cls = (nax >= 2 && nax == ny) ? PK_MGS_PAIR
-                                            : ((nax > 0 && want_sumsq) ? PK_MGS_AXPY_NRM : PK_MGS_PAIR_EDGE);
+                                            : ((nax > 0 && want_sumsq) ? PK_MGS_BLOCK_FINAL : PK_MGS_PAIR_EDGE);
     const bool p2p = pc != nullptr && ctx->p2p_on && ctx->nranks > 1;
     BlockP2P pp{};
     if (p2p) {

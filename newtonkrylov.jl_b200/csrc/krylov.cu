@@ -414,6 +414,123 @@ __global__ void __launch_bounds__(256) k_cg_update_xp(double* __restrict__ x, do
 }
 
 // ---------------------------------------------------------------------------------------
+// Small-problem regime (BASELINE config 1: 1-D Bratu, N = 10^4 — 80 KB per vector): the multi-kernel CG above is
+// launch-bound there (five launches of a few microseconds per iteration for ~100 ns of memory traffic).  This is the
+// whole of cg! as ONE persistent block: p and r live in shared memory (the three-point tangent reads p's neighbours
+// there), x and lambda e^u in registers, the two inner products are block reductions, and the block iterates until the
+// stopping test of cg! fires — no launch, no host round trip inside the solve.  Same operations per element as the
+// multi-kernel path (fma forms, exact division by dx^2); only the summation order of the inner products differs.
+// Point i = j * kSmallThreads + tid belongs to thread tid (bank-conflict-free, neighbours are neighbouring threads).
+// ---------------------------------------------------------------------------------------
+constexpr int kSmallThreads = 1024;
+constexpr int kSmallNPT = 10;                                   // points per thread (x and lambda e^u: 40 of the 64 registers)
+constexpr int64_t kSmallN = (int64_t)kSmallThreads * kSmallNPT; // 10240 unknowns: p, r = 2 x 80 KB of shared memory
+
+AK_DEV double block_sum_all(double v, double* sh, double* bcast) {  // sum over the block, result in every thread
+    const double r = block_sum(v, sh);
+    if (threadIdx.x == 0) *bcast = r;
+    __syncthreads();
+    return *bcast;
+}
+
+__global__ void __launch_bounds__(kSmallThreads, 1) k_cg_small_bratu1d(int n, double dx2v, double lambda,
+                                                                       const double* __restrict__ aux, int coef_from_u,
+                                                                       const double* __restrict__ b, double* __restrict__ x_out,
+                                                                       KrylovCtl* ctl, KrylovStatus* st, double* hist,
+                                                                       double atol, double rtol, long long itmax) {
+    extern __shared__ double smem[];
+    double* s_p = smem + 1;          // s_p[-1] and s_p[n] are the Dirichlet zeros (bratu.jl:17-18)
+    double* s_r = smem + (n + 2);
+    __shared__ double sh[32];
+    __shared__ double bc;
+    const int tid = threadIdx.x;
+    const Divisor dx2 = make_divisor(dx2v);
+    double x[kSmallNPT], kc[kSmallNPT];
+    if (tid == 0) { s_p[-1] = 0.0; s_p[n] = 0.0; }
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < kSmallNPT; ++j) {
+        const int i = j * kSmallThreads + tid;
+        x[j] = 0.0;
+        kc[j] = 0.0;
+        if (i < n) {
+            const double a = aux[i];
+            kc[j] = coef_from_u ? __dmul_rn(lambda, exp(a)) : a;
+            const double bi = b[i];
+            s_r[i] = bi;          // r = b (x0 = 0)
+            s_p[i] = bi;          // p = r
+            acc = fma(bi, bi, acc);
+        }
+    }
+    __syncthreads();
+    double gamma = block_sum_all(acc, sh, &bc);
+    double rNorm = sqrt(gamma);
+    const double beta0 = rNorm;
+    const double eps = atol + rtol * rNorm;
+    double pNorm2 = gamma;
+    int solved = (rNorm <= eps) || (gamma == 0.0);
+    int zerocurv = 0;
+    long long iter = 0;
+    if (hist != nullptr && tid == 0) hist[0] = rNorm;
+    const double epsm = 2.220446049250313e-16;
+    auto tangent = [&](int i, int j) -> double {  // (J p)_i, the 1-D Bratu tangent of stencil.cu
+        const double c = s_p[i];
+        return __dadd_rn(second_diff(s_p[i + 1], c, s_p[i - 1], dx2), __dmul_rn(kc[j], c));
+    };
+    while (!solved && iter < itmax) {
+        // pAp = <p, A p>
+        acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < kSmallNPT; ++j) {
+            const int i = j * kSmallThreads + tid;
+            if (i < n) acc = fma(s_p[i], tangent(i, j), acc);
+        }
+        const double pAp = block_sum_all(acc, sh, &bc);
+        if (pAp <= epsm * pNorm2 && fabs(pAp) <= epsm * pNorm2) { zerocurv = 1; break; }
+        const double alpha = gamma / pAp;
+        // x += alpha p ; r -= alpha A p ; gamma_next = <r, r>
+        acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < kSmallNPT; ++j) {
+            const int i = j * kSmallThreads + tid;
+            if (i < n) {
+                const double ap = tangent(i, j);
+                x[j] = fma(alpha, s_p[i], x[j]);
+                const double ri = fma(-alpha, ap, s_r[i]);
+                s_r[i] = ri;
+                acc = fma(ri, ri, acc);
+            }
+        }
+        const double gn = block_sum_all(acc, sh, &bc);  // (its barrier also orders the reads of p before the update below)
+        iter += 1;
+        rNorm = sqrt(gn);
+        if (hist != nullptr && tid == 0) hist[iter] = rNorm;
+        solved = (rNorm <= eps) || (rNorm + 1.0 <= 1.0);
+        if (solved) break;
+        const double beta = gn / gamma;
+        pNorm2 = gn + beta * beta * pNorm2;
+        gamma = gn;
+        // p = r + beta p
+#pragma unroll
+        for (int j = 0; j < kSmallNPT; ++j) {
+            const int i = j * kSmallThreads + tid;
+            if (i < n) s_p[i] = fma(beta, s_p[i], s_r[i]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < kSmallNPT; ++j) {
+        const int i = j * kSmallThreads + tid;
+        if (i < n) x_out[i] = x[j];
+    }
+    if (tid == 0) {
+        ctl->rNorm = rNorm; ctl->beta = beta0; ctl->solved = solved; ctl->zerocurv = zerocurv;
+        ctl->inconsistent = zerocurv; ctl->inner_iter = (int)iter; ctl->stop = 1;
+        st->rNorm = rNorm; st->beta = beta0; st->iter = (int)iter; st->stop = 1; st->solved = solved; st->zerocurv = zerocurv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // workspace memory
 // ---------------------------------------------------------------------------------------
 static int ws_alloc_vec(ak_krylov* ws, double** out) {
@@ -965,6 +1082,44 @@ static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, cons
     const int64_t itmax = o->itmax == 0 ? 2 * n : o->itmax;
     if (!ws->hcol) AK_TRY(ws_grow_scalars(ws, 4));
     if (want_hist) AK_TRY(ws_grow_hist(ws, 257));
+    // small-problem regime: the whole solve in one persistent block (AK_NO_SMALL_CG=1: developer switch for A/B runs)
+    static const bool no_small = getenv("AK_NO_SMALL_CG") != nullptr;
+    if (!no_small && prob->kind == AK_BRATU1D && prob->jvp_mode == AK_JVP_ANALYTIC && c->nranks == 1 && n <= kSmallN &&
+        itmax < (1ll << 31)) {
+        if (want_hist) AK_TRY(ws_grow_hist(ws, itmax + 2));
+        const size_t smem = sizeof(double) * (size_t)(2 * n + 2);
+        static bool attr_set = false;
+        if (!attr_set) {
+            AK_CUDA(cudaFuncSetAttribute(k_cg_small_bratu1d, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(double) * (2 * kSmallN + 2))));
+            attr_set = true;
+        }
+        { ProfScope prof(c, PK_SCALAR);
+        k_cg_small_bratu1d<<<1, kSmallThreads, smem, sm>>>((int)n, prob->dx * prob->dx, prob->lambda,
+                                                          prob->coef ? prob->coef : u, prob->coef ? 0 : 1, b, ws->x, ws->ctl,
+                                                          &ws->status[kStatusRing], want_hist ? ws->hist : nullptr, o->atol,
+                                                          o->rtol, (long long)itmax); }
+        c->launches++;
+        AK_CUDA(cudaGetLastError());
+        AK_CUDA(cudaStreamSynchronize(sm));
+        KrylovStatus hs0;
+        memcpy(&hs0, (const void*)&ws->status[kStatusRing], sizeof(hs0));
+        memset(st, 0, sizeof(*st));
+        st->niter = hs0.iter;
+        st->solved = hs0.solved;
+        st->inconsistent = hs0.zerocurv;
+        st->npass = 1;
+        st->rnorm = hs0.rNorm;
+        st->beta = hs0.beta;
+        if (hist_host && hist_cap > 0 && ws->hist) {
+            int64_t m = hs0.iter + 1 < hist_cap ? hs0.iter + 1 : hist_cap;
+            AK_CUDA(cudaMemcpy(hist_host, ws->hist, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost));
+        }
+        int flags0 = 0;
+        if (!hs0.solved) flags0 |= AK_FLAG_NOT_SOLVED;
+        if (hs0.zerocurv) flags0 |= AK_FLAG_INCONSISTENT;
+        return flags0;
+    }
     double *x = ws->x, *r = ws->r, *p = ws->p, *Ap = ws->Ap;
     const int* stop = &ws->ctl->stop;
     AK_TRY(launch_fill(c, n, x, 0.0));

@@ -151,8 +151,41 @@ def run_scheme_cases(ctx, rank, world, rng, tag):
             print(f"[multi-gpu x{world} {tag}] {name} midpoint/trapezoid: ok", flush=True)
 
 
+def run_linear_extras(ctx, rank, world, rng, tag):
+    """Collectives outside the plain blocked sweep, on slabs: CG (two all-reduces per iteration: NCCL, or the mailbox
+    all-reduce kernel with peer memory), and the blocked sweeps with re-orthogonalisation + restart (memory = 5)."""
+    d = P.bratu2d(48, 40, lam=1.0)
+    gy0, ny = nk.dist.slab_partition(d["ny"], world, rank)
+    sl = slice(gy0, gy0 + ny)
+    po = P.oracle_problem(O, d)
+    b0 = rng.standard_normal(d["u0"].shape)
+    p = (d["dx"], d["dy"], d["lam"], d["ny"], gy0)
+
+    def solve(algo, memory=20, **kw):
+        u = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
+        res = u.zero()
+        ws = nk.krylov_workspace(algo, nk.KrylovConstructor(res), memory=memory)
+        nk.krylov_solve_(ws, nk.JacobianOperator(nk.bratu2d_, res, u, p), nk.DeviceVector.from_numpy(b0[sl], ctx),
+                         history=True, **kw)
+        return ws.x.numpy(), ws.stats
+
+    xr, sr, hr = O.krylov_solve(po, d["u0"], b0, algo=A.AK_ALGO_CG, rtol=1e-8, hist_cap=100000)
+    x, st = solve("cg", rtol=1e-8)
+    assert (st.niter, st.solved) == (sr["niter"], sr["solved"]), ("cg", st.niter, sr)
+    assert np.max(np.abs(np.array(st.residuals) - hr)) <= 1e-9 * hr[0] and rel(x, xr[sl]) < 1e-8, "cg"
+    for fuse in ("mgs", "pair", "block8"):
+        kw = dict(rtol=1e-9, restart=True, reorthogonalization=True, itmax=33)
+        xr, sr, hr = O.krylov_solve(po, d["u0"], b0, memory=5, hist_cap=1000, **kw)
+        x, st = solve("gmres", memory=5, fuse=fuse, **kw)
+        assert (st.niter, st.solved, st.npass) == (sr["niter"], sr["solved"], sr["npass"]), (fuse, st.niter, sr)
+        assert np.max(np.abs(np.array(st.residuals) - hr)) <= 1e-9 * hr[0] and rel(x, xr[sl]) < 1e-8, fuse
+    if rank == 0:
+        print(f"[multi-gpu x{world} {tag}] cg + reorthogonalised blocked gmres: ok", flush=True)
+
+
 def run_cases(ctx, rank, world, rng, tag):
     run_1d_cases(ctx, rank, world, rng, tag)
+    run_linear_extras(ctx, rank, world, rng, tag)
     if tag == "nccl":
         run_scheme_cases(ctx, rank, world, rng, tag)
     for name, d, bc in [("bratu2d", P.generic(P.bratu2d(48, 40)), nk.bc_zero_),

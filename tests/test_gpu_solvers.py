@@ -76,7 +76,7 @@ def test_gmres_options(nk, ctx, oracle, opts, fuse):
     b0 = RNG.standard_normal(d["u0"].shape)
     ctx.profile(True)
     x, st = device_krylov(nk, ctx, d, b0, memory=5, rtol=1e-9, fuse=fuse, **opts)
-    blocked_launches = ctx.profile_read(10)[0] + ctx.profile_read(11)[0]
+    blocked_launches = sum(ctx.profile_read(cls)[0] for cls in (10, 11, 12))  # full / ragged / final blocked passes
     ctx.profile(False)
     # the blocked sweeps are really what ran (no silent fall-back to the step-wise kernels with reorthogonalization)
     assert (blocked_launches > 0) == (fuse in ("pair", "block4", "block8")), (fuse, blocked_launches)
@@ -134,16 +134,27 @@ def test_gmres_zero_rhs_and_basis_growth(nk, ctx, oracle):
     assert rel(x, xr) < 1e-8
 
 
-@pytest.mark.parametrize("name,make", [("bratu1d", lambda: P.bratu1d(300, lam=1.0)), ("bratu2d", lambda: P.bratu2d(24, lam=1.0))],
-                         ids=["bratu1d", "bratu2d"])
+@pytest.mark.parametrize("name,make", [("bratu1d", lambda: P.bratu1d(300, lam=1.0)), ("bratu2d", lambda: P.bratu2d(24, lam=1.0)),
+                                       ("bratu1d_10000", lambda: P.bratu1d(10000, lam=1.0)),
+                                       ("bratu1d_12000", lambda: P.bratu1d(12000, lam=1.0))],
+                         ids=["bratu1d", "bratu2d", "bratu1d_10000_one_block", "bratu1d_12000_multi_kernel"])
 def test_cg_matches_oracle(nk, ctx, oracle, name, make):
     """algo = :cg (every solve in examples/bratu.jl:59-108).  J is symmetric negative definite
-    for small lambda; CG is applied to it exactly as the reference does."""
+    for small lambda; CG is applied to it exactly as the reference does.  1-D Bratu up to 10 240 unknowns runs as one
+    persistent block (k_cg_small_bratu1d), anything larger through the multi-kernel path: both against the oracle."""
     d = make()
     b0 = RNG.standard_normal(d["u0"].shape)
-    x, st = device_krylov(nk, ctx, d, b0, algo="cg", rtol=1e-8)
+    kw = dict(rtol=1e-8) if d["nx"] < 5000 else dict(rtol=1e-30, atol=0.0, itmax=300)  # large N: a fixed iteration count
+    launches0 = ctx.launch_count()
+    x, st = device_krylov(nk, ctx, d, b0, algo="cg", **kw)
+    launches = ctx.launch_count() - launches0
+    one_block = d["kind"] == A.AK_BRATU1D and d["nx"] <= 10240
+    assert (launches < 20) == one_block, (name, launches)  # the small regime really runs without launches inside the solve
     po = P.oracle_problem(oracle, d)
-    xr, sr, hr = oracle.krylov_solve(po, d["u0"], b0, algo=A.AK_ALGO_CG, rtol=1e-8, hist_cap=100000)
+    xr, sr, hr = oracle.krylov_solve(po, d["u0"], b0, algo=A.AK_ALGO_CG, hist_cap=100000, **kw)
+    ledger.record("cg_vs_oracle", name, niter_gpu=st.niter, niter_oracle=sr["niter"], x_rel_dev=rel(x, xr),
+                  max_hist_dev_rel_beta=float(np.max(np.abs(np.array(st.residuals) - hr)) / hr[0]) if len(st.residuals) == len(hr) else None,
+                  kernel_launches=launches, bar="x 1e-8, history 1e-9 * beta")
     assert (st.niter, st.solved) == (sr["niter"], sr["solved"])
     assert rel(x, xr) < 1e-8
     h = np.array(st.residuals)
