@@ -91,6 +91,11 @@ struct Ctx {
     int device = 0;
     int num_sms = kNumSMsDefault;
     cudaStream_t stream = nullptr;
+    // the library's own stream-ordered memory pool (never trimmed): a Krylov workspace (22+ vectors of n doubles) is
+    // re-created by every newton_krylov! call like in the reference (src/Ariadne.jl:317-318) but costs no
+    // cudaMalloc/cudaFree after the first.  Private, so that the release threshold of the process-wide default pool
+    // (shared with torch / CUDA.jl in the same process) is left alone.
+    cudaMemPool_t pool = nullptr;
     // grid-wide reduction scratch (kernels on one stream never overlap)
     double* partials = nullptr;     // kMaxPartials doubles
     unsigned int* ticket = nullptr; // last-block-done counter, self-resetting
@@ -127,6 +132,23 @@ struct Ctx {
     double* p2p_ghost_local(int parity, int hi) const;
     double* p2p_ghost_of(int peer, int parity, int hi) const;
 };
+
+// stream-ordered allocation from the context's private pool (freed with cudaFreeAsync on the context's stream)
+inline cudaError_t pool_alloc(Ctx* c, void** out, size_t bytes) {
+    return cudaMallocFromPoolAsync(out, bytes, c->pool, c->stream);
+}
+// make the context's device current for the calling thread (a process may hold contexts on several devices)
+inline cudaError_t bind_device(const Ctx* c) {
+    int cur = -1;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return e;
+    return cur == c->device ? cudaSuccess : cudaSetDevice(c->device);
+}
+#define AK_ENTER(ctxptr)                                           \
+    do {                                                           \
+        AK_REQUIRE((ctxptr) != nullptr, "NULL context");           \
+        AK_CUDA(ak::bind_device(&(ctxptr)->c));                    \
+    } while (0)
 
 // RAII: brackets one kernel launch with events when the profiler is on (context.cu)
 struct ProfScope {

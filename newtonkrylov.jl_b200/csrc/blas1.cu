@@ -568,11 +568,13 @@ static int scalar_to_host(Ctx* c, const double* dev, double* out_host) {
 }
 
 AK_API int ak_dot(ak_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && out_host && n >= 0, "ak_dot: bad argument");
     AK_TRY(launch_dot(&ctx->c, n, x, y, ctx->c.dscal));
     return scalar_to_host(&ctx->c, ctx->c.dscal, out_host);
 }
 AK_API int ak_nrm2(ak_ctx* ctx, int64_t n, const double* x, double* out_host) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && out_host && n >= 0, "ak_nrm2: bad argument");
     AK_TRY(launch_sumsq(&ctx->c, n, x, ctx->c.dscal));
     double ss = 0.0;
@@ -581,30 +583,37 @@ AK_API int ak_nrm2(ak_ctx* ctx, int64_t n, const double* x, double* out_host) {
     return AK_OK;
 }
 AK_API int ak_scal(ak_ctx* ctx, int64_t n, double s, double* x) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && n >= 0, "ak_scal: bad argument");
     return launch_scal(&ctx->c, n, s, x);
 }
 AK_API int ak_axpy(ak_ctx* ctx, int64_t n, double s, const double* x, double* y) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && n >= 0, "ak_axpy: bad argument");
     return launch_axpy(&ctx->c, n, s, x, y);
 }
 AK_API int ak_axpby(ak_ctx* ctx, int64_t n, double s, const double* x, double t, double* y) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && n >= 0, "ak_axpby: bad argument");
     return launch_axpby(&ctx->c, n, s, x, t, y);
 }
 AK_API int ak_copy(ak_ctx* ctx, int64_t n, double* y, const double* x) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && n >= 0, "ak_copy: bad argument");
     return launch_copy(&ctx->c, n, y, x);
 }
 AK_API int ak_fill(ak_ctx* ctx, int64_t n, double* x, double val) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && n >= 0, "ak_fill: bad argument");
     return launch_fill(&ctx->c, n, x, val);
 }
 AK_API int ak_ref(ak_ctx* ctx, int64_t n, double* x, double* y, double c, double s) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && n >= 0, "ak_ref: bad argument");
     return launch_ref(&ctx->c, n, x, y, c, s);
 }
 AK_API int ak_divcopy(ak_ctx* ctx, int64_t n, double* y, const double* x, double s) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && n >= 0, "ak_divcopy: bad argument");
     return launch_divcopy(&ctx->c, n, y, x, s);
 }

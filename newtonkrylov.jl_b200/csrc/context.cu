@@ -330,24 +330,33 @@ AK_API int ak_ctx_create(int device, ak_ctx** out) {
     Ctx* c = &ctx->c;
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
-    AK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    {
-        // Stream-ordered allocations from the device pool, never trimmed: a Krylov workspace
-        // (22+ vectors of n doubles) is re-created by every newton_krylov! call like in the
-        // reference (src/Ariadne.jl:317-318) but costs no cudaMalloc/cudaFree after the first.
-        cudaMemPool_t pool;
-        AK_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    // every failure below releases what was created so far (ak_ctx_destroy copes with a partially built context)
+    auto build = [&]() -> int {
+        AK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        cudaMemPoolProps pp;
+        memset(&pp, 0, sizeof(pp));
+        pp.allocType = cudaMemAllocationTypePinned;
+        pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice;
+        pp.location.id = device;
+        AK_CUDA(cudaMemPoolCreate(&c->pool, &pp));
         uint64_t keep = UINT64_MAX;
-        AK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        AK_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        AK_CUDA(cudaMalloc(&c->partials, sizeof(double) * kMaxPartials));
+        AK_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned int)));
+        AK_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
+        AK_CUDA(cudaMalloc(&c->dscal, sizeof(double) * 64));
+        AK_CUDA(cudaMemset(c->dscal, 0, sizeof(double) * 64));
+        AK_CUDA(cudaHostAlloc((void**)&c->hscal, sizeof(double) * 64, cudaHostAllocDefault));
+        AK_CUDA(cudaEventCreate(&c->ev_t0));
+        AK_CUDA(cudaEventCreate(&c->ev_t1));
+        return AK_OK;
+    };
+    const int rc = build();
+    if (rc != AK_OK) {
+        ak_ctx_destroy(ctx);
+        return rc;
     }
-    AK_CUDA(cudaMalloc(&c->partials, sizeof(double) * kMaxPartials));
-    AK_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned int)));
-    AK_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
-    AK_CUDA(cudaMalloc(&c->dscal, sizeof(double) * 64));
-    AK_CUDA(cudaMemset(c->dscal, 0, sizeof(double) * 64));
-    AK_CUDA(cudaHostAlloc((void**)&c->hscal, sizeof(double) * 64, cudaHostAllocDefault));
-    AK_CUDA(cudaEventCreate(&c->ev_t0));
-    AK_CUDA(cudaEventCreate(&c->ev_t1));
     *out = ctx;
     return AK_OK;
 }
@@ -373,12 +382,14 @@ AK_API int ak_ctx_destroy(ak_ctx* ctx) {
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
+    if (c->pool) cudaMemPoolDestroy(c->pool);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete ctx;
     return AK_OK;
 }
 
 AK_API int ak_ctx_sync(ak_ctx* ctx) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx, "ak_ctx_sync: NULL ctx");
     AK_CUDA(cudaStreamSynchronize(ctx->c.stream));
     return AK_OK;
@@ -391,11 +402,13 @@ AK_API int64_t ak_ctx_launch_count(ak_ctx* ctx, int reset) {
     return v;
 }
 AK_API int ak_timer_start(ak_ctx* ctx) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx, "ak_timer_start: NULL ctx");
     AK_CUDA(cudaEventRecord(ctx->c.ev_t0, ctx->c.stream));
     return AK_OK;
 }
 AK_API int ak_timer_stop(ak_ctx* ctx, double* ms_out) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && ms_out, "ak_timer_stop: NULL argument");
     AK_CUDA(cudaEventRecord(ctx->c.ev_t1, ctx->c.stream));
     AK_CUDA(cudaEventSynchronize(ctx->c.ev_t1));
@@ -406,6 +419,7 @@ AK_API int ak_timer_stop(ak_ctx* ctx, double* ms_out) {
 }
 
 AK_API int ak_profile_enable(ak_ctx* ctx, int on) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx, "ak_profile_enable: NULL ctx");
     Ctx* c = &ctx->c;
     AK_CUDA(cudaStreamSynchronize(c->stream));
@@ -415,6 +429,7 @@ AK_API int ak_profile_enable(ak_ctx* ctx, int on) {
     return AK_OK;
 }
 AK_API int ak_profile_read(ak_ctx* ctx, int cls, int64_t* count_out, double* ms_total_out) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && cls >= 0 && cls < PK_NUM, "ak_profile_read: bad argument");
     Ctx* c = &ctx->c;
     AK_CUDA(cudaStreamSynchronize(c->stream));
@@ -431,9 +446,10 @@ AK_API int ak_profile_read(ak_ctx* ctx, int cls, int64_t* count_out, double* ms_
 }
 
 AK_API int ak_malloc(ak_ctx* ctx, int64_t n, double** out) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && out && n >= 0, "ak_malloc: bad argument");
     AK_CUDA(cudaSetDevice(ctx->c.device));
-    cudaError_t e = cudaMallocAsync((void**)out, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->c.stream);
+    cudaError_t e = pool_alloc(&ctx->c, (void**)out, sizeof(double) * (size_t)(n > 0 ? n : 1));
     if (e != cudaSuccess) {
         set_error("ak_malloc: %lld doubles: %s", (long long)n, cudaGetErrorString(e));
         (void)cudaGetLastError();
@@ -442,18 +458,21 @@ AK_API int ak_malloc(ak_ctx* ctx, int64_t n, double** out) {
     return AK_OK;
 }
 AK_API int ak_free(ak_ctx* ctx, double* p) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx, "ak_free: NULL ctx");
     if (!p) return AK_OK;
     AK_CUDA(cudaFreeAsync(p, ctx->c.stream));  // stream-ordered: safe behind every kernel already enqueued
     return AK_OK;
 }
 AK_API int ak_upload(ak_ctx* ctx, double* dst_dev, const double* src_host, int64_t n) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && n >= 0, "ak_upload: bad argument");
     AK_CUDA(cudaMemcpyAsync(dst_dev, src_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->c.stream));
     AK_CUDA(cudaStreamSynchronize(ctx->c.stream));
     return AK_OK;
 }
 AK_API int ak_download(ak_ctx* ctx, double* dst_host, const double* src_dev, int64_t n) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && n >= 0, "ak_download: bad argument");
     AK_CUDA(cudaMemcpyAsync(dst_host, src_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->c.stream));
     AK_CUDA(cudaStreamSynchronize(ctx->c.stream));
@@ -475,6 +494,7 @@ AK_API int ak_host_free(double* p) {
 }
 
 AK_API int ak_halo_pack(ak_ctx* ctx, double* compact, const double* padded, int64_t nx, int64_t ny) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && compact && padded && nx >= 1 && ny >= 1, "ak_halo_pack: bad argument");
     int64_t n = nx * ny;
     int blocks = (int)((n + 255) / 256 < ctx->c.num_sms * 8 ? (n + 255) / 256 : ctx->c.num_sms * 8);
@@ -484,6 +504,7 @@ AK_API int ak_halo_pack(ak_ctx* ctx, double* compact, const double* padded, int6
     return AK_OK;
 }
 AK_API int ak_halo_unpack(ak_ctx* ctx, double* padded, const double* compact, int64_t nx, int64_t ny, int32_t bc) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && compact && padded && nx >= 1 && ny >= 1, "ak_halo_unpack: bad argument");
     int64_t n = (nx + 2) * (ny + 2);
     int blocks = (int)((n + 255) / 256 < ctx->c.num_sms * 8 ? (n + 255) / 256 : ctx->c.num_sms * 8);
@@ -503,6 +524,7 @@ AK_API int ak_comm_unique_id(char id_out[128]) {
     return AK_OK;
 }
 AK_API int ak_comm_init(ak_ctx* ctx, int nranks, int rank, const char id_in[128]) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && id_in && nranks >= 1 && rank >= 0 && rank < nranks, "ak_comm_init: bad argument");
     AK_REQUIRE(ctx->c.comm == nullptr, "ak_comm_init: communicator already initialised");
     if (nranks == 1) {
@@ -527,6 +549,7 @@ AK_API int ak_comm_init(ak_ctx* ctx, int nranks, int rank, const char id_in[128]
     return AK_OK;
 }
 AK_API int ak_comm_enable_p2p(ak_ctx* ctx, int64_t halo_doubles) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && halo_doubles >= 0, "ak_comm_enable_p2p: bad argument");
     Ctx* c = &ctx->c;
     if (c->nranks <= 1) return AK_OK;
@@ -613,8 +636,10 @@ AK_API int ak_comm_enable_p2p(ak_ctx* ctx, int64_t halo_doubles) {
     c->p2p_on = true;
     return AK_OK;
 }
-AK_API int ak_comm_p2p_enabled(ak_ctx* ctx) { return (ctx && ctx->c.p2p_on) ? 1 : 0; }
+AK_API int ak_comm_p2p_enabled(ak_ctx* ctx) {
+    AK_ENTER(ctx); return (ctx && ctx->c.p2p_on) ? 1 : 0; }
 AK_API int ak_comm_use_p2p(ak_ctx* ctx, int on) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx, "ak_comm_use_p2p: NULL ctx");
     AK_REQUIRE(!on || ctx->c.p2p_block != nullptr, "ak_comm_use_p2p: peer memory was never mapped");
     AK_CUDA(cudaStreamSynchronize(ctx->c.stream));
@@ -624,12 +649,14 @@ AK_API int ak_comm_use_p2p(ak_ctx* ctx, int on) {
 }
 
 AK_API int ak_comm_rank(ak_ctx* ctx, int* rank, int* nranks) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx, "ak_comm_rank: NULL ctx");
     if (rank) *rank = ctx->c.rank;
     if (nranks) *nranks = ctx->c.nranks;
     return AK_OK;
 }
 AK_API int ak_comm_barrier(ak_ctx* ctx) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx, "ak_comm_barrier: NULL ctx");
     Ctx* c = &ctx->c;
     if (c->nranks > 1) {

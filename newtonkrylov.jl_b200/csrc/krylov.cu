@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_cg_small_bratu1d(int n, do
 // ---------------------------------------------------------------------------------------
 static int ws_alloc_vec(ak_krylov* ws, double** out) {
     double* p = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&p, sizeof(double) * (size_t)(ws->n > 0 ? ws->n : 1), ws->ctx->stream);
+    cudaError_t e = pool_alloc(ws->ctx, (void**)&p, sizeof(double) * (size_t)(ws->n > 0 ? ws->n : 1));
     if (e != cudaSuccess) {
         set_error("krylov workspace: cudaMalloc of %lld doubles failed: %s", (long long)ws->n, cudaGetErrorString(e));
         (void)cudaGetLastError();
@@ -561,7 +561,7 @@ static int ws_grow_scalars(ak_krylov* ws, int64_t kcap_new) {
     const int64_t nR = kcap_new * (kcap_new + 1) / 2;
     auto regrow = [&](double** arr, int64_t old_n, int64_t new_n) -> int {
         double* q = nullptr;
-        AK_CUDA(cudaMallocAsync((void**)&q, sizeof(double) * (size_t)new_n, c->stream));
+        AK_CUDA(pool_alloc(c, (void**)&q, sizeof(double) * (size_t)new_n));
         AK_CUDA(cudaMemsetAsync(q, 0, sizeof(double) * (size_t)new_n, c->stream));
         if (*arr && old_n > 0)
             AK_CUDA(cudaMemcpyAsync(q, *arr, sizeof(double) * (size_t)old_n, cudaMemcpyDeviceToDevice, c->stream));
@@ -589,7 +589,7 @@ static int ws_grow_hist(ak_krylov* ws, int64_t need) {
     if (nc < need) nc = need;
     AK_CUDA(cudaStreamSynchronize(c->stream));
     double* q = nullptr;
-    AK_CUDA(cudaMallocAsync((void**)&q, sizeof(double) * (size_t)nc, c->stream));
+    AK_CUDA(pool_alloc(c, (void**)&q, sizeof(double) * (size_t)nc));
     if (ws->hist) {
         AK_CUDA(cudaMemcpyAsync(q, ws->hist, sizeof(double) * (size_t)ws->hist_cap, cudaMemcpyDeviceToDevice, c->stream));
         AK_CUDA(cudaFreeAsync(ws->hist, c->stream));
@@ -629,7 +629,7 @@ static int ws_upload_basis_table(ak_krylov* ws, int64_t k, bool use_z = false) {
         if (ws->V_dev) AK_CUDA(cudaFreeAsync((void*)ws->V_dev, c->stream));
         int64_t cap = ws->V_dev_cap ? ws->V_dev_cap * 2 : 64;
         if (cap < k) cap = k;
-        AK_CUDA(cudaMallocAsync((void**)&ws->V_dev, sizeof(double*) * (size_t)cap, c->stream));
+        AK_CUDA(pool_alloc(c, (void**)&ws->V_dev, sizeof(double*) * (size_t)cap));
         ws->V_dev_cap = cap;
     }
     AK_CUDA(cudaMemcpyAsync((void*)ws->V_dev, use_z ? ws->Z.data() : ws->V.data(), sizeof(double*) * (size_t)k,
@@ -1239,6 +1239,7 @@ AK_API void ak_krylov_default_opts(ak_krylov_opts* o) {
 }
 
 AK_API int ak_krylov_create(ak_ctx* ctx, int32_t algo, int64_t n, int32_t memory, int64_t max_basis, ak_krylov** out) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && out && n >= 1, "ak_krylov_create: bad argument");
     AK_REQUIRE(algo == AK_ALGO_GMRES || algo == AK_ALGO_CG || algo == AK_ALGO_FGMRES, "ak_krylov_create: unknown algo");
     AK_REQUIRE(memory >= 1, "ak_krylov_create: memory must be >= 1");
@@ -1260,7 +1261,7 @@ AK_API int ak_krylov_create(ak_ctx* ctx, int32_t algo, int64_t n, int32_t memory
             if ((rc = ws_alloc_vec(ws, &ws->p)) != AK_OK) break;
             if ((rc = ws_alloc_vec(ws, &ws->Ap)) != AK_OK) break;
         }
-        if (cudaMallocAsync((void**)&ws->ctl, sizeof(KrylovCtl), ctx->c.stream) != cudaSuccess) { rc = AK_ERR_NOMEM; break; }
+        if (pool_alloc(&ctx->c, (void**)&ws->ctl, sizeof(KrylovCtl)) != cudaSuccess) { rc = AK_ERR_NOMEM; break; }
         cudaMemsetAsync(ws->ctl, 0, sizeof(KrylovCtl), ctx->c.stream);
         if (cudaHostAlloc((void**)&ws->status, sizeof(KrylovStatus) * kStatusSlots, cudaHostAllocMapped) != cudaSuccess) {
             rc = AK_ERR_NOMEM;
@@ -1303,6 +1304,7 @@ AK_API int ak_krylov_solve(ak_krylov* ws, const ak_problem* p, const double* u, 
                            const ak_krylov_opts* opts, ak_krylov_stats* stats_out, double* hist_host,
                            int64_t hist_cap) {
     AK_REQUIRE(ws && p && b && opts && stats_out, "ak_krylov_solve: NULL argument");
+    AK_ENTER(ws->owner);
     AK_REQUIRE(ak_problem_size(p) == ws->n, "ak_krylov_solve: problem size does not match the workspace");
     return krylov_solve_internal(ws, p, u, b, opts, stats_out, hist_host, hist_cap);
 }
@@ -1311,6 +1313,7 @@ AK_API double* ak_krylov_x(ak_krylov* ws) { return ws ? ws->x : nullptr; }
 
 AK_API int ak_krylov_basis(ak_krylov* ws, int64_t i, double** stored_dev, double* scale_host, int64_t* count_out) {
     AK_REQUIRE(ws, "ak_krylov_basis: NULL workspace");
+    AK_ENTER(ws->owner);
     if (count_out) *count_out = (int64_t)ws->V.size();
     if (stored_dev == nullptr && scale_host == nullptr) return AK_OK;
     AK_REQUIRE(i >= 0 && i < (int64_t)ws->V.size(), "ak_krylov_basis: index out of range");
@@ -1327,6 +1330,7 @@ AK_API int ak_krylov_basis(ak_krylov* ws, int64_t i, double** stored_dev, double
 
 AK_API int ak_precond_apply(ak_ctx* ctx, const ak_problem* p, const double* u, int32_t kind, int32_t itmax,
                             const double* x, double* y) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && p && x && y, "ak_precond_apply: NULL argument");
     if (kind != AK_PRECOND_INNER_GMRES) return precond_apply(&ctx->c, p, u, kind, nullptr, nullptr, x, y);
     // mul!(y, P::GmresPreconditioner, x) = copyto!(y, gmres(P.J, x; P.itmax)[1])   examples/bratu.jl:146-149

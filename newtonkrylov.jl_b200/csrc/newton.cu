@@ -123,6 +123,7 @@ AK_API void ak_newton_default_opts(ak_newton_opts* o) {
 AK_API int ak_newton_solve(ak_ctx* ctx, const ak_problem* p, double* u, double* res, const ak_newton_opts* opts,
                            ak_newton_stats* stats_out, double* hist_nres_host, int64_t* hist_inner_host,
                            double* hist_eta_host, int32_t hist_cap, ak_newton_callback cb, void* cb_user) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && p && u && res && opts && stats_out, "ak_newton_solve: NULL argument");
     Ctx* c = &ctx->c;
     const int64_t n = ak_problem_size(p);
@@ -142,6 +143,7 @@ AK_API int ak_newton_solve(ak_ctx* ctx, const ak_problem* p, double* u, double* 
 AK_API int ak_newton_solve_host(ak_ctx* ctx, const ak_problem* p_in, double* u_host, const double* un_host,
                                 const ak_newton_opts* opts, ak_newton_stats* stats_out, double* hist_nres_host,
                                 int64_t* hist_inner_host, int32_t hist_cap) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && p_in && u_host && opts && stats_out, "ak_newton_solve_host: NULL argument");
     Ctx* c = &ctx->c;
     ak_problem p = *p_in;
@@ -178,6 +180,7 @@ AK_API int ak_newton_solve_host(ak_ctx* ctx, const ak_problem* p_in, double* u_h
 AK_API int ak_implicit_solve(ak_ctx* ctx, ak_problem* p, double* un_dev, int32_t nsteps, const ak_newton_opts* opts_in,
                              int32_t* per_step_newton_host, int64_t* per_step_inner_host,
                              int32_t* per_step_solved_host) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && p && un_dev && opts_in && nsteps >= 0, "ak_implicit_solve: bad argument");
     Ctx* c = &ctx->c;
     const int64_t n = ak_problem_size(p);

@@ -204,7 +204,7 @@ struct Pool {  // stream-ordered scratch, freed when the solve has been enqueued
     explicit Pool(Ctx* ctx) : c(ctx) {}
     double* get(int64_t n) {
         void* p = nullptr;
-        if (cudaMallocAsync(&p, sizeof(double) * (size_t)(n > 0 ? n : 1), c->stream) != cudaSuccess) {
+        if (pool_alloc(c, (void**)&p, sizeof(double) * (size_t)(n > 0 ? n : 1)) != cudaSuccess) {
             (void)cudaGetLastError();
             return nullptr;
         }

@@ -1098,7 +1098,7 @@ struct PoolVec {  // stream-ordered scratch vector
     Ctx* c;
     double* p = nullptr;
     PoolVec(Ctx* ctx, int64_t n) : c(ctx) {
-        if (cudaMallocAsync((void**)&p, sizeof(double) * (size_t)(n > 0 ? n : 1), c->stream) != cudaSuccess) p = nullptr;
+        if (pool_alloc(c, (void**)&p, sizeof(double) * (size_t)(n > 0 ? n : 1)) != cudaSuccess) p = nullptr;
     }
     ~PoolVec() { if (p) cudaFreeAsync(p, c->stream); }
 };
@@ -1492,6 +1492,7 @@ AK_API int64_t ak_problem_size(const ak_problem* p) {
 }
 
 AK_API int ak_residual(ak_ctx* ctx, const ak_problem* p, double* u, double* res, double* nrm_out_host) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && p && u && res, "ak_residual: NULL argument");
     Ctx* c = &ctx->c;
     AK_TRY(launch_residual(c, p, u, res, nrm_out_host ? c->dscal : nullptr));
@@ -1504,12 +1505,14 @@ AK_API int ak_residual(ak_ctx* ctx, const ak_problem* p, double* u, double* res,
 }
 
 AK_API int ak_jvp(ak_ctx* ctx, const ak_problem* p, const double* u, double* v, double* out) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && p && v && out, "ak_jvp: NULL argument");
     return launch_jvp(&ctx->c, p, u, v, out, nullptr);
 }
 
 AK_API int ak_jvp_batched(ak_ctx* ctx, const ak_problem* p, const double* u, double* V, int64_t ldv, double* Out,
                           int64_t ldo, int32_t ncols) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && p && V && Out && ncols >= 0, "ak_jvp_batched: bad argument");
     const int64_t n = ak_problem_size(p);
     AK_REQUIRE(ldv >= n && ldo >= n, "ak_jvp_batched: leading dimensions must be >= n");
@@ -1526,6 +1529,7 @@ AK_API int ak_jvp_batched(ak_ctx* ctx, const ak_problem* p, const double* u, dou
 }
 
 AK_API int ak_jvp_transpose(ak_ctx* ctx, const ak_problem* p, const double* u, double* v, double* out) {
+    AK_ENTER(ctx);
     AK_REQUIRE(ctx && p && v && out, "ak_jvp_transpose: NULL argument");
     return launch_jvp_transpose(&ctx->c, p, u, v, out);
 }

@@ -56,7 +56,7 @@ struct Scratch {  // stream-ordered scratch vector
     Ctx* c;
     double* p = nullptr;
     Scratch(Ctx* ctx, int64_t n) : c(ctx) {
-        if (cudaMallocAsync((void**)&p, sizeof(double) * (size_t)(n > 0 ? n : 1), c->stream) != cudaSuccess) {
+        if (pool_alloc(c, (void**)&p, sizeof(double) * (size_t)(n > 0 ? n : 1)) != cudaSuccess) {
             p = nullptr;
             (void)cudaGetLastError();
         }

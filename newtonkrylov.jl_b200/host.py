@@ -1005,19 +1005,29 @@ def newton_krylov(F, u0, p=None, M=None, **kwargs):
 
 
 def _newton_opts(tol_rel, tol_abs, max_niter, forcing, algo, memory, max_basis, krylov_kwargs, verbose=0, N=None,
-                 M=None, J=None, keep=None):
+                 M=None, J=None, keep=None, native_loop=False):
     kk = dict(krylov_kwargs or {})
     override = "rtol" in kk
     fuse = kk.pop("fuse", "block8")
     ldiv = bool(kk.pop("ldiv", False))
     n = len(J.u) if J is not None else 0
+    def built_once(P, side):
+        # The reference calls N(J) / M(J) before EVERY linear solve (src/Ariadne.jl:324-329).  The native kinds read u
+        # at apply time, so building them once is equivalent; a caller-supplied object may have captured state of u0
+        # (a factorisation of collect(J), a shift ...), which the C++ loop would silently freeze.
+        if isinstance(P, UserPreconditioner) and native_loop:
+            raise NotImplementedError(
+                f"{side} = J -> UserPreconditioner(...) with the C++ Newton loop (ak_newton_solve): the object would be "
+                "built once at u0, the reference rebuilds it every Newton step; use newton_krylov_ (host-driven loop)")
+        return P
+
     if N is not None:
-        P = N(J)
+        P = built_once(N(J), "N")
         kk["precond_n"], kk["precond_itmax"], kk["n_apply"] = _precond_fields(P, n, ldiv, "N")
         if keep is not None:
             keep.append(P)
     if M is not None:
-        P = M(J)
+        P = built_once(M(J), "M")
         kk["precond_m"], kk["precond_m_itmax"], kk["m_apply"] = _precond_fields(P, n, ldiv, "M")
         if keep is not None:
             keep.append(P)
@@ -1047,7 +1057,7 @@ def newton_krylov_native_(F_, u, p=None, res=None, *, tol_rel=1.0e-6, tol_abs=1.
     prob = F_.problem(u, p, coef=coef)
     keep = []  # preconditioner objects (their ctypes callbacks) must outlive the solve
     o = _newton_opts(tol_rel, tol_abs, max_niter, forcing, algo, memory, max_basis, krylov_kwargs, verbose, N=N, M=M,
-                     J=JacobianOperator(F_, res, u, p, coef=coef), keep=keep)
+                     J=JacobianOperator(F_, res, u, p, coef=coef), keep=keep, native_loop=True)
     st = A.ak_newton_stats()
     cap = max_niter + 3
     hn, hi, he = np.zeros(cap), np.zeros(cap, dtype=np.int64), np.zeros(cap)

@@ -208,3 +208,16 @@ def test_full_bratu2d_solve_with_caller_supplied_fast_poisson_preconditioner(nk,
         assert abs(a["n_res"] - b["n_res"]) <= 1e-7 * b["n_res"] + 1e-11 * hist[0]["n_res"]
     assert rel(u.numpy(), uo) < 1e-8
     del keep
+
+
+def test_user_preconditioner_is_refused_by_the_cpp_newton_loop(nk, ctx):
+    """The reference rebuilds N(J) before every linear solve (src/Ariadne.jl:324-329); the single-call C++ loop builds
+    the object once, which is only equivalent for the native kinds — a caller-supplied object is refused there."""
+    d = P.bratu2d(12)
+    F_, u, p, _ = P.device_setup(nk, ctx, d)
+    with pytest.raises(NotImplementedError):
+        nk.newton_krylov_native_(F_, u, p, None, N=lambda J: nk.UserPreconditioner(lambda y, x: y.copy_(x)))
+    # the host-driven loop takes it (and calls the hook once per Newton step)
+    built = []
+    _, r = nk.newton_krylov_(F_, u, p, None, N=lambda J: built.append(1) or nk.UserPreconditioner(lambda y, x: y.copy_(x)))
+    assert r.solved and len(built) == r.stats.outer_iterations
