@@ -1082,9 +1082,13 @@ static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, cons
     const int64_t itmax = o->itmax == 0 ? 2 * n : o->itmax;
     if (!ws->hcol) AK_TRY(ws_grow_scalars(ws, 4));
     if (want_hist) AK_TRY(ws_grow_hist(ws, 257));
+    // kwarg M of cg! (a symmetric positive definite preconditioner): z = M r, gamma = <r, z>, p = z + beta p, the
+    // residual norm is measured in the M-norm like Krylov.jl does (rNorm = sqrt(<r, z>))
+    const bool lprec = (o->precond_m != AK_PRECOND_NONE);
+    if (lprec && !ws->qbuf) AK_TRY(ws_alloc_vec(ws, &ws->qbuf));
     // small-problem regime: the whole solve in one persistent block (AK_NO_SMALL_CG=1: developer switch for A/B runs)
     static const bool no_small = getenv("AK_NO_SMALL_CG") != nullptr;
-    if (!no_small && prob->kind == AK_BRATU1D && prob->jvp_mode == AK_JVP_ANALYTIC && c->nranks == 1 && n <= kSmallN &&
+    if (!no_small && !lprec && prob->kind == AK_BRATU1D && prob->jvp_mode == AK_JVP_ANALYTIC && c->nranks == 1 && n <= kSmallN &&
         itmax < (1ll << 31)) {
         if (want_hist) AK_TRY(ws_grow_hist(ws, itmax + 2));
         const size_t smem = sizeof(double) * (size_t)(2 * n + 2);
@@ -1121,11 +1125,14 @@ static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, cons
         return flags0;
     }
     double *x = ws->x, *r = ws->r, *p = ws->p, *Ap = ws->Ap;
+    double* z = lprec ? ws->qbuf : r;  // z === r without a preconditioner
     const int* stop = &ws->ctl->stop;
     AK_TRY(launch_fill(c, n, x, 0.0));
     AK_TRY(launch_copy(c, n, r, b));
-    AK_TRY(launch_copy(c, n, p, r));
-    AK_TRY(launch_sumsq(c, n, r, ws->hcol));
+    if (lprec) AK_TRY(apply_precond(ws, prob, u, o, true, r, z));
+    AK_TRY(launch_copy(c, n, p, z));
+    if (lprec) AK_TRY(launch_dot(c, n, r, z, ws->hcol));
+    else AK_TRY(launch_sumsq(c, n, r, ws->hcol));
     k_cg_begin<<<1, 32, 0, sm>>>(ws->ctl, ws->hcol, want_hist ? ws->hist : nullptr, o->atol, o->rtol, &ws->status[kStatusRing]);
     c->launches++;
     AK_CUDA(cudaGetLastError());
@@ -1152,7 +1159,13 @@ static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, cons
             c->launches++;
             // r -= alpha Ap (+ gamma_next = <r, r>); the x update rides with the p update below (same values:
             // x += alpha p uses the p of this iteration, which is only overwritten afterwards)
-            AK_TRY(launch_mgs_step(c, n, r, Ap, &ws->ctl->alpha, nullptr, 1, ws->hcol + 2, stop));
+            if (!lprec) {
+                AK_TRY(launch_mgs_step(c, n, r, Ap, &ws->ctl->alpha, nullptr, 1, ws->hcol + 2, stop));
+            } else {  // r -= alpha Ap ; z = M r ; gamma_next = <r, z>
+                AK_TRY(launch_mgs_step(c, n, r, Ap, &ws->ctl->alpha, nullptr, 0, nullptr, stop));
+                AK_TRY(apply_precond(ws, prob, u, o, true, r, z));
+                AK_TRY(launch_dot(c, n, r, z, ws->hcol + 2));
+            }
             k_cg_beta<<<1, 32, 0, sm>>>(ws->ctl, ws->hcol + 2, (int)k, itmax, want_hist ? ws->hist : nullptr,
                                         &ws->status[slot]);
             c->launches++;
@@ -1164,10 +1177,10 @@ static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, cons
                 if (blocks > (int64_t)c->num_sms * 4) blocks = (int64_t)c->num_sms * 4;
                 if (blocks < 1) blocks = 1;
                 const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(p) |
-                                   reinterpret_cast<uintptr_t>(r)) & 31u) == 0;
+                                   reinterpret_cast<uintptr_t>(z)) & 31u) == 0;
                 ProfScope prof(c, PK_ELEMENTWISE);
-                if (vec) k_cg_update_xp<true><<<(int)blocks, 256, 0, sm>>>(x, p, r, ws->ctl, (int)k, n);
-                else k_cg_update_xp<false><<<(int)blocks, 256, 0, sm>>>(x, p, r, ws->ctl, (int)k, n);
+                if (vec) k_cg_update_xp<true><<<(int)blocks, 256, 0, sm>>>(x, p, z, ws->ctl, (int)k, n);
+                else k_cg_update_xp<false><<<(int)blocks, 256, 0, sm>>>(x, p, z, ws->ctl, (int)k, n);
                 c->launches++;
                 AK_CUDA(cudaGetLastError());
             }
@@ -1217,8 +1230,8 @@ static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, cons
 int krylov_solve_internal(ak_krylov* ws, const ak_problem* p, const double* u, const double* b,
                           const ak_krylov_opts* opts, ak_krylov_stats* st, double* hist_host, int64_t hist_cap) {
     if (ws->algo == AK_ALGO_CG) {
-        if (opts->precond_n != AK_PRECOND_NONE || opts->precond_m != AK_PRECOND_NONE) {
-            set_error("preconditioned CG is not implemented");
+        if (opts->precond_n != AK_PRECOND_NONE) {
+            set_error("cg! has no right preconditioner (kwarg N); pass the preconditioner as M");
             return AK_ERR_UNSUPPORTED;
         }
         return cg_solve(ws, p, u, b, opts, st, hist_host, hist_cap);

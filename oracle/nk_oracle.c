@@ -826,22 +826,26 @@ OK_EXPORT int ok_gmres(ok_krylov* ws, const ak_problem* p, const double* u, cons
     return 0;
 }
 
-/* CG, Krylov.jl cg! with M = I, radius = 0, linesearch = false. */
+/* CG, Krylov.jl cg! with radius = 0, linesearch = false; kwarg M (symmetric positive definite preconditioner):
+ * z = M r, gamma = <r, z>, rNorm = sqrt(gamma) (M-norm of the residual), p = z + beta p. */
 OK_EXPORT int ok_cg(ok_krylov* ws, const ak_problem* p, const double* u, const double* b,
                     const ak_krylov_opts* o, ak_krylov_stats* st, double* hist, int64_t hist_cap) {
     const int64_t n = ws->n;
     double *x = ws->x, *r = ws->r, *pp = ws->pp, *Ap = ws->Ap;
     int64_t nh = 0;
+    const int lprec = (o->precond_m != AK_PRECOND_NONE);
+    double* z = lprec ? ok_alloc(n) : r; /* z === r without a preconditioner */
     ok_fill(n, x, 0.0);
     ok_copy(n, r, b);
-    ok_copy(n, pp, r); /* z === r, p <- z */
-    double gamma = ok_dot(n, r, r);
+    if (lprec) apply_precond_m(p, u, o, n, r, z);
+    ok_copy(n, pp, z); /* p <- z */
+    double gamma = ok_dot(n, r, z);
     double rNorm = sqrt(gamma);
     if (hist && nh < hist_cap) hist[nh++] = rNorm;
     memset(st, 0, sizeof(*st));
     st->beta = rNorm;
     st->rnorm = rNorm;
-    if (gamma == 0.0) { st->solved = 1; return 0; }
+    if (gamma == 0.0) { st->solved = 1; if (lprec) free(z); return 0; }
     int64_t itmax = o->itmax == 0 ? 2 * n : o->itmax;
     int64_t iter = 0;
     double pAp = 0.0, pNorm2 = gamma;
@@ -858,7 +862,8 @@ OK_EXPORT int ok_cg(ok_krylov* ws, const ak_problem* p, const double* u, const d
         double alpha = gamma / pAp;
         ok_axpy(n, alpha, pp, x);
         ok_axpy(n, -alpha, Ap, r);
-        double gamma_next = ok_dot(n, r, r);
+        if (lprec) apply_precond_m(p, u, o, n, r, z);
+        double gamma_next = ok_dot(n, r, z);
         rNorm = sqrt(gamma_next);
         if (hist && nh < hist_cap) hist[nh++] = rNorm;
         int mach = (rNorm + 1.0 <= 1.0);
@@ -867,11 +872,12 @@ OK_EXPORT int ok_cg(ok_krylov* ws, const ak_problem* p, const double* u, const d
             double beta = gamma_next / gamma;
             pNorm2 = gamma_next + beta * beta * pNorm2;
             gamma = gamma_next;
-            ok_axpby(n, 1.0, r, beta, pp);
+            ok_axpby(n, 1.0, z, beta, pp);
         }
         iter += 1;
         tired = iter >= itmax;
     }
+    if (lprec) free(z);
     st->niter = iter;
     st->solved = solved;
     st->inconsistent = inconsistent;

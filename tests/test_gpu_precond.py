@@ -221,3 +221,38 @@ def test_user_preconditioner_is_refused_by_the_cpp_newton_loop(nk, ctx):
     built = []
     _, r = nk.newton_krylov_(F_, u, p, None, N=lambda J: built.append(1) or nk.UserPreconditioner(lambda y, x: y.copy_(x)))
     assert r.solved and len(built) == r.stats.outer_iterations
+
+
+def test_preconditioned_cg_matches_oracle(nk, ctx, oracle):
+    """cg! with kwarg M (Krylov.jl: z = M r, gamma = <r, z>, residual norm in the M-norm).  J of 1-D Bratu is negative
+    definite and CG is applied to it as it is (like the reference does at examples/bratu.jl:59-108); M = -1 / diag(J) is
+    symmetric positive definite.  A right preconditioner (N) does not exist for cg!: refused."""
+    import torch
+
+    d = P.bratu1d(12000, lam=1.0)          # above the one-block regime: the multi-kernel path
+    F_, u, p, _ = P.device_setup(nk, ctx, d)
+    res = u.zero()
+    J = nk.JacobianOperator(F_, res, u, p)
+    diag = -2.0 / d["dx"] ** 2 + d["lam"] * np.exp(d["u0"])
+    minv = torch.as_tensor(-1.0 / diag, device="cuda")
+    b0 = RNG.standard_normal(d["nx"])
+    kw = dict(rtol=1e-30, atol=0.0, itmax=200)
+    ws = nk.krylov_workspace("cg", nk.KrylovConstructor(res))
+    nk.krylov_solve_(ws, J, nk.DeviceVector.from_numpy(b0, ctx), history=True,
+                     M=nk.UserPreconditioner(lambda y, x: torch.mul(x, minv, out=y)), **kw)
+    mh = -1.0 / diag
+
+    def apply(y, x):
+        y[:] = x * mh
+
+    fn, keep = oracle.user_precond(d["nx"], apply)
+    po = P.oracle_problem(oracle, d)
+    xr, sr, hr = oracle.krylov_solve(po, d["u0"], b0, algo=A.AK_ALGO_CG, hist_cap=1000, precond_m=A.AK_PRECOND_USER,
+                                     m_apply=fn, **kw)
+    st = ws.stats
+    assert (st.niter, st.solved) == (sr["niter"], sr["solved"]) and st.niter == 200
+    assert hr[-1] < 0.5 * hr[0]  # Jacobi does something on this operator
+    assert np.max(np.abs(np.array(st.residuals) - hr)) <= 1e-9 * hr[0]
+    assert rel(ws.x.numpy(), xr) < 1e-8
+    with pytest.raises(nk.AriadneError):
+        nk.krylov_solve_(ws, J, nk.DeviceVector.from_numpy(b0, ctx), N=nk.JacobiPreconditioner(J), **kw)

@@ -2,6 +2,9 @@
 # round 2, session F (1 GPU): profiling evidence of the default path — ncu launch list, --set full capture of the dominant
 # kernels, both bench arms, the other configs' own bench lines
 mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --maxfail=30 --deselect tests/test_gpu_multi.py > gpurun_out/r2f_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2f_pytest.log
+tail -4 gpurun_out/r2f_pytest.log
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-other-configs"
 $B > gpurun_out/r2f_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 520 -c 340 --csv --log-file gpurun_out/r02_launches_block8.csv $B > gpurun_out/r2f_ncu1.log 2>&1
