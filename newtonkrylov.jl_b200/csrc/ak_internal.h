@@ -229,6 +229,7 @@ int launch_residual(Ctx* ctx, const ak_problem* p, double* u, double* res, doubl
 struct JvpFusion {
     const double* scale_src = nullptr;  // w_prev: v <- scale_src / denom, written to v
     const double* denom_dev = nullptr;  // device scalar
+    const double* inv_denom_dev = nullptr;  // (raw) 1 / *denom_dev, precomputed by the scalar kernels: saves a division per thread
     // un-normalised basis: scale_src stays the stored basis vector and out = J(scale_src) / denom (J is linear; the
     // stencil kernels scale at the store).  `v` is then scratch (n doubles) for the problem kinds that go through a
     // normalised copy (2x2 system, Midpoint, caller-supplied tangents, finite differences), unused otherwise.

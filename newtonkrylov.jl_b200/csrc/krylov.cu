@@ -68,6 +68,7 @@ struct ak_krylov {
     bool last_raw = false;    // the last GMRES solve kept the basis un-normalised (stored V[i] = rho[i] v_i)
     double* ycoef = nullptr;  // solution of R y = z (device back-substitution), already divided by rho for the combine
     double* rho = nullptr;  // un-normalised basis (blocked sweeps): stored V[i] = rho[i] * v_i
+    double* rinv = nullptr; // 1 / rho[i], formed once by the scalar kernels (the tangent kernels multiply their result by it)
     double* gram = nullptr; // blocked sweeps: <V[i], V[a]> for the earlier vectors a of V[i]'s own block (kBlkMax per i)
     int64_t hist_cap = 0;
     ak::KrylovCtl* ctl = nullptr;
@@ -84,7 +85,7 @@ namespace ak {
 // ---------------------------------------------------------------------------------------
 // start of a solve / of a restart pass: beta = ||r0||, z[0] = beta, stopping tolerance
 __global__ void k_gmres_begin(KrylovCtl* ctl, const double* sumsq, double* z, double* hist, int first_pass,
-                              double atol, double rtol, KrylovStatus* st, double* rho) {
+                              double atol, double rtol, KrylovStatus* st, double* rho, double* rinv) {
     if (threadIdx.x != 0) return;
     const double beta = sqrt(*sumsq);
     if (first_pass) {
@@ -97,7 +98,7 @@ __global__ void k_gmres_begin(KrylovCtl* ctl, const double* sumsq, double* z, do
         if (hist) hist[0] = beta;
     }
     z[0] = beta;
-    if (rho) rho[0] = ctl->rNorm;  // un-normalised basis: V[0] stays r0, v_0 = r0 / rNorm
+    if (rho) { rho[0] = ctl->rNorm; rinv[0] = __ddiv_rn(1.0, ctl->rNorm); }  // un-normalised basis: V[0] stays r0, v_0 = r0 / rNorm
     ctl->solved = (ctl->rNorm <= ctl->eps) || (beta == 0.0);
     ctl->stop = ctl->solved;
     ctl->inner_iter = 0;
@@ -120,7 +121,8 @@ __device__ __forceinline__ double sgn(double x) { return (double)((x > 0.0) - (x
 __global__ void __launch_bounds__(32) k_gmres_givens(KrylovCtl* ctl, int k, int64_t nr, double* R, double* c, double* s,
                                                      double* z, double* hcol, int reorth, int blk, double* hist,
                                                      int64_t hist_pos, int inner_limit, KrylovStatus* st, const P2PDev pd,
-                                                     unsigned long long seq_in, double* rho_vec, double* gram) {
+                                                     unsigned long long seq_in, double* rho_vec, double* gram,
+                                                     double* rinv_vec) {
     __shared__ double s_t[kBlkSums], s_g[kBlkMax * kBlkMax], s_hb[kBlkMax], s_cb[kBlkMax];
     __shared__ double s_c[32], s_s[32], s_r[33];
     __shared__ int s_abort;
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(32) k_gmres_givens(KrylovCtl* ctl, int k, int6
     }
     if (lane != 0) return;
     const double Hbis = sqrt(hh);
-    if (rho_vec) rho_vec[k] = Hbis;  // the finished w of this iteration IS the stored basis vector k
+    if (rho_vec) { rho_vec[k] = Hbis; rinv_vec[k] = __ddiv_rn(1.0, Hbis); }  // the finished w of this iteration IS the stored basis vector k
     const double a = cur, b = Hbis;
     double ck, sk, rho;
     if (b == 0.0) {
@@ -575,6 +577,7 @@ static int ws_grow_scalars(ak_krylov* ws, int64_t kcap_new) {
     AK_TRY(regrow(&ws->s, oldk, kcap_new));
     AK_TRY(regrow(&ws->z, oldk ? oldk + 1 : 0, kcap_new + 1));
     AK_TRY(regrow(&ws->rho, oldk ? oldk + 1 : 0, kcap_new + 1));
+    AK_TRY(regrow(&ws->rinv, oldk ? oldk + 1 : 0, kcap_new + 1));
     AK_TRY(regrow(&ws->ycoef, oldk ? oldk + 1 : 0, kcap_new + 1));
     AK_TRY(regrow(&ws->gram, oldk ? (oldk + 1) * kBlkMax : 0, (kcap_new + 1) * kBlkMax));
     AK_TRY(regrow(&ws->hcol, oldk ? hcol_len(oldk) : 0, hcol_len(kcap_new)));
@@ -771,7 +774,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
             }
         }
         k_gmres_begin<<<1, 32, 0, sm>>>(ws->ctl, ws->hcol, ws->z, want_hist ? ws->hist : nullptr, npass == 0, o->atol,
-                                        o->rtol, &ws->status[kStatusRing], raw ? ws->rho : nullptr);
+                                        o->rtol, &ws->status[kStatusRing], raw ? ws->rho : nullptr, ws->rinv);
         c->launches++;
         AK_CUDA(cudaGetLastError());
         AK_CUDA(cudaEventRecord(ws->ev[kStatusRing], sm));
@@ -890,6 +893,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                     // w <- J (V[k-1] / rho[k-1]), straight into basis slot k
                     jf.scale_src = ws->V[k - 1];
                     jf.denom_dev = ws->rho + (k - 1);
+                    jf.inv_denom_dev = ws->rinv + (k - 1);
                     jf.raw = true;
                     seed = raw_needs_seed ? ws->pbuf : nullptr;
                     wout = ws->V[k];
@@ -1006,7 +1010,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 k_gmres_givens<<<1, 32, 0, sm>>>(ws->ctl, (int)k, nr, ws->R, ws->c, ws->s, ws->z, hcol, reorth, blk,
                                                  want_hist ? ws->hist : nullptr, iter + k, (int)inner_limit,
                                                  &ws->status[slot], p2p ? c->p2p_dev() : P2PDev{}, givens_seq,
-                                                 raw ? ws->rho : nullptr, ws->gram); }
+                                                 raw ? ws->rho : nullptr, ws->gram, ws->rinv); }
                 c->launches++;
                 AK_CUDA(cudaGetLastError());
                 AK_CUDA(cudaEventRecord(ws->ev[slot], sm));
@@ -1304,7 +1308,7 @@ AK_API int ak_krylov_destroy(ak_krylov* ws) {
     for (double* p : ws->chunks) rel(p);
     rel((void*)ws->V_dev);
     rel(ws->R); rel(ws->c); rel(ws->s); rel(ws->z); rel(ws->hcol); rel(ws->hist); rel(ws->rho); rel(ws->gram);
-    rel(ws->ycoef);
+    rel(ws->ycoef); rel(ws->rinv);
     rel(ws->ctl);
     if (ws->status) cudaFreeHost(ws->status);
     for (int i = 0; i < kStatusSlots; ++i)

@@ -45,6 +45,8 @@ struct StencilArgs {
     double* out;
     double* in_write;    // fused divcopy: scaled `in` is stored here (own rows) ; 1-D heat: BC write-back target
     const double* out_scale;  // tangent kernels, un-normalised Krylov basis: out = J(in) / *out_scale (device scalar)
+    const double* out_scale_inv;  // optional: 1 / *out_scale already formed (same bits as __ddiv_rn(1, *out_scale))
+    Divisor dx2d, dy2d;       // dx2, dy2 with their reciprocals, formed on the host
     const double* bminus;     // tangent kernels: out = bminus - J(in)  (restart residual b - A x of gmres!)
     // RED_PROJ: the first projection pass of the blocked Gram-Schmidt sweep folded into the tangent kernel: raw sums
     // <proj[b], out>, b < nproj, of the vector the kernel has just formed (saves re-reading it: 8n bytes per iteration)
@@ -125,11 +127,13 @@ __global__ void __launch_bounds__(kTX, OP == OP_JVP_BRATU_FD ? 4 : (RED == RED_P
     const bool active = x0 < nx;
     const int64_t y0 = (int64_t)blockIdx.y * p.ry;
     const int64_t y1 = (y0 + p.ry < ny) ? y0 + p.ry : ny;
-    const Divisor denom = make_divisor(SCALE ? *p.denom : 1.0);
-    const Divisor dx2 = make_divisor(p.dx2), dy2 = make_divisor(p.dy2);
+    Divisor denom;  // only the fused normalisation (fuse = full) divides by a device scalar
+    if (SCALE) denom = make_divisor(*p.denom);
+    else denom = Divisor{1.0, 1.0, 0};
+    const Divisor dx2 = p.dx2d, dy2 = p.dy2d;
     // un-normalised Krylov basis: J is linear, so J(v / rho) is formed as J(v) * (1 / rho) at the store
     const bool oscale_on = (OP == OP_JVP_BRATU || OP == OP_JVP_HEAT || OP == OP_JVP_BRATU_FD) && p.out_scale != nullptr;
-    const double oscale = oscale_on ? __ddiv_rn(1.0, *p.out_scale) : 1.0;
+    const double oscale = oscale_on ? (p.out_scale_inv != nullptr ? *p.out_scale_inv : __ddiv_rn(1.0, *p.out_scale)) : 1.0;
 
     auto row_ptr = [&](int64_t y) -> const double* {
         if (y < 0) return p.lo;
@@ -360,12 +364,17 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
     const int64_t n = p.nx;
     const int64_t x0 = ((int64_t)blockIdx.x * kT1 + threadIdx.x) * VEC;
     const bool active = x0 < n;
-    const Divisor denom = make_divisor(SCALE ? *p.denom : 1.0);
-    const Divisor dx2 = make_divisor(p.dx2);
+    Divisor denom;  // only the fused normalisation divides by a device scalar
+    if (SCALE) denom = make_divisor(*p.denom);
+    else denom = Divisor{1.0, 1.0, 0};
+    const Divisor dx2 = p.dx2d;
     constexpr bool HEAT = (OP == OP_RES_HEAT || OP == OP_JVP_HEAT || OP == OP_RHS_HEAT);
     constexpr bool FD = (OP == OP_JVP_BRATU_FD);
     const bool oscale_on = (OP == OP_JVP_BRATU || OP == OP_JVP_HEAT || FD) && p.out_scale != nullptr;
-    const double oscale = oscale_on ? __ddiv_rn(1.0, *p.out_scale) : 1.0;
+    const double oscale = oscale_on ? (p.out_scale_inv != nullptr ? *p.out_scale_inv : __ddiv_rn(1.0, *p.out_scale)) : 1.0;
+    // the chunks that hold a global end point of the heat problem (bc! / periodic_bc! act there, du = 0 there)
+    const bool first_chunk = HEAT && x0 == 0 && p.seg_first;
+    const bool last_chunk = HEAT && x0 + VEC == n && p.seg_last;
     // fused finite-difference JVP: second window over u (p.aux, ghosts p.aux_lo / p.aux_hi); u + eps v is never stored
     auto uvalue = [&](int64_t i) -> double {
         if (i < 0) return p.aux_lo ? p.aux_lo[0] : 0.0;
@@ -400,8 +409,8 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
             for (int i = 0; i < VEC; ++i) cur[i] = div_by(cur[i], denom);
         }
         if (HEAT) {  // the global end points take their BC value
-            if (x0 == 0 && p.seg_first) cur[0] = value(0);
-            if (x0 + VEC == n && p.seg_last) cur[VEC - 1] = value(n - 1);
+            if (first_chunk) cur[0] = value(0);
+            if (last_chunk) cur[VEC - 1] = value(n - 1);
         }
     }
     double left = __shfl_up_sync(0xffffffffu, cur[VEC - 1], 1);
@@ -448,8 +457,7 @@ __global__ void __launch_bounds__(kT1) k_stencil1d(const StencilArgs p) {
                 o[i] = __ddiv_rn(__dsub_rn(f1, f0), eps);
             } else {
                 // heat_1D.jl:22: du[i] = a * (u[i+1] - 2u[i] + u[i-1]) / dx^2 ; du[1] = du[end] = 0
-                const int64_t gi = x0 + i;
-                const bool bnd = (gi == 0 && p.seg_first) || (gi == n - 1 && p.seg_last);
+                const bool bnd = (i == 0 && first_chunk) || (i == VEC - 1 && last_chunk);
                 const double du =
                     bnd ? 0.0 : div_by(__dmul_rn(p.a, __dadd_rn(__dsub_rn(e, __dmul_rn(2.0, c)), w)), dx2);
                 if (OP == OP_RES_HEAT) o[i] = __dsub_rn(__dadd_rn(aux[i], __dmul_rn(p.dt, du)), c);
@@ -505,6 +513,8 @@ struct DgArgs {
     double* in_write;
     const double* denom;
     const double* out_scale;  // tangent with an un-normalised Krylov basis: out = J(in) / *out_scale
+    const double* out_scale_inv;  // optional: 1 / *out_scale already formed
+    Divisor mwd;              // mw with its reciprocal, formed on the host
     const double* dot_with;
     double* red_out;
     double* partials;
@@ -531,8 +541,10 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
     const int64_t ne = p.ne;
     const int64_t e = (int64_t)blockIdx.x * kT1 + threadIdx.x;
     const bool active = e < ne;
-    const Divisor denom = make_divisor(SCALE ? *p.denom : 1.0);
-    const Divisor mw = make_divisor(p.mw);
+    Divisor denom;
+    if (SCALE) denom = make_divisor(*p.denom);
+    else denom = Divisor{1.0, 1.0, 0};
+    const Divisor mw = p.mwd;
 
     auto load_elem = [&](int64_t el, double (&r)[4]) {
         ldv<4>((el < 0) ? p.lo : p.in + 4 * el, r);
@@ -590,7 +602,7 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dmul_rn(p.c1, du[i]), raw[i]);
             if (p.out_scale != nullptr) {
-                const double oscale = __ddiv_rn(1.0, *p.out_scale);
+                const double oscale = p.out_scale_inv != nullptr ? *p.out_scale_inv : __ddiv_rn(1.0, *p.out_scale);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) o[i] = __dmul_rn(o[i], oscale);
             }
@@ -928,6 +940,7 @@ static void dg_constants(DgArgs& d, double h) {
         for (int j = 0; j < 4; ++j) d.D[i][j] = M[i][j];
     d.jac = 2.0 / h;
     d.mw = (h / 2.0) * (1.0 / 6.0);
+    d.mwd = make_divisor_host(d.mw);
 }
 
 static int launch_dg(Ctx* ctx, DgArgs& d, bool residual, bool scale, int red) {
@@ -1002,6 +1015,8 @@ static void base_args(Ctx* ctx, const ak_problem* p, StencilArgs& a) {
     a.scheme = p->scheme;
     a.dx2 = p->dx * p->dx;
     a.dy2 = p->dy * p->dy;
+    a.dx2d = make_divisor_host(a.dx2);
+    a.dy2d = make_divisor_host(a.dy2);
     a.lambda = p->lambda;
     a.a = p->a;
     a.dt = p->dt;
@@ -1295,6 +1310,7 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
         d.in = scale ? f->scale_src : v;
         AK_TRY(ghost_1d(ctx, d.in, p->nx, 4, 1, true, &d.lo, &d.hi));
         d.in_write = v; d.denom = f->denom_dev; d.out_scale = raw ? f->denom_dev : nullptr;
+        d.out_scale_inv = raw ? f->inv_denom_dev : nullptr;
         d.out = out; d.dot_with = f->dot_with; d.red_out = red_out;
         d.partials = ctx->partials; d.ticket = ctx->ticket; d.stop = f->stop_flag;
         AK_REQUIRE(al(d.in, 32) && al(v, 32) && al(out, 32) && al(f->dot_with, 32), "DG vectors must be 32-byte aligned");
@@ -1308,6 +1324,7 @@ int launch_jvp(Ctx* ctx, const ak_problem* p, const double* u, double* v, double
     a.in_write = scale ? v : nullptr;
     a.denom = f->denom_dev;
     a.out_scale = raw ? f->denom_dev : nullptr;
+    a.out_scale_inv = raw ? f->inv_denom_dev : nullptr;
     a.out = out;
     a.dot_with = f->dot_with;
     a.red_out = red_out;

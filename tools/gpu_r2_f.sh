@@ -12,6 +12,7 @@ echo "ncu launch list rc=$?"
 $B > gpurun_out/r2f_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"k_mgs_block|k_stencil2d" -s 150 -c 16 -o gpurun_out/r02_prof_block8 $B > gpurun_out/r2f_ncu2.log 2>&1
 echo "ncu set full rc=$?"
+python tools/quick_bench.py > gpurun_out/r2f_quick_bench.txt 2>&1; tail -12 gpurun_out/r2f_quick_bench.txt
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2f_bench_reference.json 2> gpurun_out/r2f_bench_reference.err; echo "ref rc=$?"
 python bench.py --steps 20 --warmup 5 > gpurun_out/r2f_bench_n1.json 2> gpurun_out/r2f_bench_n1.err; echo "bench rc=$?"
 for c in c2 c5; do python bench.py --config $c --steps 10 --warmup 3 > gpurun_out/r2f_bench_$c.json 2> gpurun_out/r2f_bench_$c.err; echo "bench $c rc=$?"; done
