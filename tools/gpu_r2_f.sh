@@ -10,7 +10,7 @@ $B > gpurun_out/r2f_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 520 -c 340 --csv --log-file gpurun_out/r02_launches_block8.csv $B > gpurun_out/r2f_ncu1.log 2>&1
 echo "ncu launch list rc=$?"
 $B > gpurun_out/r2f_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"k_mgs_block|k_stencil2d" -s 150 -c 16 -o gpurun_out/r02_prof_block8 $B > gpurun_out/r2f_ncu2.log 2>&1
+ncu --set full --clock-control none -k regex:"k_mgs_block|k_stencil2d" -s 152 -c 8 -o gpurun_out/r02_prof_block8 $B > gpurun_out/r2f_ncu2.log 2>&1
 echo "ncu set full rc=$?"
 python tools/quick_bench.py > gpurun_out/r2f_quick_bench.txt 2>&1; tail -12 gpurun_out/r2f_quick_bench.txt
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2f_bench_reference.json 2> gpurun_out/r2f_bench_reference.err; echo "ref rc=$?"
