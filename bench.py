@@ -492,6 +492,7 @@ def main():
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")  # for waits that must not spin on a host core (the CPU-baseline leg)
     ctx = nk.get_context(local_rank)
     if world > 1:
         ids = [nk.comm_unique_id() if rank == 0 else None]
@@ -638,7 +639,12 @@ def main():
         e2e = {"value": e_its * world / float(te[0]), "unit": cfg["unit"], "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 8 * n * world, "steps": e_steps, "ms_per_step": 1e3 * float(te[0]) / e_steps,
                "api": "ak_newton_solve_host (pinned host u in/out, workspace allocated per call like the reference)",
-               "host_copy_GBs_per_rank": (h2d + 8 * n * world) / world / 1e9 / (float(te[0]) / e_steps),
+               # time the host<->device copies (and the per-call workspace set-up) add to a step, and the copy rate it implies
+               "copy_ms_per_step": 1e3 * float(te[0]) / e_steps - ms_max / args.steps,
+               "host_copy_GBs_per_rank": (h2d + 8 * n * world) / world / 1e9 /
+                                         max(float(te[0]) / e_steps - ms_max / args.steps * 1e-3, 1e-9),
+               "host_copy_GBs_all_ranks": (h2d + 8 * n * world) / 1e9 /
+                                          max(float(te[0]) / e_steps - ms_max / args.steps * 1e-3, 1e-9),
                "final_n_res": st.n_res}
         lib.ak_host_free(hp)
         if W.timedep:
@@ -672,7 +678,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_baseline_leg(name, cfg)
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=cpu_group)  # the other ranks block in a socket wait meanwhile: they do not take cores from the oracle
 
     if rank == 0:
         out = {

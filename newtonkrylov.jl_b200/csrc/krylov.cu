@@ -48,6 +48,7 @@ struct ak_krylov {
     ak::Ctx* ctx = nullptr;
     int32_t algo = AK_ALGO_GMRES;
     int64_t n = 0;
+    int64_t n_global = 0;  // unknowns over all ranks: Krylov.jl's default itmax = 2n is a property of the whole system
     int32_t mem = 20;
     int64_t max_basis = 0;
     // vectors
@@ -715,7 +716,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     const bool want_hist = (hist_host != nullptr && hist_cap > 0) || o->history;
     cudaStream_t sm = c->stream;
 
-    int64_t itmax = o->itmax == 0 ? 2 * n : o->itmax;
+    int64_t itmax = o->itmax == 0 ? 2 * ws->n_global : o->itmax;  // identical on every rank (the ranks must stop together)
     double* x = ws->x;
     // right-preconditioned gmres!: x += N (V y) goes through a separate xr; otherwise the combine kernel adds to x directly
     const bool xr_separate = precond && !flexible;
@@ -1083,7 +1084,7 @@ static int cg_solve(ak_krylov* ws, const ak_problem* prob, const double* u, cons
     const int64_t n = ws->n;
     cudaStream_t sm = c->stream;
     const bool want_hist = (hist_host != nullptr && hist_cap > 0) || o->history;
-    const int64_t itmax = o->itmax == 0 ? 2 * n : o->itmax;
+    const int64_t itmax = o->itmax == 0 ? 2 * ws->n_global : o->itmax;
     if (!ws->hcol) AK_TRY(ws_grow_scalars(ws, 4));
     if (want_hist) AK_TRY(ws_grow_hist(ws, 257));
     // kwarg M of cg! (a symmetric positive definite preconditioner): z = M r, gamma = <r, z>, p = z + beta p, the
@@ -1265,6 +1266,25 @@ AK_API int ak_krylov_create(ak_ctx* ctx, int32_t algo, int64_t n, int32_t memory
     ws->ctx = &ctx->c;
     ws->algo = algo;
     ws->n = n;
+    ws->n_global = n;
+    if (ctx->c.nranks > 1) {
+        // collective: every rank creates its workspace at the same point of the program (like the reference's
+        // krylov_workspace call inside newton_krylov!); local sizes may differ by a row / a point between ranks
+        Ctx* c = &ctx->c;
+        const double mine = (double)n;
+        double tot = 0.0;
+        int rcg = AK_OK;
+        if (cudaMemcpyAsync(c->dscal + 60, &mine, sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rcg = AK_ERR_CUDA;
+        if (rcg == AK_OK) rcg = allreduce_sum(c, c->dscal + 60, 1);
+        if (rcg == AK_OK && cudaMemcpyAsync(&tot, c->dscal + 60, sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rcg = AK_ERR_CUDA;
+        if (rcg == AK_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rcg = AK_ERR_CUDA;
+        if (rcg != AK_OK) {
+            set_error("ak_krylov_create: could not sum the problem size over the ranks");
+            delete ws;
+            return rcg;
+        }
+        ws->n_global = (int64_t)(tot + 0.5);
+    }
     ws->mem = memory;
     ws->max_basis = max_basis;
     int rc = AK_OK;

@@ -563,27 +563,44 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
             u[i] = RESIDUAL ? raw[i] : __dmul_rn(p.c0, raw[i]);
         }
     }
+    // Neighbour coupling: within a warp by shuffles, between the warps of a block through shared memory (the same
+    // values the neighbouring thread holds), across blocks / the periodic wrap / rank boundaries from global memory.
+    // (One thread per warp re-deriving its left neighbour from global memory stalled the whole warp: 77-80 % of peak.)
+    __shared__ double s_u0[kT1 / 32], s_t3[kT1 / 32];
+    const int wid = threadIdx.x >> 5;
+    if (lane == 0) s_u0[wid] = u[0];
+    __syncthreads();
     // D1p: needs first node of the element to the right
     double u_next0 = __shfl_down_sync(0xffffffffu, u[0], 1);
     if (active && (lane == 31 || e + 1 >= ne)) {
-        const int64_t en = (e + 1 == ne) ? 0 : e + 1;
-        double t = (e + 1 == ne && p.hi != nullptr) ? p.hi[0] : p.in[4 * en];
-        if (SCALE) t = div_by(t, denom);
-        u_next0 = RESIDUAL ? t : __dmul_rn(p.c0, t);
+        if (e + 1 < ne && wid + 1 < kT1 / 32) {
+            u_next0 = s_u0[wid + 1];
+        } else {
+            const int64_t en = (e + 1 == ne) ? 0 : e + 1;
+            double t = (e + 1 == ne && p.hi != nullptr) ? p.hi[0] : p.in[4 * en];
+            if (SCALE) t = div_by(t, denom);
+            u_next0 = RESIDUAL ? t : __dmul_rn(p.c0, t);
+        }
     }
     double t1[4] = {0, 0, 0, 0};
     if (active) {
         dg_local(p.D, p.jac, u, t1);
         t1[3] = __dadd_rn(t1[3], div_by(__dsub_rn(u_next0, u[3]), mw));
     }
+    if (lane == 31) s_t3[wid] = t1[3];
+    __syncthreads();
     // D1m: needs last node of (D1p u) of the element to the left
     double t_prev3 = __shfl_up_sync(0xffffffffu, t1[3], 1);
     if (active && lane == 0) {
-        const int64_t ep = (e == 0) ? ((p.lo != nullptr) ? -1 : ne - 1) : e - 1;
-        double up[4], tp[4];
-        load_elem(ep, up);
-        dg_local(p.D, p.jac, up, tp);
-        t_prev3 = __dadd_rn(tp[3], div_by(__dsub_rn(u[0], up[3]), mw));
+        if (wid > 0) {
+            t_prev3 = s_t3[wid - 1];
+        } else {
+            const int64_t ep = (e == 0) ? ((p.lo != nullptr) ? -1 : ne - 1) : e - 1;
+            double up[4], tp[4];
+            load_elem(ep, up);
+            dg_local(p.D, p.jac, up, tp);
+            t_prev3 = __dadd_rn(tp[3], div_by(__dsub_rn(u[0], up[3]), mw));
+        }
     }
     double acc = 0.0;
     if (active) {

@@ -179,8 +179,24 @@ def run_linear_extras(ctx, rank, world, rng, tag):
         x, st = solve("gmres", memory=5, fuse=fuse, **kw)
         assert (st.niter, st.solved, st.npass) == (sr["niter"], sr["solved"], sr["npass"]), (fuse, st.niter, sr)
         assert np.max(np.abs(np.array(st.residuals) - hr)) <= 1e-9 * hr[0] and rel(x, xr[sl]) < 1e-8, fuse
+    # Krylov.jl's default itmax = 2n counts the unknowns of the WHOLE system: with local sizes that differ between the
+    # ranks (here 6 * world + 1 points) every rank must stop at the same iteration (a rank-local 2n deadlocked 8 ranks)
+    d1 = P.generic(P.bratu1d(6 * world + 1))
+    g0, n1 = nk.dist.slab_partition(d1["nx"], world, rank)
+    s1 = slice(g0, g0 + n1)
+    po1 = P.oracle_problem(O, d1)
+    b1 = rng.standard_normal(d1["nx"])
+    kw = dict(rtol=1e-15, atol=0.0, restart=True)  # GMRES(3) stagnates: the solve runs into the default itmax
+    xr, sr, hr = O.krylov_solve(po1, d1["u0"], b1, memory=3, hist_cap=1000, **kw)
+    for fuse in ("mgs", "block8"):
+        u = nk.DeviceVector.from_numpy(d1["u0"][s1], ctx)
+        res = u.zero()
+        ws = nk.krylov_workspace("gmres", nk.KrylovConstructor(res), memory=3)
+        nk.krylov_solve_(ws, nk.JacobianOperator(nk.bratu_, res, u, (d1["dx"], d1["lam"])),
+                         nk.DeviceVector.from_numpy(b1[s1], ctx), fuse=fuse, **kw)
+        assert ws.stats.niter == sr["niter"] and (sr["solved"] or sr["niter"] == 2 * d1["nx"]), (fuse, ws.stats.niter, sr)
     if rank == 0:
-        print(f"[multi-gpu x{world} {tag}] cg + reorthogonalised blocked gmres: ok", flush=True)
+        print(f"[multi-gpu x{world} {tag}] cg + reorthogonalised blocked gmres + default itmax: ok", flush=True)
 
 
 def run_cases(ctx, rank, world, rng, tag):

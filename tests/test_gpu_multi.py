@@ -22,5 +22,5 @@ def test_slab_decomposition_matches_oracle(nk, world):
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
     # every family of cases reported in: 1-D segments, Midpoint/Trapezoid, 2-D slabs, with NCCL and with peer memory
     for needle in ("nccl] dg: ok", "heat2d midpoint/trapezoid: ok", "nccl] heat2d_periodic: ok", "p2p] bratu2d: ok",
-                   "p2p] dg: ok", "p2p] cg + reorthogonalised blocked gmres: ok", "nccl] cg + reorthogonalised blocked gmres: ok"):
+                   "p2p] dg: ok", "p2p] cg + reorthogonalised blocked gmres + default itmax: ok", "nccl] cg + reorthogonalised blocked gmres + default itmax: ok"):
         assert needle in r.stdout, (needle, r.stdout[-3000:])
