@@ -53,7 +53,8 @@ LAMBDA = 3.5
 MEMORY = 20
 ITMAX = 40
 METRIC = "gmres_iters_per_sec"
-FUSE_CODE = {"none": 0, "mgs": 1, "full": 2, "pair": 3, "block4": 4, "block8": 5}
+FUSE_CODE = {"none": 0, "mgs": 1, "full": 2, "pair": 3, "block4": 4, "block8": 5, "sweep": 6}
+SWEEP_KMAX = 24  # kSwKMax of csrc/sweep.h
 LGL = np.array([-1.0, -1.0 / np.sqrt(5.0), 1.0 / np.sqrt(5.0), 1.0])
 
 CONFIGS = {
@@ -182,7 +183,9 @@ class Workload:
     def step_bytes(self):
         """Algorithmic bytes (unique reads + writes, 8-byte reals) one step moves at this fusion level."""
         n, cfg = self.n, self.cfg
-        blk = {"pair": 2, "block4": 4, "block8": 8}.get(self.fuse, 0)
+        if self.sweep_active():
+            return 8.0 * n * (self.sweep_units() + self.boundary_units())
+        blk = {"pair": 2, "block4": 4, "block8": 8, "sweep": 8}.get(self.fuse, 0)
         sweeps = 2 if cfg["reorth"] else 1
         units = 0.0
         ncyc = ITMAX // MEMORY
@@ -202,13 +205,40 @@ class Workload:
                     units += sweeps * k * (2 + 3) + 1 + 2                # dot 16n, axpy 24n per step; nrm2; divcopy
                 else:
                     units += sweeps * k * 4 - (1 if self.fuse == "full" else 0) + 1 + 2
-            units += MEMORY + 2                                           # x (+)= V y
+        return 8.0 * n * (units + self.boundary_units())
+
+    def boundary_units(self):
+        """8n-byte units of a step outside the Arnoldi iterations: solution updates, restart residual, Newton bookkeeping."""
+        cfg = self.cfg
+        ncyc = ITMAX // MEMORY
+        units = ncyc * (MEMORY + 2)                                       # x (+)= V y
         units += (ncyc - 1) * (cfg["jvp_bytes"] / 8.0 + 1)                # restart residual b - J x (+ b)
         units += 2 + 1                                                    # w = copy(b), ||w||^2
         units += 2 + 3 + cfg["res_bytes"] / 8.0                           # copy(res), u -= d, F(u)
         if self.timedep:
             units += 2 + cfg["res_bytes"] / 8.0                           # u = copy(u_n), F(u)
-        return 8.0 * n * units
+        return units
+
+    def sweep_active(self):
+        return self.fuse == "sweep" and self.cfg["kind"] in ("bratu2d", "heat2d") and MEMORY <= SWEEP_KMAX
+
+    def sweep_units(self):
+        """8n-byte units of the sweep kernels of one step (csrc/sweep.cu): the opening sweep of a cycle reads S_0 (+ lambda
+        e^u) and writes W; iteration k reads S_0..S_{k-1} and W, writes S_k and, unless it is the last of the cycle, reads
+        lambda e^u and writes the next W; re-orthogonalisation adds a sweep without the tangent (k + 2)."""
+        cfg = self.cfg
+        tang = cfg["jvp_bytes"] / 8.0 - 1.0   # units the tangent adds to a sweep: (lambda e^u) + W out
+        units = 0.0
+        for _ in range(ITMAX // MEMORY):
+            units += 1 + tang
+            for k in range(1, MEMORY + 1):
+                if cfg["reorth"]:
+                    units += k + 2
+                units += k + 2 + (tang if k < MEMORY else 0)
+        return units
+
+    def sweep_launches(self):
+        return (ITMAX // MEMORY) * (1 + MEMORY * (2 if self.cfg["reorth"] else 1))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -341,7 +371,7 @@ def cpu_baseline_leg(name, cfg):
 
 # ---------------------------------------------------------------------------------------------
 PROF_NAMES = ["mgs_axpy_dot", "mgs_axpy_norm", "mgs_axpy", "dot", "sumsq", "jvp", "residual", "elementwise",
-              "basis_combine", "scalar", "mgs_pair", "mgs_pair_edge", "mgs_block_final"]
+              "basis_combine", "scalar", "mgs_pair", "mgs_pair_edge", "mgs_block_final", "sweep"]
 NPROF = len(PROF_NAMES)
 
 
@@ -384,7 +414,7 @@ def kernel_table(W, prof, ms, peak):
             continue
         e = {"launches": cnt, "ms": round(kms, 3), "share_of_step_time": round(kms / ms, 4)}
         b = fixed.get(PROF_NAMES[c])  # (restart residuals b - J x read one more vector: counted at the plain JVP's bytes)
-        if PROF_NAMES[c] == "jvp" and W.cfg["kind"] in ("bratu2d", "heat2d") and W.fuse in ("pair", "block4", "block8"):
+        if PROF_NAMES[c] == "jvp" and W.cfg["kind"] in ("bratu2d", "heat2d") and W.fuse in ("pair", "block4", "block8", "sweep"):
             b = None  # the 2-D tangent launches also carry the first projection pass: bytes per launch vary with k
         if b:
             e["GBs"] = round(b / (kms / cnt * 1e-3) / 1e9, 1)
@@ -552,6 +582,15 @@ def main():
     elif args.fuse == "block8":
         dom, dom_bytes = 10, 144 * n
         dom_name = "k_mgs_block<8,8> (w -= sum_b c_b S_b ; 8 projections <S'_b,w>): eight Gram-Schmidt steps per pass"
+    elif args.fuse == "sweep" and W.sweep_active():
+        # every launch of the template handles a different basis size k: bytes per launch = the mean over a step
+        dom, dom_bytes = 13, 8.0 * n * W.sweep_units() / W.sweep_launches()
+        dom_name = ("k_sweep<KB, stencil> (z = W/rho - sum_j c_j S_j ; ||z||^2, <S_j,z> ; y = J z ; <S_j,y>, <z,y>): one pass over the "
+                    "basis per GMRES iteration, 8n(k+4) bytes at basis size k; achieved = mean bytes per launch / mean "
+                    "launch time over the %d launches of a step (k = 0..%d)" % (W.sweep_launches(), MEMORY))
+    elif args.fuse == "sweep":
+        dom, dom_bytes = 10, 144 * n
+        dom_name = "k_mgs_block<8,8> (fuse = sweep applies to the 2-D problems; this config runs the eight-step blocked passes)"
     elif args.fuse == "none":
         dom, dom_bytes = 2, 24 * n
         dom_name = "k_mgs_step<AXPY> (w -= h_i v_i)"
@@ -562,7 +601,7 @@ def main():
     traffic, traffic_src = None, None
     try:  # committed constant: dram bytes per launch of this kernel from the ncu --set full capture under profiles/
         kt = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json"))).get(args.fuse)
-        if kt and kt["n"] == n:
+        if kt and kt["n"] == n and not (args.fuse == "sweep" and not W.sweep_active()):
             traffic = kt["dram_bytes_per_launch"]
             traffic_src = "committed constant from profiles/kernel_traffic.json (ncu --set full capture), not measured in this run"
     except Exception:
@@ -571,6 +610,7 @@ def main():
     step_gbs = step_bytes * args.steps / (ms * 1e-3) / 1e9
     gs_ms = sum(prof[c][1] for c in (0, 1, 2, 10, 11, 12))
     family = {
+        "one_sweep_iterations (k_sweep: Gram-Schmidt update + norms + tangent + projections)": round(prof[13][1] / ms, 4),
         "gram_schmidt_passes (k_mgs_block / k_mgs_step, all instantiations)": round(gs_ms / ms, 4),
         "jvp (k_stencil*/k_dg tangent; 2-D: with the first projection pass folded in)": round(prof[5][1] / ms, 4),
         "cycle_boundary (basis_combine + element-wise + norms)": round((prof[8][1] + prof[7][1] + prof[4][1] + prof[3][1]) / ms, 4),

@@ -252,7 +252,11 @@ enum {
     AK_FUSE_BLOCK4 = 4,/* same with four steps per sweep: h_b = <y_b,w> - sum_{a<b} h_a <y_b,y_a>
                           (20n bytes per step); the Gram entries <y_b,y_a> of a block are measured once,
                           by the final pass of the iteration that finishes y_b, and cached          */
-    AK_FUSE_BLOCK8 = 5 /* eight steps per sweep (18n bytes per step)                                */
+    AK_FUSE_BLOCK8 = 5,/* eight steps per sweep (18n bytes per step)                                */
+    AK_FUSE_SWEEP = 6  /* ONE pass over the basis per iteration (2-D problems): the Gram-Schmidt update of iteration k,
+                        * ||w||, the tangent J w of iteration k+1 and all its projections in the same kernel;
+                        * coefficients by forward substitution with the cached Gram matrix (8n(k+4) bytes per
+                        * iteration; iterations beyond 24 per pass and all other problems run as BLOCK8)       */
     /* PAIR and BLOCK4 keep the Krylov basis UN-NORMALISED: iteration k works in place on basis slot k, whose
      * finished content is the stored vector rho_k v_k (rho_k = Hbis); gmres!'s `V[k+1] = w / Hbis` is never
      * materialised, the scales enter the Gram-Schmidt coefficients and the JVP divides its result by rho_k

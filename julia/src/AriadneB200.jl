@@ -73,7 +73,7 @@ const AK_JVP_ANALYTIC, AK_JVP_FD_FUSED, AK_JVP_FD = Int32.(0:2)
 const AK_ALGO = Dict(:gmres => Int32(0), :cg => Int32(1), :fgmres => Int32(2))
 const AK_PRECOND_NONE, AK_PRECOND_INNER_GMRES, AK_PRECOND_USER, AK_PRECOND_JACOBI, AK_PRECOND_TRIDIAG_LU = Int32.(0:4)
 const AK_FORCING_NONE, AK_FORCING_FIXED, AK_FORCING_EW = Int32.(0:2)
-const AK_FUSE = Dict(:none => Int32(0), :mgs => Int32(1), :full => Int32(2), :pair => Int32(3), :block4 => Int32(4), :block8 => Int32(5))
+const AK_FUSE = Dict(:none => Int32(0), :mgs => Int32(1), :full => Int32(2), :pair => Int32(3), :block4 => Int32(4), :block8 => Int32(5), :sweep => Int32(6))
 fuse_code(f::Symbol) = AK_FUSE[f]
 fuse_code(f::Integer) = Int32(f)
 

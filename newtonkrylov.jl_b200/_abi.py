@@ -19,7 +19,7 @@ AK_STEADY, AK_EULER, AK_MIDPOINT, AK_TRAPEZOID = range(4)
 AK_JVP_ANALYTIC, AK_JVP_FD_FUSED, AK_JVP_FD = 0, 1, 2
 AK_ALGO_GMRES, AK_ALGO_CG, AK_ALGO_FGMRES = 0, 1, 2
 AK_PRECOND_NONE, AK_PRECOND_INNER_GMRES, AK_PRECOND_USER, AK_PRECOND_JACOBI, AK_PRECOND_TRIDIAG_LU = 0, 1, 2, 3, 4
-AK_FUSE_NONE, AK_FUSE_MGS, AK_FUSE_FULL, AK_FUSE_PAIR, AK_FUSE_BLOCK4, AK_FUSE_BLOCK8 = 0, 1, 2, 3, 4, 5
+AK_FUSE_NONE, AK_FUSE_MGS, AK_FUSE_FULL, AK_FUSE_PAIR, AK_FUSE_BLOCK4, AK_FUSE_BLOCK8, AK_FUSE_SWEEP = 0, 1, 2, 3, 4, 5, 6
 AK_FORCING_NONE, AK_FORCING_FIXED, AK_FORCING_EW = 0, 1, 2
 
 c_double_p = C.POINTER(C.c_double)

@@ -7,8 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libariadne_b200.so")
-SOURCES = ["context.cu", "blas1.cu", "stencil.cu", "krylov.cu", "newton.cu", "user.cu", "precond.cu"]
-HEADERS = ["ak_internal.h", "common.cuh", os.path.join("..", "..", "include", "ariadne_b200.h")]
+SOURCES = ["context.cu", "blas1.cu", "stencil.cu", "krylov.cu", "newton.cu", "user.cu", "precond.cu", "sweep.cu"]
+HEADERS = ["ak_internal.h", "common.cuh", "sweep.h", os.path.join("..", "..", "include", "ariadne_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -84,7 +84,8 @@ enum ProfClass {
     PK_MGS_PAIR = 10,      // full blocked pass: w -= sum_b h_b v_b ; projections on the next block   8n(2+2R): 48n (R=2), 80n (R=4)
     PK_MGS_PAIR_EDGE = 11, // first / ragged passes of the blocked sweep
     PK_MGS_BLOCK_FINAL = 12, // final pass of the blocked sweep: w -= sum_b c_b S_b ; ||w||^2 and the new Gram entries
-    PK_NUM = 13
+    PK_SWEEP = 13,           // one-sweep GMRES iteration: update + norms + tangent + all projections   8n(k + 4)
+    PK_NUM = 14
 };
 
 struct Ctx {
@@ -131,6 +132,10 @@ struct Ctx {
     // second set of ghost slots, used by the stand-alone exchanges (residuals, tangents outside the blocked sweep)
     double* p2p_ghost_local(int parity, int hi) const;
     double* p2p_ghost_of(int peer, int parity, int hi) const;
+    // one-sweep GMRES (sweep.cu): mailboxes for its 2k + 2 sums and one pair of ghost rows per basis vector / W buffer
+    double* p2p_swmail_of(int peer) const;
+    double* p2p_swghost_local(int slot, int hi) const;
+    double* p2p_swghost_of(int peer, int slot, int hi) const;
 };
 
 // stream-ordered allocation from the context's private pool (freed with cudaFreeAsync on the context's stream)

@@ -12,6 +12,7 @@
 
 #include "ak_internal.h"
 #include "common.cuh"
+#include "sweep.h"
 
 namespace ak {
 
@@ -175,6 +176,23 @@ static int p2p_exchange(Ctx* ctx, const double* v, int64_t n, int cnt_up, int cn
     return AK_OK;
 }
 
+// One-sweep GMRES on slabs: the opening vector of a cycle (r0) did not come out of a sweep, so its boundary rows are
+// pushed into the neighbours' ghost rows of sweep slot `slot` here (peer stores + the all-to-all signal of k_push_ghost).
+int sweep_push_rows(Ctx* ctx, const double* v, int64_t nx, int64_t ny, int32_t bc, int slot) {
+    const int P = ctx->nranks, r = ctx->rank;
+    if (P <= 1) return AK_OK;
+    AK_REQUIRE(ctx->p2p_on && nx <= ctx->p2p_halo_cap && slot >= 0 && slot < kSwGhostSlots, "sweep_push_rows: peer memory not set up for this row length");
+    const bool periodic = (bc == AK_BC_PERIODIC);
+    const int down = (r > 0) ? r - 1 : (periodic ? P - 1 : -1);
+    const int up = (r < P - 1) ? r + 1 : (periodic ? 0 : -1);
+    const unsigned long long seq = ++ctx->p2p_seq;
+    k_push_ghost<<<1, 1024, 0, ctx->stream>>>(v, nx * ny, (int)nx, (int)nx, up >= 0 ? ctx->p2p_swghost_of(up, slot, 0) : nullptr,
+                                              down >= 0 ? ctx->p2p_swghost_of(down, slot, 1) : nullptr, ctx->p2p_dev(), seq);
+    ctx->launches++;
+    AK_CUDA(cudaGetLastError());
+    return AK_OK;
+}
+
 int collective_verdict(Ctx* ctx, int* rc) {
     if (ctx->nranks <= 1) return AK_OK;
     const double mine = (*rc != AK_OK) ? 1.0 : 0.0;
@@ -268,6 +286,17 @@ double* Ctx::p2p_halo_of(int peer, int parity, int hi) const {
 }
 double* Ctx::p2p_ghost_local(int parity, int hi) const { return p2p_halo_local(parity, hi) + (size_t)4 * p2p_halo_cap; }
 double* Ctx::p2p_ghost_of(int peer, int parity, int hi) const { return p2p_halo_of(peer, parity, hi) + (size_t)4 * p2p_halo_cap; }
+// one-sweep GMRES: [sweep mailboxes | kSwGhostSlots x {lo, hi} ghost rows] behind the 8 rows above
+static inline size_t p2p_swmail_doubles(int nranks) { return (size_t)kMailSlots * nranks * kSwMailRec; }
+static inline size_t p2p_sw_offset(int nranks, int64_t hcap) { return p2p_mail_doubles(nranks) + (size_t)8 * hcap; }
+double* Ctx::p2p_swmail_of(int peer) const { return (double*)p2p_peer_block[peer] + p2p_sw_offset(nranks, p2p_halo_cap); }
+double* Ctx::p2p_swghost_local(int slot, int hi) const {
+    return p2p_block + p2p_sw_offset(nranks, p2p_halo_cap) + p2p_swmail_doubles(nranks) + ((size_t)slot * 2 + hi) * p2p_halo_cap;
+}
+double* Ctx::p2p_swghost_of(int peer, int slot, int hi) const {
+    return (double*)p2p_peer_block[peer] + p2p_sw_offset(nranks, p2p_halo_cap) + p2p_swmail_doubles(nranks) +
+           ((size_t)slot * 2 + hi) * p2p_halo_cap;
+}
 
 // ---- HaloVector layout bridge -----------------------------------------------------------
 __global__ void k_halo_pack(double* __restrict__ compact, const double* __restrict__ padded, int64_t nx, int64_t ny) {
@@ -563,7 +592,8 @@ AK_API int ak_comm_enable_p2p(ak_ctx* ctx, int64_t halo_doubles) {
     const int P = c->nranks;
     int64_t hcap = (halo_doubles + 3) & ~int64_t(3);
     if (hcap < 8) hcap = 8;  // the 1-D ghost exchanges move up to 8 values
-    const size_t doubles = p2p_mail_doubles(P) + (size_t)8 * hcap;  // mailboxes, 4 halo rows, 4 stand-alone ghost slots
+    // mailboxes, 4 halo rows, 4 stand-alone ghost slots; sweep mailboxes and one pair of ghost rows per basis vector
+    const size_t doubles = p2p_mail_doubles(P) + (size_t)8 * hcap + p2p_swmail_doubles(P) + (size_t)kSwGhostSlots * 2 * hcap;
     // cudaMalloc (not the stream-ordered pool): IPC handles exist only for plain allocations
     AK_CUDA(cudaMalloc(&c->p2p_block, sizeof(double) * doubles));
     AK_CUDA(cudaMemset(c->p2p_block, 0, sizeof(double) * doubles));

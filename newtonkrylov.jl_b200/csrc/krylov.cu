@@ -19,6 +19,7 @@
 
 #include "ak_internal.h"
 #include "common.cuh"
+#include "sweep.h"
 
 namespace ak {
 
@@ -71,6 +72,9 @@ struct ak_krylov {
     double* rho = nullptr;  // un-normalised basis (blocked sweeps): stored V[i] = rho[i] * v_i
     double* rinv = nullptr; // 1 / rho[i], formed once by the scalar kernels (the tangent kernels multiply their result by it)
     double* gram = nullptr; // blocked sweeps: <V[i], V[a]> for the earlier vectors a of V[i]'s own block (kBlkMax per i)
+    // one-sweep Gram-Schmidt (sweep.cu): sums of the last sweep, column of H under construction, update multipliers,
+    // scaled Gram matrix <v_j, v_a> of the cycle
+    double *sw_sums = nullptr, *sw_h = nullptr, *sw_c = nullptr, *sw_gam = nullptr;
     int64_t hist_cap = 0;
     ak::KrylovCtl* ctl = nullptr;
     ak::KrylovStatus* status = nullptr;  // pinned
@@ -113,6 +117,91 @@ __global__ void k_gmres_begin(KrylovCtl* ctl, const double* sumsq, double* z, do
 }
 
 __device__ __forceinline__ double sgn(double x) { return (double)((x > 0.0) - (x < 0.0)); }
+
+// Tail of one GMRES iteration (gmres! steps 6-8), shared by the Givens kernels of the pass-wise and of the one-sweep
+// Gram-Schmidt: the previous reflections applied to the new column R[nr..nr+k), Krylov.jl's sym_givens on
+// (R[nr+k-1], Hbis), the update of z and the stopping tests.  One warp; lane 0 does the (sequential) arithmetic, the
+// warp prefetches 32 rotation coefficients and column entries at a time.  hh = ||q||^2 (valid on lane 0).
+// Returns the stop verdict on lane 0.
+__device__ __forceinline__ int givens_tail(int lane, KrylovCtl* ctl, int k, int64_t nr, double* R, double* c, double* s,
+                                           double* z, double hh, double* rho_vec, double* rinv_vec, double* hist,
+                                           int64_t hist_pos, int inner_limit, KrylovStatus* st, double* s_c, double* s_s,
+                                           double* s_r) {
+    double cur = 0.0;
+    if (lane == 0) cur = R[nr];
+    // previous reflections applied to the new column (gmres! step 6), 32 at a time: lane 0 carries the running entry,
+    // the warp prefetches c_i, s_i and the untouched column entries r_{i+1}
+    for (int base = 0; base + 1 < k; base += 32) {
+        const int i = base + lane;
+        if (i + 1 < k) {
+            s_c[lane] = c[i];
+            s_s[lane] = s[i];
+            s_r[lane] = R[nr + i + 1];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const int cnt = (k - 1 - base) < 32 ? (k - 1 - base) : 32;
+            for (int q = 0; q < cnt; ++q) {
+                const double rn = s_r[q];
+                const double Rt = s_c[q] * cur + s_s[q] * rn;
+                const double nx = s_s[q] * cur - s_c[q] * rn;
+                R[nr + base + q] = Rt;
+                cur = nx;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane != 0) return 0;
+    const double Hbis = sqrt(hh);
+    if (rho_vec) { rho_vec[k] = Hbis; rinv_vec[k] = __ddiv_rn(1.0, Hbis); }  // the finished w of this iteration IS the stored basis vector k
+    const double a = cur, b = Hbis;
+    double ck, sk, rho;
+    if (b == 0.0) {
+        ck = (a == 0.0) ? 1.0 : sgn(a);
+        sk = 0.0;
+        rho = fabs(a);
+    } else if (a == 0.0) {
+        ck = 0.0;
+        sk = sgn(b);
+        rho = fabs(b);
+    } else if (fabs(b) > fabs(a)) {
+        const double t = a / b;
+        sk = sgn(b) / sqrt(1.0 + t * t);
+        ck = sk * t;
+        rho = b / sk;
+    } else {
+        const double t = b / a;
+        ck = sgn(a) / sqrt(1.0 + t * t);
+        sk = ck * t;
+        rho = a / ck;
+    }
+    c[k - 1] = ck;
+    s[k - 1] = sk;
+    R[nr + k - 1] = rho;
+    const double zeta = sk * z[k - 1];
+    z[k - 1] = ck * z[k - 1];
+    const double rNorm = fabs(zeta);
+    if (hist) hist[hist_pos] = rNorm;
+    const int mach = (rNorm + 1.0 <= 1.0);
+    const int solved = (rNorm <= ctl->eps) || mach;
+    const int breakdown = (Hbis <= ctl->btol);
+    const int tired = (k >= inner_limit);
+    ctl->rNorm = rNorm;
+    ctl->Hbis = Hbis;
+    ctl->solved = solved;
+    ctl->breakdown = breakdown;
+    ctl->inner_iter = k;
+    const int stop = solved || breakdown || tired;
+    if (!stop) z[k] = zeta;
+    ctl->stop = stop;
+    st->rNorm = rNorm;
+    st->Hbis = Hbis;
+    st->iter = k;
+    st->stop = stop;
+    st->solved = solved;
+    st->breakdown = breakdown;
+    return stop;
+}
 
 // Krylov.jl sym_givens (real), then the update of iteration k (1-based) — gmres! steps 6-8.
 // One warp.  Lane 0 does the (sequential) scalar arithmetic; the other lanes only prefetch: every run of global loads the
@@ -193,86 +282,129 @@ __global__ void __launch_bounds__(32) k_gmres_givens(KrylovCtl* ctl, int k, int6
         for (int i = lane; i < k; i += 32) R[nr + i] = reorth ? hcol[i] + h2[i] : hcol[i];
     }
     __syncwarp();
-    double hh = 0.0, cur = 0.0;
+    double hh = 0.0;
     if (lane == 0) {
         hh = blk > 0 ? hcol[kBlkSums * rec_final] : (reorth ? hcol[(k + 1) + k] : hcol[k]);
         // the vector finished by this iteration is stored as basis vector k; when it joins the last block (block not
         // full yet) its Gram entries with that block's vectors were measured by the final pass: cache them
         if (blk > 0 && mlast < blk)
             for (int a = 0; a < mlast; ++a) gram[(size_t)k * kBlkMax + a] = hcol[kBlkSums * rec_final + 1 + a];
-        cur = R[nr];
     }
-    // previous reflections applied to the new column (gmres! step 6), 32 at a time: lane 0 carries the running entry,
-    // the warp prefetches c_i, s_i and the untouched column entries r_{i+1}
-    for (int base = 0; base + 1 < k; base += 32) {
-        const int i = base + lane;
-        if (i + 1 < k) {
-            s_c[lane] = c[i];
-            s_s[lane] = s[i];
-            s_r[lane] = R[nr + i + 1];
+    givens_tail(lane, ctl, k, nr, R, c, s, z, hh, rho_vec, rinv_vec, hist, hist_pos, inner_limit, st, s_c, s_s, s_r);
+}
+
+// Scalar step of the one-sweep Gram-Schmidt (fuse = AK_FUSE_SWEEP, sweep.cu).  One warp.
+//   mode 0  after the opening sweep of a cycle (k = 0): only the multipliers of iteration 1
+//   mode 1  after the first sweep of a re-orthogonalised iteration k: multipliers of its second sweep (gmres! step 5)
+//   mode 2  after the (last) sweep of iteration k: rho_k, row k of the Gram matrix, column k of R, Givens, stopping
+//           tests, then the multipliers of iteration k + 1 from the projections the same sweep measured
+// sums (layout sweep.h): [0] ||z||^2, [1] <z,y>, [2 + j] g_j = <S_j, z>, [2 + kSwKMax + j] t_j = <S_j, y>, y = J z raw.
+// With v_j = S_j / rho_j and w = y / rho_k:  <v_j, w> = t_j / rho_j / rho_k,  <v_j, v_a> = gam[j][a], and
+//   h_j = <v_j, w> - sum_{a<j} h_a gam[j][a]        (modified Gram-Schmidt, forward substitution over the whole cycle)
+//   c_j = h_j / rho_j                               (what multiplies the stored vector in the next sweep)
+// The substitution is column-oriented (lane j owns h_j; after step a every later lane subtracts h_a gam[j][a]): each h_j
+// sees its subtractions in the order a = 0, 1, ... like the serial loop.
+// seq_in != 0: the sums arrive through the sweep mailboxes and are added in rank order (same bits on every rank).
+__global__ void __launch_bounds__(32) k_gmres_sweep_scalar(KrylovCtl* ctl, int k, int mode, int64_t nr, double* R, double* c,
+                                                           double* s, double* z, double* sums, double* hvec, double* cvec,
+                                                           double* gam, double* rho_vec, double* rinv_vec, double* gram_blk,
+                                                           double* hist, int64_t hist_pos, int inner_limit,
+                                                           KrylovStatus* st, const P2PDev pd, const double* swmail_local,
+                                                           unsigned long long seq_in) {
+    constexpr int LD = kSwKMax + 1;
+    __shared__ double s_gam[LD * LD];
+    __shared__ double s_h[32], s_sum[kSwSums];
+    __shared__ double s_c[32], s_s[32], s_r[33];
+    __shared__ int s_abort;
+    const int lane = threadIdx.x;
+    if (ctl->stop) {
+        if (mode == 2 && lane == 0) {  // repeat the verdict that ended the pass (see k_gmres_givens)
+            st->rNorm = ctl->rNorm;
+            st->Hbis = ctl->Hbis;
+            st->iter = ctl->inner_iter;
+            st->solved = ctl->solved;
+            st->breakdown = ctl->breakdown;
+            st->stop = 1;
         }
-        __syncwarp();
-        if (lane == 0) {
-            const int cnt = (k - 1 - base) < 32 ? (k - 1 - base) : 32;
-            for (int q = 0; q < cnt; ++q) {
-                const double rn = s_r[q];
-                const double Rt = s_c[q] * cur + s_s[q] * rn;
-                const double nx = s_s[q] * cur - s_c[q] * rn;
-                R[nr + base + q] = Rt;
-                cur = nx;
+        return;
+    }
+    if (lane == 0) s_abort = 0;
+    __syncwarp();
+    if (seq_in != 0) {
+        const int slot = (int)(seq_in % kMailSlots);
+        if (lane < pd.nranks) {
+            const double* rec = swmail_local + ((size_t)slot * pd.nranks + lane) * kSwMailRec;
+            const unsigned long long* tag = reinterpret_cast<const unsigned long long*>(rec + kSwSums);
+            const long long t0 = clock64();
+            while (ld_acquire_sys_u64(tag) != seq_in) {
+                if (clock64() - t0 > pd.spin_cycles) { *pd.err = 1; s_abort = 1; break; }
             }
         }
         __syncwarp();
-    }
-    if (lane != 0) return;
-    const double Hbis = sqrt(hh);
-    if (rho_vec) { rho_vec[k] = Hbis; rinv_vec[k] = __ddiv_rn(1.0, Hbis); }  // the finished w of this iteration IS the stored basis vector k
-    const double a = cur, b = Hbis;
-    double ck, sk, rho;
-    if (b == 0.0) {
-        ck = (a == 0.0) ? 1.0 : sgn(a);
-        sk = 0.0;
-        rho = fabs(a);
-    } else if (a == 0.0) {
-        ck = 0.0;
-        sk = sgn(b);
-        rho = fabs(b);
-    } else if (fabs(b) > fabs(a)) {
-        const double t = a / b;
-        sk = sgn(b) / sqrt(1.0 + t * t);
-        ck = sk * t;
-        rho = b / sk;
+        if (!s_abort) {
+            for (int q = lane; q < kSwSums; q += 32) {
+                double a = 0.0;
+                for (int r = 0; r < pd.nranks; ++r)
+                    a += __ldcv(swmail_local + ((size_t)slot * pd.nranks + r) * kSwMailRec + q);
+                s_sum[q] = a;
+                sums[q] = a;
+            }
+        } else if (lane == 0) {  // a peer fell out of step: end the pass here, the host reports the error
+            ctl->stop = 1;
+            st->rNorm = ctl->rNorm; st->Hbis = ctl->Hbis; st->iter = ctl->inner_iter;
+            st->solved = 0; st->breakdown = 0; st->stop = 1;
+        }
     } else {
-        const double t = b / a;
-        ck = sgn(a) / sqrt(1.0 + t * t);
-        sk = ck * t;
-        rho = a / ck;
+        for (int q = lane; q < kSwSums; q += 32) s_sum[q] = sums[q];
     }
-    c[k - 1] = ck;
-    s[k - 1] = sk;
-    R[nr + k - 1] = rho;
-    const double zeta = sk * z[k - 1];
-    z[k - 1] = ck * z[k - 1];
-    const double rNorm = fabs(zeta);
-    if (hist) hist[hist_pos] = rNorm;
-    const int mach = (rNorm + 1.0 <= 1.0);
-    const int solved = (rNorm <= ctl->eps) || mach;
-    const int breakdown = (Hbis <= ctl->btol);
-    const int tired = (k >= inner_limit);
-    ctl->rNorm = rNorm;
-    ctl->Hbis = Hbis;
-    ctl->solved = solved;
-    ctl->breakdown = breakdown;
-    ctl->inner_iter = k;
-    const int stop = solved || breakdown || tired;
-    if (!stop) z[k] = zeta;
-    ctl->stop = stop;
-    st->rNorm = rNorm;
-    st->Hbis = Hbis;
-    st->iter = k;
-    st->stop = stop;
-    st->solved = solved;
-    st->breakdown = breakdown;
+    // the cached (scaled) Gram rows 1..k: one round trip for the whole warp
+    for (int q = lane; q < (k + 1) * LD; q += 32) s_gam[q] = gam[q];
+    __syncwarp();
+    if (s_abort) return;
+    const int nh = (mode == 1) ? k : k + 1;  // multipliers to form
+    if (mode == 2) {
+        const double hh = s_sum[0];
+        const double Hbis = sqrt(hh);
+        // row k of the Gram matrix, scaled: <v_k, v_a> = <S_k, S_a> / rho_k / rho_a; raw entries of S_k's own block of
+        // eight for the pass-wise sweeps (a cycle that outgrows kSwKMax vectors continues with them)
+        if (lane < k) {
+            const double g = s_sum[2 + lane];
+            const double v = __ddiv_rn(__ddiv_rn(g, Hbis), rho_vec[lane]);
+            s_gam[k * LD + lane] = v;
+            gam[k * LD + lane] = v;
+            const int b0 = (k / kBlkMax) * kBlkMax;
+            if (lane >= b0) gram_blk[(size_t)k * kBlkMax + (lane - b0)] = g;
+            R[nr + lane] = hvec[lane];
+        }
+        __syncwarp();
+        int stop = givens_tail(lane, ctl, k, nr, R, c, s, z, hh, rho_vec, rinv_vec, hist, hist_pos, inner_limit, st, s_c,
+                               s_s, s_r);
+        stop = __shfl_sync(0xffffffffu, stop, 0);
+        if (stop) return;
+        __syncwarp();
+    }
+    // raw projections -> <v_j, w>
+    if (lane < nh) {
+        double pj;
+        if (mode == 1) {
+            pj = __ddiv_rn(s_sum[2 + lane], rho_vec[lane]);  // second sweep: w is already in the scale of v
+        } else {
+            const double tj = (lane == k) ? s_sum[1] : s_sum[2 + kSwKMax + lane];
+            pj = __dmul_rn(__ddiv_rn(tj, rho_vec[lane]), rinv_vec[k]);
+        }
+        s_h[lane] = pj;
+    }
+    __syncwarp();
+    for (int a = 0; a + 1 < nh; ++a) {
+        const double ha = s_h[a];
+        if (lane > a && lane < nh) s_h[lane] = __dsub_rn(s_h[lane], __dmul_rn(ha, s_gam[lane * LD + a]));
+        __syncwarp();
+    }
+    if (lane < nh) {
+        const double h = s_h[lane];
+        hvec[lane] = (mode == 1) ? hvec[lane] + h : h;  // R[nr+i] += Htmp
+        cvec[lane] = __ddiv_rn(h, rho_vec[lane]);
+    }
 }
 
 // gmres! step 9: solve R y = z (K x K packed column-major upper triangle, K = inner iterations of the pass, read from
@@ -603,6 +735,21 @@ static int ws_grow_hist(ak_krylov* ws, int64_t need) {
     return AK_OK;
 }
 
+// scalars of the one-sweep Gram-Schmidt (fixed size: a sweep handles at most kSwKMax basis vectors)
+static int ws_ensure_sweep(ak_krylov* ws) {
+    if (ws->sw_sums) return AK_OK;
+    Ctx* c = ws->ctx;
+    const size_t nd = (size_t)kSwSums + 2 * (kSwKMax + 1) + (size_t)(kSwKMax + 1) * (kSwKMax + 1);
+    double* q = nullptr;
+    AK_CUDA(pool_alloc(c, (void**)&q, sizeof(double) * nd));
+    AK_CUDA(cudaMemsetAsync(q, 0, sizeof(double) * nd, c->stream));
+    ws->sw_sums = q;
+    ws->sw_h = q + kSwSums;
+    ws->sw_c = ws->sw_h + (kSwKMax + 1);
+    ws->sw_gam = ws->sw_c + (kSwKMax + 1);
+    return AK_OK;
+}
+
 // make sure basis vectors V[0..count) exist
 static int ws_ensure_basis(ak_krylov* ws, int64_t count, bool exact = false) {
     if ((int64_t)ws->V.size() >= count) return AK_OK;
@@ -694,6 +841,15 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     // against the stored (un-normalised) vectors, only the seed of the preconditioner is a normalised copy.
     const bool hosted = flexible || precond || lprec;
     if (hosted && fuse == AK_FUSE_FULL) fuse = AK_FUSE_MGS;
+    // One sweep per iteration (sweep.cu) where it applies: 2-D analytic tangents, no preconditioner, the first kSwKMax
+    // iterations of a pass.  Everything else of such a solve runs the eight-step blocked passes on the same
+    // (un-normalised) basis.  AK_NO_SWEEP=1: developer switch for A/B timing.
+    bool sweep = false;
+    if (fuse == AK_FUSE_SWEEP) {
+        static const bool no_sweep = getenv("AK_NO_SWEEP") != nullptr;
+        sweep = !no_sweep && !hosted && sweep_supported(c, prob, u);
+        fuse = AK_FUSE_BLOCK8;
+    }
     if ((flexible || precond) && !ws->pbuf) AK_TRY(ws_alloc_vec(ws, &ws->pbuf));
     if (lprec && !ws->qbuf) AK_TRY(ws_alloc_vec(ws, &ws->qbuf));
     const int blk = fuse == AK_FUSE_PAIR ? 2 : (fuse == AK_FUSE_BLOCK4 ? 4 : (fuse == AK_FUSE_BLOCK8 ? 8 : 0));  // steps per sweep
@@ -708,7 +864,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     const bool is2d = (prob->kind == AK_BRATU2D || prob->kind == AK_HEAT2D);
     const bool p2p_halo = p2p && !hosted && is2d && prob->nx % 4 == 0 && n % 4 == 0 && prob->nx <= c->p2p_halo_cap;
     int nb_down = -1, nb_up = -1;  // owners of the ghost rows below / above this slab
-    if (p2p_halo) {
+    if (p2p_halo || (sweep && p2p)) {
         const bool per = (prob->bc == AK_BC_PERIODIC);
         nb_down = c->rank > 0 ? c->rank - 1 : (per ? c->nranks - 1 : -1);
         nb_up = c->rank < c->nranks - 1 ? c->rank + 1 : (per ? 0 : -1);
@@ -725,7 +881,8 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
         if (!ws->dx) AK_TRY(ws_alloc_vec(ws, &ws->dx));
         xr = ws->dx;
     }
-    if (fuse == AK_FUSE_FULL && !ws->w[1]) AK_TRY(ws_alloc_vec(ws, &ws->w[1]));
+    if ((fuse == AK_FUSE_FULL || sweep) && !ws->w[1]) AK_TRY(ws_alloc_vec(ws, &ws->w[1]));
+    if (sweep) AK_TRY(ws_ensure_sweep(ws));
     AK_TRY(ws_ensure_basis(ws, raw && restart ? mem + 1 : mem, raw));
     // problem kinds without a fused normalise + JVP kernel get the normalised seed in a scratch vector
     const bool raw_needs_seed = raw && !hosted && (prob->kind == AK_SIMPLE2 || prob->kind == AK_USER ||
@@ -759,6 +916,61 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     double rNorm = 0.0, beta0 = 0.0;
     ws->status[kStatusRing + 1].inconsistent = 0;
 
+    // ---- one-sweep iterations (sweep.cu) -----------------------------------------------------------------------------
+    const bool sw_p2p = sweep && p2p;
+    unsigned long long sw_seq = 0;  // record the last sweep posted its sums under (peer memory), 0 otherwise
+    auto sw_wslot = [&](int wbuf) -> int { return kSwKMax + 1 + wbuf; };  // ghost-row slot of W buffer `wbuf`
+    std::vector<const double*> sw_lo((size_t)kSwKMax, nullptr), sw_hi((size_t)kSwKMax, nullptr);
+    if (sw_p2p)
+        for (int j = 0; j < kSwKMax; ++j) {
+            sw_lo[(size_t)j] = nb_down >= 0 ? c->p2p_swghost_local(j, 0) : nullptr;
+            sw_hi[(size_t)j] = nb_up >= 0 ? c->p2p_swghost_local(j, 1) : nullptr;
+        }
+    // one sweep over S_0..S_{kk-1}: z = zin * in_scale - sum c_j S_j -> zout; (stencil) y = J z -> yout.
+    // zin_slot / zout_slot / yout_slot: ghost-row slots of those buffers on the peer-memory path (-1: none)
+    auto sweep_launch = [&](int kk, const double* zin, int zin_slot, double* zout, int zout_slot, bool stencil,
+                            double* yout, int yout_slot, const double* in_scale) -> int {
+        SweepCall sc;
+        sc.k = kk;
+        sc.S = ws->V.data();
+        sc.zin = zin;
+        sc.zout = zout;
+        sc.stencil = stencil;
+        sc.yout = yout;
+        sc.cvec = ws->sw_c;
+        sc.in_scale = in_scale;
+        sc.sums = ws->sw_sums;
+        sc.stop = &ws->ctl->stop;
+        if (sw_p2p) {
+            sc.S_lo = sw_lo.data();
+            sc.S_hi = sw_hi.data();
+            sc.zin_lo = nb_down >= 0 ? c->p2p_swghost_local(zin_slot, 0) : nullptr;
+            sc.zin_hi = nb_up >= 0 ? c->p2p_swghost_local(zin_slot, 1) : nullptr;
+            if (zout != nullptr && zout_slot >= 0) {
+                sc.push_z_down = nb_down >= 0 ? c->p2p_swghost_of(nb_down, zout_slot, 1) : nullptr;
+                sc.push_z_up = nb_up >= 0 ? c->p2p_swghost_of(nb_up, zout_slot, 0) : nullptr;
+            }
+            if (stencil) {
+                sc.push_y_down = nb_down >= 0 ? c->p2p_swghost_of(nb_down, yout_slot, 1) : nullptr;
+                sc.push_y_up = nb_up >= 0 ? c->p2p_swghost_of(nb_up, yout_slot, 0) : nullptr;
+            }
+            sc.seq_out = ++c->p2p_seq;
+            sw_seq = sc.seq_out;
+        }
+        return launch_sweep(c, prob, u, sc);
+    };
+    auto sweep_scalar = [&](int kk, int mode, int64_t nr, int64_t inner_limit, KrylovStatus* rec) -> int {
+        ProfScope prof(c, PK_SCALAR);
+        k_gmres_sweep_scalar<<<1, 32, 0, sm>>>(ws->ctl, kk, mode, nr, ws->R, ws->c, ws->s, ws->z, ws->sw_sums, ws->sw_h,
+                                               ws->sw_c, ws->sw_gam, ws->rho, ws->rinv, ws->gram,
+                                               want_hist ? ws->hist : nullptr, iter + kk, (int)inner_limit, rec,
+                                               sw_p2p ? c->p2p_dev() : P2PDev{},
+                                               sw_p2p ? c->p2p_swmail_of(c->rank) : nullptr, sw_p2p ? sw_seq : 0ull);
+        c->launches++;
+        AK_CUDA(cudaGetLastError());
+        return AK_OK;
+    };
+
     while (true) {
         // ---- pass prologue -------------------------------------------------------------
         if (restart && npass >= 1) {
@@ -782,6 +994,13 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
         // V[0] <- r0 / rNorm   (no-op when already converged / zero residual; un-normalised basis: V[0] is r0)
         if (!raw) AK_TRY(launch_divcopy_dev(c, n, ws->V[0], w, &ws->ctl->rNorm, &ws->ctl->stop));
         npass += 1;
+        int wa = 0;  // one-sweep iterations: the W buffer that holds the raw tangent J S_{k-1} of the next iteration
+        if (sweep) {
+            // opening sweep of the cycle: W <- J S_0 and <S_0, W> (queued behind the prologue; a no-op after a stop)
+            if (sw_p2p) AK_TRY(sweep_push_rows(c, ws->V[0], prob->nx, prob->ny, prob->bc, 0));
+            AK_TRY(sweep_launch(0, ws->V[0], 0, nullptr, -1, true, ws->w[wa], sw_wslot(wa), nullptr));
+            AK_TRY(sweep_scalar(0, 0, 0, 0, &ws->status[kStatusRing]));
+        }
 
         const int64_t inner_limit = restart ? (mem < inner_itmax ? mem : inner_itmax) : inner_itmax;
         int64_t K = 0;  // completed inner iterations of this pass
@@ -857,6 +1076,27 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                 double* hcol = ws->hcol;
                 unsigned long long givens_seq = 0;
 
+                const int slot = (int)(k % kStatusRing);
+                const bool sw_it = sweep && k <= kSwKMax;
+                if (sw_it) {
+                    // the whole iteration is one sweep over the basis (two with re-orthogonalisation); the tangent of the
+                    // next iteration rides along unless this is the last iteration a sweep can serve
+                    const bool next_sw = k < inner_limit && k + 1 <= kSwKMax;
+                    if (reorth) {
+                        // gmres! step 5: z' = w - V h (W[wa] -> W[wa^1]), then z = z' - V h' (-> V[k]) with the tangent -> W[wa]
+                        AK_TRY(sweep_launch((int)k, ws->w[wa], sw_wslot(wa), ws->w[wa ^ 1], sw_wslot(wa ^ 1), false, nullptr, -1,
+                                            ws->rinv + (k - 1)));
+                        AK_TRY(sweep_scalar((int)k, 1, nr, inner_limit, &ws->status[slot]));
+                        AK_TRY(sweep_launch((int)k, ws->w[wa ^ 1], sw_wslot(wa ^ 1), ws->V[k], (int)k, next_sw, ws->w[wa],
+                                            sw_wslot(wa), nullptr));
+                    } else {
+                        AK_TRY(sweep_launch((int)k, ws->w[wa], sw_wslot(wa), ws->V[k], (int)k, next_sw, ws->w[wa ^ 1],
+                                            sw_wslot(wa ^ 1), ws->rinv + (k - 1)));
+                        wa ^= 1;
+                    }
+                    AK_TRY(sweep_scalar((int)k, 2, nr, inner_limit, &ws->status[slot]));
+                    w = ws->V[k];
+                } else {
                 // fgmres / right preconditioning: z_k = N v_k (kept in Z for fgmres), then w <- A z_k
                 double* pv = ws->V[k - 1];
                 if (hosted && k > 1) {
@@ -898,7 +1138,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                     jf.raw = true;
                     seed = raw_needs_seed ? ws->pbuf : nullptr;
                     wout = ws->V[k];
-                    if (p2p_halo && k > 1) {  // ghost rows of V[k-1] were pushed by the neighbours' final pass of iteration k-1
+                    if (p2p_halo && k > 1 && !(sweep && k == kSwKMax + 1)) {  // ghost rows of V[k-1] were pushed by the neighbours' final pass of iteration k-1
                         const int par = (int)((k - 1) & 1);
                         jf.halo_given = true;
                         jf.halo_lo = nb_down >= 0 ? c->p2p_halo_local(par, 0) : nullptr;
@@ -1006,7 +1246,6 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                         AK_TRY(launch_mgs_step(c, n, w, ws->V[k - 1], hcol + k - 1, nullptr, 1, hcol + k, stop));
                     }
                 }
-                const int slot = (int)(k % kStatusRing);
                 { ProfScope prof(c, PK_SCALAR);
                 k_gmres_givens<<<1, 32, 0, sm>>>(ws->ctl, (int)k, nr, ws->R, ws->c, ws->s, ws->z, hcol, reorth, blk,
                                                  want_hist ? ws->hist : nullptr, iter + k, (int)inner_limit,
@@ -1014,6 +1253,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
                                                  raw ? ws->rho : nullptr, ws->gram, ws->rinv); }
                 c->launches++;
                 AK_CUDA(cudaGetLastError());
+                }  // !sw_it
                 AK_CUDA(cudaEventRecord(ws->ev[slot], sm));
                 // V[k] <- w / Hbis (skipped on the device when this iteration stopped the pass)
                 if (k < inner_limit && !raw) {
@@ -1328,7 +1568,7 @@ AK_API int ak_krylov_destroy(ak_krylov* ws) {
     for (double* p : ws->chunks) rel(p);
     rel((void*)ws->V_dev);
     rel(ws->R); rel(ws->c); rel(ws->s); rel(ws->z); rel(ws->hcol); rel(ws->hist); rel(ws->rho); rel(ws->gram);
-    rel(ws->ycoef); rel(ws->rinv);
+    rel(ws->ycoef); rel(ws->rinv); rel(ws->sw_sums);
     rel(ws->ctl);
     if (ws->status) cudaFreeHost(ws->status);
     for (int i = 0; i < kStatusSlots; ++i)

@@ -545,62 +545,60 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
     if (SCALE) denom = make_divisor(*p.denom);
     else denom = Divisor{1.0, 1.0, 0};
     const Divisor mw = p.mwd;
+    // scale of the un-normalised Krylov basis: read up front, not behind the arithmetic
+    double oscale = 1.0;
+    if (!RESIDUAL && p.out_scale != nullptr)
+        oscale = p.out_scale_inv != nullptr ? *p.out_scale_inv : __ddiv_rn(1.0, *p.out_scale);
 
-    auto load_elem = [&](int64_t el, double (&r)[4]) {
-        ldv<4>((el < 0) ? p.lo : p.in + 4 * el, r);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (SCALE) r[i] = div_by(r[i], denom);
-            if (!RESIDUAL) r[i] = __dmul_rn(p.c0, r[i]);
-        }
-    };
-    double u[4] = {0, 0, 0, 0}, raw[4] = {0, 0, 0, 0};
-    if (active) {
-        ldv<4>(p.in + 4 * e, raw);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (SCALE) raw[i] = div_by(raw[i], denom);
-            u[i] = RESIDUAL ? raw[i] : __dmul_rn(p.c0, raw[i]);
-        }
+    // Neighbour coupling: within a warp by shuffles; the first lane of a warp needs the element to its left, the last
+    // lane the first node of the element to its right.  Those two loads are issued TOGETHER with the warp's own 256-bit
+    // loads, before anything is used: as dependent loads behind the first round trip (round 1) they stalled the whole
+    // warp for a second memory latency (77-80 % of peak); an exchange through shared memory cost two block barriers and
+    // was slower still (69 %).
+    const bool need_l = active && lane == 0;
+    const bool need_r = active && (lane == 31 || e + 1 >= ne);
+    double u[4] = {0, 0, 0, 0}, raw[4] = {0, 0, 0, 0}, up[4] = {0, 0, 0, 0};
+    double u_next_raw = 0.0;
+    if (active) ldv<4>(p.in + 4 * e, raw);
+    if (need_l) {
+        const int64_t ep = (e == 0) ? ((p.lo != nullptr) ? -1 : ne - 1) : e - 1;
+        ldv<4>((ep < 0) ? p.lo : p.in + 4 * ep, up);
     }
-    // Neighbour coupling: within a warp by shuffles, between the warps of a block through shared memory (the same
-    // values the neighbouring thread holds), across blocks / the periodic wrap / rank boundaries from global memory.
-    // (One thread per warp re-deriving its left neighbour from global memory stalled the whole warp: 77-80 % of peak.)
-    __shared__ double s_u0[kT1 / 32], s_t3[kT1 / 32];
-    const int wid = threadIdx.x >> 5;
-    if (lane == 0) s_u0[wid] = u[0];
-    __syncthreads();
+    if (need_r) {
+        const int64_t en = (e + 1 == ne) ? 0 : e + 1;
+        u_next_raw = (e + 1 == ne && p.hi != nullptr) ? p.hi[0] : p.in[4 * en];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (SCALE) raw[i] = div_by(raw[i], denom);
+        u[i] = RESIDUAL ? raw[i] : __dmul_rn(p.c0, raw[i]);
+    }
     // D1p: needs first node of the element to the right
     double u_next0 = __shfl_down_sync(0xffffffffu, u[0], 1);
-    if (active && (lane == 31 || e + 1 >= ne)) {
-        if (e + 1 < ne && wid + 1 < kT1 / 32) {
-            u_next0 = s_u0[wid + 1];
-        } else {
-            const int64_t en = (e + 1 == ne) ? 0 : e + 1;
-            double t = (e + 1 == ne && p.hi != nullptr) ? p.hi[0] : p.in[4 * en];
-            if (SCALE) t = div_by(t, denom);
-            u_next0 = RESIDUAL ? t : __dmul_rn(p.c0, t);
-        }
+    if (need_r) {
+        double t = u_next_raw;
+        if (SCALE) t = div_by(t, denom);
+        u_next0 = RESIDUAL ? t : __dmul_rn(p.c0, t);
     }
     double t1[4] = {0, 0, 0, 0};
     if (active) {
         dg_local(p.D, p.jac, u, t1);
         t1[3] = __dadd_rn(t1[3], div_by(__dsub_rn(u_next0, u[3]), mw));
     }
-    if (lane == 31) s_t3[wid] = t1[3];
-    __syncthreads();
     // D1m: needs last node of (D1p u) of the element to the left
     double t_prev3 = __shfl_up_sync(0xffffffffu, t1[3], 1);
-    if (active && lane == 0) {
-        if (wid > 0) {
-            t_prev3 = s_t3[wid - 1];
-        } else {
-            const int64_t ep = (e == 0) ? ((p.lo != nullptr) ? -1 : ne - 1) : e - 1;
-            double up[4], tp[4];
-            load_elem(ep, up);
-            dg_local(p.D, p.jac, up, tp);
-            t_prev3 = __dadd_rn(tp[3], div_by(__dsub_rn(u[0], up[3]), mw));
+    if (need_l) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (SCALE) up[i] = div_by(up[i], denom);
+            if (!RESIDUAL) up[i] = __dmul_rn(p.c0, up[i]);
         }
+        // last row of D1p on the left element: jac * (D[3] . up) + (u[0] - up[3]) / mw
+        double sl = __dmul_rn(p.D[3][0], up[0]);
+        sl = __dadd_rn(sl, __dmul_rn(p.D[3][1], up[1]));
+        sl = __dadd_rn(sl, __dmul_rn(p.D[3][2], up[2]));
+        sl = __dadd_rn(sl, __dmul_rn(p.D[3][3], up[3]));
+        t_prev3 = __dadd_rn(__dmul_rn(p.jac, sl), div_by(__dsub_rn(u[0], up[3]), mw));
     }
     double acc = 0.0;
     if (active) {
@@ -619,7 +617,6 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] = __dsub_rn(__dmul_rn(p.c1, du[i]), raw[i]);
             if (p.out_scale != nullptr) {
-                const double oscale = p.out_scale_inv != nullptr ? *p.out_scale_inv : __ddiv_rn(1.0, *p.out_scale);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) o[i] = __dmul_rn(o[i], oscale);
             }

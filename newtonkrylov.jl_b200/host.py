@@ -732,7 +732,7 @@ NewtonResult = namedtuple("NewtonResult", "solved stats t")
 # ---------------------------------------------------------------------------------------------
 _ALGOS = {"gmres": A.AK_ALGO_GMRES, "cg": A.AK_ALGO_CG, "fgmres": A.AK_ALGO_FGMRES}
 _FUSE = {"none": A.AK_FUSE_NONE, "mgs": A.AK_FUSE_MGS, "full": A.AK_FUSE_FULL, "pair": A.AK_FUSE_PAIR,
-         "block4": A.AK_FUSE_BLOCK4, "block8": A.AK_FUSE_BLOCK8}
+         "block4": A.AK_FUSE_BLOCK4, "block8": A.AK_FUSE_BLOCK8, "sweep": A.AK_FUSE_SWEEP}
 
 
 class GmresPreconditioner:

@@ -83,7 +83,7 @@ def run_1d_cases(ctx, rank, world, rng, tag):
         # (a fixed number of iterations: 1-D Laplacians converge only when the Krylov space is exhausted, which
         #  makes the final count a knife edge)
         xr, sr, hr = O.krylov_solve(po, d["u0"], b0, rtol=1e-8, itmax=40, hist_cap=100000)
-        for fuse in ("none", "mgs", "full", "pair", "block4", "block8"):
+        for fuse in ("none", "mgs", "full", "pair", "block4", "block8", "sweep"):
             u = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
             ws = nk.krylov_workspace("gmres", nk.KrylovConstructor(res))
             nk.krylov_solve_(ws, nk.JacobianOperator(F_, res, u, p), nk.DeviceVector.from_numpy(b0[sl], ctx),
@@ -246,7 +246,7 @@ def run_cases(ctx, rank, world, rng, tag):
             assert rel(ws.x.numpy(), xr[sl]) < 1e-7, (name, side)
         # solver level
         if d["kind"] == A.AK_BRATU2D:
-            for fuse in ("none", "mgs", "full", "pair", "block4", "block8"):
+            for fuse in ("none", "mgs", "full", "pair", "block4", "block8", "sweep"):
                 u = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
                 hist = []
                 _, r = nk.newton_krylov_native_(F_, u, p, None, history=hist, krylov_kwargs=dict(fuse=fuse))

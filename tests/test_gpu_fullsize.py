@@ -13,7 +13,7 @@ import problems as P
 
 pytestmark = pytest.mark.gpu
 RNG = np.random.default_rng(4)
-FUSE_LEVELS = ("none", "mgs", "full", "pair", "block4", "block8")
+FUSE_LEVELS = ("none", "mgs", "full", "pair", "block4", "block8", "sweep")
 
 
 def rel(a, b):
@@ -134,7 +134,7 @@ def test_c4_bratu2d_8192_gmres_cycle_properties(nk, ctx):
     ws = nk.krylov_workspace("gmres", nk.KrylovConstructor(res), memory=20)
     b = res.copy()
     xs, hists = [], []
-    for fuse in ("none", "mgs", "full", "pair", "block4", "block8"):
+    for fuse in ("none", "mgs", "full", "pair", "block4", "block8", "sweep"):
         nk.krylov_solve_(ws, J, b, rtol=1e-30, atol=0.0, restart=True, itmax=20, history=True, fuse=fuse)
         st = ws.stats
         assert st.niter == 20 and st.npass == 1 and not st.solved

@@ -471,10 +471,10 @@ def test_stencil_kernels_stay_inside_their_vectors(nk, ctx, oracle, name, make):
     assert np.all(np.isnan(h[mask])), "a kernel wrote outside its vector"
 
 
-@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4", "block8"])
+@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4", "block8", "sweep"])
 def test_gmres_reads_only_its_operands(nk, ctx, oracle, fuse):
     """A whole GMRES solve (7 iterations: ragged blocks of the blocked sweep) with u and b inside NaN guard bands."""
-    d = P.bratu2d(33, 19)
+    d = P.bratu2d(34, 19) if fuse == "sweep" else P.bratu2d(33, 19)  # (the sweep kernels take even row lengths)
     b0 = RNG.standard_normal(d["u0"].shape)
     base, (u, b, res), mask = _guarded(nk, ctx, [d["u0"], b0, np.zeros_like(b0)])
     J = nk.JacobianOperator(nk.bratu2d_, res, u, (d["dx"], d["dy"], d["lam"]))
@@ -485,3 +485,8 @@ def test_gmres_reads_only_its_operands(nk, ctx, oracle, fuse):
     assert ws.stats.niter == sr["niter"] == 7
     assert np.linalg.norm(ws.x.numpy() - xr) <= 1e-9 * np.linalg.norm(xr)
     assert np.all(np.isnan(base.numpy()[mask]))
+    if fuse == "sweep":  # the bulk copies of the sweep kernel (rows of u with their rim columns) stayed inside u
+        ctx.profile(True)
+        nk.krylov_solve_(ws, J, b, itmax=7, restart=True, fuse=fuse)
+        assert ctx.profile_read(13)[0] > 0
+        ctx.profile(False)

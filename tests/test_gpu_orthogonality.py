@@ -44,15 +44,15 @@ def test_blocked_sweeps_keep_the_basis_as_orthogonal_as_the_reference_op_list(nk
     d = make()
     b0 = RNG.standard_normal(d["u0"].shape)
     loss = {}
-    for fuse in ("none", "mgs", "full", "pair", "block4", "block8"):
+    for fuse in ("none", "mgs", "full", "pair", "block4", "block8", "sweep"):
         k, loss[fuse], red = basis_loss(nk, ctx, d, b0, fuse)
         assert k == ITERS, (fuse, k)
         ledger.record("loss_of_orthogonality", f"{name}/{fuse}", iterations=k, frobenius_I_minus_VtV=loss[fuse],
                       residual_reduction=red)
-    for fuse in ("pair", "block4", "block8"):
+    for fuse in ("pair", "block4", "block8", "sweep"):
         assert loss[fuse] <= 2.0 * loss["none"] + 1e-13, (fuse, loss)
     # the second sweep restores orthogonality to rounding level, also in the blocked form
-    for fuse in ("none", "block8"):
+    for fuse in ("none", "block8", "sweep"):
         k, l2, _ = basis_loss(nk, ctx, d, b0, fuse, reorth=True)
         ledger.record("loss_of_orthogonality", f"{name}/{fuse}+reorth", iterations=k, frobenius_I_minus_VtV=l2)
         assert l2 <= max(1e-12, 1e-2 * loss["none"]), (fuse, l2, loss["none"])

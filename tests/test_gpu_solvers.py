@@ -44,7 +44,7 @@ LIN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4", "block8"])
+@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4", "block8", "sweep"])
 @pytest.mark.parametrize("name,make,kw", LIN_CASES, ids=[c[0] for c in LIN_CASES])
 def test_gmres_matches_oracle(nk, ctx, oracle, name, make, kw, fuse):
     d = make()
@@ -66,7 +66,7 @@ def test_gmres_matches_oracle(nk, ctx, oracle, name, make, kw, fuse):
     assert np.max(np.abs(h - hr)) <= 1e-10 * hr[0]
 
 
-@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4", "block8"])
+@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4", "block8", "sweep"])
 @pytest.mark.parametrize("opts", [dict(restart=True, itmax=45), dict(restart=True, reorthogonalization=True, itmax=33),
                                   dict(reorthogonalization=True), dict(itmax=7), dict(restart=True)],
                          ids=["restart45", "restart_reorth33", "reorth", "itmax7", "restart_conv"])
@@ -77,9 +77,14 @@ def test_gmres_options(nk, ctx, oracle, opts, fuse):
     ctx.profile(True)
     x, st = device_krylov(nk, ctx, d, b0, memory=5, rtol=1e-9, fuse=fuse, **opts)
     blocked_launches = sum(ctx.profile_read(cls)[0] for cls in (10, 11, 12))  # full / ragged / final blocked passes
+    sweep_launches = ctx.profile_read(13)[0]                                  # one-sweep iterations (csrc/sweep.cu)
     ctx.profile(False)
-    # the blocked sweeps are really what ran (no silent fall-back to the step-wise kernels with reorthogonalization)
-    assert (blocked_launches > 0) == (fuse in ("pair", "block4", "block8")), (fuse, blocked_launches)
+    # the blocked sweeps are really what ran (no silent fall-back to the step-wise kernels with reorthogonalization);
+    # fuse = sweep runs the one-sweep kernel (and the eight-step passes once a pass outgrows 24 vectors)
+    if fuse == "sweep":
+        assert sweep_launches > 0, (fuse, sweep_launches)
+    else:
+        assert sweep_launches == 0 and (blocked_launches > 0) == (fuse in ("pair", "block4", "block8")), (fuse, blocked_launches)
     po = P.oracle_problem(oracle, d)
     xr, sr, hr = oracle.krylov_solve(po, d["u0"], b0, memory=5, hist_cap=100000, rtol=1e-9, **opts)
     m = min(len(st.residuals), len(hr))
@@ -297,7 +302,7 @@ def test_newton_matches_oracle(nk, ctx, oracle, name, make, kw, native, fuse):
     assert_newton_parity(u, r, hist, sens, label=f"{name}/{'c_loop' if native else 'host_loop'}/{fuse}")
 
 
-@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4", "block8"])
+@pytest.mark.parametrize("fuse", ["none", "mgs", "full", "pair", "block4", "block8", "sweep"])
 def test_newton_fusion_levels_agree(nk, ctx, oracle, fuse):
     d = P.generic(P.bratu2d(40))
     u, r, hist, sens = newton_both(nk, ctx, oracle, d, True, cache_key="bratu2d_40_generic", krylov_kwargs=dict(fuse=fuse))

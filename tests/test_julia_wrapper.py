@@ -129,7 +129,7 @@ def test_enum_values_match_the_abi():
     m = re.search(r"const AK_FUSE = Dict\((.*?)\)\n", src)
     fuse = dict((k, int(v)) for k, v in re.findall(r":(\w+) => Int32\((\d)\)", m.group(1)))
     assert fuse == {"none": A.AK_FUSE_NONE, "mgs": A.AK_FUSE_MGS, "full": A.AK_FUSE_FULL, "pair": A.AK_FUSE_PAIR,
-                    "block4": A.AK_FUSE_BLOCK4, "block8": A.AK_FUSE_BLOCK8}
+                    "block4": A.AK_FUSE_BLOCK4, "block8": A.AK_FUSE_BLOCK8, "sweep": A.AK_FUSE_SWEEP}
     m = re.search(r"const AK_ALGO = Dict\((.*?)\)\n", src)
     assert dict((k, int(v)) for k, v in re.findall(r":(\w+) => Int32\((\d)\)", m.group(1))) == \
         {"gmres": A.AK_ALGO_GMRES, "cg": A.AK_ALGO_CG, "fgmres": A.AK_ALGO_FGMRES}
