@@ -533,8 +533,12 @@ AK_DEV void dg_local(const double (&D)[4][4], double jac, const double (&u)[4], 
     }
 }
 
-template <bool RESIDUAL, bool SCALE, int RED>
-__global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
+// MB: resident blocks per SM the register allocation is sized for.  One element (32 bytes) per thread: the bytes in flight
+// are set by the resident warps, so the register count decides the bandwidth (see launch_dg).
+// (Round 2 also tried: the two neighbour loads issued up front - 54 registers, 4 blocks, 71 %; the neighbour values
+// through shared memory - two block barriers, 69 %.)
+template <bool RESIDUAL, bool SCALE, int RED, int MB>
+__global__ void __launch_bounds__(kT1, MB) k_dg(const DgArgs p) {
     __shared__ double sh[32];
     if (p.stop != nullptr && *p.stop != 0) return;
     const int lane = threadIdx.x & 31;
@@ -550,33 +554,28 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
     if (!RESIDUAL && p.out_scale != nullptr)
         oscale = p.out_scale_inv != nullptr ? *p.out_scale_inv : __ddiv_rn(1.0, *p.out_scale);
 
-    // Neighbour coupling: within a warp by shuffles; the first lane of a warp needs the element to its left, the last
-    // lane the first node of the element to its right.  Those two loads are issued TOGETHER with the warp's own 256-bit
-    // loads, before anything is used: as dependent loads behind the first round trip (round 1) they stalled the whole
-    // warp for a second memory latency (77-80 % of peak); an exchange through shared memory cost two block barriers and
-    // was slower still (69 %).
-    const bool need_l = active && lane == 0;
-    const bool need_r = active && (lane == 31 || e + 1 >= ne);
-    double u[4] = {0, 0, 0, 0}, raw[4] = {0, 0, 0, 0}, up[4] = {0, 0, 0, 0};
-    double u_next_raw = 0.0;
-    if (active) ldv<4>(p.in + 4 * e, raw);
-    if (need_l) {
-        const int64_t ep = (e == 0) ? ((p.lo != nullptr) ? -1 : ne - 1) : e - 1;
-        ldv<4>((ep < 0) ? p.lo : p.in + 4 * ep, up);
-    }
-    if (need_r) {
-        const int64_t en = (e + 1 == ne) ? 0 : e + 1;
-        u_next_raw = (e + 1 == ne && p.hi != nullptr) ? p.hi[0] : p.in[4 * en];
-    }
+    auto load_elem = [&](int64_t el, double (&r)[4]) {
+        ldv<4>((el < 0) ? p.lo : p.in + 4 * el, r);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (SCALE) raw[i] = div_by(raw[i], denom);
-        u[i] = RESIDUAL ? raw[i] : __dmul_rn(p.c0, raw[i]);
+        for (int i = 0; i < 4; ++i) {
+            if (SCALE) r[i] = div_by(r[i], denom);
+            if (!RESIDUAL) r[i] = __dmul_rn(p.c0, r[i]);
+        }
+    };
+    double u[4] = {0, 0, 0, 0}, raw[4] = {0, 0, 0, 0};
+    if (active) {
+        ldv<4>(p.in + 4 * e, raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (SCALE) raw[i] = div_by(raw[i], denom);
+            u[i] = RESIDUAL ? raw[i] : __dmul_rn(p.c0, raw[i]);
+        }
     }
     // D1p: needs first node of the element to the right
     double u_next0 = __shfl_down_sync(0xffffffffu, u[0], 1);
-    if (need_r) {
-        double t = u_next_raw;
+    if (active && (lane == 31 || e + 1 >= ne)) {
+        const int64_t en = (e + 1 == ne) ? 0 : e + 1;
+        double t = (e + 1 == ne && p.hi != nullptr) ? p.hi[0] : p.in[4 * en];
         if (SCALE) t = div_by(t, denom);
         u_next0 = RESIDUAL ? t : __dmul_rn(p.c0, t);
     }
@@ -587,18 +586,12 @@ __global__ void __launch_bounds__(kT1) k_dg(const DgArgs p) {
     }
     // D1m: needs last node of (D1p u) of the element to the left
     double t_prev3 = __shfl_up_sync(0xffffffffu, t1[3], 1);
-    if (need_l) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (SCALE) up[i] = div_by(up[i], denom);
-            if (!RESIDUAL) up[i] = __dmul_rn(p.c0, up[i]);
-        }
-        // last row of D1p on the left element: jac * (D[3] . up) + (u[0] - up[3]) / mw
-        double sl = __dmul_rn(p.D[3][0], up[0]);
-        sl = __dadd_rn(sl, __dmul_rn(p.D[3][1], up[1]));
-        sl = __dadd_rn(sl, __dmul_rn(p.D[3][2], up[2]));
-        sl = __dadd_rn(sl, __dmul_rn(p.D[3][3], up[3]));
-        t_prev3 = __dadd_rn(__dmul_rn(p.jac, sl), div_by(__dsub_rn(u[0], up[3]), mw));
+    if (active && lane == 0) {
+        const int64_t ep = (e == 0) ? ((p.lo != nullptr) ? -1 : ne - 1) : e - 1;
+        double up[4], tp[4];
+        load_elem(ep, up);
+        dg_local(p.D, p.jac, up, tp);
+        t_prev3 = __dadd_rn(tp[3], div_by(__dsub_rn(u[0], up[3]), mw));
     }
     double acc = 0.0;
     if (active) {
@@ -963,7 +956,17 @@ static int launch_dg(Ctx* ctx, DgArgs& d, bool residual, bool scale, int red) {
         set_error("DG stencil with fused reduction: n too large for the partials buffer");
         return AK_ERR_UNSUPPORTED;
     }
-#define AK_LDG(RS, S, R) k_dg<RS, S, R><<<(int)grid, kT1, 0, ctx->stream>>>(d)
+    // resident blocks per SM (register budget) of the un-scaled kernels: 8 blocks = 32 registers = all 64 warps of an
+    // SM in flight (measured at 2^22 elements: tangent 59.6 us at 46 registers, 49.3 us at 40, 45.4 us at 32 = 90 % of the
+    // copy bandwidth; residual 69.8 / 64.1 / 61.4 us = 100 %).  AK_DG_MB = 1 / 6 / 8: tuning knob
+    static const int mb = [] { const char* e = getenv("AK_DG_MB"); return e ? atoi(e) : 8; }();
+#define AK_LDG1(RS, S, R, M) k_dg<RS, S, R, M><<<(int)grid, kT1, 0, ctx->stream>>>(d)
+#define AK_LDG(RS, S, R)                                        \
+    do {                                                        \
+        if (!(S) && mb == 6) AK_LDG1(RS, false, R, 6);          \
+        else if (!(S) && mb == 8) AK_LDG1(RS, false, R, 8);     \
+        else AK_LDG1(RS, S, R, 1);                              \
+    } while (0)
     if (residual) {
         if (red == RED_SUMSQ) AK_LDG(true, false, RED_SUMSQ);
         else AK_LDG(true, false, RED_NONE);
@@ -975,6 +978,7 @@ static int launch_dg(Ctx* ctx, DgArgs& d, bool residual, bool scale, int red) {
         else if (red == RED_SUMSQ) AK_LDG(false, false, RED_SUMSQ);
         else AK_LDG(false, false, RED_NONE);
     }
+#undef AK_LDG1
 #undef AK_LDG
     ctx->launches++;
     AK_CUDA(cudaGetLastError());

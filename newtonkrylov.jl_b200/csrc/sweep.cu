@@ -29,17 +29,18 @@
 
 namespace ak {
 
-constexpr int kSwTX = 256;                       // columns staged per strip (2 + 252 + 2)
-constexpr int kSwHalo = 2;                       // rim columns per side (two, so that every bulk copy is 16-byte aligned)
-constexpr int kSwTXI = kSwTX - 2 * kSwHalo;      // columns a strip owns
-constexpr int kSwConsumers = 256;
-constexpr int kSwThreads = kSwConsumers;         // every warp both streams and computes
+constexpr int kSwThreads = 256;                  // 8 warps; every warp both streams (in turn) and computes
 constexpr int kSwWarps = kSwThreads / 32;
+constexpr int kSwTW = 30;                        // columns a warp owns at most (32 lanes = 30 + one rim lane per side)
+constexpr int kSwHalo = 2;                       // rim columns staged per side (two, so that every bulk copy is 16-byte aligned)
+constexpr int kSwTXI = kSwWarps * kSwTW;         // 240: widest strip a block owns
+constexpr int kSwTX = 256;                       // doubles per staged vector row (>= kSwTXI + 2 * kSwHalo)
 constexpr int kSwMaxSlots = 8;
-// shared-memory map (bytes): barriers | coefficients | three rows of z | reduction scratch | slots
+constexpr int kSwMaxSeg = 8;                     // segments (strip, row range) one block may be given
+// shared-memory map (bytes): barriers | coefficients, flag | segment table | reduction scratch | slots
 constexpr int kSwOffCoef = 128;
-constexpr int kSwOffZ = 512;
-constexpr int kSwOffRed = kSwOffZ + 3 * kSwTX * 8;
+constexpr int kSwOffSeg = 512;
+constexpr int kSwOffRed = kSwOffSeg + 512;
 constexpr int kSwOffSlots = ((kSwOffRed + kSwWarps * kSwSums * 8 + 127) / 128) * 128;
 constexpr int kSwSmemMax = 227 * 1024;
 
@@ -51,6 +52,10 @@ struct SweepArgs {
     int32_t nslot;      // ring depth
     int32_t wrap_x;     // periodic in x
     int32_t coef_from_u;
+    int32_t txi;        // columns a strip owns (even, <= kSwTXI)
+    int32_t tw;         // columns a warp owns: ceil(txi / 8)
+    int32_t team_strips;  // > 0: block b owns strip b % team_strips, row band b / team_strips of team_bands (neighbouring
+    int32_t team_bands;   //      strips run side by side, so their shared rim sectors hit L2); 0: even split of (strip, row)
     const double* S[kSwKMax];
     const double* S_lo[kSwKMax];  // ghost row y = -1 of S_j (nullptr: zero)
     const double* S_hi[kSwKMax];  // ghost row y = ny
@@ -83,13 +88,11 @@ AK_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_sha
 AK_DEV void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-AK_DEV void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+AK_DEV void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+AK_DEV void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-AK_DEV void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-AK_DEV bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+AK_DEV bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n"
@@ -98,174 +101,223 @@ AK_DEV bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
 }
-// bounded wait: a pipeline that never completes is a bug; trap instead of hanging the GPU
-AK_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+// bounded wait: a pipeline that never completes is a bug; trap instead of hanging the GPU (cold path, not inlined)
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
-AK_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+AK_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+}
+AK_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
 
 // resident blocks per SM the register budget is sized for (8 warps: 255 / 128 / 80 registers per thread)
 constexpr int sw_min_blocks(int kb) { return kb <= 4 ? 3 : (kb <= 8 ? 2 : 1); }
 
+struct SwSeg {       // one (strip, row range) of a block; rows are consumed in the order of the table
+    int32_t c0;      // first staged column (strip start - rim), may be -2
+    int32_t r0, r1;  // rows owned
+    uint32_t f0;     // index of the segment's first staged row in the block's row sequence
+};
+
 // One sweep.  KB: compile-time bound on k (register-resident sums); STENCIL: y = J z is formed and projected.
+//
+// Rows flow through a ring of `nslot` shared-memory slots, one mbarrier pair per slot: `full` (armed with the byte count,
+// completed by the bulk copies) and `empty` (one arrival per warp when it is done with the slot).  The WARPS ARE
+// INDEPENDENT: warp w owns `tw` columns of the strip and recomputes z on one rim column per side (x-neighbours by
+// shuffle), so no block barrier sits between the phases of a row.  Staging duty rotates: staged row f is issued by warp
+// f % 8 a few steps after all warps released its slot, lane v streaming vector v.
+// The row loop is written for instruction count: at basis size 20 a lane needs 60 DFMA and 50 LDS per point, and the
+// first versions spent 5x that on bookkeeping (per-j predicates, integer divisions for slot and parity, null checks of
+// the push pointers, 64-bit index arithmetic) and were issue-bound at 55-70 % of the bandwidth (ncu: 409 instructions
+// per warp and row, stall_wait 41 %; profiles/r02_sweep_tuning.md).  Now: slot positions k..KB-1 of every slot are zero
+// padding so that all loops over j are unpredicated with immediate offsets, slot / parity / row pointers are running
+// values, and the row conditions are three compares on the loop counter.
 template <int KB, bool STENCIL, int OP>
 __global__ void __launch_bounds__(kSwThreads, sw_min_blocks(KB)) k_sweep(const SweepArgs p) {
     extern __shared__ __align__(128) unsigned char sw_smem[];
     if (p.stop != nullptr && *p.stop != 0) return;
     constexpr int NS = 2 * KB + 2;
     constexpr bool HASCOEF = STENCIL && OP == SW_OP_BRATU;
+    // slot layout: S_j at vector position j < KB (k..KB-1 zero), zin at KB, lambda e^u at KB + 1
+    constexpr int NVEC = KB + 1 + (HASCOEF ? 1 : 0);
+    constexpr int SLOTD = NVEC * kSwTX;  // doubles per slot
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(sw_smem);
+    uint64_t* bar_empty = bar_full + kSwMaxSlots;
     double* s_c = reinterpret_cast<double*>(sw_smem + kSwOffCoef);
-    double* s_z = reinterpret_cast<double*>(sw_smem + kSwOffZ);
+    int* s_last_p = reinterpret_cast<int*>(sw_smem + kSwOffCoef + kSwKMax * 8);
+    int* s_nseg = s_last_p + 1;
+    uint32_t* s_nfill = reinterpret_cast<uint32_t*>(s_last_p + 2);
+    SwSeg* s_seg = reinterpret_cast<SwSeg*>(sw_smem + kSwOffSeg);
     double* s_red = reinterpret_cast<double*>(sw_smem + kSwOffRed);
     double* slots = reinterpret_cast<double*>(sw_smem + kSwOffSlots);
-    int* s_last_p = reinterpret_cast<int*>(sw_smem + kSwOffCoef + kSwKMax * 8);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = p.k, nslot = p.nslot;
     const int64_t nx = p.nx, ny = p.ny;
-    const int nvec = k + 1 + (HASCOEF ? 1 : 0);
-    const int slot_doubles = nvec * kSwTX;
+    const int nvec = k + 1 + (HASCOEF ? 1 : 0);  // vectors streamed per row
+    const int txi = p.txi, tw = p.tw;
     if (tid == 0) {
         for (int s = 0; s < nslot; ++s) {
             mbar_init(bar_full + s, 1);
+            mbar_init(bar_empty + s, kSwWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // this block's segments
+        int ns = 0;
+        uint32_t f = 0;
+        const int halo_rows = STENCIL ? 2 : 0;
+        if (p.team_strips > 0) {
+            const int strip = (int)(blockIdx.x % (unsigned)p.team_strips), band = (int)(blockIdx.x / (unsigned)p.team_strips);
+            const int64_t r0 = ny * band / p.team_bands, r1 = ny * (band + 1) / p.team_bands;
+            if (r1 > r0) {
+                s_seg[0] = SwSeg{strip * txi - kSwHalo, (int32_t)r0, (int32_t)r1, 0u};
+                f = (uint32_t)(r1 - r0) + halo_rows;
+                ns = 1;
+            }
+        } else {
+            const int64_t nstrip = (nx + txi - 1) / txi;
+            const int64_t total = nstrip * ny;
+            int64_t u = total * (int64_t)blockIdx.x / (int64_t)gridDim.x;
+            const int64_t u_end = total * ((int64_t)blockIdx.x + 1) / (int64_t)gridDim.x;
+            while (u < u_end && ns < kSwMaxSeg) {
+                const int64_t strip = u / ny, r0 = u - strip * ny;
+                const int64_t r1 = (r0 + (u_end - u) < ny) ? r0 + (u_end - u) : ny;
+                s_seg[ns] = SwSeg{(int32_t)(strip * txi - kSwHalo), (int32_t)r0, (int32_t)r1, f};
+                f += (uint32_t)(r1 - r0) + halo_rows;
+                u += r1 - r0;
+                ++ns;
+            }
+        }
+        *s_nseg = ns;
+        *s_nfill = f;
     }
-    if (tid < k) s_c[tid] = p.cvec[tid];
+    if (tid < KB) s_c[tid] = tid < k ? p.cvec[tid] : 0.0;
+    for (int s = 0; s < nslot; ++s)  // zero padding vectors (never touched by the bulk copies)
+        for (int q = tid; q < (KB - k) * kSwTX; q += kSwThreads) slots[(size_t)s * SLOTD + (size_t)k * kSwTX + q] = 0.0;
     const double sin = p.in_scale != nullptr ? *p.in_scale : 1.0;
     __syncthreads();
-
-    // this CTA's share of the (strip, row) space: [u_begin, u_end) in strip-major order
-    const int64_t nstrip = (nx + kSwTXI - 1) / kSwTXI;
-    const int64_t total = nstrip * ny;
-    const int64_t u_begin = total * (int64_t)blockIdx.x / (int64_t)gridDim.x;
-    const int64_t u_end = total * ((int64_t)blockIdx.x + 1) / (int64_t)gridDim.x;
+    const int nseg = *s_nseg;
+    const uint32_t nfill = *s_nfill;
+    const uint32_t bar_full0 = smem_u32(bar_full), bar_empty0 = smem_u32(bar_empty), slots0 = smem_u32(slots);
 
     double acc_n = 0.0, acc_zy = 0.0;
     double acc_g[KB], acc_t[KB];
 #pragma unroll
     for (int j = 0; j < KB; ++j) acc_g[j] = acc_t[j] = 0.0;
 
-    // Thread t owns staged column t.  Rows flow through a ring of `nslot` shared-memory slots: the copies of row i + nslot - 1
-    // are issued right after the barrier of step i (every warp has then finished reading the slot of row i - 1), by the
-    // first lanes of every warp (vector v belongs to warp v % 8, lane v / 8); thread 0 arms the slot's mbarrier.
+    // ---- staging: copies of staged row f (cold path; lane v streams vector v) ----
+    auto issue = [&](uint32_t f) {
+        int sg = 0;
+        while (sg + 1 < nseg && s_seg[sg + 1].f0 <= f) ++sg;
+        const SwSeg g = s_seg[sg];
+        const int64_t rbeg = STENCIL ? (int64_t)g.r0 - 1 : (int64_t)g.r0;
+        const int64_t row = rbeg + (int64_t)(f - g.f0);
+        const int64_t c0 = g.c0;
+        const int64_t cend = c0 + txi + 2 * kSwHalo;
+        const int64_t cs = c0 < 0 ? 0 : c0, ce = cend < nx ? cend : nx;
+        const uint32_t nb = (uint32_t)(ce - cs) * 8u;
+        const int soff = (int)(cs - c0);
+        const bool wrap_l = p.wrap_x && c0 < 0;      // columns -2, -1 are columns nx-2, nx-1
+        const bool wrap_r = p.wrap_x && cend > nx;   // columns nx, nx+1 are columns 0, 1
+        const uint32_t vec_bytes = nb + (wrap_l ? 16u : 0u) + (wrap_r ? 16u : 0u);
+        const uint32_t slot = f % (uint32_t)nslot;
+        const bool inside = row >= 0 && row < ny;
+        const bool rowdata = inside || (row < 0 ? p.zin_lo != nullptr : p.zin_hi != nullptr);
+        if (f >= (uint32_t)nslot) mbar_wait(bar_empty0 + 8u * slot, ((f / (uint32_t)nslot) - 1u) & 1u);  // every warp released the slot
+        const uint32_t bar = bar_full0 + 8u * slot;
+        if (lane == 0) {
+            const uint32_t nv = rowdata ? (uint32_t)(k + 1) + ((HASCOEF && inside) ? 1u : 0u) : 0u;
+            if (nv != 0) mbar_arrive_expect_tx(bar, nv * vec_bytes);
+            else mbar_arrive(bar);
+        }
+        __syncwarp();
+        if (lane < nvec && rowdata) {
+            const double* src = nullptr;
+            if (lane < k) src = row < 0 ? p.S_lo[lane] : (row >= ny ? p.S_hi[lane] : p.S[lane] + row * nx);
+            else if (lane == k) src = row < 0 ? p.zin_lo : (row >= ny ? p.zin_hi : p.zin + row * nx);
+            else if (HASCOEF && inside) src = p.coef + row * nx;
+            if (src != nullptr) {
+                const int pos = lane < k ? lane : KB + (lane - k);
+                const uint32_t dst = slots0 + 8u * (slot * (uint32_t)SLOTD + (uint32_t)pos * kSwTX);
+                bulk_g2s(dst + 8u * soff, src + cs, nb, bar);
+                if (wrap_l) bulk_g2s(dst, src + (nx - 2), 16u, bar);
+                if (wrap_r) bulk_g2s(dst + 8u * (uint32_t)(nx - c0), src, 16u, bar);
+            }
+        }
+    };
+    // staged row f is issued by warp f % 8 when that warp starts its step f - lead; the first rows up front
+    const uint32_t lead = (uint32_t)(nslot - 2);
+    uint32_t fnext = (uint32_t)warp;  // next staged row this warp issues
+    for (; fnext < lead && fnext < nfill; fnext += kSwWarps) issue(fnext);
+
     {
-        const int t = tid;
         const Divisor dx2 = p.dx2d, dy2 = p.dy2d;
-        uint32_t cnt = 0;  // rows consumed so far by this CTA (slot = cnt % nslot, mbarrier parity = (cnt / nslot) & 1)
-        double sd[KB];     // the row of every S_j the sums of this step need
+        const int t = kSwHalo - 1 + tw * warp + lane;  // staged column of this lane: rim, tw owned columns, rim
+        const bool pushing = p.push_z_down != nullptr || p.push_z_up != nullptr || p.push_y_down != nullptr || p.push_y_up != nullptr;
+        double sd[KB];                                 // the row of every S_j the sums of this step need
 #pragma unroll
         for (int j = 0; j < KB; ++j) sd[j] = 0.0;
-        const int myvec = (lane < 4) ? lane * (kSwThreads / 32) + warp : nvec;  // the vector this lane streams (if < nvec)
-        for (int64_t u = u_begin; u < u_end;) {
-            const int64_t strip = u / ny, r0 = u - strip * ny;
-            const int64_t r1 = (r0 + (u_end - u) < ny) ? r0 + (u_end - u) : ny;
-            u += r1 - r0;
-            const int64_t c0 = strip * kSwTXI - kSwHalo;
-            const int64_t cs = c0 < 0 ? 0 : c0, ce = (c0 + kSwTX < nx) ? c0 + kSwTX : nx;
-            const uint32_t nb = (uint32_t)(ce - cs) * 8u;
-            const int soff = (int)(cs - c0);
-            const bool wrap_l = p.wrap_x && c0 < 0;           // columns -2, -1 are columns nx-2, nx-1
-            const bool wrap_r = p.wrap_x && c0 + kSwTX > nx;  // columns nx, nx+1 are columns 0, 1
-            const uint32_t vec_bytes = nb + (wrap_l ? 16u : 0u) + (wrap_r ? 16u : 0u);
+        uint32_t cnt = 0;                              // staged rows consumed so far
+        uint32_t slot = 0, par = 0;                    // = cnt % nslot, (cnt / nslot) & 1
+        const double* base = slots + t;                // this lane's column in the current slot
+        for (int sg = 0; sg < nseg; ++sg) {
+            const SwSeg g = s_seg[sg];
+            const int64_t c0 = g.c0, r0 = g.r0, r1 = g.r1;
             const int64_t gc = c0 + t;
+            const bool lane_on = lane <= tw + 1 && t < txi + 2 * kSwHalo;
             // columns whose z is meaningful: the grid, plus the periodic images next to it
-            const bool zvalid = (gc >= 0 && gc < nx) || (p.wrap_x && gc >= -kSwHalo && gc < nx + kSwHalo);
-            const bool interior = t >= kSwHalo && t < kSwTX - kSwHalo && gc < nx;
-            const int64_t rbeg = STENCIL ? r0 - 1 : r0, rend = STENCIL ? r1 + 1 : r1;
-            const int nrows = (int)(rend - rbeg);
-            const uint32_t cnt0 = cnt;  // value of cnt at the first row of this segment
-            auto issue = [&](int ri) {
-                const int64_t row = rbeg + ri;
-                const uint32_t f = cnt0 + (uint32_t)ri;
-                const int slot = (int)(f % (uint32_t)nslot);
-                const bool inside = row >= 0 && row < ny;
-                const bool rowdata = inside || (row < 0 ? p.zin_lo != nullptr : p.zin_hi != nullptr);
-                if (tid == 0) {
-                    const uint32_t nv = rowdata ? (uint32_t)(k + 1) + ((HASCOEF && inside) ? 1u : 0u) : 0u;
-                    if (nv != 0) mbar_arrive_expect_tx(bar_full + slot, nv * vec_bytes);
-                    else mbar_arrive(bar_full + slot);
-                }
-                if (myvec < nvec && rowdata) {
-                    const double* src = nullptr;
-                    if (myvec < k) src = row < 0 ? p.S_lo[myvec] : (row >= ny ? p.S_hi[myvec] : p.S[myvec] + row * nx);
-                    else if (myvec == k) src = row < 0 ? p.zin_lo : (row >= ny ? p.zin_hi : p.zin + row * nx);
-                    else if (HASCOEF && inside) src = p.coef + row * nx;
-                    if (src != nullptr) {
-                        double* dst = slots + (size_t)slot * slot_doubles + (size_t)myvec * kSwTX;
-                        bulk_g2s(dst + soff, src + cs, nb, bar_full + slot);
-                        if (wrap_l) bulk_g2s(dst, src + (nx - 2), 16u, bar_full + slot);
-                        if (wrap_r) bulk_g2s(dst + (nx - c0), src, 16u, bar_full + slot);
-                    }
-                }
-            };
-            // every warp is done with the previous segment's slots before they are refilled
-            __syncthreads();
-            for (int ri = 0; ri < nslot - 1 && ri < nrows; ++ri) issue(ri);
+            const bool zvalid = lane_on && ((gc >= 0 && gc < nx) || (p.wrap_x && gc >= -kSwHalo && gc < nx + kSwHalo));
+            const bool interior = lane_on && lane >= 1 && lane <= tw && t >= kSwHalo && t < kSwHalo + txi && gc < nx;
+            const int nown = (int)(r1 - r0);
+            const int nrows = STENCIL ? nown + 2 : nown;
+            const int first_own = STENCIL ? 1 : 0;   // loop index of row r0
+            // rim rows beyond a physical boundary carry no data: z = 0 there
+            const int zero_top = (STENCIL && r0 == 0 && p.zin_lo == nullptr) ? 0 : -1;
+            const int zero_bot = (STENCIL && r1 == ny && p.zin_hi == nullptr) ? nrows - 1 : -1;
+            double* zrow = p.zout != nullptr ? p.zout + r0 * nx + gc : nullptr;   // row r0 + (i - first_own)
+            double* yrow = STENCIL ? p.yout + r0 * nx + gc : nullptr;            // row r0 + (i - 2)
             double z1 = 0.0, z2 = 0.0, coefd = 0.0;
-            for (int i = 0; i < nrows; ++i, ++cnt) {
-                const int64_t row = rbeg + i;
-                const int slot = (int)(cnt % (uint32_t)nslot);
-                const uint32_t par = (cnt / (uint32_t)nslot) & 1u;
-                mbar_wait(bar_full + slot, par);
-                const double* base = slots + (size_t)slot * slot_doubles;
-                const bool rowdata = (row >= 0 && row < ny) || (row < 0 ? p.zin_lo != nullptr : p.zin_hi != nullptr);
-                double zt = 0.0;
+            for (int i = 0; i < nrows; ++i) {
+                if (cnt + lead == fnext) {  // staging duty of this step
+                    if (fnext < nfill) issue(fnext);
+                    fnext += kSwWarps;
+                }
+                mbar_wait(bar_full0 + 8u * slot, par);
+                const bool own_row = (unsigned)(i - first_own) < (unsigned)nown;
+                double zt = __dmul_rn(base[KB * kSwTX], sin);
                 if (!STENCIL) {
-                    if (rowdata && interior) {
-                        zt = __dmul_rn(base[k * kSwTX + t], sin);
 #pragma unroll
-                        for (int j = 0; j < KB; ++j)
-                            if (j < k) {
-                                sd[j] = base[j * kSwTX + t];
-                                zt = fma(-s_c[j], sd[j], zt);  // same order as successive kaxpy!
-                            }
+                    for (int j = 0; j < KB; ++j) {
+                        sd[j] = base[j * kSwTX];
+                        zt = fma(-s_c[j], sd[j], zt);  // same order as successive kaxpy!
+                    }
+                    if (interior) {
                         acc_n = fma(zt, zt, acc_n);
 #pragma unroll
-                        for (int j = 0; j < KB; ++j)
-                            if (j < k) acc_g[j] = fma(sd[j], zt, acc_g[j]);
-                        if (p.zout != nullptr) p.zout[row * nx + gc] = zt;
-                        if (row == 0 && p.push_z_down != nullptr) p.push_z_down[gc] = zt;
-                        if (row == ny - 1 && p.push_z_up != nullptr) p.push_z_up[gc] = zt;
+                        for (int j = 0; j < KB; ++j) acc_g[j] = fma(sd[j], zt, acc_g[j]);
+                        if (zrow != nullptr) *zrow = zt;
                     }
-                    __syncthreads();  // every warp has read the slot of row i - 1 ... and of this row
-                    if (i + nslot - 1 < nrows) issue(i + nslot - 1);
                 } else {
-                    if (rowdata && zvalid) {
-                        zt = __dmul_rn(base[k * kSwTX + t], sin);
 #pragma unroll
-                        for (int j = 0; j < KB; ++j)
-                            if (j < k) zt = fma(-s_c[j], base[j * kSwTX + t], zt);
-                    }
-                    const bool own_row = row >= r0 && row < r1;
-                    if (own_row && interior) {
-                        if (p.zout != nullptr) p.zout[row * nx + gc] = zt;
-                        if (row == 0 && p.push_z_down != nullptr) p.push_z_down[gc] = zt;
-                        if (row == ny - 1 && p.push_z_up != nullptr) p.push_z_up[gc] = zt;
-                    }
-                    s_z[(i % 3) * kSwTX + t] = zt;
-                    __syncthreads();  // z of this row is visible; every warp has finished step i - 1
-                    if (i + nslot - 1 < nrows) issue(i + nslot - 1);  // into the slot of row i - 1
+                    for (int j = 0; j < KB; ++j) zt = fma(-s_c[j], base[j * kSwTX], zt);
+                    if (!zvalid || i == zero_top || i == zero_bot) zt = 0.0;
+                    if (own_row && interior && zrow != nullptr) *zrow = zt;
+                    // y on row q = r0 + i - 2: z1 = z(q), z2 = z(q - 1), zt = z(q + 1); x-neighbours sit in the neighbouring lanes
+                    const double zl = __shfl_up_sync(0xffffffffu, z1, 1);
+                    const double zr = __shfl_down_sync(0xffffffffu, z1, 1);
                     if (i >= 2 && interior) {
-                        // y on row q = row - 1: z1 = z(q), z2 = z(q - 1), zt = z(q + 1); x-neighbours from shared memory
-                        const int64_t q = row - 1;
-                        const double* zrow = s_z + ((i + 2) % 3) * kSwTX;
-                        const double zl = zrow[t - 1], zr = zrow[t + 1];
                         const double xx = second_diff(zr, z1, zl, dx2);
                         const double yy = second_diff(zt, z1, z2, dy2);
                         const double lap = __dadd_rn(xx, yy);
@@ -276,31 +328,46 @@ __global__ void __launch_bounds__(kSwThreads, sw_min_blocks(KB)) k_sweep(const S
                         } else {  // tangent of G_Euler! / G_Trapezoid! around diffusion!: c1 * (a * lap) - v
                             y = __dsub_rn(__dmul_rn(p.c1, __dmul_rn(p.a, lap)), z1);
                         }
-                        p.yout[q * nx + gc] = y;
-                        if (q == 0 && p.push_y_down != nullptr) p.push_y_down[gc] = y;
-                        if (q == ny - 1 && p.push_y_up != nullptr) p.push_y_up[gc] = y;
+                        *yrow = y;
                         acc_n = fma(z1, z1, acc_n);
                         acc_zy = fma(z1, y, acc_zy);
 #pragma unroll
-                        for (int j = 0; j < KB; ++j)
-                            if (j < k) {
-                                acc_g[j] = fma(sd[j], z1, acc_g[j]);
-                                acc_t[j] = fma(sd[j], y, acc_t[j]);
-                            }
+                        for (int j = 0; j < KB; ++j) {
+                            acc_g[j] = fma(sd[j], z1, acc_g[j]);
+                            acc_t[j] = fma(sd[j], y, acc_t[j]);
+                        }
+                        if (pushing) {  // slabs: the first / last row of y goes to the neighbours (rare rows)
+                            const int64_t q = r0 + i - 2;
+                            if (q == 0 && p.push_y_down != nullptr) p.push_y_down[gc] = y;
+                            if (q == ny - 1 && p.push_y_up != nullptr) p.push_y_up[gc] = y;
+                        }
                     }
                     // this row becomes the delay line of the next step
                     if (own_row && interior) {
 #pragma unroll
-                        for (int j = 0; j < KB; ++j)
-                            if (j < k) sd[j] = base[j * kSwTX + t];
-                        if (HASCOEF) coefd = base[(k + 1) * kSwTX + t];
+                        for (int j = 0; j < KB; ++j) sd[j] = base[j * kSwTX];
+                        if (HASCOEF) coefd = base[(KB + 1) * kSwTX];
                     }
                     z2 = z1;
                     z1 = zt;
+                    if (i >= 2) yrow += nx;
                 }
+                if (pushing && own_row && interior) {
+                    const int64_t row = r0 + i - first_own;
+                    if (row == 0 && p.push_z_down != nullptr) p.push_z_down[gc] = zt;
+                    if (row == ny - 1 && p.push_z_up != nullptr) p.push_z_up[gc] = zt;
+                }
+                if (own_row && zrow != nullptr) zrow += nx;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty0 + 8u * slot);
+                ++cnt;
+                ++slot;
+                base += SLOTD;
+                if (slot == (uint32_t)nslot) { slot = 0; par ^= 1u; base = slots + t; }
             }
         }
     }
+    __syncthreads();
 
     // ---------------- deterministic grid reduction of the NS sums ----------------
     double vals[NS];
@@ -385,7 +452,7 @@ static int launch_sweep_t(Ctx* ctx, SweepArgs& a) {
         AK_CUDA(cudaFuncSetAttribute(k_sweep<KB, STENCIL, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwSmemMax));
         configured.store(1, std::memory_order_relaxed);
     }
-    const int nvec = a.k + 1 + ((STENCIL && OP == SW_OP_BRATU) ? 1 : 0);
+    const int nvec = KB + 1 + ((STENCIL && OP == SW_OP_BRATU) ? 1 : 0);  // slot positions (S_j padded to KB)
     const int slot_bytes = nvec * kSwTX * 8;
     int occ = sw_min_blocks(KB);
     if (const char* e = getenv("AK_SWEEP_OCC")) {  // tuning knob
@@ -409,12 +476,38 @@ static int launch_sweep_t(Ctx* ctx, SweepArgs& a) {
     }
     a.nslot = nslot;
     const size_t smem = (size_t)kSwOffSlots + (size_t)nslot * slot_bytes;
-    const int64_t nstrip = (a.nx + kSwTXI - 1) / kSwTXI;
-    const int64_t total = nstrip * a.ny;
+    // Decomposition.  Preferred: `strips` x `bands` = one wave of resident blocks, block b on strip b % strips, so that
+    // neighbouring strips advance side by side and the rim sectors they share are fetched from HBM once (L2 hit for the
+    // second reader): without it the staged rows read 8 % more than they own.  Otherwise: an even split of the
+    // (strip, row) space in strip-major order with the widest strips.
     int64_t grid = (int64_t)ctx->num_sms * occ;
-    const int64_t by_work = (total + 7) / 8;  // at least ~8 rows per block
-    if (grid > by_work) grid = by_work;
-    if (grid < 1) grid = 1;
+    a.txi = kSwTXI;
+    a.team_strips = a.team_bands = 0;
+    static const bool no_team = getenv("AK_SWEEP_NO_TEAM") != nullptr;  // tuning knob
+    if (!no_team) {
+        const int64_t smin = (a.nx + kSwTXI - 1) / kSwTXI, smax = (a.nx + 159) / 160;
+        for (int64_t st = smin; st <= smax && st <= grid; ++st) {
+            if (grid % st != 0) continue;
+            const int64_t bands = grid / st;
+            if (a.ny < 16 * bands) break;  // too few rows per band: the rim rows would dominate
+            int64_t txi = (a.nx + st - 1) / st;
+            txi += txi & 1;
+            if (txi > kSwTXI || (st - 1) * txi >= a.nx) continue;
+            a.txi = (int32_t)txi;
+            a.team_strips = (int32_t)st;
+            a.team_bands = (int32_t)bands;
+            break;
+        }
+    }
+    a.tw = (a.txi + kSwWarps - 1) / kSwWarps;
+    if (a.team_strips == 0) {
+        const int64_t nstrip = (a.nx + a.txi - 1) / a.txi;
+        const int64_t total = nstrip * a.ny;
+        const int64_t by_work = (total + 7) / 8;  // at least ~8 rows per block
+        if (grid > by_work) grid = by_work;
+        if (nstrip > 6 * grid) grid = (nstrip + 5) / 6;  // a block's share spans at most kSwMaxSeg strips
+        if (grid < 1) grid = 1;
+    }
     ProfScope prof(ctx, PK_SWEEP);
     k_sweep<KB, STENCIL, OP><<<(int)grid, kSwThreads, smem, ctx->stream>>>(a);
     ctx->launches++;

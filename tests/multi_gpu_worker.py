@@ -259,18 +259,21 @@ def run_cases(ctx, rank, world, rng, tag):
         else:
             prob = F_.problem(u, p)
             import ctypes as C
-            o = nk.host._newton_opts(1e-6, 6e-6, 50, nk.EisenstatWalker(), "gmres", 20, 0,
-                                     dict(fuse="pair") if tag == "p2p" else {})
-            nsteps = 2
-            newt, inner, solved = np.zeros(nsteps, np.int32), np.zeros(nsteps, np.int64), np.zeros(nsteps, np.int32)
-            un = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
-            nk._lib.check(ctx.lib.ak_implicit_solve(ctx.h, C.byref(prob), C.c_void_p(un.ptr), nsteps, C.byref(o),
-                                                    newt.ctypes.data_as(A.c_int32_p), inner.ctypes.data_as(A.c_int64_p),
-                                                    solved.ctypes.data_as(A.c_int32_p)))
-            ur, nr, ir, sr_ = O.implicit_solve(po, d["u0"], nsteps, o)
-            assert list(newt) == list(nr) and list(solved) == list(sr_), (name, newt, nr)
-            assert all(abs(int(a) - int(b)) <= 1 for a, b in zip(inner, ir)), (name, inner, ir)
-            assert rel(un.numpy(), ur[sl]) < 1e-7, name
+            # peer memory: the pair-wise sweep and the one-sweep kernels (ghost rows of every basis vector pushed by
+            # the neighbours; with and without the second Gram-Schmidt sweep)
+            variants = [dict(fuse="pair"), dict(fuse="sweep"), dict(fuse="sweep", reorthogonalization=True)] if tag == "p2p" else [{}]
+            for kk in variants:
+                o = nk.host._newton_opts(1e-6, 6e-6, 50, nk.EisenstatWalker(), "gmres", 20, 0, dict(kk))
+                nsteps = 2
+                newt, inner, solved = np.zeros(nsteps, np.int32), np.zeros(nsteps, np.int64), np.zeros(nsteps, np.int32)
+                un = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
+                nk._lib.check(ctx.lib.ak_implicit_solve(ctx.h, C.byref(prob), C.c_void_p(un.ptr), nsteps, C.byref(o),
+                                                        newt.ctypes.data_as(A.c_int32_p), inner.ctypes.data_as(A.c_int64_p),
+                                                        solved.ctypes.data_as(A.c_int32_p)))
+                ur, nr, ir, sr_ = O.implicit_solve(po, d["u0"], nsteps, o)
+                assert list(newt) == list(nr) and list(solved) == list(sr_), (name, kk, newt, nr)
+                assert all(abs(int(a) - int(b)) <= 1 for a, b in zip(inner, ir)), (name, kk, inner, ir)
+                assert rel(un.numpy(), ur[sl]) < 1e-7, (name, kk)
         if rank == 0:
             print(f"[multi-gpu x{world} {tag}] {name}: ok", flush=True)
 

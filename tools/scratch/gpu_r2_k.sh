@@ -1,0 +1,11 @@
+#!/bin/bash
+# round 2, session K (1 GPU): sweep kernel with unpredicated j loops (zero-padded slot layout); DG at 32 registers
+mkdir -p gpurun_out
+timeout 420 python -m pytest tests/test_gpu_sweep.py -m gpu -q --maxfail=40 --tb=short > gpurun_out/r2k_pytest_sweep.log 2>&1
+echo "pytest sweep rc=$?" | tee -a gpurun_out/r2k_pytest_sweep.log; tail -5 gpurun_out/r2k_pytest_sweep.log
+timeout 200 python tools/sweep_bench.py > gpurun_out/r2k_sweep_bench.txt 2>&1; echo "sweep_bench rc=$?"; tail -8 gpurun_out/r2k_sweep_bench.txt
+AK_SWEEP_NO_TEAM=1 timeout 200 python tools/sweep_bench.py > gpurun_out/r2k_sweep_bench_noteam.txt 2>&1; echo "noteam rc=$?"; tail -8 gpurun_out/r2k_sweep_bench_noteam.txt
+AK_SWEEP_DEBUG=1 timeout 200 python tools/sweep_bench.py --short > gpurun_out/r2k_sweep_debug.txt 2>&1; echo "debug rc=$?"; grep k_sweep gpurun_out/r2k_sweep_debug.txt | head -22
+timeout 240 ncu --kernel-name regex:k_sweep --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 21 --csv --log-file gpurun_out/r2k_sweep_launches.csv python tools/sweep_bench.py --short > gpurun_out/r2k_ncu.log 2>&1; echo "ncu rc=$?"
+timeout 100 python tools/dg_bench.py > gpurun_out/r2k_dg_bench.txt 2>&1; cat gpurun_out/r2k_dg_bench.txt
+timeout 300 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_solvers.py -m gpu -q --maxfail=20 --tb=short -k "dg or DG" > gpurun_out/r2k_pytest_dg.log 2>&1; tail -3 gpurun_out/r2k_pytest_dg.log
