@@ -996,9 +996,19 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
         npass += 1;
         int wa = 0;  // one-sweep iterations: the W buffer that holds the raw tangent J S_{k-1} of the next iteration
         if (sweep) {
-            // opening sweep of the cycle: W <- J S_0 and <S_0, W> (queued behind the prologue; a no-op after a stop)
-            if (sw_p2p) AK_TRY(sweep_push_rows(c, ws->V[0], prob->nx, prob->ny, prob->bc, 0));
-            AK_TRY(sweep_launch(0, ws->V[0], 0, nullptr, -1, true, ws->w[wa], sw_wslot(wa), nullptr));
+            // opening of the cycle: W <- J S_0 and <S_0, W>, queued behind the prologue (a no-op after a stop).  There is
+            // no basis to sweep over yet, so this is the plain tangent kernel with its fused dot (0.26 ms at 8192^2; the
+            // sweep kernel with an empty basis took 0.65 ms: its per-row bookkeeping has nothing to hide behind).
+            JvpFusion of;
+            of.stop_flag = &ws->ctl->stop;
+            of.dot_with = ws->V[0];
+            of.dot_dev = ws->sw_sums + 1;
+            AK_TRY(launch_jvp(c, prob, u, ws->V[0], ws->w[wa], &of));
+            if (sw_p2p) {  // slabs: the sweeps read the neighbours' boundary rows of S_0 and W from their ghost-row slots
+                AK_TRY(sweep_push_rows(c, ws->V[0], prob->nx, prob->ny, prob->bc, 0));
+                AK_TRY(sweep_push_rows(c, ws->w[wa], prob->nx, prob->ny, prob->bc, sw_wslot(wa)));
+            }
+            sw_seq = 0;  // the dot is already summed over the ranks
             AK_TRY(sweep_scalar(0, 0, 0, 0, &ws->status[kStatusRing]));
         }
 

@@ -34,7 +34,7 @@ constexpr int kSwWarps = kSwThreads / 32;
 constexpr int kSwTW = 30;                        // columns a warp owns at most (32 lanes = 30 + one rim lane per side)
 constexpr int kSwHalo = 2;                       // rim columns staged per side (two, so that every bulk copy is 16-byte aligned)
 constexpr int kSwTXI = kSwWarps * kSwTW;         // 240: widest strip a block owns
-constexpr int kSwTX = 256;                       // doubles per staged vector row (>= kSwTXI + 2 * kSwHalo)
+constexpr int kSwTX = kSwTXI + 2 * kSwHalo;      // 244 doubles per staged vector row (1952 bytes: a multiple of 16)
 constexpr int kSwMaxSlots = 8;
 constexpr int kSwMaxSeg = 8;                     // segments (strip, row range) one block may be given
 // shared-memory map (bytes): barriers | coefficients, flag | segment table | reduction scratch | slots
@@ -56,6 +56,7 @@ struct SweepArgs {
     int32_t tw;         // columns a warp owns: ceil(txi / 8)
     int32_t team_strips;  // > 0: block b owns strip b % team_strips, row band b / team_strips of team_bands (neighbouring
     int32_t team_bands;   //      strips run side by side, so their shared rim sectors hit L2); 0: even split of (strip, row)
+    int32_t slack;        // a staged row is issued `nslot - slack` steps ahead of its use, `slack` steps after its slot's last use
     const double* S[kSwKMax];
     const double* S_lo[kSwKMax];  // ghost row y = -1 of S_j (nullptr: zero)
     const double* S_hi[kSwKMax];  // ghost row y = ny
@@ -122,7 +123,7 @@ AK_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar
 }
 
 // resident blocks per SM the register budget is sized for (8 warps: 255 / 128 / 80 registers per thread)
-constexpr int sw_min_blocks(int kb) { return kb <= 4 ? 3 : (kb <= 8 ? 2 : 1); }
+constexpr int sw_min_blocks(int kb) { return kb <= 4 ? 3 : (kb <= 12 ? 2 : 1); }
 
 struct SwSeg {       // one (strip, row range) of a block; rows are consumed in the order of the table
     int32_t c0;      // first staged column (strip start - rim), may be -2
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(kSwThreads, sw_min_blocks(KB)) k_sweep(const S
         }
     };
     // staged row f is issued by warp f % 8 when that warp starts its step f - lead; the first rows up front
-    const uint32_t lead = (uint32_t)(nslot - 2);
+    const uint32_t lead = (uint32_t)(nslot - p.slack);
     uint32_t fnext = (uint32_t)warp;  // next staged row this warp issues
     for (; fnext < lead && fnext < nfill; fnext += kSwWarps) issue(fnext);
 
@@ -475,6 +476,11 @@ static int launch_sweep_t(Ctx* ctx, SweepArgs& a) {
         if (v >= 3 && v <= nslot) nslot = v;
     }
     a.nslot = nslot;
+    a.slack = nslot >= 4 ? 2 : 1;  // three slots: refill right behind the last reader, or nothing would be in flight
+    if (const char* e = getenv("AK_SWEEP_SLACK")) {  // tuning knob
+        const int v = atoi(e);
+        if (v >= 1 && v < nslot) a.slack = v;
+    }
     const size_t smem = (size_t)kSwOffSlots + (size_t)nslot * slot_bytes;
     // Decomposition.  Preferred: `strips` x `bands` = one wave of resident blocks, block b on strip b % strips, so that
     // neighbouring strips advance side by side and the rim sectors they share are fetched from HBM once (L2 hit for the
@@ -483,7 +489,8 @@ static int launch_sweep_t(Ctx* ctx, SweepArgs& a) {
     int64_t grid = (int64_t)ctx->num_sms * occ;
     a.txi = kSwTXI;
     a.team_strips = a.team_bands = 0;
-    static const bool no_team = getenv("AK_SWEEP_NO_TEAM") != nullptr;  // tuning knob
+    static const int team_env = [] { const char* e = getenv("AK_SWEEP_TEAM"); return e ? atoi(e) : -1; }();  // tuning knob: 0 / 1
+    const bool no_team = team_env == 0;
     if (!no_team) {
         const int64_t smin = (a.nx + kSwTXI - 1) / kSwTXI, smax = (a.nx + 159) / 160;
         for (int64_t st = smin; st <= smax && st <= grid; ++st) {
