@@ -293,7 +293,7 @@ typedef struct ak_krylov_stats {
 } ak_krylov_stats;
 
 /* Krylov.jl keyword defaults (atol = rtol = sqrt(eps), itmax = 0, no restart, no preconditioners) and
- * fuse = AK_FUSE_BLOCK8, the fastest level (falls back by itself where a level does not apply).          */
+ * fuse = AK_FUSE_SWEEP, the fastest level (falls back by itself to BLOCK8 where it does not apply).        */
 void ak_krylov_default_opts(ak_krylov_opts* o);
 /* krylov_workspace(algo, KrylovConstructor(res)): `memory` = 20 in Krylov.jl;
  * max_basis caps how far a non-restarted basis may grow (0 => as HBM allows)     */

@@ -396,7 +396,7 @@ solution(ws::Workspace) = B200Vector{1}(ccall((:ak_krylov_x, lib), Ptr{Float64},
 # Krylov.jl keyword set of the reference call sites: `verbose`, `timemax`, `callback` are accepted and ignored
 # (examples/heat_2D.jl:131 passes `verbose = 1`); `history = true` fills `ws.residuals`.
 function krylov_solve!(ws::Workspace, J::JacobianOperator, b::B200Vector; atol = √eps(Float64), rtol = √eps(Float64),
-                       itmax = 0, restart = false, reorthogonalization = false, history = false, fuse = :block8,
+                       itmax = 0, restart = false, reorthogonalization = false, history = false, fuse = :sweep,
                        M = nothing, N = nothing, ldiv = false, verbose = 0, timemax = Inf, callback = nothing)
     (N isa TridiagonalLU || M isa TridiagonalLU) && !ldiv && error("ilu(J) is applied with ldiv = true (examples/bratu.jl:126)")
     # caller-supplied preconditioners travel as (object, n) behind a rooted Ref for the duration of the solve
@@ -491,7 +491,7 @@ function newton_opts(; tol_rel = 1.0e-6, tol_abs = 1.0e-12, max_niter = 50, forc
     end
     ko = AkKrylovOpts(get(kk, :atol, √eps(Float64)), get(kk, :rtol, √eps(Float64)), get(kk, :itmax, 0),
                       get(kk, :restart, false), get(kk, :reorthogonalization, false), get(kk, :history, false),
-                      fuse_code(get(kk, :fuse, :block8)), AK_PRECOND_NONE, 0, AK_PRECOND_NONE, 0, C_NULL, C_NULL, C_NULL, C_NULL)
+                      fuse_code(get(kk, :fuse, :sweep)), AK_PRECOND_NONE, 0, AK_PRECOND_NONE, 0, C_NULL, C_NULL, C_NULL, C_NULL)
     fc, η, ηmax, γ = forcing === nothing ? (AK_FORCING_NONE, 0.1, 0.999, 0.9) :
                      forcing isa Fixed ? (AK_FORCING_FIXED, forcing.η, 0.999, 0.9) : (AK_FORCING_EW, 0.1, forcing.η_max, forcing.γ)
     return AkNewtonOpts(tol_rel, tol_abs, max_niter, fc, η, ηmax, γ, AK_ALGO[algo], memory, max_basis, ko,

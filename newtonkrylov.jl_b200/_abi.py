@@ -127,7 +127,7 @@ SQRT_EPS = 2.220446049250313e-16 ** 0.5
 
 def default_krylov_opts(**kw):
     """Krylov.jl gmres!/cg! keyword defaults (atol = rtol = sqrt(eps), itmax = 0 -> 2n)."""
-    o = ak_krylov_opts(SQRT_EPS, SQRT_EPS, 0, 0, 0, 0, AK_FUSE_BLOCK8, AK_PRECOND_NONE, 0, AK_PRECOND_NONE, 0, None, None, None, None)
+    o = ak_krylov_opts(SQRT_EPS, SQRT_EPS, 0, 0, 0, 0, AK_FUSE_SWEEP, AK_PRECOND_NONE, 0, AK_PRECOND_NONE, 0, None, None, None, None)
     for k, v in kw.items():
         if not hasattr(o, k):
             raise TypeError(f"unknown krylov kwarg {k!r}")

@@ -1503,7 +1503,7 @@ AK_API void ak_krylov_default_opts(ak_krylov_opts* o) {
     memset(o, 0, sizeof(*o));
     o->atol = sqrt(2.220446049250313e-16);
     o->rtol = sqrt(2.220446049250313e-16);
-    o->fuse = AK_FUSE_BLOCK8;
+    o->fuse = AK_FUSE_SWEEP;  // one sweep per iteration where it applies, the eight-step blocked passes everywhere else
 }
 
 AK_API int ak_krylov_create(ak_ctx* ctx, int32_t algo, int64_t n, int32_t memory, int64_t max_basis, ak_krylov** out) {

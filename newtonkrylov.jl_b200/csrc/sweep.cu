@@ -490,7 +490,9 @@ static int launch_sweep_t(Ctx* ctx, SweepArgs& a) {
     a.txi = kSwTXI;
     a.team_strips = a.team_bands = 0;
     static const int team_env = [] { const char* e = getenv("AK_SWEEP_TEAM"); return e ? atoi(e) : -1; }();  // tuning knob: 0 / 1
-    const bool no_team = team_env == 0;
+    // measured per class at 8192^2 (profiles/r02_sweep_tuning.md): side-by-side strips win wherever two or three blocks
+    // share an SM and at KB = 20; at KB = 16 (one block per SM, six slots) the 8 % wider strips of the even split do
+    const bool no_team = team_env == 0 || (team_env < 0 && KB == 16);
     if (!no_team) {
         const int64_t smin = (a.nx + kSwTXI - 1) / kSwTXI, smax = (a.nx + 159) / 160;
         for (int64_t st = smin; st <= smax && st <= grid; ++st) {

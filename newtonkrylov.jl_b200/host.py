@@ -876,7 +876,7 @@ def krylov_workspace(algo, kc, memory=20, max_basis=0):
 
 
 def krylov_solve_(workspace, J, b, atol=A.SQRT_EPS, rtol=A.SQRT_EPS, itmax=0, restart=False,
-                  reorthogonalization=False, history=False, fuse="block8", verbose=0, M=None, N=None, ldiv=False,
+                  reorthogonalization=False, history=False, fuse="sweep", verbose=0, M=None, N=None, ldiv=False,
                   **unsupported):
     """krylov_solve!(workspace, J, b; kwargs...) — solves J x = b from x0 = 0.
     `M` / `N`: left / right preconditioner objects (GmresPreconditioner, ilu(J), JacobiPreconditioner,
@@ -1008,7 +1008,7 @@ def _newton_opts(tol_rel, tol_abs, max_niter, forcing, algo, memory, max_basis, 
                  M=None, J=None, keep=None, native_loop=False):
     kk = dict(krylov_kwargs or {})
     override = "rtol" in kk
-    fuse = kk.pop("fuse", "block8")
+    fuse = kk.pop("fuse", "sweep")
     ldiv = bool(kk.pop("ldiv", False))
     n = len(J.u) if J is not None else 0
     def built_once(P, side):

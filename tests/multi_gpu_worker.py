@@ -249,7 +249,12 @@ def run_cases(ctx, rank, world, rng, tag):
             for fuse in ("none", "mgs", "full", "pair", "block4", "block8", "sweep"):
                 u = nk.DeviceVector.from_numpy(d["u0"][sl], ctx)
                 hist = []
+                ctx.profile(True)
                 _, r = nk.newton_krylov_native_(F_, u, p, None, history=hist, krylov_kwargs=dict(fuse=fuse))
+                nsweep = ctx.profile_read(13)[0]
+                ctx.profile(False)
+                # the one-sweep kernels really ran on the slabs (peer memory, even row length), and only there
+                assert (nsweep > 0) == (fuse == "sweep" and tag == "p2p" and nx % 2 == 0), (name, fuse, tag, nsweep)
                 ur, sr, hr = O.newton(po, d["u0"])
                 assert r.solved and r.stats.outer_iterations == sr["outer_iterations"], (name, fuse, r, sr)
                 assert [h["inner"] for h in hist] == [h["inner"] for h in hr], (name, fuse)

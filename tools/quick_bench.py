@@ -44,7 +44,7 @@ ws = nk.krylov_workspace("gmres", nk.KrylovConstructor(res), memory=20)
 J = nk.JacobianOperator(nk.bratu2d_, res, u, (dx, dx, 3.5), coef=coef)
 lib.ak_residual(h, C.byref(prob), P(u), P(res), None)
 b = res.copy()
-for fuse in ("none", "mgs", "full", "pair", "block4", "block8"):
+for fuse in ("none", "mgs", "full", "pair", "block4", "block8", "sweep"):
     for _ in range(2):
         ctx.sync(); ctx.launch_count(reset=True)
         ctx.timer_start()
@@ -52,7 +52,7 @@ for fuse in ("none", "mgs", "full", "pair", "block4", "block8"):
         ms = ctx.timer_stop()
     it = ws.stats.niter
     ref_bytes = 2 * 8 * n * (5 * 20 * 21 / 2 + 6 * 20)
-    print(f"gmres(20) fuse={fuse:5s} {it} its in {ms:8.2f} ms -> {it/ms*1e3:7.1f} it/s ; reference-op-list traffic {ref_bytes/ms/1e6:8.1f} GB/s "
+    print(f"gmres(20) fuse={fuse:6s} {it} its in {ms:8.2f} ms -> {it/ms*1e3:7.1f} it/s ; reference-op-list traffic {ref_bytes/ms/1e6:8.1f} GB/s "
           f"({ref_bytes/ms/1e6/6552.6*100:5.1f}% of peak); launches {ctx.launch_count()}")
 
 # ---- other BASELINE configs at full size: kernel GB/s (C2 heat 1-D 2^24, C3 heat 2-D 8192^2, C5 DG 2^22 elements)
