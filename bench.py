@@ -220,7 +220,7 @@ class Workload:
         return units
 
     def sweep_active(self):
-        return self.fuse == "sweep" and self.cfg["kind"] in ("bratu2d", "heat2d") and MEMORY <= SWEEP_KMAX
+        return self.fuse == "sweep" and MEMORY <= SWEEP_KMAX  # every config of the bench has a sweep kernel
 
     def sweep_units(self):
         """8n-byte units of the sweep kernels of one step (csrc/sweep.cu): iteration k reads S_0..S_{k-1} and W, writes S_k

@@ -178,15 +178,14 @@ static int p2p_exchange(Ctx* ctx, const double* v, int64_t n, int cnt_up, int cn
 
 // One-sweep GMRES on slabs: the opening vector of a cycle (r0) did not come out of a sweep, so its boundary rows are
 // pushed into the neighbours' ghost rows of sweep slot `slot` here (peer stores + the all-to-all signal of k_push_ghost).
-int sweep_push_rows(Ctx* ctx, const double* v, int64_t nx, int64_t ny, int32_t bc, int slot) {
+int sweep_push_rows(Ctx* ctx, const double* v, int64_t n, int count, bool periodic, int slot) {
     const int P = ctx->nranks, r = ctx->rank;
     if (P <= 1) return AK_OK;
-    AK_REQUIRE(ctx->p2p_on && nx <= ctx->p2p_halo_cap && slot >= 0 && slot < kSwGhostSlots, "sweep_push_rows: peer memory not set up for this row length");
-    const bool periodic = (bc == AK_BC_PERIODIC);
+    AK_REQUIRE(ctx->p2p_on && count <= ctx->p2p_halo_cap && slot >= 0 && slot < kSwGhostSlots, "sweep_push_rows: peer memory not set up for this row length");
     const int down = (r > 0) ? r - 1 : (periodic ? P - 1 : -1);
     const int up = (r < P - 1) ? r + 1 : (periodic ? 0 : -1);
     const unsigned long long seq = ++ctx->p2p_seq;
-    k_push_ghost<<<1, 1024, 0, ctx->stream>>>(v, nx * ny, (int)nx, (int)nx, up >= 0 ? ctx->p2p_swghost_of(up, slot, 0) : nullptr,
+    k_push_ghost<<<1, 1024, 0, ctx->stream>>>(v, n, count, count, up >= 0 ? ctx->p2p_swghost_of(up, slot, 0) : nullptr,
                                               down >= 0 ? ctx->p2p_swghost_of(down, slot, 1) : nullptr, ctx->p2p_dev(), seq);
     ctx->launches++;
     AK_CUDA(cudaGetLastError());

@@ -865,7 +865,7 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     const bool p2p_halo = p2p && !hosted && is2d && prob->nx % 4 == 0 && n % 4 == 0 && prob->nx <= c->p2p_halo_cap;
     int nb_down = -1, nb_up = -1;  // owners of the ghost rows below / above this slab
     if (p2p_halo || (sweep && p2p)) {
-        const bool per = (prob->bc == AK_BC_PERIODIC);
+        const bool per = is2d ? (prob->bc == AK_BC_PERIODIC) : (prob->kind == AK_HEAT1D_DG);
         nb_down = c->rank > 0 ? c->rank - 1 : (per ? c->nranks - 1 : -1);
         nb_up = c->rank < c->nranks - 1 ? c->rank + 1 : (per ? 0 : -1);
     }
@@ -918,6 +918,9 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
 
     // ---- one-sweep iterations (sweep.cu) -----------------------------------------------------------------------------
     const bool sw_p2p = sweep && p2p;
+    // what the neighbours exchange: a boundary row (slabs), two points (1-D segments), one element (DG, periodic mesh)
+    const int sw_cnt = is2d ? (int)prob->nx : (prob->kind == AK_HEAT1D_DG ? 4 : 2);
+    const bool sw_per = is2d ? (prob->bc == AK_BC_PERIODIC) : (prob->kind == AK_HEAT1D_DG);
     unsigned long long sw_seq = 0;  // record the last sweep posted its sums under (peer memory), 0 otherwise
     auto sw_wslot = [&](int wbuf) -> int { return kSwKMax + 1 + wbuf; };  // ghost-row slot of W buffer `wbuf`
     std::vector<const double*> sw_lo((size_t)kSwKMax, nullptr), sw_hi((size_t)kSwKMax, nullptr);
@@ -1005,8 +1008,8 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
             of.dot_dev = ws->sw_sums + 1;
             AK_TRY(launch_jvp(c, prob, u, ws->V[0], ws->w[wa], &of));
             if (sw_p2p) {  // slabs: the sweeps read the neighbours' boundary rows of S_0 and W from their ghost-row slots
-                AK_TRY(sweep_push_rows(c, ws->V[0], prob->nx, prob->ny, prob->bc, 0));
-                AK_TRY(sweep_push_rows(c, ws->w[wa], prob->nx, prob->ny, prob->bc, sw_wslot(wa)));
+                AK_TRY(sweep_push_rows(c, ws->V[0], n, sw_cnt, sw_per, 0));
+                AK_TRY(sweep_push_rows(c, ws->w[wa], n, sw_cnt, sw_per, sw_wslot(wa)));
             }
             sw_seq = 0;  // the dot is already summed over the ranks
             AK_TRY(sweep_scalar(0, 0, 0, 0, &ws->status[kStatusRing]));

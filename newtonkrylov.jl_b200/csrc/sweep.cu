@@ -19,6 +19,7 @@
 // ring of shared-memory slots with cp.async.bulk (completion on an mbarrier per slot); 256 consumer threads own one
 // column each, keep the sums in registers and the previous row of every S_j as the delay line the projections of y
 // need.  The persistent grid splits the (strip, row) space evenly, so the rim costs 2 rows per ~1800.
+#include <math.h>
 #include <stdlib.h>
 
 #include <atomic>
@@ -82,6 +83,13 @@ struct SweepArgs {
     P2PDev pd;
     unsigned long long seq_out;   // != 0: the sums travel through the ranks' sweep mailboxes
     double* swmail_peer[kMaxPeers];
+    // 1-D problems (k_sweep1d): nx = unknowns, ny = 1; S_lo / S_hi / zin_lo / zin_hi point at `halo` ghost values
+    int32_t halo;                 // rim values staged per side: 2 (three-point stencils), 4 (DG: one element)
+    int32_t wrap;                 // periodic (DG on one GPU): the rim of the first / last chunk is the other end of the vector
+    int32_t seg_first, seg_last;  // heat 1-D: this rank holds the global first / last point (bc! acts there); 0 otherwise
+    double D[4][4];               // DG: LGL derivative matrix, 2/h, (h/2) w_edge
+    double jac;
+    Divisor mwd;
 };
 
 // ---- mbarrier / bulk-copy PTX ------------------------------------------------------------------------------------
@@ -124,6 +132,88 @@ AK_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar
 
 // resident blocks per SM the register budget is sized for (8 warps: 255 / 128 / 80 registers per thread)
 constexpr int sw_min_blocks(int kb) { return kb <= 4 ? 3 : (kb <= 12 ? 2 : 1); }
+
+// Deterministic grid reduction of the 2 KB + 2 sums of a sweep and their hand-over: one partial per block, the block
+// that takes the last ticket adds them in index order and either stores the totals or posts them to every rank's sweep
+// mailbox (peer memory).  Called by all threads of every block.
+template <int KB>
+AK_DEV void sweep_reduce(const SweepArgs& p, int k, double acc_n, double acc_zy, const double (&acc_g)[KB],
+                         const double (&acc_t)[KB], double* s_red, int* s_last_p) {
+    constexpr int NS = 2 * KB + 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double vals[NS];
+    vals[0] = acc_n;
+    vals[1] = acc_zy;
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+        vals[2 + j] = acc_g[j];
+        vals[2 + KB + j] = acc_t[j];
+    }
+#pragma unroll
+    for (int c = 0; c < NS; ++c) {
+        const double v = warp_sum(vals[c]);
+        if (lane == 0) s_red[warp * NS + c] = v;
+    }
+    __syncthreads();
+    const int nblocks = gridDim.x, bid = blockIdx.x;
+    if (tid < NS) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kSwWarps; ++w) s += s_red[w * NS + tid];
+        p.partials[(size_t)bid * NS + tid] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (p.seq_out != 0) __threadfence_system();  // rows pushed to the neighbours precede the record
+        const unsigned int tk = atomicAdd(p.ticket, 1u);
+        *s_last_p = (tk == (unsigned int)(nblocks - 1));
+    }
+    __syncthreads();
+    if (!*s_last_p) return;
+    __threadfence();
+    // four threads per sum, each over a contiguous quarter of the blocks; quarters added in order
+    {
+        const int c = tid >> 2, part = tid & 3;
+        double s = 0.0;
+        if (c < NS) {
+            const int b0 = nblocks * part / 4, b1 = nblocks * (part + 1) / 4;
+            for (int b = b0; b < b1; ++b) s += __ldcg(p.partials + (size_t)b * NS + c);
+        }
+        const int gl = lane & ~3;
+        const double q0 = __shfl_sync(0xffffffffu, s, gl), q1 = __shfl_sync(0xffffffffu, s, gl + 1);
+        const double q2 = __shfl_sync(0xffffffffu, s, gl + 2), q3 = __shfl_sync(0xffffffffu, s, gl + 3);
+        if (c < NS && part == 0) s_red[c] = ((q0 + q1) + q2) + q3;
+    }
+    __syncthreads();
+    if (tid < NS) {
+        // layout of sums_out (sweep.h): [0] ||z||^2, [1] <z,y>, [2 + j] g_j, [2 + kSwKMax + j] t_j
+        const int dst = tid < 2 ? tid : (tid < 2 + KB ? tid : tid - KB + kSwKMax);
+        const bool used = tid < 2 || (tid < 2 + KB ? tid - 2 < k : tid - 2 - KB < k);
+        if (used && p.seq_out == 0) p.sums_out[dst] = s_red[tid];
+        if (p.seq_out != 0) {
+            // every rank's record goes into every rank's sweep mailbox; the scalar kernel adds them in rank order
+            const int slot = (int)(p.seq_out % kMailSlots);
+            for (int q = 0; q < p.pd.nranks; ++q) {
+                double* rec = p.swmail_peer[q] + ((size_t)slot * p.pd.nranks + p.pd.rank) * kSwMailRec;
+                rec[dst] = used ? s_red[tid] : 0.0;
+            }
+            __threadfence_system();
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (p.seq_out != 0) {
+            __threadfence_system();
+            const int slot = (int)(p.seq_out % kMailSlots);
+            for (int q = 0; q < p.pd.nranks; ++q) {
+                double* rec = p.swmail_peer[q] + ((size_t)slot * p.pd.nranks + p.pd.rank) * kSwMailRec;
+                st_release_sys_u64(reinterpret_cast<unsigned long long*>(rec + kSwSums), p.seq_out);
+            }
+        }
+        *p.ticket = 0u;
+    }
+}
 
 struct SwSeg {       // one (strip, row range) of a block; rows are consumed in the order of the table
     int32_t c0;      // first staged column (strip start - rim), may be -2
@@ -370,79 +460,205 @@ __global__ void __launch_bounds__(kSwThreads, sw_min_blocks(KB)) k_sweep(const S
     }
     __syncthreads();
 
-    // ---------------- deterministic grid reduction of the NS sums ----------------
-    double vals[NS];
-    vals[0] = acc_n;
-    vals[1] = acc_zy;
-#pragma unroll
-    for (int j = 0; j < KB; ++j) {
-        vals[2 + j] = acc_g[j];
-        vals[2 + KB + j] = acc_t[j];
-    }
-#pragma unroll
-    for (int c = 0; c < NS; ++c) {
-        const double v = warp_sum(vals[c]);
-        if (lane == 0) s_red[warp * NS + c] = v;
-    }
-    __syncthreads();
-    const int nblocks = gridDim.x, bid = blockIdx.x;
-    if (tid < NS) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kSwWarps; ++w) s += s_red[w * NS + tid];
-        p.partials[(size_t)bid * NS + tid] = s;
-        __threadfence();
-    }
-    __syncthreads();
+    sweep_reduce<KB>(p, k, acc_n, acc_zy, acc_g, acc_t, s_red, s_last_p);
+}
+
+
+// ====================================================================================================================
+// 1-D problems: Bratu 1-D (examples/bratu.jl:14-24), heat 1-D with bc! (examples/heat_1D.jl:12-37 behind G_Euler!), DG heat
+// (examples/heat_1D_DG.jl:32-36).  Same pass, same ring, same scalar step; the "rows" are consecutive chunks of the
+// vector, the stencil couples a point only to its chunk neighbours (rim values staged with the chunk), so z and y = J z
+// of a point are formed in the same step and no delay line is needed.  8n(k + 4) bytes per iteration (k + 3 for the
+// heat / DG tangents, which read no coefficient vector).
+// ====================================================================================================================
+enum { SW1_BRATU = 0, SW1_HEAT = 1, SW1_DG = 2 };
+
+template <int KB, bool STENCIL, int OP>
+__global__ void __launch_bounds__(kSwThreads, sw_min_blocks(KB)) k_sweep1d(const SweepArgs p) {
+    extern __shared__ __align__(128) unsigned char sw_smem[];
+    if (p.stop != nullptr && *p.stop != 0) return;
+    constexpr bool HASCOEF = STENCIL && OP == SW1_BRATU;
+    constexpr int H = OP == SW1_DG ? 4 : 2;            // rim values per side
+    constexpr int NVEC = KB + 1 + (HASCOEF ? 1 : 0);
+    constexpr int SLOTD = NVEC * kSwTX;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(sw_smem);
+    uint64_t* bar_empty = bar_full + kSwMaxSlots;
+    double* s_c = reinterpret_cast<double*>(sw_smem + kSwOffCoef);
+    int* s_last_p = reinterpret_cast<int*>(sw_smem + kSwOffCoef + kSwKMax * 8);
+    double* s_red = reinterpret_cast<double*>(sw_smem + kSwOffRed);
+    double* slots = reinterpret_cast<double*>(sw_smem + kSwOffSlots);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = p.k, nslot = p.nslot;
+    const int64_t n = p.nx;
+    const int nvec = k + 1 + (HASCOEF ? 1 : 0);
+    const int txi = p.txi, tw = p.tw;
     if (tid == 0) {
-        if (p.seq_out != 0) __threadfence_system();  // rows pushed to the neighbours precede the record
-        const unsigned int tk = atomicAdd(p.ticket, 1u);
-        *s_last_p = (tk == (unsigned int)(nblocks - 1));
+        for (int s = 0; s < nslot; ++s) {
+            mbar_init(bar_full + s, 1);
+            mbar_init(bar_empty + s, kSwWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (tid < KB) s_c[tid] = tid < k ? p.cvec[tid] : 0.0;
+    for (int s = 0; s < nslot; ++s)
+        for (int q = tid; q < (KB - k) * kSwTX; q += kSwThreads) slots[(size_t)s * SLOTD + (size_t)k * kSwTX + q] = 0.0;
+    const double sin = p.in_scale != nullptr ? *p.in_scale : 1.0;
     __syncthreads();
-    if (!*s_last_p) return;
-    __threadfence();
-    // four threads per sum, each over a contiguous quarter of the blocks; quarters added in order
+    const uint32_t bar_full0 = smem_u32(bar_full), bar_empty0 = smem_u32(bar_empty), slots0 = smem_u32(slots);
+    // this block's chunks [c_begin, c_end)
+    const int64_t nchunk = (n + txi - 1) / txi;
+    const int64_t c_begin = nchunk * (int64_t)blockIdx.x / (int64_t)gridDim.x;
+    const int64_t c_end = nchunk * ((int64_t)blockIdx.x + 1) / (int64_t)gridDim.x;
+    const uint32_t nfill = (uint32_t)(c_end - c_begin);
+
+    double acc_n = 0.0, acc_zy = 0.0;
+    double acc_g[KB], acc_t[KB];
+#pragma unroll
+    for (int j = 0; j < KB; ++j) acc_g[j] = acc_t[j] = 0.0;
+
+    // staging of chunk c_begin + f: values [c txi - H, c txi + txi + H) of every vector; beyond the ends of the vector the
+    // rim comes from the ghost values (slabs), from the other end (periodic) or stays unused (physical boundary)
+    auto issue = [&](uint32_t f) {
+        const int64_t c = c_begin + (int64_t)f;
+        const int64_t g0 = c * txi - H, g1 = g0 + txi + 2 * H;
+        const int64_t cs = g0 < 0 ? 0 : g0, ce = g1 < n ? g1 : n;
+        const uint32_t nb = (uint32_t)(ce - cs) * 8u;
+        const bool rim_l = g0 < 0 && (p.wrap || p.zin_lo != nullptr);
+        const bool rim_r = g1 > n && (p.wrap || p.zin_hi != nullptr);
+        const uint32_t vec_bytes = nb + (rim_l ? 8u * H : 0u) + (rim_r ? 8u * H : 0u);
+        const uint32_t slot = f % (uint32_t)nslot;
+        if (f >= (uint32_t)nslot) mbar_wait(bar_empty0 + 8u * slot, ((f / (uint32_t)nslot) - 1u) & 1u);
+        const uint32_t bar = bar_full0 + 8u * slot;
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(k + 1) * vec_bytes + (HASCOEF ? nb : 0u));
+        __syncwarp();
+        if (lane < nvec) {
+            const bool iscoef = HASCOEF && lane == k + 1;
+            const double* v = lane < k ? p.S[lane] : (lane == k ? p.zin : p.coef);
+            const int pos = lane < k ? lane : KB + (lane - k);
+            const uint32_t dst = slots0 + 8u * (slot * (uint32_t)SLOTD + (uint32_t)pos * kSwTX);
+            bulk_g2s(dst + 8u * (uint32_t)(cs - g0), v + cs, nb, bar);
+            if (!iscoef) {  // (the coefficient vector is only read at owned points)
+                if (rim_l) bulk_g2s(dst, p.wrap ? v + (n - H) : (lane < k ? p.S_lo[lane] : p.zin_lo), 8u * H, bar);
+                if (rim_r) bulk_g2s(dst + 8u * (uint32_t)(n - g0), p.wrap ? v : (lane < k ? p.S_hi[lane] : p.zin_hi), 8u * H, bar);
+            }
+        }
+    };
+    const uint32_t lead = (uint32_t)(nslot - p.slack);
+    uint32_t fnext = (uint32_t)warp;
+    for (; fnext < lead && fnext < nfill; fnext += kSwWarps) issue(fnext);
+
     {
-        const int c = tid >> 2, part = tid & 3;
-        double s = 0.0;
-        if (c < NS) {
-            const int b0 = nblocks * part / 4, b1 = nblocks * (part + 1) / 4;
-            for (int b = b0; b < b1; ++b) s += __ldcg(p.partials + (size_t)b * NS + c);
+        const Divisor dx2 = p.dx2d;
+        // staged position of this lane: three-point stencils: rim, tw owned points, rim (H - 1 unused staged values in
+        // front); DG: one rim element (4 lanes), tw = 24 owned nodes, one rim element
+        const int t = (OP == SW1_DG ? 0 : H - 1) + tw * warp + lane;
+        const int rimw = OP == SW1_DG ? 4 : 1;       // rim lanes per side
+        const bool pushing = p.push_z_down != nullptr || p.push_z_up != nullptr || p.push_y_down != nullptr || p.push_y_up != nullptr;
+        // DG: this lane's row of the derivative matrix
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+        const int node = lane & 3;
+        if (OP == SW1_DG) { d0 = p.D[node][0]; d1 = p.D[node][1]; d2 = p.D[node][2]; d3 = p.D[node][3]; }
+        double sd[KB];
+        uint32_t slot = 0, par = 0;
+        const double* base = slots + t;
+        for (uint32_t cnt = 0; cnt < nfill; ++cnt) {
+            if (cnt + lead == fnext) {
+                if (fnext < nfill) issue(fnext);
+                fnext += kSwWarps;
+            }
+            const int64_t c = c_begin + (int64_t)cnt;
+            const int64_t g0 = c * txi - H;
+            const int64_t gi = g0 + t;                       // global index of this lane's value
+            const int64_t own_end = (c + 1) * txi < n ? (c + 1) * txi : n;
+            const bool lane_on = lane < tw + 2 * rimw && t < txi + 2 * H;
+            const bool have_l = p.wrap || p.zin_lo != nullptr, have_r = p.wrap || p.zin_hi != nullptr;
+            const bool zvalid = lane_on && ((gi >= 0 && gi < n) || (gi < 0 && have_l) || (gi >= n && gi < n + H && have_r));
+            const bool interior = lane_on && lane >= rimw && lane < rimw + tw && gi >= c * txi && gi < own_end;
+            mbar_wait(bar_full0 + 8u * slot, par);
+            double zt = __dmul_rn(base[KB * kSwTX], sin);
+#pragma unroll
+            for (int j = 0; j < KB; ++j) {
+                sd[j] = base[j * kSwTX];
+                zt = fma(-s_c[j], sd[j], zt);  // same order as successive kaxpy!
+            }
+            if (!zvalid) zt = 0.0;
+            // bc!(u) of the 1-D heat example: the two global end points are zero (heat_1D.jl:34-37), in the stored vector
+            // too (seg_first / seg_last are only set for that problem; the update-only variant serves every problem)
+            if ((gi == 0 && p.seg_first) || (gi == n - 1 && p.seg_last)) zt = 0.0;
+            double y = 0.0;
+            if (STENCIL) {
+                if (OP == SW1_DG) {
+                    // D1p: t1 = jac * (D u) per element, + (u_next0 - u_3) / mw at the last node
+                    const int eb = lane & ~3;
+                    const double u0 = __shfl_sync(0xffffffffu, zt, eb), u1 = __shfl_sync(0xffffffffu, zt, eb + 1);
+                    const double u2 = __shfl_sync(0xffffffffu, zt, eb + 2), u3 = __shfl_sync(0xffffffffu, zt, eb + 3);
+                    const double unext = __shfl_down_sync(0xffffffffu, zt, 1);
+                    double sacc = __dmul_rn(d0, u0);
+                    sacc = __dadd_rn(sacc, __dmul_rn(d1, u1));
+                    sacc = __dadd_rn(sacc, __dmul_rn(d2, u2));
+                    sacc = __dadd_rn(sacc, __dmul_rn(d3, u3));
+                    double t1 = __dmul_rn(p.jac, sacc);
+                    if (node == 3) t1 = __dadd_rn(t1, div_by(__dsub_rn(unext, zt), p.mwd));
+                    // D1m: du = jac * (D t1), + (t1_0 - t1_prev3) / mw at the first node
+                    const double q0 = __shfl_sync(0xffffffffu, t1, eb), q1 = __shfl_sync(0xffffffffu, t1, eb + 1);
+                    const double q2 = __shfl_sync(0xffffffffu, t1, eb + 2), q3 = __shfl_sync(0xffffffffu, t1, eb + 3);
+                    const double tprev = __shfl_up_sync(0xffffffffu, t1, 1);
+                    double s2 = __dmul_rn(d0, q0);
+                    s2 = __dadd_rn(s2, __dmul_rn(d1, q1));
+                    s2 = __dadd_rn(s2, __dmul_rn(d2, q2));
+                    s2 = __dadd_rn(s2, __dmul_rn(d3, q3));
+                    double du = __dmul_rn(p.jac, s2);
+                    if (node == 0) du = __dadd_rn(du, div_by(__dsub_rn(t1, tprev), p.mwd));
+                    y = __dsub_rn(__dmul_rn(p.c1, du), zt);
+                } else {
+                    const double zl = __shfl_up_sync(0xffffffffu, zt, 1);
+                    const double zr = __shfl_down_sync(0xffffffffu, zt, 1);
+                    if (OP == SW1_BRATU) {
+                        const double cf = base[(KB + 1) * kSwTX];
+                        const double kc = p.coef_from_u ? __dmul_rn(p.lambda, exp(cf)) : cf;
+                        y = __dadd_rn(second_diff(zr, zt, zl, dx2), __dmul_rn(kc, zt));
+                    } else {
+                        // heat_1D.jl:22: du[i] = a * (u[i+1] - 2u[i] + u[i-1]) / dx^2 ; du[1] = du[end] = 0
+                        const bool bnd = (gi == 0 && p.seg_first) || (gi == n - 1 && p.seg_last);
+                        const double du = bnd ? 0.0 : div_by(__dmul_rn(p.a, __dadd_rn(__dsub_rn(zr, __dmul_rn(2.0, zt)), zl)), dx2);
+                        y = __dsub_rn(__dmul_rn(p.c1, du), zt);
+                    }
+                }
+            }
+            if (interior) {
+                if (p.zout != nullptr) p.zout[gi] = zt;
+                acc_n = fma(zt, zt, acc_n);
+                if (STENCIL) {
+                    p.yout[gi] = y;
+                    acc_zy = fma(zt, y, acc_zy);
+                }
+#pragma unroll
+                for (int j = 0; j < KB; ++j) {
+                    acc_g[j] = fma(sd[j], zt, acc_g[j]);
+                    if (STENCIL) acc_t[j] = fma(sd[j], y, acc_t[j]);
+                }
+                if (pushing) {  // segments: the first / last H values go to the neighbours' ghost values
+                    if (gi < H) {
+                        if (p.push_z_down != nullptr) p.push_z_down[gi] = zt;
+                        if (STENCIL && p.push_y_down != nullptr) p.push_y_down[gi] = y;
+                    }
+                    if (gi >= n - H) {
+                        if (p.push_z_up != nullptr) p.push_z_up[gi - (n - H)] = zt;
+                        if (STENCIL && p.push_y_up != nullptr) p.push_y_up[gi - (n - H)] = y;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty0 + 8u * slot);
+            ++slot;
+            base += SLOTD;
+            if (slot == (uint32_t)nslot) { slot = 0; par ^= 1u; base = slots + t; }
         }
-        const int gl = lane & ~3;
-        const double q0 = __shfl_sync(0xffffffffu, s, gl), q1 = __shfl_sync(0xffffffffu, s, gl + 1);
-        const double q2 = __shfl_sync(0xffffffffu, s, gl + 2), q3 = __shfl_sync(0xffffffffu, s, gl + 3);
-        if (c < NS && part == 0) s_red[c] = ((q0 + q1) + q2) + q3;
     }
     __syncthreads();
-    if (tid < NS) {
-        // layout of sums_out (sweep.h): [0] ||z||^2, [1] <z,y>, [2 + j] g_j, [2 + kSwKMax + j] t_j
-        const int dst = tid < 2 ? tid : (tid < 2 + KB ? tid : tid - KB + kSwKMax);
-        const bool used = tid < 2 || (tid < 2 + KB ? tid - 2 < k : tid - 2 - KB < k);
-        if (used && p.seq_out == 0) p.sums_out[dst] = s_red[tid];
-        if (p.seq_out != 0) {
-            // every rank's record goes into every rank's sweep mailbox; the scalar kernel adds them in rank order
-            const int slot = (int)(p.seq_out % kMailSlots);
-            for (int q = 0; q < p.pd.nranks; ++q) {
-                double* rec = p.swmail_peer[q] + ((size_t)slot * p.pd.nranks + p.pd.rank) * kSwMailRec;
-                rec[dst] = used ? s_red[tid] : 0.0;
-            }
-            __threadfence_system();
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        if (p.seq_out != 0) {
-            __threadfence_system();
-            const int slot = (int)(p.seq_out % kMailSlots);
-            for (int q = 0; q < p.pd.nranks; ++q) {
-                double* rec = p.swmail_peer[q] + ((size_t)slot * p.pd.nranks + p.pd.rank) * kSwMailRec;
-                st_release_sys_u64(reinterpret_cast<unsigned long long*>(rec + kSwSums), p.seq_out);
-            }
-        }
-        *p.ticket = 0u;
-    }
+    sweep_reduce<KB>(p, k, acc_n, acc_zy, acc_g, acc_t, s_red, s_last_p);
 }
 
 // ---- launch ------------------------------------------------------------------------------------------------------
@@ -531,17 +747,72 @@ static int launch_sweep_kb(Ctx* ctx, SweepArgs& a, bool stencil, int op) {
     return launch_sweep_t<KB, true, SW_OP_HEAT>(ctx, a);
 }
 
+template <int KB, bool STENCIL, int OP>
+static int launch_sweep1d_t(Ctx* ctx, SweepArgs& a) {
+    static std::atomic<int> configured{0};
+    if (!configured.load(std::memory_order_relaxed)) {
+        AK_CUDA(cudaFuncSetAttribute(k_sweep1d<KB, STENCIL, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwSmemMax));
+        configured.store(1, std::memory_order_relaxed);
+    }
+    const int nvec = KB + 1 + ((STENCIL && OP == SW1_BRATU) ? 1 : 0);
+    const int slot_bytes = nvec * kSwTX * 8;
+    int occ = sw_min_blocks(KB);
+    int nslot = 0;
+    for (; occ >= 1; --occ) {
+        const int budget = kSwSmemMax / occ - 1024;
+        nslot = (budget - kSwOffSlots) / slot_bytes;
+        if (nslot >= 3) break;
+    }
+    if (nslot < 3) {
+        set_error("launch_sweep: %d vectors do not fit the shared-memory ring", nvec);
+        return AK_ERR_UNSUPPORTED;
+    }
+    if (nslot > kSwMaxSlots) nslot = kSwMaxSlots;
+    a.nslot = nslot;
+    a.slack = nslot >= 4 ? 2 : 1;
+    a.txi = OP == SW1_DG ? 192 : kSwTXI;  // DG: whole elements, 6 per warp
+    a.tw = a.txi / kSwWarps;
+    const size_t smem = (size_t)kSwOffSlots + (size_t)nslot * slot_bytes;
+    const int64_t nchunk = (a.nx + a.txi - 1) / a.txi;
+    int64_t grid = (int64_t)ctx->num_sms * occ;
+    const int64_t by_work = (nchunk + 7) / 8;  // at least ~8 chunks per block
+    if (grid > by_work) grid = by_work;
+    if (grid < 1) grid = 1;
+    ProfScope prof(ctx, PK_SWEEP);
+    k_sweep1d<KB, STENCIL, OP><<<(int)grid, kSwThreads, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    AK_CUDA(cudaGetLastError());
+    return AK_OK;
+}
+
+template <int KB>
+static int launch_sweep1d_kb(Ctx* ctx, SweepArgs& a, bool stencil, int op) {
+    if (!stencil) return launch_sweep1d_t<KB, false, SW1_HEAT>(ctx, a);  // (the update alone does not depend on the problem)
+    if (op == SW1_BRATU) return launch_sweep1d_t<KB, true, SW1_BRATU>(ctx, a);
+    if (op == SW1_HEAT) return launch_sweep1d_t<KB, true, SW1_HEAT>(ctx, a);
+    return launch_sweep1d_t<KB, true, SW1_DG>(ctx, a);
+}
+
+static inline bool is_sweep_2d(const ak_problem* p) { return p->kind == AK_BRATU2D || p->kind == AK_HEAT2D; }
+
 bool sweep_supported(const Ctx* ctx, const ak_problem* p, const double* u) {
-    if (!(p->kind == AK_BRATU2D || p->kind == AK_HEAT2D)) return false;
+    const bool d2 = is_sweep_2d(p);
+    const bool d1 = p->kind == AK_BRATU1D || p->kind == AK_HEAT1D || p->kind == AK_HEAT1D_DG;
+    if (!d1 && !d2) return false;
     if (p->jvp_mode != AK_JVP_ANALYTIC || p->scheme == AK_MIDPOINT) return false;
-    if (p->nx < 4 || p->nx % 2 != 0 || p->ny < 1) return false;  // bulk copies move 16-byte units
-    if (p->kind == AK_BRATU2D) {  // lambda e^u (or u itself) is streamed with bulk copies like the basis
+    if (d2 && (p->nx < 4 || p->nx % 2 != 0 || p->ny < 1)) return false;  // bulk copies move 16-byte units
+    if (d1) {
+        if (p->kind == AK_HEAT1D_DG ? (p->nx % 4 != 0 || p->nx < 8) : (p->nx % 2 != 0 || p->nx < 4)) return false;
+        // periodic_bc! of the 1-D heat example copies the end points into one another in place: not reproduced here
+        if (p->kind == AK_HEAT1D && p->bc == AK_BC_PERIODIC) return false;
+    }
+    if (p->kind == AK_BRATU2D || p->kind == AK_BRATU1D) {  // lambda e^u (or u itself) is streamed with bulk copies like the basis
         const double* cf = p->coef != nullptr ? p->coef : u;
         if (cf == nullptr || (reinterpret_cast<uintptr_t>(cf) & 15u)) return false;
     }
     if (ctx->nranks > 1) {
-        // slabs: the neighbours' rows arrive through peer memory (ak_comm_enable_p2p sized the ghost rows)
-        if (!ctx->p2p_on || p->nx > ctx->p2p_halo_cap) return false;
+        // slabs / segments: the neighbours' boundary rows / values arrive through peer memory
+        if (!ctx->p2p_on || (d2 ? p->nx : 8) > ctx->p2p_halo_cap) return false;
     }
     return true;
 }
@@ -550,11 +821,12 @@ int launch_sweep(Ctx* ctx, const ak_problem* prob, const double* u, const SweepC
     AK_REQUIRE(c.k >= 0 && c.k <= kSwKMax, "launch_sweep: k out of range");
     AK_REQUIRE(c.zin != nullptr && c.sums != nullptr, "launch_sweep: NULL operand");
     AK_REQUIRE(!c.stencil || c.yout != nullptr, "launch_sweep: the tangent needs a destination");
+    const bool d2 = is_sweep_2d(prob);
     SweepArgs a{};
     a.nx = prob->nx;
-    a.ny = prob->ny;
+    a.ny = d2 ? prob->ny : 1;
     a.k = c.k;
-    a.wrap_x = (prob->bc == AK_BC_PERIODIC);
+    a.wrap_x = d2 && (prob->bc == AK_BC_PERIODIC);
     bool ok16 = (reinterpret_cast<uintptr_t>(c.zin) & 15u) == 0;
     for (int j = 0; j < c.k; ++j) {
         a.S[j] = c.S[j];
@@ -565,7 +837,7 @@ int launch_sweep(Ctx* ctx, const ak_problem* prob, const double* u, const SweepC
     a.zin = c.zin;
     a.zin_lo = c.zin_lo;
     a.zin_hi = c.zin_hi;
-    if (ctx->nranks == 1 && prob->bc == AK_BC_PERIODIC) {  // one GPU: the ghost rows are the opposite rows
+    if (d2 && ctx->nranks == 1 && prob->bc == AK_BC_PERIODIC) {  // one GPU: the ghost rows are the opposite rows
         for (int j = 0; j < c.k; ++j) { a.S_lo[j] = c.S[j] + (prob->ny - 1) * prob->nx; a.S_hi[j] = c.S[j]; }
         a.zin_lo = c.zin + (prob->ny - 1) * prob->nx;
         a.zin_hi = c.zin;
@@ -580,8 +852,7 @@ int launch_sweep(Ctx* ctx, const ak_problem* prob, const double* u, const SweepC
     a.a = prob->a;
     a.c1 = (prob->scheme == AK_TRAPEZOID) ? prob->dt / 2.0 : prob->dt;
     a.lambda = prob->lambda;
-    const int op = prob->kind == AK_BRATU2D ? SW_OP_BRATU : SW_OP_HEAT;
-    if (op == SW_OP_BRATU) {
+    if (prob->kind == AK_BRATU2D || prob->kind == AK_BRATU1D) {
         a.coef = prob->coef ? prob->coef : u;
         a.coef_from_u = prob->coef ? 0 : 1;
         AK_REQUIRE(!c.stencil || (a.coef != nullptr && (reinterpret_cast<uintptr_t>(a.coef) & 15u) == 0),
@@ -602,12 +873,37 @@ int launch_sweep(Ctx* ctx, const ak_problem* prob, const double* u, const SweepC
     }
     const int k = c.k;
     int rc;
-    if (k <= 4) rc = launch_sweep_kb<4>(ctx, a, c.stencil, op);
-    else if (k <= 8) rc = launch_sweep_kb<8>(ctx, a, c.stencil, op);
-    else if (k <= 12) rc = launch_sweep_kb<12>(ctx, a, c.stencil, op);
-    else if (k <= 16) rc = launch_sweep_kb<16>(ctx, a, c.stencil, op);
-    else if (k <= 20) rc = launch_sweep_kb<20>(ctx, a, c.stencil, op);
-    else rc = launch_sweep_kb<24>(ctx, a, c.stencil, op);
+    if (d2) {
+        const int op = prob->kind == AK_BRATU2D ? SW_OP_BRATU : SW_OP_HEAT;
+        if (k <= 4) rc = launch_sweep_kb<4>(ctx, a, c.stencil, op);
+        else if (k <= 8) rc = launch_sweep_kb<8>(ctx, a, c.stencil, op);
+        else if (k <= 12) rc = launch_sweep_kb<12>(ctx, a, c.stencil, op);
+        else if (k <= 16) rc = launch_sweep_kb<16>(ctx, a, c.stencil, op);
+        else if (k <= 20) rc = launch_sweep_kb<20>(ctx, a, c.stencil, op);
+        else rc = launch_sweep_kb<24>(ctx, a, c.stencil, op);
+    } else {
+        const int op = prob->kind == AK_BRATU1D ? SW1_BRATU : (prob->kind == AK_HEAT1D ? SW1_HEAT : SW1_DG);
+        a.halo = op == SW1_DG ? 4 : 2;
+        a.wrap = (op == SW1_DG && ctx->nranks == 1) ? 1 : 0;  // the DG mesh is periodic; on segments the ends are ghost values
+        a.seg_first = op == SW1_HEAT && ctx->rank == 0;
+        a.seg_last = op == SW1_HEAT && ctx->rank == ctx->nranks - 1;
+        if (op == SW1_DG) {
+            const double h = prob->dx, s5 = sqrt(5.0);
+            const double da = (5.0 + 5.0 * s5) / 4.0, db = (5.0 - 5.0 * s5) / 4.0;
+            const double dc = (1.0 + s5) / 4.0, dd = s5 / 2.0, de = (s5 - 1.0) / 4.0;
+            const double M[4][4] = {{-3.0, da, db, 0.5}, {-dc, 0.0, dd, -de}, {de, -dd, 0.0, dc}, {-0.5, -db, -da, 3.0}};
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) a.D[i][j] = M[i][j];
+            a.jac = 2.0 / h;
+            a.mwd = make_divisor_host((h / 2.0) * (1.0 / 6.0));
+        }
+        if (k <= 4) rc = launch_sweep1d_kb<4>(ctx, a, c.stencil, op);
+        else if (k <= 8) rc = launch_sweep1d_kb<8>(ctx, a, c.stencil, op);
+        else if (k <= 12) rc = launch_sweep1d_kb<12>(ctx, a, c.stencil, op);
+        else if (k <= 16) rc = launch_sweep1d_kb<16>(ctx, a, c.stencil, op);
+        else if (k <= 20) rc = launch_sweep1d_kb<20>(ctx, a, c.stencil, op);
+        else rc = launch_sweep1d_kb<24>(ctx, a, c.stencil, op);
+    }
     AK_TRY(rc);
     // NCCL fallback of the reduction is not offered: slabs take this path only with peer memory (sweep_supported)
     return AK_OK;

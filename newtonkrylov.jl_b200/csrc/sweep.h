@@ -33,10 +33,12 @@ struct SweepCall {
     unsigned long long seq_out = 0;
 };
 
-// can this problem take the sweep kernels on this context (2-D analytic tangents, even nx, slabs only with peer memory)
+// can this problem take the sweep kernels on this context (analytic tangents of the 2-D and 1-D stencils and of DG, even
+// row length, slabs / segments only with peer memory)
 bool sweep_supported(const Ctx* ctx, const ak_problem* p, const double* u);
 int launch_sweep(Ctx* ctx, const ak_problem* prob, const double* u, const SweepCall& c);
 // peer memory: first / last row of the slab `v` into the neighbours' ghost rows of sweep slot `slot` (context.cu)
-int sweep_push_rows(Ctx* ctx, const double* v, int64_t nx, int64_t ny, int32_t bc, int slot);
+// (2-D slabs: count = nx; 1-D segments: the first / last `count` values)
+int sweep_push_rows(Ctx* ctx, const double* v, int64_t n, int count, bool periodic, int slot);
 
 }  // namespace ak

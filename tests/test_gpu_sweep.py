@@ -47,6 +47,15 @@ GRIDS = [
     ("heat", lambda: P.heat2d(48, dt_scale=64.0, ic="poly")),
     ("heat_periodic", lambda: P.heat2d(36, dt_scale=64.0, bc=A.AK_BC_PERIODIC, ic="poly")),
     ("heat_periodic_wide", lambda: P.heat2d(300, dt_scale=64.0, bc=A.AK_BC_PERIODIC, ic="poly")),
+    # 1-D problems: chunks of 240 points (192 for DG) play the role of the rows
+    ("bratu1d_one_chunk", lambda: P.generic(P.bratu1d(200))),
+    ("bratu1d_ragged", lambda: P.generic(P.bratu1d(250))),
+    ("bratu1d_many_blocks", lambda: P.generic(P.bratu1d(100000))),
+    ("heat1d", lambda: P.heat1d(998)),
+    ("heat1d_two_chunks", lambda: P.heat1d(300)),
+    ("dg_small", lambda: P.heat1d_dg(16, dt=1e-4)),
+    ("dg_ragged", lambda: P.heat1d_dg(1000, dt=4e-7)),
+    ("dg_many_blocks", lambda: P.heat1d_dg(40000, dt=2e-10)),
 ]
 
 
@@ -54,6 +63,8 @@ GRIDS = [
 def test_sweep_basis_and_history_match_the_reference_op_list(nk, ctx, oracle, name, make):
     d = make()
     b0 = RNG.standard_normal(d["u0"].shape)
+    if d["kind"] == A.AK_HEAT1D:
+        b0[0] = b0[-1] = 0.0  # consistent with the zero boundary rows of J (heat_1D.jl:57-89)
     kw = dict(rtol=1e-30, atol=0.0, restart=True, itmax=12, memory=6)
     ws_s, nsweep = run(nk, ctx, d, b0, "sweep", **kw)
     assert nsweep > 0, "the sweep kernel did not run"
