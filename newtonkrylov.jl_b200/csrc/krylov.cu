@@ -848,6 +848,13 @@ static int gmres_solve(ak_krylov* ws, const ak_problem* prob, const double* u, c
     if (fuse == AK_FUSE_SWEEP) {
         static const bool no_sweep = getenv("AK_NO_SWEEP") != nullptr;
         sweep = !no_sweep && !hosted && sweep_supported(c, prob, u);
+        if (c->nranks > 1 && !hosted) {
+            // the ranks must take the same path (their kernels wait for one another), and the local test can differ:
+            // segment lengths differ by a point between ranks, so one rank's row length may be odd
+            int rc_sw = sweep ? AK_OK : AK_ERR_UNSUPPORTED;
+            AK_TRY(collective_verdict(c, &rc_sw));
+            sweep = (rc_sw == AK_OK);
+        }
         fuse = AK_FUSE_BLOCK8;
     }
     if ((flexible || precond) && !ws->pbuf) AK_TRY(ws_alloc_vec(ws, &ws->pbuf));
