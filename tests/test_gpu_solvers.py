@@ -360,14 +360,18 @@ def test_implicit_time_stepping_matches_oracle(nk, ctx, oracle, name, make, nste
     # reproducibility of the algorithm itself under a 1-ulp change of one entry of u0
     rng = np.random.default_rng(3)
     robust, du = np.ones(nsteps, dtype=bool), 0.0
-    for _ in range(4):
+    spread = np.zeros(nsteps)  # how far the oracle's own GMRES counts move under those perturbations
+    for _ in range(8):
         u1 = d["u0"].copy()
         i = rng.integers(1, u1.size - 1)
         u1.flat[i] = np.nextafter(u1.flat[i], np.inf)
         u1r, n1, i1, s1 = oracle.implicit_solve(P.oracle_problem(oracle, d, un=u1), u1, nsteps, o)
         robust &= (i1 == inner_r) & (n1 == newt_r)
+        spread = np.maximum(spread, np.abs(np.asarray(i1, dtype=float) - np.asarray(inner_r, dtype=float)))
         du = max(du, rel(u1r, ur))
     tol_u = max(TOL_U, 50 * du)
+    ledger.record("implicit_vs_oracle", name, oracle_inner=[int(x) for x in inner_r], oracle_count_spread_1ulp=[int(x) for x in spread],
+                  oracle_u_sensitivity_1ulp=du)
 
     def check(newt, inner, solved, un_host):
         assert list(solved) == [bool(s) for s in solved_r]
@@ -375,7 +379,10 @@ def test_implicit_time_stepping_matches_oracle(nk, ctx, oracle, name, make, nste
             if robust[k]:
                 assert (newt[k], inner[k]) == (newt_r[k], inner_r[k]), f"time step {k}"
             else:
-                assert abs(newt[k] - newt_r[k]) <= 1 and abs(inner[k] - inner_r[k]) <= max(2, 0.05 * inner_r[k])
+                # (1-D heat: the Krylov space is exhausted before GMRES converges, the count of the last step is a knife
+                #  edge — the oracle itself returns 103, 104, 110 or 111 for step 3 of heat1d under 1-ulp changes of u0)
+                assert abs(newt[k] - newt_r[k]) <= 1
+                assert abs(inner[k] - inner_r[k]) <= max(2, 0.05 * inner_r[k], 2 * spread[k]), (k, inner[k], inner_r[k], spread[k])
         assert rel(un_host, ur) < tol_u
 
     # (a) host-language time loop (mirror of implicit.jl)
