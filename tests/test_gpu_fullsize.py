@@ -81,7 +81,7 @@ def test_c3_heat2d_8192_implicit_euler_step_matches_oracle(nk, ctx, oracle):
     of examples/heat_2D.jl:72 x 16, tol_abs = 6e-6 of implicit.jl:69) with `reorthogonalization = true`
     (examples/heat_2D.jl:131), solved to tolerance: Newton count, GMRES count per step, ||F|| history, final u."""
     d = P.heat2d(8192, dt_scale=16.0, ic="poly")
-    sens = _newton_fullsize(nk, ctx, oracle, d, "C3_heat2d_8192_euler_step_reorth", ("none", "block8"), tol_abs=6e-6,
+    sens = _newton_fullsize(nk, ctx, oracle, d, "C3_heat2d_8192_euler_step_reorth", ("none", "block8", "sweep"), tol_abs=6e-6,
                             krylov_kwargs=dict(reorthogonalization=True))
     assert sens[1]["solved"] and sens[1]["outer_iterations"] >= 3
 
@@ -92,7 +92,7 @@ def test_c2_heat1d_2pow24_newton_step_matches_oracle(nk, ctx, oracle):
     overrides eta), then u .-= d and the new residual norm."""
     N = 1 << 24
     d = P.heat1d(N - 2, dt=0.1)
-    _newton_fullsize(nk, ctx, oracle, d, "C2_heat1d_2pow24_newton_step_gmres20", ("none", "block8"), tol_abs=6e-6,
+    _newton_fullsize(nk, ctx, oracle, d, "C2_heat1d_2pow24_newton_step_gmres20", ("none", "block8", "sweep"), tol_abs=6e-6,
                      max_niter=0, krylov_kwargs=dict(itmax=20, rtol=1e-12))
 
 
@@ -100,7 +100,7 @@ def test_c5_dg_2pow22_newton_step_matches_oracle(nk, ctx, oracle):
     """BASELINE config 5 at its stated size with the example's dt = 0.01 (examples/heat_1D_DG.jl:81): one Newton step
     of 20 GMRES iterations."""
     d = P.heat1d_dg(1 << 22, dt=0.01)
-    _newton_fullsize(nk, ctx, oracle, d, "C5_dg_2pow22_newton_step_gmres20", ("none", "block8"), tol_abs=6e-6,
+    _newton_fullsize(nk, ctx, oracle, d, "C5_dg_2pow22_newton_step_gmres20", ("none", "block8", "sweep"), tol_abs=6e-6,
                      max_niter=0, krylov_kwargs=dict(itmax=20, rtol=1e-12))
 
 

@@ -286,11 +286,11 @@ NEWTON_CASES = [
 ]
 
 
-@pytest.mark.parametrize("fuse", ["none", "block8"])
+@pytest.mark.parametrize("fuse", ["none", "block8", "sweep"])
 @pytest.mark.parametrize("native", [False, True], ids=["host_loop", "c_loop"])
 @pytest.mark.parametrize("name,make,kw", NEWTON_CASES, ids=[c[0] for c in NEWTON_CASES])
 def test_newton_matches_oracle(nk, ctx, oracle, name, make, kw, native, fuse):
-    """Every Newton case at the reference op list (fuse = none) and at the library default (block8)."""
+    """Every Newton case at the reference op list (fuse = none), at block8 and at the library default (sweep)."""
     kw = dict(kw)
     if kw.get("forcing") == "fixed":
         kw["forcing"] = nk.Fixed(0.1)
