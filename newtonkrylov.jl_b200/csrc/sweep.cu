@@ -664,10 +664,12 @@ __global__ void __launch_bounds__(kSwThreads, sw_min_blocks(KB)) k_sweep1d(const
 // ---- launch ------------------------------------------------------------------------------------------------------
 template <int KB, bool STENCIL, int OP>
 static int launch_sweep_t(Ctx* ctx, SweepArgs& a) {
-    static std::atomic<int> configured{0};
-    if (!configured.load(std::memory_order_relaxed)) {
+    // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute of the kernel
+    static std::atomic<unsigned long long> configured{0ull};
+    const unsigned long long devbit = 1ull << (ctx->device & 63);
+    if (!(configured.load(std::memory_order_relaxed) & devbit)) {
         AK_CUDA(cudaFuncSetAttribute(k_sweep<KB, STENCIL, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwSmemMax));
-        configured.store(1, std::memory_order_relaxed);
+        configured.fetch_or(devbit, std::memory_order_relaxed);
     }
     const int nvec = KB + 1 + ((STENCIL && OP == SW_OP_BRATU) ? 1 : 0);  // slot positions (S_j padded to KB)
     const int slot_bytes = nvec * kSwTX * 8;
@@ -749,10 +751,11 @@ static int launch_sweep_kb(Ctx* ctx, SweepArgs& a, bool stencil, int op) {
 
 template <int KB, bool STENCIL, int OP>
 static int launch_sweep1d_t(Ctx* ctx, SweepArgs& a) {
-    static std::atomic<int> configured{0};
-    if (!configured.load(std::memory_order_relaxed)) {
+    static std::atomic<unsigned long long> configured{0ull};
+    const unsigned long long devbit = 1ull << (ctx->device & 63);
+    if (!(configured.load(std::memory_order_relaxed) & devbit)) {
         AK_CUDA(cudaFuncSetAttribute(k_sweep1d<KB, STENCIL, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwSmemMax));
-        configured.store(1, std::memory_order_relaxed);
+        configured.fetch_or(devbit, std::memory_order_relaxed);
     }
     const int nvec = KB + 1 + ((STENCIL && OP == SW1_BRATU) ? 1 : 0);
     const int slot_bytes = nvec * kSwTX * 8;
@@ -801,6 +804,7 @@ bool sweep_supported(const Ctx* ctx, const ak_problem* p, const double* u) {
     if (!d1 && !d2) return false;
     if (p->jvp_mode != AK_JVP_ANALYTIC || p->scheme == AK_MIDPOINT) return false;
     if (d2 && (p->nx < 4 || p->nx % 2 != 0 || p->ny < 1)) return false;  // bulk copies move 16-byte units
+    if (d2 && (p->nx > (1 << 20) || p->ny > (1ll << 30))) return false;  // (segment table and partials buffer are sized for this)
     if (d1) {
         if (p->kind == AK_HEAT1D_DG ? (p->nx % 4 != 0 || p->nx < 8) : (p->nx % 2 != 0 || p->nx < 4)) return false;
         // periodic_bc! of the 1-D heat example copies the end points into one another in place: not reproduced here
