@@ -13,8 +13,8 @@ Workloads (`--config`, BASELINE.json configs):
   c5    DG 1-D heat, 2^22 elements x 4 LGL nodes PER GPU, periodic, dt = 0.01 (examples/heat_1D_DG.jl).
 One STEP = one Newton step of `newton_krylov!` (src/Ariadne.jl:321-368) with
 `krylov_kwargs = (; restart = true, itmax = 40, rtol = 1e-30, atol = 0)` and memory = 20: copy(res) -> GMRES(20) x 2
-restart cycles (40 iterations, each = 1 JVP + k fused modified-Gram-Schmidt steps + Givens update) -> u .-= d ->
-F!(res, u) + norm(res).  The tolerance is set so that every step does exactly 40 iterations (fixed work per step); the
+restart cycles (40 iterations, each = 1 JVP + k modified-Gram-Schmidt steps + Givens update; with the default
+--fuse sweep an iteration is ONE pass over the basis, csrc/sweep.cu) -> u .-= d -> F!(res, u) + norm(res).  The tolerance is set so that every step does exactly 40 iterations (fixed work per step); the
 time-dependent configs (c2, c3, c5) restart every step from u = u_n (one extra copy + residual, inside the timed
 region), c4 keeps iterating on the same Newton sequence.
 
@@ -23,10 +23,11 @@ value  = GMRES iterations/s per slab, summed over the slabs (= GPUs): 40*K*N / t
 e2e    = the same metric through the host-buffer entry point ak_newton_solve_host (what a Julia caller holding an
          Array{Float64} calls): every step copies u host->device from pinned memory, allocates the Krylov workspace
          like the reference does per newton_krylov! call, runs the same Newton step and copies u back.
-roofline = the dominant kernel (full pass of the blocked modified-Gram-Schmidt sweep: 144n bytes per launch = 18n per
-         Gram-Schmidt step with --fuse block8) timed live with CUDA events inside the timed region (library profiler),
-         plus the step-level figure: algorithmic bytes of the whole step / step time.  `traffic` is a COMMITTED
-         constant (profiles/kernel_traffic.json, from the ncu --set full capture of the same kernel), not measured here.
+roofline = the dominant kernel (--fuse sweep: k_sweep, 8n(k + 4) bytes at basis size k, bytes and time averaged over the
+         launches of a step; --fuse block8: the full blocked pass, 144n bytes per launch) timed live with CUDA events
+         inside the timed region (library profiler), plus the step-level figure: algorithmic bytes of the whole step /
+         step time.  `traffic` is a COMMITTED constant (profiles/kernel_traffic.json, from the ncu captures of the same
+         kernel), not measured here.
 cpu_baseline = the CPU oracle (oracle/nk_oracle.c, a port of the reference algorithm) on all host cores, one
          GMRES(20) restart cycle of the same solve; at every N (rank 0 runs it after the GPU legs).
 other_configs (default c4 line only) = c2, c3, c5 at N = 1 and c5 at N > 1: it/s and per-kernel GB/s.
