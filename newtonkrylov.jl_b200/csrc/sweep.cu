@@ -1,4 +1,5 @@
-// One sweep per GMRES iteration (fuse = AK_FUSE_SWEEP) for the 2-D five-point problems.
+// One sweep per GMRES iteration (fuse = AK_FUSE_SWEEP): k_sweep for the 2-D five-point problems, k_sweep1d for the 1-D
+// three-point problems and DG.
 //
 // Replaces, per iteration k of Krylov.jl's gmres! (called at src/Ariadne.jl:338), the whole list
 //   kaxpy!/kdot x k, knorm, V[k+1] = w / Hbis, mul!(w, J, V[k+1])          
@@ -14,11 +15,13 @@
 // the cached Gram matrix (k_gmres_sweep_scalar, krylov.cu): h_j = <v_j,w> - sum_{a<j} h_a <v_j,v_a>, the same identity
 // the blocked sweeps use inside a block, with the block = the whole restart cycle.
 //
-// The stencil needs z on the neighbouring rows and columns, so a CTA recomputes the update on a one-row / two-column
-// rim of its segment.  Data movement is TMA: a producer warp streams the rows of S_0..S_{k-1}, W and lambda e^u into a
-// ring of shared-memory slots with cp.async.bulk (completion on an mbarrier per slot); 256 consumer threads own one
-// column each, keep the sums in registers and the previous row of every S_j as the delay line the projections of y
-// need.  The persistent grid splits the (strip, row) space evenly, so the rim costs 2 rows per ~1800.
+// The stencil needs z on the neighbouring rows and columns, so a block recomputes the update on a one-row / two-column
+// rim of its part of the grid.  Data movement is TMA: the rows of S_0..S_{k-1}, W and lambda e^u are streamed into a ring
+// of shared-memory slots with cp.async.bulk (an mbarrier pair per slot); the eight warps of a block are independent
+// (each owns up to 30 columns, x-neighbours by shuffle), take turns at issuing the copies, keep the sums in registers
+// and the previous row of every S_j as the delay line the projections of y need.  Strips of neighbouring blocks advance
+// side by side, so the rim columns they share come out of L2 for the second reader.  How the kernel got from 56 % to
+// 90 % of the copy bandwidth: profiles/r02_sweep_tuning.md.
 #include <math.h>
 #include <stdlib.h>
 
